@@ -1,0 +1,566 @@
+// C-ABI entry points (include/geotrax_b200.h) and engine lifecycle.
+#include <stdarg.h>
+
+#include <cmath>
+
+#include "engine.cuh"
+
+static std::string g_create_error;
+
+void gt_set_error(gt_engine* e, const char* fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  if (e) e->err = buf; else g_create_error = buf;
+}
+
+int gt_engine::dev_alloc(void** p, size_t bytes) {
+  cudaError_t r = cudaMalloc(p, bytes ? bytes : 16);
+  if (r != cudaSuccess) {
+    gt_set_error(this, "cudaMalloc(%zu) failed: %s", bytes, cudaGetErrorString(r));
+    return GT_ERR_NOMEM;
+  }
+  dev_allocs.push_back(*p);
+  return GT_OK;
+}
+int gt_engine::host_alloc(void** p, size_t bytes) {
+  cudaError_t r = cudaMallocHost(p, bytes ? bytes : 16);
+  if (r != cudaSuccess) {
+    gt_set_error(this, "cudaMallocHost(%zu) failed: %s", bytes, cudaGetErrorString(r));
+    return GT_ERR_NOMEM;
+  }
+  host_allocs.push_back(*p);
+  return GT_OK;
+}
+
+extern "C" {
+
+int gt_abi_version(void) { return GT_ABI_VERSION; }
+
+void gt_default_config(gt_config* c) {
+  memset(c, 0, sizeof(*c));
+  c->abi_version = GT_ABI_VERSION;
+  c->frame_h = 2160; c->frame_w = 3840; c->max_batch = 16;
+  c->imgsz = 1920; c->nc = 4; c->task = GT_TASK_DETECT; c->max_det = 1000; c->max_nms = 30000;
+  c->downsample_ratio = 0.5f; c->max_features = 2000; c->ref_multiplier = 2.0f; c->mask_use = 1; c->mask_margin_ratio = 0.15f;
+  c->filter_ratio = 0.9f; c->ransac_threshold = 2.0f; c->ransac_max_iter = 5000; c->query_is_current = 1; c->ransac_full_res = 0;
+  c->seed = 0x9E3779B9u;
+}
+
+const char* gt_last_error(gt_handle h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+static int round_half_even(double v) { return (int)std::nearbyint(v); }
+
+int gt_create(const gt_config* cfg, int device, gt_handle* out) {
+  if (!cfg || !out) { gt_set_error(nullptr, "gt_create: null argument"); return GT_ERR_INVALID; }
+  *out = nullptr;
+  if (cfg->abi_version != GT_ABI_VERSION) { gt_set_error(nullptr, "gt_create: ABI version %d != %d", cfg->abi_version, GT_ABI_VERSION); return GT_ERR_INVALID; }
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    gt_set_error(nullptr, "gt_create: no CUDA device visible (this library has no CPU fallback)");
+    return GT_ERR_CUDA;
+  }
+  if (device < 0 || device >= ndev) { gt_set_error(nullptr, "gt_create: device %d out of range (%d visible)", device, ndev); return GT_ERR_INVALID; }
+  cudaDeviceProp prop;
+  cudaGetDeviceProperties(&prop, device);
+  if (prop.major != 10) { gt_set_error(nullptr, "gt_create: device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor); return GT_ERR_CUDA; }
+  gt_engine* e = new gt_engine();
+  e->cfg = *cfg;
+  e->device = device;
+  auto fail = [&](int rc) { g_create_error = e->err; gt_destroy(e); return rc; };
+#define CR(expr) do { int _rc = (expr); if (_rc != GT_OK) return fail(_rc); } while (0)
+#define CRC(call) do { cudaError_t _er = (call); if (_er != cudaSuccess) { gt_set_error(e, "%s -> %s", #call, cudaGetErrorString(_er)); return fail(GT_ERR_CUDA); } } while (0)
+  CRC(cudaSetDevice(device));
+  CRC(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
+  for (int i = 0; i < 8; ++i) CRC(cudaEventCreate(&e->ev[i]));
+  const gt_config& c = e->cfg;
+  if (c.max_batch < 1 || c.max_batch > 32 || c.nc < 1 || c.nc > 80 || c.max_det < 1 || c.max_det > 4096) {
+    gt_set_error(e, "gt_create: max_batch/nc/max_det out of range"); return fail(GT_ERR_INVALID);
+  }
+  // letterbox geometry (LetterBox auto=True, stride 32)
+  const double r = std::min((double)c.imgsz / c.frame_h, (double)c.imgsz / c.frame_w);
+  e->gain = (float)r;
+  e->new_w = round_half_even(c.frame_w * r);
+  e->new_h = round_half_even(c.frame_h * r);
+  const double dw = ((c.imgsz - e->new_w) % 32) / 2.0, dh = ((c.imgsz - e->new_h) % 32) / 2.0;
+  e->pad_top = round_half_even(dh - 0.1); e->pad_left = round_half_even(dw - 0.1);
+  const int pad_bot = round_half_even(dh + 0.1), pad_right = round_half_even(dw + 0.1);
+  e->net_h = e->new_h + e->pad_top + pad_bot;
+  e->net_w = e->new_w + e->pad_left + pad_right;
+  if (r != 0.5 || (c.frame_w % 16) || (c.frame_h % 2) || (e->net_h % 32) || (e->net_w % 32) || (e->pad_left % 8)) {
+    gt_set_error(e, "gt_create: only the exact 1/2 letterbox (imgsz = max(frame)/2, width %% 16 == 0) is implemented; got %dx%d imgsz %d",
+                 c.frame_w, c.frame_h, c.imgsz);
+    return fail(GT_ERR_INVALID);
+  }
+  if (c.downsample_ratio != 0.5f) { gt_set_error(e, "gt_create: only downsample_ratio 0.5 is implemented"); return fail(GT_ERR_INVALID); }
+  e->work_w = (int)(c.frame_w * c.downsample_ratio);
+  e->work_h = (int)(c.frame_h * c.downsample_ratio);
+  const int B = c.max_batch;
+  CR(e->dev_alloc((void**)&e->frames_dev, (size_t)B * c.frame_h * c.frame_w * 3));
+  CR(e->host_alloc((void**)&e->frames_pinned, (size_t)B * c.frame_h * c.frame_w * 3));
+  CR(e->dev_alloc((void**)&e->net_in, (size_t)B * 3 * e->net_h * e->net_w * sizeof(bf16)));
+  CR(conv_tc_init(e));
+  CR(orb_build(e));      // allocates the pyramid slabs (level 0 = stage-1 gray output)
+  CR(detector_build(e));
+  CR(stab_build(e));
+  // constant letterbox border
+  CR(detector_fill_pad(e, e->stream));
+  CRC(cudaStreamSynchronize(e->stream));
+#undef CR
+#undef CRC
+  *out = e;
+  return GT_OK;
+}
+
+int gt_destroy(gt_handle e) {
+  if (!e) return GT_OK;
+  cudaSetDevice(e->device);
+  cudaDeviceSynchronize();
+  for (void* p : e->dev_allocs) cudaFree(p);
+  for (void* p : e->host_allocs) cudaFreeHost(p);
+  for (int i = 0; i < 8; ++i) if (e->ev[i]) cudaEventDestroy(e->ev[i]);
+  if (e->stream) cudaStreamDestroy(e->stream);
+  delete e;
+  return GT_OK;
+}
+
+}  // extern "C"
+
+// ---- helpers -----------------------------------------------------------------------------------------------------------
+static bool is_device_ptr(const void* p) {
+  cudaPointerAttributes at;
+  if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return false; }
+  return at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged;
+}
+static bool is_pinned_ptr(const void* p) {
+  cudaPointerAttributes at;
+  if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return false; }
+  return at.type == cudaMemoryTypeHost;
+}
+static cudaStream_t pick_stream(gt_engine* e, void* s) { return s ? (cudaStream_t)s : e->stream; }
+
+// copy a caller buffer (host or device) into a device workspace
+static int to_device(gt_engine* e, void* dst, const void* src, size_t bytes, cudaStream_t st) {
+  if (!bytes) return GT_OK;
+  GT_CUDA(e, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDefault, st));
+  if (!is_device_ptr(src) && !is_pinned_ptr(src)) GT_CUDA(e, cudaStreamSynchronize(st));  // pageable source: keep caller semantics simple
+  return GT_OK;
+}
+static int to_caller(gt_engine* e, void* dst, const void* src, size_t bytes, cudaStream_t st) {
+  if (!bytes || !dst) return GT_OK;
+  GT_CUDA(e, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDefault, st));
+  return GT_OK;
+}
+
+#define ENTER(e)                                  \
+  if (!(e)) return GT_ERR_INVALID;                \
+  if (cudaSetDevice((e)->device) != cudaSuccess) { gt_set_error((e), "cudaSetDevice failed"); return GT_ERR_CUDA; }
+
+extern "C" {
+
+int gt_conv_count(gt_handle e) { return e ? (int)e->conv_descs.size() : GT_ERR_INVALID; }
+int gt_conv_info(gt_handle e, int idx, gt_conv_desc* out) {
+  if (!e || !out || idx < 0 || idx >= (int)e->conv_descs.size()) return GT_ERR_INVALID;
+  *out = e->conv_descs[idx];
+  return GT_OK;
+}
+int gt_load_weights(gt_handle e, const float* const* weights, const float* const* biases, int n_convs) {
+  ENTER(e);
+  return detector_load_weights(e, weights, biases, n_convs);
+}
+
+int gt_preprocess(gt_handle e, const uint8_t* frames, int B, void* stream) {
+  ENTER(e);
+  GT_CHECK(e, frames && B >= 1 && B <= e->cfg.max_batch, "gt_preprocess: bad batch %d", B);
+  cudaStream_t st = pick_stream(e, stream);
+  const uint8_t* src = frames;
+  GT_CUDA(e, cudaEventRecord(e->ev[0], st));
+  if (!is_device_ptr(frames)) {
+    const size_t bytes = (size_t)B * e->cfg.frame_h * e->cfg.frame_w * 3;
+    GT_TRY(to_device(e, e->frames_dev, frames, bytes, st));
+    src = e->frames_dev;
+  }
+  GT_TRY(detector_preprocess(e, src, B, st));
+  GT_CUDA(e, cudaEventRecord(e->ev[1], st));
+  return GT_OK;
+}
+
+int gt_get_net_input(gt_handle e, int B, uint16_t* out, int32_t* net_h, int32_t* net_w) {
+  ENTER(e);
+  if (net_h) *net_h = e->net_h;
+  if (net_w) *net_w = e->net_w;
+  if (out) {
+    GT_CUDA(e, cudaStreamSynchronize(e->stream));
+    GT_CUDA(e, cudaMemcpy(out, e->net_in, (size_t)B * 3 * e->net_h * e->net_w * 2, cudaMemcpyDefault));
+  }
+  return GT_OK;
+}
+int gt_get_gray(gt_handle e, int B, uint8_t* out, int32_t* work_h, int32_t* work_w) {
+  ENTER(e);
+  if (work_h) *work_h = e->work_h;
+  if (work_w) *work_w = e->work_w;
+  if (out) {
+    GT_CUDA(e, cudaStreamSynchronize(e->stream));
+    GT_CUDA(e, cudaMemcpy2D(out, (size_t)e->work_h * e->work_w, e->pyr, e->pyr_bytes, (size_t)e->work_h * e->work_w, B, cudaMemcpyDefault));
+  }
+  return GT_OK;
+}
+
+static int detect_impl(gt_engine* e, int B, float conf, float iou, int agnostic, uint32_t classes_mask, cudaStream_t st) {
+  GT_CUDA(e, cudaEventRecord(e->ev[2], st));
+  GT_TRY(detector_forward(e, B, st));
+  GT_CUDA(e, cudaEventRecord(e->ev[3], st));
+  GT_TRY(detector_postprocess(e, B, conf, iou, agnostic, classes_mask, st));
+  GT_CUDA(e, cudaEventRecord(e->ev[4], st));
+  return GT_OK;
+}
+
+static int copy_dets(gt_engine* e, int B, float* out_boxes, int32_t* out_counts, int32_t* out_keep, cudaStream_t st) {
+  const int row = e->cfg.task == GT_TASK_OBB ? 7 : 6;
+  GT_TRY(to_caller(e, out_boxes, e->det_out, (size_t)B * e->cfg.max_det * row * sizeof(float), st));
+  GT_TRY(to_caller(e, out_counts, e->det_count, (size_t)B * sizeof(int), st));
+  GT_TRY(to_caller(e, out_keep, e->det_keep, (size_t)B * e->cfg.max_det * sizeof(int), st));
+  return GT_OK;
+}
+
+static void update_times(gt_engine* e) {
+  float t;
+  if (cudaEventElapsedTime(&t, e->ev[0], e->ev[1]) == cudaSuccess) e->stage_ms[0] = t;
+  if (cudaEventElapsedTime(&t, e->ev[2], e->ev[3]) == cudaSuccess) { e->stage_ms[1] = t; e->conv_ms = t; }
+  if (cudaEventElapsedTime(&t, e->ev[3], e->ev[4]) == cudaSuccess) e->stage_ms[2] = t;
+  if (cudaEventElapsedTime(&t, e->ev[5], e->ev[6]) == cudaSuccess) e->stage_ms[3] = t;
+  cudaGetLastError();
+}
+
+int gt_detect(gt_handle e, int B, float conf, float iou, int agnostic, uint32_t classes_mask, float* out_boxes, int32_t* out_counts,
+              int32_t* out_keep, void* stream) {
+  ENTER(e);
+  GT_CHECK(e, B >= 1 && B <= e->cfg.max_batch, "gt_detect: bad batch %d", B);
+  cudaStream_t st = pick_stream(e, stream);
+  GT_TRY(detect_impl(e, B, conf, iou, agnostic, classes_mask, st));
+  GT_TRY(copy_dets(e, B, out_boxes, out_counts, out_keep, st));
+  GT_CUDA(e, cudaStreamSynchronize(st));
+  update_times(e);
+  return GT_OK;
+}
+
+int gt_get_raw_head(gt_handle e, int B, float* out, int32_t* A, int32_t* no) {
+  ENTER(e);
+  if (A) *A = e->A;
+  if (no) *no = e->no;
+  if (out) {
+    GT_CUDA(e, cudaStreamSynchronize(e->stream));
+    GT_CUDA(e, cudaMemcpy(out, e->raw_head, (size_t)B * e->A * e->no * sizeof(float), cudaMemcpyDefault));
+  }
+  return GT_OK;
+}
+
+int gt_get_feature(gt_handle e, int layer, int B, uint16_t* out, int32_t* C, int32_t* H, int32_t* W) {
+  ENTER(e);
+  GT_CHECK(e, layer >= 0 && layer < 23 && e->feat_views[layer].ptr, "gt_get_feature: layer %d has no buffer", layer);
+  const View& v = e->feat_views[layer];
+  if (C) *C = v.C;
+  if (H) *H = v.H;
+  if (W) *W = v.W;
+  if (out) {
+    GT_CUDA(e, cudaStreamSynchronize(e->stream));
+    GT_CUDA(e, cudaMemcpy2D(out, (size_t)v.C * 2, v.ptr + v.coff, (size_t)v.ctot * 2, (size_t)v.C * 2, (size_t)B * v.H * v.W, cudaMemcpyDefault));
+  }
+  return GT_OK;
+}
+
+int gt_nms(gt_handle e, const float* pred, int B, int A, int nc, int rotated, float conf, float iou, int agnostic, uint32_t classes_mask,
+           int max_det, float* out_rows, int32_t* out_counts, int32_t* out_keep, void* stream) {
+  ENTER(e);
+  GT_CHECK(e, pred && B >= 1 && B <= e->cfg.max_batch && A >= 1 && A <= e->A && nc >= 1 && nc <= 80, "gt_nms: bad shape B=%d A=%d nc=%d", B, A, nc);
+  cudaStream_t st = pick_stream(e, stream);
+  const int row_in = 4 + nc + (rotated ? 1 : 0);
+  const size_t bytes = (size_t)B * A * row_in * sizeof(float);
+  const float* src = pred;
+  if (!is_device_ptr(pred)) {
+    if (bytes > e->pred_tmp_bytes) {
+      GT_TRY(e->dev_alloc((void**)&e->pred_tmp, bytes));
+      e->pred_tmp_bytes = bytes;
+    }
+    GT_TRY(to_device(e, e->pred_tmp, pred, bytes, st));
+    src = e->pred_tmp;
+  }
+  GT_TRY(nms_run(e, src, B, A, nc, rotated, conf, iou, agnostic, classes_mask, max_det, false, st));
+  const int row = rotated ? 7 : 6;
+  GT_TRY(to_caller(e, out_rows, e->det_out, (size_t)B * max_det * row * sizeof(float), st));
+  GT_TRY(to_caller(e, out_counts, e->det_count, (size_t)B * sizeof(int), st));
+  GT_TRY(to_caller(e, out_keep, e->det_keep, (size_t)B * max_det * sizeof(int), st));
+  GT_CUDA(e, cudaStreamSynchronize(st));
+  return GT_OK;
+}
+
+int gt_conv2d(gt_handle e, const uint16_t* x, int B, int H, int W, int cin, const float* w, const float* bias, int cout, int k, int stride,
+              int act, const uint16_t* residual, void* out, int out_f32, void* stream) {
+  ENTER(e);
+  GT_CHECK(e, x && w && out && B >= 1 && cin >= 8 && (cin % 8) == 0 && cout >= 1, "gt_conv2d: bad arguments");
+  GT_CHECK(e, out_f32 || (cout % 8) == 0, "gt_conv2d: bf16 output needs cout %% 8 == 0");
+  cudaStream_t st = pick_stream(e, stream);
+  const int pad = k / 2, Ho = (H + 2 * pad - k) / stride + 1, Wo = (W + 2 * pad - k) / stride + 1;
+  bf16 *dx = nullptr, *dres = nullptr;
+  void* dout = nullptr;
+  const size_t mark = e->dev_allocs.size();
+  auto cleanup = [&]() {
+    cudaStreamSynchronize(st);
+    while (e->dev_allocs.size() > mark) { cudaFree(e->dev_allocs.back()); e->dev_allocs.pop_back(); }
+  };
+  int rc = GT_OK;
+  do {
+    if ((rc = e->dev_alloc((void**)&dx, (size_t)B * H * W * cin * 2)) != GT_OK) break;
+    if ((rc = e->dev_alloc(&dout, (size_t)B * Ho * Wo * cout * (out_f32 ? 4 : 2))) != GT_OK) break;
+    if ((rc = to_device(e, dx, x, (size_t)B * H * W * cin * 2, st)) != GT_OK) break;
+    View in; in.ptr = dx; in.C = cin; in.ctot = cin; in.coff = 0; in.H = H; in.W = W;
+    View ov; ov.ptr = (bf16*)dout; ov.C = cout; ov.ctot = cout; ov.coff = 0; ov.H = Ho; ov.W = Wo;
+    View rv = ov;
+    if (residual) {
+      if ((rc = e->dev_alloc((void**)&dres, (size_t)B * Ho * Wo * cout * 2)) != GT_OK) break;
+      if ((rc = to_device(e, dres, residual, (size_t)B * Ho * Wo * cout * 2, st)) != GT_OK) break;
+      rv.ptr = dres;
+    }
+    ConvOp op;
+    rc = conv_tc_plan(e, &op, in, B, cin, cout, k, stride, act, out_f32 ? nullptr : &ov, out_f32 ? (float*)dout : nullptr,
+                      (long long)Ho * Wo, cout, 0, residual ? &rv : nullptr, nullptr);
+    if (rc != GT_OK) break;
+    const float* ws[1] = {w};
+    const float* bs[1] = {bias};
+    int couts[1] = {cout};
+    if ((rc = conv_tc_pack_weights(e, &op, ws, bs, couts, 1)) != GT_OK) break;
+    if ((rc = conv_tc_launch(e, &op, B, st)) != GT_OK) break;
+    cudaError_t er = cudaStreamSynchronize(st);
+    if (er != cudaSuccess) { gt_set_error(e, "gt_conv2d kernel failed: %s", cudaGetErrorString(er)); rc = GT_ERR_CUDA; break; }
+    er = cudaMemcpy(out, dout, (size_t)B * Ho * Wo * cout * (out_f32 ? 4 : 2), cudaMemcpyDefault);
+    if (er != cudaSuccess) { gt_set_error(e, "gt_conv2d copy-out failed: %s", cudaGetErrorString(er)); rc = GT_ERR_CUDA; break; }
+  } while (0);
+  cleanup();
+  return rc;
+}
+
+// ---- stage 3 ------------------------------------------------------------------------------------------------------------
+static int upload_boxes(gt_engine* e, int slot0, int B, const float* boxes, const int32_t* nboxes, int box_stride, cudaStream_t st) {
+  const int md = e->cfg.max_det;
+  if (!boxes || !nboxes) {
+    GT_CUDA(e, cudaMemsetAsync(e->nboxes_dev + slot0, 0, sizeof(int) * B, st));
+    return GT_OK;
+  }
+  GT_CHECK(e, box_stride >= 0 && box_stride <= md, "boxes: stride %d exceeds max_det %d", box_stride, md);
+  GT_CUDA(e, cudaMemcpy2DAsync(e->boxes_dev + (size_t)slot0 * md * 4, (size_t)md * 16, boxes, (size_t)box_stride * 16, (size_t)box_stride * 16, B,
+                               cudaMemcpyDefault, st));
+  GT_CUDA(e, cudaMemcpyAsync(e->nboxes_dev + slot0, nboxes, sizeof(int) * B, cudaMemcpyDefault, st));
+  return GT_OK;
+}
+
+int gt_set_reference(gt_handle e, int frame_slot, const float* boxes, int nboxes, void* stream) {
+  ENTER(e);
+  GT_CHECK(e, frame_slot >= 0 && frame_slot < e->cfg.max_batch, "gt_set_reference: slot %d out of range", frame_slot);
+  cudaStream_t st = pick_stream(e, stream);
+  const int R = e->cfg.max_batch;  // reference slot
+  // copy gray level 0 of the chosen frame into the reference slab
+  GT_CUDA(e, cudaMemcpyAsync(e->pyr + (size_t)R * e->pyr_bytes, e->pyr + (size_t)frame_slot * e->pyr_bytes, (size_t)e->work_h * e->work_w,
+                             cudaMemcpyDeviceToDevice, st));
+  int32_t nb = nboxes;
+  GT_TRY(upload_boxes(e, R, 1, nboxes > 0 ? boxes : nullptr, nboxes > 0 ? &nb : nullptr, nboxes, st));
+  GT_CUDA(e, cudaStreamSynchronize(st));  // nb is a stack variable
+  GT_TRY(orb_run(e, R, 1, true, true, st));
+  e->have_ref = true;
+  return GT_OK;
+}
+
+static int stabilize_impl(gt_engine* e, int B, cudaStream_t st) {
+  GT_CHECK(e, e->have_ref, "gt_stabilize: no reference frame set");
+  GT_CUDA(e, cudaEventRecord(e->ev[5], st));
+  GT_TRY(orb_run(e, 0, B, false, true, st));
+  GT_TRY(stab_match_and_fit(e, B, st));
+  GT_CUDA(e, cudaEventRecord(e->ev[6], st));
+  return GT_OK;
+}
+
+int gt_stabilize(gt_handle e, int B, const float* boxes, const int32_t* nboxes, int box_stride, double* out_H, int32_t* out_status,
+                 int32_t* out_stats, void* stream) {
+  ENTER(e);
+  GT_CHECK(e, B >= 1 && B <= e->cfg.max_batch, "gt_stabilize: bad batch %d", B);
+  cudaStream_t st = pick_stream(e, stream);
+  GT_TRY(upload_boxes(e, 0, B, boxes, nboxes, box_stride, st));
+  GT_TRY(stabilize_impl(e, B, st));
+  GT_TRY(to_caller(e, out_H, e->H_dev, (size_t)B * 9 * sizeof(double), st));
+  GT_TRY(to_caller(e, out_status, e->H_status, (size_t)B * sizeof(int), st));
+  GT_TRY(to_caller(e, out_stats, e->H_stats, (size_t)B * 4 * sizeof(int), st));
+  GT_CUDA(e, cudaStreamSynchronize(st));
+  update_times(e);
+  return GT_OK;
+}
+
+int gt_warp_boxes(gt_handle e, const double* H, float* boxes, int n, void* stream) {
+  ENTER(e);
+  GT_CHECK(e, H && boxes && n >= 0 && n <= e->cfg.max_det, "gt_warp_boxes: bad arguments (n=%d)", n);
+  if (n == 0) return GT_OK;
+  cudaStream_t st = pick_stream(e, stream);
+  GT_TRY(to_device(e, e->H_dev, H, 9 * sizeof(double), st));
+  GT_TRY(to_device(e, e->boxes_dev, boxes, (size_t)n * 16, st));
+  GT_CUDA(e, cudaMemcpyAsync(e->nboxes_dev, &n, sizeof(int), cudaMemcpyHostToDevice, st));
+  GT_TRY(warp_boxes_run(e, e->H_dev, nullptr, e->boxes_dev, e->boxes_stab_dev, e->nboxes_dev, 1, e->cfg.max_det, st));
+  GT_TRY(to_caller(e, boxes, e->boxes_stab_dev, (size_t)n * 16, st));
+  GT_CUDA(e, cudaStreamSynchronize(st));
+  return GT_OK;
+}
+
+int gt_orb_level_info(gt_handle e, int level, int32_t* w, int32_t* hgt, int32_t* quota_cur, int32_t* quota_ref) {
+  if (!e || level < 0 || level >= GT_ORB_LEVELS) return GT_ERR_INVALID;
+  if (w) *w = e->lv[level].w;
+  if (hgt) *hgt = e->lv[level].h;
+  if (quota_cur) *quota_cur = e->lv[level].quota_cur;
+  if (quota_ref) *quota_ref = e->lv[level].quota_ref;
+  return GT_OK;
+}
+
+int gt_get_pyramid_level(gt_handle e, int which, int b, int level, uint8_t* out_img, uint8_t* out_mask) {
+  ENTER(e);
+  GT_CHECK(e, level >= 0 && level < GT_ORB_LEVELS && b >= 0 && b < e->cfg.max_batch, "gt_get_pyramid_level: bad index");
+  const int slot = which ? e->cfg.max_batch : b;
+  const OrbLevel& L = e->lv[level];
+  GT_CUDA(e, cudaStreamSynchronize(e->stream));
+  if (out_img) GT_CUDA(e, cudaMemcpy(out_img, e->pyr + (size_t)slot * e->pyr_bytes + L.off, (size_t)L.w * L.h, cudaMemcpyDefault));
+  if (out_mask) GT_CUDA(e, cudaMemcpy(out_mask, e->pyr_mask + (size_t)slot * e->pyr_bytes + L.off, (size_t)L.w * L.h, cudaMemcpyDefault));
+  return GT_OK;
+}
+
+int gt_get_keypoints(gt_handle e, int which, int b, int max_n, float* out_kp, uint8_t* out_desc, int32_t* n) {
+  ENTER(e);
+  GT_CHECK(e, b >= 0 && b < e->cfg.max_batch && n, "gt_get_keypoints: bad index");
+  const int slot = which ? e->cfg.max_batch : b;
+  GT_CUDA(e, cudaStreamSynchronize(e->stream));
+  int cnt = 0;
+  GT_CUDA(e, cudaMemcpy(&cnt, e->kp_count + slot, sizeof(int), cudaMemcpyDefault));
+  cnt = std::min(cnt, GT_MAX_KP);
+  *n = cnt;
+  const int m = std::min(cnt, max_n);
+  if (out_kp && m) GT_CUDA(e, cudaMemcpy(out_kp, e->kp_all + (size_t)slot * GT_MAX_KP * 6, (size_t)m * 6 * sizeof(float), cudaMemcpyDefault));
+  if (out_desc && m) GT_CUDA(e, cudaMemcpy(out_desc, e->desc_all + (size_t)slot * GT_MAX_KP * 32, (size_t)m * 32, cudaMemcpyDefault));
+  return GT_OK;
+}
+
+int gt_orb_detect(gt_handle e, const uint8_t* gray, const uint8_t* mask, int B, int as_reference, void* stream) {
+  ENTER(e);
+  GT_CHECK(e, gray && B >= 1 && B <= e->cfg.max_batch && (!as_reference || B == 1), "gt_orb_detect: bad arguments");
+  cudaStream_t st = pick_stream(e, stream);
+  const int slot0 = as_reference ? e->cfg.max_batch : 0;
+  const size_t img = (size_t)e->work_h * e->work_w;
+  GT_CUDA(e, cudaMemcpy2DAsync(e->pyr + (size_t)slot0 * e->pyr_bytes, e->pyr_bytes, gray, img, img, B, cudaMemcpyDefault, st));
+  if (mask) GT_CUDA(e, cudaMemcpy2DAsync(e->pyr_mask + (size_t)slot0 * e->pyr_bytes, e->pyr_bytes, mask, img, img, B, cudaMemcpyDefault, st));
+  else GT_CUDA(e, cudaMemset2DAsync(e->pyr_mask + (size_t)slot0 * e->pyr_bytes, e->pyr_bytes, 255, img, B, st));
+  GT_TRY(orb_run(e, slot0, B, as_reference != 0, false, st));
+  GT_CUDA(e, cudaStreamSynchronize(st));
+  if (as_reference) e->have_ref = true;
+  return GT_OK;
+}
+
+int gt_match(gt_handle e, const uint8_t* query, int nq, const uint8_t* train, int nt, int32_t* out_idx, int32_t* out_dist, void* stream) {
+  ENTER(e);
+  GT_CHECK(e, query && train && nq >= 1 && nt >= 1 && nq <= GT_MAX_KP && nt <= GT_MAX_KP && out_idx && out_dist, "gt_match: bad arguments");
+  cudaStream_t st = pick_stream(e, stream);
+  uint8_t* dq = e->desc_all;                                        // slot 0
+  uint8_t* dt = e->desc_all + (size_t)e->cfg.max_batch * GT_MAX_KP * 32;  // reference slot
+  GT_TRY(to_device(e, dq, query, (size_t)nq * 32, st));
+  GT_TRY(to_device(e, dt, train, (size_t)nt * 32, st));
+  int h_n[2] = {nq, nt};
+  GT_CUDA(e, cudaMemcpyAsync(e->kp_count, &h_n[0], sizeof(int), cudaMemcpyHostToDevice, st));
+  GT_CUDA(e, cudaMemcpyAsync(e->kp_count + e->cfg.max_batch, &h_n[1], sizeof(int), cudaMemcpyHostToDevice, st));
+  GT_CUDA(e, cudaStreamSynchronize(st));
+  GT_TRY(match_run(e, dq, e->kp_count, nq, dt, e->kp_count + e->cfg.max_batch, nt, e->match_idx, e->match_dist, 1, 0, 0, st));
+  GT_TRY(to_caller(e, out_idx, e->match_idx, (size_t)nq * 2 * sizeof(int), st));
+  GT_TRY(to_caller(e, out_dist, e->match_dist, (size_t)nq * 2 * sizeof(int), st));
+  GT_CUDA(e, cudaStreamSynchronize(st));
+  return GT_OK;
+}
+
+int gt_find_homography(gt_handle e, const float* src, const float* dst, int n, float thr, int max_iter, double* out_H, int32_t* out_inliers,
+                       void* stream) {
+  ENTER(e);
+  GT_CHECK(e, src && dst && n >= 0 && n <= GT_MAX_KP && out_H && max_iter >= 1 && max_iter <= e->cfg.ransac_max_iter,
+           "gt_find_homography: bad arguments (n=%d, max_iter=%d)", n, max_iter);
+  cudaStream_t st = pick_stream(e, stream);
+  std::vector<float> pr((size_t)std::max(n, 1) * 4);
+  for (int i = 0; i < n; ++i) { pr[i * 4] = src[i * 2]; pr[i * 4 + 1] = src[i * 2 + 1]; pr[i * 4 + 2] = dst[i * 2]; pr[i * 4 + 3] = dst[i * 2 + 1]; }
+  GT_CUDA(e, cudaMemcpyAsync(e->pairs, pr.data(), (size_t)n * 16, cudaMemcpyHostToDevice, st));
+  GT_CUDA(e, cudaMemcpyAsync(e->pair_count, &n, sizeof(int), cudaMemcpyHostToDevice, st));
+  GT_CUDA(e, cudaStreamSynchronize(st));
+  GT_TRY(homography_run(e, e->pairs, e->pair_count, 1, GT_MAX_KP, thr, max_iter, e->H_dev, e->H_status, e->H_stats, 1.0f, true, nullptr, st));
+  int stats[4], status = 0;
+  GT_CUDA(e, cudaMemcpyAsync(out_H, e->H_dev, 9 * sizeof(double), cudaMemcpyDefault, st));
+  GT_CUDA(e, cudaMemcpyAsync(stats, e->H_stats, sizeof(stats), cudaMemcpyDeviceToHost, st));
+  GT_CUDA(e, cudaMemcpyAsync(&status, e->H_status, sizeof(int), cudaMemcpyDeviceToHost, st));
+  GT_CUDA(e, cudaStreamSynchronize(st));
+  if (out_inliers) *out_inliers = stats[3];
+  return status == 0 ? GT_OK : 1;
+}
+
+// boxes (x1,y1,x2,y2,...) -> xywh mask boxes for the stabilizer, on device
+__global__ void dets_to_xywh_kernel(const float* __restrict__ det, const int* __restrict__ cnt, int row, int max_det, float* __restrict__ xywh,
+                                    int* __restrict__ nb, int B, int obb) {
+  const int b = blockIdx.y;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int n = cnt[b];
+  if (i == 0) nb[b] = n;
+  if (i >= n) return;
+  const float* d = det + ((size_t)b * max_det + i) * row;
+  float* o = xywh + ((size_t)b * max_det + i) * 4;
+  if (!obb) {
+    o[0] = (d[0] + d[2]) * 0.5f; o[1] = (d[1] + d[3]) * 0.5f; o[2] = d[2] - d[0]; o[3] = d[3] - d[1];
+  } else {  // axis-aligned envelope of the rotated box
+    const float c = fabsf(cosf(d[4])), s = fabsf(sinf(d[4]));
+    o[0] = d[0]; o[1] = d[1]; o[2] = d[2] * c + d[3] * s; o[3] = d[2] * s + d[3] * c;
+  }
+}
+
+int gt_extract_batch(gt_handle e, const uint8_t* frames, int B, int first_is_reference, float conf, float iou, int agnostic,
+                     uint32_t classes_mask, float* out_boxes, int32_t* out_counts, float* out_boxes_stab, double* out_H, int32_t* out_status,
+                     int32_t* out_stats, void* stream) {
+  ENTER(e);
+  GT_CHECK(e, frames && B >= 1 && B <= e->cfg.max_batch, "gt_extract_batch: bad batch %d", B);
+  cudaStream_t st = pick_stream(e, stream);
+  GT_TRY(gt_preprocess(e, frames, B, st));
+  GT_TRY(detect_impl(e, B, conf, iou, agnostic, classes_mask, st));
+  const int md = e->cfg.max_det;
+  const int obb = e->cfg.task == GT_TASK_OBB;
+  dim3 g((unsigned)ceil_div(md, 256), (unsigned)B);
+  dets_to_xywh_kernel<<<g, 256, 0, st>>>(e->det_out, e->det_count, obb ? 7 : 6, md, e->boxes_dev, e->nboxes_dev, B, obb);
+  e->launches++;
+  if (first_is_reference) {
+    const int R = e->cfg.max_batch;
+    GT_CUDA(e, cudaMemcpyAsync(e->pyr + (size_t)R * e->pyr_bytes, e->pyr, (size_t)e->work_h * e->work_w, cudaMemcpyDeviceToDevice, st));
+    GT_CUDA(e, cudaMemcpyAsync(e->boxes_dev + (size_t)R * md * 4, e->boxes_dev, (size_t)md * 16, cudaMemcpyDeviceToDevice, st));
+    GT_CUDA(e, cudaMemcpyAsync(e->nboxes_dev + R, e->nboxes_dev, sizeof(int), cudaMemcpyDeviceToDevice, st));
+    GT_TRY(orb_run(e, R, 1, true, true, st));
+    e->have_ref = true;
+  }
+  GT_TRY(stabilize_impl(e, B, st));
+  GT_TRY(warp_boxes_run(e, e->H_dev, e->H_status, e->boxes_dev, e->boxes_stab_dev, e->nboxes_dev, B, md, st));
+  GT_TRY(copy_dets(e, B, out_boxes, out_counts, nullptr, st));
+  GT_TRY(to_caller(e, out_boxes_stab, e->boxes_stab_dev, (size_t)B * md * 16, st));
+  GT_TRY(to_caller(e, out_H, e->H_dev, (size_t)B * 9 * sizeof(double), st));
+  GT_TRY(to_caller(e, out_status, e->H_status, (size_t)B * sizeof(int), st));
+  GT_TRY(to_caller(e, out_stats, e->H_stats, (size_t)B * 4 * sizeof(int), st));
+  GT_CUDA(e, cudaStreamSynchronize(st));
+  update_times(e);
+  return GT_OK;
+}
+
+int gt_stage_times(gt_handle e, float* ms4) {
+  if (!e || !ms4) return GT_ERR_INVALID;
+  for (int i = 0; i < 4; ++i) ms4[i] = e->stage_ms[i];
+  return GT_OK;
+}
+int64_t gt_launch_count(gt_handle e) { return e ? e->launches : -1; }
+int gt_conv_stack_stats(gt_handle e, float* ms, double* flops) {
+  if (!e) return GT_ERR_INVALID;
+  if (ms) *ms = e->conv_ms;
+  if (flops) *flops = e->conv_flops;
+  return GT_OK;
+}
+
+}  // extern "C"

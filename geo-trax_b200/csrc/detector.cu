@@ -1,0 +1,839 @@
+// Stage 1 (letterbox / normalise / gray) and stage 2 (YOLOv8s graph, DFL decode, confidence filter, NMS).
+//
+// Reference sites (un-vendored ultralytics reached from /root/reference/geotrax/extract.py:153; restated in SURVEY.md
+// section 8a-3 .. 8a-6 and Appendix A-1/A-2): LetterBox + BasePredictor.preprocess, DetectionModel.forward (fused),
+// Detect/OBB head + DFL + dist2bbox/dist2rbox, non_max_suppression (torchvision.ops.nms / nms_rotated), scale_boxes.
+#include <algorithm>
+#include <map>
+
+#include "engine.cuh"
+
+// =====================================================================================================================
+// Stage 1: fused letterbox (exact 1/2 decimation) + BGR->RGB + /255 -> planar bf16, and BGR2GRAY + 1/2 resize -> u8.
+// One thread: 8 output pixels = 2 rows x 48 B of the source (three 128-bit loads per row).
+// =====================================================================================================================
+__device__ __forceinline__ uint32_t gray15(uint32_t b, uint32_t g, uint32_t r) {
+  return (9798u * r + 19235u * g + 3735u * b + 16384u) >> 15;  // OpenCV BGR2GRAY, 15-bit coefficients
+}
+
+__global__ void __launch_bounds__(256) preprocess_half_kernel(const uint8_t* __restrict__ frames, bf16* __restrict__ net_in,
+                                                              uint8_t* __restrict__ gray, size_t gray_frame_stride, int B,
+                                                              int H, int W, int net_h, int net_w, int pad_top, int pad_left,
+                                                              int new_h, int new_w) {
+  const int groups = new_w >> 3;  // 8 output pixels per thread
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long per_frame = (long long)new_h * groups;
+  if (idx >= per_frame * B) return;
+  const int b = (int)(idx / per_frame);
+  const int rem = (int)(idx - (long long)b * per_frame);
+  const int oy = rem / groups, og = rem - oy * groups;
+  const uint8_t* src = frames + ((size_t)b * H + 2 * oy) * (size_t)W * 3 + (size_t)og * 48;
+  uint4 r0[3], r1[3];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    r0[i] = __ldg(reinterpret_cast<const uint4*>(src) + i);
+    r1[i] = __ldg(reinterpret_cast<const uint4*>(src + (size_t)W * 3) + i);
+  }
+  const uint8_t* a = reinterpret_cast<const uint8_t*>(r0);
+  const uint8_t* c = reinterpret_cast<const uint8_t*>(r1);
+  __align__(16) bf16 pr[8], pg[8], pb[8];
+  __align__(8) uint8_t gy[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int o = j * 6;
+    const uint32_t b00 = a[o], g00 = a[o + 1], r00 = a[o + 2], b01 = a[o + 3], g01 = a[o + 4], r01 = a[o + 5];
+    const uint32_t b10 = c[o], g10 = c[o + 1], r10 = c[o + 2], b11 = c[o + 3], g11 = c[o + 4], r11 = c[o + 5];
+    const uint32_t bb = (b00 + b01 + b10 + b11 + 2) >> 2;  // cv2.resize INTER_LINEAR at exactly 1/2
+    const uint32_t gg = (g00 + g01 + g10 + g11 + 2) >> 2;
+    const uint32_t rr = (r00 + r01 + r10 + r11 + 2) >> 2;
+    pr[j] = __float2bfloat16_rn(__fdiv_rn((float)rr, 255.0f));
+    pg[j] = __float2bfloat16_rn(__fdiv_rn((float)gg, 255.0f));
+    pb[j] = __float2bfloat16_rn(__fdiv_rn((float)bb, 255.0f));
+    const uint32_t y00 = gray15(b00, g00, r00), y01 = gray15(b01, g01, r01), y10 = gray15(b10, g10, r10), y11 = gray15(b11, g11, r11);
+    gy[j] = (uint8_t)((y00 + y01 + y10 + y11 + 2) >> 2);  // gray first, then the 1/2 resize (stabilo order)
+  }
+  const size_t plane = (size_t)net_h * net_w;
+  bf16* dst = net_in + (size_t)b * 3 * plane + (size_t)(oy + pad_top) * net_w + pad_left + og * 8;
+  *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(pr);
+  *reinterpret_cast<uint4*>(dst + plane) = *reinterpret_cast<const uint4*>(pg);
+  *reinterpret_cast<uint4*>(dst + 2 * plane) = *reinterpret_cast<const uint4*>(pb);
+  if (gray) *reinterpret_cast<uint2*>(gray + (size_t)b * gray_frame_stride + (size_t)oy * new_w + og * 8) = *reinterpret_cast<const uint2*>(gy);
+}
+
+// letterbox padding (value 114) for the rows/columns outside the resized image
+__global__ void preprocess_pad_kernel(bf16* __restrict__ net_in, int B, int net_h, int net_w, int pad_top, int pad_left, int new_h,
+                                      int new_w) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long total = (long long)B * 3 * net_h * net_w;
+  if (idx >= total) return;
+  const int x = (int)(idx % net_w);
+  const int y = (int)((idx / net_w) % net_h);
+  if (y >= pad_top && y < pad_top + new_h && x >= pad_left && x < pad_left + new_w) return;
+  net_in[idx] = __float2bfloat16_rn(__fdiv_rn(114.0f, 255.0f));
+}
+
+int detector_fill_pad(gt_engine* e, cudaStream_t st) {
+  const int B = e->cfg.max_batch;
+  const long long total = (long long)B * 3 * e->net_h * e->net_w;
+  preprocess_pad_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(e->net_in, B, e->net_h, e->net_w, e->pad_top, e->pad_left, e->new_h,
+                                                                         e->new_w);
+  GT_CUDA(e, cudaGetLastError());
+  return GT_OK;
+}
+
+int detector_preprocess(gt_engine* e, const uint8_t* frames_dev, int B, cudaStream_t st) {
+  const long long threads = (long long)B * e->new_h * (e->new_w / 8);
+  uint8_t* gray = e->pyr;  // level 0 of each frame's pyramid slab
+  preprocess_half_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(frames_dev, e->net_in, gray, e->pyr_bytes, B, e->cfg.frame_h,
+                                                                            e->cfg.frame_w, e->net_h, e->net_w, e->pad_top, e->pad_left,
+                                                                            e->new_h, e->new_w);
+  e->launches++;
+  GT_CUDA(e, cudaGetLastError());
+  e->cur_frames = frames_dev;
+  return GT_OK;
+}
+
+// =====================================================================================================================
+// Layer 0: Conv(3 -> 32, k3, s2) + folded BN + SiLU on CUDA cores (K = 27 is too thin for the tensor pipe; the layer is
+// HBM-bound: AI 20 FLOP/B).  Planar bf16 in, NHWC bf16 out.  Block = 32 x 8 output pixels.
+// =====================================================================================================================
+__global__ void __launch_bounds__(256) conv0_kernel(const bf16* __restrict__ in, bf16* __restrict__ out, const float* __restrict__ w,
+                                                    const float* __restrict__ bias, int H, int W, int Ho, int Wo) {
+  __shared__ float s_in[3][17][66];
+  __shared__ __align__(16) float s_w[27][32];
+  __shared__ float s_b[32];
+  const int b = blockIdx.z;
+  const int x0 = blockIdx.x * 32, y0 = blockIdx.y * 8;
+  for (int i = threadIdx.x; i < 27 * 32; i += 256) (&s_w[0][0])[i] = w[i];
+  if (threadIdx.x < 32) s_b[threadIdx.x] = bias[threadIdx.x];
+  const size_t plane = (size_t)H * W;
+  for (int i = threadIdx.x; i < 3 * 17 * 65; i += 256) {
+    const int cch = i / (17 * 65);
+    const int r = (i / 65) % 17, cc = i % 65;
+    const int iy = 2 * y0 - 1 + r, ix = 2 * x0 - 1 + cc;
+    float v = 0.f;
+    if (iy >= 0 && iy < H && ix >= 0 && ix < W) v = __bfloat162float(in[((size_t)b * 3 + cch) * plane + (size_t)iy * W + ix]);
+    s_in[cch][r][cc] = v;
+  }
+  __syncthreads();
+  const int lx = threadIdx.x & 31, ly = threadIdx.x >> 5;
+  const int ox = x0 + lx, oy = y0 + ly;
+  float acc[32];
+#pragma unroll
+  for (int i = 0; i < 32; ++i) acc[i] = s_b[i];
+#pragma unroll
+  for (int cch = 0; cch < 3; ++cch)
+#pragma unroll
+    for (int dy = 0; dy < 3; ++dy)
+#pragma unroll
+      for (int dx = 0; dx < 3; ++dx) {
+        const float v = s_in[cch][2 * ly + dy][2 * lx + dx];
+        const float4* wr = reinterpret_cast<const float4*>(&s_w[cch * 9 + dy * 3 + dx][0]);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const float4 ww = wr[q];
+          acc[q * 4 + 0] = fmaf(v, ww.x, acc[q * 4 + 0]);
+          acc[q * 4 + 1] = fmaf(v, ww.y, acc[q * 4 + 1]);
+          acc[q * 4 + 2] = fmaf(v, ww.z, acc[q * 4 + 2]);
+          acc[q * 4 + 3] = fmaf(v, ww.w, acc[q * 4 + 3]);
+        }
+      }
+  if (ox >= Wo || oy >= Ho) return;
+  __align__(16) bf16 o[32];
+#pragma unroll
+  for (int i = 0; i < 32; ++i) o[i] = __float2bfloat16_rn(silu_f(acc[i]));
+  uint4* dst = reinterpret_cast<uint4*>(out + (((size_t)b * Ho + oy) * Wo + ox) * 32);
+#pragma unroll
+  for (int q = 0; q < 4; ++q) dst[q] = reinterpret_cast<const uint4*>(o)[q];
+}
+
+// =====================================================================================================================
+// SPPF max pool 5x5 / stride 1 / pad 2 on a channel slice (NHWC, 8 channels per thread)
+// =====================================================================================================================
+__global__ void __launch_bounds__(256) maxpool5_kernel(const bf16* __restrict__ in, int in_ctot, int in_coff, bf16* __restrict__ out,
+                                                       int out_ctot, int out_coff, int B, int H, int W, int C) {
+  const int c8 = C >> 3;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long total = (long long)B * H * W * c8;
+  if (idx >= total) return;
+  const int cg = (int)(idx % c8);
+  const int x = (int)((idx / c8) % W);
+  const int y = (int)((idx / ((long long)c8 * W)) % H);
+  const int b = (int)(idx / ((long long)c8 * W * H));
+  __nv_bfloat162 m[4];
+  const __nv_bfloat162 ninf = __float2bfloat162_rn(-INFINITY);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) m[i] = ninf;
+  for (int dy = -2; dy <= 2; ++dy) {
+    const int yy = y + dy;
+    if (yy < 0 || yy >= H) continue;
+    for (int dx = -2; dx <= 2; ++dx) {
+      const int xx = x + dx;
+      if (xx < 0 || xx >= W) continue;
+      const uint4 v = __ldg(reinterpret_cast<const uint4*>(in + (((size_t)b * H + yy) * W + xx) * in_ctot + in_coff + cg * 8));
+      const __nv_bfloat162* pv = reinterpret_cast<const __nv_bfloat162*>(&v);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) m[i] = __hmax2(m[i], pv[i]);
+    }
+  }
+  *reinterpret_cast<uint4*>(out + (((size_t)b * H + y) * W + x) * out_ctot + out_coff + cg * 8) = *reinterpret_cast<const uint4*>(m);
+}
+
+// =====================================================================================================================
+// Decode + confidence filter: raw head rows [B][A][no] f32 -> dense candidate arrays indexed by anchor + a key list.
+// key = conf bits << 32 | ~anchor : descending key order == (conf desc, anchor asc) == the order torchvision.ops.nms's
+// stable descending sort gives to ultralytics' anchor-ordered candidate rows.
+// =====================================================================================================================
+struct DecodeGeom {
+  int lvl_w[3], lvl_h[3], lvl_off[3];
+  float stride[3];
+};
+
+__device__ __forceinline__ float sigmoid_f(float x) { return 1.0f / (1.0f + expf(-x)); }
+
+__device__ __forceinline__ float dfl_side(const float* p) {
+  float m = p[0];
+#pragma unroll
+  for (int i = 1; i < 16; ++i) m = fmaxf(m, p[i]);
+  float s = 0.f, ws = 0.f;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    const float ex = expf(p[i] - m);
+    s += ex;
+    ws += ex * (float)i;
+  }
+  return ws / s;
+}
+
+__global__ void __launch_bounds__(256) decode_filter_kernel(const float* __restrict__ raw, int B, int A, int no, int nc, int obb,
+                                                            DecodeGeom g, float conf_thr, uint32_t classes_mask,
+                                                            float* __restrict__ cand_box, float* __restrict__ cand_conf,
+                                                            int* __restrict__ cand_cls, unsigned long long* __restrict__ keys,
+                                                            int key_stride, int* __restrict__ count) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)B * A) return;
+  const int b = (int)(idx / A), a = (int)(idx - (long long)b * A);
+  const float* r = raw + (size_t)idx * no;
+  float best = r[64];
+  int bj = 0;
+  for (int j = 1; j < nc; ++j) {
+    const float v = r[64 + j];
+    if (v > best) { best = v; bj = j; }
+  }
+  const float conf = sigmoid_f(best);
+  if (!(conf > conf_thr)) return;
+  if (classes_mask && !((classes_mask >> bj) & 1u)) return;
+  int lvl = 0;
+  if (a >= g.lvl_off[2]) lvl = 2; else if (a >= g.lvl_off[1]) lvl = 1;
+  const int la = a - g.lvl_off[lvl];
+  const float ax = (float)(la % g.lvl_w[lvl]) + 0.5f, ay = (float)(la / g.lvl_w[lvl]) + 0.5f;
+  const float s = g.stride[lvl];
+  float box[16];
+  float d[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) box[i] = r[k * 16 + i];
+    d[k] = dfl_side(box);
+  }
+  float* o = cand_box + ((size_t)b * A + a) * 5;
+  if (!obb) {
+    const float x1 = ax - d[0], y1 = ay - d[1], x2 = ax + d[2], y2 = ay + d[3];
+    const float cx = __fmul_rn(__fmul_rn(__fadd_rn(x1, x2), 0.5f), s), cy = __fmul_rn(__fmul_rn(__fadd_rn(y1, y2), 0.5f), s);
+    const float w = __fmul_rn(__fsub_rn(x2, x1), s), h = __fmul_rn(__fsub_rn(y2, y1), s);
+    const float hw = __fmul_rn(w, 0.5f), hh = __fmul_rn(h, 0.5f);
+    o[0] = __fsub_rn(cx, hw); o[1] = __fsub_rn(cy, hh); o[2] = __fadd_rn(cx, hw); o[3] = __fadd_rn(cy, hh); o[4] = 0.f;
+  } else {
+    const float ang = (sigmoid_f(r[64 + nc]) - 0.25f) * 3.14159265358979323846f;
+    const float cs = cosf(ang), sn = sinf(ang);
+    const float xf = (d[2] - d[0]) * 0.5f, yf = (d[3] - d[1]) * 0.5f;
+    o[0] = (xf * cs - yf * sn + ax) * s; o[1] = (xf * sn + yf * cs + ay) * s;
+    o[2] = (d[0] + d[2]) * s; o[3] = (d[1] + d[3]) * s; o[4] = ang;
+  }
+  cand_conf[(size_t)b * A + a] = conf;
+  cand_cls[(size_t)b * A + a] = bj;
+  const int slot = atomicAdd(&count[b], 1);
+  keys[(size_t)b * key_stride + slot] = ((unsigned long long)__float_as_uint(conf) << 32) | (unsigned long long)(0xFFFFFFFFu - (uint32_t)a);
+}
+
+// same filter for caller-supplied decoded predictions [B][A][4+nc(+1)] (gt_nms)
+__global__ void __launch_bounds__(256) pred_filter_kernel(const float* __restrict__ pred, int B, int A, int nc, int rotated, float conf_thr,
+                                                          uint32_t classes_mask, float* __restrict__ cand_box, float* __restrict__ cand_conf,
+                                                          int* __restrict__ cand_cls, unsigned long long* __restrict__ keys, int key_stride,
+                                                          int* __restrict__ count) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)B * A) return;
+  const int b = (int)(idx / A), a = (int)(idx - (long long)b * A);
+  const int row = 4 + nc + (rotated ? 1 : 0);
+  const float* r = pred + (size_t)idx * row;
+  float best = r[4];
+  int bj = 0;
+  for (int j = 1; j < nc; ++j) {
+    const float v = r[4 + j];
+    if (v > best) { best = v; bj = j; }
+  }
+  if (!(best > conf_thr)) return;
+  if (classes_mask && !((classes_mask >> bj) & 1u)) return;
+  float* o = cand_box + ((size_t)b * A + a) * 5;
+  if (!rotated) {
+    const float hw = __fmul_rn(r[2], 0.5f), hh = __fmul_rn(r[3], 0.5f);  // xywh2xyxy: xy -+ wh/2
+    o[0] = __fsub_rn(r[0], hw); o[1] = __fsub_rn(r[1], hh); o[2] = __fadd_rn(r[0], hw); o[3] = __fadd_rn(r[1], hh); o[4] = 0.f;
+  } else {
+    o[0] = r[0]; o[1] = r[1]; o[2] = r[2]; o[3] = r[3]; o[4] = r[4 + nc];
+  }
+  cand_conf[(size_t)b * A + a] = best;
+  cand_cls[(size_t)b * A + a] = bj;
+  const int slot = atomicAdd(&count[b], 1);
+  keys[(size_t)b * key_stride + slot] = ((unsigned long long)__float_as_uint(best) << 32) | (unsigned long long)(0xFFFFFFFFu - (uint32_t)a);
+}
+
+// ---- per-image descending bitonic sort of the key list (one CTA per image) -------------------------------------------
+__global__ void __launch_bounds__(1024) sort_keys_kernel(unsigned long long* __restrict__ keys, int key_stride, const int* __restrict__ count) {
+  extern __shared__ unsigned long long s_keys[];
+  const int b = blockIdx.x;
+  const int n = min(count[b], key_stride);
+  if (n <= 1) return;
+  int np2 = 1;
+  while (np2 < n) np2 <<= 1;
+  unsigned long long* k = keys + (size_t)b * key_stride;
+  const bool in_smem = np2 <= 4096;
+  unsigned long long* w = in_smem ? s_keys : k;
+  if (in_smem) {
+    for (int i = threadIdx.x; i < np2; i += blockDim.x) s_keys[i] = i < n ? k[i] : 0ull;
+  } else {
+    for (int i = n + threadIdx.x; i < np2; i += blockDim.x) k[i] = 0ull;  // key_stride is a power of two >= A
+  }
+  __syncthreads();
+  for (int size = 2; size <= np2; size <<= 1) {
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      for (int t = threadIdx.x; t < (np2 >> 1); t += blockDim.x) {
+        const int lo = 2 * t - (t & (stride - 1));
+        const int hi = lo + stride;
+        const bool desc = ((lo & size) == 0);
+        const unsigned long long a = w[lo], c = w[hi];
+        if ((a < c) == desc) { w[lo] = c; w[hi] = a; }
+      }
+      __syncthreads();
+    }
+  }
+  if (in_smem)
+    for (int i = threadIdx.x; i < n; i += blockDim.x) k[i] = s_keys[i];
+}
+
+// ---- gather sorted boxes (+ class offset) -----------------------------------------------------------------------------
+__global__ void nms_gather_kernel(const unsigned long long* __restrict__ keys, int key_stride, const int* __restrict__ count, int A,
+                                  int max_nms, const float* __restrict__ cand_box, const int* __restrict__ cand_cls, int agnostic,
+                                  int rotated, float* __restrict__ sbox, int n_cap) {
+  const int b = blockIdx.y;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int n = min(min(count[b], max_nms), n_cap);
+  if (i >= n) return;
+  const unsigned long long key = keys[(size_t)b * key_stride + i];
+  const int a = (int)(0xFFFFFFFFu - (uint32_t)(key & 0xFFFFFFFFull));
+  const float* src = cand_box + ((size_t)b * A + a) * 5;
+  const float c = agnostic ? 0.f : __fmul_rn((float)cand_cls[(size_t)b * A + a], 7680.0f);
+  float* d = sbox + ((size_t)b * n_cap + i) * 5;
+  d[0] = __fadd_rn(src[0], c); d[1] = __fadd_rn(src[1], c);
+  if (rotated) { d[2] = src[2]; d[3] = src[3]; } else { d[2] = __fadd_rn(src[2], c); d[3] = __fadd_rn(src[3], c); }
+  d[4] = src[4];
+}
+
+// ---- bitmask IoU matrix: mask[i][cb] bit j = IoU(i, cb*64+j) > thr, for j > i (torchvision semantics: strict >) -------
+__device__ __forceinline__ bool iou_gt(const float* a, const float* b, float thr) {
+  const float xx1 = fmaxf(a[0], b[0]), yy1 = fmaxf(a[1], b[1]);
+  const float xx2 = fminf(a[2], b[2]), yy2 = fminf(a[3], b[3]);
+  const float w = fmaxf(0.f, __fsub_rn(xx2, xx1)), h = fmaxf(0.f, __fsub_rn(yy2, yy1));
+  const float inter = __fmul_rn(w, h);
+  const float aa = __fmul_rn(__fsub_rn(a[2], a[0]), __fsub_rn(a[3], a[1]));
+  const float ab = __fmul_rn(__fsub_rn(b[2], b[0]), __fsub_rn(b[3], b[1]));
+  const float ovr = __fdiv_rn(inter, __fsub_rn(__fadd_rn(aa, ab), inter));
+  return ovr > thr;
+}
+
+__device__ __forceinline__ void cov_abc(const float* o, float* a, float* b, float* c) {
+  const float ga = o[2] * o[2] / 12.f, gb = o[3] * o[3] / 12.f;
+  const float cs = cosf(o[4]), sn = sinf(o[4]);
+  const float c2 = cs * cs, s2 = sn * sn;
+  *a = ga * c2 + gb * s2;
+  *b = ga * s2 + gb * c2;
+  *c = (ga - gb) * cs * sn;
+}
+
+__device__ __forceinline__ float probiou(const float* o1, const float* o2) {
+  const float eps = 1e-7f;
+  float a1, b1, c1, a2, b2, c2;
+  cov_abc(o1, &a1, &b1, &c1);
+  cov_abc(o2, &a2, &b2, &c2);
+  const float dx = o1[0] - o2[0], dy = o1[1] - o2[1];
+  const float den = (a1 + a2) * (b1 + b2) - (c1 + c2) * (c1 + c2);
+  const float t1 = (((a1 + a2) * dy * dy + (b1 + b2) * dx * dx) / (den + eps)) * 0.25f;
+  const float t2 = (((c1 + c2) * (-dx) * dy) / (den + eps)) * 0.5f;
+  const float d1 = fmaxf(a1 * b1 - c1 * c1, 0.f), d2 = fmaxf(a2 * b2 - c2 * c2, 0.f);
+  const float t3 = logf(den / (4.f * sqrtf(d1 * d2) + eps) + eps) * 0.5f;
+  const float bd = fminf(fmaxf(t1 + t2 + t3, eps), 100.f);
+  const float hd = sqrtf(1.f - expf(-bd) + eps);
+  return 1.f - hd;
+}
+
+__global__ void __launch_bounds__(64) nms_mask_kernel(const float* __restrict__ sbox, const int* __restrict__ count, int max_nms, int n_cap,
+                                                      int words, float thr, unsigned long long* __restrict__ mask, int rotated) {
+  const int b = blockIdx.z;
+  const int n = min(min(count[b], max_nms), n_cap);
+  const int rb = blockIdx.y, cb = blockIdx.x;
+  if (cb < rb || rb * 64 >= n || cb * 64 >= n) return;
+  __shared__ float s_col[64][5];
+  const int cj = cb * 64 + threadIdx.x;
+  if (cj < n) {
+#pragma unroll
+    for (int k = 0; k < 5; ++k) s_col[threadIdx.x][k] = sbox[((size_t)b * n_cap + cj) * 5 + k];
+  }
+  __syncthreads();
+  const int i = rb * 64 + threadIdx.x;
+  if (i >= n) return;
+  float me[5];
+#pragma unroll
+  for (int k = 0; k < 5; ++k) me[k] = sbox[((size_t)b * n_cap + i) * 5 + k];
+  const int ncol = min(64, n - cb * 64);
+  unsigned long long bits = 0ull;
+  const int start = (rb == cb) ? threadIdx.x + 1 : 0;
+  for (int j = start; j < ncol; ++j) {
+    const bool sup = rotated ? (probiou(me, s_col[j]) >= thr) : iou_gt(me, s_col[j], thr);
+    if (sup) bits |= 1ull << j;
+  }
+  mask[((size_t)b * n_cap + i) * words + cb] = bits;
+}
+
+// ---- sweep + output.  HBB: greedy (a suppressed box does not suppress).  Rotated: Fast-NMS (every higher box suppresses).
+// Writes det_out rows in source-frame pixels (scale_boxes + clip) or letterboxed pixels (scale == 0).
+__global__ void __launch_bounds__(512) nms_sweep_kernel(const unsigned long long* __restrict__ mask, const float* __restrict__ sbox,
+                                                        const unsigned long long* __restrict__ keys, int key_stride,
+                                                        const int* __restrict__ count, int max_nms, int n_cap, int words, int A,
+                                                        const float* __restrict__ cand_box, const float* __restrict__ cand_conf,
+                                                        const int* __restrict__ cand_cls, int rotated, int max_det, int scale,
+                                                        float pad_x, float pad_y, float gain, float fw, float fh, float* __restrict__ det_out,
+                                                        int* __restrict__ det_count, int* __restrict__ det_keep, int* __restrict__ overflow) {
+  extern __shared__ unsigned long long s_removed[];  // [words]
+  __shared__ int s_kept[64];
+  __shared__ int s_nk, s_total;
+  const int b = blockIdx.x;
+  const int ntrue = min(count[b], max_nms);
+  if (ntrue > n_cap) {
+    if (threadIdx.x == 0) { overflow[b] = 1; det_count[b] = 0; }
+    return;
+  }
+  const int n = ntrue;
+  const int w_used = (n + 63) >> 6;
+  for (int i = threadIdx.x; i < w_used; i += blockDim.x) s_removed[i] = 0ull;
+  if (threadIdx.x == 0) s_total = 0;
+  __syncthreads();
+  const int row = rotated ? 7 : 6;
+  for (int chunk = 0; chunk < w_used; ++chunk) {
+    if (s_total >= max_det) break;
+    if (threadIdx.x == 0) {
+      unsigned long long rem = s_removed[chunk];
+      int nk = 0;
+      const int lim = min(64, n - chunk * 64);
+      for (int j = 0; j < lim; ++j) {
+        if (!((rem >> j) & 1ull)) {
+          if (s_total + nk < max_det) s_kept[nk++] = chunk * 64 + j;
+          if (!rotated) rem |= mask[((size_t)b * n_cap + chunk * 64 + j) * words + chunk];
+        }
+        if (rotated) rem |= mask[((size_t)b * n_cap + chunk * 64 + j) * words + chunk];
+      }
+      s_nk = nk;
+    }
+    __syncthreads();
+    const int nk = s_nk;
+    // propagate suppression to later chunks
+    if (!rotated) {
+      for (int wd = chunk + 1 + threadIdx.x; wd < w_used; wd += blockDim.x) {
+        unsigned long long acc = 0ull;
+        for (int k = 0; k < nk; ++k) acc |= mask[((size_t)b * n_cap + s_kept[k]) * words + wd];
+        s_removed[wd] |= acc;
+      }
+    } else {
+      const int lim = min(64, n - chunk * 64);
+      for (int wd = chunk + 1 + threadIdx.x; wd < w_used; wd += blockDim.x) {
+        unsigned long long acc = 0ull;
+        for (int j = 0; j < lim; ++j) acc |= mask[((size_t)b * n_cap + chunk * 64 + j) * words + wd];
+        s_removed[wd] |= acc;
+      }
+    }
+    // emit kept rows of this chunk
+    for (int k = threadIdx.x; k < nk; k += blockDim.x) {
+      const int si = s_kept[k];
+      const unsigned long long key = keys[(size_t)b * key_stride + si];
+      const int a = (int)(0xFFFFFFFFu - (uint32_t)(key & 0xFFFFFFFFull));
+      const float* bx = cand_box + ((size_t)b * A + a) * 5;
+      float* o = det_out + ((size_t)b * max_det + s_total + k) * row;
+      const float cf = cand_conf[(size_t)b * A + a];
+      const float cl = (float)cand_cls[(size_t)b * A + a];
+      if (!rotated) {
+        float x1 = bx[0], y1 = bx[1], x2 = bx[2], y2 = bx[3];
+        if (scale) {
+          x1 = __fdiv_rn(__fsub_rn(x1, pad_x), gain); y1 = __fdiv_rn(__fsub_rn(y1, pad_y), gain);
+          x2 = __fdiv_rn(__fsub_rn(x2, pad_x), gain); y2 = __fdiv_rn(__fsub_rn(y2, pad_y), gain);
+          x1 = fminf(fmaxf(x1, 0.f), fw); x2 = fminf(fmaxf(x2, 0.f), fw);
+          y1 = fminf(fmaxf(y1, 0.f), fh); y2 = fminf(fmaxf(y2, 0.f), fh);
+        }
+        o[0] = x1; o[1] = y1; o[2] = x2; o[3] = y2; o[4] = cf; o[5] = cl;
+      } else {
+        float x = bx[0], y = bx[1], w = bx[2], h = bx[3], t = bx[4];
+        if (scale) {
+          const float PI = 3.14159265358979323846f;
+          float tm = fmodf(t, PI);
+          if (tm < 0.f) tm += PI;
+          const bool swap = tm >= PI * 0.5f;  // regularize_rboxes
+          const float w2 = swap ? h : w, h2 = swap ? w : h;
+          float t2 = fmodf(t, PI * 0.5f);
+          if (t2 < 0.f) t2 += PI * 0.5f;
+          x = __fdiv_rn(__fsub_rn(x, pad_x), gain); y = __fdiv_rn(__fsub_rn(y, pad_y), gain);
+          w = __fdiv_rn(w2, gain); h = __fdiv_rn(h2, gain); t = t2;
+        }
+        o[0] = x; o[1] = y; o[2] = w; o[3] = h; o[4] = t; o[5] = cf; o[6] = cl;
+      }
+      det_keep[(size_t)b * max_det + s_total + k] = a;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) s_total += nk;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) det_count[b] = s_total;
+}
+
+int nms_run(gt_engine* e, const float* pred_dev, int B, int A, int nc, int rotated, float conf, float iou, int agnostic,
+            uint32_t classes_mask, int max_det, bool scale_to_frame, cudaStream_t st) {
+  // pred_dev == nullptr: candidates come from the raw head (decode_filter); else from decoded predictions.
+  const int key_stride = e->cand_cap;
+  GT_CHECK(e, A <= e->A, "nms: A=%d exceeds engine anchors %d", A, e->A);
+  GT_CHECK(e, max_det <= e->cfg.max_det, "nms: max_det %d exceeds configured %d", max_det, e->cfg.max_det);
+  GT_CUDA(e, cudaMemsetAsync(e->cand_count, 0, sizeof(int) * B, st));
+  const long long total = (long long)B * A;
+  if (pred_dev) {
+    pred_filter_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(pred_dev, B, A, nc, rotated, conf, classes_mask, e->cand_box,
+                                                                        e->cand_conf, e->cand_cls, e->cand_key, key_stride, e->cand_count);
+  } else {
+    DecodeGeom g;
+    for (int i = 0; i < 3; ++i) { g.lvl_w[i] = e->lvl_w[i]; g.lvl_h[i] = e->lvl_h[i]; g.lvl_off[i] = e->lvl_off[i]; g.stride[i] = (float)(8 << i); }
+    decode_filter_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(e->raw_head, B, A, e->no, nc, rotated, g, conf, classes_mask,
+                                                                          e->cand_box, e->cand_conf, e->cand_cls, e->cand_key, key_stride,
+                                                                          e->cand_count);
+  }
+  e->launches++;
+  sort_keys_kernel<<<B, 1024, 4096 * sizeof(unsigned long long), st>>>(e->cand_key, key_stride, e->cand_count);
+  e->launches++;
+  const int max_nms = e->cfg.max_nms;
+  // pass 1: batched, capacity nms_cap per image
+  int* overflow = e->det_keep + (size_t)e->cfg.max_batch * e->cfg.max_det;  // [max_batch] tail of det_keep
+  GT_CUDA(e, cudaMemsetAsync(overflow, 0, sizeof(int) * B, st));
+  auto run_pass = [&](int b0, int nb, int n_cap) -> int {
+    const int words = (n_cap + 63) / 64;
+    float* sb = reinterpret_cast<float*>(e->nms_mask + (size_t)nb * n_cap * words);  // sorted boxes live after the mask
+    dim3 gg((unsigned)((n_cap + 255) / 256), (unsigned)nb);
+    nms_gather_kernel<<<gg, 256, 0, st>>>(e->cand_key + (size_t)b0 * key_stride, key_stride, e->cand_count + b0, A, max_nms,
+                                          e->cand_box + (size_t)b0 * A * 5, e->cand_cls + (size_t)b0 * A, agnostic, rotated, sb, n_cap);
+    dim3 gm((unsigned)words, (unsigned)words, (unsigned)nb);
+    nms_mask_kernel<<<gm, 64, 0, st>>>(sb, e->cand_count + b0, max_nms, n_cap, words, iou, e->nms_mask, rotated);
+    const float fw = (float)e->cfg.frame_w, fh = (float)e->cfg.frame_h;
+    nms_sweep_kernel<<<nb, 512, words * sizeof(unsigned long long), st>>>(
+        e->nms_mask, sb, e->cand_key + (size_t)b0 * key_stride, key_stride, e->cand_count + b0, max_nms, n_cap, words, A,
+        e->cand_box + (size_t)b0 * A * 5, e->cand_conf + (size_t)b0 * A, e->cand_cls + (size_t)b0 * A, rotated, max_det,
+        scale_to_frame ? 1 : 0, (float)e->pad_left, (float)e->pad_top, e->gain, fw, fh,
+        e->det_out + (size_t)b0 * max_det * (rotated ? 7 : 6), e->det_count + b0, e->det_keep + (size_t)b0 * max_det, overflow + b0);
+    e->launches += 3;
+    GT_CUDA(e, cudaGetLastError());
+    return GT_OK;
+  };
+  GT_TRY(run_pass(0, B, e->nms_cap));
+  // pass 2 (rare): images with more than nms_cap candidates, one at a time with the full max_nms capacity
+  std::vector<int> ov(B);
+  GT_CUDA(e, cudaMemcpyAsync(ov.data(), overflow, sizeof(int) * B, cudaMemcpyDeviceToHost, st));
+  GT_CUDA(e, cudaStreamSynchronize(st));
+  for (int b = 0; b < B; ++b)
+    if (ov[b]) GT_TRY(run_pass(b, 1, ((max_nms + 63) / 64) * 64));
+  return GT_OK;
+}
+
+// =====================================================================================================================
+// Network plan
+// =====================================================================================================================
+namespace {
+
+struct Builder {
+  gt_engine* e;
+  int B;
+  std::map<std::string, int> idx;
+  int rc = GT_OK;
+
+  View alloc(int C, int H, int W) {
+    View v;
+    bf16* p = nullptr;
+    if (e->dev_alloc((void**)&p, (size_t)B * H * W * C * sizeof(bf16)) != GT_OK) rc = GT_ERR_NOMEM;
+    v.ptr = p; v.C = C; v.ctot = C; v.coff = 0; v.H = H; v.W = W;
+    return v;
+  }
+  int find(const std::string& name) {
+    auto it = idx.find(name);
+    if (it == idx.end()) { gt_set_error(e, "plan: unknown conv %s", name.c_str()); rc = GT_ERR_INVALID; return 0; }
+    return it->second;
+  }
+  // bf16 conv writing a channel slice
+  void conv(std::vector<std::string> names, const View& in, const View& out, const View* res = nullptr, const View* up = nullptr) {
+    if (rc != GT_OK) return;
+    ConvOp op;
+    int cout = 0;
+    op.n_src = (int)names.size();
+    for (int i = 0; i < op.n_src; ++i) { op.src[i] = find(names[i]); cout += e->conv_descs[op.src[i]].cout; }
+    const gt_conv_desc& d = e->conv_descs[op.src[0]];
+    rc = conv_tc_plan(e, &op, in, B, d.cin, cout, d.k, d.stride, d.act, &out, nullptr, 0, 0, 0, res, up);
+    if (rc != GT_OK) return;
+    e->conv_ops.push_back(op);
+    PlanOp po; po.type = OP_CONV; po.conv = (int)e->conv_ops.size() - 1;
+    e->plan.push_back(po);
+  }
+  // final head conv writing fp32 raw rows
+  void conv_raw(const std::string& name, const View& in, int lvl_off, int coff) {
+    if (rc != GT_OK) return;
+    ConvOp op;
+    op.n_src = 1; op.src[0] = find(name);
+    const gt_conv_desc& d = e->conv_descs[op.src[0]];
+    rc = conv_tc_plan(e, &op, in, B, d.cin, d.cout, d.k, d.stride, d.act, nullptr, e->raw_head + (size_t)lvl_off * e->no, e->A, e->no, coff,
+                      nullptr, nullptr);
+    if (rc != GT_OK) return;
+    e->conv_ops.push_back(op);
+    PlanOp po; po.type = OP_CONV; po.conv = (int)e->conv_ops.size() - 1;
+    e->plan.push_back(po);
+  }
+  void c2f(const std::string& pre, const View& in, int c2, int n, bool shortcut, const View& out, const View* up = nullptr) {
+    const int c = c2 / 2;
+    View cat = alloc((2 + n) * c, in.H, in.W);
+    View tmp = alloc(c, in.H, in.W);
+    conv({pre + ".cv1"}, in, cat.slice(0, 2 * c));
+    for (int i = 0; i < n; ++i) {
+      View src = cat.slice(c * (1 + i), c);
+      conv({pre + ".m." + std::to_string(i) + ".cv1"}, src, tmp);
+      View dst = cat.slice(c * (2 + i), c);
+      conv({pre + ".m." + std::to_string(i) + ".cv2"}, tmp, dst, shortcut ? &src : nullptr);
+    }
+    conv({pre + ".cv2"}, cat, out, nullptr, up);
+  }
+};
+
+void add_desc(gt_engine* e, const std::string& name, int cin, int cout, int k, int s, int act) {
+  gt_conv_desc d;
+  memset(&d, 0, sizeof(d));
+  snprintf(d.name, sizeof(d.name), "%s", name.c_str());
+  d.cin = cin; d.cout = cout; d.k = k; d.stride = s; d.act = act;
+  e->conv_descs.push_back(d);
+}
+void add_c2f_desc(gt_engine* e, const std::string& pre, int c1, int c2, int n) {
+  const int c = c2 / 2;
+  add_desc(e, pre + ".cv1", c1, 2 * c, 1, 1, 1);
+  add_desc(e, pre + ".cv2", (2 + n) * c, c2, 1, 1, 1);
+  for (int i = 0; i < n; ++i) {
+    add_desc(e, pre + ".m." + std::to_string(i) + ".cv1", c, c, 3, 1, 1);
+    add_desc(e, pre + ".m." + std::to_string(i) + ".cv2", c, c, 3, 1, 1);
+  }
+}
+
+}  // namespace
+
+int detector_build(gt_engine* e) {
+  const int B = e->cfg.max_batch, nc = e->cfg.nc;
+  const bool obb = e->cfg.task == GT_TASK_OBB;
+  const int c1 = 32, c2 = 64, c3 = 128, c4 = 256, c5 = 512;  // YOLOv8 s-scale widths
+  // canonical conv list (ultralytics module order)
+  add_desc(e, "model.0", 3, c1, 3, 2, 1);
+  add_desc(e, "model.1", c1, c2, 3, 2, 1);
+  add_c2f_desc(e, "model.2", c2, c2, 1);
+  add_desc(e, "model.3", c2, c3, 3, 2, 1);
+  add_c2f_desc(e, "model.4", c3, c3, 2);
+  add_desc(e, "model.5", c3, c4, 3, 2, 1);
+  add_c2f_desc(e, "model.6", c4, c4, 2);
+  add_desc(e, "model.7", c4, c5, 3, 2, 1);
+  add_c2f_desc(e, "model.8", c5, c5, 1);
+  add_desc(e, "model.9.cv1", c5, c5 / 2, 1, 1, 1);
+  add_desc(e, "model.9.cv2", c5 * 2, c5, 1, 1, 1);
+  add_c2f_desc(e, "model.12", c5 + c4, c4, 1);
+  add_c2f_desc(e, "model.15", c4 + c3, c3, 1);
+  add_desc(e, "model.16", c3, c3, 3, 2, 1);
+  add_c2f_desc(e, "model.18", c3 + c4, c4, 1);
+  add_desc(e, "model.19", c4, c4, 3, 2, 1);
+  add_c2f_desc(e, "model.21", c4 + c5, c5, 1);
+  const int ch[3] = {c3, c4, c5};
+  const int hc2 = 64, hc3 = std::max(c3, std::min(nc, 100)), hc4 = std::max(c3 / 4, 1);
+  for (int i = 0; i < 3; ++i) {
+    const std::string p = "model.22.cv2." + std::to_string(i);
+    add_desc(e, p + ".0", ch[i], hc2, 3, 1, 1);
+    add_desc(e, p + ".1", hc2, hc2, 3, 1, 1);
+    add_desc(e, p + ".2", hc2, 64, 1, 1, 0);
+  }
+  for (int i = 0; i < 3; ++i) {
+    const std::string p = "model.22.cv3." + std::to_string(i);
+    add_desc(e, p + ".0", ch[i], hc3, 3, 1, 1);
+    add_desc(e, p + ".1", hc3, hc3, 3, 1, 1);
+    add_desc(e, p + ".2", hc3, nc, 1, 1, 0);
+  }
+  if (obb)
+    for (int i = 0; i < 3; ++i) {
+      const std::string p = "model.22.cv4." + std::to_string(i);
+      add_desc(e, p + ".0", ch[i], hc4, 3, 1, 1);
+      add_desc(e, p + ".1", hc4, hc4, 3, 1, 1);
+      add_desc(e, p + ".2", hc4, 1, 1, 1, 0);
+    }
+
+  Builder bl;
+  bl.e = e; bl.B = B;
+  for (size_t i = 0; i < e->conv_descs.size(); ++i) bl.idx[e->conv_descs[i].name] = (int)i;
+
+  const int H = e->net_h, W = e->net_w;
+  const int H1 = H / 2, W1 = W / 2, H2 = H / 4, W2 = W / 4, H3 = H / 8, W3 = W / 8, H4 = H / 16, W4 = W / 16, H5 = H / 32, W5 = W / 32;
+  e->lvl_h[0] = H3; e->lvl_w[0] = W3; e->lvl_h[1] = H4; e->lvl_w[1] = W4; e->lvl_h[2] = H5; e->lvl_w[2] = W5;
+  e->lvl_off[0] = 0; e->lvl_off[1] = H3 * W3; e->lvl_off[2] = H3 * W3 + H4 * W4;
+  e->A = H3 * W3 + H4 * W4 + H5 * W5;
+  e->no = 64 + nc + (obb ? 1 : 0);
+  GT_TRY(e->dev_alloc((void**)&e->raw_head, (size_t)B * e->A * e->no * sizeof(float)));
+  GT_TRY(e->dev_alloc((void**)&e->conv0_w, 27 * 32 * sizeof(float)));
+  GT_TRY(e->dev_alloc((void**)&e->conv0_b, 32 * sizeof(float)));
+
+  View T0 = bl.alloc(c1, H1, W1);
+  e->conv0_out = T0;
+  { PlanOp po; po.type = OP_CONV0; e->plan.push_back(po); }
+  View T1 = bl.alloc(c2, H2, W2);
+  bl.conv({"model.1"}, T0, T1);
+  View T2 = bl.alloc(c2, H2, W2);
+  bl.c2f("model.2", T1, c2, 1, true, T2);
+  View T3 = bl.alloc(c3, H3, W3);
+  bl.conv({"model.3"}, T2, T3);
+  View cat14 = bl.alloc(c4 + c3, H3, W3);   // [up(12) | 4]
+  View L4 = cat14.slice(c4, c3);
+  bl.c2f("model.4", T3, c3, 2, true, L4);
+  View T5 = bl.alloc(c4, H4, W4);
+  bl.conv({"model.5"}, L4, T5);
+  View cat11 = bl.alloc(c5 + c4, H4, W4);   // [up(9) | 6]
+  View L6 = cat11.slice(c5, c4);
+  bl.c2f("model.6", T5, c4, 2, true, L6);
+  View T7 = bl.alloc(c5, H5, W5);
+  bl.conv({"model.7"}, L6, T7);
+  View T8 = bl.alloc(c5, H5, W5);
+  bl.c2f("model.8", T7, c5, 1, true, T8);
+  // SPPF
+  View s9 = bl.alloc(c5 * 2, H5, W5);
+  bl.conv({"model.9.cv1"}, T8, s9.slice(0, c5 / 2));
+  for (int i = 0; i < 3; ++i) {
+    PlanOp po; po.type = OP_MAXPOOL;
+    po.pool.in = s9.slice(i * (c5 / 2), c5 / 2);
+    po.pool.out = s9.slice((i + 1) * (c5 / 2), c5 / 2);
+    e->plan.push_back(po);
+  }
+  View cat20 = bl.alloc(c4 + c5, H5, W5);   // [19 | 9]
+  View L9 = cat20.slice(c4, c5);
+  View up9 = cat11.slice(0, c5);
+  bl.conv({"model.9.cv2"}, s9, L9, nullptr, &up9);
+  View cat17 = bl.alloc(c3 + c4, H4, W4);   // [16 | 12]
+  View L12 = cat17.slice(c3, c4);
+  View up12 = cat14.slice(0, c4);
+  bl.c2f("model.12", cat11, c4, 1, false, L12, &up12);
+  View P3 = bl.alloc(c3, H3, W3);
+  bl.c2f("model.15", cat14, c3, 1, false, P3);
+  bl.conv({"model.16"}, P3, cat17.slice(0, c3));
+  View P4 = bl.alloc(c4, H4, W4);
+  bl.c2f("model.18", cat17, c4, 1, false, P4);
+  bl.conv({"model.19"}, P4, cat20.slice(0, c4));
+  View P5 = bl.alloc(c5, H5, W5);
+  bl.c2f("model.21", cat20, c5, 1, false, P5);
+  // head
+  const View feats[3] = {P3, P4, P5};
+  for (int i = 0; i < 3; ++i) {
+    const std::string s = std::to_string(i);
+    const int ha = hc2 + hc3 + (obb ? hc4 : 0);
+    View a = bl.alloc(ha, feats[i].H, feats[i].W);
+    std::vector<std::string> first = {"model.22.cv2." + s + ".0", "model.22.cv3." + s + ".0"};
+    if (obb) first.push_back("model.22.cv4." + s + ".0");
+    bl.conv(first, feats[i], a);
+    View b2 = bl.alloc(hc2, feats[i].H, feats[i].W), b3 = bl.alloc(hc3, feats[i].H, feats[i].W);
+    bl.conv({"model.22.cv2." + s + ".1"}, a.slice(0, hc2), b2);
+    bl.conv({"model.22.cv3." + s + ".1"}, a.slice(hc2, hc3), b3);
+    bl.conv_raw("model.22.cv2." + s + ".2", b2, e->lvl_off[i], 0);
+    bl.conv_raw("model.22.cv3." + s + ".2", b3, e->lvl_off[i], 64);
+    if (obb) {
+      View b4 = bl.alloc(hc4, feats[i].H, feats[i].W);
+      bl.conv({"model.22.cv4." + s + ".1"}, a.slice(hc2 + hc3, hc4), b4);
+      bl.conv_raw("model.22.cv4." + s + ".2", b4, e->lvl_off[i], 64 + nc);
+    }
+  }
+  if (bl.rc != GT_OK) return bl.rc;
+  e->feat_views[0] = T0; e->feat_views[1] = T1; e->feat_views[2] = T2; e->feat_views[3] = T3; e->feat_views[4] = L4;
+  e->feat_views[5] = T5; e->feat_views[6] = L6; e->feat_views[7] = T7; e->feat_views[8] = T8; e->feat_views[9] = L9;
+  e->feat_views[12] = L12; e->feat_views[15] = P3; e->feat_views[16] = cat17.slice(0, c3); e->feat_views[18] = P4;
+  e->feat_views[19] = cat20.slice(0, c4); e->feat_views[21] = P5;
+
+  e->conv_flops = 2.0 * H1 * W1 * 32.0 * 27.0;
+  for (const ConvOp& op : e->conv_ops) e->conv_flops += op.flops;
+
+  // decode / NMS workspaces
+  int cap = 1;
+  while (cap < e->A) cap <<= 1;
+  e->cand_cap = cap;
+  GT_TRY(e->dev_alloc((void**)&e->cand_box, (size_t)B * e->A * 5 * sizeof(float)));
+  GT_TRY(e->dev_alloc((void**)&e->cand_conf, (size_t)B * e->A * sizeof(float)));
+  GT_TRY(e->dev_alloc((void**)&e->cand_cls, (size_t)B * e->A * sizeof(int)));
+  GT_TRY(e->dev_alloc((void**)&e->cand_key, (size_t)B * cap * sizeof(unsigned long long)));
+  GT_TRY(e->dev_alloc((void**)&e->cand_count, (size_t)B * sizeof(int)));
+  e->nms_cap = 4096;
+  const size_t big_cap = (size_t)((e->cfg.max_nms + 63) / 64) * 64;
+  const size_t batched = (size_t)B * e->nms_cap * (e->nms_cap / 64) * 8 + (size_t)B * e->nms_cap * 5 * 4;
+  const size_t single = big_cap * (big_cap / 64) * 8 + big_cap * 5 * 4;
+  GT_TRY(e->dev_alloc((void**)&e->nms_mask, std::max(batched, single)));
+  GT_TRY(e->dev_alloc((void**)&e->det_out, (size_t)B * e->cfg.max_det * 7 * sizeof(float)));
+  GT_TRY(e->dev_alloc((void**)&e->det_count, (size_t)B * sizeof(int)));
+  GT_TRY(e->dev_alloc((void**)&e->det_keep, ((size_t)B * e->cfg.max_det + B) * sizeof(int)));
+  return GT_OK;
+}
+
+int detector_load_weights(gt_engine* e, const float* const* w, const float* const* b, int n) {
+  GT_CHECK(e, n == (int)e->conv_descs.size(), "load_weights: expected %d convs, got %d", (int)e->conv_descs.size(), n);
+  // layer 0: [32][3][3][3] -> [27][32]
+  {
+    std::vector<float> hw(27 * 32);
+    for (int co = 0; co < 32; ++co)
+      for (int k = 0; k < 27; ++k) hw[k * 32 + co] = w[0][co * 27 + k];
+    GT_CUDA(e, cudaMemcpy(e->conv0_w, hw.data(), hw.size() * sizeof(float), cudaMemcpyHostToDevice));
+    GT_CUDA(e, cudaMemcpy(e->conv0_b, b[0], 32 * sizeof(float), cudaMemcpyHostToDevice));
+  }
+  for (ConvOp& op : e->conv_ops) {
+    const float* ws[3];
+    const float* bs[3];
+    int couts[3];
+    for (int i = 0; i < op.n_src; ++i) { ws[i] = w[op.src[i]]; bs[i] = b[op.src[i]]; couts[i] = e->conv_descs[op.src[i]].cout; }
+    GT_TRY(conv_tc_pack_weights(e, &op, ws, bs, couts, op.n_src));
+  }
+  e->weights_loaded = true;
+  return GT_OK;
+}
+
+int detector_forward(gt_engine* e, int B, cudaStream_t st) {
+  GT_CHECK(e, e->weights_loaded, "detect: weights not loaded");
+  for (const PlanOp& po : e->plan) {
+    if (po.type == OP_CONV0) {
+      const View& o = e->conv0_out;
+      dim3 grid((unsigned)ceil_div(o.W, 32), (unsigned)ceil_div(o.H, 8), (unsigned)B);
+      conv0_kernel<<<grid, 256, 0, st>>>(e->net_in, o.ptr, e->conv0_w, e->conv0_b, e->net_h, e->net_w, o.H, o.W);
+      e->launches++;
+    } else if (po.type == OP_CONV) {
+      GT_TRY(conv_tc_launch(e, &e->conv_ops[po.conv], B, st));
+    } else {
+      const View& i = po.pool.in;
+      const View& o = po.pool.out;
+      const long long total = (long long)B * i.H * i.W * (i.C / 8);
+      maxpool5_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(i.ptr, i.ctot, i.coff, o.ptr, o.ctot, o.coff, B, i.H, i.W, i.C);
+      e->launches++;
+    }
+  }
+  GT_CUDA(e, cudaGetLastError());
+  return GT_OK;
+}
+
+int detector_postprocess(gt_engine* e, int B, float conf, float iou, int agnostic, uint32_t classes_mask, cudaStream_t st) {
+  return nms_run(e, nullptr, B, e->A, e->cfg.nc, e->cfg.task == GT_TASK_OBB, conf, iou, agnostic, classes_mask, e->cfg.max_det, true, st);
+}

@@ -1,0 +1,148 @@
+// Engine state behind the opaque gt_handle.
+#pragma once
+#include "common.cuh"
+
+struct MaxpoolOp { View in, out; };  // 5x5 stride-1 max pool (SPPF chain)
+struct UpsampleOp { View in, out; }; // 2x nearest (only used when not fused in a conv epilogue)
+
+enum OpType { OP_CONV0 = 0, OP_CONV = 1, OP_MAXPOOL = 2 };
+struct PlanOp {
+  OpType type;
+  int conv = -1;      // index into conv_ops
+  MaxpoolOp pool;
+};
+
+// ORB per-level geometry
+struct OrbLevel {
+  int w, h;
+  size_t off;         // byte offset of this level inside one frame's pyramid slab
+  float scale;        // 1.2^level (float, as OpenCV's getScale)
+  int quota_cur, quota_ref;
+  int cand_cap;       // FAST candidate capacity
+  size_t cand_off;    // element offset inside one frame's candidate slab
+};
+
+#define GT_ORB_LEVELS 8
+#define GT_MAX_KP 8192      // per-frame keypoint capacity (>= max_features * ref_multiplier)
+
+struct OrbSet {             // one frame's final features (device pointers into slabs)
+  float* kp = nullptr;      // [GT_MAX_KP][6] x,y,size,angle,response,octave
+  uint8_t* desc = nullptr;  // [GT_MAX_KP][32]
+  int* count = nullptr;     // [1]
+};
+
+struct gt_engine {
+  gt_config cfg;
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  std::string err;
+  int64_t launches = 0;
+  std::vector<void*> dev_allocs;
+  std::vector<void*> host_allocs;
+
+  // geometry
+  int net_h = 0, net_w = 0, new_h = 0, new_w = 0, pad_top = 0, pad_left = 0;
+  float gain = 1.f;
+  int work_h = 0, work_w = 0;
+  int A = 0, no = 0;                    // anchors, raw head row width
+  int lvl_h[3], lvl_w[3], lvl_off[3];
+
+  // staging + stage 1
+  uint8_t* frames_dev = nullptr;        // [B][H][W][3]
+  uint8_t* frames_pinned = nullptr;
+  bf16* net_in = nullptr;               // [B][3][net_h][net_w] planar RGB/255
+  const uint8_t* cur_frames = nullptr;  // device pointer of the frames of the last gt_preprocess
+
+  // detector
+  bool weights_loaded = false;
+  std::vector<gt_conv_desc> conv_descs;             // canonical list
+  std::vector<ConvOp> conv_ops;                     // fused tcgen05 ops
+  std::vector<PlanOp> plan;
+  float* conv0_w = nullptr;                         // [27][32] f32
+  float* conv0_b = nullptr;                         // [32]
+  View conv0_out;
+  View feat_views[23];
+  float* raw_head = nullptr;                        // [B][A][no]
+  // decode + NMS workspaces
+  int cand_cap = 0;                                 // candidates per image
+  float* cand_box = nullptr;                        // [B][cand_cap][5] x1,y1,x2,y2 (or x,y,w,h) + angle
+  unsigned long long* cand_key = nullptr;           // [B][cand_cap_pow2] sort keys
+  float* cand_conf = nullptr;
+  int* cand_cls = nullptr;
+  int* cand_anchor = nullptr;
+  int* cand_count = nullptr;                        // [B]
+  unsigned long long* nms_mask = nullptr;
+  int nms_cap = 0;
+  float* det_out = nullptr;                         // [B][max_det][7]
+  int* det_count = nullptr;                         // [B]
+  int* det_keep = nullptr;                          // [B][max_det]
+  float* pred_tmp = nullptr; size_t pred_tmp_bytes = 0;
+
+  // stage 3
+  OrbLevel lv[GT_ORB_LEVELS];
+  size_t pyr_bytes = 0;                             // one frame's pyramid slab
+  size_t cand_total = 0;
+  uint8_t* pyr = nullptr;                           // [B+1][pyr_bytes]  (slot B = reference)
+  uint8_t* pyr_mask = nullptr;                      // same geometry
+  uint8_t* pyr_blur = nullptr;                      // blurred copy
+  unsigned int* fast_cand = nullptr;                // [B+1][cand_total] packed (y<<16|x)
+  uint8_t* fast_score = nullptr;                    // [B+1][cand_total]
+  int* fast_count = nullptr;                        // [B+1][8]
+  unsigned int* sel_xy = nullptr;                   // [B+1][8][sel_cap]
+  float* sel_resp = nullptr;
+  int* sel_count = nullptr;                         // [B+1][8]
+  int sel_cap = 0;
+  float* kp_all = nullptr;                          // [B+1][GT_MAX_KP][6]
+  uint8_t* desc_all = nullptr;                      // [B+1][GT_MAX_KP][32]
+  int* kp_count = nullptr;                          // [B+1]
+  int* lvl_kp_off = nullptr;                        // [B+1][9]
+  float* boxes_dev = nullptr;                       // [B+1][max_det][4]
+  int* nboxes_dev = nullptr;                        // [B+1]
+  bool have_ref = false;
+  OrbLevel* lv_dev = nullptr;                       // device copy of lv[]
+  int* rs_tab[GT_ORB_LEVELS][4] = {};               // per-level resize tables: xofs, xc1, yofs, yc1
+  // matching / RANSAC
+  int* match_idx = nullptr;                         // [B][GT_MAX_KP][2]
+  int* match_dist = nullptr;                        // [B][GT_MAX_KP][2]
+  float* pairs = nullptr;                           // [B][GT_MAX_KP][4] cur x,y, ref x,y (working res)
+  int* pair_count = nullptr;                        // [B]
+  float* npairs = nullptr;                          // [B][GT_MAX_KP][4] Hartley-normalised pairs
+  float* norms = nullptr;                           // [B][8] normalisation parameters
+  float* hyp_score = nullptr;                       // [B][max_iter]
+  double* H_dev = nullptr;                          // [B][9]
+  int* H_status = nullptr;                          // [B]
+  int* H_stats = nullptr;                           // [B][4]
+  float* boxes_stab_dev = nullptr;                  // [B][max_det][4]
+
+  // timing
+  cudaEvent_t ev[8];
+  float stage_ms[4] = {0, 0, 0, 0};
+  float conv_ms = 0;
+  double conv_flops = 0;
+
+  int dev_alloc(void** p, size_t bytes);
+  int host_alloc(void** p, size_t bytes);
+};
+
+// detector.cu
+int detector_build(gt_engine* e);
+int detector_load_weights(gt_engine* e, const float* const* w, const float* const* b, int n);
+int detector_fill_pad(gt_engine* e, cudaStream_t st);
+int detector_preprocess(gt_engine* e, const uint8_t* frames_dev, int B, cudaStream_t st);
+int detector_forward(gt_engine* e, int B, cudaStream_t st);
+int detector_postprocess(gt_engine* e, int B, float conf, float iou, int agnostic, uint32_t classes_mask, cudaStream_t st);
+int nms_run(gt_engine* e, const float* pred_dev, int B, int A, int nc, int rotated, float conf, float iou, int agnostic,
+            uint32_t classes_mask, int max_det, bool scale_to_frame, cudaStream_t st);
+
+// orb.cu
+int orb_build(gt_engine* e);
+int orb_run(gt_engine* e, int slot0, int nslots, bool as_reference, bool build_mask, cudaStream_t st);
+// match_ransac.cu
+int stab_build(gt_engine* e);
+int stab_match_and_fit(gt_engine* e, int B, cudaStream_t st);
+int match_run(gt_engine* e, const uint8_t* q, const int* nq_dev, int nq_max, const uint8_t* t, const int* nt_dev, int nt_max,
+              int* out_idx, int* out_dist, int batch, size_t q_stride, size_t out_stride, cudaStream_t st);
+int homography_run(gt_engine* e, const float* pairs, const int* counts, int B, int pair_stride, float thr, int max_iter,
+                   double* out_H, int* out_status, int* out_stats, float ratio, bool full_res, const int* kp_count, cudaStream_t st);
+int warp_boxes_run(gt_engine* e, const double* H_dev, const int* status_dev, const float* in, float* out, const int* counts, int B,
+                   int stride, cudaStream_t st);

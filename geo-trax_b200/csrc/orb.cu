@@ -1,0 +1,579 @@
+// Stage 3a: ORB key points + rBRIEF descriptors on the half-resolution gray frame (batched over frames).
+//
+// Restates cv2.ORB_create(nfeatures).detectAndCompute(gray, mask) as stabilo calls it
+// (/root/reference/geotrax/extract.py:177,181 -> stabilo.Stabilizer; OpenCV defaults scaleFactor 1.2, nlevels 8,
+// edgeThreshold 31, HARRIS_SCORE, patchSize 31, fastThreshold 20 -- SURVEY.md 8a-10, Appendix A-3).  Every integer stage
+// is bit-exact with OpenCV 4.13 (chained INTER_LINEAR_EXACT pyramid, FAST-9/16 score + 3x3 NMS, mask / border filter,
+// "retain best" with ties kept); the float stages follow OpenCV's operation order (Harris 7x7, intensity-centroid angle
+// with fastAtan2, float32 separable 7x7 sigma-2 blur, rotated 256-pair test pattern recovered by probing cv2).
+#include <cmath>
+
+#include "engine.cuh"
+
+namespace {
+
+constexpr int kFastThr = 20;
+constexpr int kEdge = 31;
+constexpr int kSelCap = 8192;   // per (frame, level) candidates surviving the FAST-score cut
+constexpr int kLvlKeep = 2048;  // per (frame, level) final key points
+
+
+__constant__ int c_umax[16] = {15, 15, 15, 15, 14, 14, 14, 13, 13, 12, 11, 10, 9, 8, 6, 3};
+__constant__ float c_gauss[7] = {0.07015932351350784f, 0.13107487559318542f, 0.1907128244638443f, 0.21610593795776367f,
+                                 0.1907128244638443f, 0.13107487559318542f, 0.07015932351350784f};
+__device__ const signed char d_pattern[256][4] = {
+#include "orb_pattern.inc"
+};
+
+// ---- mask level 0 from boxes (xywh, source-frame pixels): rect grown by margin, scaled, floor/ceil, clipped ---------------
+__global__ void mask_rects_kernel(uint8_t* __restrict__ mask, size_t slab, const float* __restrict__ boxes, const int* __restrict__ nboxes,
+                                  int max_det, int slot0, int w, int h, float margin, float ratio) {
+  const int slot = slot0 + blockIdx.y;
+  const int n = nboxes[slot];
+  const int i = blockIdx.x;
+  if (i >= n) return;
+  const float* b = boxes + ((size_t)slot * max_det + i) * 4;
+  const double gw = (double)b[2] * (1.0 + (double)margin), gh = (double)b[3] * (1.0 + (double)margin);
+  int x0 = (int)floor(((double)b[0] - gw / 2) * (double)ratio), y0 = (int)floor(((double)b[1] - gh / 2) * (double)ratio);
+  int x1 = (int)ceil(((double)b[0] + gw / 2) * (double)ratio), y1 = (int)ceil(((double)b[1] + gh / 2) * (double)ratio);
+  x0 = min(max(x0, 0), w); x1 = min(max(x1, 0), w); y0 = min(max(y0, 0), h); y1 = min(max(y1, 0), h);
+  uint8_t* m = mask + (size_t)slot * slab;
+  const int rw = x1 - x0;
+  for (int y = y0 + (int)(threadIdx.x / 32); y < y1; y += blockDim.x / 32)
+    for (int x = threadIdx.x % 32; x < rw; x += 32) m[(size_t)y * w + x0 + x] = 0;
+}
+
+// ---- one pyramid level from the previous one: cv2.resize(INTER_LINEAR_EXACT) in Q8.8 x Q8.8, (v + 2^15) >> 16 -------------
+// blockIdx.z = slot * 2 + plane (0 image, 1 mask; the mask is thresholded: <= 254 -> 0)
+__global__ void __launch_bounds__(256) pyr_resize_kernel(uint8_t* __restrict__ img, uint8_t* __restrict__ msk, size_t slab, int slot0,
+                                                         size_t src_off, int sw, int sh, size_t dst_off, int dw, int dh,
+                                                         const int* __restrict__ xofs, const int* __restrict__ xc1,
+                                                         const int* __restrict__ yofs, const int* __restrict__ yc1) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x;
+  const int y = blockIdx.y;
+  if (x >= dw) return;
+  const int slot = slot0 + (blockIdx.z >> 1);
+  const bool is_mask = blockIdx.z & 1;
+  uint8_t* base = (is_mask ? msk : img) + (size_t)slot * slab;
+  const uint8_t* s = base + src_off;
+  const int xo = xofs[x], cx1 = xc1[x], cx0 = 256 - cx1, xo1 = min(xo + 1, sw - 1);
+  const int yo = yofs[y], cy1 = yc1[y], cy0 = 256 - cy1, yo1 = min(yo + 1, sh - 1);
+  const uint8_t* r0 = s + (size_t)yo * sw;
+  const uint8_t* r1 = s + (size_t)yo1 * sw;
+  const int h0 = r0[xo] * cx0 + r0[xo1] * cx1;
+  const int h1 = r1[xo] * cx0 + r1[xo1] * cx1;
+  int v = (h0 * cy0 + h1 * cy1 + 32768) >> 16;
+  if (is_mask && v <= 254) v = 0;
+  base[dst_off + (size_t)y * dw + x] = (uint8_t)v;
+}
+
+// ---- FAST-9/16 score + 3x3 non-max suppression + mask / border filter -> candidate list ------------------------------------
+#define FT_X 64
+#define FT_Y 16
+__device__ __forceinline__ int fast_score(const uint8_t (*t)[FT_X + 8], int x, int y) {
+  // t is the smem image tile; (x, y) tile coordinates of the centre (>= 3 from the tile edge)
+  const int v = t[y][x];
+  int d[16];
+  d[0] = v - t[y + 3][x];      d[1] = v - t[y + 3][x + 1];  d[2] = v - t[y + 2][x + 2];  d[3] = v - t[y + 1][x + 3];
+  d[4] = v - t[y][x + 3];      d[5] = v - t[y - 1][x + 3];  d[6] = v - t[y - 2][x + 2];  d[7] = v - t[y - 3][x + 1];
+  d[8] = v - t[y - 3][x];      d[9] = v - t[y - 3][x - 1];  d[10] = v - t[y - 2][x - 2]; d[11] = v - t[y - 1][x - 3];
+  d[12] = v - t[y][x - 3];     d[13] = v - t[y + 1][x - 3]; d[14] = v - t[y + 2][x - 2]; d[15] = v - t[y + 3][x - 1];
+  unsigned dark = 0, bright = 0;  // d > thr : ring pixel darker than centre;  d < -thr : brighter
+#pragma unroll
+  for (int k = 0; k < 16; ++k) {
+    dark |= (unsigned)(d[k] > kFastThr) << k;
+    bright |= (unsigned)(d[k] < -kFastThr) << k;
+  }
+  auto run9 = [](unsigned m) {
+    m |= m << 16;  // circular
+    unsigned a = m & (m >> 1);
+    a = a & (a >> 2);
+    a = a & (a >> 4);       // runs of 8
+    a = a & (m >> 8);       // runs of 9
+    return (a & 0xFFFFu) != 0;
+  };
+  if (!run9(dark) && !run9(bright)) return 0;
+  // exact corner score: the largest threshold for which the pixel is still a corner
+  int best = 0;
+#pragma unroll
+  for (int k = 0; k < 16; ++k) {
+    int mn = d[k], mx = d[k];
+#pragma unroll
+    for (int j = 1; j < 9; ++j) {
+      const int e = d[(k + j) & 15];
+      mn = min(mn, e);
+      mx = max(mx, e);
+    }
+    best = max(best, max(mn, -mx));
+  }
+  return best - 1;
+}
+
+__global__ void __launch_bounds__(256) fast_kernel(const uint8_t* __restrict__ img, const uint8_t* __restrict__ msk, size_t slab, int slot0,
+                                                   size_t lvl_off, int w, int h, unsigned int* __restrict__ cand, uint8_t* __restrict__ cscore,
+                                                   size_t cand_slab, size_t cand_off, int cand_cap, int* __restrict__ counts, int level) {
+  __shared__ uint8_t s_img[FT_Y + 8][FT_X + 8];
+  __shared__ uint8_t s_sc[FT_Y + 2][FT_X + 2];
+  __shared__ int s_n, s_base;
+  __shared__ unsigned int s_xy[FT_X * FT_Y / 4];
+  __shared__ uint8_t s_s[FT_X * FT_Y / 4];
+  const int slot = slot0 + blockIdx.z;
+  const uint8_t* im = img + (size_t)slot * slab + lvl_off;
+  const int x0 = blockIdx.x * FT_X, y0 = blockIdx.y * FT_Y;
+  if (threadIdx.x == 0) s_n = 0;
+  for (int i = threadIdx.x; i < (FT_Y + 8) * (FT_X + 8); i += 256) {
+    const int ty = i / (FT_X + 8), tx = i - ty * (FT_X + 8);
+    const int gx = x0 - 4 + tx, gy = y0 - 4 + ty;
+    s_img[ty][tx] = (gx >= 0 && gx < w && gy >= 0 && gy < h) ? im[(size_t)gy * w + gx] : 0;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < (FT_Y + 2) * (FT_X + 2); i += 256) {
+    const int sy = i / (FT_X + 2), sx = i - sy * (FT_X + 2);
+    const int gx = x0 - 1 + sx, gy = y0 - 1 + sy;
+    int sc = 0;
+    if (gx >= 3 && gx < w - 3 && gy >= 3 && gy < h - 3) sc = fast_score(s_img, sx + 3, sy + 3);
+    s_sc[sy][sx] = (uint8_t)sc;
+  }
+  __syncthreads();
+  const uint8_t* mk = msk + (size_t)slot * slab + lvl_off;
+  for (int i = threadIdx.x; i < FT_X * FT_Y; i += 256) {
+    const int ly = i / FT_X, lx = i - ly * FT_X;
+    const int gx = x0 + lx, gy = y0 + ly;
+    const int sc = s_sc[ly + 1][lx + 1];
+    if (sc < kFastThr) continue;
+    if (gx < kEdge || gx >= w - kEdge || gy < kEdge || gy >= h - kEdge) continue;
+    if (!(sc > s_sc[ly][lx] && sc > s_sc[ly][lx + 1] && sc > s_sc[ly][lx + 2] && sc > s_sc[ly + 1][lx] && sc > s_sc[ly + 1][lx + 2] &&
+          sc > s_sc[ly + 2][lx] && sc > s_sc[ly + 2][lx + 1] && sc > s_sc[ly + 2][lx + 2]))
+      continue;
+    if (mk[(size_t)gy * w + gx] == 0) continue;
+    const int k = atomicAdd(&s_n, 1);  // NMS guarantees <= 1 survivor per 2x2 block, so k < FT_X*FT_Y/4
+    s_xy[k] = ((unsigned)gy << 16) | (unsigned)gx;
+    s_s[k] = (uint8_t)sc;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0 && s_n) s_base = atomicAdd(&counts[slot * GT_ORB_LEVELS + level], s_n);
+  __syncthreads();
+  for (int k = threadIdx.x; k < s_n; k += 256) {
+    const int dst = s_base + k;
+    if (dst < cand_cap) {
+      cand[(size_t)slot * cand_slab + cand_off + dst] = s_xy[k];
+      cscore[(size_t)slot * cand_slab + cand_off + dst] = s_s[k];
+    }
+  }
+}
+
+// ---- per (frame, level): FAST-score cut (2 x quota, ties kept) -> Harris -> quota cut (ties kept) -> sort by position ------
+__device__ __forceinline__ float harris_at(const uint8_t* im, int w, int x0, int y0) {
+  int a = 0, b = 0, c = 0;
+  for (int dy = -3; dy <= 3; ++dy) {
+    const uint8_t* pm = im + (size_t)(y0 + dy - 1) * w + x0;
+    const uint8_t* p0 = pm + w;
+    const uint8_t* pp = p0 + w;
+    for (int dx = -3; dx <= 3; ++dx) {
+      const int Ix = ((int)p0[dx + 1] - (int)p0[dx - 1]) * 2 + ((int)pm[dx + 1] - (int)pm[dx - 1]) + ((int)pp[dx + 1] - (int)pp[dx - 1]);
+      const int Iy = ((int)pp[dx] - (int)pm[dx]) * 2 + ((int)pp[dx - 1] - (int)pm[dx - 1]) + ((int)pp[dx + 1] - (int)pm[dx + 1]);
+      a += Ix * Ix; b += Iy * Iy; c += Ix * Iy;
+    }
+  }
+  const float scale = 1.0f / (4.0f * 7.0f * 255.0f);
+  const float s2 = __fmul_rn(scale, scale), s4 = __fmul_rn(s2, s2);
+  const float fa = (float)a, fb = (float)b, fc = (float)c;
+  const float ab = __fadd_rn(fa, fb);
+  const float r = __fsub_rn(__fsub_rn(__fmul_rn(fa, fb), __fmul_rn(fc, fc)), __fmul_rn(__fmul_rn(0.04f, ab), ab));
+  return __fmul_rn(r, s4);
+}
+
+__device__ __forceinline__ unsigned f2key(float f) {  // order-preserving float -> uint
+  const unsigned u = __float_as_uint(f);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+
+__global__ void __launch_bounds__(1024) orb_select_kernel(const uint8_t* __restrict__ img, size_t slab, int slot0, const OrbLevel* __restrict__ lv,
+                                                          const unsigned int* __restrict__ cand, const uint8_t* __restrict__ cscore,
+                                                          size_t cand_slab, const int* __restrict__ fast_count, int as_ref,
+                                                          unsigned int* __restrict__ sel_xy, float* __restrict__ sel_resp,
+                                                          int* __restrict__ sel_count) {
+  extern __shared__ unsigned char s_raw[];
+  unsigned* s_keys = reinterpret_cast<unsigned*>(s_raw);                           // [kSelCap] response keys
+  unsigned long long* s_sort = reinterpret_cast<unsigned long long*>(s_raw);       // [kLvlKeep] aliases s_keys after the cut
+  __shared__ int s_hist[256];
+  __shared__ int s_cut, s_m, s_k, s_need;
+  __shared__ unsigned s_prefix;
+  const int level = blockIdx.x, slot = slot0 + blockIdx.y;
+  const OrbLevel L = lv[level];
+  const int quota = as_ref ? L.quota_ref : L.quota_cur;
+  const int n = min(fast_count[slot * GT_ORB_LEVELS + level], L.cand_cap);
+  const unsigned int* cxy = cand + (size_t)slot * cand_slab + L.cand_off;
+  const uint8_t* csc = cscore + (size_t)slot * cand_slab + L.cand_off;
+  unsigned int* oxy = sel_xy + ((size_t)slot * GT_ORB_LEVELS + level) * kSelCap;
+  float* orsp = sel_resp + ((size_t)slot * GT_ORB_LEVELS + level) * kSelCap;
+  const uint8_t* im = img + (size_t)slot * slab + L.off;
+
+  // (a) FAST-score histogram and cut: keep score >= score of the (2*quota)-th best
+  for (int i = threadIdx.x; i < 256; i += blockDim.x) s_hist[i] = 0;
+  if (threadIdx.x == 0) { s_m = 0; s_k = 0; }
+  __syncthreads();
+  for (int i = threadIdx.x; i < n; i += blockDim.x) atomicAdd(&s_hist[csc[i]], 1);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int cut = 0;
+    const int want = 2 * quota;
+    if (n > want) {
+      int acc = 0;
+      for (int s = 255; s >= 0; --s) {
+        acc += s_hist[s];
+        if (acc >= want) { cut = s; break; }
+      }
+    }
+    s_cut = cut;
+  }
+  __syncthreads();
+  const int cut = s_cut;
+  // (b) compact survivors + Harris response
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    if (csc[i] >= cut) {
+      const int k = atomicAdd(&s_m, 1);
+      if (k < kSelCap) {
+        const unsigned xy = cxy[i];
+        const float r = harris_at(im, L.w, (int)(xy & 0xFFFF), (int)(xy >> 16));
+        oxy[k] = xy;
+        orsp[k] = r;
+        s_keys[k] = f2key(r);
+      }
+    }
+  }
+  __syncthreads();
+  const int m = min(s_m, kSelCap);
+  // (c) Harris cut: key of the quota-th largest response (MSB-first radix select), ties kept
+  unsigned cutkey = 0;
+  if (m > quota && quota > 0) {
+    if (threadIdx.x == 0) { s_prefix = 0; s_need = quota; }
+    __syncthreads();
+    for (int shift = 24; shift >= 0; shift -= 8) {
+      for (int i = threadIdx.x; i < 256; i += blockDim.x) s_hist[i] = 0;
+      __syncthreads();
+      const unsigned prefix = s_prefix;
+      const unsigned himask = shift == 24 ? 0u : (0xFFFFFFFFu << (shift + 8));
+      for (int i = threadIdx.x; i < m; i += blockDim.x) {
+        const unsigned k = s_keys[i];
+        if ((k & himask) == (prefix & himask)) atomicAdd(&s_hist[(k >> shift) & 0xFF], 1);
+      }
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        int need = s_need, acc = 0;
+        for (int bkt = 255; bkt >= 0; --bkt) {
+          if (acc + s_hist[bkt] >= need) { s_prefix = prefix | ((unsigned)bkt << shift); s_need = need - acc; break; }
+          acc += s_hist[bkt];
+        }
+      }
+      __syncthreads();
+    }
+    cutkey = s_prefix;
+  } else if (quota <= 0) {
+    cutkey = 0xFFFFFFFFu;
+  }
+  // (d) gather the kept ones (position-major key) and sort ascending by (y, x)
+  unsigned long long mine[(kSelCap + 1023) / 1024];
+  int nmine = 0;
+  for (int i = threadIdx.x; i < m; i += blockDim.x)
+    if (s_keys[i] >= cutkey && quota > 0) mine[nmine++] = ((unsigned long long)oxy[i] << 32) | (unsigned long long)__float_as_uint(orsp[i]);
+  __syncthreads();  // s_keys is dead from here on; s_sort aliases it
+  for (int j = 0; j < nmine; ++j) {
+    const int k = atomicAdd(&s_k, 1);
+    if (k < kLvlKeep) s_sort[k] = mine[j];
+  }
+  __syncthreads();
+  const int kept = min(s_k, kLvlKeep);
+  int np2 = 1;
+  while (np2 < kept) np2 <<= 1;
+  for (int i = kept + threadIdx.x; i < np2; i += blockDim.x) s_sort[i] = ~0ull;
+  __syncthreads();
+  for (int size = 2; size <= np2; size <<= 1)
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      for (int t = threadIdx.x; t < (np2 >> 1); t += blockDim.x) {
+        const int lo = 2 * t - (t & (stride - 1)), hi = lo + stride;
+        const bool asc = ((lo & size) == 0);
+        const unsigned long long a = s_sort[lo], c = s_sort[hi];
+        if ((a > c) == asc) { s_sort[lo] = c; s_sort[hi] = a; }
+      }
+      __syncthreads();
+    }
+  for (int i = threadIdx.x; i < kept; i += blockDim.x) {
+    oxy[i] = (unsigned)(s_sort[i] >> 32);
+    orsp[i] = __uint_as_float((unsigned)(s_sort[i] & 0xFFFFFFFFull));
+  }
+  if (threadIdx.x == 0) sel_count[slot * GT_ORB_LEVELS + level] = kept;
+}
+
+// ---- float32 separable 7x7 sigma-2 blur (BORDER_REFLECT_101), as cv2.GaussianBlur does inside ORB ---------------------------
+__device__ __forceinline__ int reflect101(int p, int n) {
+  if (p < 0) p = -p;
+  if (p >= n) p = 2 * n - 2 - p;
+  return p;
+}
+__global__ void __launch_bounds__(256) blur7_kernel(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, size_t slab, int slot0, size_t off,
+                                                    int w, int h) {
+  __shared__ uint8_t s_in[16 + 6][64 + 6];
+  __shared__ float s_h[16 + 6][64];
+  const int slot = slot0 + blockIdx.z;
+  const uint8_t* im = src + (size_t)slot * slab + off;
+  const int x0 = blockIdx.x * 64, y0 = blockIdx.y * 16;
+  for (int i = threadIdx.x; i < 22 * 70; i += 256) {
+    const int ty = i / 70, tx = i - ty * 70;
+    const int gx = reflect101(min(x0 - 3 + tx, w + 2), w), gy = reflect101(min(y0 - 3 + ty, h + 2), h);
+    s_in[ty][tx] = im[(size_t)min(max(gy, 0), h - 1) * w + min(max(gx, 0), w - 1)];
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 22 * 64; i += 256) {
+    const int ty = i / 64, tx = i - ty * 64;
+    float acc = __fmul_rn((float)s_in[ty][tx], c_gauss[0]);
+#pragma unroll
+    for (int k = 1; k < 7; ++k) acc = __fadd_rn(acc, __fmul_rn((float)s_in[ty][tx + k], c_gauss[k]));
+    s_h[ty][tx] = acc;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 16 * 64; i += 256) {
+    const int ty = i / 64, tx = i - ty * 64;
+    const int gx = x0 + tx, gy = y0 + ty;
+    if (gx >= w || gy >= h) continue;
+    float acc = __fmul_rn(s_h[ty][tx], c_gauss[0]);
+#pragma unroll
+    for (int k = 1; k < 7; ++k) acc = __fadd_rn(acc, __fmul_rn(s_h[ty + k][tx], c_gauss[k]));
+    const int v = __float2int_rn(acc);
+    dst[(size_t)slot * slab + off + (size_t)gy * w + gx] = (uint8_t)min(max(v, 0), 255);
+  }
+}
+
+// ---- one warp per key point: intensity-centroid angle, key-point record, 256-bit rotated BRIEF -------------------------------
+__device__ __forceinline__ float fast_atan2_deg(float y, float x) {
+  const float p1 = 0.9997878412794807f * 57.29577951308232f, p3 = -0.3258083974640975f * 57.29577951308232f;
+  const float p5 = 0.1555786518463281f * 57.29577951308232f, p7 = -0.04432655554792128f * 57.29577951308232f;
+  const float ax = fabsf(x), ay = fabsf(y);
+  float a, c, c2;
+  if (ax >= ay) {
+    c = __fdiv_rn(ay, ax + 2.220446049250313e-16f);
+    c2 = __fmul_rn(c, c);
+    a = __fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(p7, c2), p5), c2), p3), c2), p1), c);
+  } else {
+    c = __fdiv_rn(ax, ay + 2.220446049250313e-16f);
+    c2 = __fmul_rn(c, c);
+    a = 90.f - __fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(p7, c2), p5), c2), p3), c2), p1), c);
+  }
+  if (x < 0.f) a = 180.f - a;
+  if (y < 0.f) a = 360.f - a;
+  return a;
+}
+
+__global__ void __launch_bounds__(256) orb_describe_kernel(const uint8_t* __restrict__ img, const uint8_t* __restrict__ blur, size_t slab, int slot0,
+                                                           const OrbLevel* __restrict__ lv, const unsigned int* __restrict__ sel_xy,
+                                                           const float* __restrict__ sel_resp, const int* __restrict__ sel_count,
+                                                           float* __restrict__ kp_all, uint8_t* __restrict__ desc_all, int* __restrict__ kp_count,
+                                                           int* __restrict__ lvl_kp_off) {
+  __shared__ signed char s_pat[256][4];
+  __shared__ int s_off[GT_ORB_LEVELS + 1];
+  const int slot = slot0 + blockIdx.y;
+  for (int i = threadIdx.x; i < 256; i += blockDim.x) {
+    s_pat[i][0] = d_pattern[i][0]; s_pat[i][1] = d_pattern[i][1]; s_pat[i][2] = d_pattern[i][2]; s_pat[i][3] = d_pattern[i][3];
+  }
+  if (threadIdx.x == 0) {
+    int acc = 0;
+    for (int l = 0; l < GT_ORB_LEVELS; ++l) {
+      s_off[l] = acc;
+      acc = min(acc + sel_count[slot * GT_ORB_LEVELS + l], GT_MAX_KP);
+    }
+    s_off[GT_ORB_LEVELS] = acc;
+    if (blockIdx.x == 0) {
+      kp_count[slot] = acc;
+      for (int l = 0; l <= GT_ORB_LEVELS; ++l) lvl_kp_off[slot * (GT_ORB_LEVELS + 1) + l] = s_off[l];
+    }
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int kpi = blockIdx.x * (blockDim.x >> 5) + warp;
+  if (kpi >= s_off[GT_ORB_LEVELS]) return;
+  int level = 0;
+  while (kpi >= s_off[level + 1]) ++level;
+  const int li = kpi - s_off[level];
+  const OrbLevel L = lv[level];
+  const unsigned xy = sel_xy[((size_t)slot * GT_ORB_LEVELS + level) * kSelCap + li];
+  const int x = (int)(xy & 0xFFFF), y = (int)(xy >> 16);
+  const uint8_t* im = img + (size_t)slot * slab + L.off;
+  // intensity centroid over the radius-15 disc: lane = column u
+  int m10 = 0, m01 = 0;
+  if (lane < 31) {
+    const int u = lane - 15, au = abs(u);
+    for (int v = -15; v <= 15; ++v) {
+      if (au <= c_umax[abs(v)]) {
+        const int I = im[(size_t)(y + v) * L.w + x + u];
+        m10 += u * I;
+        m01 += v * I;
+      }
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    m10 += __shfl_xor_sync(0xffffffffu, m10, o);
+    m01 += __shfl_xor_sync(0xffffffffu, m01, o);
+  }
+  const float angle = fast_atan2_deg((float)m01, (float)m10);
+  float* kp = kp_all + ((size_t)slot * GT_MAX_KP + kpi) * 6;
+  if (lane == 0) {
+    kp[0] = __fmul_rn((float)x, L.scale);
+    kp[1] = __fmul_rn((float)y, L.scale);
+    kp[2] = __fmul_rn(31.0f, L.scale);
+    kp[3] = angle;
+    kp[4] = sel_resp[((size_t)slot * GT_ORB_LEVELS + level) * kSelCap + li];
+    kp[5] = (float)level;
+  }
+  // descriptor: lane computes byte `lane` (bits 8*lane .. 8*lane+7)
+  const float ar = __fmul_rn(angle, 0.017453292519943295f);  // (float)(CV_PI/180)
+  const float ca = (float)cos((double)ar), sa = (float)sin((double)ar);
+  const uint8_t* bl = blur + (size_t)slot * slab + L.off;
+  unsigned byte = 0;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const signed char* p = s_pat[lane * 8 + j];
+    const float px = (float)p[0], py = (float)p[1], qx = (float)p[2], qy = (float)p[3];
+    const int ix0 = __float2int_rn(__fsub_rn(__fmul_rn(px, ca), __fmul_rn(py, sa)));
+    const int iy0 = __float2int_rn(__fadd_rn(__fmul_rn(px, sa), __fmul_rn(py, ca)));
+    const int ix1 = __float2int_rn(__fsub_rn(__fmul_rn(qx, ca), __fmul_rn(qy, sa)));
+    const int iy1 = __float2int_rn(__fadd_rn(__fmul_rn(qx, sa), __fmul_rn(qy, ca)));
+    const int t0 = bl[(size_t)(y + iy0) * L.w + x + ix0];
+    const int t1 = bl[(size_t)(y + iy1) * L.w + x + ix1];
+    byte |= (unsigned)(t0 < t1) << j;
+  }
+  desc_all[((size_t)slot * GT_MAX_KP + kpi) * 32 + lane] = (uint8_t)byte;
+}
+
+void resize_tables(int n_src, int n_dst, std::vector<int>& ofs, std::vector<int>& c1) {
+  ofs.resize(n_dst);
+  c1.resize(n_dst);
+  const double scale = (double)n_src / n_dst;
+  for (int d = 0; d < n_dst; ++d) {
+    double f = (d + 0.5) * scale - 0.5;
+    int s = (int)std::floor(f);
+    double fr = f - s;
+    if (s < 0) { s = 0; fr = 0; }
+    if (s >= n_src - 1) { s = n_src - 1; fr = 0; }
+    ofs[d] = s;
+    c1[d] = (int)std::nearbyint(fr * 256.0);
+  }
+}
+
+}  // namespace
+
+int orb_build(gt_engine* e) {
+  const int B = e->cfg.max_batch, S = B + 1;
+  const int nfeat_cur = e->cfg.max_features;
+  const int nfeat_ref = (int)(e->cfg.max_features * e->cfg.ref_multiplier);
+  GT_CHECK(e, nfeat_ref <= GT_MAX_KP && nfeat_cur >= 8, "orb: max_features * ref_multiplier = %d exceeds %d", nfeat_ref, GT_MAX_KP);
+  auto quotas = [](int n, int* out) {
+    const float factor = (float)(1.0 / 1.2);
+    float nd = n * (1 - factor) / (1 - (float)std::pow((double)factor, (double)GT_ORB_LEVELS));
+    int sum = 0;
+    for (int l = 0; l < GT_ORB_LEVELS - 1; ++l) {
+      out[l] = (int)std::nearbyint(nd);
+      sum += out[l];
+      nd *= factor;
+    }
+    out[GT_ORB_LEVELS - 1] = std::max(n - sum, 0);
+  };
+  int qc[GT_ORB_LEVELS], qr[GT_ORB_LEVELS];
+  quotas(nfeat_cur, qc);
+  quotas(nfeat_ref, qr);
+  size_t off = 0, coff = 0;
+  for (int l = 0; l < GT_ORB_LEVELS; ++l) {
+    OrbLevel& L = e->lv[l];
+    L.scale = (float)std::pow(1.2, (double)l);
+    L.w = (int)std::nearbyint((float)e->work_w / L.scale);
+    L.h = (int)std::nearbyint((float)e->work_h / L.scale);
+    L.off = off;
+    off += (((size_t)L.w * L.h) + 255) & ~(size_t)255;
+    L.quota_cur = qc[l]; L.quota_ref = qr[l];
+    GT_CHECK(e, qr[l] <= kLvlKeep, "orb: per-level quota %d exceeds %d", qr[l], kLvlKeep);
+    L.cand_cap = std::max(4096, ((L.w * L.h / 16 + 1023) / 1024) * 1024);
+    L.cand_off = coff;
+    coff += L.cand_cap;
+  }
+  e->pyr_bytes = off;
+  e->cand_total = coff;
+  e->sel_cap = kSelCap;
+  GT_TRY(e->dev_alloc((void**)&e->pyr, (size_t)S * off));
+  GT_TRY(e->dev_alloc((void**)&e->pyr_mask, (size_t)S * off));
+  GT_TRY(e->dev_alloc((void**)&e->pyr_blur, (size_t)S * off));
+  GT_TRY(e->dev_alloc((void**)&e->fast_cand, (size_t)S * coff * sizeof(unsigned)));
+  GT_TRY(e->dev_alloc((void**)&e->fast_score, (size_t)S * coff));
+  GT_TRY(e->dev_alloc((void**)&e->fast_count, (size_t)S * GT_ORB_LEVELS * sizeof(int)));
+  GT_TRY(e->dev_alloc((void**)&e->sel_xy, (size_t)S * GT_ORB_LEVELS * kSelCap * sizeof(unsigned)));
+  GT_TRY(e->dev_alloc((void**)&e->sel_resp, (size_t)S * GT_ORB_LEVELS * kSelCap * sizeof(float)));
+  GT_TRY(e->dev_alloc((void**)&e->sel_count, (size_t)S * GT_ORB_LEVELS * sizeof(int)));
+  GT_TRY(e->dev_alloc((void**)&e->kp_all, (size_t)S * GT_MAX_KP * 6 * sizeof(float)));
+  GT_TRY(e->dev_alloc((void**)&e->desc_all, (size_t)S * GT_MAX_KP * 32));
+  GT_TRY(e->dev_alloc((void**)&e->kp_count, (size_t)S * sizeof(int)));
+  GT_TRY(e->dev_alloc((void**)&e->lvl_kp_off, (size_t)S * (GT_ORB_LEVELS + 1) * sizeof(int)));
+  GT_TRY(e->dev_alloc((void**)&e->boxes_dev, (size_t)S * e->cfg.max_det * 4 * sizeof(float)));
+  GT_TRY(e->dev_alloc((void**)&e->nboxes_dev, (size_t)S * sizeof(int)));
+  GT_CUDA(e, cudaMemset(e->nboxes_dev, 0, (size_t)S * sizeof(int)));
+  GT_CUDA(e, cudaMemset(e->kp_count, 0, (size_t)S * sizeof(int)));
+  GT_CUDA(e, cudaMemset(e->pyr_mask, 255, (size_t)S * off));
+  GT_TRY(e->dev_alloc((void**)&e->lv_dev, sizeof(OrbLevel) * GT_ORB_LEVELS));
+  GT_CUDA(e, cudaMemcpy(e->lv_dev, e->lv, sizeof(OrbLevel) * GT_ORB_LEVELS, cudaMemcpyHostToDevice));
+  for (int l = 1; l < GT_ORB_LEVELS; ++l) {
+    std::vector<int> xo, xc, yo, yc;
+    resize_tables(e->lv[l - 1].w, e->lv[l].w, xo, xc);
+    resize_tables(e->lv[l - 1].h, e->lv[l].h, yo, yc);
+    const std::vector<int>* src[4] = {&xo, &xc, &yo, &yc};
+    for (int k = 0; k < 4; ++k) {
+      GT_TRY(e->dev_alloc((void**)&e->rs_tab[l][k], src[k]->size() * 4));
+      GT_CUDA(e, cudaMemcpy(e->rs_tab[l][k], src[k]->data(), src[k]->size() * 4, cudaMemcpyHostToDevice));
+    }
+  }
+  GT_CUDA(e, cudaFuncSetAttribute(orb_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSelCap * 4));
+  return GT_OK;
+}
+
+int orb_run(gt_engine* e, int slot0, int nslots, bool as_reference, bool build_mask, cudaStream_t st) {
+  const size_t slab = e->pyr_bytes;
+  const OrbLevel& L0 = e->lv[0];
+  if (build_mask) {
+    GT_CUDA(e, cudaMemset2DAsync(e->pyr_mask + (size_t)slot0 * slab, slab, 255, (size_t)L0.w * L0.h, nslots, st));
+    if (e->cfg.mask_use) {
+      dim3 g((unsigned)e->cfg.max_det, (unsigned)nslots);
+      mask_rects_kernel<<<g, 128, 0, st>>>(e->pyr_mask, slab, e->boxes_dev, e->nboxes_dev, e->cfg.max_det, slot0, L0.w, L0.h,
+                                           e->cfg.mask_margin_ratio, e->cfg.downsample_ratio);
+      e->launches++;
+    }
+  }
+  for (int l = 1; l < GT_ORB_LEVELS; ++l) {
+    const OrbLevel& S = e->lv[l - 1];
+    const OrbLevel& D = e->lv[l];
+    int* const* t = e->rs_tab[l];
+    dim3 g((unsigned)ceil_div(D.w, 256), (unsigned)D.h, (unsigned)(nslots * 2));
+    pyr_resize_kernel<<<g, 256, 0, st>>>(e->pyr, e->pyr_mask, slab, slot0, S.off, S.w, S.h, D.off, D.w, D.h, t[0], t[1], t[2], t[3]);
+    e->launches++;
+  }
+  GT_CUDA(e, cudaMemsetAsync(e->fast_count + (size_t)slot0 * GT_ORB_LEVELS, 0, (size_t)nslots * GT_ORB_LEVELS * sizeof(int), st));
+  for (int l = 0; l < GT_ORB_LEVELS; ++l) {
+    const OrbLevel& L = e->lv[l];
+    dim3 g((unsigned)ceil_div(L.w, FT_X), (unsigned)ceil_div(L.h, FT_Y), (unsigned)nslots);
+    fast_kernel<<<g, 256, 0, st>>>(e->pyr, e->pyr_mask, slab, slot0, L.off, L.w, L.h, e->fast_cand, e->fast_score, e->cand_total, L.cand_off,
+                                   L.cand_cap, e->fast_count, l);
+    dim3 gb((unsigned)ceil_div(L.w, 64), (unsigned)ceil_div(L.h, 16), (unsigned)nslots);
+    blur7_kernel<<<gb, 256, 0, st>>>(e->pyr, e->pyr_blur, slab, slot0, L.off, L.w, L.h);
+    e->launches += 2;
+  }
+  {
+    dim3 g(GT_ORB_LEVELS, (unsigned)nslots);
+    orb_select_kernel<<<g, 1024, kSelCap * 4, st>>>(e->pyr, slab, slot0, e->lv_dev, e->fast_cand, e->fast_score, e->cand_total, e->fast_count,
+                                                    as_reference ? 1 : 0, e->sel_xy, e->sel_resp, e->sel_count);
+    e->launches++;
+  }
+  {
+    dim3 g((unsigned)(GT_MAX_KP / 8), (unsigned)nslots);  // one warp per key point; warps past the count exit
+    orb_describe_kernel<<<g, 256, 0, st>>>(e->pyr, e->pyr_blur, slab, slot0, e->lv_dev, e->sel_xy, e->sel_resp, e->sel_count, e->kp_all,
+                                           e->desc_all, e->kp_count, e->lvl_kp_off);
+    e->launches++;
+  }
+  GT_CUDA(e, cudaGetLastError());
+  return GT_OK;
+}

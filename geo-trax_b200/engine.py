@@ -1,0 +1,271 @@
+"""Thin Python owner of one gt_handle (one per GPU).  numpy / torch buffers in, numpy out; all compute is in the .so."""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, Optional, Sequence, Tuple
+
+import numpy as np
+
+from . import _lib
+from ._lib import GT_MAX_KP, GT_ORB_LEVELS, GtError, gt_config, gt_conv_desc
+
+
+def _ptr(a) -> int:
+    """Address of a numpy array or a torch tensor (host or CUDA); None -> 0."""
+    if a is None:
+        return 0
+    if isinstance(a, np.ndarray):
+        assert a.flags["C_CONTIGUOUS"], "buffer must be C-contiguous"
+        return a.ctypes.data
+    if hasattr(a, "data_ptr"):
+        assert a.is_contiguous(), "tensor must be contiguous"
+        return a.data_ptr()
+    raise TypeError(type(a))
+
+
+def classes_to_mask(classes: Optional[Sequence[int]]) -> int:
+    if classes is None:
+        return 0
+    m = 0
+    for c in classes:
+        m |= 1 << int(c)
+    return m
+
+
+class Engine:
+    """One B200's worth of the extract hot path: preprocess -> detect -> stabilize -> warp."""
+
+    def __init__(self, frame_hw: Tuple[int, int] = (2160, 3840), imgsz: int = 1920, nc: int = 4, task: str = "detect", max_batch: int = 16,
+                 device: int = 0, max_det: int = 1000, **stab):
+        self.lib = _lib.load_library()
+        cfg = gt_config()
+        self.lib.gt_default_config(C.byref(cfg))
+        cfg.frame_h, cfg.frame_w, cfg.imgsz, cfg.nc, cfg.max_batch, cfg.max_det = frame_hw[0], frame_hw[1], imgsz, nc, max_batch, max_det
+        cfg.task = _lib.GT_TASK_OBB if task == "obb" else _lib.GT_TASK_DETECT
+        for k, v in stab.items():
+            if not hasattr(cfg, k):
+                raise GtError(f"unknown engine option {k}")
+            setattr(cfg, k, v)
+        self.cfg = cfg
+        self.task = task
+        self.h = C.c_void_p()
+        rc = self.lib.gt_create(C.byref(cfg), device, C.byref(self.h))
+        if rc != 0:
+            raise GtError(f"gt_create failed ({rc}): {self.lib.gt_last_error(None).decode()}")
+        self.max_batch, self.max_det, self.nc = max_batch, max_det, nc
+        self.row = 7 if task == "obb" else 6
+        A, no = C.c_int32(), C.c_int32()
+        self._ck(self.lib.gt_get_raw_head(self.h, 0, None, C.byref(A), C.byref(no)))
+        self.A, self.no = A.value, no.value
+        nh, nw = C.c_int32(), C.c_int32()
+        self._ck(self.lib.gt_get_net_input(self.h, 0, None, C.byref(nh), C.byref(nw)))
+        self.net_h, self.net_w = nh.value, nw.value
+        self._ck(self.lib.gt_get_gray(self.h, 0, None, C.byref(nh), C.byref(nw)))
+        self.work_h, self.work_w = nh.value, nw.value
+        self._keep = []
+
+    # -- plumbing --------------------------------------------------------------------------------------------------------
+    def _ck(self, rc: int):
+        if rc < 0:
+            raise GtError(f"geotrax_b200 error {rc}: {self.lib.gt_last_error(self.h).decode()}")
+        return rc
+
+    def close(self):
+        if getattr(self, "h", None) and self.h.value:
+            self.lib.gt_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- weights -----------------------------------------------------------------------------------------------------------
+    def conv_descs(self):
+        n = self._ck(self.lib.gt_conv_count(self.h))
+        out = []
+        for i in range(n):
+            d = gt_conv_desc()
+            self._ck(self.lib.gt_conv_info(self.h, i, C.byref(d)))
+            out.append((d.name.decode(), d.cin, d.cout, d.k, d.stride, d.act))
+        return out
+
+    def load_weights(self, folded: Dict[str, Tuple[np.ndarray, np.ndarray]]):
+        descs = self.conv_descs()
+        n = len(descs)
+        W, Bv = (C.c_void_p * n)(), (C.c_void_p * n)()
+        keep = []
+        for i, (name, cin, cout, k, s, act) in enumerate(descs):
+            w, b = folded[name]
+            w = np.ascontiguousarray(w, dtype=np.float32)
+            b = np.ascontiguousarray(b, dtype=np.float32)
+            assert w.shape == (cout, cin, k, k) and b.shape == (cout,), f"{name}: {w.shape} {b.shape}"
+            keep += [w, b]
+            W[i], Bv[i] = w.ctypes.data, b.ctypes.data
+        self._ck(self.lib.gt_load_weights(self.h, W, Bv, n))
+
+    # -- stages ------------------------------------------------------------------------------------------------------------
+    def preprocess(self, frames, stream=None):
+        B = int(frames.shape[0])
+        self._ck(self.lib.gt_preprocess(self.h, _ptr(frames), B, stream))
+        return B
+
+    def net_input(self, B: int) -> np.ndarray:
+        out = np.empty((B, 3, self.net_h, self.net_w), np.uint16)
+        self._ck(self.lib.gt_get_net_input(self.h, B, out.ctypes.data, None, None))
+        return out
+
+    def gray(self, B: int) -> np.ndarray:
+        out = np.empty((B, self.work_h, self.work_w), np.uint8)
+        self._ck(self.lib.gt_get_gray(self.h, B, out.ctypes.data, None, None))
+        return out
+
+    def detect(self, B: int, conf=0.25, iou=0.7, agnostic=True, classes=None, want_keep=False, stream=None):
+        boxes = np.zeros((B, self.max_det, self.row), np.float32)
+        counts = np.zeros((B,), np.int32)
+        keep = np.zeros((B, self.max_det), np.int32) if want_keep else None
+        self._ck(self.lib.gt_detect(self.h, B, conf, iou, int(bool(agnostic)), classes_to_mask(classes), boxes.ctypes.data, counts.ctypes.data,
+                                    _ptr(keep), stream))
+        return (boxes, counts, keep) if want_keep else (boxes, counts)
+
+    def raw_head(self, B: int) -> np.ndarray:
+        out = np.empty((B, self.A, self.no), np.float32)
+        self._ck(self.lib.gt_get_raw_head(self.h, B, out.ctypes.data, None, None))
+        return out
+
+    def feature(self, layer: int, B: int) -> np.ndarray:
+        c, h, w = C.c_int32(), C.c_int32(), C.c_int32()
+        self._ck(self.lib.gt_get_feature(self.h, layer, 0, None, C.byref(c), C.byref(h), C.byref(w)))
+        out = np.empty((B, h.value, w.value, c.value), np.uint16)
+        self._ck(self.lib.gt_get_feature(self.h, layer, B, out.ctypes.data, None, None, None))
+        return out
+
+    def nms(self, pred: np.ndarray, nc: int, rotated=False, conf=0.25, iou=0.7, agnostic=True, classes=None, max_det=None):
+        pred = np.ascontiguousarray(pred, dtype=np.float32)
+        B, A = pred.shape[0], pred.shape[1]
+        md = max_det or self.max_det
+        row = 7 if rotated else 6
+        rows = np.zeros((B, md, row), np.float32)
+        counts = np.zeros((B,), np.int32)
+        keep = np.zeros((B, md), np.int32)
+        self._ck(self.lib.gt_nms(self.h, pred.ctypes.data, B, A, nc, int(rotated), conf, iou, int(bool(agnostic)), classes_to_mask(classes), md,
+                                 rows.ctypes.data, counts.ctypes.data, keep.ctypes.data, None))
+        return rows, counts, keep
+
+    def conv2d(self, x_bf16: np.ndarray, w: np.ndarray, bias: Optional[np.ndarray], k: int, stride: int, act: bool,
+               residual: Optional[np.ndarray] = None, out_f32: bool = False) -> np.ndarray:
+        B, H, W, cin = x_bf16.shape
+        cout = w.shape[0]
+        pad = k // 2
+        Ho, Wo = (H + 2 * pad - k) // stride + 1, (W + 2 * pad - k) // stride + 1
+        out = np.empty((B, Ho, Wo, cout), np.float32 if out_f32 else np.uint16)
+        w = np.ascontiguousarray(w, np.float32)
+        b = None if bias is None else np.ascontiguousarray(bias, np.float32)
+        self._ck(self.lib.gt_conv2d(self.h, _ptr(np.ascontiguousarray(x_bf16)), B, H, W, cin, w.ctypes.data, _ptr(b), cout, k, stride, int(act),
+                                    _ptr(residual), out.ctypes.data, int(out_f32), None))
+        return out
+
+    # -- stabilizer --------------------------------------------------------------------------------------------------------
+    def set_reference(self, slot: int, boxes: Optional[np.ndarray] = None):
+        n = 0 if boxes is None else len(boxes)
+        b = None if n == 0 else np.ascontiguousarray(boxes, np.float32)
+        self._ck(self.lib.gt_set_reference(self.h, slot, _ptr(b), n, None))
+
+    def stabilize(self, B: int, boxes: Optional[Sequence[Optional[np.ndarray]]] = None):
+        md = self.max_det
+        bx = np.zeros((B, md, 4), np.float32)
+        nb = np.zeros((B,), np.int32)
+        if boxes is not None:
+            for i, b in enumerate(boxes):
+                if b is not None and len(b):
+                    nb[i] = min(len(b), md)
+                    bx[i, : nb[i]] = np.asarray(b, np.float32)[: nb[i]]
+        H = np.zeros((B, 9), np.float64)
+        status = np.zeros((B,), np.int32)
+        stats = np.zeros((B, 4), np.int32)
+        self._ck(self.lib.gt_stabilize(self.h, B, bx.ctypes.data, nb.ctypes.data, md, H.ctypes.data, status.ctypes.data, stats.ctypes.data, None))
+        return H.reshape(B, 3, 3), status, stats
+
+    def warp_boxes(self, H: np.ndarray, boxes_xywh: np.ndarray) -> np.ndarray:
+        b = np.ascontiguousarray(boxes_xywh, np.float32).copy()
+        Hc = np.ascontiguousarray(H, np.float64)
+        self._ck(self.lib.gt_warp_boxes(self.h, Hc.ctypes.data, b.ctypes.data, len(b), None))
+        return b
+
+    def orb_level_info(self):
+        out = []
+        for l in range(GT_ORB_LEVELS):
+            w, h, qc, qr = C.c_int32(), C.c_int32(), C.c_int32(), C.c_int32()
+            self._ck(self.lib.gt_orb_level_info(self.h, l, C.byref(w), C.byref(h), C.byref(qc), C.byref(qr)))
+            out.append((w.value, h.value, qc.value, qr.value))
+        return out
+
+    def pyramid_level(self, which: int, b: int, level: int):
+        w, h, _, _ = self.orb_level_info()[level]
+        img, msk = np.empty((h, w), np.uint8), np.empty((h, w), np.uint8)
+        self._ck(self.lib.gt_get_pyramid_level(self.h, which, b, level, img.ctypes.data, msk.ctypes.data))
+        return img, msk
+
+    def keypoints(self, which: int, b: int):
+        kp = np.zeros((GT_MAX_KP, 6), np.float32)
+        desc = np.zeros((GT_MAX_KP, 32), np.uint8)
+        n = C.c_int32()
+        self._ck(self.lib.gt_get_keypoints(self.h, which, b, GT_MAX_KP, kp.ctypes.data, desc.ctypes.data, C.byref(n)))
+        return kp[: n.value].copy(), desc[: n.value].copy()
+
+    def orb_detect(self, gray: np.ndarray, mask: Optional[np.ndarray] = None, as_reference=False):
+        gray = np.ascontiguousarray(gray, np.uint8)
+        if gray.ndim == 2:
+            gray = gray[None]
+        if mask is not None:
+            mask = np.ascontiguousarray(mask, np.uint8)
+        self._ck(self.lib.gt_orb_detect(self.h, gray.ctypes.data, _ptr(mask), gray.shape[0], int(as_reference), None))
+
+    def match(self, query: np.ndarray, train: np.ndarray):
+        q, t = np.ascontiguousarray(query, np.uint8), np.ascontiguousarray(train, np.uint8)
+        idx = np.zeros((len(q), 2), np.int32)
+        dist = np.zeros((len(q), 2), np.int32)
+        self._ck(self.lib.gt_match(self.h, q.ctypes.data, len(q), t.ctypes.data, len(t), idx.ctypes.data, dist.ctypes.data, None))
+        return idx, dist
+
+    def find_homography(self, src: np.ndarray, dst: np.ndarray, thr=2.0, max_iter=5000):
+        s, d = np.ascontiguousarray(src, np.float32), np.ascontiguousarray(dst, np.float32)
+        H = np.zeros(9, np.float64)
+        inl = C.c_int32()
+        rc = self._ck(self.lib.gt_find_homography(self.h, s.ctypes.data, d.ctypes.data, len(s), thr, max_iter, H.ctypes.data, C.byref(inl), None))
+        return (None if rc != 0 else H.reshape(3, 3)), inl.value
+
+    # -- fused batch -------------------------------------------------------------------------------------------------------
+    def alloc_outputs(self, pinned=False):
+        """Output buffers for extract_batch (optionally pinned torch tensors for async D2H)."""
+        B, md = self.max_batch, self.max_det
+        shapes = dict(boxes=((B, md, self.row), np.float32), counts=((B,), np.int32), boxes_stab=((B, md, 4), np.float32),
+                      H=((B, 9), np.float64), status=((B,), np.int32), stats=((B, 4), np.int32))
+        if pinned:
+            import torch
+            tmap = {np.float32: torch.float32, np.int32: torch.int32, np.float64: torch.float64}
+            self._keep = [torch.zeros(s, dtype=tmap[d]).pin_memory() for s, d in shapes.values()]
+            return {k: t.numpy() for k, t in zip(shapes, self._keep)}
+        return {k: np.zeros(s, d) for k, (s, d) in shapes.items()}
+
+    def extract_batch(self, frames, first_is_reference=False, conf=0.25, iou=0.7, agnostic=True, classes=None, out=None, stream=None):
+        B = int(frames.shape[0])
+        o = out or self.alloc_outputs()
+        self._ck(self.lib.gt_extract_batch(self.h, _ptr(frames), B, int(first_is_reference), conf, iou, int(bool(agnostic)), classes_to_mask(classes),
+                                           o["boxes"].ctypes.data, o["counts"].ctypes.data, o["boxes_stab"].ctypes.data, o["H"].ctypes.data,
+                                           o["status"].ctypes.data, o["stats"].ctypes.data, stream))
+        return o
+
+    def stage_times(self):
+        ms = (C.c_float * 4)()
+        self._ck(self.lib.gt_stage_times(self.h, ms))
+        return dict(preprocess=ms[0], inference=ms[1], postprocess=ms[2], stabilize=ms[3])
+
+    def launch_count(self) -> int:
+        return int(self.lib.gt_launch_count(self.h))
+
+    def conv_stack_stats(self):
+        ms, fl = C.c_float(), C.c_double()
+        self._ck(self.lib.gt_conv_stack_stats(self.h, C.byref(ms), C.byref(fl)))
+        return ms.value, fl.value

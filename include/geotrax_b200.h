@@ -1,0 +1,166 @@
+/*
+ * geotrax_b200.h -- C-ABI of the B200-native geo-trax extraction hot path.
+ *
+ * Drop-in boundary for the per-frame loop of /root/reference/geotrax/extract.py:134-214.  The reference reaches
+ * this arithmetic through two Python objects:
+ *     ultralytics.YOLO(...).track(frame, **cfg)            extract.py:153, 217-236
+ *     stabilo.Stabilizer(**cfg).set_ref_frame/stabilize/   extract.py:139, 177-187; utils/registration.py:59-85
+ *         transform_cur_boxes/get_cur_trans_matrix
+ * The Python shims in geo-trax_b200/ keep those two surfaces and call the entry points below through ctypes.
+ *
+ * Conventions: extern "C"; every call returns 0 on success or a negative gt_status; no exceptions cross the
+ * boundary; gt_last_error() gives the text.  Pointers are plain caller-owned buffers.  Unless a parameter is
+ * documented "device", it may be either a host pointer or a CUDA device pointer (detected with
+ * cudaPointerGetAttributes); host inputs are staged through the library's own pinned ring.  `stream` is a
+ * cudaStream_t passed as void* (NULL = the handle's own stream).  One handle per GPU; a handle is not
+ * thread-safe; calls on one handle are serialised on its stream.  The library owns all device workspaces.
+ */
+#ifndef GEOTRAX_B200_H_
+#define GEOTRAX_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GT_ABI_VERSION 1
+
+typedef struct gt_engine* gt_handle;
+
+typedef enum {
+  GT_OK = 0,
+  GT_ERR_INVALID = -1,  /* bad argument / unsupported configuration            */
+  GT_ERR_CUDA = -2,     /* a CUDA runtime / driver call failed                 */
+  GT_ERR_STATE = -3,    /* call order violated (e.g. detect before weights)    */
+  GT_ERR_NOMEM = -4
+} gt_status;
+
+enum { GT_TASK_DETECT = 0, GT_TASK_OBB = 1 };
+
+/* Mirrors the YAML keys the reference splats into the two objects:
+ *   ultralytics: block  /root/reference/geotrax/cfg/default.yaml:229-250  (imgsz, conf, iou, max_det, classes, agnostic_nms)
+ *   stabilo: block      /root/reference/geotrax/cfg/default.yaml:103-145                                               */
+typedef struct gt_config {
+  int32_t abi_version;         /* GT_ABI_VERSION */
+  /* frame geometry */
+  int32_t frame_h, frame_w;    /* source frame, u8 BGR HWC (2160 x 3840) */
+  int32_t max_batch;           /* frames per call (<= 32) */
+  /* detector */
+  int32_t imgsz;               /* 1920 */
+  int32_t nc;                  /* number of classes (4) */
+  int32_t task;                /* GT_TASK_DETECT | GT_TASK_OBB */
+  int32_t max_det;             /* 1000 */
+  int32_t max_nms;             /* 30000 */
+  /* stabilizer */
+  float   downsample_ratio;    /* 0.5 (only 0.5 and 1.0 are implemented) */
+  int32_t max_features;        /* 2000 */
+  float   ref_multiplier;      /* 2.0 */
+  int32_t mask_use;            /* 1 */
+  float   mask_margin_ratio;   /* 0.15 */
+  float   filter_ratio;        /* 0.9  (Lowe) */
+  float   ransac_threshold;    /* 2.0 px, in the working (downsampled) image */
+  int32_t ransac_max_iter;     /* 5000 hypotheses */
+  int32_t query_is_current;    /* 1: knnMatch(query=current, train=reference) */
+  int32_t ransac_full_res;     /* 0: threshold applies at working resolution, H conjugated afterwards */
+  uint32_t seed;               /* RANSAC sampling seed (deterministic) */
+  int32_t reserved[8];
+} gt_config;
+
+void gt_default_config(gt_config* cfg);
+
+int gt_create(const gt_config* cfg, int device, gt_handle* out);
+int gt_destroy(gt_handle h);
+const char* gt_last_error(gt_handle h);     /* h may be NULL: last creation error */
+int gt_abi_version(void);
+
+/* ---- detector weights -----------------------------------------------------------------------------------------
+ * Host passes BN-folded convolutions in the canonical order returned by gt_conv_count()/gt_conv_info():
+ * weight[i] is f32 [cout][cin][k][k] (PyTorch layout), bias[i] f32 [cout].  The library converts to bf16,
+ * reorders to [cout][k*k][cin_pad] and uploads.  Replaces ultralytics' AutoBackend + Model.fuse() (extract.py:222). */
+typedef struct gt_conv_desc {
+  char    name[48];            /* ultralytics state_dict prefix, e.g. "model.2.m.0.cv1" */
+  int32_t cin, cout, k, stride;
+  int32_t act;                 /* 1 = SiLU, 0 = linear (final head convs) */
+} gt_conv_desc;
+
+int gt_conv_count(gt_handle h);
+int gt_conv_info(gt_handle h, int idx, gt_conv_desc* out);
+int gt_load_weights(gt_handle h, const float* const* weights, const float* const* biases, int n_convs);
+
+/* ---- stage 1: letterbox / normalise (+ half-res gray for stage 3) ---------------------------------------------
+ * frames: u8 [B][frame_h][frame_w][3] BGR.  Replaces LetterBox + BasePredictor.preprocess (extract.py:153) and
+ * stabilo's BGR2GRAY + resize front end (extract.py:177,181).  Results stay in the handle's workspaces.        */
+int gt_preprocess(gt_handle h, const uint8_t* frames, int B, void* stream);
+/* debug/parity read-back: bf16 planar RGB [B][3][net_h][net_w] as uint16 and u8 gray [B][work_h][work_w] */
+int gt_get_net_input(gt_handle h, int B, uint16_t* out_bf16, int32_t* net_h, int32_t* net_w);
+int gt_get_gray(gt_handle h, int B, uint8_t* out, int32_t* work_h, int32_t* work_w);
+
+/* ---- stage 2: YOLOv8s forward + DFL decode + confidence filter + NMS ------------------------------------------
+ * Consumes the tensor left by gt_preprocess.  out_boxes: f32 [B][max_det][6] = x1,y1,x2,y2,conf,cls in source
+ * frame pixels (task OBB: [B][max_det][7] = x,y,w,h,r,conf,cls).  out_keep: optional int32 [B][max_det] anchor index
+ * of each kept box.  classes_mask: bit c set = class c allowed (0 = all).  Replaces model.track(...)'s
+ * inference + non_max_suppression + scale_boxes (extract.py:153).                                             */
+int gt_detect(gt_handle h, int B, float conf, float iou, int agnostic, uint32_t classes_mask,
+              float* out_boxes, int32_t* out_counts, int32_t* out_keep, void* stream);
+/* raw head tensor f32 [B][A][no] (A = anchors, no = 64+nc(+1)), anchor-major; parity gate (1) */
+int gt_get_raw_head(gt_handle h, int B, float* out, int32_t* A, int32_t* no);
+/* any intermediate feature map by ultralytics layer index (0..21): bf16 NHWC as uint16 */
+int gt_get_feature(gt_handle h, int layer, int B, uint16_t* out, int32_t* C, int32_t* H, int32_t* W);
+
+/* stand-alone NMS on caller-supplied decoded predictions (for bit-exact index parity):
+ * pred f32 [B][A][4+nc(+1)] xywh(+angle last) + class probabilities, letterboxed pixels.                       */
+int gt_nms(gt_handle h, const float* pred, int B, int A, int nc, int rotated, float conf, float iou, int agnostic,
+           uint32_t classes_mask, int max_det, float* out_rows /*[B][max_det][6|7] letterboxed*/, int32_t* out_counts,
+           int32_t* out_keep, void* stream);
+
+/* stand-alone convolution (unit parity of the tcgen05 implicit-GEMM kernel against torch.conv2d):
+ * x bf16 NHWC [B][H][W][cin] as uint16, w f32 [cout][cin][k][k], bias f32, optional residual bf16 NHWC;
+ * out bf16 NHWC [B][Ho][Wo][cout] (out_f32 != 0: f32).                                                         */
+int gt_conv2d(gt_handle h, const uint16_t* x, int B, int H, int W, int cin, const float* w, const float* bias,
+              int cout, int k, int stride, int act, const uint16_t* residual, void* out, int out_f32, void* stream);
+
+/* ---- stage 3: Stabilo-style frame-to-reference homography -------------------------------------------------------
+ * Works on the half-res gray left by gt_preprocess.  boxes: f32 xywh in source-frame pixels (the vehicle mask),
+ * nboxes[b] per frame, box_stride boxes reserved per frame.                                                    */
+int gt_set_reference(gt_handle h, int frame_slot, const float* boxes, int nboxes, void* stream);
+/* out_H f64 [B][9] row-major current->reference in source-frame pixels, h33 = 1;
+ * out_status int32 [B]: 0 ok, 1 no homography;  out_stats int32 [B][4] = kp_ref, kp_cur, matches, inliers.       */
+int gt_stabilize(gt_handle h, int B, const float* boxes, const int32_t* nboxes, int box_stride,
+                 double* out_H, int32_t* out_status, int32_t* out_stats, void* stream);
+/* boxes xywh (n,4) warped in place: 4 corners -> H -> axis-aligned envelope -> xywh (extract.py:183)            */
+int gt_warp_boxes(gt_handle h, const double* H, float* boxes, int n, void* stream);
+
+/* ORB stage read-backs for stage-wise parity against OpenCV.  which: 0 = current batch slot b, 1 = reference.   */
+int gt_orb_level_info(gt_handle h, int level, int32_t* w, int32_t* hgt, int32_t* quota_cur, int32_t* quota_ref);
+int gt_get_pyramid_level(gt_handle h, int which, int b, int level, uint8_t* out_img, uint8_t* out_mask);
+/* keypoints f32 [n][6] = x, y (level-0 pixel units), size, angle(deg), response, octave; descriptors u8 [n][32]  */
+int gt_get_keypoints(gt_handle h, int which, int b, int max_n, float* out_kp, uint8_t* out_desc, int32_t* n);
+/* run ORB alone on a caller-supplied gray image [B][work_h][work_w] (+ optional masks), into current slots      */
+int gt_orb_detect(gt_handle h, const uint8_t* gray, const uint8_t* mask, int B, int as_reference, void* stream);
+/* stand-alone 2-NN Hamming matcher + ratio test: query [nq][32], train [nt][32] -> per query best/second index/dist */
+int gt_match(gt_handle h, const uint8_t* query, int nq, const uint8_t* train, int nt, int32_t* out_idx /*[nq][2]*/,
+             int32_t* out_dist /*[nq][2]*/, void* stream);
+/* stand-alone robust homography: pts f32 [n][2] each -> H f64[9], inlier count                                  */
+int gt_find_homography(gt_handle h, const float* src, const float* dst, int n, float thr, int max_iter,
+                       double* out_H, int32_t* out_inliers, void* stream);
+
+/* ---- fused per-batch call used by the shims and bench.py --------------------------------------------------------
+ * preprocess -> detect -> (mask = own detections) -> stabilize -> warp.  out_boxes_stab f32 [B][max_det][4] xywh.
+ * first_is_reference != 0: frame 0 of this batch becomes the reference (H = identity for it).                  */
+int gt_extract_batch(gt_handle h, const uint8_t* frames, int B, int first_is_reference, float conf, float iou,
+                     int agnostic, uint32_t classes_mask, float* out_boxes, int32_t* out_counts,
+                     float* out_boxes_stab, double* out_H, int32_t* out_status, int32_t* out_stats, void* stream);
+
+/* ---- instrumentation ---------------------------------------------------------------------------------------------
+ * ms[0..3] = preprocess, inference, postprocess(decode+NMS), stabilize of the last call (fills Results.speed,
+ * extract.py:155-156).  gt_launch_count: kernels launched by this handle since creation.                         */
+int gt_stage_times(gt_handle h, float* ms4);
+int64_t gt_launch_count(gt_handle h);
+/* time (ms, CUDA events on the handle's stream) the conv stack took in the last gt_detect, and its FLOPs        */
+int gt_conv_stack_stats(gt_handle h, float* ms, double* flops);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GEOTRAX_B200_H_ */

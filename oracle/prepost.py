@@ -1,0 +1,203 @@
+"""numpy / torch restatement of ultralytics pre- and post-processing (oracle; test infrastructure only).
+
+Restates (un-vendored): ``data/augment.py:LetterBox``, ``engine/predictor.py:preprocess``,
+``utils/nms.py:non_max_suppression`` + ``nms_rotated``, ``utils/metrics.py:batch_probiou``,
+``utils/ops.py:{scale_boxes,clip_boxes,xywh2xyxy,regularize_rboxes}``.  Reference call site:
+/root/reference/geotrax/extract.py:153 (``model.track``) with the keys of
+/root/reference/geotrax/cfg/default.yaml:229-250 (conf 0.25, iou 0.7, max_det 1000, classes, agnostic_nms).
+"""
+from __future__ import annotations
+
+import math
+from typing import List, Optional, Sequence, Tuple
+
+import cv2
+import numpy as np
+import torch
+import torchvision
+
+MAX_WH = 7680
+MAX_NMS = 30000
+
+
+def letterbox_params(h0: int, w0: int, imgsz: int = 1920, stride: int = 32):
+    """-> (new_w, new_h, top, bottom, left, right, gain).  LetterBox(auto=True, center=True, scaleup=True)."""
+    r = min(imgsz / h0, imgsz / w0)
+    new_w, new_h = int(round(w0 * r)), int(round(h0 * r))
+    dw, dh = (imgsz - new_w) % stride, (imgsz - new_h) % stride
+    dw, dh = dw / 2, dh / 2
+    top, bottom = int(round(dh - 0.1)), int(round(dh + 0.1))
+    left, right = int(round(dw - 0.1)), int(round(dw + 0.1))
+    return new_w, new_h, top, bottom, left, right, r
+
+
+def letterbox_u8(frame_bgr: np.ndarray, imgsz: int = 1920, stride: int = 32) -> np.ndarray:
+    """u8 HWC BGR -> u8 HWC BGR letterboxed (pad value 114)."""
+    h0, w0 = frame_bgr.shape[:2]
+    new_w, new_h, top, bottom, left, right, _ = letterbox_params(h0, w0, imgsz, stride)
+    img = frame_bgr
+    if (w0, h0) != (new_w, new_h):
+        img = cv2.resize(img, (new_w, new_h), interpolation=cv2.INTER_LINEAR)
+    return cv2.copyMakeBorder(img, top, bottom, left, right, cv2.BORDER_CONSTANT, value=(114, 114, 114))
+
+
+def preprocess(frames_bgr: Sequence[np.ndarray], imgsz: int = 1920) -> torch.Tensor:
+    """list of u8 HWC BGR -> f32 NCHW RGB in [0,1]."""
+    im = np.stack([letterbox_u8(f, imgsz) for f in frames_bgr])
+    im = np.ascontiguousarray(im[..., ::-1].transpose((0, 3, 1, 2)))
+    return torch.from_numpy(im).float() / 255.0
+
+
+def xywh2xyxy(x: torch.Tensor) -> torch.Tensor:
+    y = torch.empty_like(x)
+    xy, wh = x[..., :2], x[..., 2:4] / 2
+    y[..., :2] = xy - wh
+    y[..., 2:4] = xy + wh
+    return y
+
+
+def _cov(boxes: torch.Tensor):
+    gbbs = torch.cat((boxes[:, 2:4].pow(2) / 12, boxes[:, 4:]), dim=-1)
+    a, b, c = gbbs.split(1, dim=-1)
+    cos, sin = c.cos(), c.sin()
+    cos2, sin2 = cos.pow(2), sin.pow(2)
+    return a * cos2 + b * sin2, a * sin2 + b * cos2, (a - b) * cos * sin
+
+
+def batch_probiou(obb1: torch.Tensor, obb2: torch.Tensor, eps: float = 1e-7) -> torch.Tensor:
+    """(N,5) x (M,5) xywhr -> (N,M) ProbIoU."""
+    x1, y1 = obb1[..., :2].split(1, dim=-1)
+    x2, y2 = (x.squeeze(-1)[None] for x in obb2[..., :2].split(1, dim=-1))
+    a1, b1, c1 = _cov(obb1)
+    a2, b2, c2 = (x.squeeze(-1)[None] for x in _cov(obb2))
+    t1 = (((a1 + a2) * (y1 - y2).pow(2) + (b1 + b2) * (x1 - x2).pow(2)) / ((a1 + a2) * (b1 + b2) - (c1 + c2).pow(2) + eps)) * 0.25
+    t2 = (((c1 + c2) * (x2 - x1) * (y1 - y2)) / ((a1 + a2) * (b1 + b2) - (c1 + c2).pow(2) + eps)) * 0.5
+    t3 = (((a1 + a2) * (b1 + b2) - (c1 + c2).pow(2))
+          / (4 * ((a1 * b1 - c1.pow(2)).clamp_(0) * (a2 * b2 - c2.pow(2)).clamp_(0)).sqrt() + eps) + eps).log() * 0.5
+    bd = (t1 + t2 + t3).clamp(eps, 100.0)
+    hd = (1.0 - (-bd).exp() + eps).sqrt()
+    return 1 - hd
+
+
+def nms_rotated(boxes: torch.Tensor, scores: torch.Tensor, threshold: float) -> torch.Tensor:
+    """Fast-NMS semantics: j survives iff no higher-scored i has probiou(i,j) >= thr (suppressed boxes still suppress)."""
+    order = torch.argsort(scores, descending=True, stable=True)
+    b = boxes[order]
+    ious = batch_probiou(b, b).triu_(diagonal=1)
+    pick = torch.nonzero(ious.max(dim=0)[0] < threshold).squeeze(-1)
+    return order[pick]
+
+
+def non_max_suppression(pred: torch.Tensor, conf_thres=0.25, iou_thres=0.7, classes: Optional[Sequence[int]] = None,
+                        agnostic=False, max_det=1000, nc=0, rotated=False, return_idxs=False):
+    """pred (B, 4+nc+nm, A) -> list of (n, 6+nm) [xyxy|xywh, conf, cls, extra].  Also the kept anchor indices."""
+    bs = pred.shape[0]
+    nc = nc or (pred.shape[1] - 4)
+    nm = pred.shape[1] - nc - 4
+    mi = 4 + nc
+    xc = pred[:, 4:mi].amax(1) > conf_thres
+    pred = pred.transpose(-1, -2).clone()
+    if not rotated:
+        pred[..., :4] = xywh2xyxy(pred[..., :4])
+    out = [torch.zeros((0, 6 + nm))] * bs
+    idxs = [torch.zeros((0,), dtype=torch.long)] * bs
+    cls_t = None if classes is None else torch.tensor(list(classes), dtype=torch.float32)
+    for xi, x in enumerate(pred):
+        ai = torch.nonzero(xc[xi]).squeeze(-1)
+        x = x[ai]
+        if not x.shape[0]:
+            continue
+        box, cls, extra = x.split((4, nc, nm), 1)
+        conf, j = cls.max(1, keepdim=True)
+        keep = conf.view(-1) > conf_thres
+        x = torch.cat((box, conf, j.float(), extra), 1)[keep]
+        ai = ai[keep]
+        if cls_t is not None:
+            k2 = (x[:, 5:6] == cls_t).any(1)
+            x, ai = x[k2], ai[k2]
+        n = x.shape[0]
+        if not n:
+            continue
+        if n > MAX_NMS:
+            top = x[:, 4].argsort(descending=True, stable=True)[:MAX_NMS]
+            x, ai = x[top], ai[top]
+        c = x[:, 5:6] * (0 if agnostic else MAX_WH)
+        scores = x[:, 4]
+        if rotated:
+            boxes = torch.cat((x[:, :2] + c, x[:, 2:4], x[:, -1:]), dim=-1)
+            i = nms_rotated(boxes, scores, iou_thres)
+        else:
+            i = torchvision.ops.nms(x[:, :4] + c, scores, iou_thres)
+        i = i[:max_det]
+        out[xi], idxs[xi] = x[i], ai[i]
+    return (out, idxs) if return_idxs else out
+
+
+def clip_boxes(boxes: torch.Tensor, shape: Tuple[int, int]) -> torch.Tensor:
+    boxes[..., 0].clamp_(0, shape[1])
+    boxes[..., 1].clamp_(0, shape[0])
+    boxes[..., 2].clamp_(0, shape[1])
+    boxes[..., 3].clamp_(0, shape[0])
+    return boxes
+
+
+def scale_boxes(img1_shape, boxes: torch.Tensor, img0_shape, xywh=False) -> torch.Tensor:
+    """Letterboxed-pixel boxes -> original-frame pixels (in place on a clone)."""
+    boxes = boxes.clone()
+    gain = min(img1_shape[0] / img0_shape[0], img1_shape[1] / img0_shape[1])
+    pad_x = round((img1_shape[1] - img0_shape[1] * gain) / 2 - 0.1)
+    pad_y = round((img1_shape[0] - img0_shape[0] * gain) / 2 - 0.1)
+    boxes[..., 0] -= pad_x
+    boxes[..., 1] -= pad_y
+    if not xywh:
+        boxes[..., 2] -= pad_x
+        boxes[..., 3] -= pad_y
+    boxes[..., :4] /= gain
+    return boxes if xywh else clip_boxes(boxes, img0_shape)
+
+
+def regularize_rboxes(rboxes: torch.Tensor) -> torch.Tensor:
+    x, y, w, h, t = rboxes.unbind(dim=-1)
+    swap = t % math.pi >= math.pi / 2
+    w_ = torch.where(swap, h, w)
+    h_ = torch.where(swap, w, h)
+    t = t % (math.pi / 2)
+    return torch.stack([x, y, w_, h_, t], dim=-1)
+
+
+def xyxy2xywh(x: torch.Tensor) -> torch.Tensor:
+    y = torch.empty_like(x)
+    y[..., 0] = (x[..., 0] + x[..., 2]) / 2
+    y[..., 1] = (x[..., 1] + x[..., 3]) / 2
+    y[..., 2] = x[..., 2] - x[..., 0]
+    y[..., 3] = x[..., 3] - x[..., 1]
+    return y
+
+
+def postprocess_detect(decoded: torch.Tensor, in_shape, orig_shape, conf=0.25, iou=0.7, classes=None, agnostic=True,
+                       max_det=1000) -> List[torch.Tensor]:
+    """decoded (B,4+nc,A) -> per image (n,6) [x1,y1,x2,y2,conf,cls] in original-frame pixels."""
+    outs = non_max_suppression(decoded, conf, iou, classes, agnostic, max_det, nc=decoded.shape[1] - 4)
+    res = []
+    for o in outs:
+        o = o.clone()
+        if o.shape[0]:
+            o[:, :4] = scale_boxes(in_shape, o[:, :4], orig_shape)
+        res.append(o)
+    return res
+
+
+def postprocess_obb(decoded: torch.Tensor, in_shape, orig_shape, conf=0.25, iou=0.7, classes=None, agnostic=True,
+                    max_det=1000) -> List[torch.Tensor]:
+    """decoded (B,4+nc+1,A) -> per image (n,7) [x,y,w,h,r,conf,cls] in original-frame pixels."""
+    nc = decoded.shape[1] - 5
+    outs = non_max_suppression(decoded, conf, iou, classes, agnostic, max_det, nc=nc, rotated=True)
+    res = []
+    for o in outs:
+        if not o.shape[0]:
+            res.append(torch.zeros((0, 7)))
+            continue
+        rb = regularize_rboxes(torch.cat([o[:, :4], o[:, -1:]], dim=-1))
+        rb[:, :4] = scale_boxes(in_shape, rb[:, :4], orig_shape, xywh=True)
+        res.append(torch.cat([rb, o[:, 4:6]], dim=-1))
+    return res

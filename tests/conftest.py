@@ -1,0 +1,42 @@
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (B200); run with -m gpu on the GPU box")
+
+
+def f32_to_bf16_bits(x: np.ndarray) -> np.ndarray:
+    """float32 -> bf16 bit pattern (uint16), round-to-nearest-even."""
+    u = np.ascontiguousarray(x, np.float32).view(np.uint32).astype(np.uint64)
+    r = ((u >> 16) & 1) + 0x7FFF
+    return ((u + r) >> 16).astype(np.uint16)
+
+
+def bf16_bits_to_f32(b: np.ndarray) -> np.ndarray:
+    return (b.astype(np.uint32) << 16).view(np.float32)
+
+
+def bf16_round(x: np.ndarray) -> np.ndarray:
+    return bf16_bits_to_f32(f32_to_bf16_bits(x))
+
+
+@pytest.fixture(scope="session")
+def small_engine():
+    """Engine on a 512x768 frame (imgsz 384 -> net 256x384), batch 2, with seeded random weights."""
+    import geotrax_b200
+    from geotrax_b200 import weights
+
+    eng = geotrax_b200.Engine(frame_hw=(512, 768), imgsz=384, nc=4, max_batch=2, max_det=300, max_features=500)
+    sd = weights.random_state_dict(4, "detect", seed=0, frame_hw=(512, 768), imgsz=384, cls_bias=-4.0)
+    eng.load_weights(weights.fold(sd))
+    eng._sd = sd
+    yield eng
+    eng.close()

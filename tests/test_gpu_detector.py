@@ -1,0 +1,185 @@
+"""GPU parity of stage 1 + stage 2 against the oracle, through the C-ABI (geo-trax_b200/_lib.py -> libgeotrax_b200.so)."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import bf16_bits_to_f32, bf16_round, f32_to_bf16_bits
+
+pytestmark = pytest.mark.gpu
+
+
+def _frames(n, h, w, seed=0):
+    from geotrax_b200 import synth
+    return np.stack(synth.make_flight(n, h, w, seed, n_vehicles=20)[0])
+
+
+def _oracle_model(sd, nc=4, task="detect"):
+    from oracle.yolov8 import YOLOv8
+    m = YOLOv8(nc, task).eval()
+    missing = m.load_state_dict(sd, strict=False)
+    assert not missing.unexpected_keys
+    return m
+
+
+def test_preprocess_bit_exact(small_engine):
+    import cv2
+    from oracle import prepost
+    eng = small_engine
+    rng = np.random.default_rng(0)
+    frames = rng.integers(0, 256, (2, 512, 768, 3), dtype=np.uint8)
+    eng.preprocess(frames)
+    got = eng.net_input(2)
+    ref = prepost.preprocess(list(frames), 384).numpy()
+    assert got.shape == ref.shape == (2, 3, 256, 384)
+    assert np.array_equal(got, f32_to_bf16_bits(ref)), "letterbox/normalise differs from the oracle (bf16 bit-exact expected)"
+    gray = eng.gray(2)
+    for i in range(2):
+        g = cv2.resize(cv2.cvtColor(frames[i], cv2.COLOR_BGR2GRAY), (384, 256), interpolation=cv2.INTER_LINEAR)
+        assert np.array_equal(gray[i], g), "gray half-res differs from cv2 (bit-exact expected)"
+
+
+CONV_CASES = [
+    # (B, H, W, cin, cout, k, stride, act, residual, f32)
+    (2, 32, 48, 64, 64, 1, 1, True, False, False),
+    (2, 32, 48, 64, 128, 3, 1, True, False, False),
+    (1, 34, 60, 32, 32, 3, 1, True, True, False),      # cin < 64 (zero-filled K), residual, ragged tiles
+    (2, 32, 48, 64, 128, 3, 2, True, False, False),     # stride 2 (TMA elementStrides)
+    (1, 17, 30, 96, 64, 1, 1, True, False, False),      # cin not a multiple of 64
+    (1, 16, 24, 128, 512, 1, 1, True, False, False),    # two N tiles
+    (1, 16, 24, 256, 192, 3, 1, True, False, False),    # fused head width (N = 192)
+    (1, 20, 28, 128, 4, 1, 1, False, False, True),      # final class conv: N padded to 16, fp32 rows
+    (1, 20, 28, 64, 64, 1, 1, False, False, True),      # final box conv, fp32 rows
+    (1, 68, 120, 128, 128, 3, 2, True, False, False),
+]
+
+
+@pytest.mark.parametrize("case", CONV_CASES)
+def test_conv2d_tcgen05_matches_torch(small_engine, case):
+    B, H, W, cin, cout, k, s, act, use_res, f32 = case
+    g = torch.Generator().manual_seed(hash(case) % (2 ** 31))
+    x = bf16_round(torch.randn(B, H, W, cin, generator=g).numpy())
+    w = (torch.randn(cout, cin, k, k, generator=g) / (cin * k * k) ** 0.5).numpy()
+    b = torch.randn(cout, generator=g).numpy() * 0.1
+    ref = torch.nn.functional.conv2d(torch.from_numpy(x).permute(0, 3, 1, 2), torch.from_numpy(bf16_round(w)), torch.from_numpy(b), s, k // 2)
+    if act:
+        ref = torch.nn.functional.silu(ref)
+    res_bits = None
+    if use_res:
+        res = bf16_round(torch.randn(*ref.permute(0, 2, 3, 1).shape, generator=g).numpy())
+        ref = ref + torch.from_numpy(res).permute(0, 3, 1, 2)
+        res_bits = f32_to_bf16_bits(res)
+    ref = ref.permute(0, 2, 3, 1).numpy()
+    out = small_engine.conv2d(f32_to_bf16_bits(x), w, b, k, s, act, res_bits, out_f32=f32)
+    got = out if f32 else bf16_bits_to_f32(out)
+    assert got.shape == ref.shape
+    tol = 2e-3 if f32 else 1e-2      # fp32 rows: accumulation order only; bf16 rows: one bf16 rounding (2^-9) on top
+    err = np.abs(got - ref).max() / max(1e-6, np.abs(ref).max())
+    assert err < tol, f"conv {case}: max-normalised error {err:.3e}"
+
+
+def test_raw_head_within_1e2_of_fp32_oracle(small_engine):
+    """north_star criterion (1): raw head tensor within 1e-2 relative of the fp32 reference (bf16 compute)."""
+    from oracle import prepost
+    eng = small_engine
+    frames = _frames(2, 512, 768, seed=3)
+    eng.preprocess(frames)
+    eng.detect(2, conf=0.25)
+    raw = eng.raw_head(2)                                  # (B, A, no)
+    m = _oracle_model(eng._sd)
+    with torch.no_grad():
+        dec, ref = m(prepost.preprocess(list(frames), 384))  # (B, no, A)
+    ref = ref.permute(0, 2, 1).numpy()
+    assert raw.shape == ref.shape
+    rel = np.linalg.norm(raw - ref) / np.linalg.norm(ref)
+    print("raw head rel L2 error", rel, "max abs", np.abs(raw - ref).max(), "ref absmax", np.abs(ref).max())
+    assert rel < 1e-2
+
+
+def test_intermediate_features_close(small_engine):
+    from oracle import prepost
+    eng = small_engine
+    frames = _frames(1, 512, 768, seed=4)
+    eng.preprocess(frames)
+    eng.detect(1, conf=0.25)
+    m = _oracle_model(eng._sd)
+    taps = {}
+    with torch.no_grad():
+        m(prepost.preprocess(list(frames), 384), taps)
+    for layer in (0, 1, 2, 4, 6, 9, 12, 15, 18, 21):
+        got = bf16_bits_to_f32(eng.feature(layer, 1))
+        ref = taps[str(layer)].permute(0, 2, 3, 1).numpy()
+        rel = np.linalg.norm(got - ref) / np.linalg.norm(ref)
+        print("layer", layer, "rel", rel)
+        assert rel < 1e-2, f"layer {layer}: rel {rel}"
+
+
+def _rand_pred(B, A, nc, rng, rotated=False, frac=0.05):
+    xy = rng.uniform(0, 1900, (B, A, 2))
+    wh = rng.uniform(10, 120, (B, A, 2))
+    cls = rng.uniform(0, 0.2, (B, A, nc))
+    hot = rng.random((B, A)) < frac
+    cls[hot, rng.integers(0, nc, hot.sum())] = rng.uniform(0.25, 0.99, hot.sum())
+    parts = [xy, wh, cls]
+    if rotated:
+        parts.append(rng.uniform(-0.7, 2.3, (B, A, 1)))
+    return np.concatenate(parts, 2).astype(np.float32)
+
+
+@pytest.mark.parametrize("agnostic", [True, False])
+@pytest.mark.parametrize("A,frac", [(3000, 0.05), (3000, 0.0), (8064, 0.9)])
+def test_nms_indices_bit_exact(small_engine, agnostic, A, frac):
+    """criterion (2): identical keep indices / classes; boxes equal (same decoded inputs on both sides)."""
+    from oracle import prepost
+    rng = np.random.default_rng(A + int(agnostic))
+    pred = _rand_pred(2, A, 4, rng, frac=frac)
+    # clustered boxes so that suppression actually happens
+    pred[:, ::3, :2] = pred[:, 1::3, :2][:, : pred[:, ::3].shape[1]] + rng.uniform(-6, 6, pred[:, ::3, :2].shape).astype(np.float32)
+    rows, counts, keep = small_engine.nms(pred, 4, False, 0.25, 0.7, agnostic, [0, 1, 2, 3], 300)
+    ref, idxs = prepost.non_max_suppression(torch.from_numpy(pred).permute(0, 2, 1), 0.25, 0.7, [0, 1, 2, 3], agnostic, 300, nc=4, return_idxs=True)
+    for b in range(2):
+        n = int(counts[b])
+        assert n == len(ref[b]), f"image {b}: kept {n} vs oracle {len(ref[b])}"
+        assert np.array_equal(keep[b, :n], idxs[b].numpy()), "keep indices differ"
+        assert np.array_equal(rows[b, :n, 5], ref[b][:, 5].numpy())
+        assert np.array_equal(rows[b, :n, :5], ref[b][:, :5].numpy()), "boxes/conf differ bitwise"
+
+
+def test_nms_rotated_matches_oracle(small_engine):
+    from oracle import prepost
+    rng = np.random.default_rng(7)
+    pred = _rand_pred(2, 2500, 4, rng, rotated=True, frac=0.08)
+    rows, counts, keep = small_engine.nms(pred, 4, True, 0.25, 0.5, True, None, 300)
+    ref, idxs = prepost.non_max_suppression(torch.from_numpy(pred).permute(0, 2, 1), 0.25, 0.5, None, True, 300, nc=4, rotated=True, return_idxs=True)
+    for b in range(2):
+        n = int(counts[b])
+        got, want = set(keep[b, :n].tolist()), set(idxs[b].numpy().tolist())
+        # probiou uses transcendental functions: allow boundary flips on < 1 % of the kept set
+        assert len(got ^ want) <= max(1, len(want) // 100), f"rotated keep sets differ: {len(got ^ want)} of {len(want)}"
+
+
+def test_detect_end_to_end_matches_oracle_on_same_raw(small_engine):
+    """GPU decode + filter + NMS + scale_boxes vs the oracle's, both fed the GPU's raw head tensor."""
+    from oracle import prepost
+    from oracle.yolov8 import YOLOv8
+    eng = small_engine
+    frames = _frames(2, 512, 768, seed=9)
+    eng.preprocess(frames)
+    boxes, counts, keep = eng.detect(2, conf=0.05, iou=0.7, agnostic=True, classes=[0, 1, 2, 3], want_keep=True)
+    raw = torch.from_numpy(eng.raw_head(2)).permute(0, 2, 1).contiguous()
+    head = YOLOv8(4).model[22]
+    shapes = [(32, 48), (16, 24), (8, 12)]
+    dec = head.decode(raw, shapes)
+    outs, idxs = prepost.non_max_suppression(dec, 0.05, 0.7, [0, 1, 2, 3], True, 300, nc=4, return_idxs=True)
+    assert counts.sum() > 10, "test needs some detections; lower conf"
+    for b in range(2):
+        n = int(counts[b])
+        ref = outs[b].clone()
+        ref[:, :4] = prepost.scale_boxes((256, 384), ref[:, :4], (512, 768))
+        got_set, ref_set = set(keep[b, :n].tolist()), set(idxs[b].numpy().tolist())
+        assert len(got_set ^ ref_set) <= max(1, len(ref_set) // 50), f"keep sets differ by {len(got_set ^ ref_set)} of {len(ref_set)}"
+        common = [i for i in keep[b, :n] if i in ref_set]
+        ref_by = {int(a): r for a, r in zip(idxs[b].numpy(), ref.numpy())}
+        got_by = {int(a): r for a, r in zip(keep[b, :n], boxes[b, :n])}
+        for a in common:
+            assert got_by[a][5] == ref_by[a][5]
+            np.testing.assert_allclose(got_by[a][:5], ref_by[a][:5], rtol=2e-4, atol=2e-3)

@@ -1,0 +1,175 @@
+"""GPU parity of stage 3 (ORB / Hamming 2-NN / RANSAC homography / box warp) against OpenCV and the golden files."""
+import os
+
+import cv2
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden", "u_video_cut_golden.npz")
+
+
+@pytest.fixture(scope="module")
+def stab_engine():
+    import geotrax_b200
+    eng = geotrax_b200.Engine(frame_hw=(1080, 1920), imgsz=960, nc=4, max_batch=2, max_det=300, max_features=2000)
+    yield eng
+    eng.close()
+
+
+@pytest.fixture(scope="module")
+def flight():
+    from geotrax_b200 import synth
+    return synth.make_flight(3, 1080, 1920, seed=11, n_vehicles=40)
+
+
+def _gray_half(frame):
+    g = cv2.cvtColor(frame, cv2.COLOR_BGR2GRAY)
+    return cv2.resize(g, (g.shape[1] // 2, g.shape[0] // 2), interpolation=cv2.INTER_LINEAR)
+
+
+def test_pyramid_bit_exact(stab_engine, flight):
+    eng = stab_engine
+    g = _gray_half(flight[0][0])
+    eng.orb_detect(g[None], None)
+    prev = g
+    for lvl, (w, h, _, _) in enumerate(eng.orb_level_info()):
+        img, msk = eng.pyramid_level(0, 0, lvl)
+        if lvl > 0:
+            prev = cv2.resize(prev, (w, h), interpolation=cv2.INTER_LINEAR_EXACT)
+        assert img.shape == prev.shape
+        assert np.array_equal(img, prev), f"pyramid level {lvl} differs from cv2 INTER_LINEAR_EXACT chain"
+        assert (msk == 255).all()
+
+
+def test_keypoints_match_opencv_orb(stab_engine, flight):
+    """Same key-point set as cv2.ORB (positions, octave), Harris response and angle within float tolerance."""
+    eng = stab_engine
+    g = _gray_half(flight[0][1])
+    eng.orb_detect(g[None], None)
+    kp, desc = eng.keypoints(0, 0)
+    ref_kp, ref_desc = cv2.ORB_create(nfeatures=2000).detectAndCompute(g, None)
+    ref = {(round(k.pt[0], 2), round(k.pt[1], 2), k.octave): (k, d) for k, d in zip(ref_kp, ref_desc)}
+    got = {(round(float(r[0]), 2), round(float(r[1]), 2), int(r[5])): (r, d) for r, d in zip(kp, desc)}
+    common = set(ref) & set(got)
+    print("opencv", len(ref), "gpu", len(got), "common", len(common))
+    assert len(common) >= 0.98 * len(ref), f"only {len(common)} of {len(ref)} OpenCV key points reproduced"
+    ang_bad = resp_bad = bit_bad = 0
+    for key in common:
+        k, d = ref[key]
+        r, dd = got[key]
+        da = abs(((r[3] - k.angle) + 180) % 360 - 180)
+        ang_bad += da > 0.02
+        resp_bad += abs(r[4] - k.response) > 1e-5 * max(1e-9, abs(k.response)) + 1e-12
+        bit_bad += int(np.unpackbits(np.bitwise_xor(d, dd)).sum())
+    print("angle mismatches", ang_bad, "response mismatches", resp_bad, "descriptor bit mismatches", bit_bad, "of", 256 * len(common))
+    assert ang_bad <= 0.01 * len(common)
+    assert resp_bad <= 0.01 * len(common)
+    assert bit_bad <= 0.002 * 256 * len(common)
+
+
+def test_mask_excludes_boxes(stab_engine, flight):
+    eng = stab_engine
+    frames, boxes, _ = flight
+    eng.preprocess(np.stack(frames[:1]))
+    eng.set_reference(0, boxes[0])
+    kp, _ = eng.keypoints(1, 0)
+    assert len(kp) > 1000
+    b = boxes[0]
+    x, y = kp[:, 0] * 2, kp[:, 1] * 2   # level-0 working pixels -> full-res
+    inside = ((x[:, None] > b[None, :, 0] - b[None, :, 2] / 2) & (x[:, None] < b[None, :, 0] + b[None, :, 2] / 2)
+              & (y[:, None] > b[None, :, 1] - b[None, :, 3] / 2) & (y[:, None] < b[None, :, 1] + b[None, :, 3] / 2)).any(1)
+    lvl0 = kp[:, 5] == 0
+    assert not inside[lvl0].any(), "level-0 key points found inside masked vehicle boxes"
+
+
+def test_matcher_bit_exact(stab_engine):
+    rng = np.random.default_rng(5)
+    train = rng.integers(0, 256, (4000, 32), dtype=np.uint8)
+    query = train[rng.integers(0, 4000, 1999)].copy()
+    flip = rng.integers(0, 256, query.shape, dtype=np.uint8) & rng.integers(0, 256, query.shape, dtype=np.uint8) & rng.integers(0, 256, query.shape, dtype=np.uint8)
+    query ^= flip
+    query[:50] = rng.integers(0, 256, (50, 32), dtype=np.uint8)
+    train[100] = train[50]; train[200] = train[50]      # exact ties -> lower index must win
+    idx, dist = stab_engine.match(query, train)
+    ref = cv2.BFMatcher(cv2.NORM_HAMMING).knnMatch(query, train, k=2)
+    ri = np.array([[m.trainIdx, n.trainIdx] for m, n in ref])
+    rd = np.array([[int(m.distance), int(n.distance)] for m, n in ref])
+    assert np.array_equal(dist, rd)
+    assert np.array_equal(idx, ri)
+
+
+def test_find_homography_recovers_ground_truth(stab_engine):
+    rng = np.random.default_rng(3)
+    from geotrax_b200 import synth
+    Hgt = synth.small_homography(rng, 1080, 1920, max_t=20.0, max_rot_deg=1.0, max_persp=1e-5)
+    n = 2300
+    src = np.stack([rng.uniform(0, 1920, n), rng.uniform(0, 1080, n)], 1)
+    p = np.c_[src, np.ones(n)] @ Hgt.T
+    dst = p[:, :2] / p[:, 2:] + rng.normal(0, 0.3, (n, 2))
+    out = rng.random(n) < 0.35
+    dst[out] = np.stack([rng.uniform(0, 1920, out.sum()), rng.uniform(0, 1080, out.sum())], 1)
+    H, inl = stab_engine.find_homography(src.astype(np.float32), dst.astype(np.float32), 2.0, 2000)
+    assert H is not None
+    probe = np.array([[100, 100, 1], [1800, 100, 1], [960, 540, 1], [100, 1000, 1], [1800, 1000, 1.0]])
+    a, b = probe @ H.T, probe @ Hgt.T
+    err = np.linalg.norm(a[:, :2] / a[:, 2:] - b[:, :2] / b[:, 2:], axis=1)
+    Hcv, m = cv2.findHomography(src.astype(np.float32), dst.astype(np.float32), cv2.USAC_MAGSAC, 2.0, maxIters=5000, confidence=0.999999)
+    c = probe @ Hcv.T
+    err_cv = np.linalg.norm(c[:, :2] / c[:, 2:] - b[:, :2] / b[:, 2:], axis=1)
+    print("gpu err", err.max(), "inliers", inl, "| cv2 MAGSAC err", err_cv.max(), "inliers", int(m.sum()))
+    assert err.max() < 0.15
+    assert abs(inl - int((~out).sum())) < 0.05 * n
+
+
+def test_find_homography_degenerate_inputs(stab_engine):
+    H, inl = stab_engine.find_homography(np.zeros((3, 2), np.float32), np.zeros((3, 2), np.float32))
+    assert H is None
+    H, inl = stab_engine.find_homography(np.zeros((0, 2), np.float32), np.zeros((0, 2), np.float32))
+    assert H is None
+
+
+def test_stabilize_matches_oracle_and_truth(stab_engine, flight):
+    """criterion (3): stabilised box centres within 0.5 px mean of the oracle's (and of ground truth)."""
+    from oracle.stabilo_cv import Stabilizer, warp_boxes_xywh
+    eng = stab_engine
+    frames, boxes, Hs = flight
+    eng.preprocess(np.stack(frames[:1]))
+    eng.set_reference(0, boxes[0])
+    eng.preprocess(np.stack(frames[1:3]))
+    H, status, stats = eng.stabilize(2, boxes[1:3])
+    ora = Stabilizer()
+    ora.set_ref_frame(frames[0], boxes[0])
+    for i in range(2):
+        assert status[i] == 0
+        ora.stabilize(frames[1 + i], boxes[1 + i])
+        Ho = ora.get_cur_trans_matrix()
+        got = eng.warp_boxes(H[i], boxes[1 + i])
+        want = ora.transform_cur_boxes()
+        truth = warp_boxes_xywh(boxes[1 + i], Hs[1 + i])
+        d_or = np.linalg.norm(got[:, :2] - want[:, :2], axis=1)
+        d_gt = np.linalg.norm(got[:, :2] - truth[:, :2], axis=1)
+        d_or_gt = np.linalg.norm(want[:, :2] - truth[:, :2], axis=1)
+        print(f"frame {i + 1}: stats {stats[i].tolist()} oracle matches {ora.get_cur_num_matches()} inl {ora.get_cur_inliers_count()}",
+              f"| centre err vs oracle mean {d_or.mean():.3f} max {d_or.max():.3f} | vs truth mean {d_gt.mean():.3f} | oracle vs truth {d_or_gt.mean():.3f}")
+        assert d_or.mean() < 0.5
+        assert d_gt.mean() < 0.5
+        assert abs(H[i][2, 2] - 1.0) < 1e-12 and np.linalg.det(H[i]) > 0
+
+
+def test_warp_boxes_reproduces_golden_rows(stab_engine):
+    """Known-answer test from the reference's golden output (box-warp semantics)."""
+    z = np.load(GOLDEN)
+    tracks, transf = z["tracks"], z["transforms"]
+    Hby = {int(r[0]): r[1:].reshape(3, 3) for r in transf}
+    checked = 0
+    for f in np.unique(tracks[:, 0]).astype(int):
+        if f == 0:
+            continue
+        rows = tracks[tracks[:, 0] == f]
+        out = stab_engine.warp_boxes(Hby[f], rows[:, 2:6])
+        assert np.abs(out[:, :2] - rows[:, 6:8]).max() < 2.5e-2     # '%g' keeps 6 significant digits
+        assert np.abs(out[:, 2:] - rows[:, 8:10]).max() < 5e-3
+        checked += len(rows)
+    assert checked > 1000
