@@ -1,0 +1,302 @@
+#!/usr/bin/env python
+"""bench.py -- 4K frames/s of the extract hot path (letterbox -> YOLOv8s detect+NMS -> ORB/match/RANSAC -> box warp).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--dtype fp16|bf16]
+
+One "step" = one batch of 16 synthetic 3840x2160 BGR frames through the whole path (BASELINE.json configs[1]+[2] fused,
+the default preset of /root/reference/geotrax/cfg/default.yaml).  Prints ONE JSON line (rank 0).  N > 1 is launched by
+torchrun, one rank per GPU; frames are sharded by contiguous range (each rank owns its own frames: weak scaling) and
+the per-frame boxes + homographies are gathered to rank 0 over NCCL inside the timed region.
+
+`--impl reference` times the CPU oracle port of the same path (the reference's engines are CPU OpenCV + fp32 PyTorch;
+the packages ultralytics/stabilo themselves are not installable offline -- DESIGN.md) on the host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+FRAME_HW = (2160, 3840)
+IMGSZ = 1920
+BATCH = 16
+CONF, IOU = 0.25, 0.7
+CLS_BIAS = -4.4           # random-init class bias giving ~300 candidates / frame at conf 0.25 (golden: 127-136 kept / frame)
+METRIC = "4K frames/sec detect+stabilize"
+UNIT = "frames/s"
+# algorithmic work per 4K frame (SURVEY.md 8d / BASELINE.md section 2)
+CONV_GFLOP_PER_FRAME = 145.03
+
+
+def _peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return dict(hbm=d.get("hbm_gbs", 6650.0), tf_burst=d.get("bf16_tflops", 1590.0), tf_sust=d.get("bf16_tflops_sustained", 1400.0), src="measured")
+    return dict(hbm=6650.0, tf_burst=1590.0, tf_sust=1400.0, src="fallback")
+
+
+class ClockSampler(threading.Thread):
+    """Samples nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        super().__init__(daemon=True)
+        self.index, self.rows, self._halt = index, [], threading.Event()
+
+    def run(self):
+        while not self._halt.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([c.strip() for c in out.split(",")])
+            except Exception:
+                pass
+            self._halt.wait(0.2)
+
+    def stop(self):
+        self._halt.set()
+        self.join(timeout=3)
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        reasons = set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            for n, v in zip(names, r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return dict(sm_mhz=float(np.median(sm)) if sm else None, sm_max_mhz=max(mx) if mx else None, reasons=sorted(reasons), samples=len(self.rows))
+
+
+# ------------------------------------------------------------------------------------------------------------------------
+# CPU oracle port (cpu_baseline leg and --impl reference)
+# ------------------------------------------------------------------------------------------------------------------------
+class CpuPath:
+    def __init__(self, sd, threads: int):
+        import cv2
+        import torch
+        from oracle.stabilo_cv import Stabilizer
+        from oracle.yolov8 import YOLOv8
+
+        torch.set_num_threads(threads)
+        cv2.setNumThreads(threads)
+        self.model = YOLOv8(4, "detect").eval()
+        self.model.load_state_dict(sd, strict=False)
+        self.stab = Stabilizer()
+        self.have_ref = False
+        self.torch = torch
+
+    def frame(self, frame):
+        """One iteration of /root/reference/geotrax/extract.py:145-197 minus decode and tracker."""
+        from oracle import prepost
+        x = prepost.preprocess([frame], IMGSZ)
+        with self.torch.no_grad():
+            dec, _ = self.model(x)
+        det = prepost.postprocess_detect(dec, x.shape[2:], frame.shape[:2], CONF, IOU, [0, 1, 2, 3], True, 1000)[0]
+        xywh = prepost.xyxy2xywh(det[:, :4]).numpy() if len(det) else None
+        if not self.have_ref:
+            self.stab.set_ref_frame(frame, xywh)
+            self.have_ref = True
+            return det, np.eye(3)
+        self.stab.stabilize(frame, xywh)
+        self.stab.transform_cur_boxes()
+        return det, self.stab.get_cur_trans_matrix()
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from geotrax_b200 import synth, weights
+    cores = os.cpu_count() or 1
+    sd = weights.random_state_dict(4, "detect", seed=0, frame_hw=FRAME_HW, imgsz=IMGSZ, cls_bias=CLS_BIAS)
+    frames = synth.make_flight(3, FRAME_HW[0], FRAME_HW[1], seed=100)[0]
+    cpu = CpuPath(sd, cores)
+    cpu.frame(frames[0])                       # reference frame
+    per_step = 2                               # bounded sample: 2 of the 16 frames of a step
+    for _ in range(args.warmup):
+        cpu.frame(frames[1])
+    t0 = time.perf_counter()
+    for s in range(args.steps):
+        for j in range(per_step):
+            cpu.frame(frames[1 + (s + j) % 2])
+    dt = time.perf_counter() - t0
+    fps = args.steps * per_step / dt
+    line = dict(metric=METRIC, value=fps, unit=UNIT, n_gpus=args.gpus, steps=args.steps, warmup=args.warmup, ms_per_step=1000 * dt / args.steps,
+                higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32", data="synthetic", impl="reference",
+                config=dict(workload="detect+stabilize, 3840x2160 synthetic frames, YOLOv8s nc=4 imgsz 1920, ORB 2000/4000 + BF + MAGSAC++ (default preset)",
+                            frames_per_step=per_step, note="CPU oracle port (fp32 PyTorch + OpenCV), batch 1 like extract.py"),
+                cpu_baseline=dict(value=fps, unit=UNIT, cores=cores, kind="port",
+                                  sample=f"{per_step} frames per step x {args.steps} steps (a full step is {BATCH} frames)"),
+                e2e=dict(value=fps, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0), gpu_launches=0)
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    import geotrax_b200
+    from geotrax_b200 import synth, weights
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dev = torch.device("cuda", local)
+
+    eng = geotrax_b200.Engine(frame_hw=FRAME_HW, imgsz=IMGSZ, nc=4, max_batch=BATCH, device=local, act_dtype=args.dtype)
+    sd = weights.random_state_dict(4, "detect", seed=0, frame_hw=FRAME_HW, imgsz=IMGSZ, cls_bias=CLS_BIAS)
+    eng.load_weights(weights.fold(sd))
+    # this rank's contiguous frame range of the synthetic flight: BATCH distinct frames (cycled), + the shared reference frame
+    flight = synth.make_flight(BATCH, FRAME_HW[0], FRAME_HW[1], seed=100 + rank)
+    frames_np = np.stack(flight[0])
+    ref_np = frames_np[:1].copy()
+    # vehicle masks = the generator's 132 golden-like boxes per frame ("dense vehicle masks", configs[2]); in the reference
+    # they are the tracker's boxes (extract.py:166,181) -- a random-init detector's own boxes are meaningless as masks
+    mask = eng.pack_boxes(flight[1])
+    mask_dev = (torch.from_numpy(mask[0]).to(dev), torch.from_numpy(mask[1]).to(dev))
+    mask_ref = eng.pack_boxes(flight[1][:1])
+    frames_dev = torch.from_numpy(frames_np).to(dev)
+    frames_pin = torch.from_numpy(frames_np).pin_memory()
+    out = eng.alloc_outputs(pinned=True)
+    tstream = torch.cuda.Stream(device=dev)     # every kernel / copy of the path is issued on this stream; events time it
+    torch.cuda.set_stream(tstream)
+    stream = tstream.cuda_stream
+    eng.extract_batch(torch.from_numpy(ref_np).to(dev), first_is_reference=True, conf=CONF, iou=IOU, classes=[0, 1, 2, 3], out=out, stream=stream,
+                      mask_boxes=mask_ref)
+
+    rec = None
+    gathered = None
+    if world > 1:  # fixed-stride per-frame records gathered to rank 0: counts | boxes | H | status
+        rec_len = BATCH * (1 + eng.max_det * 6 + 9 + 1)
+        rec = torch.zeros(rec_len, dtype=torch.float32, device=dev)
+        gathered = [torch.zeros_like(rec) for _ in range(world)] if rank == 0 else None
+
+    def step(src):
+        o = eng.extract_batch(src, conf=CONF, iou=IOU, agnostic=True, classes=[0, 1, 2, 3], out=out, stream=stream,
+                              mask_boxes=mask_dev if src is frames_dev else mask)
+        if world > 1:
+            h = torch.from_numpy(np.concatenate([o["counts"].astype(np.float32).ravel(), o["boxes"].ravel(), o["H"].astype(np.float32).ravel(),
+                                                 o["status"].astype(np.float32).ravel()]))
+            rec.copy_(h, non_blocking=True)
+            dist.gather(rec, gathered, dst=0)
+        return o
+
+    def timed(src, steps):
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        l0 = eng.launch_count()
+        t0 = time.perf_counter()
+        e0.record()
+        stage = np.zeros(4)
+        conv_ms = 0.0
+        for _ in range(steps):
+            step(src)
+            st = eng.stage_times()
+            stage += [st["preprocess"], st["inference"], st["postprocess"], st["stabilize"]]
+            conv_ms += eng.conv_stack_stats()[0]
+        e1.record()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        wall = time.perf_counter() - t0
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms, wall * 1000], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms, wall = float(t[0]), float(t[1]) / 1000
+        return ms, wall, stage / steps, conv_ms / steps, eng.launch_count() - l0
+
+    for _ in range(max(args.warmup, 3)):
+        step(frames_dev)
+    sampler = ClockSampler(local)
+    sampler.start()
+    ms, wall, stage, conv_ms, launches = timed(frames_dev, args.steps)          # inputs resident in HBM
+    clocks = sampler.stop()
+    for _ in range(2):
+        step(frames_pin)
+    ms_e2e, wall_e2e, stage_e2e, _, _ = timed(frames_pin, args.steps)            # pinned host frames: H2D inside the timed region
+    det_counts = out["counts"].copy()
+    ok_h = int((out["status"] == 0).sum())
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    peaks = _peaks()
+    total_frames = world * args.steps * BATCH
+    value = total_frames / (ms / 1000)
+    e2e = total_frames / max(wall_e2e, ms_e2e / 1000)
+    conv_tflops = CONV_GFLOP_PER_FRAME * BATCH / conv_ms  # GFLOP / ms = TFLOP/s
+    h2d = int(frames_np.nbytes)
+    d2h = int(sum(v.nbytes for v in out.values()))
+    h2d += int(mask[0].nbytes + mask[1].nbytes)
+    cpu_base = None
+    if world == 1 and not args.no_cpu_baseline:
+        cores = os.cpu_count() or 1
+        cpu = CpuPath(sd, cores)
+        cpu.frame(ref_np[0])
+        cpu.frame(frames_np[0])
+        n = 6
+        t0 = time.perf_counter()
+        for i in range(n):
+            cpu.frame(frames_np[1 + i % (BATCH - 1)])
+        cdt = time.perf_counter() - t0
+        cpu_base = dict(value=n / cdt, unit=UNIT, cores=cores, kind="port", sample=f"{n} of the step's {BATCH} frames, batch 1, fp32 PyTorch + OpenCV")
+    line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=max(args.warmup, 3), ms_per_step=ms / args.steps,
+                higher_is_better=True, scaling="weak", vs_baseline=None, dtype=args.dtype, data="synthetic",
+                config=dict(workload="detect+stabilize (configs[1]+[2] fused): 16 x 3840x2160 synthetic BGR frames / step, YOLOv8s nc=4 random-init "
+                                     "imgsz 1920 (1088x1920), conf 0.25 iou 0.7 agnostic, ORB 2000/4000 + Hamming 2-NN + 5000-hyp RANSAC, box warp",
+                            frames_per_step=BATCH, parallelism=f"frame-range shard x{world}", l2="inputs (398 MB / step) larger than the 126 MB L2",
+                            stage_ms_per_step=dict(preprocess=stage[0], inference=stage[1], postprocess=stage[2], stabilize=stage[3]),
+                            detections_per_frame=float(det_counts.mean()), mask_boxes_per_frame=float(mask[1].mean()), homographies_ok=f"{ok_h}/{BATCH}",
+                            matches_per_frame=float(out["stats"][:, 2].mean()), inliers_per_frame=float(out["stats"][:, 3].mean())),
+                roofline=dict(bound="tensor", achieved=conv_tflops, peak=peaks["tf_sust"], unit="TFLOP/s", frac=conv_tflops / peaks["tf_sust"], traffic=None,
+                              kernel="conv_tc_kernel x62 + conv0 (the conv stack of one step)", peak_source=peaks["src"] + " bf16_tflops_sustained",
+                              algorithmic_flops_per_launch_set=CONV_GFLOP_PER_FRAME * BATCH * 1e9),
+                cpu_baseline=cpu_base,
+                e2e=dict(value=e2e, unit=UNIT, h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h, ms_per_step=1000 * wall_e2e / args.steps),
+                gpu_launches=int(launches), clocks=clocks)
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--dtype", default="fp16", choices=["fp16", "bf16"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

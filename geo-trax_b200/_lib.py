@@ -9,6 +9,7 @@ LIB_PATH = os.path.join(HERE, "libgeotrax_b200.so")
 
 GT_ABI_VERSION = 1
 GT_TASK_DETECT, GT_TASK_OBB = 0, 1
+GT_ACT_BF16, GT_ACT_FP16 = 0, 1
 GT_MAX_KP = 8192
 GT_ORB_LEVELS = 8
 
@@ -24,7 +25,7 @@ class gt_config(C.Structure):
         ("downsample_ratio", C.c_float), ("max_features", C.c_int32), ("ref_multiplier", C.c_float),
         ("mask_use", C.c_int32), ("mask_margin_ratio", C.c_float), ("filter_ratio", C.c_float),
         ("ransac_threshold", C.c_float), ("ransac_max_iter", C.c_int32), ("query_is_current", C.c_int32),
-        ("ransac_full_res", C.c_int32), ("seed", C.c_uint32), ("reserved", C.c_int32 * 8),
+        ("ransac_full_res", C.c_int32), ("seed", C.c_uint32), ("act_dtype", C.c_int32), ("reserved", C.c_int32 * 7),
     ]
 
 
@@ -62,10 +63,11 @@ SYMBOLS = {
     "gt_orb_level_info": (_i, [_H, _i, _ip, _ip, _ip, _ip]),
     "gt_get_pyramid_level": (_i, [_H, _i, _i, _i, _P, _P]),
     "gt_get_keypoints": (_i, [_H, _i, _i, _i, _P, _P, _ip]),
+    "gt_orb_get_candidates": (_i, [_H, _i, _i, _i, _i, _P, _P, _ip]),
     "gt_orb_detect": (_i, [_H, _P, _P, _i, _i, _P]),
     "gt_match": (_i, [_H, _P, _i, _P, _i, _P, _P, _P]),
     "gt_find_homography": (_i, [_H, _P, _P, _i, _f, _i, _P, _ip, _P]),
-    "gt_extract_batch": (_i, [_H, _P, _i, _i, _f, _f, _i, _u, _P, _P, _P, _P, _P, _P, _P]),
+    "gt_extract_batch": (_i, [_H, _P, _i, _i, _f, _f, _i, _u, _P, _P, _i, _P, _P, _P, _P, _P, _P, _P]),
     "gt_stage_times": (_i, [_H, _P]),
     "gt_launch_count": (C.c_int64, [_H]),
     "gt_conv_stack_stats": (_i, [_H, _P, _P]),

@@ -47,6 +47,7 @@ void gt_default_config(gt_config* c) {
   c->downsample_ratio = 0.5f; c->max_features = 2000; c->ref_multiplier = 2.0f; c->mask_use = 1; c->mask_margin_ratio = 0.15f;
   c->filter_ratio = 0.9f; c->ransac_threshold = 2.0f; c->ransac_max_iter = 5000; c->query_is_current = 1; c->ransac_full_res = 0;
   c->seed = 0x9E3779B9u;
+  c->act_dtype = GT_ACT_FP16;
 }
 
 const char* gt_last_error(gt_handle h) { return h ? h->err.c_str() : g_create_error.c_str(); }
@@ -76,6 +77,7 @@ int gt_create(const gt_config* cfg, int device, gt_handle* out) {
   CRC(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
   for (int i = 0; i < 8; ++i) CRC(cudaEventCreate(&e->ev[i]));
   const gt_config& c = e->cfg;
+  if (c.act_dtype != GT_ACT_BF16 && c.act_dtype != GT_ACT_FP16) { gt_set_error(e, "gt_create: bad act_dtype %d", c.act_dtype); return fail(GT_ERR_INVALID); }
   if (c.max_batch < 1 || c.max_batch > 32 || c.nc < 1 || c.nc > 80 || c.max_det < 1 || c.max_det > 4096) {
     gt_set_error(e, "gt_create: max_batch/nc/max_det out of range"); return fail(GT_ERR_INVALID);
   }
@@ -100,7 +102,7 @@ int gt_create(const gt_config* cfg, int device, gt_handle* out) {
   const int B = c.max_batch;
   CR(e->dev_alloc((void**)&e->frames_dev, (size_t)B * c.frame_h * c.frame_w * 3));
   CR(e->host_alloc((void**)&e->frames_pinned, (size_t)B * c.frame_h * c.frame_w * 3));
-  CR(e->dev_alloc((void**)&e->net_in, (size_t)B * 3 * e->net_h * e->net_w * sizeof(bf16)));
+  CR(e->dev_alloc((void**)&e->net_in, (size_t)B * 3 * e->net_h * e->net_w));
   CR(conv_tc_init(e));
   CR(orb_build(e));      // allocates the pyramid slabs (level 0 = stage-1 gray output)
   CR(detector_build(e));
@@ -187,13 +189,13 @@ int gt_preprocess(gt_handle e, const uint8_t* frames, int B, void* stream) {
   return GT_OK;
 }
 
-int gt_get_net_input(gt_handle e, int B, uint16_t* out, int32_t* net_h, int32_t* net_w) {
+int gt_get_net_input(gt_handle e, int B, uint8_t* out, int32_t* net_h, int32_t* net_w) {
   ENTER(e);
   if (net_h) *net_h = e->net_h;
   if (net_w) *net_w = e->net_w;
   if (out) {
     GT_CUDA(e, cudaStreamSynchronize(e->stream));
-    GT_CUDA(e, cudaMemcpy(out, e->net_in, (size_t)B * 3 * e->net_h * e->net_w * 2, cudaMemcpyDefault));
+    GT_CUDA(e, cudaMemcpy(out, e->net_in, (size_t)B * 3 * e->net_h * e->net_w, cudaMemcpyDefault));
   }
   return GT_OK;
 }
@@ -444,6 +446,22 @@ int gt_get_keypoints(gt_handle e, int which, int b, int max_n, float* out_kp, ui
   return GT_OK;
 }
 
+int gt_orb_get_candidates(gt_handle e, int which, int b, int level, int max_n, uint32_t* out_xy, uint8_t* out_score, int32_t* n) {
+  ENTER(e);
+  GT_CHECK(e, level >= 0 && level < GT_ORB_LEVELS && b >= 0 && b < e->cfg.max_batch && n, "gt_orb_get_candidates: bad index");
+  const int slot = which ? e->cfg.max_batch : b;
+  GT_CUDA(e, cudaStreamSynchronize(e->stream));
+  int cnt = 0;
+  GT_CUDA(e, cudaMemcpy(&cnt, e->fast_count + slot * GT_ORB_LEVELS + level, sizeof(int), cudaMemcpyDefault));
+  cnt = std::min(cnt, e->lv[level].cand_cap);
+  *n = cnt;
+  const int m = std::min(cnt, max_n);
+  const size_t off = (size_t)slot * e->cand_total + e->lv[level].cand_off;
+  if (out_xy && m) GT_CUDA(e, cudaMemcpy(out_xy, e->fast_cand + off, (size_t)m * 4, cudaMemcpyDefault));
+  if (out_score && m) GT_CUDA(e, cudaMemcpy(out_score, e->fast_score + off, (size_t)m, cudaMemcpyDefault));
+  return GT_OK;
+}
+
 int gt_orb_detect(gt_handle e, const uint8_t* gray, const uint8_t* mask, int B, int as_reference, void* stream) {
   ENTER(e);
   GT_CHECK(e, gray && B >= 1 && B <= e->cfg.max_batch && (!as_reference || B == 1), "gt_orb_detect: bad arguments");
@@ -518,8 +536,8 @@ __global__ void dets_to_xywh_kernel(const float* __restrict__ det, const int* __
 }
 
 int gt_extract_batch(gt_handle e, const uint8_t* frames, int B, int first_is_reference, float conf, float iou, int agnostic,
-                     uint32_t classes_mask, float* out_boxes, int32_t* out_counts, float* out_boxes_stab, double* out_H, int32_t* out_status,
-                     int32_t* out_stats, void* stream) {
+                     uint32_t classes_mask, const float* mask_boxes, const int32_t* mask_nboxes, int mask_stride, float* out_boxes,
+                     int32_t* out_counts, float* out_boxes_stab, double* out_H, int32_t* out_status, int32_t* out_stats, void* stream) {
   ENTER(e);
   GT_CHECK(e, frames && B >= 1 && B <= e->cfg.max_batch, "gt_extract_batch: bad batch %d", B);
   cudaStream_t st = pick_stream(e, stream);
@@ -528,8 +546,14 @@ int gt_extract_batch(gt_handle e, const uint8_t* frames, int B, int first_is_ref
   const int md = e->cfg.max_det;
   const int obb = e->cfg.task == GT_TASK_OBB;
   dim3 g((unsigned)ceil_div(md, 256), (unsigned)B);
-  dets_to_xywh_kernel<<<g, 256, 0, st>>>(e->det_out, e->det_count, obb ? 7 : 6, md, e->boxes_dev, e->nboxes_dev, B, obb);
+  dets_to_xywh_kernel<<<g, 256, 0, st>>>(e->det_out, e->det_count, obb ? 7 : 6, md, e->det_xywh_dev, e->det_nbox_dev, B, obb);
   e->launches++;
+  if (mask_boxes && mask_nboxes) {
+    GT_TRY(upload_boxes(e, 0, B, mask_boxes, mask_nboxes, mask_stride, st));
+  } else {
+    GT_CUDA(e, cudaMemcpyAsync(e->boxes_dev, e->det_xywh_dev, (size_t)B * md * 16, cudaMemcpyDeviceToDevice, st));
+    GT_CUDA(e, cudaMemcpyAsync(e->nboxes_dev, e->det_nbox_dev, (size_t)B * sizeof(int), cudaMemcpyDeviceToDevice, st));
+  }
   if (first_is_reference) {
     const int R = e->cfg.max_batch;
     GT_CUDA(e, cudaMemcpyAsync(e->pyr + (size_t)R * e->pyr_bytes, e->pyr, (size_t)e->work_h * e->work_w, cudaMemcpyDeviceToDevice, st));
@@ -539,7 +563,7 @@ int gt_extract_batch(gt_handle e, const uint8_t* frames, int B, int first_is_ref
     e->have_ref = true;
   }
   GT_TRY(stabilize_impl(e, B, st));
-  GT_TRY(warp_boxes_run(e, e->H_dev, e->H_status, e->boxes_dev, e->boxes_stab_dev, e->nboxes_dev, B, md, st));
+  GT_TRY(warp_boxes_run(e, e->H_dev, e->H_status, e->det_xywh_dev, e->boxes_stab_dev, e->det_nbox_dev, B, md, st));
   GT_TRY(copy_dets(e, B, out_boxes, out_counts, nullptr, st));
   GT_TRY(to_caller(e, out_boxes_stab, e->boxes_stab_dev, (size_t)B * md * 16, st));
   GT_TRY(to_caller(e, out_H, e->H_dev, (size_t)B * 9 * sizeof(double), st));

@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -73,7 +74,8 @@ struct ConvParams {
   int stages;
   int cout;               // real output channels
   int act;                // 1 = SiLU
-  int out_f32;            // 1: out is float (raw head), 0: bf16
+  int out_f32;            // 1: out is float (raw head), 0: 16-bit act dtype
+  int fp16;               // 16-bit format: 1 = fp16, 0 = bf16
   void* out;
   long long out_img_stride;  // destination pixels per image
   int out_ctot, out_coff;
@@ -107,3 +109,18 @@ int conv_tc_launch(gt_engine* e, const ConvOp* op, int B, cudaStream_t st);
 
 // ---- small helpers ------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ float silu_f(float x) { return x / (1.0f + __expf(-x)); }
+// 16-bit activation formats: storage type is always a 2-byte word (typedef bf16 in signatures); `fp16` picks the encoding
+__device__ __forceinline__ uint32_t pack2_act(float a, float b, int fp16) {
+  if (fp16) { __half2 v = __floats2half2_rn(a, b); return *reinterpret_cast<uint32_t*>(&v); }
+  __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+__device__ __forceinline__ float2 unpack2_act(uint32_t u, int fp16) {
+  if (fp16) return __half22float2(*reinterpret_cast<__half2*>(&u));
+  return make_float2(__uint_as_float(u << 16), __uint_as_float(u & 0xFFFF0000u));
+}
+static inline uint16_t host_to_act(float f, int fp16) {
+  if (fp16) { __half h = __float2half_rn(f); return *reinterpret_cast<uint16_t*>(&h); }
+  __nv_bfloat16 h = __float2bfloat16_rn(f);
+  return *reinterpret_cast<uint16_t*>(&h);
+}

@@ -73,8 +73,9 @@ __device__ __forceinline__ uint64_t make_sw128_desc(uint32_t saddr) {
 }
 
 // kind::f16 instruction descriptor: D = f32, A = B = bf16, both K-major, M = 128, N = bn.
-__device__ __forceinline__ uint32_t make_idesc(int bn) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+__device__ __forceinline__ uint32_t make_idesc(int bn, int fp16) {
+  const uint32_t fmt = fp16 ? 0u : 1u;  // a/b format: 0 = F16, 1 = BF16
+  return (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
 }
 
 __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
@@ -114,12 +115,6 @@ __device__ __forceinline__ void tmem_ld_x16(uint32_t taddr, uint32_t* v) {
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
-__device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
-  __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
-  return *reinterpret_cast<uint32_t*>(&v);
-}
-__device__ __forceinline__ float bf16lo(uint32_t u) { return __uint_as_float(u << 16); }
-__device__ __forceinline__ float bf16hi(uint32_t u) { return __uint_as_float(u & 0xFFFF0000u); }
 
 // Epilogue for `ncols` (16 or 32) consecutive accumulator columns of one output pixel.
 template <int NC>
@@ -146,20 +141,19 @@ __device__ __forceinline__ void epilogue_chunk(const ConvParams& p, const uint32
     const uint4* r = reinterpret_cast<const uint4*>(p.res + rp * p.res_ctot + p.res_coff + gc0);
 #pragma unroll
     for (int q = 0; q < NC / 8; ++q) {
-      uint4 u = __ldg(r + q);
-      f[q * 8 + 0] += bf16lo(u.x); f[q * 8 + 1] += bf16hi(u.x);
-      f[q * 8 + 2] += bf16lo(u.y); f[q * 8 + 3] += bf16hi(u.y);
-      f[q * 8 + 4] += bf16lo(u.z); f[q * 8 + 5] += bf16hi(u.z);
-      f[q * 8 + 6] += bf16lo(u.w); f[q * 8 + 7] += bf16hi(u.w);
+      const uint4 u = __ldg(r + q);
+      const float2 a0 = unpack2_act(u.x, p.fp16), a1 = unpack2_act(u.y, p.fp16), a2 = unpack2_act(u.z, p.fp16), a3 = unpack2_act(u.w, p.fp16);
+      f[q * 8 + 0] += a0.x; f[q * 8 + 1] += a0.y; f[q * 8 + 2] += a1.x; f[q * 8 + 3] += a1.y;
+      f[q * 8 + 4] += a2.x; f[q * 8 + 5] += a2.y; f[q * 8 + 6] += a3.x; f[q * 8 + 7] += a3.y;
     }
   }
   uint4 pk[NC / 8];
 #pragma unroll
   for (int q = 0; q < NC / 8; ++q) {
-    pk[q].x = pack_bf16x2(f[q * 8 + 0], f[q * 8 + 1]);
-    pk[q].y = pack_bf16x2(f[q * 8 + 2], f[q * 8 + 3]);
-    pk[q].z = pack_bf16x2(f[q * 8 + 4], f[q * 8 + 5]);
-    pk[q].w = pack_bf16x2(f[q * 8 + 6], f[q * 8 + 7]);
+    pk[q].x = pack2_act(f[q * 8 + 0], f[q * 8 + 1], p.fp16);
+    pk[q].y = pack2_act(f[q * 8 + 2], f[q * 8 + 3], p.fp16);
+    pk[q].z = pack2_act(f[q * 8 + 4], f[q * 8 + 5], p.fp16);
+    pk[q].w = pack2_act(f[q * 8 + 6], f[q * 8 + 7], p.fp16);
   }
   uint4* o = reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(p.out) + pix * p.out_ctot + p.out_coff + gc0);
 #pragma unroll
@@ -244,7 +238,7 @@ __global__ void __launch_bounds__(kThreads) conv_tc_kernel(const __grid_constant
   } else if (warp == 1) {
     // ===== MMA issuer (one thread) =====
     if (lane == 0) {
-      const uint32_t idesc = make_idesc(p.BN);
+      const uint32_t idesc = make_idesc(p.BN, p.fp16);
       for (int kb = 0; kb < p.num_kb; ++kb) {
         const int s = kb % p.stages;
         const uint32_t ph = (uint32_t)(kb / p.stages) & 1u;
@@ -359,7 +353,7 @@ int conv_tc_plan(gt_engine* e, ConvOp* op, const View& in, int Bmax, int cin, in
   if (stages > 8) stages = 8;
   if (stages > p.num_kb) stages = p.num_kb < 2 ? 2 : p.num_kb;
   p.stages = stages;
-  p.cout = cout_total; p.act = act;
+  p.cout = cout_total; p.act = act; p.fp16 = e->cfg.act_dtype == GT_ACT_FP16 ? 1 : 0;
   if (out_f32_ptr) {
     p.out_f32 = 1; p.out = out_f32_ptr; p.out_img_stride = out_img_stride; p.out_ctot = out_ctot_f32; p.out_coff = out_coff_f32;
   } else {
@@ -394,7 +388,7 @@ int conv_tc_plan(gt_engine* e, ConvOp* op, const View& in, int Bmax, int cin, in
     cuuint64_t gstr[3] = {(cuuint64_t)in.ctot * 2, (cuuint64_t)in.W * in.ctot * 2, (cuuint64_t)in.H * in.W * in.ctot * 2};
     cuuint32_t box[4] = {64, (cuuint32_t)(p.tw * stride), (cuuint32_t)(p.th * stride), 1};
     cuuint32_t estr[4] = {1, (cuuint32_t)stride, (cuuint32_t)stride, 1};
-    CUresult r = g_encode(&op->tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, (void*)(in.ptr + in.coff), gdim, gstr, box, estr,
+    CUresult r = g_encode(&op->tmA, p.fp16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, (void*)(in.ptr + in.coff), gdim, gstr, box, estr,
                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     GT_CHECK(e, r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(A) failed: %d (C=%d W=%d H=%d ctot=%d box %dx%dx%d s=%d)", (int)r, cin,
@@ -407,7 +401,7 @@ int conv_tc_plan(gt_engine* e, ConvOp* op, const View& in, int Bmax, int cin, in
     cuuint64_t gstr[1] = {ktot * 2};
     cuuint32_t box[2] = {64, (cuuint32_t)p.BN};
     cuuint32_t estr[2] = {1, 1};
-    CUresult r = g_encode(&op->tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (void*)op->w_dev, gdim, gstr, box, estr,
+    CUresult r = g_encode(&op->tmB, p.fp16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (void*)op->w_dev, gdim, gstr, box, estr,
                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     GT_CHECK(e, r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(B) failed: %d (ktot=%llu cout_pad=%d BN=%d)", (int)r,
@@ -419,14 +413,15 @@ int conv_tc_plan(gt_engine* e, ConvOp* op, const View& in, int Bmax, int cin, in
 int conv_tc_pack_weights(gt_engine* e, ConvOp* op, const float* const* w, const float* const* b, const int* couts, int n) {
   const int taps = op->k * op->k;
   const size_t wn = (size_t)op->cout_pad * taps * op->cin_pad;
-  std::vector<bf16> hw(wn, __float2bfloat16(0.f));
+  const int fp16 = op->p.fp16;
+  std::vector<uint16_t> hw(wn, 0);
   std::vector<float> hb(op->cout_pad, 0.f);
   int co0 = 0;
   for (int s = 0; s < n; ++s) {
     for (int co = 0; co < couts[s]; ++co) {
       for (int ci = 0; ci < op->cin; ++ci)
         for (int t = 0; t < taps; ++t)
-          hw[((size_t)(co0 + co) * taps + t) * op->cin_pad + ci] = __float2bfloat16(w[s][((size_t)co * op->cin + ci) * taps + t]);
+          hw[((size_t)(co0 + co) * taps + t) * op->cin_pad + ci] = host_to_act(w[s][((size_t)co * op->cin + ci) * taps + t], fp16);
       hb[co0 + co] = b[s] ? b[s][co] : 0.f;
     }
     co0 += couts[s];

@@ -5,6 +5,7 @@
 // Detect/OBB head + DFL + dist2bbox/dist2rbox, non_max_suppression (torchvision.ops.nms / nms_rotated), scale_boxes.
 #include <algorithm>
 #include <map>
+#include <type_traits>
 
 #include "engine.cuh"
 
@@ -16,7 +17,7 @@ __device__ __forceinline__ uint32_t gray15(uint32_t b, uint32_t g, uint32_t r) {
   return (9798u * r + 19235u * g + 3735u * b + 16384u) >> 15;  // OpenCV BGR2GRAY, 15-bit coefficients
 }
 
-__global__ void __launch_bounds__(256) preprocess_half_kernel(const uint8_t* __restrict__ frames, bf16* __restrict__ net_in,
+__global__ void __launch_bounds__(256) preprocess_half_kernel(const uint8_t* __restrict__ frames, uint8_t* __restrict__ net_in,
                                                               uint8_t* __restrict__ gray, size_t gray_frame_stride, int B,
                                                               int H, int W, int net_h, int net_w, int pad_top, int pad_left,
                                                               int new_h, int new_w) {
@@ -36,8 +37,7 @@ __global__ void __launch_bounds__(256) preprocess_half_kernel(const uint8_t* __r
   }
   const uint8_t* a = reinterpret_cast<const uint8_t*>(r0);
   const uint8_t* c = reinterpret_cast<const uint8_t*>(r1);
-  __align__(16) bf16 pr[8], pg[8], pb[8];
-  __align__(8) uint8_t gy[8];
+  __align__(8) uint8_t pr[8], pg[8], pb[8], gy[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     const int o = j * 6;
@@ -46,38 +46,20 @@ __global__ void __launch_bounds__(256) preprocess_half_kernel(const uint8_t* __r
     const uint32_t bb = (b00 + b01 + b10 + b11 + 2) >> 2;  // cv2.resize INTER_LINEAR at exactly 1/2
     const uint32_t gg = (g00 + g01 + g10 + g11 + 2) >> 2;
     const uint32_t rr = (r00 + r01 + r10 + r11 + 2) >> 2;
-    pr[j] = __float2bfloat16_rn(__fdiv_rn((float)rr, 255.0f));
-    pg[j] = __float2bfloat16_rn(__fdiv_rn((float)gg, 255.0f));
-    pb[j] = __float2bfloat16_rn(__fdiv_rn((float)bb, 255.0f));
+    pr[j] = (uint8_t)rr; pg[j] = (uint8_t)gg; pb[j] = (uint8_t)bb;  // exact; the 1/255 lives in layer 0's f32 weights
     const uint32_t y00 = gray15(b00, g00, r00), y01 = gray15(b01, g01, r01), y10 = gray15(b10, g10, r10), y11 = gray15(b11, g11, r11);
     gy[j] = (uint8_t)((y00 + y01 + y10 + y11 + 2) >> 2);  // gray first, then the 1/2 resize (stabilo order)
   }
   const size_t plane = (size_t)net_h * net_w;
-  bf16* dst = net_in + (size_t)b * 3 * plane + (size_t)(oy + pad_top) * net_w + pad_left + og * 8;
-  *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(pr);
-  *reinterpret_cast<uint4*>(dst + plane) = *reinterpret_cast<const uint4*>(pg);
-  *reinterpret_cast<uint4*>(dst + 2 * plane) = *reinterpret_cast<const uint4*>(pb);
+  uint8_t* dst = net_in + (size_t)b * 3 * plane + (size_t)(oy + pad_top) * net_w + pad_left + og * 8;
+  *reinterpret_cast<uint2*>(dst) = *reinterpret_cast<const uint2*>(pr);
+  *reinterpret_cast<uint2*>(dst + plane) = *reinterpret_cast<const uint2*>(pg);
+  *reinterpret_cast<uint2*>(dst + 2 * plane) = *reinterpret_cast<const uint2*>(pb);
   if (gray) *reinterpret_cast<uint2*>(gray + (size_t)b * gray_frame_stride + (size_t)oy * new_w + og * 8) = *reinterpret_cast<const uint2*>(gy);
 }
 
-// letterbox padding (value 114) for the rows/columns outside the resized image
-__global__ void preprocess_pad_kernel(bf16* __restrict__ net_in, int B, int net_h, int net_w, int pad_top, int pad_left, int new_h,
-                                      int new_w) {
-  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  const long long total = (long long)B * 3 * net_h * net_w;
-  if (idx >= total) return;
-  const int x = (int)(idx % net_w);
-  const int y = (int)((idx / net_w) % net_h);
-  if (y >= pad_top && y < pad_top + new_h && x >= pad_left && x < pad_left + new_w) return;
-  net_in[idx] = __float2bfloat16_rn(__fdiv_rn(114.0f, 255.0f));
-}
-
-int detector_fill_pad(gt_engine* e, cudaStream_t st) {
-  const int B = e->cfg.max_batch;
-  const long long total = (long long)B * 3 * e->net_h * e->net_w;
-  preprocess_pad_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(e->net_in, B, e->net_h, e->net_w, e->pad_top, e->pad_left, e->new_h,
-                                                                         e->new_w);
-  GT_CUDA(e, cudaGetLastError());
+int detector_fill_pad(gt_engine* e, cudaStream_t st) {  // constant letterbox border (value 114); the interior is rewritten per batch
+  GT_CUDA(e, cudaMemsetAsync(e->net_in, 114, (size_t)e->cfg.max_batch * 3 * e->net_h * e->net_w, st));
   return GT_OK;
 }
 
@@ -95,10 +77,11 @@ int detector_preprocess(gt_engine* e, const uint8_t* frames_dev, int B, cudaStre
 
 // =====================================================================================================================
 // Layer 0: Conv(3 -> 32, k3, s2) + folded BN + SiLU on CUDA cores (K = 27 is too thin for the tensor pipe; the layer is
-// HBM-bound: AI 20 FLOP/B).  Planar bf16 in, NHWC bf16 out.  Block = 32 x 8 output pixels.
+// HBM-bound: AI 20 FLOP/B).  Planar u8 in (exact), f32 math with weights pre-scaled by 1/255, NHWC 16-bit out.
+// Block = 32 x 8 output pixels.
 // =====================================================================================================================
-__global__ void __launch_bounds__(256) conv0_kernel(const bf16* __restrict__ in, bf16* __restrict__ out, const float* __restrict__ w,
-                                                    const float* __restrict__ bias, int H, int W, int Ho, int Wo) {
+__global__ void __launch_bounds__(256) conv0_kernel(const uint8_t* __restrict__ in, bf16* __restrict__ out, const float* __restrict__ w,
+                                                    const float* __restrict__ bias, int H, int W, int Ho, int Wo, int fp16) {
   __shared__ float s_in[3][17][66];
   __shared__ __align__(16) float s_w[27][32];
   __shared__ float s_b[32];
@@ -112,7 +95,7 @@ __global__ void __launch_bounds__(256) conv0_kernel(const bf16* __restrict__ in,
     const int r = (i / 65) % 17, cc = i % 65;
     const int iy = 2 * y0 - 1 + r, ix = 2 * x0 - 1 + cc;
     float v = 0.f;
-    if (iy >= 0 && iy < H && ix >= 0 && ix < W) v = __bfloat162float(in[((size_t)b * 3 + cch) * plane + (size_t)iy * W + ix]);
+    if (iy >= 0 && iy < H && ix >= 0 && ix < W) v = (float)in[((size_t)b * 3 + cch) * plane + (size_t)iy * W + ix];
     s_in[cch][r][cc] = v;
   }
   __syncthreads();
@@ -139,9 +122,9 @@ __global__ void __launch_bounds__(256) conv0_kernel(const bf16* __restrict__ in,
         }
       }
   if (ox >= Wo || oy >= Ho) return;
-  __align__(16) bf16 o[32];
+  __align__(16) uint32_t o[16];
 #pragma unroll
-  for (int i = 0; i < 32; ++i) o[i] = __float2bfloat16_rn(silu_f(acc[i]));
+  for (int i = 0; i < 16; ++i) o[i] = pack2_act(silu_f(acc[2 * i]), silu_f(acc[2 * i + 1]), fp16);
   uint4* dst = reinterpret_cast<uint4*>(out + (((size_t)b * Ho + oy) * Wo + ox) * 32);
 #pragma unroll
   for (int q = 0; q < 4; ++q) dst[q] = reinterpret_cast<const uint4*>(o)[q];
@@ -150,6 +133,7 @@ __global__ void __launch_bounds__(256) conv0_kernel(const bf16* __restrict__ in,
 // =====================================================================================================================
 // SPPF max pool 5x5 / stride 1 / pad 2 on a channel slice (NHWC, 8 channels per thread)
 // =====================================================================================================================
+template <typename T2>
 __global__ void __launch_bounds__(256) maxpool5_kernel(const bf16* __restrict__ in, int in_ctot, int in_coff, bf16* __restrict__ out,
                                                        int out_ctot, int out_coff, int B, int H, int W, int C) {
   const int c8 = C >> 3;
@@ -160,8 +144,9 @@ __global__ void __launch_bounds__(256) maxpool5_kernel(const bf16* __restrict__ 
   const int x = (int)((idx / c8) % W);
   const int y = (int)((idx / ((long long)c8 * W)) % H);
   const int b = (int)(idx / ((long long)c8 * W * H));
-  __nv_bfloat162 m[4];
-  const __nv_bfloat162 ninf = __float2bfloat162_rn(-INFINITY);
+  T2 m[4];
+  T2 ninf;
+  if constexpr (sizeof(T2) == 4 && std::is_same<T2, __half2>::value) ninf = __float2half2_rn(-INFINITY); else ninf = __float2bfloat162_rn(-INFINITY);
 #pragma unroll
   for (int i = 0; i < 4; ++i) m[i] = ninf;
   for (int dy = -2; dy <= 2; ++dy) {
@@ -171,7 +156,7 @@ __global__ void __launch_bounds__(256) maxpool5_kernel(const bf16* __restrict__ 
       const int xx = x + dx;
       if (xx < 0 || xx >= W) continue;
       const uint4 v = __ldg(reinterpret_cast<const uint4*>(in + (((size_t)b * H + yy) * W + xx) * in_ctot + in_coff + cg * 8));
-      const __nv_bfloat162* pv = reinterpret_cast<const __nv_bfloat162*>(&v);
+      const T2* pv = reinterpret_cast<const T2*>(&v);
 #pragma unroll
       for (int i = 0; i < 4; ++i) m[i] = __hmax2(m[i], pv[i]);
     }
@@ -222,6 +207,10 @@ __global__ void __launch_bounds__(256) decode_filter_kernel(const float* __restr
   }
   const float conf = sigmoid_f(best);
   if (!(conf > conf_thr)) return;
+  // the reference takes max/argmax over the *probabilities* (cls.sigmoid().max(1)): when the sigmoid saturates, several
+  // classes tie at the same float and the first index wins
+  for (int j = 0; j < bj; ++j)
+    if (sigmoid_f(r[64 + j]) >= conf) { bj = j; break; }
   if (classes_mask && !((classes_mask >> bj) & 1u)) return;
   int lvl = 0;
   if (a >= g.lvl_off[2]) lvl = 2; else if (a >= g.lvl_off[1]) lvl = 1;
@@ -797,7 +786,7 @@ int detector_load_weights(gt_engine* e, const float* const* w, const float* cons
   {
     std::vector<float> hw(27 * 32);
     for (int co = 0; co < 32; ++co)
-      for (int k = 0; k < 27; ++k) hw[k * 32 + co] = w[0][co * 27 + k];
+      for (int k = 0; k < 27; ++k) hw[k * 32 + co] = w[0][co * 27 + k] / 255.0f;  // input is the raw u8 pixel
     GT_CUDA(e, cudaMemcpy(e->conv0_w, hw.data(), hw.size() * sizeof(float), cudaMemcpyHostToDevice));
     GT_CUDA(e, cudaMemcpy(e->conv0_b, b[0], 32 * sizeof(float), cudaMemcpyHostToDevice));
   }
@@ -818,7 +807,7 @@ int detector_forward(gt_engine* e, int B, cudaStream_t st) {
     if (po.type == OP_CONV0) {
       const View& o = e->conv0_out;
       dim3 grid((unsigned)ceil_div(o.W, 32), (unsigned)ceil_div(o.H, 8), (unsigned)B);
-      conv0_kernel<<<grid, 256, 0, st>>>(e->net_in, o.ptr, e->conv0_w, e->conv0_b, e->net_h, e->net_w, o.H, o.W);
+      conv0_kernel<<<grid, 256, 0, st>>>(e->net_in, o.ptr, e->conv0_w, e->conv0_b, e->net_h, e->net_w, o.H, o.W, e->cfg.act_dtype == GT_ACT_FP16);
       e->launches++;
     } else if (po.type == OP_CONV) {
       GT_TRY(conv_tc_launch(e, &e->conv_ops[po.conv], B, st));
@@ -826,7 +815,10 @@ int detector_forward(gt_engine* e, int B, cudaStream_t st) {
       const View& i = po.pool.in;
       const View& o = po.pool.out;
       const long long total = (long long)B * i.H * i.W * (i.C / 8);
-      maxpool5_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(i.ptr, i.ctot, i.coff, o.ptr, o.ctot, o.coff, B, i.H, i.W, i.C);
+      if (e->cfg.act_dtype == GT_ACT_FP16)
+        maxpool5_kernel<__half2><<<(unsigned)((total + 255) / 256), 256, 0, st>>>(i.ptr, i.ctot, i.coff, o.ptr, o.ctot, o.coff, B, i.H, i.W, i.C);
+      else
+        maxpool5_kernel<__nv_bfloat162><<<(unsigned)((total + 255) / 256), 256, 0, st>>>(i.ptr, i.ctot, i.coff, o.ptr, o.ctot, o.coff, B, i.H, i.W, i.C);
       e->launches++;
     }
   }

@@ -50,7 +50,7 @@ struct gt_engine {
   // staging + stage 1
   uint8_t* frames_dev = nullptr;        // [B][H][W][3]
   uint8_t* frames_pinned = nullptr;
-  bf16* net_in = nullptr;               // [B][3][net_h][net_w] planar RGB/255
+  uint8_t* net_in = nullptr;            // [B][3][net_h][net_w] planar RGB u8 (letterboxed, pad 114)
   const uint8_t* cur_frames = nullptr;  // device pointer of the frames of the last gt_preprocess
 
   // detector
@@ -98,6 +98,8 @@ struct gt_engine {
   int* lvl_kp_off = nullptr;                        // [B+1][9]
   float* boxes_dev = nullptr;                       // [B+1][max_det][4]
   int* nboxes_dev = nullptr;                        // [B+1]
+  float* det_xywh_dev = nullptr;                    // [B][max_det][4] detections as xywh (warp input)
+  int* det_nbox_dev = nullptr;                      // [B]
   bool have_ref = false;
   OrbLevel* lv_dev = nullptr;                       // device copy of lv[]
   int* rs_tab[GT_ORB_LEVELS][4] = {};               // per-level resize tables: xofs, xc1, yofs, yc1

@@ -93,20 +93,26 @@ __device__ __forceinline__ int fast_score(const uint8_t (*t)[FT_X + 8], int x, i
     return (a & 0xFFFFu) != 0;
   };
   if (!run9(dark) && !run9(bright)) return 0;
-  // exact corner score: the largest threshold for which the pixel is still a corner
+  // exact corner score: the largest threshold for which the pixel is still a corner = max over the 16 circular 9-arcs of
+  // min(d) (darker arcs) and of min(-d) (brighter arcs), minus 1.  Written as a doubling min-network on d and on an
+  // explicitly negated copy: the straightforward "max(mn, -mx)" form is miscompiled by ptxas 12.9 -O1..-O3 for sm_100a
+  // (wrong VIMNMX3 fusion; repro in tools/scratch/fast_test.cu: 7,325 wrong scores at -O3, 0 at -Xptxas -O0).
+  int nd[16], a2[16], a4[16], a8[16], b2[16], b4[16], b8[16];
+#pragma unroll
+  for (int k = 0; k < 16; ++k) nd[k] = -d[k];
+#pragma unroll
+  for (int k = 0; k < 16; ++k) { a2[k] = min(d[k], d[(k + 1) & 15]); b2[k] = min(nd[k], nd[(k + 1) & 15]); }
+#pragma unroll
+  for (int k = 0; k < 16; ++k) { a4[k] = min(a2[k], a2[(k + 2) & 15]); b4[k] = min(b2[k], b2[(k + 2) & 15]); }
+#pragma unroll
+  for (int k = 0; k < 16; ++k) { a8[k] = min(a4[k], a4[(k + 4) & 15]); b8[k] = min(b4[k], b4[(k + 4) & 15]); }
   int best = 0;
 #pragma unroll
   for (int k = 0; k < 16; ++k) {
-    int mn = d[k], mx = d[k];
-#pragma unroll
-    for (int j = 1; j < 9; ++j) {
-      const int e = d[(k + j) & 15];
-      mn = min(mn, e);
-      mx = max(mx, e);
-    }
-    best = max(best, max(mn, -mx));
+    best = max(best, min(a8[k], d[(k + 8) & 15]));
+    best = max(best, min(b8[k], nd[(k + 8) & 15]));
   }
-  return best - 1;
+  return best > kFastThr ? best - 1 : 0;
 }
 
 __global__ void __launch_bounds__(256) fast_kernel(const uint8_t* __restrict__ img, const uint8_t* __restrict__ msk, size_t slab, int slot0,
@@ -513,6 +519,8 @@ int orb_build(gt_engine* e) {
   GT_TRY(e->dev_alloc((void**)&e->lvl_kp_off, (size_t)S * (GT_ORB_LEVELS + 1) * sizeof(int)));
   GT_TRY(e->dev_alloc((void**)&e->boxes_dev, (size_t)S * e->cfg.max_det * 4 * sizeof(float)));
   GT_TRY(e->dev_alloc((void**)&e->nboxes_dev, (size_t)S * sizeof(int)));
+  GT_TRY(e->dev_alloc((void**)&e->det_xywh_dev, (size_t)S * e->cfg.max_det * 4 * sizeof(float)));
+  GT_TRY(e->dev_alloc((void**)&e->det_nbox_dev, (size_t)S * sizeof(int)));
   GT_CUDA(e, cudaMemset(e->nboxes_dev, 0, (size_t)S * sizeof(int)));
   GT_CUDA(e, cudaMemset(e->kp_count, 0, (size_t)S * sizeof(int)));
   GT_CUDA(e, cudaMemset(e->pyr_mask, 255, (size_t)S * off));

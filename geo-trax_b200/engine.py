@@ -36,12 +36,15 @@ class Engine:
     """One B200's worth of the extract hot path: preprocess -> detect -> stabilize -> warp."""
 
     def __init__(self, frame_hw: Tuple[int, int] = (2160, 3840), imgsz: int = 1920, nc: int = 4, task: str = "detect", max_batch: int = 16,
-                 device: int = 0, max_det: int = 1000, **stab):
+                 device: int = 0, max_det: int = 1000, act_dtype: str = "fp16", **stab):
         self.lib = _lib.load_library()
         cfg = gt_config()
         self.lib.gt_default_config(C.byref(cfg))
         cfg.frame_h, cfg.frame_w, cfg.imgsz, cfg.nc, cfg.max_batch, cfg.max_det = frame_hw[0], frame_hw[1], imgsz, nc, max_batch, max_det
         cfg.task = _lib.GT_TASK_OBB if task == "obb" else _lib.GT_TASK_DETECT
+        assert act_dtype in ("fp16", "bf16")
+        cfg.act_dtype = _lib.GT_ACT_FP16 if act_dtype == "fp16" else _lib.GT_ACT_BF16
+        self.act_dtype = act_dtype
         for k, v in stab.items():
             if not hasattr(cfg, k):
                 raise GtError(f"unknown engine option {k}")
@@ -112,7 +115,7 @@ class Engine:
         return B
 
     def net_input(self, B: int) -> np.ndarray:
-        out = np.empty((B, 3, self.net_h, self.net_w), np.uint16)
+        out = np.empty((B, 3, self.net_h, self.net_w), np.uint8)
         self._ck(self.lib.gt_get_net_input(self.h, B, out.ctypes.data, None, None))
         return out
 
@@ -214,6 +217,15 @@ class Engine:
         self._ck(self.lib.gt_get_keypoints(self.h, which, b, GT_MAX_KP, kp.ctypes.data, desc.ctypes.data, C.byref(n)))
         return kp[: n.value].copy(), desc[: n.value].copy()
 
+    def fast_candidates(self, which: int, b: int, level: int):
+        cap = 1 << 18
+        xy = np.zeros(cap, np.uint32)
+        sc = np.zeros(cap, np.uint8)
+        n = C.c_int32()
+        self._ck(self.lib.gt_orb_get_candidates(self.h, which, b, level, cap, xy.ctypes.data, sc.ctypes.data, C.byref(n)))
+        m = min(n.value, cap)
+        return (xy[:m] & 0xFFFF).astype(np.int32), (xy[:m] >> 16).astype(np.int32), sc[:m].astype(np.int32)
+
     def orb_detect(self, gray: np.ndarray, mask: Optional[np.ndarray] = None, as_reference=False):
         gray = np.ascontiguousarray(gray, np.uint8)
         if gray.ndim == 2:
@@ -249,13 +261,40 @@ class Engine:
             return {k: t.numpy() for k, t in zip(shapes, self._keep)}
         return {k: np.zeros(s, d) for k, (s, d) in shapes.items()}
 
-    def extract_batch(self, frames, first_is_reference=False, conf=0.25, iou=0.7, agnostic=True, classes=None, out=None, stream=None):
+    def pack_boxes(self, boxes: Sequence[Optional[np.ndarray]]):
+        """list of per-frame (n,4) xywh -> ([B][max_det][4] f32, [B] i32) buffers for mask_boxes."""
+        B, md = len(boxes), self.max_det
+        bx, nb = np.zeros((B, md, 4), np.float32), np.zeros((B,), np.int32)
+        for i, b in enumerate(boxes):
+            if b is not None and len(b):
+                nb[i] = min(len(b), md)
+                bx[i, : nb[i]] = np.asarray(b, np.float32)[: nb[i]]
+        return bx, nb
+
+    def extract_batch(self, frames, first_is_reference=False, conf=0.25, iou=0.7, agnostic=True, classes=None, out=None, stream=None,
+                      mask_boxes=None):
+        """mask_boxes: None (mask = own detections) or the (bx, nb) pair from pack_boxes() (numpy or device tensors)."""
         B = int(frames.shape[0])
         o = out or self.alloc_outputs()
+        mb, mn = (mask_boxes if mask_boxes is not None else (None, None))
         self._ck(self.lib.gt_extract_batch(self.h, _ptr(frames), B, int(first_is_reference), conf, iou, int(bool(agnostic)), classes_to_mask(classes),
+                                           _ptr(mb), _ptr(mn), self.max_det,
                                            o["boxes"].ctypes.data, o["counts"].ctypes.data, o["boxes_stab"].ctypes.data, o["H"].ctypes.data,
                                            o["status"].ctypes.data, o["stats"].ctypes.data, stream))
         return o
+
+    # -- 16-bit activation helpers (bit patterns <-> float32) -----------------------------------------------------------------
+    def act_to_f32(self, bits: np.ndarray) -> np.ndarray:
+        if self.act_dtype == "fp16":
+            return bits.view(np.float16).astype(np.float32)
+        return (bits.astype(np.uint32) << 16).view(np.float32)
+
+    def f32_to_act(self, x: np.ndarray) -> np.ndarray:
+        x = np.ascontiguousarray(x, np.float32)
+        if self.act_dtype == "fp16":
+            return x.astype(np.float16).view(np.uint16)
+        u = x.view(np.uint32).astype(np.uint64)
+        return ((u + (((u >> 16) & 1) + 0x7FFF)) >> 16).astype(np.uint16)
 
     def stage_times(self):
         ms = (C.c_float * 4)()

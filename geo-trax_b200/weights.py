@@ -67,7 +67,7 @@ def random_state_dict(nc: int = 4, task: str = "detect", seed: int = 0, cls_bias
         if act:  # Conv = conv(no bias) + BN + SiLU
             sd[name + ".conv.weight"] = w
             sd[name + ".bn.weight"] = 0.8 + 0.4 * torch.rand(cout, generator=g)
-            sd[name + ".bn.bias"] = 0.1 * torch.randn(cout, generator=g)
+            sd[name + ".bn.bias"] = 0.5 + 0.1 * torch.randn(cout, generator=g)  # positive shift keeps SiLU in its well-conditioned range
             sd[name + ".bn.running_mean"] = 0.1 * torch.randn(cout, generator=g)
             sd[name + ".bn.running_var"] = 0.8 + 0.4 * torch.rand(cout, generator=g)
         else:   # plain nn.Conv2d with bias (last conv of each head branch)

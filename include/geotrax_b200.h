@@ -37,6 +37,7 @@ typedef enum {
 } gt_status;
 
 enum { GT_TASK_DETECT = 0, GT_TASK_OBB = 1 };
+enum { GT_ACT_BF16 = 0, GT_ACT_FP16 = 1 };
 
 /* Mirrors the YAML keys the reference splats into the two objects:
  *   ultralytics: block  /root/reference/geotrax/cfg/default.yaml:229-250  (imgsz, conf, iou, max_det, classes, agnostic_nms)
@@ -64,7 +65,8 @@ typedef struct gt_config {
   int32_t query_is_current;    /* 1: knnMatch(query=current, train=reference) */
   int32_t ransac_full_res;     /* 0: threshold applies at working resolution, H conjugated afterwards */
   uint32_t seed;               /* RANSAC sampling seed (deterministic) */
-  int32_t reserved[8];
+  int32_t act_dtype;           /* 16-bit storage format of activations + weights: GT_ACT_BF16 | GT_ACT_FP16 (f32 accumulate) */
+  int32_t reserved[7];
 } gt_config;
 
 void gt_default_config(gt_config* cfg);
@@ -76,7 +78,7 @@ int gt_abi_version(void);
 
 /* ---- detector weights -----------------------------------------------------------------------------------------
  * Host passes BN-folded convolutions in the canonical order returned by gt_conv_count()/gt_conv_info():
- * weight[i] is f32 [cout][cin][k][k] (PyTorch layout), bias[i] f32 [cout].  The library converts to bf16,
+ * weight[i] is f32 [cout][cin][k][k] (PyTorch layout), bias[i] f32 [cout].  The library converts to act_dtype,
  * reorders to [cout][k*k][cin_pad] and uploads.  Replaces ultralytics' AutoBackend + Model.fuse() (extract.py:222). */
 typedef struct gt_conv_desc {
   char    name[48];            /* ultralytics state_dict prefix, e.g. "model.2.m.0.cv1" */
@@ -92,8 +94,9 @@ int gt_load_weights(gt_handle h, const float* const* weights, const float* const
  * frames: u8 [B][frame_h][frame_w][3] BGR.  Replaces LetterBox + BasePredictor.preprocess (extract.py:153) and
  * stabilo's BGR2GRAY + resize front end (extract.py:177,181).  Results stay in the handle's workspaces.        */
 int gt_preprocess(gt_handle h, const uint8_t* frames, int B, void* stream);
-/* debug/parity read-back: bf16 planar RGB [B][3][net_h][net_w] as uint16 and u8 gray [B][work_h][work_w] */
-int gt_get_net_input(gt_handle h, int B, uint16_t* out_bf16, int32_t* net_h, int32_t* net_w);
+/* debug/parity read-back: letterboxed planar RGB u8 [B][3][net_h][net_w] (the 1/255 scale is folded into layer 0's
+ * f32 weights, so the network input is exact) and u8 gray [B][work_h][work_w] */
+int gt_get_net_input(gt_handle h, int B, uint8_t* out_u8, int32_t* net_h, int32_t* net_w);
 int gt_get_gray(gt_handle h, int B, uint8_t* out, int32_t* work_h, int32_t* work_w);
 
 /* ---- stage 2: YOLOv8s forward + DFL decode + confidence filter + NMS ------------------------------------------
@@ -105,7 +108,7 @@ int gt_detect(gt_handle h, int B, float conf, float iou, int agnostic, uint32_t 
               float* out_boxes, int32_t* out_counts, int32_t* out_keep, void* stream);
 /* raw head tensor f32 [B][A][no] (A = anchors, no = 64+nc(+1)), anchor-major; parity gate (1) */
 int gt_get_raw_head(gt_handle h, int B, float* out, int32_t* A, int32_t* no);
-/* any intermediate feature map by ultralytics layer index (0..21): bf16 NHWC as uint16 */
+/* any intermediate feature map by ultralytics layer index (0..21): act_dtype NHWC as uint16 bit patterns */
 int gt_get_feature(gt_handle h, int layer, int B, uint16_t* out, int32_t* C, int32_t* H, int32_t* W);
 
 /* stand-alone NMS on caller-supplied decoded predictions (for bit-exact index parity):
@@ -115,8 +118,8 @@ int gt_nms(gt_handle h, const float* pred, int B, int A, int nc, int rotated, fl
            int32_t* out_keep, void* stream);
 
 /* stand-alone convolution (unit parity of the tcgen05 implicit-GEMM kernel against torch.conv2d):
- * x bf16 NHWC [B][H][W][cin] as uint16, w f32 [cout][cin][k][k], bias f32, optional residual bf16 NHWC;
- * out bf16 NHWC [B][Ho][Wo][cout] (out_f32 != 0: f32).                                                         */
+  * x act_dtype NHWC [B][H][W][cin] as uint16 bits, w f32 [cout][cin][k][k], bias f32, optional residual NHWC;
+ * out act_dtype NHWC [B][Ho][Wo][cout] (out_f32 != 0: f32).                                                       */
 int gt_conv2d(gt_handle h, const uint16_t* x, int B, int H, int W, int cin, const float* w, const float* bias,
               int cout, int k, int stride, int act, const uint16_t* residual, void* out, int out_f32, void* stream);
 
@@ -136,6 +139,8 @@ int gt_orb_level_info(gt_handle h, int level, int32_t* w, int32_t* hgt, int32_t*
 int gt_get_pyramid_level(gt_handle h, int which, int b, int level, uint8_t* out_img, uint8_t* out_mask);
 /* keypoints f32 [n][6] = x, y (level-0 pixel units), size, angle(deg), response, octave; descriptors u8 [n][32]  */
 int gt_get_keypoints(gt_handle h, int which, int b, int max_n, float* out_kp, uint8_t* out_desc, int32_t* n);
+/* FAST candidates of one level after 3x3 NMS + mask + border filter: packed (y << 16 | x) and corner score              */
+int gt_orb_get_candidates(gt_handle h, int which, int b, int level, int max_n, uint32_t* out_xy, uint8_t* out_score, int32_t* n);
 /* run ORB alone on a caller-supplied gray image [B][work_h][work_w] (+ optional masks), into current slots      */
 int gt_orb_detect(gt_handle h, const uint8_t* gray, const uint8_t* mask, int B, int as_reference, void* stream);
 /* stand-alone 2-NN Hamming matcher + ratio test: query [nq][32], train [nt][32] -> per query best/second index/dist */
@@ -146,10 +151,13 @@ int gt_find_homography(gt_handle h, const float* src, const float* dst, int n, f
                        double* out_H, int32_t* out_inliers, void* stream);
 
 /* ---- fused per-batch call used by the shims and bench.py --------------------------------------------------------
- * preprocess -> detect -> (mask = own detections) -> stabilize -> warp.  out_boxes_stab f32 [B][max_det][4] xywh.
- * first_is_reference != 0: frame 0 of this batch becomes the reference (H = identity for it).                  */
+ * preprocess -> detect -> stabilize -> warp the detections.  out_boxes_stab f32 [B][max_det][4] xywh.
+ * mask_boxes (xywh, source-frame pixels, [B][mask_stride][4], mask_nboxes[B]) are the vehicle boxes masked out of the
+ * ORB input -- in the reference they are the tracker's boxes of the same frame (extract.py:166,181); NULL = use this
+ * call's own detections.  first_is_reference != 0: frame 0 of this batch becomes the reference.                 */
 int gt_extract_batch(gt_handle h, const uint8_t* frames, int B, int first_is_reference, float conf, float iou,
-                     int agnostic, uint32_t classes_mask, float* out_boxes, int32_t* out_counts,
+                     int agnostic, uint32_t classes_mask, const float* mask_boxes, const int32_t* mask_nboxes,
+                     int mask_stride, float* out_boxes, int32_t* out_counts,
                      float* out_boxes_stab, double* out_H, int32_t* out_status, int32_t* out_stats, void* stream);
 
 /* ---- instrumentation ---------------------------------------------------------------------------------------------

@@ -28,15 +28,35 @@ def bf16_round(x: np.ndarray) -> np.ndarray:
     return bf16_bits_to_f32(f32_to_bf16_bits(x))
 
 
-@pytest.fixture(scope="session")
-def small_engine():
-    """Engine on a 512x768 frame (imgsz 384 -> net 256x384), batch 2, with seeded random weights."""
+def _make_engine(act_dtype, frame_hw=(512, 768), imgsz=384, **kw):
     import geotrax_b200
     from geotrax_b200 import weights
 
-    eng = geotrax_b200.Engine(frame_hw=(512, 768), imgsz=384, nc=4, max_batch=2, max_det=300, max_features=500)
-    sd = weights.random_state_dict(4, "detect", seed=0, frame_hw=(512, 768), imgsz=384, cls_bias=-4.0)
+    eng = geotrax_b200.Engine(frame_hw=frame_hw, imgsz=imgsz, nc=4, max_batch=2, max_det=300, max_features=500, act_dtype=act_dtype, **kw)
+    sd = weights.random_state_dict(4, "detect", seed=0, frame_hw=frame_hw, imgsz=imgsz, cls_bias=-4.0)
     eng.load_weights(weights.fold(sd))
     eng._sd = sd
+    return eng
+
+
+@pytest.fixture(scope="session")
+def small_engine():
+    """Engine on a 512x768 frame (imgsz 384 -> net 256x384), batch 2, seeded random weights, fp16 activations (default)."""
+    eng = _make_engine("fp16")
+    yield eng
+    eng.close()
+
+
+@pytest.fixture(scope="session")
+def small_engine_bf16():
+    eng = _make_engine("bf16")
+    yield eng
+    eng.close()
+
+
+@pytest.fixture(scope="session")
+def mid_engine():
+    """1024x1536 frame (imgsz 768 -> net 512x768, 8064 anchors): big enough for the > 4096-candidate NMS path."""
+    eng = _make_engine("fp16", frame_hw=(1024, 1536), imgsz=768)
     yield eng
     eng.close()
