@@ -1,0 +1,139 @@
+"""Batched, frame-range-sharded driver of the hot path and the host-side replay that turns its output
+into exactly what /root/reference/geotrax/extract.py:134-214 ``track_with_model`` returns.
+
+One process per GPU.  Rank k owns the contiguous frame range ``frame_ranges(n, world)[k]``; detection is per-frame
+independent and stabilisation is frame-to-REFERENCE (extract.py:176-181), so the only shared state is the reference frame,
+which every rank recomputes locally (deterministic kernels => identical features).  There is no data-path collective; one
+gather of per-frame records (boxes, homography, status) to rank 0 follows, over NCCL on the GPU box (gloo in the CPU tests).
+Rank 0 then replays the sequential host tracker over the frames in order and warps the tracker's boxes with each frame's H.
+"""
+from __future__ import annotations
+
+from typing import Callable, Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+
+
+def frame_ranges(n_frames: int, world: int, start: int = 0) -> List[Tuple[int, int]]:
+    """Contiguous [lo, hi) ranges, sizes differing by at most one, earlier ranks get the longer ones."""
+    base, rem = divmod(max(n_frames, 0), world)
+    out, lo = [], start
+    for r in range(world):
+        n = base + (1 if r < rem else 0)
+        out.append((lo, lo + n))
+        lo += n
+    return out
+
+
+def run_range(engine, get_frames: Callable[[int, int], np.ndarray], lo: int, hi: int, ref_frame_index: int, batch: int = 16, conf: float = 0.25,
+              iou: float = 0.7, agnostic: bool = True, classes: Optional[Sequence[int]] = None, stream=None) -> Dict[str, np.ndarray]:
+    """Runs frames [lo, hi) of a flight through ``engine.extract_batch`` in batches; -> per-frame arrays (see keys below).
+
+    The frame ``ref_frame_index`` (the first processed frame of the whole video, ``cut_frame_left``) is the stabilizer
+    reference: processed first on every rank; its own record is only kept by the rank that owns it."""
+    md, row = engine.max_det, engine.row
+    n = max(hi - lo, 0)
+    res = dict(frame=np.arange(lo, hi, dtype=np.int64), count=np.zeros(n, np.int32), status=np.zeros(n, np.int32), stats=np.zeros((n, 4), np.int32),
+               H=np.zeros((n, 9), np.float64), boxes=np.zeros((n, md, row), np.float32), boxes_stab=np.zeros((n, md, 4), np.float32))
+    ref = engine.extract_batch(get_frames(ref_frame_index, ref_frame_index + 1), first_is_reference=True, conf=conf, iou=iou, agnostic=agnostic,
+                               classes=classes, stream=stream)
+    ref = {k: v.copy() for k, v in ref.items()}
+    out = engine.alloc_outputs()
+    for b0 in range(lo, hi, batch):
+        b1 = min(b0 + batch, hi)
+        o = engine.extract_batch(get_frames(b0, b1), conf=conf, iou=iou, agnostic=agnostic, classes=classes, out=out, stream=stream)
+        s = slice(b0 - lo, b1 - lo)
+        k = b1 - b0
+        res["count"][s], res["status"][s], res["stats"][s], res["H"][s] = o["counts"][:k], o["status"][:k], o["stats"][:k], o["H"][:k]
+        res["boxes"][s], res["boxes_stab"][s] = o["boxes"][:k], o["boxes_stab"][:k]
+    if lo <= ref_frame_index < hi:   # the reference frame maps to itself: identity, boxes unchanged (extract.py:176-179)
+        i = ref_frame_index - lo
+        res["count"][i], res["status"][i], res["stats"][i] = ref["counts"][0], 0, ref["stats"][0]
+        res["H"][i] = np.eye(3).ravel()
+        res["boxes"][i], res["boxes_stab"][i] = ref["boxes"][0], ref["boxes_stab"][0]
+    return res
+
+
+def gather_records(local: Dict[str, np.ndarray], rank: int, world: int, device=None) -> Optional[Dict[str, np.ndarray]]:
+    """Gathers every rank's per-frame records on rank 0 (returns None elsewhere).  Boxes are trimmed to the largest
+    per-frame count over all ranks before they travel (real payload ~3 KB / frame instead of max_det rows)."""
+    if world == 1:
+        return local
+    import torch
+    import torch.distributed as dist
+
+    dev = device if device is not None else torch.device("cpu")
+    n_local = len(local["frame"])
+    meta = torch.tensor([n_local, int(local["count"].max()) if n_local else 0], dtype=torch.int64, device=dev)
+    metas = [torch.zeros_like(meta) for _ in range(world)]
+    dist.all_gather(metas, meta)
+    n_max = max(int(m[0]) for m in metas)
+    c_max = max(1, max(int(m[1]) for m in metas))
+    gathered: Dict[str, np.ndarray] = {}
+    for key, arr in local.items():
+        a = arr[:, :c_max] if key in ("boxes", "boxes_stab") else arr
+        pad = np.zeros((n_max,) + a.shape[1:], a.dtype)
+        pad[:n_local] = a
+        t = torch.from_numpy(np.ascontiguousarray(pad)).view(torch.uint8).to(dev)   # bytes: keeps f64 / i64 exact
+        parts = [torch.zeros_like(t) for _ in range(world)] if rank == 0 else None
+        dist.gather(t, parts, dst=0)
+        if rank == 0:
+            chunks = []
+            for r, p in enumerate(parts):
+                full = p.cpu().numpy().view(a.dtype).reshape((n_max,) + a.shape[1:])
+                chunks.append(full[: int(metas[r][0])])
+            gathered[key] = np.concatenate(chunks, 0)
+    return gathered if rank == 0 else None
+
+
+def replay_tracks(rec: Dict[str, np.ndarray], tracker, warp_boxes: Callable[[np.ndarray, np.ndarray], np.ndarray], ref_frame_index: int,
+                  obb: bool = False) -> Tuple[np.ndarray, np.ndarray]:
+    """Rank 0: sequential tracker over the gathered detections, then the stabilizer's box warp with the stored H.
+
+    -> (tracks (N,12) f32 [frame,id,x,y,w,h,xs,ys,ws,hs,cls,conf], transforms (F,10) f64 [frame, H row-major]) -- the arrays
+    extract.py:273-293 ``aggregate_results`` builds; untracked rows (id -1) are dropped as extract.py:287 does."""
+    import types
+
+    order = np.argsort(rec["frame"], kind="stable")
+    tracks, transforms = [], []
+    for i in order:
+        f, n = int(rec["frame"][i]), int(rec["count"][i])
+        H = rec["H"][i].reshape(3, 3) if int(rec["status"][i]) == 0 else None
+        if f != ref_frame_index and H is not None:
+            transforms.append(np.concatenate([[float(f)], H.ravel()])[None])
+        if n == 0:
+            continue
+        d = rec["boxes"][i, :n]
+        if obb:
+            c, s = np.abs(np.cos(d[:, 4])), np.abs(np.sin(d[:, 4]))
+            hw, hh = (d[:, 2] * c + d[:, 3] * s) / 2, (d[:, 2] * s + d[:, 3] * c) / 2
+            xyxy = np.stack([d[:, 0] - hw, d[:, 1] - hh, d[:, 0] + hw, d[:, 1] + hh], 1)
+            conf, cls = d[:, 5], d[:, 6]
+        else:
+            xyxy, conf, cls = d[:, :4], d[:, 4], d[:, 5]
+        rows = tracker.update(types.SimpleNamespace(xyxy=xyxy, conf=conf, cls=cls), None, None)
+        if len(rows) == 0:
+            continue
+        b = np.asarray(rows[:, :4], np.float32)
+        xywh = np.stack([(b[:, 0] + b[:, 2]) / 2, (b[:, 1] + b[:, 3]) / 2, b[:, 2] - b[:, 0], b[:, 3] - b[:, 1]], 1).astype(np.float32)
+        stab = xywh if (f == ref_frame_index or H is None) else warp_boxes(H, xywh)
+        ids = rows[:, 4].astype(np.uint16).astype(np.float32)          # extract.py:162 casts ids to uint16
+        tracks.append(np.concatenate([np.full((len(b), 1), f, np.float32), ids[:, None], xywh, stab.astype(np.float32),
+                                      rows[:, 6:7].astype(np.uint8).astype(np.float32), rows[:, 5:6].astype(np.float32)], 1))
+    t = np.concatenate(tracks, 0).astype(np.float32) if tracks else np.empty((0, 12), np.float32)
+    t = t[t[:, 1] != -1] if t.size else t
+    tr = np.concatenate(transforms, 0) if transforms else np.empty((0, 10))
+    return t, tr
+
+
+def run_flight(engine, get_frames: Callable[[int, int], np.ndarray], n_frames: int, rank: int = 0, world: int = 1, first_frame: int = 0,
+               batch: int = 16, tracker=None, gather_device=None, **det_kw):
+    """Whole sharded job: local range -> gather -> (rank 0) tracker replay.  Returns (tracks, transforms) on rank 0, else None."""
+    from .tracker import GreedyIoUTracker
+
+    lo, hi = frame_ranges(n_frames, world, first_frame)[rank]
+    local = run_range(engine, get_frames, lo, hi, first_frame, batch=batch, **det_kw)
+    rec = gather_records(local, rank, world, gather_device)
+    if rank != 0:
+        return None
+    return replay_tracks(rec, tracker or GreedyIoUTracker(), engine.warp_boxes, first_frame, obb=(engine.row == 7))

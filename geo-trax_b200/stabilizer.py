@@ -1,0 +1,135 @@
+"""``stabilo.Stabilizer``-shaped front end of the CUDA stabilizer (drop-in for /root/reference/geotrax/extract.py:139,
+177-187 and /root/reference/geotrax/utils/registration.py:59-85).
+
+    stabilizer = Stabilizer(**config['stabilo'])                 # default.yaml:103-145
+    stabilizer.set_ref_frame(frame, boxes_xywh or None)          # first processed frame
+    stabilizer.stabilize(frame, boxes_xywh or None)              # every later frame
+    stabilizer.transform_cur_boxes() -> (n,4) xywh f32           # 4 corners -> H -> envelope (pinned by the golden files)
+    stabilizer.get_cur_trans_matrix() -> (3,3) f64 | None        # current -> reference, full-res px, h33 = 1
+    stabilizer.get_cur_num_keypoints() / get_cur_inliers_count() / get_cur_num_matches()
+
+ORB, matching, RANSAC and the box warp run in libgeotrax_b200.so (gt_set_reference / gt_stabilize / gt_warp_boxes).  Poor
+matches never raise: the matrix is ``None`` (extract.py:185 then skips the transform row).  Unsupported presets raise
+``NotImplementedError`` at construction instead of silently computing something else.
+"""
+from __future__ import annotations
+
+import logging
+from typing import Optional
+
+import numpy as np
+
+from . import session
+from ._lib import GtError
+
+log = logging.getLogger("geotrax_b200")
+
+
+class Stabilizer:
+    def __init__(self, detector_name: str = "orb", matcher_name: str = "bf", filter_type: str = "ratio", transformation_type: str = "projective",
+                 clahe: bool = False, downsample_ratio: float = 0.5, max_features: int = 2000, ref_multiplier: float = 2.0,
+                 mask_use: bool = True, mask_margin_ratio: float = 0.15, filter_ratio: float = 0.9, ransac_method: int = 38,
+                 ransac_epipolar_threshold: float = 2.0, ransac_max_iter: int = 5000, ransac_confidence: float = 0.999999,
+                 match_query_frame: str = "current", gpu: bool = False, viz: bool = False, benchmark: bool = False,
+                 min_good_match_count_warning: int = 20, min_inliers_match_count_warning: int = 10, device=None, **other):
+        # `other` swallows the detector-specific keys of the YAML block that do not apply to ORB
+        # (sift_enable_precise_upscale, rsift_eps, brisk_threshold, kaze_threshold, akaze_threshold)
+        unsupported = []
+        if detector_name != "orb": unsupported.append(f"detector_name={detector_name!r} (orb)")
+        if matcher_name != "bf": unsupported.append(f"matcher_name={matcher_name!r} (bf)")
+        if filter_type != "ratio": unsupported.append(f"filter_type={filter_type!r} (ratio)")
+        if transformation_type != "projective": unsupported.append(f"transformation_type={transformation_type!r} (projective)")
+        if clahe: unsupported.append("clahe=True")
+        if float(downsample_ratio) != 0.5: unsupported.append(f"downsample_ratio={downsample_ratio} (0.5)")
+        if match_query_frame not in ("current", "reference"): unsupported.append(f"match_query_frame={match_query_frame!r}")
+        if unsupported:
+            raise NotImplementedError("B200 stabilizer implements the default preset only; unsupported: " + ", ".join(unsupported))
+        self.cfg = dict(downsample_ratio=float(downsample_ratio), max_features=int(max_features), ref_multiplier=float(ref_multiplier),
+                        mask_use=bool(mask_use), mask_margin_ratio=float(mask_margin_ratio), filter_ratio=float(filter_ratio),
+                        ransac_epipolar_threshold=float(ransac_epipolar_threshold), ransac_max_iter=int(ransac_max_iter),
+                        match_query_frame=match_query_frame)
+        self.ransac_method, self.ransac_confidence = int(ransac_method), float(ransac_confidence)  # the estimator is the library's own
+        self.min_good, self.min_inl = int(min_good_match_count_warning), int(min_inliers_match_count_warning)
+        self.device = session.device_index(device)
+        session.register_stab_cfg(self.cfg)
+        self._eng = None
+        self._H: Optional[np.ndarray] = None
+        self._boxes: Optional[np.ndarray] = None
+        self._stats = np.zeros(4, np.int32)
+        self._have_ref = False
+
+    # -- engine --------------------------------------------------------------------------------------------------------------
+    def _engine_for(self, frame: np.ndarray):
+        if frame.ndim != 3 or frame.shape[2] != 3 or frame.dtype != np.uint8:
+            raise GtError(f"Stabilizer expects a BGR uint8 frame (H,W,3); got {frame.dtype} {frame.shape}")
+        hw = tuple(frame.shape[:2])
+        eng = self._eng
+        if eng is None or (eng.cfg.frame_h, eng.cfg.frame_w) != hw or not eng.h:
+            eng = session.find_for_stabilizer(hw, self.device, self.cfg)
+            if eng is None:
+                eng = session.acquire(hw, None, 4, "detect", self.device, 1, self.cfg)
+            if eng is not self._eng:
+                self._have_ref = False
+            self._eng = eng
+        return eng
+
+    def _upload(self, eng, frame: np.ndarray):
+        tok = session.frame_token(frame)
+        if getattr(eng, "_frame_token", None) != tok:      # the detector shim has not just pre-processed this very frame
+            eng.preprocess(np.ascontiguousarray(frame)[None])
+            eng._frame_token = tok
+
+    @staticmethod
+    def _clean_boxes(boxes) -> Optional[np.ndarray]:
+        if boxes is None:
+            return None
+        b = np.asarray(boxes, np.float32).reshape(-1, 4)
+        return b if len(b) else None
+
+    # -- stabilo surface -----------------------------------------------------------------------------------------------------
+    def set_ref_frame(self, frame: np.ndarray, boxes=None) -> None:
+        eng = self._engine_for(frame)
+        self._upload(eng, frame)
+        b = self._clean_boxes(boxes)
+        eng.set_reference(0, b)
+        self._have_ref = True
+        self._H, self._boxes = None, b
+        self._stats[:] = 0
+
+    def stabilize(self, frame: np.ndarray, boxes=None) -> None:
+        eng = self._engine_for(frame)
+        if not self._have_ref:
+            raise GtError("Stabilizer.stabilize() called before set_ref_frame()")
+        self._upload(eng, frame)
+        b = self._clean_boxes(boxes)
+        H, status, stats = eng.stabilize(1, [b])
+        self._boxes = b
+        self._stats = stats[0].copy()
+        self._H = H[0].copy() if int(status[0]) == 0 else None
+        if self._stats[2] < self.min_good:
+            log.warning("stabilizer: only %d good matches", int(self._stats[2]))
+        if self._H is not None and self._stats[3] < self.min_inl:
+            log.warning("stabilizer: only %d RANSAC inliers", int(self._stats[3]))
+
+    def get_cur_trans_matrix(self) -> Optional[np.ndarray]:
+        return self._H
+
+    def transform_cur_boxes(self) -> Optional[np.ndarray]:
+        if self._boxes is None:
+            return None
+        if self._H is None:
+            return self._boxes.copy()
+        out = np.empty_like(self._boxes)
+        md = self._eng.max_det
+        for i in range(0, len(self._boxes), md):
+            out[i:i + md] = self._eng.warp_boxes(self._H, self._boxes[i:i + md])
+        return out
+
+    def get_cur_num_keypoints(self):
+        return int(self._stats[0]), int(self._stats[1])     # (reference, current)
+
+    def get_cur_inliers_count(self) -> int:
+        return int(self._stats[3])
+
+    def get_cur_num_matches(self) -> int:
+        return int(self._stats[2])

@@ -1,0 +1,261 @@
+"""CPU tests of the host side: result containers, tracker hand-off, shims, weight folding / checkpoint harvesting, frame-range
+sharding and the world_size-2 gather (gloo).  No CUDA call is made here."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+# ---- result containers (ultralytics-shaped) -----------------------------------------------------------------------------
+def test_boxes_surface_as_extract_py_uses_it():
+    from geotrax_b200.results import Boxes, Results
+    rows = torch.tensor([[10.0, 20, 50, 60, 0.9, 1], [0, 0, 4, 8, 0.5, 3]])
+    r = Results(np.zeros((100, 200, 3), np.uint8), names={0: "car"}, boxes=rows, speed={"preprocess": 1.0, "inference": 2.0, "postprocess": 0.5})
+    b = r.boxes
+    assert len(b) == 2 and b.id is None                                           # extract.py:158-164
+    assert b.xywh.detach().numpy(force=True).astype(np.float32).tolist() == [[30, 40, 40, 40], [2, 4, 4, 8]]
+    assert b.cls.detach().numpy(force=True).astype(np.uint8).tolist() == [1, 3]
+    assert sum(r.speed.values()) == 3.5                                           # extract.py:156
+    r.update(boxes=np.array([[10.0, 20, 50, 60, 7, 0.9, 1]], np.float32))         # tracker rows [xyxy, id, conf, cls]
+    assert r.boxes.is_track and r.boxes.id.tolist() == [7.0] and r.boxes.conf.tolist() == [pytest.approx(0.9)]
+    assert len(r[0:1]) == 1 and r.boxes.cpu().numpy().data.shape == (1, 7)
+    assert r.orig_shape == (100, 200)
+
+
+def test_obb_surface():
+    from geotrax_b200.results import OBB
+    o = OBB(torch.tensor([[50.0, 50, 40, 20, 0.0, 0.8, 2]]), (100, 100))
+    assert o.xywhr.shape == (1, 5) and o.id is None and o.cls.tolist() == [2.0]
+    assert torch.allclose(o.xyxy, torch.tensor([[30.0, 40, 70, 60]]))
+    o2 = OBB(torch.tensor([[50.0, 50, 40, 20, np.pi / 2, 0.8, 2]]), (100, 100))
+    assert torch.allclose(o2.xyxy, torch.tensor([[40.0, 30, 60, 70]]), atol=1e-4)
+
+
+# ---- tracker stand-in + replay ----------------------------------------------------------------------------------------------
+def _det(xyxy, conf=None, cls=None):
+    import types
+    xyxy = np.asarray(xyxy, np.float32)
+    n = len(xyxy)
+    return types.SimpleNamespace(xyxy=xyxy, conf=np.full(n, 0.9, np.float32) if conf is None else np.asarray(conf, np.float32),
+                                 cls=np.zeros(n, np.float32) if cls is None else np.asarray(cls, np.float32))
+
+
+def test_greedy_tracker_keeps_ids_across_frames():
+    from geotrax_b200.tracker import GreedyIoUTracker
+    t = GreedyIoUTracker()
+    a = t.update(_det([[0, 0, 10, 10], [100, 100, 120, 110]]))
+    assert a[:, 4].tolist() == [1, 2] and a[:, 7].tolist() == [0, 1]
+    b = t.update(_det([[101, 100, 121, 110], [1, 0, 11, 10], [300, 300, 310, 310]]))
+    assert b[:, 4].tolist() == [2, 1, 3]
+    c = t.update(_det(np.zeros((0, 4))))
+    assert c.shape == (0, 8)
+    d = t.update(_det([[2, 0, 12, 10]]))
+    assert d[:, 4].tolist() == [1]            # survived one missed frame
+
+
+def test_replay_builds_extract_py_arrays():
+    from geotrax_b200 import pipeline
+    from geotrax_b200.tracker import GreedyIoUTracker
+    md = 8
+    rec = dict(frame=np.array([2, 0, 1]), count=np.array([1, 2, 0], np.int32), status=np.array([0, 0, 1], np.int32), stats=np.zeros((3, 4), np.int32),
+               H=np.tile(np.eye(3).ravel(), (3, 1)), boxes=np.zeros((3, md, 6), np.float32), boxes_stab=np.zeros((3, md, 4), np.float32))
+    rec["H"][0, 2] = 5.0                       # frame 2: shift x by +5
+    rec["boxes"][1, :2] = [[0, 0, 10, 10, 0.9, 0], [50, 50, 70, 60, 0.8, 2]]
+    rec["boxes"][0, :1] = [[1, 0, 11, 10, 0.7, 0]]
+    warp = lambda H, b: b + np.array([H[0, 2], H[1, 2], 0, 0], np.float32)
+    tracks, transforms = pipeline.replay_tracks(rec, GreedyIoUTracker(), warp, ref_frame_index=0)
+    assert tracks.dtype == np.float32 and tracks.shape == (3, 12)
+    assert tracks[:, 0].tolist() == [0, 0, 2] and tracks[:, 1].tolist() == [1, 2, 1]
+    assert np.array_equal(tracks[:2, 2:6], tracks[:2, 6:10])                      # reference frame: stab == raw
+    assert tracks[2, 6] == tracks[2, 2] + 5 and tracks[2, 10] == 0 and tracks[2, 11] == pytest.approx(0.7)
+    assert transforms.shape == (1, 10) and transforms[0, 0] == 2                  # frame 1 had no H (status 1) -> no row; frame 0 is the reference
+
+
+def test_frame_ranges_partition():
+    from geotrax_b200.pipeline import frame_ranges
+    assert frame_ranges(27000, 8) == [(i * 3375, (i + 1) * 3375) for i in range(8)]
+    r = frame_ranges(10, 4, start=5)
+    assert r == [(5, 8), (8, 11), (11, 13), (13, 15)]
+    assert frame_ranges(2, 4) == [(0, 1), (1, 2), (2, 2), (2, 2)]                  # ragged: empty tail ranks
+    assert frame_ranges(0, 2) == [(0, 0), (0, 0)]
+
+
+# ---- world_size 2 over gloo: shard -> gather -> replay equals the single-process result ------------------------------------
+class FakeEngine:
+    """Deterministic stand-in for Engine (host-logic test only): detections and H are functions of the frame content."""
+    max_det, row, max_batch = 16, 6, 4
+
+    def __init__(self):
+        self.ref = None
+
+    def alloc_outputs(self):
+        B, md = self.max_batch, self.max_det
+        return dict(boxes=np.zeros((B, md, 6), np.float32), counts=np.zeros(B, np.int32), boxes_stab=np.zeros((B, md, 4), np.float32),
+                    H=np.zeros((B, 9)), status=np.zeros(B, np.int32), stats=np.zeros((B, 4), np.int32))
+
+    def extract_batch(self, frames, first_is_reference=False, out=None, **kw):
+        o = out or self.alloc_outputs()
+        if first_is_reference:
+            self.ref = int(frames[0, 0, 0, 0])
+        for i, f in enumerate(frames):
+            t = int(f[0, 0, 0])                      # the fake frame carries its index
+            n = 1 + t % 3
+            o["counts"][i] = n
+            for j in range(n):
+                o["boxes"][i, j] = [10 * j + t, 5, 10 * j + t + 8, 11, 0.5 + 0.1 * j, j % 2]
+            H = np.eye(3); H[0, 2] = -(t - self.ref)
+            o["H"][i] = H.ravel()
+            o["status"][i] = 0 if t % 5 != 4 else 1
+            o["stats"][i] = [4000, 2000, 1500, 1200]
+            o["boxes_stab"][i, :n, :2] = t
+        return o
+
+    @staticmethod
+    def warp_boxes(H, b):
+        return (b + np.array([H[0, 2], H[1, 2], 0, 0], np.float32)).astype(np.float32)
+
+
+def _get_frames(lo, hi):
+    return np.arange(lo, hi, dtype=np.uint8).reshape(-1, 1, 1, 1) * np.ones((1, 2, 2, 3), np.uint8)
+
+
+def _worker(rank, world, port, n_frames, q):
+    import torch.distributed as dist
+    from geotrax_b200 import pipeline
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    out = pipeline.run_flight(FakeEngine(), _get_frames, n_frames, rank, world, first_frame=0, batch=4)
+    if rank == 0:
+        q.put(out)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("n_frames", [11, 1])
+def test_sharded_gather_equals_single_process(n_frames):
+    import socket
+    import torch.multiprocessing as mp
+    from geotrax_b200 import pipeline
+    single = pipeline.run_flight(FakeEngine(), _get_frames, n_frames, 0, 1, first_frame=0, batch=4)
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, n_frames, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    tracks, transforms = q.get(timeout=120)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert np.array_equal(tracks, single[0]) and np.array_equal(transforms, single[1])
+    assert transforms.dtype == np.float64
+    if n_frames == 11:
+        assert len(transforms) == 8                  # frames 1..10 minus status-1 frames 4 and 9
+        assert set(tracks[:, 0].astype(int)) == set(range(11))
+
+
+# ---- shims -------------------------------------------------------------------------------------------------------------------
+def test_install_shims_resolves_reference_imports():
+    import geotrax_b200
+    saved = {k: sys.modules.get(k) for k in list(sys.modules) if k.split(".")[0] in ("ultralytics", "stabilo")}
+    try:
+        geotrax_b200.install_shims(force=True)
+        from stabilo import Stabilizer
+        from ultralytics import RTDETR, YOLO
+        from ultralytics.utils.checks import check_yolo
+        from ultralytics.utils.files import increment_path
+        assert YOLO is geotrax_b200.YOLO and Stabilizer is geotrax_b200.Stabilizer and callable(check_yolo)
+        assert increment_path("/tmp/definitely_not_there_gt", exist_ok=False).name == "definitely_not_there_gt"
+        ref = "/root/reference"
+        if os.path.isdir(os.path.join(ref, "geotrax")):     # only in the build container; the GPU box has no reference tree
+            sys.path.insert(0, ref)
+            try:
+                import importlib
+                ex = importlib.import_module("geotrax.extract")
+                assert ex.YOLO is geotrax_b200.YOLO and ex.Stabilizer is geotrax_b200.Stabilizer
+            finally:
+                sys.path.remove(ref)
+                for k in [k for k in sys.modules if k == "geotrax" or k.startswith("geotrax.")]:
+                    del sys.modules[k]
+    finally:
+        for k in [k for k in sys.modules if k.split(".")[0] in ("ultralytics", "stabilo")]:
+            del sys.modules[k]
+        sys.modules.update({k: v for k, v in saved.items() if v is not None})
+
+
+def test_increment_path(tmp_path):
+    from geotrax_b200.shims import increment_path
+    p = tmp_path / "exp"
+    p.mkdir()
+    assert increment_path(p).name == "exp2"
+    (tmp_path / "exp2").mkdir()
+    assert increment_path(p).name == "exp3"
+    assert increment_path(p, exist_ok=True) == p
+    f = tmp_path / "r.txt"
+    f.write_text("x")
+    assert increment_path(f).name == "r2.txt"
+
+
+def test_stabilizer_rejects_unsupported_presets():
+    from geotrax_b200 import Stabilizer
+    for kw in (dict(detector_name="sift"), dict(matcher_name="flann"), dict(clahe=True), dict(downsample_ratio=1.0), dict(transformation_type="affine")):
+        with pytest.raises(NotImplementedError):
+            Stabilizer(**kw)
+    s = Stabilizer(rsift_eps=1e-8, brisk_threshold=130, viz=False, benchmark=False, gpu=False)      # the whole default.yaml block is accepted
+    assert s.get_cur_trans_matrix() is None and s.transform_cur_boxes() is None and s.get_cur_num_keypoints() == (0, 0)
+
+
+def test_device_parsing_refuses_cpu():
+    from geotrax_b200 import GtError, session
+    assert session.device_index(None) == 0 and session.device_index("cuda:1") == 1 and session.device_index([2, 3]) == 2 and session.device_index("") == 0
+    with pytest.raises(GtError):
+        session.device_index("cpu")
+
+
+# ---- weights ---------------------------------------------------------------------------------------------------------------------
+def test_fold_equals_conv_bn_eval():
+    from geotrax_b200 import weights
+    sd = weights.random_state_dict(4, "detect", seed=3, calibrate=False)
+    f = weights.fold(sd)
+    assert len(f) == len(weights.conv_specs(4, "detect")) == 63   # 63 convs
+    name = "model.4.m.1.cv2"
+    w, b = f[name]
+    x = torch.randn(1, 64, 9, 11)
+    conv = torch.nn.functional.conv2d(x, sd[name + ".conv.weight"], None, 1, 1)
+    bn = torch.nn.functional.batch_norm(conv, sd[name + ".bn.running_mean"], sd[name + ".bn.running_var"], sd[name + ".bn.weight"],
+                                        sd[name + ".bn.bias"], False, 0.0, 1e-3)
+    got = torch.nn.functional.conv2d(x, torch.from_numpy(w), torch.from_numpy(b), 1, 1)
+    assert torch.allclose(got, bn, atol=1e-4, rtol=1e-4)
+    assert f["model.22.cv3.0.2"][0].shape == (4, 128, 1, 1)
+
+
+def test_conv_specs_obb_adds_cv4():
+    from geotrax_b200 import weights
+    names = [s[0] for s in weights.conv_specs(4, "obb")]
+    assert len(names) == 63 + 9 and "model.22.cv4.2.2" in names
+
+
+def test_load_pt_harvests_pickled_model_without_ultralytics(tmp_path):
+    """An ultralytics checkpoint pickles the whole module tree; the restricted unpickler must recover its state_dict."""
+    from geotrax_b200 import weights
+    from oracle.yolov8 import YOLOv8
+    m = YOLOv8(4).half()
+    m.names = {0: "car", 1: "bus", 2: "truck", 3: "motorcycle"}
+    m.yaml = {"nc": 4, "yaml_file": "yolov8s.yaml"}
+    p = tmp_path / "fake.pt"
+    torch.save({"model": m, "ema": None, "epoch": -1}, p)
+    sd, names, task, nc = weights.load_pt(str(p))
+    assert task == "detect" and nc == 4 and names[2] == "truck"
+    ref = m.state_dict()
+    assert set(k for k in ref) <= set(sd) | {"model.22.dfl.conv.weight"}
+    k = "model.6.m.0.cv1.conv.weight"
+    assert torch.equal(sd[k], ref[k].float())
+    folded = weights.fold(sd)
+    assert folded["model.0"][0].shape == (32, 3, 3, 3)
