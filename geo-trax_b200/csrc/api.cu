@@ -91,7 +91,7 @@ int gt_create(const gt_config* cfg, int device, gt_handle* out) {
   const int pad_bot = round_half_even(dh + 0.1), pad_right = round_half_even(dw + 0.1);
   e->net_h = e->new_h + e->pad_top + pad_bot;
   e->net_w = e->new_w + e->pad_left + pad_right;
-  if (r != 0.5 || (c.frame_w % 16) || (c.frame_h % 2) || (e->net_h % 32) || (e->net_w % 32) || (e->pad_left % 8)) {
+  if (r != 0.5 || (c.frame_w % 16) || (c.frame_h % 4) || (e->net_h % 32) || (e->net_w % 32) || (e->pad_left % 8) || (e->pad_top % 2)) {
     gt_set_error(e, "gt_create: only the exact 1/2 letterbox (imgsz = max(frame)/2, width %% 16 == 0) is implemented; got %dx%d imgsz %d",
                  c.frame_w, c.frame_h, c.imgsz);
     return fail(GT_ERR_INVALID);
@@ -102,7 +102,6 @@ int gt_create(const gt_config* cfg, int device, gt_handle* out) {
   const int B = c.max_batch;
   CR(e->dev_alloc((void**)&e->frames_dev, (size_t)B * c.frame_h * c.frame_w * 3));
   CR(e->host_alloc((void**)&e->frames_pinned, (size_t)B * c.frame_h * c.frame_w * 3));
-  CR(e->dev_alloc((void**)&e->net_in, (size_t)B * 3 * e->net_h * e->net_w));
   CR(conv_tc_init(e));
   CR(orb_build(e));      // allocates the pyramid slabs (level 0 = stage-1 gray output)
   CR(detector_build(e));
@@ -193,9 +192,28 @@ int gt_get_net_input(gt_handle e, int B, uint8_t* out, int32_t* net_h, int32_t* 
   ENTER(e);
   if (net_h) *net_h = e->net_h;
   if (net_w) *net_w = e->net_w;
-  if (out) {
+  if (out) {  // debug read-back: space-to-depth 16-bit tensor -> planar RGB u8
+    GT_CHECK(e, B >= 1 && B <= e->cfg.max_batch, "gt_get_net_input: bad batch %d", B);
     GT_CUDA(e, cudaStreamSynchronize(e->stream));
-    GT_CUDA(e, cudaMemcpy(out, e->net_in, (size_t)B * 3 * e->net_h * e->net_w, cudaMemcpyDefault));
+    const int sh = e->net_h / 2, sw = e->net_w / 2;
+    std::vector<uint16_t> h((size_t)B * sh * sw * 16);
+    GT_CUDA(e, cudaMemcpy(h.data(), e->net_s2d, h.size() * 2, cudaMemcpyDefault));
+    const bool fp16 = e->cfg.act_dtype == GT_ACT_FP16;
+    const size_t plane = (size_t)e->net_h * e->net_w;
+    for (int b = 0; b < B; ++b)
+      for (int sy = 0; sy < sh; ++sy)
+        for (int sx = 0; sx < sw; ++sx) {
+          const uint16_t* px = &h[(((size_t)b * sh + sy) * sw + sx) * 16];
+          for (int r = 0; r < 2; ++r)
+            for (int c = 0; c < 2; ++c)
+              for (int ch = 0; ch < 3; ++ch) {
+                const uint16_t bits = px[(r * 2 + c) * 4 + ch];
+                float f;
+                if (fp16) { __half hv; memcpy(&hv, &bits, 2); f = __half2float(hv); }
+                else { uint32_t u = (uint32_t)bits << 16; memcpy(&f, &u, 4); }
+                out[((size_t)b * 3 + ch) * plane + (size_t)(2 * sy + r) * e->net_w + 2 * sx + c] = (uint8_t)(f + 0.5f);
+              }
+        }
   }
   return GT_OK;
 }
@@ -326,8 +344,12 @@ int gt_conv2d(gt_handle e, const uint16_t* x, int B, int H, int W, int cin, cons
       rv.ptr = dres;
     }
     ConvOp op;
-    rc = conv_tc_plan(e, &op, in, B, cin, cout, k, stride, act, out_f32 ? nullptr : &ov, out_f32 ? (float*)dout : nullptr,
-                      (long long)Ho * Wo, cout, 0, residual ? &rv : nullptr, nullptr);
+    ConvPlanArgs pa;
+    pa.in = in; pa.Bmax = B; pa.cin = cin; pa.cout = cout; pa.k = k; pa.stride = stride; pa.act = act;
+    if (out_f32) { pa.out_f32 = (float*)dout; pa.out_img_stride = (long long)Ho * Wo; pa.out_ctot_f32 = cout; pa.out_coff_f32 = 0; }
+    else pa.out = &ov;
+    pa.res = residual ? &rv : nullptr;
+    rc = conv_tc_plan(e, &op, pa);
     if (rc != GT_OK) break;
     const float* ws[1] = {w};
     const float* bs[1] = {bias};

@@ -63,19 +63,25 @@ struct View {
 
 // ---- tcgen05 implicit-GEMM convolution ------------------------------------------------------------------------------
 struct ConvParams {
-  int B, H, W;            // output spatial dims
+  int B, H, W;            // images in this launch, output spatial dims
+  int img0;               // first image of this launch (tiles address images img0 .. img0 + B - 1)
   int tw, th;             // spatial tile (tw*th == 128 GEMM rows)
   int tiles_x, tiles_y;
   int stride, ksize, pad;
-  int kc_blocks;          // ceil(cin / 64)
+  int kb_elems;           // channels per k-block: 64 (SWIZZLE_128B rows) or 16 (SWIZZLE_32B rows)
+  int kc_blocks;          // ceil(cin / kb_elems)
   int num_kb;             // ksize*ksize*kc_blocks
   int BN;                 // GEMM N tile (<= 256, multiple of 16)
-  int tmem_cols;          // power of two >= max(32, BN)
+  int n_tiles;            // N tiles (cout_pad / BN)
+  int total_tiles;        // tiles_x * tiles_y * B * n_tiles
+  int tmem_cols;          // power of two >= max(32, 2*BN): two accumulators
+  int acc_stride;         // TMEM column offset of the second accumulator
   int stages;
   int cout;               // real output channels
   int act;                // 1 = SiLU
   int out_f32;            // 1: out is float (raw head), 0: 16-bit act dtype
   int fp16;               // 16-bit format: 1 = fp16, 0 = bf16
+  float scale;            // accumulator scale applied before the bias (1/255 for layer 0, else 1)
   void* out;
   long long out_img_stride;  // destination pixels per image
   int out_ctot, out_coff;
@@ -89,26 +95,41 @@ struct ConvParams {
 struct ConvOp {
   CUtensorMap tmA, tmB;
   ConvParams p;
-  dim3 grid;
   size_t smem = 0;
   bf16* w_dev = nullptr;     // [cout_pad][taps][cin_pad]
   float* b_dev = nullptr;    // [cout_pad]
   int cin = 0, cout = 0, cout_pad = 0, cin_pad = 0, k = 1, stride = 1;
   int n_src = 0;             // 1..3 canonical convs fused along cout
   int src[3] = {0, 0, 0};    // canonical conv indices
-  double flops = 0;
+  double flops = 0;          // per image
+  double bytes = 0;          // algorithmic HBM bytes per image (unfused: input + output (+ residual))
+};
+
+struct ConvPlanArgs {
+  View in;
+  int Bmax = 1;
+  int cin = 0, cout = 0, k = 1, stride = 1, act = 1;
+  int pad = -1;              // -1: k / 2
+  int Ho = -1, Wo = -1;      // -1: derived from the input dims
+  int kb_elems = 64;
+  float scale = 1.0f;
+  const View* out = nullptr;   // 16-bit NHWC destination slice, or
+  float* out_f32 = nullptr;    // fp32 rows [img][pixel][out_ctot_f32] at column out_coff_f32
+  long long out_img_stride = 0;
+  int out_ctot_f32 = 0, out_coff_f32 = 0;
+  const View* res = nullptr;
+  const View* up = nullptr;
 };
 
 int conv_tc_init(gt_engine* e);  // resolves cuTensorMapEncodeTiled, sets kernel attributes
-// builds tensor maps + launch geometry; in/out views may be channel slices.  out_f32_ptr != null -> fp32 raw-head store
-int conv_tc_plan(gt_engine* e, ConvOp* op, const View& in, int Bmax, int cin, int cout_total, int k, int stride, int act,
-                 const View* out, float* out_f32_ptr, long long out_img_stride, int out_ctot_f32, int out_coff_f32,
-                 const View* res, const View* up);
+int conv_tc_plan(gt_engine* e, ConvOp* op, const ConvPlanArgs& a);  // tensor maps + launch geometry + weight storage
 int conv_tc_pack_weights(gt_engine* e, ConvOp* op, const float* const* w, const float* const* b, const int* couts, int n);
+int conv_tc_upload_packed(gt_engine* e, ConvOp* op, const uint16_t* packed, const float* bias);
 int conv_tc_launch(gt_engine* e, const ConvOp* op, int B, cudaStream_t st);
+int conv_tc_launch_range(gt_engine* e, const ConvOp* op, int b0, int nb, cudaStream_t st);
 
 // ---- small helpers ------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ float silu_f(float x) { return x / (1.0f + __expf(-x)); }
+__device__ __forceinline__ float silu_f(float x) { return __fdividef(x, 1.0f + __expf(-x)); }  // MUFU.EX2 + MUFU.RCP
 // 16-bit activation formats: storage type is always a 2-byte word (typedef bf16 in signatures); `fp16` picks the encoding
 __device__ __forceinline__ uint32_t pack2_act(float a, float b, int fp16) {
   if (fp16) { __half2 v = __floats2half2_rn(a, b); return *reinterpret_cast<uint32_t*>(&v); }

@@ -1,20 +1,24 @@
-// bf16 implicit-GEMM convolution on tcgen05 / TMEM, operands staged by TMA (sm_100a).
+// 16-bit implicit-GEMM convolution on tcgen05 / TMEM, operands staged by TMA (sm_100a).  Persistent, warp-specialised.
 //
 // Replaces torch.nn.Conv2d + folded BatchNorm + SiLU of the fused YOLOv8s graph that the reference reaches through
 // ultralytics (/root/reference/geotrax/extract.py:153; layer table SURVEY.md section 8a-4).
 //
 // Mapping: GEMM M = 128 output pixels (a tw x th spatial patch of one image), N = BN output channels (<= 256),
-// K = taps x cin in blocks of 64 channels.  For each (tap, channel-block) the A tile is ONE 4-D TMA box
-// {64 ch, tw*s, th*s, 1} of the NHWC input shifted by the tap offset -- out-of-image rows/columns are zero-filled by
-// the TMA unit (the convolution's zero padding), the conv stride is the tensor map's elementStrides, and the box lands
-// in shared memory as 128 rows x 128 B, which is exactly the K-major SWIZZLE_128B layout tcgen05.mma consumes.  No
-// im2col buffer exists anywhere.  B tiles are {64, BN} boxes of the packed weights [cout][tap][cin_pad].
-// Accumulators live in TMEM (128 lanes x BN fp32 columns); the epilogue reads them with tcgen05.ld and applies
-// bias + SiLU (+ residual) and writes bf16 NHWC straight into a channel slice of the consumer's concat buffer
-// (optionally also a 2x nearest-upsampled copy), or fp32 rows of the raw head tensor.
+// K = taps x cin in k-blocks of `kb_elems` channels (64 -> 128-byte rows, SWIZZLE_128B; 16 -> 32-byte rows, SWIZZLE_32B,
+// used by layer 0 on its space-to-depth input).  For each (tap, channel-block) the A tile is ONE 4-D TMA box
+// {kb_elems ch, tw*s, th*s, 1} of the NHWC input shifted by the tap offset -- out-of-image rows/columns are zero-filled
+// by the TMA unit (the convolution's zero padding), the conv stride is the tensor map's elementStrides, and the box
+// lands in shared memory as 128 rows of one k-block, which is exactly the K-major swizzled layout tcgen05.mma consumes.
+// No im2col buffer exists anywhere.  B tiles are {kb_elems, BN} boxes of the packed weights [cout][tap][cin_pad].
 //
-// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + single-thread MMA issuer,
-// warps 2..5 = epilogue (TMEM lane quarter = warp_idx % 4).
+// One CTA per SM loops over its tiles (tile = blockIdx.x, += gridDim.x).  Three pipelines run concurrently:
+//   warp 0      TMA producer    : shared-memory ring (full/empty mbarriers) that keeps flowing across tile boundaries
+//   warp 1      MMA issuer      : one thread issues tcgen05.mma into one of TWO TMEM accumulators (tmem full/empty mbarriers)
+//   warps 2..9  epilogue        : tcgen05.ld the other accumulator, scale + bias + SiLU (+ residual), 16-bit NHWC stores
+//                                 straight into a channel slice of the consumer's concat buffer (optionally also a 2x
+//                                 nearest-upsampled copy), or fp32 rows of the raw head tensor
+// so the epilogue of tile i overlaps the loads and MMAs of tile i+1 and the per-CTA prologue (barrier init, TMEM
+// allocation, descriptor prefetch) is paid once per SM instead of once per tile.
 #include "engine.cuh"
 
 namespace {
@@ -23,9 +27,11 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 EncodeTiledFn g_encode = nullptr;
+int g_num_sms = GT_NUM_SMS;
 
-constexpr int kThreads = 192;
-constexpr int kABytes = 128 * 128;  // 128 rows x 64 bf16
+constexpr int kEpiWarps = 8;
+constexpr int kThreads = 64 + kEpiWarps * 32;  // 320
+constexpr int kMaxStages = 12;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -34,6 +40,9 @@ __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
 }
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   asm volatile(
@@ -61,18 +70,19 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* tm,
       : "memory");
 }
 
-// K-major, SWIZZLE_128B shared-memory operand descriptor (sm_100 UMMA format): start>>4 | SBO(1024 B)>>4 @32 |
-// version 1 @46 | layout SWIZZLE_128B (2) @61.  LBO is unused for swizzled K-major operands.
-__device__ __forceinline__ uint64_t make_sw128_desc(uint32_t saddr) {
+// K-major swizzled shared-memory operand descriptor (sm_100 UMMA format): start>>4 | SBO>>4 @32 | version 1 @46 |
+// layout type @61 (2 = SWIZZLE_128B with SBO 1024 B, 6 = SWIZZLE_32B with SBO 256 B: 8 rows of one swizzle atom).
+// LBO is unused for swizzled K-major operands.
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t sbo_bytes, uint32_t layout) {
   uint64_t d = 0;
   d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
-  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)(sbo_bytes >> 4) << 32;
   d |= (uint64_t)1 << 46;
-  d |= (uint64_t)2 << 61;
+  d |= (uint64_t)layout << 61;
   return d;
 }
 
-// kind::f16 instruction descriptor: D = f32, A = B = bf16, both K-major, M = 128, N = bn.
+// kind::f16 instruction descriptor: D = f32, A = B = bf16 or f16, both K-major, M = 128, N = bn.
 __device__ __forceinline__ uint32_t make_idesc(int bn, int fp16) {
   const uint32_t fmt = fp16 ? 0u : 1u;  // a/b format: 0 = F16, 1 = BF16
   return (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
@@ -115,25 +125,24 @@ __device__ __forceinline__ void tmem_ld_x16(uint32_t taddr, uint32_t* v) {
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
-
-// Epilogue for `ncols` (16 or 32) consecutive accumulator columns of one output pixel.
+// Epilogue for NC (16 or 32) consecutive accumulator columns of one output pixel.
 template <int NC>
-__device__ __forceinline__ void epilogue_chunk(const ConvParams& p, const uint32_t* v, const float* s_bias, int col0, int n0,
-                                               bool valid, int n, int y, int x) {
-  if (!valid) return;
-  const int gc0 = n0 + col0;  // first global output channel of this chunk
-  if (gc0 >= p.cout) return;
+__device__ __forceinline__ void epilogue_chunk(const ConvParams& p, const uint32_t* v, const float* s_bias, int gc0, bool valid, int n,
+                                               int y, int x) {
+  if (!valid || gc0 >= p.cout) return;
   float f[NC];
 #pragma unroll
   for (int i = 0; i < NC; ++i) {
-    float a = __uint_as_float(v[i]) + s_bias[col0 + i];
+    const float a = fmaf(__uint_as_float(v[i]), p.scale, s_bias[gc0 + i]);
     f[i] = p.act ? silu_f(a) : a;
   }
   const long long pix = (long long)n * p.out_img_stride + (long long)y * p.W + x;
   if (p.out_f32) {
     float* o = reinterpret_cast<float*>(p.out) + pix * p.out_ctot + p.out_coff + gc0;
-    const int nv = min(NC, p.cout - gc0);
-    for (int i = 0; i < nv; ++i) o[i] = f[i];
+    const int nv = p.cout - gc0;
+#pragma unroll
+    for (int i = 0; i < NC; ++i)
+      if (i < nv) o[i] = f[i];
     return;
   }
   if (p.res) {
@@ -170,30 +179,41 @@ __device__ __forceinline__ void epilogue_chunk(const ConvParams& p, const uint32
   }
 }
 
-__global__ void __launch_bounds__(kThreads) conv_tc_kernel(const __grid_constant__ CUtensorMap tmA,
-                                                           const __grid_constant__ CUtensorMap tmB, const ConvParams p) {
+struct TileCoord { int n, y0, x0, n0; };
+__device__ __forceinline__ TileCoord decode_tile(const ConvParams& p, int tile) {
+  TileCoord t;
+  const int nt = tile % p.n_tiles;
+  const int m = tile / p.n_tiles;
+  const int tx = m % p.tiles_x;
+  const int r = m / p.tiles_x;
+  const int ty = r % p.tiles_y;
+  t.n = r / p.tiles_y + p.img0;
+  t.x0 = tx * p.tw;
+  t.y0 = ty * p.th;
+  t.n0 = nt * p.BN;
+  return t;
+}
+
+__global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_constant__ CUtensorMap tmA,
+                                                              const __grid_constant__ CUtensorMap tmB, const ConvParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  // carve: 1024-aligned tiles first, then barriers / tmem pointer / bias
+  // carve: 1024-aligned operand ring first, then barriers / tmem pointer / bias
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  const int b_bytes = p.BN * 128;
-  const int stage_bytes = kABytes + b_bytes;
+  const int row_bytes = p.kb_elems * 2;
+  const int a_bytes = 128 * row_bytes;
+  const int b_bytes = p.BN * row_bytes;
+  const int stage_bytes = a_bytes + b_bytes;
   uint8_t* tail = smem + (size_t)p.stages * stage_bytes;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(tail);
-  uint64_t* empty_bar = full_bar + p.stages;
-  uint64_t* tmem_full_bar = empty_bar + p.stages;
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+  uint64_t* empty_bar = full_bar + kMaxStages;
+  uint64_t* tfull_bar = empty_bar + kMaxStages;   // [2] accumulator ready
+  uint64_t* tempty_bar = tfull_bar + 2;           // [2] accumulator drained
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tempty_bar + 2);
   float* s_bias = reinterpret_cast<float*>(tmem_ptr_smem + 2);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-
-  // tile coordinates
-  const int m = blockIdx.x;
-  const int tx = m % p.tiles_x;
-  const int ty = (m / p.tiles_x) % p.tiles_y;
-  const int n = m / (p.tiles_x * p.tiles_y);
-  const int x0 = tx * p.tw, y0 = ty * p.th;
-  const int n0 = blockIdx.y * p.BN;
+  const int total_tiles = p.total_tiles;
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
@@ -202,7 +222,10 @@ __global__ void __launch_bounds__(kThreads) conv_tc_kernel(const __grid_constant
       mbar_init(smem_u32(&full_bar[s]), 1);
       mbar_init(smem_u32(&empty_bar[s]), 1);
     }
-    mbar_init(smem_u32(tmem_full_bar), 1);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(smem_u32(&tfull_bar[s]), 1);
+      mbar_init(smem_u32(&tempty_bar[s]), kEpiWarps);
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -211,7 +234,8 @@ __global__ void __launch_bounds__(kThreads) conv_tc_kernel(const __grid_constant
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   if (warp >= 2) {
-    for (int i = threadIdx.x - 64; i < p.BN; i += 128) s_bias[i] = p.bias[n0 + i];
+    const int nb = p.n_tiles * p.BN;
+    for (int i = threadIdx.x - 64; i < nb; i += kEpiWarps * 32) s_bias[i] = p.bias[i];
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
@@ -222,62 +246,87 @@ __global__ void __launch_bounds__(kThreads) conv_tc_kernel(const __grid_constant
     // ===== TMA producer =====
     if (lane == 0) {
       const uint32_t tx_bytes = (uint32_t)stage_bytes;
-      for (int kb = 0; kb < p.num_kb; ++kb) {
-        const int s = kb % p.stages;
-        const uint32_t ph = (uint32_t)(kb / p.stages) & 1u;
-        mbar_wait(smem_u32(&empty_bar[s]), ph ^ 1u);
-        const uint32_t fb = smem_u32(&full_bar[s]);
-        mbar_expect_tx(fb, tx_bytes);
-        const int tap = kb / p.kc_blocks, kc = kb - tap * p.kc_blocks;
-        const int dy = tap / p.ksize, dx = tap - dy * p.ksize;
-        uint8_t* sa = smem + (size_t)s * stage_bytes;
-        tma_load_4d(smem_u32(sa), &tmA, fb, kc * 64, x0 * p.stride + dx - p.pad, y0 * p.stride + dy - p.pad, n);
-        tma_load_2d(smem_u32(sa + kABytes), &tmB, fb, kb * 64, n0);
+      uint32_t it = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const TileCoord t = decode_tile(p, tile);
+        const int cx = t.x0 * p.stride - p.pad, cy = t.y0 * p.stride - p.pad;
+        for (int kb = 0; kb < p.num_kb; ++kb, ++it) {
+          const uint32_t s = it % (uint32_t)p.stages;
+          const uint32_t ph = (it / (uint32_t)p.stages) & 1u;
+          mbar_wait(smem_u32(&empty_bar[s]), ph ^ 1u);
+          const uint32_t fb = smem_u32(&full_bar[s]);
+          mbar_expect_tx(fb, tx_bytes);
+          const int tap = kb / p.kc_blocks, kc = kb - tap * p.kc_blocks;
+          const int dy = tap / p.ksize, dx = tap - dy * p.ksize;
+          uint8_t* sa = smem + (size_t)s * stage_bytes;
+          tma_load_4d(smem_u32(sa), &tmA, fb, kc * p.kb_elems, cx + dx, cy + dy, t.n);
+          tma_load_2d(smem_u32(sa + a_bytes), &tmB, fb, kb * p.kb_elems, t.n0);
+        }
       }
     }
   } else if (warp == 1) {
     // ===== MMA issuer (one thread) =====
     if (lane == 0) {
       const uint32_t idesc = make_idesc(p.BN, p.fp16);
-      for (int kb = 0; kb < p.num_kb; ++kb) {
-        const int s = kb % p.stages;
-        const uint32_t ph = (uint32_t)(kb / p.stages) & 1u;
-        mbar_wait(smem_u32(&full_bar[s]), ph);
+      const bool sw128 = p.kb_elems == 64;
+      const uint32_t sbo = sw128 ? 1024u : 256u, layout = sw128 ? 2u : 6u;
+      const int mma_per_kb = p.kb_elems >> 4;
+      uint32_t it = 0, li = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++li) {
+        const uint32_t as = li & 1u;
+        mbar_wait(smem_u32(&tempty_bar[as]), ((li >> 1) & 1u) ^ 1u);   // epilogue has drained this accumulator
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        uint8_t* sa = smem + (size_t)s * stage_bytes;
-        const uint64_t adesc = make_sw128_desc(smem_u32(sa));
-        const uint64_t bdesc = make_sw128_desc(smem_u32(sa + kABytes));
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          // advance 16 bf16 = 32 B along K inside the 128-B swizzle atom: +2 in the (>>4) start-address field
-          umma_f16(tmem_base, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kb | k) ? 1u : 0u);
+        const uint32_t tacc = tmem_base + as * (uint32_t)p.acc_stride;
+        for (int kb = 0; kb < p.num_kb; ++kb, ++it) {
+          const uint32_t s = it % (uint32_t)p.stages;
+          const uint32_t ph = (it / (uint32_t)p.stages) & 1u;
+          mbar_wait(smem_u32(&full_bar[s]), ph);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          uint8_t* sa = smem + (size_t)s * stage_bytes;
+          const uint64_t adesc = make_desc(smem_u32(sa), sbo, layout);
+          const uint64_t bdesc = make_desc(smem_u32(sa + a_bytes), sbo, layout);
+          for (int k = 0; k < mma_per_kb; ++k) {
+            // advance 16 elements = 32 B along K inside the 128-B swizzle atom: +2 in the (>>4) start-address field
+            umma_f16(tacc, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kb | k) ? 1u : 0u);
+          }
+          umma_commit(smem_u32(&empty_bar[s]));  // frees this smem stage when the MMAs above retire
         }
-        umma_commit(smem_u32(&empty_bar[s]));  // frees this smem stage when the MMAs above retire
+        umma_commit(smem_u32(&tfull_bar[as]));   // accumulator complete
       }
-      umma_commit(smem_u32(tmem_full_bar));    // accumulator complete
     }
   } else {
-    // ===== epilogue: TMEM -> registers -> bias/SiLU/residual -> global =====
-    const int q = warp & 3;  // TMEM lane quarter this warp may touch
+    // ===== epilogue: TMEM -> registers -> scale/bias/SiLU/residual -> global =====
+    const int q = warp & 3;             // TMEM lane quarter this warp may touch (warp id % 4)
+    const int half = (warp - 2) >> 2;   // two warps share a quarter and alternate 32-column chunks
     const int row = q * 32 + lane;
     const int ly = row / p.tw, lx = row - ly * p.tw;
-    const int y = y0 + ly, x = x0 + lx;
-    const bool valid = (y < p.H) && (x < p.W) && (n < p.B);
-    mbar_wait(smem_u32(tmem_full_bar), 0);
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
-    int c0 = 0;
-    for (; c0 + 32 <= p.BN; c0 += 32) {
-      uint32_t v[32];
-      tmem_ld_x32(trow + (uint32_t)c0, v);
-      tmem_ld_wait();
-      epilogue_chunk<32>(p, v, s_bias, c0, n0, valid, n, y, x);
-    }
-    if (c0 < p.BN) {
-      uint32_t v[16];
-      tmem_ld_x16(trow + (uint32_t)c0, v);
-      tmem_ld_wait();
-      epilogue_chunk<16>(p, v, s_bias, c0, n0, valid, n, y, x);
+    uint32_t li = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++li) {
+      const uint32_t as = li & 1u;
+      const TileCoord t = decode_tile(p, tile);
+      const int y = t.y0 + ly, x = t.x0 + lx;
+      const bool valid = (y < p.H) && (x < p.W);
+      mbar_wait(smem_u32(&tfull_bar[as]), (li >> 1) & 1u);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + as * (uint32_t)p.acc_stride;
+      int ci = 0;
+      for (int c0 = 0; c0 < p.BN; c0 += 32, ++ci) {
+        if ((ci & 1) != half) continue;
+        if (c0 + 32 <= p.BN) {
+          uint32_t v[32];
+          tmem_ld_x32(trow + (uint32_t)c0, v);
+          tmem_ld_wait();
+          epilogue_chunk<32>(p, v, s_bias, t.n0 + c0, valid, t.n, y, x);
+        } else {
+          uint32_t v[16];
+          tmem_ld_x16(trow + (uint32_t)c0, v);
+          tmem_ld_wait();
+          epilogue_chunk<16>(p, v, s_bias, t.n0 + c0, valid, t.n, y, x);
+        }
+      }
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&tempty_bar[as]));
     }
   }
 
@@ -289,8 +338,8 @@ __global__ void __launch_bounds__(kThreads) conv_tc_kernel(const __grid_constant
   }
 }
 
-size_t conv_smem_bytes(int stages, int bn) {
-  return 1024 /*alignment slack*/ + (size_t)stages * (kABytes + bn * 128) + (2 * stages + 1) * 8 + 8 + (size_t)bn * 4 + 16;
+size_t conv_smem_bytes(int stages, int stage_bytes, int bias_floats) {
+  return 1024 /*alignment slack*/ + (size_t)stages * stage_bytes + (2 * kMaxStages + 4) * 8 + 8 + (size_t)bias_floats * 4 + 16;
 }
 
 }  // namespace
@@ -303,6 +352,9 @@ int conv_tc_init(gt_engine* e) {
     GT_CHECK(e, fn != nullptr && qres == cudaDriverEntryPointSuccess, "cuTensorMapEncodeTiled not available in this driver");
     g_encode = reinterpret_cast<EncodeTiledFn>(fn);
   }
+  cudaDeviceProp prop;
+  GT_CUDA(e, cudaGetDeviceProperties(&prop, e->device));
+  g_num_sms = prop.multiProcessorCount;
   GT_CUDA(e, cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
   return GT_OK;
 }
@@ -322,57 +374,67 @@ static void pick_tile(int H, int W, int* tw, int* th) {
   }
 }
 
-int conv_tc_plan(gt_engine* e, ConvOp* op, const View& in, int Bmax, int cin, int cout_total, int k, int stride, int act,
-                 const View* out, float* out_f32_ptr, long long out_img_stride, int out_ctot_f32, int out_coff_f32,
-                 const View* res, const View* up) {
+int conv_tc_plan(gt_engine* e, ConvOp* op, const ConvPlanArgs& a) {
   GT_CHECK(e, g_encode != nullptr, "conv_tc_init not called");
+  const View& in = a.in;
+  const int cin = a.cin, k = a.k, stride = a.stride, kbe = a.kb_elems;
   GT_CHECK(e, in.C == cin, "conv plan: input view has %d channels, conv expects %d", in.C, cin);
   GT_CHECK(e, (in.ctot % 8) == 0 && (in.coff % 8) == 0, "conv plan: input slice must be 16-byte aligned");
-  GT_CHECK(e, k == 1 || k == 3, "conv plan: k=%d unsupported", k);
+  GT_CHECK(e, k >= 1 && k <= 3, "conv plan: k=%d unsupported", k);
   GT_CHECK(e, stride == 1 || stride == 2, "conv plan: stride=%d unsupported", stride);
+  GT_CHECK(e, kbe == 64 || kbe == 16, "conv plan: kb_elems=%d unsupported", kbe);
   ConvParams& p = op->p;
   memset(&p, 0, sizeof(p));
-  const int pad = k / 2;
-  const int Ho = (in.H + 2 * pad - k) / stride + 1, Wo = (in.W + 2 * pad - k) / stride + 1;
+  const int pad = a.pad >= 0 ? a.pad : k / 2;
+  const int Ho = a.Ho > 0 ? a.Ho : (in.H + 2 * pad - k) / stride + 1, Wo = a.Wo > 0 ? a.Wo : (in.W + 2 * pad - k) / stride + 1;
+  const int cout_total = a.cout;
   op->cin = cin; op->cout = cout_total; op->k = k; op->stride = stride;
-  p.B = Bmax; p.H = Ho; p.W = Wo;
+  p.B = a.Bmax; p.H = Ho; p.W = Wo;
   pick_tile(Ho, Wo, &p.tw, &p.th);
   p.tiles_x = ceil_div(Wo, p.tw); p.tiles_y = ceil_div(Ho, p.th);
   p.stride = stride; p.ksize = k; p.pad = pad;
-  p.kc_blocks = ceil_div(cin, 64);
-  op->cin_pad = p.kc_blocks * 64;
+  p.kb_elems = kbe;
+  p.kc_blocks = ceil_div(cin, kbe);
+  op->cin_pad = p.kc_blocks * kbe;
   p.num_kb = k * k * p.kc_blocks;
   const int cout16 = ceil_div(cout_total, 16) * 16;
   p.BN = cout16 <= 256 ? cout16 : 256;
-  const int n_tiles = ceil_div(cout16, p.BN);
-  op->cout_pad = n_tiles * p.BN;
+  p.n_tiles = ceil_div(cout16, p.BN);
+  op->cout_pad = p.n_tiles * p.BN;
+  // two accumulators of BN fp32 columns each; the allocation is a power of two >= 32 columns
   p.tmem_cols = 32;
-  while (p.tmem_cols < p.BN) p.tmem_cols *= 2;
-  const int stage_bytes = kABytes + p.BN * 128;
-  int stages = p.BN <= 128 ? (100 * 1024) / stage_bytes : (200 * 1024) / stage_bytes;  // <=128: two CTAs per SM
-  if (stages > 8) stages = 8;
-  if (stages > p.num_kb) stages = p.num_kb < 2 ? 2 : p.num_kb;
+  while (p.tmem_cols < 2 * p.BN) p.tmem_cols *= 2;
+  p.acc_stride = p.tmem_cols / 2;
+  const int stage_bytes = (128 + p.BN) * kbe * 2;
+  const size_t fixed = conv_smem_bytes(0, stage_bytes, op->cout_pad);
+  int stages = (int)((227 * 1024 - fixed) / stage_bytes);
+  if (stages > kMaxStages) stages = kMaxStages;
+  GT_CHECK(e, stages >= 2, "conv plan: tile does not fit shared memory (BN=%d)", p.BN);
   p.stages = stages;
-  p.cout = cout_total; p.act = act; p.fp16 = e->cfg.act_dtype == GT_ACT_FP16 ? 1 : 0;
-  if (out_f32_ptr) {
-    p.out_f32 = 1; p.out = out_f32_ptr; p.out_img_stride = out_img_stride; p.out_ctot = out_ctot_f32; p.out_coff = out_coff_f32;
+  p.cout = cout_total; p.act = a.act; p.fp16 = e->cfg.act_dtype == GT_ACT_FP16 ? 1 : 0;
+  p.scale = a.scale;
+  if (a.out_f32) {
+    p.out_f32 = 1; p.out = a.out_f32; p.out_img_stride = a.out_img_stride; p.out_ctot = a.out_ctot_f32; p.out_coff = a.out_coff_f32;
   } else {
+    const View* out = a.out;
     GT_CHECK(e, out && out->H == Ho && out->W == Wo && out->C == cout_total, "conv plan: output view mismatch (%dx%dx%d vs %dx%dx%d)",
              out ? out->H : -1, out ? out->W : -1, out ? out->C : -1, Ho, Wo, cout_total);
     GT_CHECK(e, (out->ctot % 8) == 0 && (out->coff % 8) == 0 && (cout_total % 8) == 0, "conv plan: output slice must be 16-byte aligned");
     p.out_f32 = 0; p.out = out->ptr; p.out_img_stride = (long long)Ho * Wo; p.out_ctot = out->ctot; p.out_coff = out->coff;
   }
-  if (res) {
-    GT_CHECK(e, res->H == Ho && res->W == Wo && res->C == cout_total && !out_f32_ptr, "conv plan: residual view mismatch");
-    p.res = res->ptr; p.res_ctot = res->ctot; p.res_coff = res->coff;
+  if (a.res) {
+    GT_CHECK(e, a.res->H == Ho && a.res->W == Wo && a.res->C == cout_total && !a.out_f32, "conv plan: residual view mismatch");
+    p.res = a.res->ptr; p.res_ctot = a.res->ctot; p.res_coff = a.res->coff;
   }
-  if (up) {
-    GT_CHECK(e, up->H == 2 * Ho && up->W == 2 * Wo && up->C == cout_total && !out_f32_ptr, "conv plan: upsample view mismatch");
-    p.up = up->ptr; p.up_ctot = up->ctot; p.up_coff = up->coff;
+  if (a.up) {
+    GT_CHECK(e, a.up->H == 2 * Ho && a.up->W == 2 * Wo && a.up->C == cout_total && !a.out_f32, "conv plan: upsample view mismatch");
+    p.up = a.up->ptr; p.up_ctot = a.up->ctot; p.up_coff = a.up->coff;
   }
-  op->grid = dim3((unsigned)(p.tiles_x * p.tiles_y * Bmax), (unsigned)n_tiles, 1);
-  op->smem = conv_smem_bytes(p.stages, p.BN);
+  op->smem = conv_smem_bytes(p.stages, stage_bytes, op->cout_pad);
   op->flops = 2.0 * Ho * Wo * (double)cout_total * cin * k * k;
+  // algorithmic HBM bytes per image: input slice + output (+ residual, + upsampled copy) + weights (once per launch, ignored)
+  op->bytes = (double)in.H * in.W * cin * 2 + (double)Ho * Wo * cout_total * (a.out_f32 ? 4 : 2) * (a.up ? 5 : 1) +
+              (a.res ? (double)Ho * Wo * cout_total * 2 : 0.0);
 
   // weights + bias storage
   const size_t wn = (size_t)op->cout_pad * k * k * op->cin_pad;
@@ -382,34 +444,35 @@ int conv_tc_plan(gt_engine* e, ConvOp* op, const View& in, int Bmax, int cin, in
   GT_CUDA(e, cudaMemset(op->b_dev, 0, (size_t)op->cout_pad * sizeof(float)));
   p.bias = op->b_dev;
 
+  const CUtensorMapDataType dt = p.fp16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+  const CUtensorMapSwizzle sw = kbe == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_32B;
   // A: NHWC input slice as a 4-D tensor {C, W, H, N}
   {
-    cuuint64_t gdim[4] = {(cuuint64_t)cin, (cuuint64_t)in.W, (cuuint64_t)in.H, (cuuint64_t)Bmax};
+    cuuint64_t gdim[4] = {(cuuint64_t)cin, (cuuint64_t)in.W, (cuuint64_t)in.H, (cuuint64_t)a.Bmax};
     cuuint64_t gstr[3] = {(cuuint64_t)in.ctot * 2, (cuuint64_t)in.W * in.ctot * 2, (cuuint64_t)in.H * in.W * in.ctot * 2};
-    cuuint32_t box[4] = {64, (cuuint32_t)(p.tw * stride), (cuuint32_t)(p.th * stride), 1};
+    cuuint32_t box[4] = {(cuuint32_t)kbe, (cuuint32_t)(p.tw * stride), (cuuint32_t)(p.th * stride), 1};
     cuuint32_t estr[4] = {1, (cuuint32_t)stride, (cuuint32_t)stride, 1};
-    CUresult r = g_encode(&op->tmA, p.fp16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, (void*)(in.ptr + in.coff), gdim, gstr, box, estr,
-                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    CUresult r = g_encode(&op->tmA, dt, 4, (void*)(in.ptr + in.coff), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+                          CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     GT_CHECK(e, r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(A) failed: %d (C=%d W=%d H=%d ctot=%d box %dx%dx%d s=%d)", (int)r, cin,
-             in.W, in.H, in.ctot, 64, p.tw * stride, p.th * stride, stride);
+             in.W, in.H, in.ctot, kbe, p.tw * stride, p.th * stride, stride);
   }
   // B: packed weights as a 2-D tensor {Ktot, cout_pad}
   {
     const cuuint64_t ktot = (cuuint64_t)k * k * op->cin_pad;
     cuuint64_t gdim[2] = {ktot, (cuuint64_t)op->cout_pad};
     cuuint64_t gstr[1] = {ktot * 2};
-    cuuint32_t box[2] = {64, (cuuint32_t)p.BN};
+    cuuint32_t box[2] = {(cuuint32_t)kbe, (cuuint32_t)p.BN};
     cuuint32_t estr[2] = {1, 1};
-    CUresult r = g_encode(&op->tmB, p.fp16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (void*)op->w_dev, gdim, gstr, box, estr,
-                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    CUresult r = g_encode(&op->tmB, dt, 2, (void*)op->w_dev, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+                          CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     GT_CHECK(e, r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(B) failed: %d (ktot=%llu cout_pad=%d BN=%d)", (int)r,
              (unsigned long long)ktot, op->cout_pad, p.BN);
   }
   return GT_OK;
 }
 
+// w[s]: f32 [couts[s]][cin][k][k] (PyTorch layout); several convs reading the same input are stacked along cout
 int conv_tc_pack_weights(gt_engine* e, ConvOp* op, const float* const* w, const float* const* b, const int* couts, int n) {
   const int taps = op->k * op->k;
   const size_t wn = (size_t)op->cout_pad * taps * op->cin_pad;
@@ -427,15 +490,26 @@ int conv_tc_pack_weights(gt_engine* e, ConvOp* op, const float* const* w, const 
     co0 += couts[s];
   }
   GT_CHECK(e, co0 == op->cout, "pack weights: cout mismatch %d vs %d", co0, op->cout);
-  GT_CUDA(e, cudaMemcpy(op->w_dev, hw.data(), wn * sizeof(bf16), cudaMemcpyHostToDevice));
-  GT_CUDA(e, cudaMemcpy(op->b_dev, hb.data(), hb.size() * sizeof(float), cudaMemcpyHostToDevice));
+  return conv_tc_upload_packed(e, op, hw.data(), hb.data());
+}
+
+// packed: 16-bit [cout_pad][taps][cin_pad] already in the activation format; bias f32 [cout_pad]
+int conv_tc_upload_packed(gt_engine* e, ConvOp* op, const uint16_t* packed, const float* bias) {
+  const size_t wn = (size_t)op->cout_pad * op->k * op->k * op->cin_pad;
+  GT_CUDA(e, cudaMemcpy(op->w_dev, packed, wn * sizeof(bf16), cudaMemcpyHostToDevice));
+  GT_CUDA(e, cudaMemcpy(op->b_dev, bias, (size_t)op->cout_pad * sizeof(float), cudaMemcpyHostToDevice));
   return GT_OK;
 }
 
-int conv_tc_launch(gt_engine* e, const ConvOp* op, int B, cudaStream_t st) {
+int conv_tc_launch(gt_engine* e, const ConvOp* op, int B, cudaStream_t st) { return conv_tc_launch_range(e, op, 0, B, st); }
+
+// images [b0, b0 + nb) of the batch the op was planned for (tensor maps cover Bmax images; tiles are offset by b0)
+int conv_tc_launch_range(gt_engine* e, const ConvOp* op, int b0, int nb, cudaStream_t st) {
   ConvParams p = op->p;
-  p.B = B;
-  dim3 grid((unsigned)(p.tiles_x * p.tiles_y * B), op->grid.y, 1);
+  p.B = nb;
+  p.img0 = b0;
+  p.total_tiles = p.tiles_x * p.tiles_y * nb * p.n_tiles;
+  const int grid = p.total_tiles < g_num_sms ? p.total_tiles : g_num_sms;
   conv_tc_kernel<<<grid, kThreads, op->smem, st>>>(op->tmA, op->tmB, p);
   e->launches++;
   GT_CUDA(e, cudaGetLastError());

@@ -10,124 +10,95 @@
 #include "engine.cuh"
 
 // =====================================================================================================================
-// Stage 1: fused letterbox (exact 1/2 decimation) + BGR->RGB + /255 -> planar bf16, and BGR2GRAY + 1/2 resize -> u8.
-// One thread: 8 output pixels = 2 rows x 48 B of the source (three 128-bit loads per row).
+// Stage 1: fused letterbox (exact 1/2 decimation) + BGR->RGB -> 16-bit space-to-depth NHWC tensor for layer 0, and
+// BGR2GRAY + 1/2 resize -> u8 (level 0 of the ORB pyramid).  One pass over the 24.9 MB frame feeds stages 2 and 3.
+//
+// Network input layout: [B][net_h/2][net_w/2][16], channel = (row parity * 2 + column parity) * 4 + {R, G, B, 0}; values are
+// the exact u8 pixel (0..255 is exact in fp16 and bf16) -- the 1/255 of BasePredictor.preprocess is layer 0's epilogue
+// scale.  With this layout the stride-2 3x3 layer-0 convolution is a stride-1 2x2 convolution over 16 channels, which the
+// tcgen05 implicit-GEMM kernel consumes directly through TMA (32-byte rows, SWIZZLE_32B).
+// One thread: 2 output rows x 8 output pixels = 4 source rows x 48 B (three 128-bit loads per row) -> one 128-byte line.
 // =====================================================================================================================
 __device__ __forceinline__ uint32_t gray15(uint32_t b, uint32_t g, uint32_t r) {
   return (9798u * r + 19235u * g + 3735u * b + 16384u) >> 15;  // OpenCV BGR2GRAY, 15-bit coefficients
 }
 
-__global__ void __launch_bounds__(256) preprocess_half_kernel(const uint8_t* __restrict__ frames, uint8_t* __restrict__ net_in,
+__global__ void __launch_bounds__(256) preprocess_half_kernel(const uint8_t* __restrict__ frames, bf16* __restrict__ s2d,
                                                               uint8_t* __restrict__ gray, size_t gray_frame_stride, int B,
                                                               int H, int W, int net_h, int net_w, int pad_top, int pad_left,
-                                                              int new_h, int new_w) {
+                                                              int new_h, int new_w, int fp16) {
   const int groups = new_w >> 3;  // 8 output pixels per thread
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  const long long per_frame = (long long)new_h * groups;
+  const long long per_frame = (long long)(new_h >> 1) * groups;
   if (idx >= per_frame * B) return;
   const int b = (int)(idx / per_frame);
   const int rem = (int)(idx - (long long)b * per_frame);
-  const int oy = rem / groups, og = rem - oy * groups;
-  const uint8_t* src = frames + ((size_t)b * H + 2 * oy) * (size_t)W * 3 + (size_t)og * 48;
-  uint4 r0[3], r1[3];
+  const int oy2 = rem / groups, og = rem - oy2 * groups;
+  const uint8_t* src = frames + ((size_t)b * H + 4 * oy2) * (size_t)W * 3 + (size_t)og * 48;
+  __align__(16) uint32_t line[32];  // 4 s2d pixels x 16 channels x 16 bit
+  __align__(8) uint8_t gy[2][8];
 #pragma unroll
-  for (int i = 0; i < 3; ++i) {
-    r0[i] = __ldg(reinterpret_cast<const uint4*>(src) + i);
-    r1[i] = __ldg(reinterpret_cast<const uint4*>(src + (size_t)W * 3) + i);
-  }
-  const uint8_t* a = reinterpret_cast<const uint8_t*>(r0);
-  const uint8_t* c = reinterpret_cast<const uint8_t*>(r1);
-  __align__(8) uint8_t pr[8], pg[8], pb[8], gy[8];
+  for (int r = 0; r < 2; ++r) {     // output row parity
+    uint4 r0[3], r1[3];
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    const int o = j * 6;
-    const uint32_t b00 = a[o], g00 = a[o + 1], r00 = a[o + 2], b01 = a[o + 3], g01 = a[o + 4], r01 = a[o + 5];
-    const uint32_t b10 = c[o], g10 = c[o + 1], r10 = c[o + 2], b11 = c[o + 3], g11 = c[o + 4], r11 = c[o + 5];
-    const uint32_t bb = (b00 + b01 + b10 + b11 + 2) >> 2;  // cv2.resize INTER_LINEAR at exactly 1/2
-    const uint32_t gg = (g00 + g01 + g10 + g11 + 2) >> 2;
-    const uint32_t rr = (r00 + r01 + r10 + r11 + 2) >> 2;
-    pr[j] = (uint8_t)rr; pg[j] = (uint8_t)gg; pb[j] = (uint8_t)bb;  // exact; the 1/255 lives in layer 0's f32 weights
-    const uint32_t y00 = gray15(b00, g00, r00), y01 = gray15(b01, g01, r01), y10 = gray15(b10, g10, r10), y11 = gray15(b11, g11, r11);
-    gy[j] = (uint8_t)((y00 + y01 + y10 + y11 + 2) >> 2);  // gray first, then the 1/2 resize (stabilo order)
+    for (int i = 0; i < 3; ++i) {
+      r0[i] = __ldg(reinterpret_cast<const uint4*>(src + (size_t)(2 * r) * W * 3) + i);
+      r1[i] = __ldg(reinterpret_cast<const uint4*>(src + (size_t)(2 * r + 1) * W * 3) + i);
+    }
+    const uint8_t* a = reinterpret_cast<const uint8_t*>(r0);
+    const uint8_t* c = reinterpret_cast<const uint8_t*>(r1);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int o = j * 6;
+      const uint32_t b00 = a[o], g00 = a[o + 1], r00 = a[o + 2], b01 = a[o + 3], g01 = a[o + 4], r01 = a[o + 5];
+      const uint32_t b10 = c[o], g10 = c[o + 1], r10 = c[o + 2], b11 = c[o + 3], g11 = c[o + 4], r11 = c[o + 5];
+      const uint32_t bb = (b00 + b01 + b10 + b11 + 2) >> 2;  // cv2.resize INTER_LINEAR at exactly 1/2
+      const uint32_t gg = (g00 + g01 + g10 + g11 + 2) >> 2;
+      const uint32_t rr = (r00 + r01 + r10 + r11 + 2) >> 2;
+      // s2d pixel j>>1, column parity j&1, row parity r  ->  words ((j>>1)*16 + (r*2 + (j&1))*4) / 2 ...
+      const int w0 = (j >> 1) * 8 + (r * 2 + (j & 1)) * 2;
+      line[w0] = pack2_act((float)rr, (float)gg, fp16);
+      line[w0 + 1] = pack2_act((float)bb, 0.f, fp16);
+      const uint32_t y00 = gray15(b00, g00, r00), y01 = gray15(b01, g01, r01), y10 = gray15(b10, g10, r10), y11 = gray15(b11, g11, r11);
+      gy[r][j] = (uint8_t)((y00 + y01 + y10 + y11 + 2) >> 2);  // gray first, then the 1/2 resize (stabilo order)
+    }
   }
-  const size_t plane = (size_t)net_h * net_w;
-  uint8_t* dst = net_in + (size_t)b * 3 * plane + (size_t)(oy + pad_top) * net_w + pad_left + og * 8;
-  *reinterpret_cast<uint2*>(dst) = *reinterpret_cast<const uint2*>(pr);
-  *reinterpret_cast<uint2*>(dst + plane) = *reinterpret_cast<const uint2*>(pg);
-  *reinterpret_cast<uint2*>(dst + 2 * plane) = *reinterpret_cast<const uint2*>(pb);
-  if (gray) *reinterpret_cast<uint2*>(gray + (size_t)b * gray_frame_stride + (size_t)oy * new_w + og * 8) = *reinterpret_cast<const uint2*>(gy);
+  const int sh = net_h >> 1, sw = net_w >> 1;
+  uint4* dst = reinterpret_cast<uint4*>(s2d + (((size_t)b * sh + oy2 + (pad_top >> 1)) * sw + (pad_left >> 1) + og * 4) * 16);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) dst[i] = reinterpret_cast<const uint4*>(line)[i];
+  if (gray) {
+    uint8_t* g = gray + (size_t)b * gray_frame_stride + (size_t)(2 * oy2) * new_w + og * 8;
+    *reinterpret_cast<uint2*>(g) = *reinterpret_cast<const uint2*>(gy[0]);
+    *reinterpret_cast<uint2*>(g + new_w) = *reinterpret_cast<const uint2*>(gy[1]);
+  }
+}
+
+__global__ void fill_s2d_kernel(uint2* __restrict__ s2d, size_t n_quads, uint32_t w0, uint32_t w1) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n_quads) s2d[i] = make_uint2(w0, w1);
 }
 
 int detector_fill_pad(gt_engine* e, cudaStream_t st) {  // constant letterbox border (value 114); the interior is rewritten per batch
-  GT_CUDA(e, cudaMemsetAsync(e->net_in, 114, (size_t)e->cfg.max_batch * 3 * e->net_h * e->net_w, st));
+  const int fp16 = e->cfg.act_dtype == GT_ACT_FP16;
+  const uint16_t v = host_to_act(114.f, fp16);
+  const size_t n_quads = (size_t)e->cfg.max_batch * (e->net_h / 2) * (e->net_w / 2) * 4;  // one quad = R,G,B,0
+  fill_s2d_kernel<<<(unsigned)((n_quads + 255) / 256), 256, 0, st>>>(reinterpret_cast<uint2*>(e->net_s2d), n_quads, (uint32_t)v | ((uint32_t)v << 16),
+                                                                      (uint32_t)v);
+  GT_CUDA(e, cudaGetLastError());
   return GT_OK;
 }
 
 int detector_preprocess(gt_engine* e, const uint8_t* frames_dev, int B, cudaStream_t st) {
-  const long long threads = (long long)B * e->new_h * (e->new_w / 8);
+  const long long threads = (long long)B * (e->new_h / 2) * (e->new_w / 8);
   uint8_t* gray = e->pyr;  // level 0 of each frame's pyramid slab
-  preprocess_half_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(frames_dev, e->net_in, gray, e->pyr_bytes, B, e->cfg.frame_h,
+  preprocess_half_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(frames_dev, e->net_s2d, gray, e->pyr_bytes, B, e->cfg.frame_h,
                                                                             e->cfg.frame_w, e->net_h, e->net_w, e->pad_top, e->pad_left,
-                                                                            e->new_h, e->new_w);
+                                                                            e->new_h, e->new_w, e->cfg.act_dtype == GT_ACT_FP16);
   e->launches++;
   GT_CUDA(e, cudaGetLastError());
   e->cur_frames = frames_dev;
   return GT_OK;
-}
-
-// =====================================================================================================================
-// Layer 0: Conv(3 -> 32, k3, s2) + folded BN + SiLU on CUDA cores (K = 27 is too thin for the tensor pipe; the layer is
-// HBM-bound: AI 20 FLOP/B).  Planar u8 in (exact), f32 math with weights pre-scaled by 1/255, NHWC 16-bit out.
-// Block = 32 x 8 output pixels.
-// =====================================================================================================================
-__global__ void __launch_bounds__(256) conv0_kernel(const uint8_t* __restrict__ in, bf16* __restrict__ out, const float* __restrict__ w,
-                                                    const float* __restrict__ bias, int H, int W, int Ho, int Wo, int fp16) {
-  __shared__ float s_in[3][17][66];
-  __shared__ __align__(16) float s_w[27][32];
-  __shared__ float s_b[32];
-  const int b = blockIdx.z;
-  const int x0 = blockIdx.x * 32, y0 = blockIdx.y * 8;
-  for (int i = threadIdx.x; i < 27 * 32; i += 256) (&s_w[0][0])[i] = w[i];
-  if (threadIdx.x < 32) s_b[threadIdx.x] = bias[threadIdx.x];
-  const size_t plane = (size_t)H * W;
-  for (int i = threadIdx.x; i < 3 * 17 * 65; i += 256) {
-    const int cch = i / (17 * 65);
-    const int r = (i / 65) % 17, cc = i % 65;
-    const int iy = 2 * y0 - 1 + r, ix = 2 * x0 - 1 + cc;
-    float v = 0.f;
-    if (iy >= 0 && iy < H && ix >= 0 && ix < W) v = (float)in[((size_t)b * 3 + cch) * plane + (size_t)iy * W + ix];
-    s_in[cch][r][cc] = v;
-  }
-  __syncthreads();
-  const int lx = threadIdx.x & 31, ly = threadIdx.x >> 5;
-  const int ox = x0 + lx, oy = y0 + ly;
-  float acc[32];
-#pragma unroll
-  for (int i = 0; i < 32; ++i) acc[i] = s_b[i];
-#pragma unroll
-  for (int cch = 0; cch < 3; ++cch)
-#pragma unroll
-    for (int dy = 0; dy < 3; ++dy)
-#pragma unroll
-      for (int dx = 0; dx < 3; ++dx) {
-        const float v = s_in[cch][2 * ly + dy][2 * lx + dx];
-        const float4* wr = reinterpret_cast<const float4*>(&s_w[cch * 9 + dy * 3 + dx][0]);
-#pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          const float4 ww = wr[q];
-          acc[q * 4 + 0] = fmaf(v, ww.x, acc[q * 4 + 0]);
-          acc[q * 4 + 1] = fmaf(v, ww.y, acc[q * 4 + 1]);
-          acc[q * 4 + 2] = fmaf(v, ww.z, acc[q * 4 + 2]);
-          acc[q * 4 + 3] = fmaf(v, ww.w, acc[q * 4 + 3]);
-        }
-      }
-  if (ox >= Wo || oy >= Ho) return;
-  __align__(16) uint32_t o[16];
-#pragma unroll
-  for (int i = 0; i < 16; ++i) o[i] = pack2_act(silu_f(acc[2 * i]), silu_f(acc[2 * i + 1]), fp16);
-  uint4* dst = reinterpret_cast<uint4*>(out + (((size_t)b * Ho + oy) * Wo + ox) * 32);
-#pragma unroll
-  for (int q = 0; q < 4; ++q) dst[q] = reinterpret_cast<const uint4*>(o)[q];
 }
 
 // =====================================================================================================================
@@ -566,7 +537,12 @@ struct Builder {
     if (it == idx.end()) { gt_set_error(e, "plan: unknown conv %s", name.c_str()); rc = GT_ERR_INVALID; return 0; }
     return it->second;
   }
-  // bf16 conv writing a channel slice
+  void push(const ConvOp& op) {
+    e->conv_ops.push_back(op);
+    PlanOp po; po.type = OP_CONV; po.conv = (int)e->conv_ops.size() - 1;
+    e->plan.push_back(po);
+  }
+  // 16-bit conv writing a channel slice; several canonical convs reading the same input are fused along cout
   void conv(std::vector<std::string> names, const View& in, const View& out, const View* res = nullptr, const View* up = nullptr) {
     if (rc != GT_OK) return;
     ConvOp op;
@@ -574,11 +550,10 @@ struct Builder {
     op.n_src = (int)names.size();
     for (int i = 0; i < op.n_src; ++i) { op.src[i] = find(names[i]); cout += e->conv_descs[op.src[i]].cout; }
     const gt_conv_desc& d = e->conv_descs[op.src[0]];
-    rc = conv_tc_plan(e, &op, in, B, d.cin, cout, d.k, d.stride, d.act, &out, nullptr, 0, 0, 0, res, up);
-    if (rc != GT_OK) return;
-    e->conv_ops.push_back(op);
-    PlanOp po; po.type = OP_CONV; po.conv = (int)e->conv_ops.size() - 1;
-    e->plan.push_back(po);
+    ConvPlanArgs a;
+    a.in = in; a.Bmax = B; a.cin = d.cin; a.cout = cout; a.k = d.k; a.stride = d.stride; a.act = d.act; a.out = &out; a.res = res; a.up = up;
+    rc = conv_tc_plan(e, &op, a);
+    if (rc == GT_OK) push(op);
   }
   // final head conv writing fp32 raw rows
   void conv_raw(const std::string& name, const View& in, int lvl_off, int coff) {
@@ -586,12 +561,25 @@ struct Builder {
     ConvOp op;
     op.n_src = 1; op.src[0] = find(name);
     const gt_conv_desc& d = e->conv_descs[op.src[0]];
-    rc = conv_tc_plan(e, &op, in, B, d.cin, d.cout, d.k, d.stride, d.act, nullptr, e->raw_head + (size_t)lvl_off * e->no, e->A, e->no, coff,
-                      nullptr, nullptr);
+    ConvPlanArgs a;
+    a.in = in; a.Bmax = B; a.cin = d.cin; a.cout = d.cout; a.k = d.k; a.stride = d.stride; a.act = d.act;
+    a.out_f32 = e->raw_head + (size_t)lvl_off * e->no; a.out_img_stride = e->A; a.out_ctot_f32 = e->no; a.out_coff_f32 = coff;
+    rc = conv_tc_plan(e, &op, a);
+    if (rc == GT_OK) push(op);
+  }
+  // layer 0: Conv(3 -> 32, k3, s2) as a stride-1 2x2 convolution over the 16-channel space-to-depth input (see stage 1)
+  void conv0(const View& s2d, const View& out) {
     if (rc != GT_OK) return;
-    e->conv_ops.push_back(op);
-    PlanOp po; po.type = OP_CONV; po.conv = (int)e->conv_ops.size() - 1;
-    e->plan.push_back(po);
+    ConvOp op;
+    op.n_src = 1; op.src[0] = find("model.0");
+    ConvPlanArgs a;
+    a.in = s2d; a.Bmax = B; a.cin = 16; a.cout = 32; a.k = 2; a.stride = 1; a.pad = 1; a.Ho = s2d.H; a.Wo = s2d.W; a.kb_elems = 16;
+    a.act = 1; a.scale = 1.0f / 255.0f; a.out = &out;
+    rc = conv_tc_plan(e, &op, a);
+    if (rc != GT_OK) return;
+    op.flops = 2.0 * s2d.H * s2d.W * 32.0 * 27.0;   // the algorithmic 3x3x3 work, not the zero-padded 2x2x16
+    e->conv0_op = (int)e->conv_ops.size();
+    push(op);
   }
   void c2f(const std::string& pre, const View& in, int c2, int n, bool shortcut, const View& out, const View* up = nullptr) {
     const int c = c2 / 2;
@@ -682,12 +670,11 @@ int detector_build(gt_engine* e) {
   e->A = H3 * W3 + H4 * W4 + H5 * W5;
   e->no = 64 + nc + (obb ? 1 : 0);
   GT_TRY(e->dev_alloc((void**)&e->raw_head, (size_t)B * e->A * e->no * sizeof(float)));
-  GT_TRY(e->dev_alloc((void**)&e->conv0_w, 27 * 32 * sizeof(float)));
-  GT_TRY(e->dev_alloc((void**)&e->conv0_b, 32 * sizeof(float)));
 
+  View S2D = bl.alloc(16, H1, W1);          // written by stage 1
+  e->net_s2d = S2D.ptr;
   View T0 = bl.alloc(c1, H1, W1);
-  e->conv0_out = T0;
-  { PlanOp po; po.type = OP_CONV0; e->plan.push_back(po); }
+  bl.conv0(S2D, T0);
   View T1 = bl.alloc(c2, H2, W2);
   bl.conv({"model.1"}, T0, T1);
   View T2 = bl.alloc(c2, H2, W2);
@@ -757,7 +744,7 @@ int detector_build(gt_engine* e) {
   e->feat_views[12] = L12; e->feat_views[15] = P3; e->feat_views[16] = cat17.slice(0, c3); e->feat_views[18] = P4;
   e->feat_views[19] = cat20.slice(0, c4); e->feat_views[21] = P5;
 
-  e->conv_flops = 2.0 * H1 * W1 * 32.0 * 27.0;
+  e->conv_flops = 0;
   for (const ConvOp& op : e->conv_ops) e->conv_flops += op.flops;
 
   // decode / NMS workspaces
@@ -782,15 +769,30 @@ int detector_build(gt_engine* e) {
 
 int detector_load_weights(gt_engine* e, const float* const* w, const float* const* b, int n) {
   GT_CHECK(e, n == (int)e->conv_descs.size(), "load_weights: expected %d convs, got %d", (int)e->conv_descs.size(), n);
-  // layer 0: [32][3][3][3] -> [27][32]
-  {
-    std::vector<float> hw(27 * 32);
-    for (int co = 0; co < 32; ++co)
-      for (int k = 0; k < 27; ++k) hw[k * 32 + co] = w[0][co * 27 + k] / 255.0f;  // input is the raw u8 pixel
-    GT_CUDA(e, cudaMemcpy(e->conv0_w, hw.data(), hw.size() * sizeof(float), cudaMemcpyHostToDevice));
-    GT_CUDA(e, cudaMemcpy(e->conv0_b, b[0], 32 * sizeof(float), cudaMemcpyHostToDevice));
-  }
-  for (ConvOp& op : e->conv_ops) {
+  const int fp16 = e->cfg.act_dtype == GT_ACT_FP16;
+  for (size_t oi = 0; oi < e->conv_ops.size(); ++oi) {
+    ConvOp& op = e->conv_ops[oi];
+    if ((int)oi == e->conv0_op) {
+      // layer 0: [32][3][3][3] (cout, RGB, ky, kx) -> [32][tap = dy*2+dx][16 = (r*2+c)*4 + ch]; the s2d tap (dy, r) holds kernel
+      // row ky: (0,1)->0, (1,0)->1, (1,1)->2, (0,0)-> none (zero); columns likewise.  Unscaled: the 1/255 is the epilogue scale.
+      std::vector<uint16_t> hw((size_t)op.cout_pad * 4 * 16, 0);
+      std::vector<float> hb(op.cout_pad, 0.f);
+      const int kmap[2][2] = {{-1, 0}, {1, 2}};
+      for (int co = 0; co < 32; ++co) {
+        for (int dy = 0; dy < 2; ++dy)
+          for (int dx = 0; dx < 2; ++dx)
+            for (int r = 0; r < 2; ++r)
+              for (int c = 0; c < 2; ++c) {
+                const int ky = kmap[dy][r], kx = kmap[dx][c];
+                if (ky < 0 || kx < 0) continue;
+                for (int chn = 0; chn < 3; ++chn)
+                  hw[((size_t)co * 4 + dy * 2 + dx) * 16 + (r * 2 + c) * 4 + chn] = host_to_act(w[0][((co * 3 + chn) * 3 + ky) * 3 + kx], fp16);
+              }
+        hb[co] = b[0][co];
+      }
+      GT_TRY(conv_tc_upload_packed(e, &op, hw.data(), hb.data()));
+      continue;
+    }
     const float* ws[3];
     const float* bs[3];
     int couts[3];
@@ -801,26 +803,23 @@ int detector_load_weights(gt_engine* e, const float* const* w, const float* cons
   return GT_OK;
 }
 
+static int launch_pool(gt_engine* e, const MaxpoolOp& po, int B, cudaStream_t st) {
+  const View& i = po.in;
+  const View& o = po.out;
+  const long long total = (long long)B * i.H * i.W * (i.C / 8);
+  if (e->cfg.act_dtype == GT_ACT_FP16)
+    maxpool5_kernel<__half2><<<(unsigned)((total + 255) / 256), 256, 0, st>>>(i.ptr, i.ctot, i.coff, o.ptr, o.ctot, o.coff, B, i.H, i.W, i.C);
+  else
+    maxpool5_kernel<__nv_bfloat162><<<(unsigned)((total + 255) / 256), 256, 0, st>>>(i.ptr, i.ctot, i.coff, o.ptr, o.ctot, o.coff, B, i.H, i.W, i.C);
+  e->launches++;
+  return GT_OK;
+}
+
 int detector_forward(gt_engine* e, int B, cudaStream_t st) {
   GT_CHECK(e, e->weights_loaded, "detect: weights not loaded");
   for (const PlanOp& po : e->plan) {
-    if (po.type == OP_CONV0) {
-      const View& o = e->conv0_out;
-      dim3 grid((unsigned)ceil_div(o.W, 32), (unsigned)ceil_div(o.H, 8), (unsigned)B);
-      conv0_kernel<<<grid, 256, 0, st>>>(e->net_in, o.ptr, e->conv0_w, e->conv0_b, e->net_h, e->net_w, o.H, o.W, e->cfg.act_dtype == GT_ACT_FP16);
-      e->launches++;
-    } else if (po.type == OP_CONV) {
-      GT_TRY(conv_tc_launch(e, &e->conv_ops[po.conv], B, st));
-    } else {
-      const View& i = po.pool.in;
-      const View& o = po.pool.out;
-      const long long total = (long long)B * i.H * i.W * (i.C / 8);
-      if (e->cfg.act_dtype == GT_ACT_FP16)
-        maxpool5_kernel<__half2><<<(unsigned)((total + 255) / 256), 256, 0, st>>>(i.ptr, i.ctot, i.coff, o.ptr, o.ctot, o.coff, B, i.H, i.W, i.C);
-      else
-        maxpool5_kernel<__nv_bfloat162><<<(unsigned)((total + 255) / 256), 256, 0, st>>>(i.ptr, i.ctot, i.coff, o.ptr, o.ctot, o.coff, B, i.H, i.W, i.C);
-      e->launches++;
-    }
+    if (po.type == OP_CONV) GT_TRY(conv_tc_launch(e, &e->conv_ops[po.conv], B, st));
+    else GT_TRY(launch_pool(e, po.pool, B, st));
   }
   GT_CUDA(e, cudaGetLastError());
   return GT_OK;

@@ -5,7 +5,7 @@
 struct MaxpoolOp { View in, out; };  // 5x5 stride-1 max pool (SPPF chain)
 struct UpsampleOp { View in, out; }; // 2x nearest (only used when not fused in a conv epilogue)
 
-enum OpType { OP_CONV0 = 0, OP_CONV = 1, OP_MAXPOOL = 2 };
+enum OpType { OP_CONV = 1, OP_MAXPOOL = 2 };
 struct PlanOp {
   OpType type;
   int conv = -1;      // index into conv_ops
@@ -50,7 +50,7 @@ struct gt_engine {
   // staging + stage 1
   uint8_t* frames_dev = nullptr;        // [B][H][W][3]
   uint8_t* frames_pinned = nullptr;
-  uint8_t* net_in = nullptr;            // [B][3][net_h][net_w] planar RGB u8 (letterboxed, pad 114)
+  bf16* net_s2d = nullptr;              // [B][net_h/2][net_w/2][16] space-to-depth letterboxed RGB0 (exact u8 values, 16-bit)
   const uint8_t* cur_frames = nullptr;  // device pointer of the frames of the last gt_preprocess
 
   // detector
@@ -58,9 +58,7 @@ struct gt_engine {
   std::vector<gt_conv_desc> conv_descs;             // canonical list
   std::vector<ConvOp> conv_ops;                     // fused tcgen05 ops
   std::vector<PlanOp> plan;
-  float* conv0_w = nullptr;                         // [27][32] f32
-  float* conv0_b = nullptr;                         // [32]
-  View conv0_out;
+  int conv0_op = -1;                                // index of layer 0 in conv_ops (custom weight packing)
   View feat_views[23];
   float* raw_head = nullptr;                        // [B][A][no]
   // decode + NMS workspaces
