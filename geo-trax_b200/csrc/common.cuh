@@ -77,6 +77,8 @@ struct ConvParams {
   int tmem_cols;          // power of two >= max(32, 2*BN): two accumulators
   int acc_stride;         // TMEM column offset of the second accumulator
   int stages;
+  int b_resident;         // 1: all weight k-blocks stay in shared memory for the CTA's lifetime (ring holds A only)
+  int epi_mode;           // 0: 16-bit 128-B slabs, 1: 16-bit 64-B slab, 2: f32 128-B slabs, 3: f32 64-B slab
   int cout;               // real output channels
   int act;                // 1 = SiLU
   int out_f32;            // 1: out is float (raw head), 0: 16-bit act dtype
@@ -92,8 +94,11 @@ struct ConvParams {
   const float* bias;      // [n_tiles * BN]
 };
 
+struct ConvUpMaps { CUtensorMap m[4]; };   // the four (dy, dx) phases of the 2x nearest-upsampled destination
+
 struct ConvOp {
-  CUtensorMap tmA, tmB;
+  CUtensorMap tmA, tmB, tmOut;
+  ConvUpMaps tmUp;
   ConvParams p;
   size_t smem = 0;
   bf16* w_dev = nullptr;     // [cout_pad][taps][cin_pad]

@@ -19,6 +19,8 @@
 //                                 nearest-upsampled copy), or fp32 rows of the raw head tensor
 // so the epilogue of tile i overlaps the loads and MMAs of tile i+1 and the per-CTA prologue (barrier init, TMEM
 // allocation, descriptor prefetch) is paid once per SM instead of once per tile.
+#include <algorithm>
+
 #include "engine.cuh"
 
 namespace {
@@ -123,92 +125,180 @@ __device__ __forceinline__ void tmem_ld_x16(uint32_t taddr, uint32_t* v) {
       : "r"(taddr)
       : "memory");
 }
-__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-
-// Epilogue for NC (16 or 32) consecutive accumulator columns of one output pixel.
-template <int NC>
-__device__ __forceinline__ void epilogue_chunk(const ConvParams& p, const uint32_t* v, const float* s_bias, int gc0, bool valid, int n,
-                                               int y, int x) {
-  if (!valid || gc0 >= p.cout) return;
-  float f[NC];
-#pragma unroll
-  for (int i = 0; i < NC; ++i) {
-    const float a = fmaf(__uint_as_float(v[i]), p.scale, s_bias[gc0 + i]);
-    f[i] = p.act ? silu_f(a) : a;
-  }
-  const long long pix = (long long)n * p.out_img_stride + (long long)y * p.W + x;
-  if (p.out_f32) {
-    float* o = reinterpret_cast<float*>(p.out) + pix * p.out_ctot + p.out_coff + gc0;
-    const int nv = p.cout - gc0;
-#pragma unroll
-    for (int i = 0; i < NC; ++i)
-      if (i < nv) o[i] = f[i];
-    return;
-  }
-  if (p.res) {
-    const long long rp = ((long long)n * p.H + y) * p.W + x;
-    const uint4* r = reinterpret_cast<const uint4*>(p.res + rp * p.res_ctot + p.res_coff + gc0);
-#pragma unroll
-    for (int q = 0; q < NC / 8; ++q) {
-      const uint4 u = __ldg(r + q);
-      const float2 a0 = unpack2_act(u.x, p.fp16), a1 = unpack2_act(u.y, p.fp16), a2 = unpack2_act(u.z, p.fp16), a3 = unpack2_act(u.w, p.fp16);
-      f[q * 8 + 0] += a0.x; f[q * 8 + 1] += a0.y; f[q * 8 + 2] += a1.x; f[q * 8 + 3] += a1.y;
-      f[q * 8 + 4] += a2.x; f[q * 8 + 5] += a2.y; f[q * 8 + 6] += a3.x; f[q * 8 + 7] += a3.y;
-    }
-  }
-  uint4 pk[NC / 8];
-#pragma unroll
-  for (int q = 0; q < NC / 8; ++q) {
-    pk[q].x = pack2_act(f[q * 8 + 0], f[q * 8 + 1], p.fp16);
-    pk[q].y = pack2_act(f[q * 8 + 2], f[q * 8 + 3], p.fp16);
-    pk[q].z = pack2_act(f[q * 8 + 4], f[q * 8 + 5], p.fp16);
-    pk[q].w = pack2_act(f[q * 8 + 6], f[q * 8 + 7], p.fp16);
-  }
-  uint4* o = reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(p.out) + pix * p.out_ctot + p.out_coff + gc0);
-#pragma unroll
-  for (int q = 0; q < NC / 8; ++q) o[q] = pk[q];
-  if (p.up) {
-    const int W2 = p.W * 2;
-#pragma unroll
-    for (int d = 0; d < 4; ++d) {
-      const long long up = ((long long)n * (p.H * 2) + (y * 2 + (d >> 1))) * W2 + (x * 2 + (d & 1));
-      uint4* u = reinterpret_cast<uint4*>(p.up + up * p.up_ctot + p.up_coff + gc0);
-#pragma unroll
-      for (int q = 0; q < NC / 8; ++q) u[q] = pk[q];
-    }
-  }
+__device__ __forceinline__ void tmem_ld_x8(uint32_t taddr, uint32_t* v) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+               : "r"(taddr)
+               : "memory");
 }
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+template <int CW>
+__device__ __forceinline__ void tmem_ld(uint32_t taddr, uint32_t* v) {
+  if constexpr (CW == 32) tmem_ld_x32(taddr, v);
+  else if constexpr (CW == 16) tmem_ld_x16(taddr, v);
+  else tmem_ld_x8(taddr, v);
+}
+
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* tm, uint32_t src, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(tm), "r"(src), "r"(c0), "r"(c1),
+               "r"(c2), "r"(c3)
+               : "memory");
+}
+__device__ __forceinline__ float4 lds_f4(uint32_t saddr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(saddr));
+  return v;
+}
+__device__ __forceinline__ void sts_u4(uint32_t saddr, const uint4& v) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+// SiLU in 5 instructions: FMUL, MUFU.EX2, FADD, MUFU.RCP, FMUL (flush-to-zero approximations, ~1e-6 relative error)
+__device__ __forceinline__ float silu_fast(float a) {
+  float e, r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(a * -1.4426950408889634f));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + e));
+  return a * r;
+}
+__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, %0;" ::"n"(kEpiWarps * 32) : "memory"); }
 
 struct TileCoord { int n, y0, x0, n0; };
-__device__ __forceinline__ TileCoord decode_tile(const ConvParams& p, int tile) {
-  TileCoord t;
-  const int nt = tile % p.n_tiles;
-  const int m = tile / p.n_tiles;
-  const int tx = m % p.tiles_x;
-  const int r = m / p.tiles_x;
-  const int ty = r % p.tiles_y;
-  t.n = r / p.tiles_y + p.img0;
-  t.x0 = tx * p.tw;
-  t.y0 = ty * p.th;
-  t.n0 = nt * p.BN;
-  return t;
+// Walks tile = blockIdx.x, += gridDim.x over the (image, tile row, tile column, N tile) space without per-tile divisions.
+struct TileIter {
+  int nt, tx, ty, n;       // current coordinates
+  int d_nt, d_tx, d_ty, d_n;  // gridDim.x decomposed in the same mixed radix
+  __device__ __forceinline__ void init(const ConvParams& p, int first, int step) {
+    nt = first % p.n_tiles; int m = first / p.n_tiles;
+    tx = m % p.tiles_x; m /= p.tiles_x;
+    ty = m % p.tiles_y; n = m / p.tiles_y;
+    d_nt = step % p.n_tiles; m = step / p.n_tiles;
+    d_tx = m % p.tiles_x; m /= p.tiles_x;
+    d_ty = m % p.tiles_y; d_n = m / p.tiles_y;
+  }
+  __device__ __forceinline__ void next(const ConvParams& p) {
+    nt += d_nt; if (nt >= p.n_tiles) { nt -= p.n_tiles; ++tx; }
+    tx += d_tx; if (tx >= p.tiles_x) { tx -= p.tiles_x; ++ty; }
+    ty += d_ty; if (ty >= p.tiles_y) { ty -= p.tiles_y; ++n; }
+    n += d_n;
+  }
+  __device__ __forceinline__ TileCoord coord(const ConvParams& p) const {
+    TileCoord t;
+    t.n = n + p.img0; t.x0 = tx * p.tw; t.y0 = ty * p.th; t.n0 = nt * p.BN;
+    return t;
+  }
+};
+
+// Epilogue of one accumulator: slabs of 128 rows x SLAB_BYTES (128 or 64) are staged in shared memory in the TMA swizzle
+// layout and written with one bulk tensor store each (plus four for the 2x nearest-upsampled copy).  CW = accumulator
+// columns per warp per slab; two warps share a TMEM lane quarter and take the two halves of a slab's columns.
+template <int CW, bool F32>
+__device__ __forceinline__ void epilogue_tile(const ConvParams& p, const TileCoord& t, uint32_t trow, uint32_t stage_base, uint32_t s_bias,
+                                              const CUtensorMap* tmOut, const CUtensorMap* tmUp, int half, int row, int y, int x, bool valid,
+                                              uint32_t& slab_ctr, uint32_t tempty_bar, int lane, bool leader) {
+  constexpr int ELEM = F32 ? 4 : 2;
+  constexpr int ROW_BYTES = 2 * CW * ELEM;            // slab row: both halves
+  constexpr int CHUNKS = CW * ELEM / 16;              // 16-byte chunks this thread writes per slab row
+  constexpr uint32_t SWZ_MASK = ROW_BYTES == 128 ? 7u : (ROW_BYTES == 64 ? 3u : 1u);
+  const int n_slabs = p.BN / (2 * CW);
+  for (int j = 0; j < n_slabs; ++j, ++slab_ctr) {
+    const uint32_t buf = stage_base + (slab_ctr & 1u) * (128 * 128);
+    // the bulk store that last read this buffer (two slabs ago) must have finished reading shared memory
+    if (leader && slab_ctr >= 2) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+    epi_bar();
+    uint32_t v[CW];
+    const int c0 = j * 2 * CW + half * CW;            // first accumulator column of this warp's part
+    tmem_ld<CW>(trow + (uint32_t)c0, v);
+    tmem_ld_wait();
+    if (j == n_slabs - 1) {                           // accumulator fully read: hand it back to the MMA warp
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar);
+    }
+    const int gc0 = t.n0 + c0;
+    float f[CW];
+    const uint32_t bias_addr = s_bias + (uint32_t)gc0 * 4u;
+#pragma unroll
+    for (int i = 0; i < CW; i += 4) {
+      const float4 bv = lds_f4(bias_addr + (uint32_t)i * 4u);
+      f[i] = fmaf(__uint_as_float(v[i]), p.scale, bv.x);
+      f[i + 1] = fmaf(__uint_as_float(v[i + 1]), p.scale, bv.y);
+      f[i + 2] = fmaf(__uint_as_float(v[i + 2]), p.scale, bv.z);
+      f[i + 3] = fmaf(__uint_as_float(v[i + 3]), p.scale, bv.w);
+    }
+    if (p.act) {
+#pragma unroll
+      for (int i = 0; i < CW; ++i) f[i] = silu_fast(f[i]);
+    }
+    uint4 pk[CHUNKS];
+    if constexpr (F32) {
+#pragma unroll
+      for (int c = 0; c < CHUNKS; ++c)
+        pk[c] = make_uint4(__float_as_uint(f[c * 4]), __float_as_uint(f[c * 4 + 1]), __float_as_uint(f[c * 4 + 2]), __float_as_uint(f[c * 4 + 3]));
+    } else {
+      if (p.res && valid && gc0 < p.cout) {
+        const long long rp = ((long long)t.n * p.H + y) * p.W + x;
+        const uint4* r = reinterpret_cast<const uint4*>(p.res + rp * p.res_ctot + p.res_coff + gc0);
+#pragma unroll
+        for (int c = 0; c < CHUNKS; ++c) {
+          const uint4 u = __ldg(r + c);
+          const float2 a0 = unpack2_act(u.x, p.fp16), a1 = unpack2_act(u.y, p.fp16), a2 = unpack2_act(u.z, p.fp16), a3 = unpack2_act(u.w, p.fp16);
+          f[c * 8 + 0] += a0.x; f[c * 8 + 1] += a0.y; f[c * 8 + 2] += a1.x; f[c * 8 + 3] += a1.y;
+          f[c * 8 + 4] += a2.x; f[c * 8 + 5] += a2.y; f[c * 8 + 6] += a3.x; f[c * 8 + 7] += a3.y;
+        }
+      }
+      if (p.fp16) {   // warp-uniform: keeps the two encodings out of each other's instruction stream
+#pragma unroll
+        for (int c = 0; c < CHUNKS; ++c) {
+          pk[c].x = pack2_act(f[c * 8 + 0], f[c * 8 + 1], 1); pk[c].y = pack2_act(f[c * 8 + 2], f[c * 8 + 3], 1);
+          pk[c].z = pack2_act(f[c * 8 + 4], f[c * 8 + 5], 1); pk[c].w = pack2_act(f[c * 8 + 6], f[c * 8 + 7], 1);
+        }
+      } else {
+#pragma unroll
+        for (int c = 0; c < CHUNKS; ++c) {
+          pk[c].x = pack2_act(f[c * 8 + 0], f[c * 8 + 1], 0); pk[c].y = pack2_act(f[c * 8 + 2], f[c * 8 + 3], 0);
+          pk[c].z = pack2_act(f[c * 8 + 4], f[c * 8 + 5], 0); pk[c].w = pack2_act(f[c * 8 + 6], f[c * 8 + 7], 0);
+        }
+      }
+    }
+    // swizzled staging write: byte address bits [4:6] ^= bits [7:9] (masked to the swizzle span), as the TMA unit expects
+#pragma unroll
+    for (int c = 0; c < CHUNKS; ++c) {
+      const uint32_t logical = (uint32_t)row * ROW_BYTES + (uint32_t)(half * CHUNKS + c) * 16u;
+      const uint32_t phys = logical ^ (((logical >> 7) & SWZ_MASK) << 4);
+      sts_u4(buf + phys, pk[c]);
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    epi_bar();
+    if (leader) {
+      const int cch = (t.n0 + j * 2 * CW);            // first channel of this slab inside the destination slice
+      tma_store_4d(tmOut, buf, cch, t.x0, t.y0, t.n);
+      if (p.up) {
+#pragma unroll
+        for (int d = 0; d < 4; ++d) tma_store_4d(tmUp + d, buf, cch, t.x0, t.y0, t.n);
+      }
+      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    }
+  }
 }
 
-__global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_constant__ CUtensorMap tmA,
-                                                              const __grid_constant__ CUtensorMap tmB, const ConvParams p) {
+__global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                                                              const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ ConvUpMaps tmUp,
+                                                              const ConvParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  // carve: 1024-aligned operand ring first, then barriers / tmem pointer / bias
+  // carve (all 1024-aligned): operand ring | resident weights (optional) | 2 output staging slabs | barriers / tmem pointer / bias
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const int row_bytes = p.kb_elems * 2;
   const int a_bytes = 128 * row_bytes;
   const int b_bytes = p.BN * row_bytes;
-  const int stage_bytes = a_bytes + b_bytes;
-  uint8_t* tail = smem + (size_t)p.stages * stage_bytes;
+  const int stage_bytes = p.b_resident ? a_bytes : a_bytes + b_bytes;
+  uint8_t* b_res = smem + (size_t)p.stages * stage_bytes;
+  uint8_t* out_stage = b_res + (p.b_resident ? (size_t)p.num_kb * b_bytes : 0);
+  uint8_t* tail = out_stage + 2 * 128 * 128;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(tail);
   uint64_t* empty_bar = full_bar + kMaxStages;
   uint64_t* tfull_bar = empty_bar + kMaxStages;   // [2] accumulator ready
   uint64_t* tempty_bar = tfull_bar + 2;           // [2] accumulator drained
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  uint64_t* bres_bar = tempty_bar + 2;            // resident weights landed
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bres_bar + 1);
   float* s_bias = reinterpret_cast<float*>(tmem_ptr_smem + 2);
 
   const int warp = threadIdx.x >> 5;
@@ -218,6 +308,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmOut) : "memory");
     for (int s = 0; s < p.stages; ++s) {
       mbar_init(smem_u32(&full_bar[s]), 1);
       mbar_init(smem_u32(&empty_bar[s]), 1);
@@ -226,6 +317,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
       mbar_init(smem_u32(&tfull_bar[s]), 1);
       mbar_init(smem_u32(&tempty_bar[s]), kEpiWarps);
     }
+    mbar_init(smem_u32(bres_bar), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -245,23 +337,30 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
   if (warp == 0) {
     // ===== TMA producer =====
     if (lane == 0) {
+      if (p.b_resident) {   // all weights of this layer stay in shared memory for the CTA's lifetime
+        const uint32_t bb = smem_u32(bres_bar);
+        mbar_expect_tx(bb, (uint32_t)(p.num_kb * b_bytes));
+        for (int kb = 0; kb < p.num_kb; ++kb) tma_load_2d(smem_u32(b_res + (size_t)kb * b_bytes), &tmB, bb, kb * p.kb_elems, 0);
+      }
       const uint32_t tx_bytes = (uint32_t)stage_bytes;
-      uint32_t it = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const TileCoord t = decode_tile(p, tile);
+      uint32_t s = 0, ph = 0;
+      TileIter ti;
+      ti.init(p, blockIdx.x, gridDim.x);
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ti.next(p)) {
+        const TileCoord t = ti.coord(p);
         const int cx = t.x0 * p.stride - p.pad, cy = t.y0 * p.stride - p.pad;
-        for (int kb = 0; kb < p.num_kb; ++kb, ++it) {
-          const uint32_t s = it % (uint32_t)p.stages;
-          const uint32_t ph = (it / (uint32_t)p.stages) & 1u;
-          mbar_wait(smem_u32(&empty_bar[s]), ph ^ 1u);
-          const uint32_t fb = smem_u32(&full_bar[s]);
-          mbar_expect_tx(fb, tx_bytes);
-          const int tap = kb / p.kc_blocks, kc = kb - tap * p.kc_blocks;
-          const int dy = tap / p.ksize, dx = tap - dy * p.ksize;
-          uint8_t* sa = smem + (size_t)s * stage_bytes;
-          tma_load_4d(smem_u32(sa), &tmA, fb, kc * p.kb_elems, cx + dx, cy + dy, t.n);
-          tma_load_2d(smem_u32(sa + a_bytes), &tmB, fb, kb * p.kb_elems, t.n0);
-        }
+        int kb = 0;
+        for (int dy = 0; dy < p.ksize; ++dy)
+          for (int dx = 0; dx < p.ksize; ++dx)
+            for (int kc = 0; kc < p.kc_blocks; ++kc, ++kb) {
+              mbar_wait(smem_u32(&empty_bar[s]), ph ^ 1u);
+              const uint32_t fb = smem_u32(&full_bar[s]);
+              mbar_expect_tx(fb, tx_bytes);
+              uint8_t* sa = smem + (size_t)s * stage_bytes;
+              tma_load_4d(smem_u32(sa), &tmA, fb, kc * p.kb_elems, cx + dx, cy + dy, t.n);
+              if (!p.b_resident) tma_load_2d(smem_u32(sa + a_bytes), &tmB, fb, kb * p.kb_elems, t.n0);
+              if (++s == (uint32_t)p.stages) { s = 0; ph ^= 1u; }
+            }
       }
     }
   } else if (warp == 1) {
@@ -271,63 +370,58 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
       const bool sw128 = p.kb_elems == 64;
       const uint32_t sbo = sw128 ? 1024u : 256u, layout = sw128 ? 2u : 6u;
       const int mma_per_kb = p.kb_elems >> 4;
-      uint32_t it = 0, li = 0;
+      if (p.b_resident) mbar_wait(smem_u32(bres_bar), 0);
+      uint32_t s = 0, ph = 0, li = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++li) {
         const uint32_t as = li & 1u;
         mbar_wait(smem_u32(&tempty_bar[as]), ((li >> 1) & 1u) ^ 1u);   // epilogue has drained this accumulator
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t tacc = tmem_base + as * (uint32_t)p.acc_stride;
-        for (int kb = 0; kb < p.num_kb; ++kb, ++it) {
-          const uint32_t s = it % (uint32_t)p.stages;
-          const uint32_t ph = (it / (uint32_t)p.stages) & 1u;
+        for (int kb = 0; kb < p.num_kb; ++kb) {
           mbar_wait(smem_u32(&full_bar[s]), ph);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           uint8_t* sa = smem + (size_t)s * stage_bytes;
           const uint64_t adesc = make_desc(smem_u32(sa), sbo, layout);
-          const uint64_t bdesc = make_desc(smem_u32(sa + a_bytes), sbo, layout);
+          const uint64_t bdesc = make_desc(smem_u32(p.b_resident ? b_res + (size_t)kb * b_bytes : sa + a_bytes), sbo, layout);
           for (int k = 0; k < mma_per_kb; ++k) {
-            // advance 16 elements = 32 B along K inside the 128-B swizzle atom: +2 in the (>>4) start-address field
+            // advance 16 elements = 32 B along K inside the swizzle atom: +2 in the (>>4) start-address field
             umma_f16(tacc, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kb | k) ? 1u : 0u);
           }
           umma_commit(smem_u32(&empty_bar[s]));  // frees this smem stage when the MMAs above retire
+          if (++s == (uint32_t)p.stages) { s = 0; ph ^= 1u; }
         }
         umma_commit(smem_u32(&tfull_bar[as]));   // accumulator complete
       }
     }
   } else {
-    // ===== epilogue: TMEM -> registers -> scale/bias/SiLU/residual -> global =====
+    // ===== epilogue: TMEM -> registers -> scale/bias/SiLU/residual -> swizzled smem slab -> TMA store =====
     const int q = warp & 3;             // TMEM lane quarter this warp may touch (warp id % 4)
-    const int half = (warp - 2) >> 2;   // two warps share a quarter and alternate 32-column chunks
+    const int half = (warp - 2) >> 2;   // two warps share a quarter and split each slab's columns
     const int row = q * 32 + lane;
     const int ly = row / p.tw, lx = row - ly * p.tw;
-    uint32_t li = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++li) {
+    const bool leader = threadIdx.x == 64;
+    uint32_t li = 0, slab_ctr = 0;
+    const uint32_t out_stage_a = smem_u32(out_stage), s_bias_a = smem_u32(s_bias);
+    TileIter ti;
+    ti.init(p, blockIdx.x, gridDim.x);
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++li, ti.next(p)) {
       const uint32_t as = li & 1u;
-      const TileCoord t = decode_tile(p, tile);
+      const TileCoord t = ti.coord(p);
       const int y = t.y0 + ly, x = t.x0 + lx;
       const bool valid = (y < p.H) && (x < p.W);
-      mbar_wait(smem_u32(&tfull_bar[as]), (li >> 1) & 1u);
+      if (lane == 0) mbar_wait(smem_u32(&tfull_bar[as]), (li >> 1) & 1u);   // one lane polls; the warp reconverges below
+      __syncwarp();
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + as * (uint32_t)p.acc_stride;
-      int ci = 0;
-      for (int c0 = 0; c0 < p.BN; c0 += 32, ++ci) {
-        if ((ci & 1) != half) continue;
-        if (c0 + 32 <= p.BN) {
-          uint32_t v[32];
-          tmem_ld_x32(trow + (uint32_t)c0, v);
-          tmem_ld_wait();
-          epilogue_chunk<32>(p, v, s_bias, t.n0 + c0, valid, t.n, y, x);
-        } else {
-          uint32_t v[16];
-          tmem_ld_x16(trow + (uint32_t)c0, v);
-          tmem_ld_wait();
-          epilogue_chunk<16>(p, v, s_bias, t.n0 + c0, valid, t.n, y, x);
-        }
+      const uint32_t teb = smem_u32(&tempty_bar[as]);
+      switch (p.epi_mode) {
+        case 0: epilogue_tile<32, false>(p, t, trow, out_stage_a, s_bias_a, &tmOut, tmUp.m, half, row, y, x, valid, slab_ctr, teb, lane, leader); break;
+        case 1: epilogue_tile<16, false>(p, t, trow, out_stage_a, s_bias_a, &tmOut, tmUp.m, half, row, y, x, valid, slab_ctr, teb, lane, leader); break;
+        case 2: epilogue_tile<16, true>(p, t, trow, out_stage_a, s_bias_a, &tmOut, tmUp.m, half, row, y, x, valid, slab_ctr, teb, lane, leader); break;
+        default: epilogue_tile<8, true>(p, t, trow, out_stage_a, s_bias_a, &tmOut, tmUp.m, half, row, y, x, valid, slab_ctr, teb, lane, leader); break;
       }
-      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-      __syncwarp();
-      if (lane == 0) mbar_arrive(smem_u32(&tempty_bar[as]));
     }
+    if (leader) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // all output stores complete before the CTA retires
   }
 
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -338,8 +432,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
   }
 }
 
-size_t conv_smem_bytes(int stages, int stage_bytes, int bias_floats) {
-  return 1024 /*alignment slack*/ + (size_t)stages * stage_bytes + (2 * kMaxStages + 4) * 8 + 8 + (size_t)bias_floats * 4 + 16;
+size_t conv_smem_bytes(int stages, int stage_bytes, int bres_bytes, int bias_floats) {
+  return 1024 /*alignment slack*/ + (size_t)stages * stage_bytes + (size_t)bres_bytes + 2 * 128 * 128 /*output staging*/ +
+         (2 * kMaxStages + 5) * 8 + 8 + (size_t)bias_floats * 4 + 16;
 }
 
 }  // namespace
@@ -398,15 +493,27 @@ int conv_tc_plan(gt_engine* e, ConvOp* op, const ConvPlanArgs& a) {
   op->cin_pad = p.kc_blocks * kbe;
   p.num_kb = k * k * p.kc_blocks;
   const int cout16 = ceil_div(cout_total, 16) * 16;
-  p.BN = cout16 <= 256 ? cout16 : 256;
+  // N tile: whole output slabs of 128 bytes per row (64 16-bit or 32 fp32 columns), or one 64-byte slab for narrow outputs
+  const int elem = a.out_f32 ? 4 : 2;
+  const int slab_cols = 128 / elem;
+  if (cout16 * elem <= 64 || (!a.out_f32 && cout16 <= 32)) {
+    p.BN = 64 / elem;                       // 32 (16-bit) or 16 (fp32) columns: one 64-byte slab
+    p.epi_mode = a.out_f32 ? 3 : 1;
+  } else {
+    p.BN = std::min(256, ceil_div(cout16, slab_cols) * slab_cols);
+    p.epi_mode = a.out_f32 ? 2 : 0;
+  }
   p.n_tiles = ceil_div(cout16, p.BN);
   op->cout_pad = p.n_tiles * p.BN;
   // two accumulators of BN fp32 columns each; the allocation is a power of two >= 32 columns
   p.tmem_cols = 32;
   while (p.tmem_cols < 2 * p.BN) p.tmem_cols *= 2;
   p.acc_stride = p.tmem_cols / 2;
-  const int stage_bytes = (128 + p.BN) * kbe * 2;
-  const size_t fixed = conv_smem_bytes(0, stage_bytes, op->cout_pad);
+  const int a_bytes = 128 * kbe * 2, b_bytes = p.BN * kbe * 2;
+  const int bres_bytes = p.num_kb * b_bytes;
+  p.b_resident = (p.n_tiles == 1 && bres_bytes <= 112 * 1024) ? 1 : 0;
+  const int stage_bytes = p.b_resident ? a_bytes : a_bytes + b_bytes;
+  const size_t fixed = conv_smem_bytes(0, stage_bytes, p.b_resident ? bres_bytes : 0, op->cout_pad);
   int stages = (int)((227 * 1024 - fixed) / stage_bytes);
   if (stages > kMaxStages) stages = kMaxStages;
   GT_CHECK(e, stages >= 2, "conv plan: tile does not fit shared memory (BN=%d)", p.BN);
@@ -430,7 +537,7 @@ int conv_tc_plan(gt_engine* e, ConvOp* op, const ConvPlanArgs& a) {
     GT_CHECK(e, a.up->H == 2 * Ho && a.up->W == 2 * Wo && a.up->C == cout_total && !a.out_f32, "conv plan: upsample view mismatch");
     p.up = a.up->ptr; p.up_ctot = a.up->ctot; p.up_coff = a.up->coff;
   }
-  op->smem = conv_smem_bytes(p.stages, stage_bytes, op->cout_pad);
+  op->smem = conv_smem_bytes(p.stages, stage_bytes, p.b_resident ? bres_bytes : 0, op->cout_pad);
   op->flops = 2.0 * Ho * Wo * (double)cout_total * cin * k * k;
   // algorithmic HBM bytes per image: input slice + output (+ residual, + upsampled copy) + weights (once per launch, ignored)
   op->bytes = (double)in.H * in.W * cin * 2 + (double)Ho * Wo * cout_total * (a.out_f32 ? 4 : 2) * (a.up ? 5 : 1) +
@@ -468,6 +575,42 @@ int conv_tc_plan(gt_engine* e, ConvOp* op, const ConvPlanArgs& a) {
                           CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     GT_CHECK(e, r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(B) failed: %d (ktot=%llu cout_pad=%d BN=%d)", (int)r,
              (unsigned long long)ktot, op->cout_pad, p.BN);
+  }
+  // Output: destination slice as a 4-D tensor {C, W, H, N}; one box = one staging slab (128 rows x 128 or 64 bytes).
+  // Out-of-range rows / columns / channels of ragged tiles are clipped by the TMA unit.
+  {
+    const int box_c = (p.epi_mode == 0) ? 64 : (p.epi_mode == 2 ? 32 : p.BN);
+    const CUtensorMapSwizzle osw = (p.epi_mode == 0 || p.epi_mode == 2) ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
+    const CUtensorMapDataType odt = a.out_f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : dt;
+    auto enc = [&](CUtensorMap* tm, void* base, cuuint64_t W_, cuuint64_t H_, cuuint64_t pix_stride_b, cuuint64_t row_stride_b,
+                   cuuint64_t img_stride_b) -> CUresult {
+      cuuint64_t gdim[4] = {(cuuint64_t)cout_total, W_, H_, (cuuint64_t)a.Bmax};
+      cuuint64_t gstr[3] = {pix_stride_b, row_stride_b, img_stride_b};
+      cuuint32_t box[4] = {(cuuint32_t)box_c, (cuuint32_t)p.tw, (cuuint32_t)p.th, 1};
+      cuuint32_t estr[4] = {1, 1, 1, 1};
+      return g_encode(tm, odt, 4, base, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, osw, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    };
+    CUresult r;
+    if (a.out_f32) {
+      const cuuint64_t ps = (cuuint64_t)a.out_ctot_f32 * 4;
+      GT_CHECK(e, (ps % 16) == 0 && (a.out_coff_f32 % 4) == 0, "conv plan: fp32 output rows must be 16-byte aligned (row %d floats, col %d)",
+               a.out_ctot_f32, a.out_coff_f32);
+      r = enc(&op->tmOut, (void*)(a.out_f32 + a.out_coff_f32), Wo, Ho, ps, (cuuint64_t)Wo * ps, (cuuint64_t)a.out_img_stride * ps);
+    } else {
+      const cuuint64_t ps = (cuuint64_t)a.out->ctot * 2;
+      r = enc(&op->tmOut, (void*)(a.out->ptr + a.out->coff), Wo, Ho, ps, (cuuint64_t)Wo * ps, (cuuint64_t)Ho * Wo * ps);
+    }
+    GT_CHECK(e, r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(out) failed: %d (cout=%d box_c=%d)", (int)r, cout_total, box_c);
+    memset(&op->tmUp, 0, sizeof(op->tmUp));
+    if (a.up) {
+      const cuuint64_t ps = (cuuint64_t)a.up->ctot * 2, W2 = (cuuint64_t)2 * Wo, H2 = (cuuint64_t)2 * Ho;
+      for (int d = 0; d < 4; ++d) {
+        bf16* base = a.up->ptr + a.up->coff + ((size_t)(d >> 1) * W2 + (d & 1)) * a.up->ctot;
+        r = enc(&op->tmUp.m[d], (void*)base, Wo, Ho, 2 * ps, 2 * W2 * ps, H2 * W2 * ps);
+        GT_CHECK(e, r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(up %d) failed: %d", d, (int)r);
+      }
+    }
   }
   return GT_OK;
 }
@@ -510,7 +653,7 @@ int conv_tc_launch_range(gt_engine* e, const ConvOp* op, int b0, int nb, cudaStr
   p.img0 = b0;
   p.total_tiles = p.tiles_x * p.tiles_y * nb * p.n_tiles;
   const int grid = p.total_tiles < g_num_sms ? p.total_tiles : g_num_sms;
-  conv_tc_kernel<<<grid, kThreads, op->smem, st>>>(op->tmA, op->tmB, p);
+  conv_tc_kernel<<<grid, kThreads, op->smem, st>>>(op->tmA, op->tmB, op->tmOut, op->tmUp, p);
   e->launches++;
   GT_CUDA(e, cudaGetLastError());
   return GT_OK;

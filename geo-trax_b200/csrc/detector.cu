@@ -161,7 +161,7 @@ __device__ __forceinline__ float dfl_side(const float* p) {
   return ws / s;
 }
 
-__global__ void __launch_bounds__(256) decode_filter_kernel(const float* __restrict__ raw, int B, int A, int no, int nc, int obb,
+__global__ void __launch_bounds__(256) decode_filter_kernel(const float* __restrict__ raw, int B, int A, int no, int ang_col, int nc, int obb,
                                                             DecodeGeom g, float conf_thr, uint32_t classes_mask,
                                                             float* __restrict__ cand_box, float* __restrict__ cand_conf,
                                                             int* __restrict__ cand_cls, unsigned long long* __restrict__ keys,
@@ -204,7 +204,7 @@ __global__ void __launch_bounds__(256) decode_filter_kernel(const float* __restr
     const float hw = __fmul_rn(w, 0.5f), hh = __fmul_rn(h, 0.5f);
     o[0] = __fsub_rn(cx, hw); o[1] = __fsub_rn(cy, hh); o[2] = __fadd_rn(cx, hw); o[3] = __fadd_rn(cy, hh); o[4] = 0.f;
   } else {
-    const float ang = (sigmoid_f(r[64 + nc]) - 0.25f) * 3.14159265358979323846f;
+    const float ang = (sigmoid_f(r[ang_col]) - 0.25f) * 3.14159265358979323846f;
     const float cs = cosf(ang), sn = sinf(ang);
     const float xf = (d[2] - d[0]) * 0.5f, yf = (d[3] - d[1]) * 0.5f;
     o[0] = (xf * cs - yf * sn + ax) * s; o[1] = (xf * sn + yf * cs + ay) * s;
@@ -475,7 +475,7 @@ int nms_run(gt_engine* e, const float* pred_dev, int B, int A, int nc, int rotat
   } else {
     DecodeGeom g;
     for (int i = 0; i < 3; ++i) { g.lvl_w[i] = e->lvl_w[i]; g.lvl_h[i] = e->lvl_h[i]; g.lvl_off[i] = e->lvl_off[i]; g.stride[i] = (float)(8 << i); }
-    decode_filter_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(e->raw_head, B, A, e->no, nc, rotated, g, conf, classes_mask,
+    decode_filter_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(e->raw_head, B, A, e->no_pad, e->ang_col, nc, rotated, g, conf, classes_mask,
                                                                           e->cand_box, e->cand_conf, e->cand_cls, e->cand_key, key_stride,
                                                                           e->cand_count);
   }
@@ -563,7 +563,7 @@ struct Builder {
     const gt_conv_desc& d = e->conv_descs[op.src[0]];
     ConvPlanArgs a;
     a.in = in; a.Bmax = B; a.cin = d.cin; a.cout = d.cout; a.k = d.k; a.stride = d.stride; a.act = d.act;
-    a.out_f32 = e->raw_head + (size_t)lvl_off * e->no; a.out_img_stride = e->A; a.out_ctot_f32 = e->no; a.out_coff_f32 = coff;
+    a.out_f32 = e->raw_head + (size_t)lvl_off * e->no_pad; a.out_img_stride = e->A; a.out_ctot_f32 = e->no_pad; a.out_coff_f32 = coff;
     rc = conv_tc_plan(e, &op, a);
     if (rc == GT_OK) push(op);
   }
@@ -669,7 +669,10 @@ int detector_build(gt_engine* e) {
   e->lvl_off[0] = 0; e->lvl_off[1] = H3 * W3; e->lvl_off[2] = H3 * W3 + H4 * W4;
   e->A = H3 * W3 + H4 * W4 + H5 * W5;
   e->no = 64 + nc + (obb ? 1 : 0);
-  GT_TRY(e->dev_alloc((void**)&e->raw_head, (size_t)B * e->A * e->no * sizeof(float)));
+  e->ang_col = (64 + nc + 3) / 4 * 4;
+  e->no_pad = ((obb ? e->ang_col + 1 : 64 + nc) + 3) / 4 * 4;
+  GT_TRY(e->dev_alloc((void**)&e->raw_head, (size_t)B * e->A * e->no_pad * sizeof(float)));
+  GT_CUDA(e, cudaMemset(e->raw_head, 0, (size_t)B * e->A * e->no_pad * sizeof(float)));
 
   View S2D = bl.alloc(16, H1, W1);          // written by stage 1
   e->net_s2d = S2D.ptr;
@@ -735,7 +738,7 @@ int detector_build(gt_engine* e) {
     if (obb) {
       View b4 = bl.alloc(hc4, feats[i].H, feats[i].W);
       bl.conv({"model.22.cv4." + s + ".1"}, a.slice(hc2 + hc3, hc4), b4);
-      bl.conv_raw("model.22.cv4." + s + ".2", b4, e->lvl_off[i], 64 + nc);
+      bl.conv_raw("model.22.cv4." + s + ".2", b4, e->lvl_off[i], e->ang_col);
     }
   }
   if (bl.rc != GT_OK) return bl.rc;

@@ -44,7 +44,8 @@ struct gt_engine {
   int net_h = 0, net_w = 0, new_h = 0, new_w = 0, pad_top = 0, pad_left = 0;
   float gain = 1.f;
   int work_h = 0, work_w = 0;
-  int A = 0, no = 0;                    // anchors, raw head row width
+  int A = 0, no = 0;                    // anchors, raw head row width (64 + nc (+1))
+  int no_pad = 0, ang_col = 0;          // raw_head row stride in floats (multiple of 4: TMA store rows are 16-byte aligned); OBB angle column
   int lvl_h[3], lvl_w[3], lvl_off[3];
 
   // staging + stage 1
@@ -60,7 +61,7 @@ struct gt_engine {
   std::vector<PlanOp> plan;
   int conv0_op = -1;                                // index of layer 0 in conv_ops (custom weight packing)
   View feat_views[23];
-  float* raw_head = nullptr;                        // [B][A][no]
+  float* raw_head = nullptr;                        // [B][A][no_pad]
   // decode + NMS workspaces
   int cand_cap = 0;                                 // candidates per image
   float* cand_box = nullptr;                        // [B][cand_cap][5] x1,y1,x2,y2 (or x,y,w,h) + angle
