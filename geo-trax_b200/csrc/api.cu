@@ -1,5 +1,6 @@
 // C-ABI entry points (include/geotrax_b200.h) and engine lifecycle.
 #include <stdarg.h>
+#include <stdlib.h>
 
 #include <cmath>
 
@@ -70,6 +71,7 @@ int gt_create(const gt_config* cfg, int device, gt_handle* out) {
   gt_engine* e = new gt_engine();
   e->cfg = *cfg;
   e->device = device;
+  if (const char* hm = getenv("GT_HALO")) e->halo_mode = atoi(hm);
   auto fail = [&](int rc) { g_create_error = e->err; gt_destroy(e); return rc; };
 #define CR(expr) do { int _rc = (expr); if (_rc != GT_OK) return fail(_rc); } while (0)
 #define CRC(call) do { cudaError_t _er = (call); if (_er != cudaSuccess) { gt_set_error(e, "%s -> %s", #call, cudaGetErrorString(_er)); return fail(GT_ERR_CUDA); } } while (0)

@@ -77,6 +77,10 @@ struct ConvParams {
   int tmem_cols;          // power of two >= max(32, 2*BN): two accumulators
   int acc_stride;         // TMEM column offset of the second accumulator
   int stages;
+  int halo;               // 0: one TMA box per (tap, k-block); 1: one halo box per k-block, taps are shifted smem descriptors
+  int a_stages;           // halo ring depth
+  int halo_bytes;         // halo ring stage stride (1024-multiple); the box itself is 16 x (th + k - 1) rows of one k-block
+  int halo_tx;            // bytes one halo box delivers
   int b_resident;         // 1: all weight k-blocks stay in shared memory for the CTA's lifetime (ring holds A only)
   int epi_mode;           // 0: 16-bit 128-B slabs, 1: 16-bit 64-B slab, 2: f32 128-B slabs, 3: f32 64-B slab
   int cout;               // real output channels

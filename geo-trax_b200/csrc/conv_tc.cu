@@ -34,6 +34,9 @@ int g_num_sms = GT_NUM_SMS;
 constexpr int kEpiWarps = 8;
 constexpr int kThreads = 64 + kEpiWarps * 32;  // 320
 constexpr int kMaxStages = 12;
+constexpr int kMaxHaloStages = 8;
+constexpr int kHaloW = 16;   // halo row pitch in pixels: 8-pixel tile rows + (k - 1) halo columns, padded so that every image row
+                             // of the halo starts a fresh swizzle atom (8 rows)
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -83,6 +86,9 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t sbo_bytes
   d |= (uint64_t)layout << 61;
   return d;
 }
+// Halo taps use the same descriptor with a start address that is a whole number of rows into a swizzle atom.  The hardware
+// applies the swizzle XOR on absolute shared-memory address bits (measured: base-offset field 0 reproduces torch.conv2d
+// bit-for-bit-equivalently for every shift, setting it to (addr >> 7) & 7 does not), so no base offset is encoded.
 
 // kind::f16 instruction descriptor: D = f32, A = B = bf16 or f16, both K-major, M = 128, N = bn.
 __device__ __forceinline__ uint32_t make_idesc(int bn, int fp16) {
@@ -144,6 +150,17 @@ __device__ __forceinline__ void tma_store_4d(const CUtensorMap* tm, uint32_t src
                "r"(c2), "r"(c3)
                : "memory");
 }
+__device__ __forceinline__ bool elect_one() {   // true in exactly one lane of the (converged) warp
+  uint32_t pred;
+  asm volatile(
+      "{\n"
+      ".reg .pred P;\n"
+      "elect.sync _|P, 0xffffffff;\n"
+      "selp.u32 %0, 1, 0, P;\n"
+      "}\n"
+      : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ float4 lds_f4(uint32_t saddr) {
   float4 v;
   asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(saddr));
@@ -193,7 +210,7 @@ struct TileIter {
 template <int CW, bool F32>
 __device__ __forceinline__ void epilogue_tile(const ConvParams& p, const TileCoord& t, uint32_t trow, uint32_t stage_base, uint32_t s_bias,
                                               const CUtensorMap* tmOut, const CUtensorMap* tmUp, int half, int row, int y, int x, bool valid,
-                                              uint32_t& slab_ctr, uint32_t tempty_bar, int lane, bool leader) {
+                                              uint32_t& slab_ctr, uint32_t tempty_bar, int lane, bool leader_warp) {
   constexpr int ELEM = F32 ? 4 : 2;
   constexpr int ROW_BYTES = 2 * CW * ELEM;            // slab row: both halves
   constexpr int CHUNKS = CW * ELEM / 16;              // 16-byte chunks this thread writes per slab row
@@ -202,7 +219,7 @@ __device__ __forceinline__ void epilogue_tile(const ConvParams& p, const TileCoo
   for (int j = 0; j < n_slabs; ++j, ++slab_ctr) {
     const uint32_t buf = stage_base + (slab_ctr & 1u) * (128 * 128);
     // the bulk store that last read this buffer (two slabs ago) must have finished reading shared memory
-    if (leader && slab_ctr >= 2) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+    if (leader_warp && slab_ctr >= 2 && lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
     epi_bar();
     uint32_t v[CW];
     const int c0 = j * 2 * CW + half * CW;            // first accumulator column of this warp's part
@@ -268,7 +285,7 @@ __device__ __forceinline__ void epilogue_tile(const ConvParams& p, const TileCoo
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     epi_bar();
-    if (leader) {
+    if (leader_warp && lane == 0) {
       const int cch = (t.n0 + j * 2 * CW);            // first channel of this slab inside the destination slice
       tma_store_4d(tmOut, buf, cch, t.x0, t.y0, t.n);
       if (p.up) {
@@ -289,13 +306,16 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
   const int row_bytes = p.kb_elems * 2;
   const int a_bytes = 128 * row_bytes;
   const int b_bytes = p.BN * row_bytes;
-  const int stage_bytes = p.b_resident ? a_bytes : a_bytes + b_bytes;
-  uint8_t* b_res = smem + (size_t)p.stages * stage_bytes;
+  const int stage_bytes = p.halo ? b_bytes : (p.b_resident ? a_bytes : a_bytes + b_bytes);
+  uint8_t* halo_ring = smem + (size_t)p.stages * stage_bytes;
+  uint8_t* b_res = halo_ring + (size_t)p.a_stages * p.halo_bytes;
   uint8_t* out_stage = b_res + (p.b_resident ? (size_t)p.num_kb * b_bytes : 0);
   uint8_t* tail = out_stage + 2 * 128 * 128;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(tail);
   uint64_t* empty_bar = full_bar + kMaxStages;
-  uint64_t* tfull_bar = empty_bar + kMaxStages;   // [2] accumulator ready
+  uint64_t* afull_bar = empty_bar + kMaxStages;   // halo ring
+  uint64_t* aempty_bar = afull_bar + kMaxHaloStages;
+  uint64_t* tfull_bar = aempty_bar + kMaxHaloStages;   // [2] accumulator ready
   uint64_t* tempty_bar = tfull_bar + 2;           // [2] accumulator drained
   uint64_t* bres_bar = tempty_bar + 2;            // resident weights landed
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bres_bar + 1);
@@ -312,6 +332,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
     for (int s = 0; s < p.stages; ++s) {
       mbar_init(smem_u32(&full_bar[s]), 1);
       mbar_init(smem_u32(&empty_bar[s]), 1);
+    }
+    for (int s = 0; s < p.a_stages; ++s) {
+      mbar_init(smem_u32(&afull_bar[s]), 1);
+      mbar_init(smem_u32(&aempty_bar[s]), 1);
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(smem_u32(&tfull_bar[s]), 1);
@@ -335,17 +359,50 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
   const uint32_t tmem_base = *tmem_ptr_smem;
 
   if (warp == 0) {
-    // ===== TMA producer =====
-    if (lane == 0) {
-      if (p.b_resident) {   // all weights of this layer stay in shared memory for the CTA's lifetime
+    // ===== TMA producer: the whole warp walks the loop (converged), one elected lane issues =====
+    // (issuing from inside an `if (lane == 0)` region makes the compiler wrap every uniform-register operand of UTMALDG /
+    // UTCHMMA in an ELECT / R2UR.BROADCAST waterfall loop -- measured ~190 cycles per MMA)
+    if (p.b_resident) {   // all weights of this layer stay in shared memory for the CTA's lifetime
+      if (elect_one()) {
         const uint32_t bb = smem_u32(bres_bar);
         mbar_expect_tx(bb, (uint32_t)(p.num_kb * b_bytes));
         for (int kb = 0; kb < p.num_kb; ++kb) tma_load_2d(smem_u32(b_res + (size_t)kb * b_bytes), &tmB, bb, kb * p.kb_elems, 0);
       }
-      const uint32_t tx_bytes = (uint32_t)stage_bytes;
-      uint32_t s = 0, ph = 0;
-      TileIter ti;
-      ti.init(p, blockIdx.x, gridDim.x);
+      __syncwarp();
+    }
+    const uint32_t tx_bytes = (uint32_t)stage_bytes;
+    uint32_t s = 0, ph = 0;
+    TileIter ti;
+    ti.init(p, blockIdx.x, gridDim.x);
+    if (p.halo) {
+      uint32_t hs = 0, hph = 0;
+      const int taps = p.ksize * p.ksize;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ti.next(p)) {
+        const TileCoord t = ti.coord(p);
+        for (int kc = 0; kc < p.kc_blocks; ++kc) {
+          mbar_wait(smem_u32(&aempty_bar[hs]), hph ^ 1u);
+          if (elect_one()) {
+            const uint32_t ab = smem_u32(&afull_bar[hs]);
+            mbar_expect_tx(ab, (uint32_t)p.halo_tx);
+            tma_load_4d(smem_u32(halo_ring + (size_t)hs * p.halo_bytes), &tmA, ab, kc * p.kb_elems, t.x0 - p.pad, t.y0 - p.pad, t.n);
+          }
+          __syncwarp();
+          if (++hs == (uint32_t)p.a_stages) { hs = 0; hph ^= 1u; }
+          if (!p.b_resident) {
+            for (int tap = 0; tap < taps; ++tap) {
+              mbar_wait(smem_u32(&empty_bar[s]), ph ^ 1u);
+              if (elect_one()) {
+                const uint32_t fb = smem_u32(&full_bar[s]);
+                mbar_expect_tx(fb, tx_bytes);
+                tma_load_2d(smem_u32(smem + (size_t)s * stage_bytes), &tmB, fb, (tap * p.kc_blocks + kc) * p.kb_elems, t.n0);
+              }
+              __syncwarp();
+              if (++s == (uint32_t)p.stages) { s = 0; ph ^= 1u; }
+            }
+          }
+        }
+      }
+    } else {
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ti.next(p)) {
         const TileCoord t = ti.coord(p);
         const int cx = t.x0 * p.stride - p.pad, cy = t.y0 * p.stride - p.pad;
@@ -354,44 +411,82 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
           for (int dx = 0; dx < p.ksize; ++dx)
             for (int kc = 0; kc < p.kc_blocks; ++kc, ++kb) {
               mbar_wait(smem_u32(&empty_bar[s]), ph ^ 1u);
-              const uint32_t fb = smem_u32(&full_bar[s]);
-              mbar_expect_tx(fb, tx_bytes);
-              uint8_t* sa = smem + (size_t)s * stage_bytes;
-              tma_load_4d(smem_u32(sa), &tmA, fb, kc * p.kb_elems, cx + dx, cy + dy, t.n);
-              if (!p.b_resident) tma_load_2d(smem_u32(sa + a_bytes), &tmB, fb, kb * p.kb_elems, t.n0);
+              if (elect_one()) {
+                const uint32_t fb = smem_u32(&full_bar[s]);
+                mbar_expect_tx(fb, tx_bytes);
+                uint8_t* sa = smem + (size_t)s * stage_bytes;
+                tma_load_4d(smem_u32(sa), &tmA, fb, kc * p.kb_elems, cx + dx, cy + dy, t.n);
+                if (!p.b_resident) tma_load_2d(smem_u32(sa + a_bytes), &tmB, fb, kb * p.kb_elems, t.n0);
+              }
+              __syncwarp();
               if (++s == (uint32_t)p.stages) { s = 0; ph ^= 1u; }
             }
       }
     }
   } else if (warp == 1) {
-    // ===== MMA issuer (one thread) =====
-    if (lane == 0) {
-      const uint32_t idesc = make_idesc(p.BN, p.fp16);
-      const bool sw128 = p.kb_elems == 64;
-      const uint32_t sbo = sw128 ? 1024u : 256u, layout = sw128 ? 2u : 6u;
-      const int mma_per_kb = p.kb_elems >> 4;
-      if (p.b_resident) mbar_wait(smem_u32(bres_bar), 0);
-      uint32_t s = 0, ph = 0, li = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++li) {
-        const uint32_t as = li & 1u;
-        mbar_wait(smem_u32(&tempty_bar[as]), ((li >> 1) & 1u) ^ 1u);   // epilogue has drained this accumulator
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t tacc = tmem_base + as * (uint32_t)p.acc_stride;
+    // ===== MMA issuer: converged warp, one elected lane issues tcgen05.mma / tcgen05.commit =====
+    const uint32_t idesc = make_idesc(p.BN, p.fp16);
+    const bool sw128 = p.kb_elems == 64;
+    const uint32_t sbo = sw128 ? 1024u : 256u, layout = sw128 ? 2u : 6u;
+    const int mma_per_kb = p.kb_elems >> 4;
+    if (p.b_resident) mbar_wait(smem_u32(bres_bar), 0);
+    uint32_t s = 0, ph = 0, li = 0, hs = 0, hph = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++li) {
+      const uint32_t as = li & 1u;
+      mbar_wait(smem_u32(&tempty_bar[as]), ((li >> 1) & 1u) ^ 1u);   // epilogue has drained this accumulator
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t tacc = tmem_base + as * (uint32_t)p.acc_stride;
+      if (p.halo) {
+        const uint32_t hsbo = (uint32_t)(kHaloW * row_bytes);   // one halo image row = one 8-row group stride
+        for (int kc = 0; kc < p.kc_blocks; ++kc) {
+          mbar_wait(smem_u32(&afull_bar[hs]), hph);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint32_t hbase = smem_u32(halo_ring + (size_t)hs * p.halo_bytes);
+          int tap = 0;
+          for (int dy = 0; dy < p.ksize; ++dy)
+            for (int dx = 0; dx < p.ksize; ++dx, ++tap) {
+              const int kb = tap * p.kc_blocks + kc;
+              uint32_t baddr;
+              if (p.b_resident) baddr = smem_u32(b_res + (size_t)kb * b_bytes);
+              else {
+                mbar_wait(smem_u32(&full_bar[s]), ph);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                baddr = smem_u32(smem + (size_t)s * stage_bytes);
+              }
+              if (elect_one()) {
+                const uint64_t adesc = make_desc(hbase + (uint32_t)((dy * kHaloW + dx) * row_bytes), hsbo, layout);
+                const uint64_t bdesc = make_desc(baddr, sbo, layout);
+                for (int k = 0; k < mma_per_kb; ++k)
+                  umma_f16(tacc, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kc | tap | k) ? 1u : 0u);
+                if (!p.b_resident) umma_commit(smem_u32(&empty_bar[s]));
+              }
+              __syncwarp();
+              if (!p.b_resident) { if (++s == (uint32_t)p.stages) { s = 0; ph ^= 1u; } }
+            }
+          if (elect_one()) umma_commit(smem_u32(&aempty_bar[hs]));   // halo stage free once its taps have retired
+          __syncwarp();
+          if (++hs == (uint32_t)p.a_stages) { hs = 0; hph ^= 1u; }
+        }
+      } else {
         for (int kb = 0; kb < p.num_kb; ++kb) {
           mbar_wait(smem_u32(&full_bar[s]), ph);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-          uint8_t* sa = smem + (size_t)s * stage_bytes;
-          const uint64_t adesc = make_desc(smem_u32(sa), sbo, layout);
-          const uint64_t bdesc = make_desc(smem_u32(p.b_resident ? b_res + (size_t)kb * b_bytes : sa + a_bytes), sbo, layout);
-          for (int k = 0; k < mma_per_kb; ++k) {
-            // advance 16 elements = 32 B along K inside the swizzle atom: +2 in the (>>4) start-address field
-            umma_f16(tacc, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kb | k) ? 1u : 0u);
+          if (elect_one()) {
+            uint8_t* sa = smem + (size_t)s * stage_bytes;
+            const uint64_t adesc = make_desc(smem_u32(sa), sbo, layout);
+            const uint64_t bdesc = make_desc(smem_u32(p.b_resident ? b_res + (size_t)kb * b_bytes : sa + a_bytes), sbo, layout);
+            for (int k = 0; k < mma_per_kb; ++k) {
+              // advance 16 elements = 32 B along K inside the swizzle atom: +2 in the (>>4) start-address field
+              umma_f16(tacc, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kb | k) ? 1u : 0u);
+            }
+            umma_commit(smem_u32(&empty_bar[s]));  // frees this smem stage when the MMAs above retire
           }
-          umma_commit(smem_u32(&empty_bar[s]));  // frees this smem stage when the MMAs above retire
+          __syncwarp();
           if (++s == (uint32_t)p.stages) { s = 0; ph ^= 1u; }
         }
-        umma_commit(smem_u32(&tfull_bar[as]));   // accumulator complete
       }
+      if (elect_one()) umma_commit(smem_u32(&tfull_bar[as]));   // accumulator complete
+      __syncwarp();
     }
   } else {
     // ===== epilogue: TMEM -> registers -> scale/bias/SiLU/residual -> swizzled smem slab -> TMA store =====
@@ -399,7 +494,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
     const int half = (warp - 2) >> 2;   // two warps share a quarter and split each slab's columns
     const int row = q * 32 + lane;
     const int ly = row / p.tw, lx = row - ly * p.tw;
-    const bool leader = threadIdx.x == 64;
+    const bool leader_warp = warp == 2;
     uint32_t li = 0, slab_ctr = 0;
     const uint32_t out_stage_a = smem_u32(out_stage), s_bias_a = smem_u32(s_bias);
     TileIter ti;
@@ -415,13 +510,13 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
       const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + as * (uint32_t)p.acc_stride;
       const uint32_t teb = smem_u32(&tempty_bar[as]);
       switch (p.epi_mode) {
-        case 0: epilogue_tile<32, false>(p, t, trow, out_stage_a, s_bias_a, &tmOut, tmUp.m, half, row, y, x, valid, slab_ctr, teb, lane, leader); break;
-        case 1: epilogue_tile<16, false>(p, t, trow, out_stage_a, s_bias_a, &tmOut, tmUp.m, half, row, y, x, valid, slab_ctr, teb, lane, leader); break;
-        case 2: epilogue_tile<16, true>(p, t, trow, out_stage_a, s_bias_a, &tmOut, tmUp.m, half, row, y, x, valid, slab_ctr, teb, lane, leader); break;
-        default: epilogue_tile<8, true>(p, t, trow, out_stage_a, s_bias_a, &tmOut, tmUp.m, half, row, y, x, valid, slab_ctr, teb, lane, leader); break;
+        case 0: epilogue_tile<32, false>(p, t, trow, out_stage_a, s_bias_a, &tmOut, tmUp.m, half, row, y, x, valid, slab_ctr, teb, lane, leader_warp); break;
+        case 1: epilogue_tile<16, false>(p, t, trow, out_stage_a, s_bias_a, &tmOut, tmUp.m, half, row, y, x, valid, slab_ctr, teb, lane, leader_warp); break;
+        case 2: epilogue_tile<16, true>(p, t, trow, out_stage_a, s_bias_a, &tmOut, tmUp.m, half, row, y, x, valid, slab_ctr, teb, lane, leader_warp); break;
+        default: epilogue_tile<8, true>(p, t, trow, out_stage_a, s_bias_a, &tmOut, tmUp.m, half, row, y, x, valid, slab_ctr, teb, lane, leader_warp); break;
       }
     }
-    if (leader) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // all output stores complete before the CTA retires
+    if (leader_warp && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // all output stores complete before the CTA retires
   }
 
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -432,9 +527,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
   }
 }
 
-size_t conv_smem_bytes(int stages, int stage_bytes, int bres_bytes, int bias_floats) {
-  return 1024 /*alignment slack*/ + (size_t)stages * stage_bytes + (size_t)bres_bytes + 2 * 128 * 128 /*output staging*/ +
-         (2 * kMaxStages + 5) * 8 + 8 + (size_t)bias_floats * 4 + 16;
+size_t conv_smem_bytes(int stages, int stage_bytes, int halo_total, int bres_bytes, int bias_floats) {
+  return 1024 /*alignment slack*/ + (size_t)stages * stage_bytes + (size_t)halo_total + (size_t)bres_bytes + 2 * 128 * 128 /*output staging*/ +
+         (2 * kMaxStages + 2 * kMaxHaloStages + 5) * 8 + 8 + (size_t)bias_floats * 4 + 16;
 }
 
 }  // namespace
@@ -486,6 +581,15 @@ int conv_tc_plan(gt_engine* e, ConvOp* op, const ConvPlanArgs& a) {
   op->cin = cin; op->cout = cout_total; op->k = k; op->stride = stride;
   p.B = a.Bmax; p.H = Ho; p.W = Wo;
   pick_tile(Ho, Wo, &p.tw, &p.th);
+  // Halo mode (stride-1 k x k): 8 x 16 output tiles; one TMA box per k-block brings the (16-pitch) x (16 + k - 1) halo and the
+  // k*k taps are shifted shared-memory descriptors -> k*k times fewer A bytes from L2 and k*k times fewer TMA issues.
+  int want_halo = 0;
+  if (e->halo_mode && stride == 1 && k >= 2) {
+    const double u_halo = (double)Ho * Wo / ((double)ceil_div(Wo, 8) * 8 * ceil_div(Ho, 16) * 16);
+    const double u_best = (double)Ho * Wo / ((double)ceil_div(Wo, p.tw) * p.tw * ceil_div(Ho, p.th) * p.th);
+    if (u_halo >= 0.75 * u_best) want_halo = e->halo_mode;
+  }
+  if (want_halo) { p.tw = 8; p.th = 16; }
   p.tiles_x = ceil_div(Wo, p.tw); p.tiles_y = ceil_div(Ho, p.th);
   p.stride = stride; p.ksize = k; p.pad = pad;
   p.kb_elems = kbe;
@@ -512,12 +616,38 @@ int conv_tc_plan(gt_engine* e, ConvOp* op, const ConvPlanArgs& a) {
   const int a_bytes = 128 * kbe * 2, b_bytes = p.BN * kbe * 2;
   const int bres_bytes = p.num_kb * b_bytes;
   p.b_resident = (p.n_tiles == 1 && bres_bytes <= 112 * 1024) ? 1 : 0;
-  const int stage_bytes = p.b_resident ? a_bytes : a_bytes + b_bytes;
-  const size_t fixed = conv_smem_bytes(0, stage_bytes, p.b_resident ? bres_bytes : 0, op->cout_pad);
-  int stages = (int)((227 * 1024 - fixed) / stage_bytes);
-  if (stages > kMaxStages) stages = kMaxStages;
-  GT_CHECK(e, stages >= 2, "conv plan: tile does not fit shared memory (BN=%d)", p.BN);
-  p.stages = stages;
+  const size_t budget = 227 * 1024;
+  int stage_bytes = p.b_resident ? a_bytes : a_bytes + b_bytes;
+  int halo_total = 0;
+  if (want_halo) {
+    const int hrows = p.th + k - 1;
+    p.halo_tx = kHaloW * hrows * kbe * 2;
+    p.halo_bytes = (p.halo_tx + 1023) / 1024 * 1024;
+    const size_t fixed = conv_smem_bytes(0, 0, 0, p.b_resident ? bres_bytes : 0, op->cout_pad);
+    int a_st, b_st = 0;
+    if (p.b_resident) a_st = (int)((budget - fixed) / p.halo_bytes);
+    else {
+      a_st = 2;
+      b_st = (int)((budget - fixed - (size_t)a_st * p.halo_bytes) / b_bytes);
+      if (b_st > kMaxStages) { b_st = kMaxStages; a_st = (int)((budget - fixed - (size_t)b_st * b_bytes) / p.halo_bytes); }
+    }
+    if (a_st > kMaxHaloStages) a_st = kMaxHaloStages;
+    if (a_st >= 2 && (p.b_resident || b_st >= 3)) {
+      p.halo = want_halo; p.a_stages = a_st; p.stages = b_st; stage_bytes = b_bytes;
+      halo_total = a_st * p.halo_bytes;
+    } else {
+      pick_tile(Ho, Wo, &p.tw, &p.th);
+      p.halo_tx = p.halo_bytes = 0;
+    }
+  }
+  p.tiles_x = ceil_div(Wo, p.tw); p.tiles_y = ceil_div(Ho, p.th);
+  if (!p.halo) {
+    const size_t fixed = conv_smem_bytes(0, stage_bytes, 0, p.b_resident ? bres_bytes : 0, op->cout_pad);
+    int stages = (int)((budget - fixed) / stage_bytes);
+    if (stages > kMaxStages) stages = kMaxStages;
+    GT_CHECK(e, stages >= 2, "conv plan: tile does not fit shared memory (BN=%d)", p.BN);
+    p.stages = stages;
+  }
   p.cout = cout_total; p.act = a.act; p.fp16 = e->cfg.act_dtype == GT_ACT_FP16 ? 1 : 0;
   p.scale = a.scale;
   if (a.out_f32) {
@@ -537,7 +667,7 @@ int conv_tc_plan(gt_engine* e, ConvOp* op, const ConvPlanArgs& a) {
     GT_CHECK(e, a.up->H == 2 * Ho && a.up->W == 2 * Wo && a.up->C == cout_total && !a.out_f32, "conv plan: upsample view mismatch");
     p.up = a.up->ptr; p.up_ctot = a.up->ctot; p.up_coff = a.up->coff;
   }
-  op->smem = conv_smem_bytes(p.stages, stage_bytes, p.b_resident ? bres_bytes : 0, op->cout_pad);
+  op->smem = conv_smem_bytes(p.stages, stage_bytes, halo_total, p.b_resident ? bres_bytes : 0, op->cout_pad);
   op->flops = 2.0 * Ho * Wo * (double)cout_total * cin * k * k;
   // algorithmic HBM bytes per image: input slice + output (+ residual, + upsampled copy) + weights (once per launch, ignored)
   op->bytes = (double)in.H * in.W * cin * 2 + (double)Ho * Wo * cout_total * (a.out_f32 ? 4 : 2) * (a.up ? 5 : 1) +
@@ -558,6 +688,7 @@ int conv_tc_plan(gt_engine* e, ConvOp* op, const ConvPlanArgs& a) {
     cuuint64_t gdim[4] = {(cuuint64_t)cin, (cuuint64_t)in.W, (cuuint64_t)in.H, (cuuint64_t)a.Bmax};
     cuuint64_t gstr[3] = {(cuuint64_t)in.ctot * 2, (cuuint64_t)in.W * in.ctot * 2, (cuuint64_t)in.H * in.W * in.ctot * 2};
     cuuint32_t box[4] = {(cuuint32_t)kbe, (cuuint32_t)(p.tw * stride), (cuuint32_t)(p.th * stride), 1};
+    if (p.halo) { box[1] = kHaloW; box[2] = (cuuint32_t)(p.th + k - 1); }
     cuuint32_t estr[4] = {1, (cuuint32_t)stride, (cuuint32_t)stride, 1};
     CUresult r = g_encode(&op->tmA, dt, 4, (void*)(in.ptr + in.coff), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
                           CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
