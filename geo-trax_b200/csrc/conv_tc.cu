@@ -426,8 +426,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
   } else if (warp == 1) {
     // ===== MMA issuer: converged warp, one elected lane issues tcgen05.mma / tcgen05.commit =====
     const uint32_t idesc = make_idesc(p.BN, p.fp16);
-    const bool sw128 = p.kb_elems == 64;
-    const uint32_t sbo = sw128 ? 1024u : 256u, layout = sw128 ? 2u : 6u;
+    // swizzle span = one k-block row: 128 B (64 ch), 64 B (32 ch) or 32 B (16 ch); SBO = 8 rows of it
+    const uint32_t sbo = 8u * (uint32_t)row_bytes, layout = p.kb_elems == 64 ? 2u : (p.kb_elems == 32 ? 4u : 6u);
     const int mma_per_kb = p.kb_elems >> 4;
     if (p.b_resident) mbar_wait(smem_u32(bres_bar), 0);
     uint32_t s = 0, ph = 0, li = 0, hs = 0, hph = 0;
@@ -567,12 +567,13 @@ static void pick_tile(int H, int W, int* tw, int* th) {
 int conv_tc_plan(gt_engine* e, ConvOp* op, const ConvPlanArgs& a) {
   GT_CHECK(e, g_encode != nullptr, "conv_tc_init not called");
   const View& in = a.in;
-  const int cin = a.cin, k = a.k, stride = a.stride, kbe = a.kb_elems;
+  const int cin = a.cin, k = a.k, stride = a.stride;
+  const int kbe = (a.kb_elems == 64 && cin == 32) ? 32 : a.kb_elems;   // 32-channel inputs: 64-byte rows instead of half-empty 128-byte rows
   GT_CHECK(e, in.C == cin, "conv plan: input view has %d channels, conv expects %d", in.C, cin);
   GT_CHECK(e, (in.ctot % 8) == 0 && (in.coff % 8) == 0, "conv plan: input slice must be 16-byte aligned");
   GT_CHECK(e, k >= 1 && k <= 3, "conv plan: k=%d unsupported", k);
   GT_CHECK(e, stride == 1 || stride == 2, "conv plan: stride=%d unsupported", stride);
-  GT_CHECK(e, kbe == 64 || kbe == 16, "conv plan: kb_elems=%d unsupported", kbe);
+  GT_CHECK(e, kbe == 64 || kbe == 32 || kbe == 16, "conv plan: kb_elems=%d unsupported", kbe);
   ConvParams& p = op->p;
   memset(&p, 0, sizeof(p));
   const int pad = a.pad >= 0 ? a.pad : k / 2;
@@ -682,7 +683,7 @@ int conv_tc_plan(gt_engine* e, ConvOp* op, const ConvPlanArgs& a) {
   p.bias = op->b_dev;
 
   const CUtensorMapDataType dt = p.fp16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
-  const CUtensorMapSwizzle sw = kbe == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_32B;
+  const CUtensorMapSwizzle sw = kbe == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : (kbe == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
   // A: NHWC input slice as a 4-D tensor {C, W, H, N}
   {
     cuuint64_t gdim[4] = {(cuuint64_t)cin, (cuuint64_t)in.W, (cuuint64_t)in.H, (cuuint64_t)a.Bmax};

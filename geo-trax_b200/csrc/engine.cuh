@@ -37,7 +37,7 @@ struct gt_engine {
   cudaStream_t stream = nullptr;
   std::string err;
   int64_t launches = 0;
-  int halo_mode = 1;                    // conv A-operand staging: 0 per-tap boxes, 1 halo boxes + shifted descriptors (GT_HALO=0 disables, for A/B timing)
+  int halo_mode = 0;                    // conv A-operand staging: 0 per-tap boxes, 1 halo boxes + shifted descriptors (GT_HALO=1 enables: fewer L2->SM bytes, but the layers are tensor-issue bound)
   std::vector<void*> dev_allocs;
   std::vector<void*> host_allocs;
 
