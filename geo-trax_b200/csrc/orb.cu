@@ -44,40 +44,74 @@ __global__ void mask_rects_kernel(uint8_t* __restrict__ mask, size_t slab, const
 }
 
 // ---- one pyramid level from the previous one: cv2.resize(INTER_LINEAR_EXACT) in Q8.8 x Q8.8, (v + 2^15) >> 16 -------------
-// blockIdx.z = slot * 2 + plane (0 image, 1 mask; the mask is thresholded: <= 254 -> 0)
+// One thread = 4 adjacent output pixels of BOTH planes (image and mask share coordinates and weights; the mask is
+// thresholded: <= 254 -> 0).  blockIdx.z = slot.
 __global__ void __launch_bounds__(256) pyr_resize_kernel(uint8_t* __restrict__ img, uint8_t* __restrict__ msk, size_t slab, int slot0,
                                                          size_t src_off, int sw, int sh, size_t dst_off, int dw, int dh,
                                                          const int* __restrict__ xofs, const int* __restrict__ xc1,
                                                          const int* __restrict__ yofs, const int* __restrict__ yc1) {
-  const int x = blockIdx.x * blockDim.x + threadIdx.x;
+  const int x4 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
   const int y = blockIdx.y;
-  if (x >= dw) return;
-  const int slot = slot0 + (blockIdx.z >> 1);
-  const bool is_mask = blockIdx.z & 1;
-  uint8_t* base = (is_mask ? msk : img) + (size_t)slot * slab;
-  const uint8_t* s = base + src_off;
-  const int xo = xofs[x], cx1 = xc1[x], cx0 = 256 - cx1, xo1 = min(xo + 1, sw - 1);
-  const int yo = yofs[y], cy1 = yc1[y], cy0 = 256 - cy1, yo1 = min(yo + 1, sh - 1);
-  const uint8_t* r0 = s + (size_t)yo * sw;
-  const uint8_t* r1 = s + (size_t)yo1 * sw;
-  const int h0 = r0[xo] * cx0 + r0[xo1] * cx1;
-  const int h1 = r1[xo] * cx0 + r1[xo1] * cx1;
-  int v = (h0 * cy0 + h1 * cy1 + 32768) >> 16;
-  if (is_mask && v <= 254) v = 0;
-  base[dst_off + (size_t)y * dw + x] = (uint8_t)v;
+  if (x4 >= dw) return;
+  const int slot = slot0 + blockIdx.z;
+  const int yo = __ldg(yofs + y), cy1 = __ldg(yc1 + y), cy0 = 256 - cy1, yo1 = min(yo + 1, sh - 1);
+  int xo[4], cx1[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int x = min(x4 + k, dw - 1);
+    xo[k] = __ldg(xofs + x);
+    cx1[k] = __ldg(xc1 + x);
+  }
+  const int nvalid = min(4, dw - x4);
+#pragma unroll
+  for (int plane = 0; plane < 2; ++plane) {
+    uint8_t* base = (plane ? msk : img) + (size_t)slot * slab;
+    const uint8_t* r0 = base + src_off + (size_t)yo * sw;
+    const uint8_t* r1 = base + src_off + (size_t)yo1 * sw;
+    uint32_t packed = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int a = xo[k], b = min(a + 1, sw - 1), c1 = cx1[k], c0 = 256 - c1;
+      const int h0 = r0[a] * c0 + r0[b] * c1;
+      const int h1 = r1[a] * c0 + r1[b] * c1;
+      int v = (h0 * cy0 + h1 * cy1 + 32768) >> 16;
+      if (plane && v <= 254) v = 0;
+      packed |= (uint32_t)v << (8 * k);
+    }
+    uint8_t* d = base + dst_off + (size_t)y * dw + x4;
+    if (nvalid == 4 && (reinterpret_cast<uintptr_t>(d) & 3) == 0) *reinterpret_cast<uint32_t*>(d) = packed;
+    else
+      for (int k = 0; k < nvalid; ++k) d[k] = (uint8_t)(packed >> (8 * k));
+  }
 }
 
 // ---- FAST-9/16 score + 3x3 non-max suppression + mask / border filter -> candidate list ------------------------------------
+// Three phases per 64 x 32 tile so that the expensive part runs in dense warps:
+//   1. corner test for every position of the (tile + 1) ring: compass quick-reject, then the 16-bit arc masks; corners are
+//      compacted into a shared list;
+//   2. exact corner score (OpenCV cornerScore<16>) only for the listed positions;
+//   3. 3x3 non-max suppression, border / mask filter, block-level compaction into the per-(frame, level) candidate list.
 #define FT_X 64
-#define FT_Y 16
-__device__ __forceinline__ int fast_score(const uint8_t (*t)[FT_X + 8], int x, int y) {
-  // t is the smem image tile; (x, y) tile coordinates of the centre (>= 3 from the tile edge)
-  const int v = t[y][x];
-  int d[16];
+#define FT_Y 32
+#define FT_LIST ((FT_X + 2) * (FT_Y + 2))
+
+__device__ __forceinline__ void fast_ring(const uint8_t (*t)[FT_X + 8], int x, int y, int v, int* d) {
   d[0] = v - t[y + 3][x];      d[1] = v - t[y + 3][x + 1];  d[2] = v - t[y + 2][x + 2];  d[3] = v - t[y + 1][x + 3];
   d[4] = v - t[y][x + 3];      d[5] = v - t[y - 1][x + 3];  d[6] = v - t[y - 2][x + 2];  d[7] = v - t[y - 3][x + 1];
   d[8] = v - t[y - 3][x];      d[9] = v - t[y - 3][x - 1];  d[10] = v - t[y - 2][x - 2]; d[11] = v - t[y - 1][x - 3];
   d[12] = v - t[y][x - 3];     d[13] = v - t[y + 1][x - 3]; d[14] = v - t[y + 2][x - 2]; d[15] = v - t[y + 3][x - 1];
+}
+
+// is (x, y) a FAST-9/16 corner at threshold kFastThr?  (x, y) are tile coordinates >= 3 from the tile edge
+__device__ __forceinline__ bool fast_is_corner(const uint8_t (*t)[FT_X + 8], int x, int y) {
+  const int v = t[y][x];
+  // any 9 contiguous ring pixels contain two of the four compass pixels (0, 4, 8, 12): cheap necessary condition
+  const int c0 = v - t[y + 3][x], c4 = v - t[y][x + 3], c8 = v - t[y - 3][x], c12 = v - t[y][x - 3];
+  const int nd = (c0 > kFastThr) + (c4 > kFastThr) + (c8 > kFastThr) + (c12 > kFastThr);
+  const int nb = (c0 < -kFastThr) + (c4 < -kFastThr) + (c8 < -kFastThr) + (c12 < -kFastThr);
+  if (nd < 2 && nb < 2) return false;
+  int d[16];
+  fast_ring(t, x, y, v, d);
   unsigned dark = 0, bright = 0;  // d > thr : ring pixel darker than centre;  d < -thr : brighter
 #pragma unroll
   for (int k = 0; k < 16; ++k) {
@@ -92,7 +126,13 @@ __device__ __forceinline__ int fast_score(const uint8_t (*t)[FT_X + 8], int x, i
     a = a & (m >> 8);       // runs of 9
     return (a & 0xFFFFu) != 0;
   };
-  if (!run9(dark) && !run9(bright)) return 0;
+  return run9(dark) || run9(bright);
+}
+
+__device__ __forceinline__ int fast_corner_score(const uint8_t (*t)[FT_X + 8], int x, int y) {
+  const int v = t[y][x];
+  int d[16];
+  fast_ring(t, x, y, v, d);
   // exact corner score: the largest threshold for which the pixel is still a corner = max over the 16 circular 9-arcs of
   // min(d) (darker arcs) and of min(-d) (brighter arcs), minus 1.  Written as a doubling min-network on d and on an
   // explicitly negated copy: the straightforward "max(mn, -mx)" form is miscompiled by ptxas 12.9 -O1..-O3 for sm_100a
@@ -118,43 +158,78 @@ __device__ __forceinline__ int fast_score(const uint8_t (*t)[FT_X + 8], int x, i
 __global__ void __launch_bounds__(256) fast_kernel(const uint8_t* __restrict__ img, const uint8_t* __restrict__ msk, size_t slab, int slot0,
                                                    size_t lvl_off, int w, int h, unsigned int* __restrict__ cand, uint8_t* __restrict__ cscore,
                                                    size_t cand_slab, size_t cand_off, int cand_cap, int* __restrict__ counts, int level) {
-  __shared__ uint8_t s_img[FT_Y + 8][FT_X + 8];
+  __shared__ __align__(16) uint8_t s_img[FT_Y + 8][FT_X + 8];
   __shared__ uint8_t s_sc[FT_Y + 2][FT_X + 2];
-  __shared__ int s_n, s_base;
+  __shared__ unsigned short s_list[FT_LIST];      // corner positions (sy * (FT_X + 2) + sx) of phase 1
+  __shared__ int s_nl, s_n, s_base;
   __shared__ unsigned int s_xy[FT_X * FT_Y / 4];
   __shared__ uint8_t s_s[FT_X * FT_Y / 4];
   const int slot = slot0 + blockIdx.z;
   const uint8_t* im = img + (size_t)slot * slab + lvl_off;
   const int x0 = blockIdx.x * FT_X, y0 = blockIdx.y * FT_Y;
-  if (threadIdx.x == 0) s_n = 0;
-  for (int i = threadIdx.x; i < (FT_Y + 8) * (FT_X + 8); i += 256) {
-    const int ty = i / (FT_X + 8), tx = i - ty * (FT_X + 8);
-    const int gx = x0 - 4 + tx, gy = y0 - 4 + ty;
-    s_img[ty][tx] = (gx >= 0 && gx < w && gy >= 0 && gy < h) ? im[(size_t)gy * w + gx] : 0;
+  if (threadIdx.x == 0) { s_n = 0; s_nl = 0; }
+  // stage the tile + 4-pixel apron: 4 bytes per thread-iteration where the row is 4-byte aligned, else bytes
+  for (int i = threadIdx.x; i < (FT_Y + 8) * ((FT_X + 8) / 4); i += 256) {
+    const int ty = i / ((FT_X + 8) / 4), tq = i - ty * ((FT_X + 8) / 4);
+    const int gy = y0 - 4 + ty, gx = x0 - 4 + tq * 4;
+    uint32_t v = 0;
+    if (gy >= 0 && gy < h) {
+      const uint8_t* row = im + (size_t)gy * w;
+      if (gx >= 0 && gx + 3 < w && ((reinterpret_cast<uintptr_t>(row + gx) & 3) == 0)) v = *reinterpret_cast<const uint32_t*>(row + gx);
+      else {
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          if (gx + k >= 0 && gx + k < w) v |= (uint32_t)row[gx + k] << (8 * k);
+      }
+    }
+    *reinterpret_cast<uint32_t*>(&s_img[ty][tq * 4]) = v;
+  }
+  for (int i = threadIdx.x; i < (FT_Y + 2) * (FT_X + 2); i += 256) (&s_sc[0][0])[i] = 0;
+  __syncthreads();
+  // phase 1: corner test, warp-aggregated compaction
+  for (int i0 = 0; i0 < FT_LIST; i0 += 256) {
+    const int i = i0 + threadIdx.x;
+    bool corner = false;
+    if (i < FT_LIST) {
+      const int sy = i / (FT_X + 2), sx = i - sy * (FT_X + 2);
+      const int gx = x0 - 1 + sx, gy = y0 - 1 + sy;
+      if (gx >= 3 && gx < w - 3 && gy >= 3 && gy < h - 3) corner = fast_is_corner(s_img, sx + 3, sy + 3);
+    }
+    const unsigned bal = __ballot_sync(0xffffffffu, corner);
+    if (bal) {
+      const int lane = threadIdx.x & 31;
+      int base = 0;
+      if (lane == 0) base = atomicAdd(&s_nl, __popc(bal));
+      base = __shfl_sync(0xffffffffu, base, 0);
+      if (corner) s_list[base + __popc(bal & ((1u << lane) - 1))] = (unsigned short)i;
+    }
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < (FT_Y + 2) * (FT_X + 2); i += 256) {
+  // phase 2: exact score of the listed corners
+  for (int k = threadIdx.x; k < s_nl; k += 256) {
+    const int i = s_list[k];
     const int sy = i / (FT_X + 2), sx = i - sy * (FT_X + 2);
-    const int gx = x0 - 1 + sx, gy = y0 - 1 + sy;
-    int sc = 0;
-    if (gx >= 3 && gx < w - 3 && gy >= 3 && gy < h - 3) sc = fast_score(s_img, sx + 3, sy + 3);
-    s_sc[sy][sx] = (uint8_t)sc;
+    s_sc[sy][sx] = (uint8_t)fast_corner_score(s_img, sx + 3, sy + 3);
   }
   __syncthreads();
+  // phase 3: 3x3 NMS over the listed corners that lie inside the tile, border + mask filter
   const uint8_t* mk = msk + (size_t)slot * slab + lvl_off;
-  for (int i = threadIdx.x; i < FT_X * FT_Y; i += 256) {
-    const int ly = i / FT_X, lx = i - ly * FT_X;
+  for (int k = threadIdx.x; k < s_nl; k += 256) {
+    const int i = s_list[k];
+    const int sy = i / (FT_X + 2), sx = i - sy * (FT_X + 2);
+    if (sx < 1 || sx > FT_X || sy < 1 || sy > FT_Y) continue;
+    const int lx = sx - 1, ly = sy - 1;
     const int gx = x0 + lx, gy = y0 + ly;
-    const int sc = s_sc[ly + 1][lx + 1];
+    const int sc = s_sc[sy][sx];
     if (sc < kFastThr) continue;
     if (gx < kEdge || gx >= w - kEdge || gy < kEdge || gy >= h - kEdge) continue;
     if (!(sc > s_sc[ly][lx] && sc > s_sc[ly][lx + 1] && sc > s_sc[ly][lx + 2] && sc > s_sc[ly + 1][lx] && sc > s_sc[ly + 1][lx + 2] &&
           sc > s_sc[ly + 2][lx] && sc > s_sc[ly + 2][lx + 1] && sc > s_sc[ly + 2][lx + 2]))
       continue;
     if (mk[(size_t)gy * w + gx] == 0) continue;
-    const int k = atomicAdd(&s_n, 1);  // NMS guarantees <= 1 survivor per 2x2 block, so k < FT_X*FT_Y/4
-    s_xy[k] = ((unsigned)gy << 16) | (unsigned)gx;
-    s_s[k] = (uint8_t)sc;
+    const int q = atomicAdd(&s_n, 1);  // NMS guarantees <= 1 survivor per 2x2 block, so q < FT_X*FT_Y/4
+    s_xy[q] = ((unsigned)gy << 16) | (unsigned)gx;
+    s_s[q] = (uint8_t)sc;
   }
   __syncthreads();
   if (threadIdx.x == 0 && s_n) s_base = atomicAdd(&counts[slot * GT_ORB_LEVELS + level], s_n);
@@ -317,36 +392,65 @@ __device__ __forceinline__ int reflect101(int p, int n) {
   if (p >= n) p = 2 * n - 2 - p;
   return p;
 }
+// Tile 64 x 16: the u8 tile (+3 apron) is converted to float once, the horizontal pass produces 4 adjacent pixels per thread
+// from 3 vector loads, the vertical pass 4 adjacent pixels from 7 float4 loads and one 32-bit store.  Every product and sum
+// is rounded separately (__fmul_rn / __fadd_rn), in OpenCV's accumulation order.
 __global__ void __launch_bounds__(256) blur7_kernel(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, size_t slab, int slot0, size_t off,
                                                     int w, int h) {
-  __shared__ uint8_t s_in[16 + 6][64 + 6];
-  __shared__ float s_h[16 + 6][64];
+  __shared__ __align__(16) float s_in[16 + 6][72];   // 70 used
+  __shared__ __align__(16) float s_h[16 + 6][64];
   const int slot = slot0 + blockIdx.z;
   const uint8_t* im = src + (size_t)slot * slab + off;
   const int x0 = blockIdx.x * 64, y0 = blockIdx.y * 16;
-  for (int i = threadIdx.x; i < 22 * 70; i += 256) {
-    const int ty = i / 70, tx = i - ty * 70;
+  for (int i = threadIdx.x; i < 22 * 72; i += 256) {
+    const int ty = i / 72, tx = i - ty * 72;
     const int gx = reflect101(min(x0 - 3 + tx, w + 2), w), gy = reflect101(min(y0 - 3 + ty, h + 2), h);
-    s_in[ty][tx] = im[(size_t)min(max(gy, 0), h - 1) * w + min(max(gx, 0), w - 1)];
+    s_in[ty][tx] = (float)im[(size_t)min(max(gy, 0), h - 1) * w + min(max(gx, 0), w - 1)];
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < 22 * 64; i += 256) {
-    const int ty = i / 64, tx = i - ty * 64;
-    float acc = __fmul_rn((float)s_in[ty][tx], c_gauss[0]);
+  for (int i = threadIdx.x; i < 22 * 16; i += 256) {
+    const int ty = i >> 4, tq = i & 15;
+    const float4 a = *reinterpret_cast<const float4*>(&s_in[ty][tq * 4]);
+    const float4 b = *reinterpret_cast<const float4*>(&s_in[ty][tq * 4 + 4]);
+    const float2 c = *reinterpret_cast<const float2*>(&s_in[ty][tq * 4 + 8]);
+    const float v[10] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, c.x, c.y};
+    float o[4];
 #pragma unroll
-    for (int k = 1; k < 7; ++k) acc = __fadd_rn(acc, __fmul_rn((float)s_in[ty][tx + k], c_gauss[k]));
-    s_h[ty][tx] = acc;
+    for (int j = 0; j < 4; ++j) {
+      float acc = __fmul_rn(v[j], c_gauss[0]);
+#pragma unroll
+      for (int k = 1; k < 7; ++k) acc = __fadd_rn(acc, __fmul_rn(v[j + k], c_gauss[k]));
+      o[j] = acc;
+    }
+    *reinterpret_cast<float4*>(&s_h[ty][tq * 4]) = make_float4(o[0], o[1], o[2], o[3]);
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < 16 * 64; i += 256) {
-    const int ty = i / 64, tx = i - ty * 64;
-    const int gx = x0 + tx, gy = y0 + ty;
-    if (gx >= w || gy >= h) continue;
-    float acc = __fmul_rn(s_h[ty][tx], c_gauss[0]);
+  {
+    const int ty = threadIdx.x >> 4, tq = threadIdx.x & 15;   // 16 rows x 16 quads
+    const int gx = x0 + tq * 4, gy = y0 + ty;
+    if (gx < w && gy < h) {
+      float4 acc;
+      {
+        const float4 r = *reinterpret_cast<const float4*>(&s_h[ty][tq * 4]);
+        acc = make_float4(__fmul_rn(r.x, c_gauss[0]), __fmul_rn(r.y, c_gauss[0]), __fmul_rn(r.z, c_gauss[0]), __fmul_rn(r.w, c_gauss[0]));
+      }
 #pragma unroll
-    for (int k = 1; k < 7; ++k) acc = __fadd_rn(acc, __fmul_rn(s_h[ty + k][tx], c_gauss[k]));
-    const int v = __float2int_rn(acc);
-    dst[(size_t)slot * slab + off + (size_t)gy * w + gx] = (uint8_t)min(max(v, 0), 255);
+      for (int k = 1; k < 7; ++k) {
+        const float4 r = *reinterpret_cast<const float4*>(&s_h[ty + k][tq * 4]);
+        acc.x = __fadd_rn(acc.x, __fmul_rn(r.x, c_gauss[k])); acc.y = __fadd_rn(acc.y, __fmul_rn(r.y, c_gauss[k]));
+        acc.z = __fadd_rn(acc.z, __fmul_rn(r.z, c_gauss[k])); acc.w = __fadd_rn(acc.w, __fmul_rn(r.w, c_gauss[k]));
+      }
+      const int v0 = min(max(__float2int_rn(acc.x), 0), 255), v1 = min(max(__float2int_rn(acc.y), 0), 255);
+      const int v2 = min(max(__float2int_rn(acc.z), 0), 255), v3 = min(max(__float2int_rn(acc.w), 0), 255);
+      uint8_t* d = dst + (size_t)slot * slab + off + (size_t)gy * w + gx;
+      const int nvalid = min(4, w - gx);
+      if (nvalid == 4 && (reinterpret_cast<uintptr_t>(d) & 3) == 0)
+        *reinterpret_cast<uint32_t*>(d) = (uint32_t)v0 | ((uint32_t)v1 << 8) | ((uint32_t)v2 << 16) | ((uint32_t)v3 << 24);
+      else {
+        const int vv[4] = {v0, v1, v2, v3};
+        for (int k = 0; k < nvalid; ++k) d[k] = (uint8_t)vv[k];
+      }
+    }
   }
 }
 
@@ -556,7 +660,7 @@ int orb_run(gt_engine* e, int slot0, int nslots, bool as_reference, bool build_m
     const OrbLevel& S = e->lv[l - 1];
     const OrbLevel& D = e->lv[l];
     int* const* t = e->rs_tab[l];
-    dim3 g((unsigned)ceil_div(D.w, 256), (unsigned)D.h, (unsigned)(nslots * 2));
+    dim3 g((unsigned)ceil_div(D.w, 4 * 256), (unsigned)D.h, (unsigned)nslots);
     pyr_resize_kernel<<<g, 256, 0, st>>>(e->pyr, e->pyr_mask, slab, slot0, S.off, S.w, S.h, D.off, D.w, D.h, t[0], t[1], t[2], t[3]);
     e->launches++;
   }
