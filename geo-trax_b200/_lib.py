@@ -50,6 +50,8 @@ SYMBOLS = {
     "gt_conv_info": (_i, [_H, _i, C.POINTER(gt_conv_desc)]),
     "gt_load_weights": (_i, [_H, C.POINTER(_P), C.POINTER(_P), _i]),
     "gt_preprocess": (_i, [_H, _P, _i, _P]),
+    "gt_prefetch_frames": (_i, [_H, _P, _i]),
+    "gt_prefetch_frames_deferred": (_i, [_H, _P, _i]),
     "gt_get_net_input": (_i, [_H, _i, _P, _ip, _ip]),
     "gt_get_gray": (_i, [_H, _i, _P, _ip, _ip]),
     "gt_detect": (_i, [_H, _i, _f, _f, _i, _u, _P, _P, _P, _P]),

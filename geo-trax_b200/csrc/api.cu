@@ -103,7 +103,12 @@ int gt_create(const gt_config* cfg, int device, gt_handle* out) {
   e->work_h = (int)(c.frame_h * c.downsample_ratio);
   const int B = c.max_batch;
   CR(e->dev_alloc((void**)&e->frames_dev, (size_t)B * c.frame_h * c.frame_w * 3));
-  CR(e->host_alloc((void**)&e->frames_pinned, (size_t)B * c.frame_h * c.frame_w * 3));
+  CR(e->dev_alloc((void**)&e->frames_dev2, (size_t)B * c.frame_h * c.frame_w * 3));
+  CRC(cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking));
+  for (int i = 0; i < 2; ++i) {
+    CRC(cudaEventCreateWithFlags(&e->ev_copied[i], cudaEventDisableTiming));
+    CRC(cudaEventCreateWithFlags(&e->ev_consumed[i], cudaEventDisableTiming));
+  }
   CR(conv_tc_init(e));
   CR(orb_build(e));      // allocates the pyramid slabs (level 0 = stage-1 gray output)
   CR(detector_build(e));
@@ -124,6 +129,11 @@ int gt_destroy(gt_handle e) {
   for (void* p : e->dev_allocs) cudaFree(p);
   for (void* p : e->host_allocs) cudaFreeHost(p);
   for (int i = 0; i < 8; ++i) if (e->ev[i]) cudaEventDestroy(e->ev[i]);
+  for (int i = 0; i < 2; ++i) {
+    if (e->ev_copied[i]) cudaEventDestroy(e->ev_copied[i]);
+    if (e->ev_consumed[i]) cudaEventDestroy(e->ev_consumed[i]);
+  }
+  if (e->copy_stream) cudaStreamDestroy(e->copy_stream);
   if (e->stream) cudaStreamDestroy(e->stream);
   delete e;
   return GT_OK;
@@ -174,18 +184,64 @@ int gt_load_weights(gt_handle e, const float* const* weights, const float* const
   return detector_load_weights(e, weights, biases, n_convs);
 }
 
+// Starts the host->device copy of a batch on the copy stream into the idle staging buffer; a later gt_preprocess /
+// gt_extract_batch with the same `frames` pointer consumes it instead of copying.  Overlaps PCIe ingest with compute.
+int gt_prefetch_frames(gt_handle e, const uint8_t* frames, int B) {
+  ENTER(e);
+  GT_CHECK(e, frames && B >= 1 && B <= e->cfg.max_batch, "gt_prefetch_frames: bad batch %d", B);
+  if (is_device_ptr(frames)) return GT_OK;   // nothing to stage
+  int k = e->prefetch_next;
+  if (e->prefetched_src[k] != nullptr && e->prefetched_src[k ^ 1] == nullptr) k ^= 1;   // never overwrite an unconsumed prefetch
+  e->prefetch_next = k ^ 1;
+  uint8_t* dst = k ? e->frames_dev2 : e->frames_dev;
+  GT_CUDA(e, cudaStreamWaitEvent(e->copy_stream, e->ev_consumed[k], 0));   // the kernel that last read this buffer is done
+  // one copy per frame: small uploads of the running batch (mask boxes) are not stuck behind one 400 MB transfer
+  const size_t fb = (size_t)e->cfg.frame_h * e->cfg.frame_w * 3;
+  for (int b = 0; b < B; ++b) GT_CUDA(e, cudaMemcpyAsync(dst + b * fb, frames + b * fb, fb, cudaMemcpyHostToDevice, e->copy_stream));
+  GT_CUDA(e, cudaEventRecord(e->ev_copied[k], e->copy_stream));
+  e->prefetched_src[k] = frames;
+  return GT_OK;
+}
+
+// Same, but the copy is started by the next gt_extract_batch right after it has queued its own small inputs (mask boxes),
+// so those are not stuck behind 400 MB of frames on the copy engine.
+int gt_prefetch_frames_deferred(gt_handle e, const uint8_t* frames, int B) {
+  ENTER(e);
+  GT_CHECK(e, frames && B >= 1 && B <= e->cfg.max_batch, "gt_prefetch_frames_deferred: bad batch %d", B);
+  e->deferred_src = frames;
+  e->deferred_B = B;
+  return GT_OK;
+}
+
 int gt_preprocess(gt_handle e, const uint8_t* frames, int B, void* stream) {
   ENTER(e);
   GT_CHECK(e, frames && B >= 1 && B <= e->cfg.max_batch, "gt_preprocess: bad batch %d", B);
   cudaStream_t st = pick_stream(e, stream);
   const uint8_t* src = frames;
+  int used = -1;
   GT_CUDA(e, cudaEventRecord(e->ev[0], st));
   if (!is_device_ptr(frames)) {
-    const size_t bytes = (size_t)B * e->cfg.frame_h * e->cfg.frame_w * 3;
-    GT_TRY(to_device(e, e->frames_dev, frames, bytes, st));
-    src = e->frames_dev;
+    for (int k = 0; k < 2; ++k)
+      if (e->prefetched_src[k] == frames) used = k;
+    if (used >= 0) {   // already on its way (gt_prefetch_frames): just order this stream after the copy
+      GT_CUDA(e, cudaStreamWaitEvent(st, e->ev_copied[used], 0));
+      e->prefetched_src[used] = nullptr;
+    } else {
+      used = e->prefetch_next;
+      if (e->prefetched_src[used] != nullptr && e->prefetched_src[used ^ 1] == nullptr) used ^= 1;   // keep a pending prefetch intact
+      if (e->prefetched_src[used] != nullptr) {   // both staging buffers hold pending prefetches: the older one is dropped
+        GT_CUDA(e, cudaStreamWaitEvent(st, e->ev_copied[used], 0));
+        e->prefetched_src[used] = nullptr;
+      }
+      e->prefetch_next = used ^ 1;
+      GT_CUDA(e, cudaStreamWaitEvent(st, e->ev_consumed[used], 0));
+      const size_t bytes = (size_t)B * e->cfg.frame_h * e->cfg.frame_w * 3;
+      GT_TRY(to_device(e, used ? e->frames_dev2 : e->frames_dev, frames, bytes, st));
+    }
+    src = used ? e->frames_dev2 : e->frames_dev;
   }
   GT_TRY(detector_preprocess(e, src, B, st));
+  if (used >= 0) GT_CUDA(e, cudaEventRecord(e->ev_consumed[used], st));
   GT_CUDA(e, cudaEventRecord(e->ev[1], st));
   return GT_OK;
 }
@@ -568,16 +624,21 @@ int gt_extract_batch(gt_handle e, const uint8_t* frames, int B, int first_is_ref
   ENTER(e);
   GT_CHECK(e, frames && B >= 1 && B <= e->cfg.max_batch, "gt_extract_batch: bad batch %d", B);
   cudaStream_t st = pick_stream(e, stream);
-  GT_TRY(gt_preprocess(e, frames, B, st));
-  GT_TRY(detect_impl(e, B, conf, iou, agnostic, classes_mask, st));
   const int md = e->cfg.max_det;
   const int obb = e->cfg.task == GT_TASK_OBB;
+  const bool ext_mask = mask_boxes && mask_nboxes;
+  if (ext_mask) GT_TRY(upload_boxes(e, 0, B, mask_boxes, mask_nboxes, mask_stride, st));   // small inputs first ...
+  if (e->deferred_src) {                                                                   // ... then the next batch's frames
+    const uint8_t* nxt = e->deferred_src;
+    e->deferred_src = nullptr;
+    GT_TRY(gt_prefetch_frames(e, nxt, e->deferred_B));
+  }
+  GT_TRY(gt_preprocess(e, frames, B, st));
+  GT_TRY(detect_impl(e, B, conf, iou, agnostic, classes_mask, st));
   dim3 g((unsigned)ceil_div(md, 256), (unsigned)B);
   dets_to_xywh_kernel<<<g, 256, 0, st>>>(e->det_out, e->det_count, obb ? 7 : 6, md, e->det_xywh_dev, e->det_nbox_dev, B, obb);
   e->launches++;
-  if (mask_boxes && mask_nboxes) {
-    GT_TRY(upload_boxes(e, 0, B, mask_boxes, mask_nboxes, mask_stride, st));
-  } else {
+  if (!ext_mask) {
     GT_CUDA(e, cudaMemcpyAsync(e->boxes_dev, e->det_xywh_dev, (size_t)B * md * 16, cudaMemcpyDeviceToDevice, st));
     GT_CUDA(e, cudaMemcpyAsync(e->nboxes_dev, e->det_nbox_dev, (size_t)B * sizeof(int), cudaMemcpyDeviceToDevice, st));
   }

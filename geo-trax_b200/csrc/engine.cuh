@@ -50,8 +50,15 @@ struct gt_engine {
   int lvl_h[3], lvl_w[3], lvl_off[3];
 
   // staging + stage 1
-  uint8_t* frames_dev = nullptr;        // [B][H][W][3]
-  uint8_t* frames_pinned = nullptr;
+  uint8_t* frames_dev = nullptr;        // [B][H][W][3] staging buffer 0 (host inputs)
+  uint8_t* frames_dev2 = nullptr;       // staging buffer 1: gt_prefetch_frames copies batch i+1 while batch i computes
+  cudaStream_t copy_stream = nullptr;
+  cudaEvent_t ev_copied[2] = {nullptr, nullptr};   // H2D of staging buffer k finished (copy stream)
+  cudaEvent_t ev_consumed[2] = {nullptr, nullptr}; // the preprocess kernel that read staging buffer k finished
+  const void* prefetched_src[2] = {nullptr, nullptr};
+  int prefetch_next = 0;
+  const uint8_t* deferred_src = nullptr;   // gt_prefetch_frames_deferred: started by the next gt_extract_batch
+  int deferred_B = 0;
   bf16* net_s2d = nullptr;              // [B][net_h/2][net_w/2][16] space-to-depth letterboxed RGB0 (exact u8 values, 16-bit)
   const uint8_t* cur_frames = nullptr;  // device pointer of the frames of the last gt_preprocess
 

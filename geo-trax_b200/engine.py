@@ -114,6 +114,13 @@ class Engine:
         self._ck(self.lib.gt_preprocess(self.h, _ptr(frames), B, stream))
         return B
 
+    def prefetch(self, frames, deferred=False):
+        """Start the H2D copy of a pinned host batch; the next preprocess / extract_batch on the same buffer consumes it.
+        deferred=True: the copy is started inside the next extract_batch, after that call's own small uploads."""
+        self._keep_next = frames
+        fn = self.lib.gt_prefetch_frames_deferred if deferred else self.lib.gt_prefetch_frames
+        self._ck(fn(self.h, _ptr(frames), int(frames.shape[0])))
+
     def net_input(self, B: int) -> np.ndarray:
         out = np.empty((B, 3, self.net_h, self.net_w), np.uint8)
         self._ck(self.lib.gt_get_net_input(self.h, B, out.ctypes.data, None, None))

@@ -94,6 +94,12 @@ int gt_load_weights(gt_handle h, const float* const* weights, const float* const
  * frames: u8 [B][frame_h][frame_w][3] BGR.  Replaces LetterBox + BasePredictor.preprocess (extract.py:153) and
  * stabilo's BGR2GRAY + resize front end (extract.py:177,181).  Results stay in the handle's workspaces.        */
 int gt_preprocess(gt_handle h, const uint8_t* frames, int B, void* stream);
+/* optional ingest pipelining (replaces nothing in the reference, whose cv2.VideoCapture loop is synchronous, extract.py:146):
+ * starts the H2D copy of a (pinned) host batch on the library's copy stream; the next gt_preprocess / gt_extract_batch
+ * called with the same pointer consumes it.  Two staging buffers: copy of batch i+1 overlaps compute of batch i.      */
+int gt_prefetch_frames(gt_handle h, const uint8_t* frames, int B);
+/* same, started by the next gt_extract_batch right after it has queued its own small inputs (mask boxes) */
+int gt_prefetch_frames_deferred(gt_handle h, const uint8_t* frames, int B);
 /* debug/parity read-back: letterboxed planar RGB u8 [B][3][net_h][net_w] (the 1/255 scale is folded into layer 0's
  * f32 weights, so the network input is exact) and u8 gray [B][work_h][work_w] */
 int gt_get_net_input(gt_handle h, int B, uint8_t* out_u8, int32_t* net_h, int32_t* net_w);
