@@ -37,6 +37,16 @@ UNIT = "frames/s"
 CONV_GFLOP_PER_FRAME = 145.03
 
 
+def _conv_traffic():
+    """DRAM bytes of the conv launches of one step, from the committed ncu capture (profiles/conv_traffic_r1.json)."""
+    p = os.path.join(ROOT, "profiles", "conv_traffic_r1.json")
+    try:
+        with open(p) as f:
+            return float(json.load(f)["traffic_bytes_per_step"])
+    except Exception:
+        return None
+
+
 def _peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -281,8 +291,8 @@ def run_ours(args):
                             stage_ms_per_step=dict(preprocess=stage[0], inference=stage[1], postprocess=stage[2], stabilize=stage[3]),
                             detections_per_frame=float(det_counts.mean()), mask_boxes_per_frame=float(mask[1].mean()), homographies_ok=f"{ok_h}/{BATCH}",
                             matches_per_frame=float(out["stats"][:, 2].mean()), inliers_per_frame=float(out["stats"][:, 3].mean())),
-                roofline=dict(bound="tensor", achieved=conv_tflops, peak=peaks["tf_sust"], unit="TFLOP/s", frac=conv_tflops / peaks["tf_sust"], traffic=None,
-                              kernel="conv_tc_kernel x62 + conv0 (the conv stack of one step)", peak_source=peaks["src"] + " bf16_tflops_sustained",
+                roofline=dict(bound="tensor", achieved=conv_tflops, peak=peaks["tf_sust"], unit="TFLOP/s", frac=conv_tflops / peaks["tf_sust"], traffic=_conv_traffic(),
+                              kernel="conv_tc_kernel x63 (the conv stack of one 16-frame step = one launch set; traffic = dram bytes of that set, ncu)", peak_source=peaks["src"] + " bf16_tflops_sustained",
                               algorithmic_flops_per_launch_set=CONV_GFLOP_PER_FRAME * BATCH * 1e9),
                 cpu_baseline=cpu_base,
                 e2e=dict(value=e2e, unit=UNIT, h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h, ms_per_step=1000 * wall_e2e / args.steps),
