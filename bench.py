@@ -290,7 +290,8 @@ def run_ours(args):
                             frames_per_step=BATCH, parallelism=f"frame-range shard x{world}", l2="inputs (398 MB / step) larger than the 126 MB L2",
                             stage_ms_per_step=dict(preprocess=stage[0], inference=stage[1], postprocess=stage[2], stabilize=stage[3]),
                             detections_per_frame=float(det_counts.mean()), mask_boxes_per_frame=float(mask[1].mean()), homographies_ok=f"{ok_h}/{BATCH}",
-                            matches_per_frame=float(out["stats"][:, 2].mean()), inliers_per_frame=float(out["stats"][:, 3].mean())),
+                            matches_per_frame=float(out["stats"][:, 2].mean()), inliers_per_frame=float(out["stats"][:, 3].mean()),
+                            conv_launches_per_step=eng.conv_kernel_info()[0], convs_on_swapped_kernel=eng.conv_kernel_info()[1]),
                 roofline=dict(bound="tensor", achieved=conv_tflops, peak=peaks["tf_sust"], unit="TFLOP/s", frac=conv_tflops / peaks["tf_sust"], traffic=_conv_traffic(),
                               kernel="conv_tc_kernel x63 (the conv stack of one 16-frame step = one launch set; traffic = dram bytes of that set, ncu)", peak_source=peaks["src"] + " bf16_tflops_sustained",
                               algorithmic_flops_per_launch_set=CONV_GFLOP_PER_FRAME * BATCH * 1e9),

@@ -72,6 +72,7 @@ int gt_create(const gt_config* cfg, int device, gt_handle* out) {
   e->cfg = *cfg;
   e->device = device;
   if (const char* hm = getenv("GT_HALO")) e->halo_mode = atoi(hm);
+  if (const char* sm = getenv("GT_SWAP")) e->swap_mode = atoi(sm);
   auto fail = [&](int rc) { g_create_error = e->err; gt_destroy(e); return rc; };
 #define CR(expr) do { int _rc = (expr); if (_rc != GT_OK) return fail(_rc); } while (0)
 #define CRC(call) do { cudaError_t _er = (call); if (_er != cudaSuccess) { gt_set_error(e, "%s -> %s", #call, cudaGetErrorString(_er)); return fail(GT_ERR_CUDA); } } while (0)
@@ -181,7 +182,10 @@ int gt_conv_info(gt_handle e, int idx, gt_conv_desc* out) {
 }
 int gt_load_weights(gt_handle e, const float* const* weights, const float* const* biases, int n_convs) {
   ENTER(e);
-  return detector_load_weights(e, weights, biases, n_convs);
+  GT_TRY(detector_load_weights(e, weights, biases, n_convs));
+  GT_TRY(detector_autotune(e, e->stream));
+  GT_CUDA(e, cudaStreamSynchronize(e->stream));
+  return GT_OK;
 }
 
 // Starts the host->device copy of a batch on the copy stream into the idle staging buffer; a later gt_preprocess /
@@ -410,7 +414,9 @@ int gt_conv2d(gt_handle e, const uint16_t* x, int B, int H, int W, int cin, cons
     if (out_f32) { pa.out_f32 = (float*)dout; pa.out_img_stride = (long long)Ho * Wo; pa.out_ctot_f32 = cout; pa.out_coff_f32 = 0; }
     else pa.out = &ov;
     pa.res = residual ? &rv : nullptr;
+    e->plan_variant = e->swap_mode < 0 ? 1 : e->swap_mode;   // unit parity of the swapped kernel by default, GT_SWAP=0: the pixel-major one
     rc = conv_tc_plan(e, &op, pa);
+    e->plan_variant = 0;
     if (rc != GT_OK) break;
     const float* ws[1] = {w};
     const float* bs[1] = {bias};
@@ -668,6 +674,14 @@ int gt_stage_times(gt_handle e, float* ms4) {
   return GT_OK;
 }
 int64_t gt_launch_count(gt_handle e) { return e ? e->launches : -1; }
+int gt_conv_kernel_info(gt_handle e, int32_t* n_ops, int32_t* n_swapped) {
+  if (!e) return GT_ERR_INVALID;
+  int ns = 0;
+  for (const ConvOp& op : e->conv_ops) ns += op.swapped;
+  if (n_ops) *n_ops = (int)e->conv_ops.size();
+  if (n_swapped) *n_swapped = ns;
+  return GT_OK;
+}
 int gt_conv_stack_stats(gt_handle e, float* ms, double* flops) {
   if (!e) return GT_ERR_INVALID;
   if (ms) *ms = e->conv_ms;

@@ -101,13 +101,14 @@ struct ConvParams {
 struct ConvUpMaps { CUtensorMap m[4]; };   // the four (dy, dx) phases of the 2x nearest-upsampled destination
 
 struct ConvOp {
-  CUtensorMap tmA, tmB, tmOut;
+  CUtensorMap tmA, tmB, tmOut, tmRes;
   ConvUpMaps tmUp;
   ConvParams p;
   size_t smem = 0;
   bf16* w_dev = nullptr;     // [cout_pad][taps][cin_pad]
   float* b_dev = nullptr;    // [cout_pad]
   int cin = 0, cout = 0, cout_pad = 0, cin_pad = 0, k = 1, stride = 1;
+  int swapped = 0;           // 1: conv_sw.cu (weights = A operand, 256-pixel tile = B operand); tmA = activations, tmB = weights either way
   int n_src = 0;             // 1..3 canonical convs fused along cout
   int src[3] = {0, 0, 0};    // canonical conv indices
   double flops = 0;          // per image
@@ -136,6 +137,14 @@ int conv_tc_pack_weights(gt_engine* e, ConvOp* op, const float* const* w, const 
 int conv_tc_upload_packed(gt_engine* e, ConvOp* op, const uint16_t* packed, const float* bias);
 int conv_tc_launch(gt_engine* e, const ConvOp* op, int B, cudaStream_t st);
 int conv_tc_launch_range(gt_engine* e, const ConvOp* op, int b0, int nb, cudaStream_t st);
+// swapped-operand variant (conv_sw.cu); conv_tc_plan / conv_tc_launch* dispatch to it when the engine's swap_mode is on
+typedef CUresult (*GtEncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                    const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+GtEncodeTiledFn conv_tc_encode();
+int conv_tc_num_sms();
+int conv_sw_init(gt_engine* e);
+int conv_sw_plan(gt_engine* e, ConvOp* op, const ConvPlanArgs& a);
+int conv_sw_launch_range(gt_engine* e, const ConvOp* op, int b0, int nb, cudaStream_t st);
 
 // ---- small helpers ------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ float silu_f(float x) { return __fdividef(x, 1.0f + __expf(-x)); }  // MUFU.EX2 + MUFU.RCP

@@ -1,0 +1,466 @@
+// Swapped-operand tcgen05 implicit-GEMM convolution (sm_100a): D[cout][pixels] = W[cout][K] . X[pixels][K]^T.
+//
+// Why: with both operands in shared memory a K=16 tcgen05.mma with M = 128 costs ~130-150 cycles however small N is
+// (profiles/conv_findings_r1.md) -- its 4 KB A slice is read at ~32 B/clk.  YOLOv8s has cout in {32, 64, 128} on its large
+// feature maps, so "pixels as M, cout as N" (conv_tc.cu) leaves the pipe at 12-50 %.  Here the WEIGHTS are the A operand
+// (M = 128 output channels, zero rows above cout) and a 256-pixel spatial tile is the B operand (N = 256): one instruction
+// per 256 pixels x K16 instead of two, for every cout <= 128; cout > 128 runs ceil(cout / 128) M tiles.
+//
+// Same skeleton as conv_tc.cu: persistent CTA per SM, warp 0 TMA producer, warp 1 MMA issuer (elect.sync), warps 2..9
+// epilogue, shared-memory operand ring across tiles, two TMEM accumulators (2 x 256 columns = all of TMEM), weights resident
+// in shared memory when they fit.  The accumulator arrives transposed (TMEM lane = output channel, column = pixel), so the
+// epilogue thread owns ONE channel: bias is a register, and each value is written as a 2-byte (or 4-byte, fp32 head rows)
+// element into a [pixel][channel] staging granule in the TMA swizzle layout, stored with bulk tensor stores:
+//   16-bit: granule = 128 pixels x 64 channels (16 KB), filled by the two warps of a channel half; 4 granules per tile
+//   fp32  : granule = 32 pixels x 32 channels (4 KB), private to a warp, double-buffered
+#include <algorithm>
+
+#include "engine.cuh"
+#include "tc_ptx.cuh"
+
+namespace {
+
+constexpr int kSwThreads = 64 + kEpiWarps * 32;  // 320
+constexpr int kSwMaxStages = 8;
+constexpr int kPx = 256;        // pixels per tile (GEMM N)
+constexpr int kCo = 128;        // output channels per tile (GEMM M)
+constexpr int kStagingBytes = 64 * 1024;
+
+__device__ __forceinline__ void sts_u16(uint32_t saddr, uint32_t v) {
+  asm volatile("st.shared.b16 [%0], %1;" ::"r"(saddr), "h"((unsigned short)v) : "memory");
+}
+__device__ __forceinline__ void sts_u32(uint32_t saddr, uint32_t v) { asm volatile("st.shared.b32 [%0], %1;" ::"r"(saddr), "r"(v) : "memory"); }
+__device__ __forceinline__ void named_bar(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
+
+__device__ __forceinline__ uint32_t to_act16(float f, int fp16) {
+  if (fp16) { __half h = __float2half_rn(f); return (uint32_t)*reinterpret_cast<unsigned short*>(&h); }
+  __nv_bfloat16 h = __float2bfloat16_rn(f);
+  return (uint32_t)*reinterpret_cast<unsigned short*>(&h);
+}
+__device__ __forceinline__ float from_act16(unsigned short u, int fp16) {
+  if (fp16) return __half2float(*reinterpret_cast<__half*>(&u));
+  return __uint_as_float((uint32_t)u << 16);
+}
+
+__global__ void __launch_bounds__(kSwThreads, 1) conv_sw_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmX,
+                                                                const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ ConvUpMaps tmUp,
+                                                                const __grid_constant__ CUtensorMap tmRes, const ConvParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const int row_bytes = p.kb_elems * 2;
+  const int w_bytes = kCo * row_bytes;          // A: 128 weight rows of one k-block
+  const int x_bytes = kPx * row_bytes;          // B: 256 pixel rows of one k-block
+  const int stage_bytes = p.b_resident ? x_bytes : x_bytes + w_bytes;
+  uint8_t* w_res = smem + (size_t)p.stages * stage_bytes;
+  uint8_t* staging = w_res + (p.b_resident ? (size_t)p.num_kb * w_bytes : 0);
+  uint8_t* tail = staging + kStagingBytes;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(tail);
+  uint64_t* empty_bar = full_bar + kSwMaxStages;
+  uint64_t* tfull_bar = empty_bar + kSwMaxStages;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint64_t* wres_bar = tempty_bar + 2;
+  uint64_t* res_bar = wres_bar + 1;               // [4] residual granule landed (one per 16-bit staging granule)
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(res_bar + 4);
+  float* s_bias = reinterpret_cast<float*>(tmem_ptr_smem + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int total_tiles = p.total_tiles;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmW) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmX) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmOut) : "memory");
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(smem_u32(&full_bar[s]), 1);
+      mbar_init(smem_u32(&empty_bar[s]), 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(smem_u32(&tfull_bar[s]), 1);
+      mbar_init(smem_u32(&tempty_bar[s]), kEpiWarps);
+    }
+    mbar_init(smem_u32(wres_bar), 1);
+    for (int s = 0; s < 4; ++s) mbar_init(smem_u32(&res_bar[s]), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_smem)), "r"(512) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  if (warp >= 2) {
+    const int nb = p.n_tiles * kCo;
+    for (int i = threadIdx.x - 64; i < nb; i += kEpiWarps * 32) s_bias[i] = p.bias[i];
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  if (warp == 0) {
+    // ===== TMA producer (converged warp, elected lane issues) =====
+    if (p.b_resident) {
+      if (elect_one()) {
+        const uint32_t bb = smem_u32(wres_bar);
+        mbar_expect_tx(bb, (uint32_t)(p.num_kb * w_bytes));
+        for (int kb = 0; kb < p.num_kb; ++kb) tma_load_2d(smem_u32(w_res + (size_t)kb * w_bytes), &tmW, bb, kb * p.kb_elems, 0);
+      }
+      __syncwarp();
+    }
+    const uint32_t tx_bytes = (uint32_t)stage_bytes;
+    uint32_t s = 0, ph = 0;
+    TileIter ti;
+    ti.init(p, blockIdx.x, gridDim.x);
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ti.next(p)) {
+      const TileCoord t = ti.coord(p);
+      const int m0 = ti.nt * kCo;
+      const int cx = t.x0 * p.stride - p.pad, cy = t.y0 * p.stride - p.pad;
+      int kb = 0;
+      for (int dy = 0; dy < p.ksize; ++dy)
+        for (int dx = 0; dx < p.ksize; ++dx)
+          for (int kc = 0; kc < p.kc_blocks; ++kc, ++kb) {
+            mbar_wait(smem_u32(&empty_bar[s]), ph ^ 1u);
+            if (elect_one()) {
+              const uint32_t fb = smem_u32(&full_bar[s]);
+              mbar_expect_tx(fb, tx_bytes);
+              uint8_t* sx = smem + (size_t)s * stage_bytes;
+              tma_load_4d(smem_u32(sx), &tmX, fb, kc * p.kb_elems, cx + dx, cy + dy, t.n);
+              if (!p.b_resident) tma_load_2d(smem_u32(sx + x_bytes), &tmW, fb, kb * p.kb_elems, m0);
+            }
+            __syncwarp();
+            if (++s == (uint32_t)p.stages) { s = 0; ph ^= 1u; }
+          }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    const uint32_t fmt = p.fp16 ? 0u : 1u;
+    const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(kPx >> 3) << 17) | ((uint32_t)(kCo >> 4) << 24);
+    const uint32_t sbo = 8u * (uint32_t)row_bytes, layout = p.kb_elems == 64 ? 2u : (p.kb_elems == 32 ? 4u : 6u);
+    const int mma_per_kb = p.kb_elems >> 4;
+    if (p.b_resident) mbar_wait(smem_u32(wres_bar), 0);
+    uint32_t s = 0, ph = 0, li = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++li) {
+      const uint32_t as = li & 1u;
+      mbar_wait(smem_u32(&tempty_bar[as]), ((li >> 1) & 1u) ^ 1u);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t tacc = tmem_base + as * (uint32_t)kPx;
+      for (int kb = 0; kb < p.num_kb; ++kb) {
+        mbar_wait(smem_u32(&full_bar[s]), ph);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        if (elect_one()) {
+          uint8_t* sx = smem + (size_t)s * stage_bytes;
+          const uint64_t adesc = make_desc(smem_u32(p.b_resident ? w_res + (size_t)kb * w_bytes : sx + x_bytes), sbo, layout);   // weights
+          const uint64_t bdesc = make_desc(smem_u32(sx), sbo, layout);                                                          // pixels
+          for (int k = 0; k < mma_per_kb; ++k)
+            umma_f16(tacc, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kb | k) ? 1u : 0u);
+          umma_commit(smem_u32(&empty_bar[s]));
+        }
+        __syncwarp();
+        if (++s == (uint32_t)p.stages) { s = 0; ph ^= 1u; }
+      }
+      if (elect_one()) umma_commit(smem_u32(&tfull_bar[as]));
+      __syncwarp();
+    }
+  } else {
+    // ===== epilogue =====
+    const int q = warp & 3;             // TMEM lane quarter = channels [32q, 32q + 32) of the cout tile
+    const int h = (warp - 2) >> 2;      // pixel half: accumulator columns [128h, 128h + 128)
+    const int g = q >> 1;               // 16-bit staging granule (channel half) this warp fills together with its neighbour quarter
+    const int cg = (q & 1) * 32 + lane; // channel inside the granule
+    const bool gran_leader = ((q & 1) == 0) && lane == 0;
+    const int half_rows = p.th >> 1;    // image rows per pixel half
+    const int tw_shift = __ffs(p.tw) - 1, tw_mask = p.tw - 1;
+    const uint32_t stg = smem_u32(staging);
+    uint32_t li = 0, nstore = 0, res_uses = 0;
+    TileIter ti;
+    ti.init(p, blockIdx.x, gridDim.x);
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++li, ti.next(p)) {
+      const uint32_t as = li & 1u;
+      const TileCoord t = ti.coord(p);
+      const int m0 = ti.nt * kCo;
+      const int ch = m0 + q * 32 + lane;                 // this thread's output channel
+      const bool warp_active = (m0 + q * 32) < p.cout;   // any valid channel in this lane quarter
+      const float bias = s_bias[min(ch, p.n_tiles * kCo - 1)];
+      const int ybase = t.y0 + h * half_rows;            // first image row of this pixel half
+      const bool gran_active = !p.out_f32 && (m0 + g * 64) < p.cout;
+      const uint32_t buf = stg + (uint32_t)((h * 2 + g) * 16384);
+      if (gran_active) {
+        // the granule is free once last tile's bulk stores have read it; then (residual layers) the residual tile is fetched
+        // straight into the granule while the MMAs of this tile are still running
+        if (gran_leader) {
+          if (li > 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+          if (p.res) {
+            const uint32_t rb = smem_u32(&res_bar[h * 2 + g]);
+            mbar_expect_tx(rb, 16384u);
+            tma_load_4d(buf, &tmRes, rb, m0 + g * 64, t.x0, ybase, t.n);
+          }
+        }
+      }
+      if (lane == 0) mbar_wait(smem_u32(&tfull_bar[as]), (li >> 1) & 1u);
+      __syncwarp();
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + as * (uint32_t)kPx + (uint32_t)(h * 128);
+      if (!p.out_f32) {
+        // ---- 16-bit: granule (h, g) = 128 pixels x 64 channels, shared by quarters 2g and 2g+1 ----
+        if (gran_active) {
+          named_bar(2 + h * 2 + g, 64);                  // leader's wait_group.read is visible to the neighbour warp
+          if (p.res) { mbar_wait(smem_u32(&res_bar[h * 2 + g]), res_uses & 1u); ++res_uses; }
+        }
+        // staging address = row * 128 + ((chunk ^ (row & 7)) << 4) + (cg & 7) * 2; rows advance by compile-time steps
+        uint32_t base_k[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) base_k[k] = buf + (uint32_t)((((cg >> 3) ^ k) << 4) + (cg & 7) * 2);
+#pragma unroll 1
+        for (int c = 0; c < 4; ++c) {
+          uint32_t v[32];
+          if (warp_active) {
+            tmem_ld_x32(trow + (uint32_t)(c * 32), v);
+            tmem_ld_wait();
+          }
+          if (c == 3) {                                   // accumulator fully read by this warp
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) mbar_arrive(smem_u32(&tempty_bar[as]));
+          }
+          if (!warp_active) continue;
+          float f[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const float a = fmaf(__uint_as_float(v[i]), p.scale, bias);
+            f[i] = p.act ? silu_fast(a) : a;
+          }
+          const uint32_t rowoff = (uint32_t)(c * 32) * 128u;
+          if (p.res) {   // residual values sit in the granule at the very addresses this thread is about to overwrite
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              unsigned short rv;
+              asm volatile("ld.shared.u16 %0, [%1];" : "=h"(rv) : "r"(base_k[i & 7] + rowoff + (uint32_t)i * 128u));
+              f[i] += from_act16(rv, p.fp16);
+            }
+          }
+          if (p.fp16) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) sts_u16(base_k[i & 7] + rowoff + (uint32_t)i * 128u, to_act16(f[i], 1));
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) sts_u16(base_k[i & 7] + rowoff + (uint32_t)i * 128u, to_act16(f[i], 0));
+          }
+        }
+        if (gran_active) {
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          named_bar(2 + h * 2 + g, 64);
+          if (gran_leader) {
+            const int cch = m0 + g * 64;
+            tma_store_4d(&tmOut, buf, cch, t.x0, ybase, t.n);
+            if (p.up) {
+#pragma unroll
+              for (int d = 0; d < 4; ++d) tma_store_4d(tmUp.m + d, buf, cch, t.x0, ybase, t.n);
+            }
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+          }
+        }
+      } else {
+        // ---- fp32 head rows: per-warp granules of 32 pixels x 32 channels (128-byte rows), double-buffered ----
+        const int rows_per_chunk = 32 / p.tw;             // image rows covered by 32 pixels (tw <= 32 for fp32 outputs)
+        const uint32_t wbuf = stg + (uint32_t)((warp - 2) * 8192);
+#pragma unroll 1
+        for (int c = 0; c < 4; ++c) {
+          uint32_t v[32];
+          if (warp_active) {
+            tmem_ld_x32(trow + (uint32_t)(c * 32), v);
+            tmem_ld_wait();
+          }
+          if (c == 3) {
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) mbar_arrive(smem_u32(&tempty_bar[as]));
+          }
+          if (!warp_active) continue;
+          const uint32_t buf = wbuf + (nstore & 1u) * 4096u;
+          if (lane == 0 && nstore >= 2) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+          __syncwarp();
+          // row i (pixel), 4-byte element `lane`: chunk = lane >> 2, swizzled with row & 7
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const float a = fmaf(__uint_as_float(v[i]), p.scale, bias);
+            const float o = p.act ? silu_fast(a) : a;
+            sts_u32(buf + (uint32_t)i * 128u + (uint32_t)((((lane >> 2) ^ (i & 7)) << 4) + (lane & 3) * 4), __float_as_uint(o));
+          }
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_4d(&tmOut, buf, m0 + q * 32, t.x0, ybase + c * rows_per_chunk, t.n);
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+          }
+          ++nstore;
+        }
+      }
+    }
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+  }
+
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+  }
+}
+
+size_t sw_smem_bytes(int stages, int stage_bytes, int wres_bytes, int bias_floats) {
+  return 1024 + (size_t)stages * stage_bytes + (size_t)wres_bytes + kStagingBytes + (2 * kSwMaxStages + 9) * 8 + 8 + (size_t)bias_floats * 4 + 16;
+}
+
+void pick_tile256(int H, int W, bool f32, int* tw, int* th) {
+  const int cand[5][2] = {{16, 16}, {32, 8}, {8, 32}, {64, 4}, {128, 2}};
+  double best = -1;
+  for (int i = 0; i < 5; ++i) {
+    const int w = cand[i][0], h = cand[i][1];
+    if (f32 && w > 32) continue;   // fp32 granules are 32 pixels = whole image rows of the tile
+    const double util = (double)H * W / ((double)ceil_div(W, w) * w * (double)ceil_div(H, h) * h);
+    if (util > best + 1e-9) { best = util; *tw = w; *th = h; }
+  }
+}
+
+}  // namespace
+
+int conv_sw_init(gt_engine* e) {
+  GT_CUDA(e, cudaFuncSetAttribute(conv_sw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  return GT_OK;
+}
+
+int conv_sw_plan(gt_engine* e, ConvOp* op, const ConvPlanArgs& a) {
+  const View& in = a.in;
+  const int cin = a.cin, k = a.k, stride = a.stride;
+  const int kbe = (a.kb_elems == 64 && cin == 32) ? 32 : a.kb_elems;
+  GT_CHECK(e, in.C == cin, "conv plan: input view has %d channels, conv expects %d", in.C, cin);
+  GT_CHECK(e, (in.ctot % 8) == 0 && (in.coff % 8) == 0, "conv plan: input slice must be 16-byte aligned");
+  GT_CHECK(e, k >= 1 && k <= 3 && (stride == 1 || stride == 2), "conv plan: k=%d stride=%d unsupported", k, stride);
+  ConvParams& p = op->p;
+  memset(&p, 0, sizeof(p));
+  op->swapped = 1;
+  const int pad = a.pad >= 0 ? a.pad : k / 2;
+  const int Ho = a.Ho > 0 ? a.Ho : (in.H + 2 * pad - k) / stride + 1, Wo = a.Wo > 0 ? a.Wo : (in.W + 2 * pad - k) / stride + 1;
+  const int cout = a.cout;
+  op->cin = cin; op->cout = cout; op->k = k; op->stride = stride;
+  p.B = a.Bmax; p.H = Ho; p.W = Wo;
+  pick_tile256(Ho, Wo, a.out_f32 != nullptr, &p.tw, &p.th);
+  GT_CHECK(e, p.tw * stride <= 256 && p.th * stride <= 256, "conv plan: TMA box too large");
+  p.tiles_x = ceil_div(Wo, p.tw); p.tiles_y = ceil_div(Ho, p.th);
+  p.stride = stride; p.ksize = k; p.pad = pad;
+  p.kb_elems = kbe;
+  p.kc_blocks = ceil_div(cin, kbe);
+  op->cin_pad = p.kc_blocks * kbe;
+  p.num_kb = k * k * p.kc_blocks;
+  p.n_tiles = ceil_div(cout, kCo);
+  op->cout_pad = p.n_tiles * kCo;
+  p.BN = kCo;                       // TileIter::coord's n0 = nt * BN = first output channel of the tile
+  p.tmem_cols = 512; p.acc_stride = kPx;
+  const int w_bytes = kCo * kbe * 2, x_bytes = kPx * kbe * 2;
+  const int wres_bytes = p.num_kb * w_bytes;
+  const size_t budget = 227 * 1024;
+  p.b_resident = (p.n_tiles == 1 && wres_bytes <= 80 * 1024) ? 1 : 0;
+  const int stage_bytes = p.b_resident ? x_bytes : x_bytes + w_bytes;
+  const size_t fixed = sw_smem_bytes(0, stage_bytes, p.b_resident ? wres_bytes : 0, op->cout_pad);
+  int stages = (int)((budget - fixed) / stage_bytes);
+  if (stages > kSwMaxStages) stages = kSwMaxStages;
+  GT_CHECK(e, stages >= 2, "conv plan (swapped): operands do not fit shared memory");
+  p.stages = stages;
+  p.cout = cout; p.act = a.act; p.fp16 = e->cfg.act_dtype == GT_ACT_FP16 ? 1 : 0;
+  p.scale = a.scale;
+  if (a.out_f32) {
+    p.out_f32 = 1; p.out = a.out_f32; p.out_img_stride = a.out_img_stride; p.out_ctot = a.out_ctot_f32; p.out_coff = a.out_coff_f32;
+  } else {
+    const View* out = a.out;
+    GT_CHECK(e, out && out->H == Ho && out->W == Wo && out->C == cout, "conv plan: output view mismatch");
+    GT_CHECK(e, (out->ctot % 8) == 0 && (out->coff % 8) == 0 && (cout % 8) == 0, "conv plan: output slice must be 16-byte aligned");
+    p.out_f32 = 0; p.out = out->ptr; p.out_img_stride = (long long)Ho * Wo; p.out_ctot = out->ctot; p.out_coff = out->coff;
+  }
+  if (a.res) {
+    GT_CHECK(e, a.res->H == Ho && a.res->W == Wo && a.res->C == cout && !a.out_f32, "conv plan: residual view mismatch");
+    p.res = a.res->ptr; p.res_ctot = a.res->ctot; p.res_coff = a.res->coff;
+  }
+  if (a.up) {
+    GT_CHECK(e, a.up->H == 2 * Ho && a.up->W == 2 * Wo && a.up->C == cout && !a.out_f32, "conv plan: upsample view mismatch");
+    p.up = a.up->ptr; p.up_ctot = a.up->ctot; p.up_coff = a.up->coff;
+  }
+  op->smem = sw_smem_bytes(p.stages, stage_bytes, p.b_resident ? wres_bytes : 0, op->cout_pad);
+  op->flops = 2.0 * Ho * Wo * (double)cout * cin * k * k;
+  op->bytes = (double)in.H * in.W * cin * 2 + (double)Ho * Wo * cout * (a.out_f32 ? 4 : 2) * (a.up ? 5 : 1) + (a.res ? (double)Ho * Wo * cout * 2 : 0.0);
+
+  const size_t wn = (size_t)op->cout_pad * k * k * op->cin_pad;
+  GT_TRY(e->dev_alloc((void**)&op->w_dev, wn * sizeof(bf16)));
+  GT_TRY(e->dev_alloc((void**)&op->b_dev, (size_t)op->cout_pad * sizeof(float)));
+  GT_CUDA(e, cudaMemset(op->w_dev, 0, wn * sizeof(bf16)));
+  GT_CUDA(e, cudaMemset(op->b_dev, 0, (size_t)op->cout_pad * sizeof(float)));
+  p.bias = op->b_dev;
+
+  const CUtensorMapDataType dt = p.fp16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+  const CUtensorMapSwizzle sw = kbe == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : (kbe == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
+  {  // X: NHWC input slice {C, W, H, N}, box = one 256-pixel tile of one k-block (op->tmB keeps the "activation" map)
+    cuuint64_t gdim[4] = {(cuuint64_t)cin, (cuuint64_t)in.W, (cuuint64_t)in.H, (cuuint64_t)a.Bmax};
+    cuuint64_t gstr[3] = {(cuuint64_t)in.ctot * 2, (cuuint64_t)in.W * in.ctot * 2, (cuuint64_t)in.H * in.W * in.ctot * 2};
+    cuuint32_t box[4] = {(cuuint32_t)kbe, (cuuint32_t)(p.tw * stride), (cuuint32_t)(p.th * stride), 1};
+    cuuint32_t estr[4] = {1, (cuuint32_t)stride, (cuuint32_t)stride, 1};
+    CUresult r = conv_tc_encode()(&op->tmA, dt, 4, (void*)(in.ptr + in.coff), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+                                  CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    GT_CHECK(e, r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(X) failed: %d", (int)r);
+  }
+  {  // W: packed weights {Ktot, cout_pad}, box = 128 rows of one k-block
+    const cuuint64_t ktot = (cuuint64_t)k * k * op->cin_pad;
+    cuuint64_t gdim[2] = {ktot, (cuuint64_t)op->cout_pad};
+    cuuint64_t gstr[1] = {ktot * 2};
+    cuuint32_t box[2] = {(cuuint32_t)kbe, (cuuint32_t)kCo};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = conv_tc_encode()(&op->tmB, dt, 2, (void*)op->w_dev, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+                                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    GT_CHECK(e, r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(W) failed: %d", (int)r);
+  }
+  {  // output granules
+    auto enc = [&](CUtensorMap* tm, CUtensorMapDataType odt, void* base, int box_c, int box_w, int box_h, cuuint64_t W_, cuuint64_t H_,
+                   cuuint64_t pix_b, cuuint64_t row_b, cuuint64_t img_b) -> CUresult {
+      cuuint64_t gdim[4] = {(cuuint64_t)cout, W_, H_, (cuuint64_t)a.Bmax};
+      cuuint64_t gstr[3] = {pix_b, row_b, img_b};
+      cuuint32_t box[4] = {(cuuint32_t)box_c, (cuuint32_t)box_w, (cuuint32_t)box_h, 1};
+      cuuint32_t estr[4] = {1, 1, 1, 1};
+      return conv_tc_encode()(tm, odt, 4, base, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                              CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    };
+    CUresult r;
+    memset(&op->tmUp, 0, sizeof(op->tmUp));
+    memset(&op->tmRes, 0, sizeof(op->tmRes));
+    if (a.out_f32) {
+      const cuuint64_t ps = (cuuint64_t)a.out_ctot_f32 * 4;
+      GT_CHECK(e, (ps % 16) == 0 && (a.out_coff_f32 % 4) == 0, "conv plan: fp32 output rows must be 16-byte aligned");
+      r = enc(&op->tmOut, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (void*)(a.out_f32 + a.out_coff_f32), 32, p.tw, 32 / p.tw, Wo, Ho, ps, (cuuint64_t)Wo * ps,
+              (cuuint64_t)a.out_img_stride * ps);
+    } else {
+      const cuuint64_t ps = (cuuint64_t)a.out->ctot * 2;
+      r = enc(&op->tmOut, dt, (void*)(a.out->ptr + a.out->coff), 64, p.tw, p.th / 2, Wo, Ho, ps, (cuuint64_t)Wo * ps, (cuuint64_t)Ho * Wo * ps);
+      if (r == CUDA_SUCCESS && a.res) {
+        const cuuint64_t rs = (cuuint64_t)a.res->ctot * 2;
+        r = enc(&op->tmRes, dt, (void*)(a.res->ptr + a.res->coff), 64, p.tw, p.th / 2, Wo, Ho, rs, (cuuint64_t)Wo * rs, (cuuint64_t)Ho * Wo * rs);
+      }
+      if (r == CUDA_SUCCESS && a.up) {
+        const cuuint64_t us = (cuuint64_t)a.up->ctot * 2, W2 = (cuuint64_t)2 * Wo, H2 = (cuuint64_t)2 * Ho;
+        for (int d = 0; d < 4 && r == CUDA_SUCCESS; ++d) {
+          bf16* base = a.up->ptr + a.up->coff + ((size_t)(d >> 1) * W2 + (d & 1)) * a.up->ctot;
+          r = enc(&op->tmUp.m[d], dt, (void*)base, 64, p.tw, p.th / 2, Wo, Ho, 2 * us, 2 * W2 * us, H2 * W2 * us);
+        }
+      }
+    }
+    GT_CHECK(e, r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(out, swapped) failed: %d (cout=%d)", (int)r, cout);
+  }
+  return GT_OK;
+}
+
+int conv_sw_launch_range(gt_engine* e, const ConvOp* op, int b0, int nb, cudaStream_t st) {
+  ConvParams p = op->p;
+  p.B = nb;
+  p.img0 = b0;
+  p.total_tiles = p.tiles_x * p.tiles_y * nb * p.n_tiles;
+  const int grid = p.total_tiles < conv_tc_num_sms() ? p.total_tiles : conv_tc_num_sms();
+  conv_sw_kernel<<<grid, kSwThreads, op->smem, st>>>(op->tmB, op->tmA, op->tmOut, op->tmUp, op->tmRes, p);   // (weights, activations, ...)
+  e->launches++;
+  GT_CUDA(e, cudaGetLastError());
+  return GT_OK;
+}

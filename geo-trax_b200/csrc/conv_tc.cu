@@ -22,6 +22,7 @@
 #include <algorithm>
 
 #include "engine.cuh"
+#include "tc_ptx.cuh"
 
 namespace {
 
@@ -31,178 +32,11 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
 EncodeTiledFn g_encode = nullptr;
 int g_num_sms = GT_NUM_SMS;
 
-constexpr int kEpiWarps = 8;
 constexpr int kThreads = 64 + kEpiWarps * 32;  // 320
 constexpr int kMaxStages = 12;
 constexpr int kMaxHaloStages = 8;
 constexpr int kHaloW = 16;   // halo row pitch in pixels: 8-pixel tile rows + (k - 1) halo columns, padded so that every image row
                              // of the halo starts a fresh swizzle atom (8 rows)
-
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  asm volatile(
-      "{\n"
-      ".reg .pred P1;\n"
-      "WAIT_LOOP:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
-      "@P1 bra DONE;\n"
-      "bra WAIT_LOOP;\n"
-      "DONE:\n"
-      "}\n" ::"r"(bar),
-      "r"(parity)
-      : "memory");
-}
-__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1, int c2, int c3) {
-  asm volatile(
-      "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(dst),
-      "l"(tm), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
-      : "memory");
-}
-__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
-      "l"(tm), "r"(bar), "r"(c0), "r"(c1)
-      : "memory");
-}
-
-// K-major swizzled shared-memory operand descriptor (sm_100 UMMA format): start>>4 | SBO>>4 @32 | version 1 @46 |
-// layout type @61 (2 = SWIZZLE_128B with SBO 1024 B, 6 = SWIZZLE_32B with SBO 256 B: 8 rows of one swizzle atom).
-// LBO is unused for swizzled K-major operands.
-__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t sbo_bytes, uint32_t layout) {
-  uint64_t d = 0;
-  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
-  d |= (uint64_t)(sbo_bytes >> 4) << 32;
-  d |= (uint64_t)1 << 46;
-  d |= (uint64_t)layout << 61;
-  return d;
-}
-// Halo taps use the same descriptor with a start address that is a whole number of rows into a swizzle atom.  The hardware
-// applies the swizzle XOR on absolute shared-memory address bits (measured: base-offset field 0 reproduces torch.conv2d
-// bit-for-bit-equivalently for every shift, setting it to (addr >> 7) & 7 does not), so no base offset is encoded.
-
-// kind::f16 instruction descriptor: D = f32, A = B = bf16 or f16, both K-major, M = 128, N = bn.
-__device__ __forceinline__ uint32_t make_idesc(int bn, int fp16) {
-  const uint32_t fmt = fp16 ? 0u : 1u;  // a/b format: 0 = F16, 1 = BF16
-  return (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-}
-
-__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "setp.ne.b32 p, %4, 0;\n"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
-      "}\n" ::"r"(tmem_d),
-      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-
-__device__ __forceinline__ void tmem_ld_x32(uint32_t taddr, uint32_t* v) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
-        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
-        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
-        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-      : "r"(taddr)
-      : "memory");
-}
-__device__ __forceinline__ void tmem_ld_x16(uint32_t taddr, uint32_t* v) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
-        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
-      : "r"(taddr)
-      : "memory");
-}
-__device__ __forceinline__ void tmem_ld_x8(uint32_t taddr, uint32_t* v) {
-  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
-               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
-               : "r"(taddr)
-               : "memory");
-}
-__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-template <int CW>
-__device__ __forceinline__ void tmem_ld(uint32_t taddr, uint32_t* v) {
-  if constexpr (CW == 32) tmem_ld_x32(taddr, v);
-  else if constexpr (CW == 16) tmem_ld_x16(taddr, v);
-  else tmem_ld_x8(taddr, v);
-}
-
-__device__ __forceinline__ void tma_store_4d(const CUtensorMap* tm, uint32_t src, int c0, int c1, int c2, int c3) {
-  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(tm), "r"(src), "r"(c0), "r"(c1),
-               "r"(c2), "r"(c3)
-               : "memory");
-}
-__device__ __forceinline__ bool elect_one() {   // true in exactly one lane of the (converged) warp
-  uint32_t pred;
-  asm volatile(
-      "{\n"
-      ".reg .pred P;\n"
-      "elect.sync _|P, 0xffffffff;\n"
-      "selp.u32 %0, 1, 0, P;\n"
-      "}\n"
-      : "=r"(pred));
-  return pred != 0;
-}
-__device__ __forceinline__ float4 lds_f4(uint32_t saddr) {
-  float4 v;
-  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(saddr));
-  return v;
-}
-__device__ __forceinline__ void sts_u4(uint32_t saddr, const uint4& v) {
-  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
-}
-// SiLU in 5 instructions: FMUL, MUFU.EX2, FADD, MUFU.RCP, FMUL (flush-to-zero approximations, ~1e-6 relative error)
-__device__ __forceinline__ float silu_fast(float a) {
-  float e, r;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(a * -1.4426950408889634f));
-  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + e));
-  return a * r;
-}
-__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, %0;" ::"n"(kEpiWarps * 32) : "memory"); }
-
-struct TileCoord { int n, y0, x0, n0; };
-// Walks tile = blockIdx.x, += gridDim.x over the (image, tile row, tile column, N tile) space without per-tile divisions.
-struct TileIter {
-  int nt, tx, ty, n;       // current coordinates
-  int d_nt, d_tx, d_ty, d_n;  // gridDim.x decomposed in the same mixed radix
-  __device__ __forceinline__ void init(const ConvParams& p, int first, int step) {
-    nt = first % p.n_tiles; int m = first / p.n_tiles;
-    tx = m % p.tiles_x; m /= p.tiles_x;
-    ty = m % p.tiles_y; n = m / p.tiles_y;
-    d_nt = step % p.n_tiles; m = step / p.n_tiles;
-    d_tx = m % p.tiles_x; m /= p.tiles_x;
-    d_ty = m % p.tiles_y; d_n = m / p.tiles_y;
-  }
-  __device__ __forceinline__ void next(const ConvParams& p) {
-    nt += d_nt; if (nt >= p.n_tiles) { nt -= p.n_tiles; ++tx; }
-    tx += d_tx; if (tx >= p.tiles_x) { tx -= p.tiles_x; ++ty; }
-    ty += d_ty; if (ty >= p.tiles_y) { ty -= p.tiles_y; ++n; }
-    n += d_n;
-  }
-  __device__ __forceinline__ TileCoord coord(const ConvParams& p) const {
-    TileCoord t;
-    t.n = n + p.img0; t.x0 = tx * p.tw; t.y0 = ty * p.th; t.n0 = nt * p.BN;
-    return t;
-  }
-};
 
 // Epilogue of one accumulator: slabs of 128 rows x SLAB_BYTES (128 or 64) are staged in shared memory in the TMA swizzle
 // layout and written with one bulk tensor store each (plus four for the 2x nearest-upsampled copy).  CW = accumulator
@@ -534,6 +368,9 @@ size_t conv_smem_bytes(int stages, int stage_bytes, int halo_total, int bres_byt
 
 }  // namespace
 
+GtEncodeTiledFn conv_tc_encode() { return g_encode; }
+int conv_tc_num_sms() { return g_num_sms; }
+
 int conv_tc_init(gt_engine* e) {
   if (!g_encode) {
     void* fn = nullptr;
@@ -546,7 +383,7 @@ int conv_tc_init(gt_engine* e) {
   GT_CUDA(e, cudaGetDeviceProperties(&prop, e->device));
   g_num_sms = prop.multiProcessorCount;
   GT_CUDA(e, cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-  return GT_OK;
+  return conv_sw_init(e);
 }
 
 static void pick_tile(int H, int W, int* tw, int* th) {
@@ -566,6 +403,7 @@ static void pick_tile(int H, int W, int* tw, int* th) {
 
 int conv_tc_plan(gt_engine* e, ConvOp* op, const ConvPlanArgs& a) {
   GT_CHECK(e, g_encode != nullptr, "conv_tc_init not called");
+  if (e->plan_variant == 1) return conv_sw_plan(e, op, a);
   const View& in = a.in;
   const int cin = a.cin, k = a.k, stride = a.stride;
   const int kbe = (a.kb_elems == 64 && cin == 32) ? 32 : a.kb_elems;   // 32-channel inputs: 64-byte rows instead of half-empty 128-byte rows
@@ -780,6 +618,7 @@ int conv_tc_launch(gt_engine* e, const ConvOp* op, int B, cudaStream_t st) { ret
 
 // images [b0, b0 + nb) of the batch the op was planned for (tensor maps cover Bmax images; tiles are offset by b0)
 int conv_tc_launch_range(gt_engine* e, const ConvOp* op, int b0, int nb, cudaStream_t st) {
+  if (op->swapped) return conv_sw_launch_range(e, op, b0, nb, st);
   ConvParams p = op->p;
   p.B = nb;
   p.img0 = b0;

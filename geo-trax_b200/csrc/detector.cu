@@ -542,6 +542,19 @@ struct Builder {
     PlanOp po; po.type = OP_CONV; po.conv = (int)e->conv_ops.size() - 1;
     e->plan.push_back(po);
   }
+  // plans the op in the forced variant, or in both when the engine autotunes (conv_ops gets variant 0, conv_alt variant 1)
+  int plan_both(ConvOp& op, const ConvPlanArgs& a) {
+    const bool tune = e->swap_mode < 0;
+    e->plan_variant = tune ? 0 : e->swap_mode;
+    int r = conv_tc_plan(e, &op, a);
+    if (r != GT_OK || !tune) return r;
+    ConvOp alt = op;
+    e->plan_variant = 1;
+    r = conv_tc_plan(e, &alt, a);
+    e->plan_variant = 0;
+    if (r == GT_OK) e->conv_alt.push_back(alt);
+    return r;
+  }
   // 16-bit conv writing a channel slice; several canonical convs reading the same input are fused along cout
   void conv(std::vector<std::string> names, const View& in, const View& out, const View* res = nullptr, const View* up = nullptr) {
     if (rc != GT_OK) return;
@@ -552,7 +565,7 @@ struct Builder {
     const gt_conv_desc& d = e->conv_descs[op.src[0]];
     ConvPlanArgs a;
     a.in = in; a.Bmax = B; a.cin = d.cin; a.cout = cout; a.k = d.k; a.stride = d.stride; a.act = d.act; a.out = &out; a.res = res; a.up = up;
-    rc = conv_tc_plan(e, &op, a);
+    rc = plan_both(op, a);
     if (rc == GT_OK) push(op);
   }
   // final head conv writing fp32 raw rows
@@ -564,7 +577,7 @@ struct Builder {
     ConvPlanArgs a;
     a.in = in; a.Bmax = B; a.cin = d.cin; a.cout = d.cout; a.k = d.k; a.stride = d.stride; a.act = d.act;
     a.out_f32 = e->raw_head + (size_t)lvl_off * e->no_pad; a.out_img_stride = e->A; a.out_ctot_f32 = e->no_pad; a.out_coff_f32 = coff;
-    rc = conv_tc_plan(e, &op, a);
+    rc = plan_both(op, a);
     if (rc == GT_OK) push(op);
   }
   // layer 0: Conv(3 -> 32, k3, s2) as a stride-1 2x2 convolution over the 16-channel space-to-depth input (see stage 1)
@@ -575,9 +588,10 @@ struct Builder {
     ConvPlanArgs a;
     a.in = s2d; a.Bmax = B; a.cin = 16; a.cout = 32; a.k = 2; a.stride = 1; a.pad = 1; a.Ho = s2d.H; a.Wo = s2d.W; a.kb_elems = 16;
     a.act = 1; a.scale = 1.0f / 255.0f; a.out = &out;
-    rc = conv_tc_plan(e, &op, a);
+    rc = plan_both(op, a);
     if (rc != GT_OK) return;
     op.flops = 2.0 * s2d.H * s2d.W * 32.0 * 27.0;   // the algorithmic 3x3x3 work, not the zero-padded 2x2x16
+    if (!e->conv_alt.empty()) e->conv_alt.back().flops = op.flops;
     e->conv0_op = (int)e->conv_ops.size();
     push(op);
   }
@@ -770,39 +784,74 @@ int detector_build(gt_engine* e) {
   return GT_OK;
 }
 
+static int load_op_weights(gt_engine* e, ConvOp& op, bool is_conv0, const float* const* w, const float* const* b) {
+  const int fp16 = e->cfg.act_dtype == GT_ACT_FP16;
+  if (is_conv0) {
+    // layer 0: [32][3][3][3] (cout, RGB, ky, kx) -> [cout_pad][tap = dy*2+dx][16 = (r*2+c)*4 + ch]; the s2d tap (dy, r) holds kernel
+    // row ky: (0,1)->0, (1,0)->1, (1,1)->2, (0,0)-> none (zero); columns likewise.  Unscaled: the 1/255 is the epilogue scale.
+    std::vector<uint16_t> hw((size_t)op.cout_pad * 4 * 16, 0);
+    std::vector<float> hb(op.cout_pad, 0.f);
+    const int kmap[2][2] = {{-1, 0}, {1, 2}};
+    for (int co = 0; co < 32; ++co) {
+      for (int dy = 0; dy < 2; ++dy)
+        for (int dx = 0; dx < 2; ++dx)
+          for (int r = 0; r < 2; ++r)
+            for (int c = 0; c < 2; ++c) {
+              const int ky = kmap[dy][r], kx = kmap[dx][c];
+              if (ky < 0 || kx < 0) continue;
+              for (int chn = 0; chn < 3; ++chn)
+                hw[((size_t)co * 4 + dy * 2 + dx) * 16 + (r * 2 + c) * 4 + chn] = host_to_act(w[0][((co * 3 + chn) * 3 + ky) * 3 + kx], fp16);
+            }
+      hb[co] = b[0][co];
+    }
+    return conv_tc_upload_packed(e, &op, hw.data(), hb.data());
+  }
+  const float* ws[3];
+  const float* bs[3];
+  int couts[3];
+  for (int i = 0; i < op.n_src; ++i) { ws[i] = w[op.src[i]]; bs[i] = b[op.src[i]]; couts[i] = e->conv_descs[op.src[i]].cout; }
+  return conv_tc_pack_weights(e, &op, ws, bs, couts, op.n_src);
+}
+
 int detector_load_weights(gt_engine* e, const float* const* w, const float* const* b, int n) {
   GT_CHECK(e, n == (int)e->conv_descs.size(), "load_weights: expected %d convs, got %d", (int)e->conv_descs.size(), n);
-  const int fp16 = e->cfg.act_dtype == GT_ACT_FP16;
   for (size_t oi = 0; oi < e->conv_ops.size(); ++oi) {
-    ConvOp& op = e->conv_ops[oi];
-    if ((int)oi == e->conv0_op) {
-      // layer 0: [32][3][3][3] (cout, RGB, ky, kx) -> [32][tap = dy*2+dx][16 = (r*2+c)*4 + ch]; the s2d tap (dy, r) holds kernel
-      // row ky: (0,1)->0, (1,0)->1, (1,1)->2, (0,0)-> none (zero); columns likewise.  Unscaled: the 1/255 is the epilogue scale.
-      std::vector<uint16_t> hw((size_t)op.cout_pad * 4 * 16, 0);
-      std::vector<float> hb(op.cout_pad, 0.f);
-      const int kmap[2][2] = {{-1, 0}, {1, 2}};
-      for (int co = 0; co < 32; ++co) {
-        for (int dy = 0; dy < 2; ++dy)
-          for (int dx = 0; dx < 2; ++dx)
-            for (int r = 0; r < 2; ++r)
-              for (int c = 0; c < 2; ++c) {
-                const int ky = kmap[dy][r], kx = kmap[dx][c];
-                if (ky < 0 || kx < 0) continue;
-                for (int chn = 0; chn < 3; ++chn)
-                  hw[((size_t)co * 4 + dy * 2 + dx) * 16 + (r * 2 + c) * 4 + chn] = host_to_act(w[0][((co * 3 + chn) * 3 + ky) * 3 + kx], fp16);
-              }
-        hb[co] = b[0][co];
-      }
-      GT_TRY(conv_tc_upload_packed(e, &op, hw.data(), hb.data()));
-      continue;
-    }
-    const float* ws[3];
-    const float* bs[3];
-    int couts[3];
-    for (int i = 0; i < op.n_src; ++i) { ws[i] = w[op.src[i]]; bs[i] = b[op.src[i]]; couts[i] = e->conv_descs[op.src[i]].cout; }
-    GT_TRY(conv_tc_pack_weights(e, &op, ws, bs, couts, op.n_src));
+    GT_TRY(load_op_weights(e, e->conv_ops[oi], (int)oi == e->conv0_op, w, b));
+    if (!e->conv_alt.empty()) GT_TRY(load_op_weights(e, e->conv_alt[oi], (int)oi == e->conv0_op, w, b));
   }
   e->weights_loaded = true;
+  return GT_OK;
+}
+
+// Times both kernel variants of every conv on the full batch and keeps the faster one in conv_ops ("measure, don't guess":
+// which operand order wins depends on cout, K and the epilogue, see profiles/conv_findings_r1.md).
+int detector_autotune(gt_engine* e, cudaStream_t st) {
+  if (e->conv_alt.empty() || e->tuned) return GT_OK;
+  const int B = e->cfg.max_batch;
+  cudaEvent_t a, b;
+  GT_CUDA(e, cudaEventCreate(&a));
+  GT_CUDA(e, cudaEventCreate(&b));
+  auto time_op = [&](const ConvOp& op, float* ms) -> int {
+    GT_TRY(conv_tc_launch(e, &op, B, st));   // warm-up
+    GT_CUDA(e, cudaEventRecord(a, st));
+    for (int i = 0; i < 2; ++i) GT_TRY(conv_tc_launch(e, &op, B, st));
+    GT_CUDA(e, cudaEventRecord(b, st));
+    GT_CUDA(e, cudaEventSynchronize(b));
+    GT_CUDA(e, cudaEventElapsedTime(ms, a, b));
+    return GT_OK;
+  };
+  int n_swapped = 0;
+  for (size_t i = 0; i < e->conv_ops.size(); ++i) {
+    float t0 = 0, t1 = 0;
+    GT_TRY(time_op(e->conv_ops[i], &t0));
+    GT_TRY(time_op(e->conv_alt[i], &t1));
+    if (t1 < t0) { std::swap(e->conv_ops[i], e->conv_alt[i]); ++n_swapped; }
+  }
+  e->launches -= (int64_t)e->conv_ops.size() * 6;   // tuning launches are not part of any step
+  cudaEventDestroy(a);
+  cudaEventDestroy(b);
+  e->tuned = true;
+  e->n_swapped = n_swapped;
   return GT_OK;
 }
 

@@ -37,6 +37,8 @@ struct gt_engine {
   cudaStream_t stream = nullptr;
   std::string err;
   int64_t launches = 0;
+  int swap_mode = -1;                   // conv kernel per layer: -1 autotune (time both at weight load), 0 pixel-major (conv_tc.cu), 1 swapped (conv_sw.cu); GT_SWAP env
+  int plan_variant = 0;                 // variant conv_tc_plan builds right now (0 / 1)
   int halo_mode = 0;                    // conv A-operand staging: 0 per-tap boxes, 1 halo boxes + shifted descriptors (GT_HALO=1 enables: fewer L2->SM bytes, but the layers are tensor-issue bound)
   std::vector<void*> dev_allocs;
   std::vector<void*> host_allocs;
@@ -64,8 +66,11 @@ struct gt_engine {
 
   // detector
   bool weights_loaded = false;
+  bool tuned = false;
+  int n_swapped = 0;                                // convs running the swapped-operand kernel after autotune
   std::vector<gt_conv_desc> conv_descs;             // canonical list
-  std::vector<ConvOp> conv_ops;                     // fused tcgen05 ops
+  std::vector<ConvOp> conv_ops;                     // fused tcgen05 ops (the variant in use)
+  std::vector<ConvOp> conv_alt;                     // the other variant of each op (autotune), same indexing; empty when a variant is forced
   std::vector<PlanOp> plan;
   int conv0_op = -1;                                // index of layer 0 in conv_ops (custom weight packing)
   View feat_views[23];
@@ -136,6 +141,7 @@ struct gt_engine {
 // detector.cu
 int detector_build(gt_engine* e);
 int detector_load_weights(gt_engine* e, const float* const* w, const float* const* b, int n);
+int detector_autotune(gt_engine* e, cudaStream_t st);
 int detector_fill_pad(gt_engine* e, cudaStream_t st);
 int detector_preprocess(gt_engine* e, const uint8_t* frames_dev, int B, cudaStream_t st);
 int detector_forward(gt_engine* e, int B, cudaStream_t st);

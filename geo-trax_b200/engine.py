@@ -311,6 +311,12 @@ class Engine:
     def launch_count(self) -> int:
         return int(self.lib.gt_launch_count(self.h))
 
+    def conv_kernel_info(self):
+        """-> (fused conv launches per forward, how many run the swapped-operand kernel after autotune)."""
+        n, ns = C.c_int32(), C.c_int32()
+        self._ck(self.lib.gt_conv_kernel_info(self.h, C.byref(n), C.byref(ns)))
+        return n.value, ns.value
+
     def conv_stack_stats(self):
         ms, fl = C.c_float(), C.c_double()
         self._ck(self.lib.gt_conv_stack_stats(self.h, C.byref(ms), C.byref(fl)))

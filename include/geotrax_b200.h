@@ -173,6 +173,8 @@ int gt_stage_times(gt_handle h, float* ms4);
 int64_t gt_launch_count(gt_handle h);
 /* time (ms, CUDA events on the handle's stream) the conv stack took in the last gt_detect, and its FLOPs        */
 int gt_conv_stack_stats(gt_handle h, float* ms, double* flops);
+/* fused conv launches per forward, and how many of them the load-time autotune assigned to the swapped-operand kernel */
+int gt_conv_kernel_info(gt_handle h, int32_t* n_ops, int32_t* n_swapped);
 
 #ifdef __cplusplus
 }

@@ -48,6 +48,23 @@ def small_engine():
 
 
 @pytest.fixture(scope="session")
+def small_engine_tc():
+    """Same, forced onto the pixel-major conv kernel (conv_tc.cu); the default engines autotune and unit-test the swapped one."""
+    import os
+    old = os.environ.get("GT_SWAP")
+    os.environ["GT_SWAP"] = "0"
+    try:
+        eng = _make_engine("fp16")
+    finally:
+        if old is None:
+            os.environ.pop("GT_SWAP")
+        else:
+            os.environ["GT_SWAP"] = old
+    yield eng
+    eng.close()
+
+
+@pytest.fixture(scope="session")
 def small_engine_bf16():
     eng = _make_engine("bf16")
     yield eng

@@ -53,10 +53,10 @@ CONV_CASES = [
 ]
 
 
-@pytest.mark.parametrize("dtype", ["fp16", "bf16"])
+@pytest.mark.parametrize("dtype", ["fp16", "bf16", "fp16-pixel-major"])
 @pytest.mark.parametrize("case", CONV_CASES)
-def test_conv2d_tcgen05_matches_torch(small_engine, small_engine_bf16, case, dtype):
-    eng = small_engine if dtype == "fp16" else small_engine_bf16
+def test_conv2d_tcgen05_matches_torch(small_engine, small_engine_bf16, small_engine_tc, case, dtype):
+    eng = {"fp16": small_engine, "bf16": small_engine_bf16, "fp16-pixel-major": small_engine_tc}[dtype]
     rnd = lambda a: eng.act_to_f32(eng.f32_to_act(a))
     B, H, W, cin, cout, k, s, act, use_res, f32 = case
     g = torch.Generator().manual_seed(abs(hash(case)) % (2 ** 31))
@@ -76,7 +76,7 @@ def test_conv2d_tcgen05_matches_torch(small_engine, small_engine_bf16, case, dty
     got = out if f32 else eng.act_to_f32(out)
     assert got.shape == ref.shape
     # fp32 rows: accumulation order only; 16-bit rows: one output rounding on top (2^-9 bf16, 2^-12 fp16)
-    tol = 2e-3 if (f32 or dtype == "fp16") else 1e-2
+    tol = 2e-3 if (f32 or dtype != "bf16") else 1e-2
     err = np.abs(got - ref).max() / max(1e-6, np.abs(ref).max())
     assert err < tol, f"conv {case}: max-normalised error {err:.3e}"
 
@@ -120,6 +120,22 @@ def test_raw_head_within_1e2_of_fp32_oracle(small_engine, small_engine_bf16, dty
         rel_emu = np.linalg.norm(emu - ref) / np.linalg.norm(ref)
         print("bf16 emulated-on-CPU rel L2 error", rel_emu)
         assert rel < max(2.5 * rel_emu, 1e-2)   # the GPU also rounds the folded weights to bf16
+
+
+def test_pixel_major_kernel_raw_head(small_engine_tc):
+    """The forced pixel-major conv kernel (conv_tc.cu) through the whole network."""
+    from oracle import prepost
+    eng = small_engine_tc
+    assert eng.conv_kernel_info()[1] == 0
+    frames = _frames(2, 512, 768, seed=3)
+    eng.preprocess(frames)
+    eng.detect(2, conf=0.25)
+    raw = eng.raw_head(2)
+    m = _oracle_model(eng._sd)
+    with torch.no_grad():
+        _, ref = m(prepost.preprocess(list(frames), 384))
+    ref = ref.permute(0, 2, 1).numpy()
+    assert np.linalg.norm(raw - ref) / np.linalg.norm(ref) < 1e-2
 
 
 def test_intermediate_features_close(small_engine):
