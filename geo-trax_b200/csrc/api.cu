@@ -2,6 +2,7 @@
 #include <stdarg.h>
 #include <stdlib.h>
 
+#include <algorithm>
 #include <cmath>
 
 #include "engine.cuh"
@@ -73,6 +74,9 @@ int gt_create(const gt_config* cfg, int device, gt_handle* out) {
   e->device = device;
   if (const char* hm = getenv("GT_HALO")) e->halo_mode = atoi(hm);
   if (const char* sm = getenv("GT_SWAP")) e->swap_mode = atoi(sm);
+  if (const char* ov = getenv("GT_OVERLAP")) e->overlap = atoi(ov);
+  if (const char* kb = getenv("GT_CONV_SMEM_KB")) e->conv_smem_kb = std::min(227, std::max(96, atoi(kb)));
+  if (e->overlap && !getenv("GT_CONV_SMEM_KB")) e->conv_smem_kb = 200;
   auto fail = [&](int rc) { g_create_error = e->err; gt_destroy(e); return rc; };
 #define CR(expr) do { int _rc = (expr); if (_rc != GT_OK) return fail(_rc); } while (0)
 #define CRC(call) do { cudaError_t _er = (call); if (_er != cudaSuccess) { gt_set_error(e, "%s -> %s", #call, cudaGetErrorString(_er)); return fail(GT_ERR_CUDA); } } while (0)
@@ -106,6 +110,13 @@ int gt_create(const gt_config* cfg, int device, gt_handle* out) {
   CR(e->dev_alloc((void**)&e->frames_dev, (size_t)B * c.frame_h * c.frame_w * 3));
   CR(e->dev_alloc((void**)&e->frames_dev2, (size_t)B * c.frame_h * c.frame_w * 3));
   CRC(cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking));
+  {
+    int lo = 0, hi = 0;
+    CRC(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    CRC(cudaStreamCreateWithPriority(&e->aux_stream, cudaStreamNonBlocking, lo));
+    CRC(cudaEventCreateWithFlags(&e->ev_pre, cudaEventDisableTiming));
+    CRC(cudaEventCreateWithFlags(&e->ev_front, cudaEventDisableTiming));
+  }
   for (int i = 0; i < 2; ++i) {
     CRC(cudaEventCreateWithFlags(&e->ev_copied[i], cudaEventDisableTiming));
     CRC(cudaEventCreateWithFlags(&e->ev_consumed[i], cudaEventDisableTiming));
@@ -135,6 +146,9 @@ int gt_destroy(gt_handle e) {
     if (e->ev_consumed[i]) cudaEventDestroy(e->ev_consumed[i]);
   }
   if (e->copy_stream) cudaStreamDestroy(e->copy_stream);
+  if (e->aux_stream) cudaStreamDestroy(e->aux_stream);
+  if (e->ev_pre) cudaEventDestroy(e->ev_pre);
+  if (e->ev_front) cudaEventDestroy(e->ev_front);
   if (e->stream) cudaStreamDestroy(e->stream);
   delete e;
   return GT_OK;
@@ -462,10 +476,12 @@ int gt_set_reference(gt_handle e, int frame_slot, const float* boxes, int nboxes
   return GT_OK;
 }
 
-static int stabilize_impl(gt_engine* e, int B, cudaStream_t st) {
+static int stabilize_impl(gt_engine* e, int B, cudaStream_t st, bool front_on_aux = false) {
   GT_CHECK(e, e->have_ref, "gt_stabilize: no reference frame set");
   GT_CUDA(e, cudaEventRecord(e->ev[5], st));
-  GT_TRY(orb_run(e, 0, B, false, true, st));
+  if (front_on_aux) GT_CUDA(e, cudaStreamWaitEvent(st, e->ev_front, 0));   // pyramid / blur / FAST were produced on the aux stream
+  else GT_TRY(orb_front(e, 0, B, st));
+  GT_TRY(orb_back(e, 0, B, false, true, st));
   GT_TRY(stab_match_and_fit(e, B, st));
   GT_CUDA(e, cudaEventRecord(e->ev[6], st));
   return GT_OK;
@@ -640,6 +656,13 @@ int gt_extract_batch(gt_handle e, const uint8_t* frames, int B, int first_is_ref
     GT_TRY(gt_prefetch_frames(e, nxt, e->deferred_B));
   }
   GT_TRY(gt_preprocess(e, frames, B, st));
+  const bool ov = e->overlap != 0;
+  if (ov) {   // fork: the mask-independent half of ORB needs only the gray frames and runs beside the detector
+    GT_CUDA(e, cudaEventRecord(e->ev_pre, st));
+    GT_CUDA(e, cudaStreamWaitEvent(e->aux_stream, e->ev_pre, 0));
+    GT_TRY(orb_front(e, 0, B, e->aux_stream));
+    GT_CUDA(e, cudaEventRecord(e->ev_front, e->aux_stream));
+  }
   GT_TRY(detect_impl(e, B, conf, iou, agnostic, classes_mask, st));
   dim3 g((unsigned)ceil_div(md, 256), (unsigned)B);
   dets_to_xywh_kernel<<<g, 256, 0, st>>>(e->det_out, e->det_count, obb ? 7 : 6, md, e->det_xywh_dev, e->det_nbox_dev, B, obb);
@@ -656,7 +679,7 @@ int gt_extract_batch(gt_handle e, const uint8_t* frames, int B, int first_is_ref
     GT_TRY(orb_run(e, R, 1, true, true, st));
     e->have_ref = true;
   }
-  GT_TRY(stabilize_impl(e, B, st));
+  GT_TRY(stabilize_impl(e, B, st, ov));
   GT_TRY(warp_boxes_run(e, e->H_dev, e->H_status, e->det_xywh_dev, e->boxes_stab_dev, e->det_nbox_dev, B, md, st));
   GT_TRY(copy_dets(e, B, out_boxes, out_counts, nullptr, st));
   GT_TRY(to_caller(e, out_boxes_stab, e->boxes_stab_dev, (size_t)B * md * 16, st));

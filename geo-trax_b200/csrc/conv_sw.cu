@@ -357,11 +357,16 @@ int conv_sw_plan(gt_engine* e, ConvOp* op, const ConvPlanArgs& a) {
   p.tmem_cols = 512; p.acc_stride = kPx;
   const int w_bytes = kCo * kbe * 2, x_bytes = kPx * kbe * 2;
   const int wres_bytes = p.num_kb * w_bytes;
-  const size_t budget = 227 * 1024;
+  const size_t budget = (size_t)e->conv_smem_kb * 1024;
   p.b_resident = (p.n_tiles == 1 && wres_bytes <= 80 * 1024) ? 1 : 0;
-  const int stage_bytes = p.b_resident ? x_bytes : x_bytes + w_bytes;
-  const size_t fixed = sw_smem_bytes(0, stage_bytes, p.b_resident ? wres_bytes : 0, op->cout_pad);
-  int stages = (int)((budget - fixed) / stage_bytes);
+  int stage_bytes = 0, stages = 0;
+  for (int attempt = 0; attempt < 2; ++attempt) {   // resident weights only if at least 3 ring stages remain
+    stage_bytes = p.b_resident ? x_bytes : x_bytes + w_bytes;
+    const size_t fixed = sw_smem_bytes(0, stage_bytes, p.b_resident ? wres_bytes : 0, op->cout_pad);
+    stages = fixed < budget ? (int)((budget - fixed) / stage_bytes) : 0;
+    if (stages >= 3 || !p.b_resident) break;
+    p.b_resident = 0;
+  }
   if (stages > kSwMaxStages) stages = kSwMaxStages;
   GT_CHECK(e, stages >= 2, "conv plan (swapped): operands do not fit shared memory");
   p.stages = stages;

@@ -454,8 +454,8 @@ int conv_tc_plan(gt_engine* e, ConvOp* op, const ConvPlanArgs& a) {
   p.acc_stride = p.tmem_cols / 2;
   const int a_bytes = 128 * kbe * 2, b_bytes = p.BN * kbe * 2;
   const int bres_bytes = p.num_kb * b_bytes;
-  p.b_resident = (p.n_tiles == 1 && bres_bytes <= 112 * 1024) ? 1 : 0;
-  const size_t budget = 227 * 1024;
+  p.b_resident = (p.n_tiles == 1 && bres_bytes <= 112 * 1024 && (size_t)bres_bytes + 3 * a_bytes + 40 * 1024 <= (size_t)e->conv_smem_kb * 1024) ? 1 : 0;
+  const size_t budget = (size_t)e->conv_smem_kb * 1024;
   int stage_bytes = p.b_resident ? a_bytes : a_bytes + b_bytes;
   int halo_total = 0;
   if (want_halo) {

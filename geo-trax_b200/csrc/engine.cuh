@@ -55,6 +55,10 @@ struct gt_engine {
   uint8_t* frames_dev = nullptr;        // [B][H][W][3] staging buffer 0 (host inputs)
   uint8_t* frames_dev2 = nullptr;       // staging buffer 1: gt_prefetch_frames copies batch i+1 while batch i computes
   cudaStream_t copy_stream = nullptr;
+  cudaStream_t aux_stream = nullptr;    // low priority: the mask-independent half of ORB runs here next to the detector
+  cudaEvent_t ev_pre = nullptr, ev_front = nullptr;
+  int overlap = 0;                      // GT_OVERLAP=1: ORB front on the aux stream beside the detector (measured +2 %: the conv CTAs own the SMs)
+  int conv_smem_kb = 227;               // dynamic smem budget of the conv kernels (200 with GT_OVERLAP=1 to leave room for ORB blocks); GT_CONV_SMEM_KB
   cudaEvent_t ev_copied[2] = {nullptr, nullptr};   // H2D of staging buffer k finished (copy stream)
   cudaEvent_t ev_consumed[2] = {nullptr, nullptr}; // the preprocess kernel that read staging buffer k finished
   const void* prefetched_src[2] = {nullptr, nullptr};
@@ -152,6 +156,8 @@ int nms_run(gt_engine* e, const float* pred_dev, int B, int A, int nc, int rotat
 // orb.cu
 int orb_build(gt_engine* e);
 int orb_run(gt_engine* e, int slot0, int nslots, bool as_reference, bool build_mask, cudaStream_t st);
+int orb_front(gt_engine* e, int slot0, int nslots, cudaStream_t st);   // image pyramid, blur, FAST: independent of the mask
+int orb_back(gt_engine* e, int slot0, int nslots, bool as_reference, bool build_mask, cudaStream_t st);
 // match_ransac.cu
 int stab_build(gt_engine* e);
 int stab_match_and_fit(gt_engine* e, int B, cudaStream_t st);

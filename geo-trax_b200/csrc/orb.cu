@@ -44,45 +44,36 @@ __global__ void mask_rects_kernel(uint8_t* __restrict__ mask, size_t slab, const
 }
 
 // ---- one pyramid level from the previous one: cv2.resize(INTER_LINEAR_EXACT) in Q8.8 x Q8.8, (v + 2^15) >> 16 -------------
-// One thread = 4 adjacent output pixels of BOTH planes (image and mask share coordinates and weights; the mask is
-// thresholded: <= 254 -> 0).  blockIdx.z = slot.
-__global__ void __launch_bounds__(256) pyr_resize_kernel(uint8_t* __restrict__ img, uint8_t* __restrict__ msk, size_t slab, int slot0,
-                                                         size_t src_off, int sw, int sh, size_t dst_off, int dw, int dh,
-                                                         const int* __restrict__ xofs, const int* __restrict__ xc1,
+// One thread = 4 adjacent output pixels.  MASK = false: image plane.  MASK = true: mask plane, thresholded (<= 254 -> 0); the
+// mask pyramid depends on the detections and is built later than the image pyramid (see orb_front / orb_back).
+template <bool MASK>
+__global__ void __launch_bounds__(256) pyr_resize_kernel(uint8_t* __restrict__ plane, size_t slab, int slot0, size_t src_off, int sw, int sh,
+                                                         size_t dst_off, int dw, int dh, const int* __restrict__ xofs, const int* __restrict__ xc1,
                                                          const int* __restrict__ yofs, const int* __restrict__ yc1) {
   const int x4 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
   const int y = blockIdx.y;
   if (x4 >= dw) return;
   const int slot = slot0 + blockIdx.z;
   const int yo = __ldg(yofs + y), cy1 = __ldg(yc1 + y), cy0 = 256 - cy1, yo1 = min(yo + 1, sh - 1);
-  int xo[4], cx1[4];
+  uint8_t* base = plane + (size_t)slot * slab;
+  const uint8_t* r0 = base + src_off + (size_t)yo * sw;
+  const uint8_t* r1 = base + src_off + (size_t)yo1 * sw;
+  const int nvalid = min(4, dw - x4);
+  uint32_t packed = 0;
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
     const int x = min(x4 + k, dw - 1);
-    xo[k] = __ldg(xofs + x);
-    cx1[k] = __ldg(xc1 + x);
+    const int a = __ldg(xofs + x), b = min(a + 1, sw - 1), c1 = __ldg(xc1 + x), c0 = 256 - c1;
+    const int h0 = r0[a] * c0 + r0[b] * c1;
+    const int h1 = r1[a] * c0 + r1[b] * c1;
+    int v = (h0 * cy0 + h1 * cy1 + 32768) >> 16;
+    if (MASK && v <= 254) v = 0;
+    packed |= (uint32_t)v << (8 * k);
   }
-  const int nvalid = min(4, dw - x4);
-#pragma unroll
-  for (int plane = 0; plane < 2; ++plane) {
-    uint8_t* base = (plane ? msk : img) + (size_t)slot * slab;
-    const uint8_t* r0 = base + src_off + (size_t)yo * sw;
-    const uint8_t* r1 = base + src_off + (size_t)yo1 * sw;
-    uint32_t packed = 0;
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const int a = xo[k], b = min(a + 1, sw - 1), c1 = cx1[k], c0 = 256 - c1;
-      const int h0 = r0[a] * c0 + r0[b] * c1;
-      const int h1 = r1[a] * c0 + r1[b] * c1;
-      int v = (h0 * cy0 + h1 * cy1 + 32768) >> 16;
-      if (plane && v <= 254) v = 0;
-      packed |= (uint32_t)v << (8 * k);
-    }
-    uint8_t* d = base + dst_off + (size_t)y * dw + x4;
-    if (nvalid == 4 && (reinterpret_cast<uintptr_t>(d) & 3) == 0) *reinterpret_cast<uint32_t*>(d) = packed;
-    else
-      for (int k = 0; k < nvalid; ++k) d[k] = (uint8_t)(packed >> (8 * k));
-  }
+  uint8_t* d = base + dst_off + (size_t)y * dw + x4;
+  if (nvalid == 4 && (reinterpret_cast<uintptr_t>(d) & 3) == 0) *reinterpret_cast<uint32_t*>(d) = packed;
+  else
+    for (int k = 0; k < nvalid; ++k) d[k] = (uint8_t)(packed >> (8 * k));
 }
 
 // ---- FAST-9/16 score + 3x3 non-max suppression + mask / border filter -> candidate list ------------------------------------
@@ -90,7 +81,9 @@ __global__ void __launch_bounds__(256) pyr_resize_kernel(uint8_t* __restrict__ i
 //   1. corner test for every position of the (tile + 1) ring: compass quick-reject, then the 16-bit arc masks; corners are
 //      compacted into a shared list;
 //   2. exact corner score (OpenCV cornerScore<16>) only for the listed positions;
-//   3. 3x3 non-max suppression, border / mask filter, block-level compaction into the per-(frame, level) candidate list.
+//   3. 3x3 non-max suppression, border filter, block-level compaction into the per-(frame, level) candidate list.
+// The vehicle mask is NOT applied here (it depends on the detections, which are computed concurrently): orb_select_kernel
+// drops masked candidates before its score cut, which is equivalent to OpenCV's order (mask, then retain-best).
 #define FT_X 64
 #define FT_Y 32
 #define FT_LIST ((FT_X + 2) * (FT_Y + 2))
@@ -155,7 +148,7 @@ __device__ __forceinline__ int fast_corner_score(const uint8_t (*t)[FT_X + 8], i
   return best > kFastThr ? best - 1 : 0;
 }
 
-__global__ void __launch_bounds__(256) fast_kernel(const uint8_t* __restrict__ img, const uint8_t* __restrict__ msk, size_t slab, int slot0,
+__global__ void __launch_bounds__(256) fast_kernel(const uint8_t* __restrict__ img, size_t slab, int slot0,
                                                    size_t lvl_off, int w, int h, unsigned int* __restrict__ cand, uint8_t* __restrict__ cscore,
                                                    size_t cand_slab, size_t cand_off, int cand_cap, int* __restrict__ counts, int level) {
   __shared__ __align__(16) uint8_t s_img[FT_Y + 8][FT_X + 8];
@@ -212,8 +205,7 @@ __global__ void __launch_bounds__(256) fast_kernel(const uint8_t* __restrict__ i
     s_sc[sy][sx] = (uint8_t)fast_corner_score(s_img, sx + 3, sy + 3);
   }
   __syncthreads();
-  // phase 3: 3x3 NMS over the listed corners that lie inside the tile, border + mask filter
-  const uint8_t* mk = msk + (size_t)slot * slab + lvl_off;
+  // phase 3: 3x3 NMS over the listed corners that lie inside the tile, border filter
   for (int k = threadIdx.x; k < s_nl; k += 256) {
     const int i = s_list[k];
     const int sy = i / (FT_X + 2), sx = i - sy * (FT_X + 2);
@@ -226,7 +218,6 @@ __global__ void __launch_bounds__(256) fast_kernel(const uint8_t* __restrict__ i
     if (!(sc > s_sc[ly][lx] && sc > s_sc[ly][lx + 1] && sc > s_sc[ly][lx + 2] && sc > s_sc[ly + 1][lx] && sc > s_sc[ly + 1][lx + 2] &&
           sc > s_sc[ly + 2][lx] && sc > s_sc[ly + 2][lx + 1] && sc > s_sc[ly + 2][lx + 2]))
       continue;
-    if (mk[(size_t)gy * w + gx] == 0) continue;
     const int q = atomicAdd(&s_n, 1);  // NMS guarantees <= 1 survivor per 2x2 block, so q < FT_X*FT_Y/4
     s_xy[q] = ((unsigned)gy << 16) | (unsigned)gx;
     s_s[q] = (uint8_t)sc;
@@ -269,7 +260,8 @@ __device__ __forceinline__ unsigned f2key(float f) {  // order-preserving float 
   return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
 }
 
-__global__ void __launch_bounds__(1024) orb_select_kernel(const uint8_t* __restrict__ img, size_t slab, int slot0, const OrbLevel* __restrict__ lv,
+__global__ void __launch_bounds__(1024) orb_select_kernel(const uint8_t* __restrict__ img, const uint8_t* __restrict__ msk, size_t slab, int slot0,
+                                                          const OrbLevel* __restrict__ lv,
                                                           const unsigned int* __restrict__ cand, const uint8_t* __restrict__ cscore,
                                                           size_t cand_slab, const int* __restrict__ fast_count, int as_ref,
                                                           unsigned int* __restrict__ sel_xy, float* __restrict__ sel_resp,
@@ -278,7 +270,7 @@ __global__ void __launch_bounds__(1024) orb_select_kernel(const uint8_t* __restr
   unsigned* s_keys = reinterpret_cast<unsigned*>(s_raw);                           // [kSelCap] response keys
   unsigned long long* s_sort = reinterpret_cast<unsigned long long*>(s_raw);       // [kLvlKeep] aliases s_keys after the cut
   __shared__ int s_hist[256];
-  __shared__ int s_cut, s_m, s_k, s_need;
+  __shared__ int s_cut, s_m, s_k, s_need, s_nu;
   __shared__ unsigned s_prefix;
   const int level = blockIdx.x, slot = slot0 + blockIdx.y;
   const OrbLevel L = lv[level];
@@ -289,17 +281,24 @@ __global__ void __launch_bounds__(1024) orb_select_kernel(const uint8_t* __restr
   unsigned int* oxy = sel_xy + ((size_t)slot * GT_ORB_LEVELS + level) * kSelCap;
   float* orsp = sel_resp + ((size_t)slot * GT_ORB_LEVELS + level) * kSelCap;
   const uint8_t* im = img + (size_t)slot * slab + L.off;
+  const uint8_t* mk = msk + (size_t)slot * slab + L.off;
+  auto unmasked = [&](unsigned xy) { return mk[(size_t)(xy >> 16) * L.w + (xy & 0xFFFF)] != 0; };
 
-  // (a) FAST-score histogram and cut: keep score >= score of the (2*quota)-th best
+  // (a) FAST-score histogram over the unmasked candidates and cut: keep score >= score of the (2*quota)-th best
   for (int i = threadIdx.x; i < 256; i += blockDim.x) s_hist[i] = 0;
   if (threadIdx.x == 0) { s_m = 0; s_k = 0; }
   __syncthreads();
-  for (int i = threadIdx.x; i < n; i += blockDim.x) atomicAdd(&s_hist[csc[i]], 1);
+  if (threadIdx.x == 0) s_nu = 0;
+  __syncthreads();
+  int my_unmasked = 0;
+  for (int i = threadIdx.x; i < n; i += blockDim.x)
+    if (unmasked(cxy[i])) { atomicAdd(&s_hist[csc[i]], 1); ++my_unmasked; }
+  if (my_unmasked) atomicAdd(&s_nu, my_unmasked);
   __syncthreads();
   if (threadIdx.x == 0) {
     int cut = 0;
     const int want = 2 * quota;
-    if (n > want) {
+    if (s_nu > want) {
       int acc = 0;
       for (int s = 255; s >= 0; --s) {
         acc += s_hist[s];
@@ -312,7 +311,7 @@ __global__ void __launch_bounds__(1024) orb_select_kernel(const uint8_t* __restr
   const int cut = s_cut;
   // (b) compact survivors + Harris response
   for (int i = threadIdx.x; i < n; i += blockDim.x) {
-    if (csc[i] >= cut) {
+    if (csc[i] >= cut && unmasked(cxy[i])) {
       const int k = atomicAdd(&s_m, 1);
       if (k < kSelCap) {
         const unsigned xy = cxy[i];
@@ -644,7 +643,35 @@ int orb_build(gt_engine* e) {
   return GT_OK;
 }
 
-int orb_run(gt_engine* e, int slot0, int nslots, bool as_reference, bool build_mask, cudaStream_t st) {
+// Mask-independent half of ORB: image pyramid, blurred pyramid, FAST candidates.  Needs only the gray level 0, so it can run on
+// a second stream while the detector works on the same frames.
+int orb_front(gt_engine* e, int slot0, int nslots, cudaStream_t st) {
+  const size_t slab = e->pyr_bytes;
+  for (int l = 1; l < GT_ORB_LEVELS; ++l) {
+    const OrbLevel& S = e->lv[l - 1];
+    const OrbLevel& D = e->lv[l];
+    int* const* t = e->rs_tab[l];
+    dim3 g((unsigned)ceil_div(D.w, 4 * 256), (unsigned)D.h, (unsigned)nslots);
+    pyr_resize_kernel<false><<<g, 256, 0, st>>>(e->pyr, slab, slot0, S.off, S.w, S.h, D.off, D.w, D.h, t[0], t[1], t[2], t[3]);
+    e->launches++;
+  }
+  GT_CUDA(e, cudaMemsetAsync(e->fast_count + (size_t)slot0 * GT_ORB_LEVELS, 0, (size_t)nslots * GT_ORB_LEVELS * sizeof(int), st));
+  for (int l = 0; l < GT_ORB_LEVELS; ++l) {
+    const OrbLevel& L = e->lv[l];
+    dim3 g((unsigned)ceil_div(L.w, FT_X), (unsigned)ceil_div(L.h, FT_Y), (unsigned)nslots);
+    fast_kernel<<<g, 256, 0, st>>>(e->pyr, slab, slot0, L.off, L.w, L.h, e->fast_cand, e->fast_score, e->cand_total, L.cand_off, L.cand_cap,
+                                   e->fast_count, l);
+    dim3 gb((unsigned)ceil_div(L.w, 64), (unsigned)ceil_div(L.h, 16), (unsigned)nslots);
+    blur7_kernel<<<gb, 256, 0, st>>>(e->pyr, e->pyr_blur, slab, slot0, L.off, L.w, L.h);
+    e->launches += 2;
+  }
+  GT_CUDA(e, cudaGetLastError());
+  return GT_OK;
+}
+
+// Mask-dependent half: vehicle mask (level 0 from the boxes unless the caller supplied one) + its pyramid, masked candidate
+// selection (score cut, Harris, quota cut), orientation + descriptors.
+int orb_back(gt_engine* e, int slot0, int nslots, bool as_reference, bool build_mask, cudaStream_t st) {
   const size_t slab = e->pyr_bytes;
   const OrbLevel& L0 = e->lv[0];
   if (build_mask) {
@@ -661,23 +688,13 @@ int orb_run(gt_engine* e, int slot0, int nslots, bool as_reference, bool build_m
     const OrbLevel& D = e->lv[l];
     int* const* t = e->rs_tab[l];
     dim3 g((unsigned)ceil_div(D.w, 4 * 256), (unsigned)D.h, (unsigned)nslots);
-    pyr_resize_kernel<<<g, 256, 0, st>>>(e->pyr, e->pyr_mask, slab, slot0, S.off, S.w, S.h, D.off, D.w, D.h, t[0], t[1], t[2], t[3]);
+    pyr_resize_kernel<true><<<g, 256, 0, st>>>(e->pyr_mask, slab, slot0, S.off, S.w, S.h, D.off, D.w, D.h, t[0], t[1], t[2], t[3]);
     e->launches++;
-  }
-  GT_CUDA(e, cudaMemsetAsync(e->fast_count + (size_t)slot0 * GT_ORB_LEVELS, 0, (size_t)nslots * GT_ORB_LEVELS * sizeof(int), st));
-  for (int l = 0; l < GT_ORB_LEVELS; ++l) {
-    const OrbLevel& L = e->lv[l];
-    dim3 g((unsigned)ceil_div(L.w, FT_X), (unsigned)ceil_div(L.h, FT_Y), (unsigned)nslots);
-    fast_kernel<<<g, 256, 0, st>>>(e->pyr, e->pyr_mask, slab, slot0, L.off, L.w, L.h, e->fast_cand, e->fast_score, e->cand_total, L.cand_off,
-                                   L.cand_cap, e->fast_count, l);
-    dim3 gb((unsigned)ceil_div(L.w, 64), (unsigned)ceil_div(L.h, 16), (unsigned)nslots);
-    blur7_kernel<<<gb, 256, 0, st>>>(e->pyr, e->pyr_blur, slab, slot0, L.off, L.w, L.h);
-    e->launches += 2;
   }
   {
     dim3 g(GT_ORB_LEVELS, (unsigned)nslots);
-    orb_select_kernel<<<g, 1024, kSelCap * 4, st>>>(e->pyr, slab, slot0, e->lv_dev, e->fast_cand, e->fast_score, e->cand_total, e->fast_count,
-                                                    as_reference ? 1 : 0, e->sel_xy, e->sel_resp, e->sel_count);
+    orb_select_kernel<<<g, 1024, kSelCap * 4, st>>>(e->pyr, e->pyr_mask, slab, slot0, e->lv_dev, e->fast_cand, e->fast_score, e->cand_total,
+                                                    e->fast_count, as_reference ? 1 : 0, e->sel_xy, e->sel_resp, e->sel_count);
     e->launches++;
   }
   {
@@ -688,4 +705,9 @@ int orb_run(gt_engine* e, int slot0, int nslots, bool as_reference, bool build_m
   }
   GT_CUDA(e, cudaGetLastError());
   return GT_OK;
+}
+
+int orb_run(gt_engine* e, int slot0, int nslots, bool as_reference, bool build_mask, cudaStream_t st) {
+  GT_TRY(orb_front(e, slot0, nslots, st));
+  return orb_back(e, slot0, nslots, as_reference, build_mask, st);
 }

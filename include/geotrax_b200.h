@@ -145,7 +145,7 @@ int gt_orb_level_info(gt_handle h, int level, int32_t* w, int32_t* hgt, int32_t*
 int gt_get_pyramid_level(gt_handle h, int which, int b, int level, uint8_t* out_img, uint8_t* out_mask);
 /* keypoints f32 [n][6] = x, y (level-0 pixel units), size, angle(deg), response, octave; descriptors u8 [n][32]  */
 int gt_get_keypoints(gt_handle h, int which, int b, int max_n, float* out_kp, uint8_t* out_desc, int32_t* n);
-/* FAST candidates of one level after 3x3 NMS + mask + border filter: packed (y << 16 | x) and corner score              */
+/* FAST candidates of one level after 3x3 NMS + border filter (the vehicle mask is applied at selection): (y << 16 | x), score */
 int gt_orb_get_candidates(gt_handle h, int which, int b, int level, int max_n, uint32_t* out_xy, uint8_t* out_score, int32_t* n);
 /* run ORB alone on a caller-supplied gray image [B][work_h][work_w] (+ optional masks), into current slots      */
 int gt_orb_detect(gt_handle h, const uint8_t* gray, const uint8_t* mask, int B, int as_reference, void* stream);
