@@ -100,7 +100,6 @@ struct gt_engine {
   size_t cand_total = 0;
   uint8_t* pyr = nullptr;                           // [B+1][pyr_bytes]  (slot B = reference)
   uint8_t* pyr_mask = nullptr;                      // same geometry
-  uint8_t* pyr_blur = nullptr;                      // blurred copy
   unsigned int* fast_cand = nullptr;                // [B+1][cand_total] packed (y<<16|x)
   uint8_t* fast_score = nullptr;                    // [B+1][cand_total]
   int* fast_count = nullptr;                        // [B+1][8]

@@ -6,6 +6,7 @@
 // is bit-exact with OpenCV 4.13 (chained INTER_LINEAR_EXACT pyramid, FAST-9/16 score + 3x3 NMS, mask / border filter,
 // "retain best" with ties kept); the float stages follow OpenCV's operation order (Harris 7x7, intensity-centroid angle
 // with fastAtan2, float32 separable 7x7 sigma-2 blur, rotated 256-pair test pattern recovered by probing cv2).
+#include <algorithm>
 #include <cmath>
 
 #include "engine.cuh"
@@ -385,74 +386,6 @@ __global__ void __launch_bounds__(1024) orb_select_kernel(const uint8_t* __restr
   if (threadIdx.x == 0) sel_count[slot * GT_ORB_LEVELS + level] = kept;
 }
 
-// ---- float32 separable 7x7 sigma-2 blur (BORDER_REFLECT_101), as cv2.GaussianBlur does inside ORB ---------------------------
-__device__ __forceinline__ int reflect101(int p, int n) {
-  if (p < 0) p = -p;
-  if (p >= n) p = 2 * n - 2 - p;
-  return p;
-}
-// Tile 64 x 16: the u8 tile (+3 apron) is converted to float once, the horizontal pass produces 4 adjacent pixels per thread
-// from 3 vector loads, the vertical pass 4 adjacent pixels from 7 float4 loads and one 32-bit store.  Every product and sum
-// is rounded separately (__fmul_rn / __fadd_rn), in OpenCV's accumulation order.
-__global__ void __launch_bounds__(256) blur7_kernel(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, size_t slab, int slot0, size_t off,
-                                                    int w, int h) {
-  __shared__ __align__(16) float s_in[16 + 6][72];   // 70 used
-  __shared__ __align__(16) float s_h[16 + 6][64];
-  const int slot = slot0 + blockIdx.z;
-  const uint8_t* im = src + (size_t)slot * slab + off;
-  const int x0 = blockIdx.x * 64, y0 = blockIdx.y * 16;
-  for (int i = threadIdx.x; i < 22 * 72; i += 256) {
-    const int ty = i / 72, tx = i - ty * 72;
-    const int gx = reflect101(min(x0 - 3 + tx, w + 2), w), gy = reflect101(min(y0 - 3 + ty, h + 2), h);
-    s_in[ty][tx] = (float)im[(size_t)min(max(gy, 0), h - 1) * w + min(max(gx, 0), w - 1)];
-  }
-  __syncthreads();
-  for (int i = threadIdx.x; i < 22 * 16; i += 256) {
-    const int ty = i >> 4, tq = i & 15;
-    const float4 a = *reinterpret_cast<const float4*>(&s_in[ty][tq * 4]);
-    const float4 b = *reinterpret_cast<const float4*>(&s_in[ty][tq * 4 + 4]);
-    const float2 c = *reinterpret_cast<const float2*>(&s_in[ty][tq * 4 + 8]);
-    const float v[10] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, c.x, c.y};
-    float o[4];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      float acc = __fmul_rn(v[j], c_gauss[0]);
-#pragma unroll
-      for (int k = 1; k < 7; ++k) acc = __fadd_rn(acc, __fmul_rn(v[j + k], c_gauss[k]));
-      o[j] = acc;
-    }
-    *reinterpret_cast<float4*>(&s_h[ty][tq * 4]) = make_float4(o[0], o[1], o[2], o[3]);
-  }
-  __syncthreads();
-  {
-    const int ty = threadIdx.x >> 4, tq = threadIdx.x & 15;   // 16 rows x 16 quads
-    const int gx = x0 + tq * 4, gy = y0 + ty;
-    if (gx < w && gy < h) {
-      float4 acc;
-      {
-        const float4 r = *reinterpret_cast<const float4*>(&s_h[ty][tq * 4]);
-        acc = make_float4(__fmul_rn(r.x, c_gauss[0]), __fmul_rn(r.y, c_gauss[0]), __fmul_rn(r.z, c_gauss[0]), __fmul_rn(r.w, c_gauss[0]));
-      }
-#pragma unroll
-      for (int k = 1; k < 7; ++k) {
-        const float4 r = *reinterpret_cast<const float4*>(&s_h[ty + k][tq * 4]);
-        acc.x = __fadd_rn(acc.x, __fmul_rn(r.x, c_gauss[k])); acc.y = __fadd_rn(acc.y, __fmul_rn(r.y, c_gauss[k]));
-        acc.z = __fadd_rn(acc.z, __fmul_rn(r.z, c_gauss[k])); acc.w = __fadd_rn(acc.w, __fmul_rn(r.w, c_gauss[k]));
-      }
-      const int v0 = min(max(__float2int_rn(acc.x), 0), 255), v1 = min(max(__float2int_rn(acc.y), 0), 255);
-      const int v2 = min(max(__float2int_rn(acc.z), 0), 255), v3 = min(max(__float2int_rn(acc.w), 0), 255);
-      uint8_t* d = dst + (size_t)slot * slab + off + (size_t)gy * w + gx;
-      const int nvalid = min(4, w - gx);
-      if (nvalid == 4 && (reinterpret_cast<uintptr_t>(d) & 3) == 0)
-        *reinterpret_cast<uint32_t*>(d) = (uint32_t)v0 | ((uint32_t)v1 << 8) | ((uint32_t)v2 << 16) | ((uint32_t)v3 << 24);
-      else {
-        const int vv[4] = {v0, v1, v2, v3};
-        for (int k = 0; k < nvalid; ++k) d[k] = (uint8_t)vv[k];
-      }
-    }
-  }
-}
-
 // ---- one warp per key point: intensity-centroid angle, key-point record, 256-bit rotated BRIEF -------------------------------
 __device__ __forceinline__ float fast_atan2_deg(float y, float x) {
   const float p1 = 0.9997878412794807f * 57.29577951308232f, p3 = -0.3258083974640975f * 57.29577951308232f;
@@ -473,11 +406,23 @@ __device__ __forceinline__ float fast_atan2_deg(float y, float x) {
   return a;
 }
 
-__global__ void __launch_bounds__(256) orb_describe_kernel(const uint8_t* __restrict__ img, const uint8_t* __restrict__ blur, size_t slab, int slot0,
-                                                           const OrbLevel* __restrict__ lv, const unsigned int* __restrict__ sel_xy,
-                                                           const float* __restrict__ sel_resp, const int* __restrict__ sel_count,
-                                                           float* __restrict__ kp_all, uint8_t* __restrict__ desc_all, int* __restrict__ kp_count,
-                                                           int* __restrict__ lvl_kp_off) {
+// Per key point (one warp): the 45 x 45 source patch is staged in shared memory, blurred there (7x7 sigma-2, float32 separable,
+// every product and sum rounded separately in OpenCV's accumulation order -- bit-identical to blurring the whole level, which is
+// what cv2.ORB does, because key points stay 31 px away from the border so no reflection is involved), then the intensity
+// centroid and the 256 rotated pair tests read the patch.  Blurring only the ~2000 patches instead of the 6.4 MPix pyramid
+// removes a full read+write pass over the pyramid and ~55 % of the MACs.
+constexpr int kDescWarps = 4;
+constexpr int kSrcR = 22, kSrcW = 2 * kSrcR + 1;       // 45: descriptor reach 19 (pattern radius 13*sqrt2 rounded) + blur 3
+constexpr int kBlurR = 19, kBlurW = 2 * kBlurR + 1;    // 39
+constexpr int kSrcPitch = 48, kBlurPitch = 40;
+constexpr int kDescSmemPerWarp = kSrcW * kSrcPitch + kSrcW * kBlurW * 4 + kBlurW * kBlurPitch;   // 2160 + 7020 + 1560
+
+__global__ void __launch_bounds__(kDescWarps * 32) orb_describe_kernel(const uint8_t* __restrict__ img, size_t slab, int slot0,
+                                                                       const OrbLevel* __restrict__ lv, const unsigned int* __restrict__ sel_xy,
+                                                                       const float* __restrict__ sel_resp, const int* __restrict__ sel_count,
+                                                                       float* __restrict__ kp_all, uint8_t* __restrict__ desc_all,
+                                                                       int* __restrict__ kp_count, int* __restrict__ lvl_kp_off) {
+  extern __shared__ __align__(16) unsigned char s_dyn[];
   __shared__ signed char s_pat[256][4];
   __shared__ int s_off[GT_ORB_LEVELS + 1];
   const int slot = slot0 + blockIdx.y;
@@ -498,7 +443,7 @@ __global__ void __launch_bounds__(256) orb_describe_kernel(const uint8_t* __rest
   }
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int kpi = blockIdx.x * (blockDim.x >> 5) + warp;
+  const int kpi = blockIdx.x * kDescWarps + warp;
   if (kpi >= s_off[GT_ORB_LEVELS]) return;
   int level = 0;
   while (kpi >= s_off[level + 1]) ++level;
@@ -507,13 +452,24 @@ __global__ void __launch_bounds__(256) orb_describe_kernel(const uint8_t* __rest
   const unsigned xy = sel_xy[((size_t)slot * GT_ORB_LEVELS + level) * kSelCap + li];
   const int x = (int)(xy & 0xFFFF), y = (int)(xy >> 16);
   const uint8_t* im = img + (size_t)slot * slab + L.off;
+  unsigned char* base = s_dyn + (size_t)warp * ((kDescSmemPerWarp + 15) & ~15);
+  uint8_t (*s_src)[kSrcPitch] = reinterpret_cast<uint8_t (*)[kSrcPitch]>(base);
+  float (*s_hp)[kBlurW] = reinterpret_cast<float (*)[kBlurW]>(base + kSrcW * kSrcPitch);
+  uint8_t (*s_bl)[kBlurPitch] = reinterpret_cast<uint8_t (*)[kBlurPitch]>(base + kSrcW * kSrcPitch + kSrcW * kBlurW * 4);
+  // stage the source patch (clamped reads: positions outside the image are never used, see above)
+  for (int i = lane; i < kSrcW * kSrcW; i += 32) {
+    const int r = i / kSrcW, c = i - r * kSrcW;
+    const int gy = min(max(y - kSrcR + r, 0), L.h - 1), gx = min(max(x - kSrcR + c, 0), L.w - 1);
+    s_src[r][c] = im[(size_t)gy * L.w + gx];
+  }
+  __syncwarp();
   // intensity centroid over the radius-15 disc: lane = column u
   int m10 = 0, m01 = 0;
   if (lane < 31) {
     const int u = lane - 15, au = abs(u);
     for (int v = -15; v <= 15; ++v) {
       if (au <= c_umax[abs(v)]) {
-        const int I = im[(size_t)(y + v) * L.w + x + u];
+        const int I = s_src[kSrcR + v][kSrcR + u];
         m10 += u * I;
         m01 += v * I;
       }
@@ -534,10 +490,27 @@ __global__ void __launch_bounds__(256) orb_describe_kernel(const uint8_t* __rest
     kp[4] = sel_resp[((size_t)slot * GT_ORB_LEVELS + level) * kSelCap + li];
     kp[5] = (float)level;
   }
+  // horizontal pass: 45 rows x 39 columns
+  for (int i = lane; i < kSrcW * kBlurW; i += 32) {
+    const int r = i / kBlurW, c = i - r * kBlurW;
+    float acc = __fmul_rn((float)s_src[r][c], c_gauss[0]);
+#pragma unroll
+    for (int k = 1; k < 7; ++k) acc = __fadd_rn(acc, __fmul_rn((float)s_src[r][c + k], c_gauss[k]));
+    s_hp[r][c] = acc;
+  }
+  __syncwarp();
+  // vertical pass: 39 x 39, rounded to u8 like the blurred image
+  for (int i = lane; i < kBlurW * kBlurW; i += 32) {
+    const int r = i / kBlurW, c = i - r * kBlurW;
+    float acc = __fmul_rn(s_hp[r][c], c_gauss[0]);
+#pragma unroll
+    for (int k = 1; k < 7; ++k) acc = __fadd_rn(acc, __fmul_rn(s_hp[r + k][c], c_gauss[k]));
+    s_bl[r][c] = (uint8_t)min(max(__float2int_rn(acc), 0), 255);
+  }
+  __syncwarp();
   // descriptor: lane computes byte `lane` (bits 8*lane .. 8*lane+7)
   const float ar = __fmul_rn(angle, 0.017453292519943295f);  // (float)(CV_PI/180)
   const float ca = (float)cos((double)ar), sa = (float)sin((double)ar);
-  const uint8_t* bl = blur + (size_t)slot * slab + L.off;
   unsigned byte = 0;
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
@@ -547,8 +520,8 @@ __global__ void __launch_bounds__(256) orb_describe_kernel(const uint8_t* __rest
     const int iy0 = __float2int_rn(__fadd_rn(__fmul_rn(px, sa), __fmul_rn(py, ca)));
     const int ix1 = __float2int_rn(__fsub_rn(__fmul_rn(qx, ca), __fmul_rn(qy, sa)));
     const int iy1 = __float2int_rn(__fadd_rn(__fmul_rn(qx, sa), __fmul_rn(qy, ca)));
-    const int t0 = bl[(size_t)(y + iy0) * L.w + x + ix0];
-    const int t1 = bl[(size_t)(y + iy1) * L.w + x + ix1];
+    const int t0 = s_bl[kBlurR + iy0][kBlurR + ix0];
+    const int t1 = s_bl[kBlurR + iy1][kBlurR + ix1];
     byte |= (unsigned)(t0 < t1) << j;
   }
   desc_all[((size_t)slot * GT_MAX_KP + kpi) * 32 + lane] = (uint8_t)byte;
@@ -609,7 +582,6 @@ int orb_build(gt_engine* e) {
   e->sel_cap = kSelCap;
   GT_TRY(e->dev_alloc((void**)&e->pyr, (size_t)S * off));
   GT_TRY(e->dev_alloc((void**)&e->pyr_mask, (size_t)S * off));
-  GT_TRY(e->dev_alloc((void**)&e->pyr_blur, (size_t)S * off));
   GT_TRY(e->dev_alloc((void**)&e->fast_cand, (size_t)S * coff * sizeof(unsigned)));
   GT_TRY(e->dev_alloc((void**)&e->fast_score, (size_t)S * coff));
   GT_TRY(e->dev_alloc((void**)&e->fast_count, (size_t)S * GT_ORB_LEVELS * sizeof(int)));
@@ -640,6 +612,7 @@ int orb_build(gt_engine* e) {
     }
   }
   GT_CUDA(e, cudaFuncSetAttribute(orb_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSelCap * 4));
+  GT_CUDA(e, cudaFuncSetAttribute(orb_describe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kDescWarps * ((kDescSmemPerWarp + 15) & ~15)));
   return GT_OK;
 }
 
@@ -661,9 +634,7 @@ int orb_front(gt_engine* e, int slot0, int nslots, cudaStream_t st) {
     dim3 g((unsigned)ceil_div(L.w, FT_X), (unsigned)ceil_div(L.h, FT_Y), (unsigned)nslots);
     fast_kernel<<<g, 256, 0, st>>>(e->pyr, slab, slot0, L.off, L.w, L.h, e->fast_cand, e->fast_score, e->cand_total, L.cand_off, L.cand_cap,
                                    e->fast_count, l);
-    dim3 gb((unsigned)ceil_div(L.w, 64), (unsigned)ceil_div(L.h, 16), (unsigned)nslots);
-    blur7_kernel<<<gb, 256, 0, st>>>(e->pyr, e->pyr_blur, slab, slot0, L.off, L.w, L.h);
-    e->launches += 2;
+    e->launches++;
   }
   GT_CUDA(e, cudaGetLastError());
   return GT_OK;
@@ -698,9 +669,11 @@ int orb_back(gt_engine* e, int slot0, int nslots, bool as_reference, bool build_
     e->launches++;
   }
   {
-    dim3 g((unsigned)(GT_MAX_KP / 8), (unsigned)nslots);  // one warp per key point; warps past the count exit
-    orb_describe_kernel<<<g, 256, 0, st>>>(e->pyr, e->pyr_blur, slab, slot0, e->lv_dev, e->sel_xy, e->sel_resp, e->sel_count, e->kp_all,
-                                           e->desc_all, e->kp_count, e->lvl_kp_off);
+    const int nkp = std::min(GT_MAX_KP, (as_reference ? (int)(e->cfg.max_features * e->cfg.ref_multiplier) : e->cfg.max_features) + GT_ORB_LEVELS * 64);
+    dim3 g((unsigned)ceil_div(nkp, kDescWarps), (unsigned)nslots);  // one warp per key point; warps past the count exit
+    const size_t dsm = (size_t)kDescWarps * ((kDescSmemPerWarp + 15) & ~15);
+    orb_describe_kernel<<<g, kDescWarps * 32, dsm, st>>>(e->pyr, slab, slot0, e->lv_dev, e->sel_xy, e->sel_resp, e->sel_count, e->kp_all,
+                                                         e->desc_all, e->kp_count, e->lvl_kp_off);
     e->launches++;
   }
   GT_CUDA(e, cudaGetLastError());
