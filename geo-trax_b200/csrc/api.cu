@@ -271,23 +271,23 @@ int gt_get_net_input(gt_handle e, int B, uint8_t* out, int32_t* net_h, int32_t* 
   if (out) {  // debug read-back: space-to-depth 16-bit tensor -> planar RGB u8
     GT_CHECK(e, B >= 1 && B <= e->cfg.max_batch, "gt_get_net_input: bad batch %d", B);
     GT_CUDA(e, cudaStreamSynchronize(e->stream));
-    const int sh = e->net_h / 2, sw = e->net_w / 2;
-    std::vector<uint16_t> h((size_t)B * sh * sw * 16);
+    const int sh = e->net_h / 4, sw = e->net_w / 4;
+    std::vector<uint16_t> h((size_t)B * sh * sw * 64);
     GT_CUDA(e, cudaMemcpy(h.data(), e->net_s2d, h.size() * 2, cudaMemcpyDefault));
     const bool fp16 = e->cfg.act_dtype == GT_ACT_FP16;
     const size_t plane = (size_t)e->net_h * e->net_w;
     for (int b = 0; b < B; ++b)
       for (int sy = 0; sy < sh; ++sy)
         for (int sx = 0; sx < sw; ++sx) {
-          const uint16_t* px = &h[(((size_t)b * sh + sy) * sw + sx) * 16];
-          for (int r = 0; r < 2; ++r)
-            for (int c = 0; c < 2; ++c)
+          const uint16_t* px = &h[(((size_t)b * sh + sy) * sw + sx) * 64];
+          for (int r = 0; r < 4; ++r)
+            for (int c = 0; c < 4; ++c)
               for (int ch = 0; ch < 3; ++ch) {
-                const uint16_t bits = px[(r * 2 + c) * 4 + ch];
+                const uint16_t bits = px[(r * 4 + c) * 4 + ch];
                 float f;
                 if (fp16) { __half hv; memcpy(&hv, &bits, 2); f = __half2float(hv); }
                 else { uint32_t u = (uint32_t)bits << 16; memcpy(&f, &u, 4); }
-                out[((size_t)b * 3 + ch) * plane + (size_t)(2 * sy + r) * e->net_w + 2 * sx + c] = (uint8_t)(f + 0.5f);
+                out[((size_t)b * 3 + ch) * plane + (size_t)(4 * sy + r) * e->net_w + 4 * sx + c] = (uint8_t)(f + 0.5f);
               }
         }
   }

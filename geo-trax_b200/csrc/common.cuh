@@ -88,6 +88,9 @@ struct ConvParams {
   int out_f32;            // 1: out is float (raw head), 0: 16-bit act dtype
   int fp16;               // 16-bit format: 1 = fp16, 0 = bf16
   float scale;            // accumulator scale applied before the bias (1/255 for layer 0, else 1)
+  int out_s2d;            // layer 0: the 128 GEMM outputs of a row are a 2x2 block of output pixels x 32 channels; each 64-channel
+                          // slab (one row parity) goes out through the tensor map {64 = (col parity, c), row parity, X, n*rows + Y}
+  int out_rows;           // rows per image of that map
   void* out;
   long long out_img_stride;  // destination pixels per image
   int out_ctot, out_coff;
@@ -123,6 +126,7 @@ struct ConvPlanArgs {
   int Ho = -1, Wo = -1;      // -1: derived from the input dims
   int kb_elems = 64;
   float scale = 1.0f;
+  bool out_s2d = false;        // see ConvParams::out_s2d (out then is the full-resolution NHWC tensor, 2Ho x 2Wo x cout/4)
   const View* out = nullptr;   // 16-bit NHWC destination slice, or
   float* out_f32 = nullptr;    // fp32 rows [img][pixel][out_ctot_f32] at column out_coff_f32
   long long out_img_stride = 0;
@@ -141,6 +145,8 @@ int conv_tc_launch_range(gt_engine* e, const ConvOp* op, int b0, int nb, cudaStr
 typedef CUresult (*GtEncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
                                     const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 GtEncodeTiledFn conv_tc_encode();
+struct View;
+CUresult encode_s2d_out(CUtensorMap* tm, CUtensorMapDataType dt, const View* out, int Wo, int Ho, int B, int tw, int th);
 int conv_tc_num_sms();
 int conv_sw_init(gt_engine* e);
 int conv_sw_plan(gt_engine* e, ConvOp* op, const ConvPlanArgs& a);

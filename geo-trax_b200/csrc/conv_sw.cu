@@ -248,9 +248,10 @@ __global__ void __launch_bounds__(kSwThreads, 1) conv_sw_kernel(const __grid_con
         if (gran_active) {
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
           named_bar(2 + h * 2 + g, 64);
-          if (gran_leader) {
+          if (gran_leader && !(p.out_s2d && ybase >= p.H)) {   // (s2d rows are folded over images: a fully out-of-range granule must not wrap)
             const int cch = m0 + g * 64;
-            tma_store_4d(&tmOut, buf, cch, t.x0, ybase, t.n);
+            if (p.out_s2d) tma_store_4d(&tmOut, buf, 0, g, t.x0, t.n * p.out_rows + ybase);
+            else tma_store_4d(&tmOut, buf, cch, t.x0, ybase, t.n);
             if (p.up) {
 #pragma unroll
               for (int d = 0; d < 4; ++d) tma_store_4d(tmUp.m + d, buf, cch, t.x0, ybase, t.n);
@@ -344,6 +345,7 @@ int conv_sw_plan(gt_engine* e, ConvOp* op, const ConvPlanArgs& a) {
   op->cin = cin; op->cout = cout; op->k = k; op->stride = stride;
   p.B = a.Bmax; p.H = Ho; p.W = Wo;
   pick_tile256(Ho, Wo, a.out_f32 != nullptr, &p.tw, &p.th);
+  if (a.out_s2d) { p.tw = 16; p.th = 16; GT_CHECK(e, (Ho % 8) == 0, "conv plan: s2d output needs Ho %% 8 == 0"); }   // granules are 16 x 8: never straddle images
   GT_CHECK(e, p.tw * stride <= 256 && p.th * stride <= 256, "conv plan: TMA box too large");
   p.tiles_x = ceil_div(Wo, p.tw); p.tiles_y = ceil_div(Ho, p.th);
   p.stride = stride; p.ksize = k; p.pad = pad;
@@ -376,9 +378,11 @@ int conv_sw_plan(gt_engine* e, ConvOp* op, const ConvPlanArgs& a) {
     p.out_f32 = 1; p.out = a.out_f32; p.out_img_stride = a.out_img_stride; p.out_ctot = a.out_ctot_f32; p.out_coff = a.out_coff_f32;
   } else {
     const View* out = a.out;
-    GT_CHECK(e, out && out->H == Ho && out->W == Wo && out->C == cout, "conv plan: output view mismatch");
+    if (a.out_s2d) GT_CHECK(e, out && out->H == 2 * Ho && out->W == 2 * Wo && out->C * 4 == cout && cout == 128, "conv plan: s2d output view mismatch");
+    else GT_CHECK(e, out && out->H == Ho && out->W == Wo && out->C == cout, "conv plan: output view mismatch");
     GT_CHECK(e, (out->ctot % 8) == 0 && (out->coff % 8) == 0 && (cout % 8) == 0, "conv plan: output slice must be 16-byte aligned");
     p.out_f32 = 0; p.out = out->ptr; p.out_img_stride = (long long)Ho * Wo; p.out_ctot = out->ctot; p.out_coff = out->coff;
+    p.out_s2d = a.out_s2d ? 1 : 0; p.out_rows = Ho;
   }
   if (a.res) {
     GT_CHECK(e, a.res->H == Ho && a.res->W == Wo && a.res->C == cout && !a.out_f32, "conv plan: residual view mismatch");
@@ -440,7 +444,8 @@ int conv_sw_plan(gt_engine* e, ConvOp* op, const ConvPlanArgs& a) {
               (cuuint64_t)a.out_img_stride * ps);
     } else {
       const cuuint64_t ps = (cuuint64_t)a.out->ctot * 2;
-      r = enc(&op->tmOut, dt, (void*)(a.out->ptr + a.out->coff), 64, p.tw, p.th / 2, Wo, Ho, ps, (cuuint64_t)Wo * ps, (cuuint64_t)Ho * Wo * ps);
+      if (a.out_s2d) r = encode_s2d_out(&op->tmOut, dt, a.out, Wo, Ho, a.Bmax, p.tw, p.th / 2);
+      else r = enc(&op->tmOut, dt, (void*)(a.out->ptr + a.out->coff), 64, p.tw, p.th / 2, Wo, Ho, ps, (cuuint64_t)Wo * ps, (cuuint64_t)Ho * Wo * ps);
       if (r == CUDA_SUCCESS && a.res) {
         const cuuint64_t rs = (cuuint64_t)a.res->ctot * 2;
         r = enc(&op->tmRes, dt, (void*)(a.res->ptr + a.res->coff), 64, p.tw, p.th / 2, Wo, Ho, rs, (cuuint64_t)Wo * rs, (cuuint64_t)Ho * Wo * rs);

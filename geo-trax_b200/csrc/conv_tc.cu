@@ -121,7 +121,8 @@ __device__ __forceinline__ void epilogue_tile(const ConvParams& p, const TileCoo
     epi_bar();
     if (leader_warp && lane == 0) {
       const int cch = (t.n0 + j * 2 * CW);            // first channel of this slab inside the destination slice
-      tma_store_4d(tmOut, buf, cch, t.x0, t.y0, t.n);
+      if (p.out_s2d) tma_store_4d(tmOut, buf, 0, cch >> 6, t.x0, t.n * p.out_rows + t.y0);
+      else tma_store_4d(tmOut, buf, cch, t.x0, t.y0, t.n);
       if (p.up) {
 #pragma unroll
         for (int d = 0; d < 4; ++d) tma_store_4d(tmUp + d, buf, cch, t.x0, t.y0, t.n);
@@ -369,6 +370,20 @@ size_t conv_smem_bytes(int stages, int stage_bytes, int halo_total, int bres_byt
 }  // namespace
 
 GtEncodeTiledFn conv_tc_encode() { return g_encode; }
+
+// Layer-0 output: the destination is the full-resolution NHWC tensor [B][2Ho][2Wo][32] (a dedicated 32-channel buffer); one
+// staging slab holds, for every super-pixel (Y, X) of the tile, the two pixels (2Y + oy, 2X + {0,1}) x 32 channels = 128
+// contiguous bytes.  4-D view of the destination: {64 = (ox, c), oy 2, X Wo, Y' = n * Ho + Y}; box {64, 1, tw, th}; tiles never
+// straddle images (Ho % th == 0).
+CUresult encode_s2d_out(CUtensorMap* tm, CUtensorMapDataType dt, const View* out, int Wo, int Ho, int B, int tw, int th) {
+  const cuuint64_t ps = (cuuint64_t)out->ctot * 2;   // one full-resolution pixel (64 bytes)
+  cuuint64_t gdim[4] = {64, 2, (cuuint64_t)Wo, (cuuint64_t)Ho * B};
+  cuuint64_t gstr[3] = {(cuuint64_t)2 * Wo * ps, 2 * ps, (cuuint64_t)4 * Wo * ps};
+  cuuint32_t box[4] = {64, 1, (cuuint32_t)tw, (cuuint32_t)th};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  return g_encode(tm, dt, 4, (void*)(out->ptr + out->coff), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+}
 int conv_tc_num_sms() { return g_num_sms; }
 
 int conv_tc_init(gt_engine* e) {
@@ -429,6 +444,7 @@ int conv_tc_plan(gt_engine* e, ConvOp* op, const ConvPlanArgs& a) {
     if (u_halo >= 0.75 * u_best) want_halo = e->halo_mode;
   }
   if (want_halo) { p.tw = 8; p.th = 16; }
+  if (a.out_s2d) { p.tw = 16; p.th = 8; want_halo = 0; }   // Ho is a multiple of 8: tiles never straddle images in the folded row index
   p.tiles_x = ceil_div(Wo, p.tw); p.tiles_y = ceil_div(Ho, p.th);
   p.stride = stride; p.ksize = k; p.pad = pad;
   p.kb_elems = kbe;
@@ -493,10 +509,15 @@ int conv_tc_plan(gt_engine* e, ConvOp* op, const ConvPlanArgs& a) {
     p.out_f32 = 1; p.out = a.out_f32; p.out_img_stride = a.out_img_stride; p.out_ctot = a.out_ctot_f32; p.out_coff = a.out_coff_f32;
   } else {
     const View* out = a.out;
+    if (a.out_s2d) GT_CHECK(e, out && out->H == 2 * Ho && out->W == 2 * Wo && out->C * 4 == cout_total && cout_total == 128 && (Ho % p.th) == 0 &&
+                                   out->ctot == 32 && out->coff == 0,
+                            "conv plan: s2d output view mismatch");
+    else
     GT_CHECK(e, out && out->H == Ho && out->W == Wo && out->C == cout_total, "conv plan: output view mismatch (%dx%dx%d vs %dx%dx%d)",
              out ? out->H : -1, out ? out->W : -1, out ? out->C : -1, Ho, Wo, cout_total);
     GT_CHECK(e, (out->ctot % 8) == 0 && (out->coff % 8) == 0 && (cout_total % 8) == 0, "conv plan: output slice must be 16-byte aligned");
     p.out_f32 = 0; p.out = out->ptr; p.out_img_stride = (long long)Ho * Wo; p.out_ctot = out->ctot; p.out_coff = out->coff;
+    p.out_s2d = a.out_s2d ? 1 : 0; p.out_rows = Ho;
   }
   if (a.res) {
     GT_CHECK(e, a.res->H == Ho && a.res->W == Wo && a.res->C == cout_total && !a.out_f32, "conv plan: residual view mismatch");
@@ -567,6 +588,8 @@ int conv_tc_plan(gt_engine* e, ConvOp* op, const ConvPlanArgs& a) {
       GT_CHECK(e, (ps % 16) == 0 && (a.out_coff_f32 % 4) == 0, "conv plan: fp32 output rows must be 16-byte aligned (row %d floats, col %d)",
                a.out_ctot_f32, a.out_coff_f32);
       r = enc(&op->tmOut, (void*)(a.out_f32 + a.out_coff_f32), Wo, Ho, ps, (cuuint64_t)Wo * ps, (cuuint64_t)a.out_img_stride * ps);
+    } else if (a.out_s2d) {
+      r = encode_s2d_out(&op->tmOut, odt, a.out, Wo, Ho, a.Bmax, p.tw, p.th);
     } else {
       const cuuint64_t ps = (cuuint64_t)a.out->ctot * 2;
       r = enc(&op->tmOut, (void*)(a.out->ptr + a.out->coff), Wo, Ho, ps, (cuuint64_t)Wo * ps, (cuuint64_t)Ho * Wo * ps);

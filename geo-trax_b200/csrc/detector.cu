@@ -13,11 +13,12 @@
 // Stage 1: fused letterbox (exact 1/2 decimation) + BGR->RGB -> 16-bit space-to-depth NHWC tensor for layer 0, and
 // BGR2GRAY + 1/2 resize -> u8 (level 0 of the ORB pyramid).  One pass over the 24.9 MB frame feeds stages 2 and 3.
 //
-// Network input layout: [B][net_h/2][net_w/2][16], channel = (row parity * 2 + column parity) * 4 + {R, G, B, 0}; values are
-// the exact u8 pixel (0..255 is exact in fp16 and bf16) -- the 1/255 of BasePredictor.preprocess is layer 0's epilogue
-// scale.  With this layout the stride-2 3x3 layer-0 convolution is a stride-1 2x2 convolution over 16 channels, which the
-// tcgen05 implicit-GEMM kernel consumes directly through TMA (32-byte rows, SWIZZLE_32B).
-// One thread: 2 output rows x 8 output pixels = 4 source rows x 48 B (three 128-bit loads per row) -> one 128-byte line.
+// Network input layout: [B][net_h/4][net_w/4][64] = 4x4 space-to-depth of the letterboxed image, channel = (r * 4 + c) * 4 +
+// {R, G, B, 0} for row r / column c inside the block; values are the exact u8 pixel (0..255 is exact in fp16 and bf16) -- the
+// 1/255 of BasePredictor.preprocess is layer 0's epilogue scale.  With this layout the stride-2 3x3 layer-0 convolution becomes
+// a stride-1 2x2 convolution over 64 channels that produces a 2x2 block of output pixels x 32 channels (N = 128) per row: a
+// well-shaped GEMM (K = 256, N = 128) for the tcgen05 kernels instead of K = 27, N = 32.
+// One thread: 2 letterboxed rows x 8 pixels = 4 source rows x 48 B (three 128-bit loads per row) -> two 64-byte segments.
 // =====================================================================================================================
 __device__ __forceinline__ uint32_t gray15(uint32_t b, uint32_t g, uint32_t r) {
   return (9798u * r + 19235u * g + 3735u * b + 16384u) >> 15;  // OpenCV BGR2GRAY, 15-bit coefficients
@@ -55,18 +56,23 @@ __global__ void __launch_bounds__(256) preprocess_half_kernel(const uint8_t* __r
       const uint32_t bb = (b00 + b01 + b10 + b11 + 2) >> 2;  // cv2.resize INTER_LINEAR at exactly 1/2
       const uint32_t gg = (g00 + g01 + g10 + g11 + 2) >> 2;
       const uint32_t rr = (r00 + r01 + r10 + r11 + 2) >> 2;
-      // s2d pixel j>>1, column parity j&1, row parity r  ->  words ((j>>1)*16 + (r*2 + (j&1))*4) / 2 ...
-      const int w0 = (j >> 1) * 8 + (r * 2 + (j & 1)) * 2;
+      // block j>>2 (of the two 4-wide blocks this thread touches), column j&3, row r of this thread's row pair: 2 words per pixel
+      const int w0 = (j >> 2) * 16 + (r * 4 + (j & 3)) * 2;
       line[w0] = pack2_act((float)rr, (float)gg, fp16);
       line[w0 + 1] = pack2_act((float)bb, 0.f, fp16);
       const uint32_t y00 = gray15(b00, g00, r00), y01 = gray15(b01, g01, r01), y10 = gray15(b10, g10, r10), y11 = gray15(b11, g11, r11);
       gy[r][j] = (uint8_t)((y00 + y01 + y10 + y11 + 2) >> 2);  // gray first, then the 1/2 resize (stabilo order)
     }
   }
-  const int sh = net_h >> 1, sw = net_w >> 1;
-  uint4* dst = reinterpret_cast<uint4*>(s2d + (((size_t)b * sh + oy2 + (pad_top >> 1)) * sw + (pad_left >> 1) + og * 4) * 16);
+  // letterboxed rows 2*oy2 + pad_top + {0,1} = rows (rb, rb + 1) of block row Y; pixels og*8 + pad_left .. +7 = blocks X, X + 1
+  const int sh = net_h >> 2, sw = net_w >> 2;
+  const int ly = 2 * oy2 + pad_top, Y = ly >> 2, rb = ly & 3, X = (og * 8 + pad_left) >> 2;
 #pragma unroll
-  for (int i = 0; i < 8; ++i) dst[i] = reinterpret_cast<const uint4*>(line)[i];
+  for (int blk = 0; blk < 2; ++blk) {
+    uint4* dst = reinterpret_cast<uint4*>(s2d + (((size_t)b * sh + Y) * sw + X + blk) * 64 + rb * 16);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) dst[i] = reinterpret_cast<const uint4*>(line)[blk * 4 + i];
+  }
   if (gray) {
     uint8_t* g = gray + (size_t)b * gray_frame_stride + (size_t)(2 * oy2) * new_w + og * 8;
     *reinterpret_cast<uint2*>(g) = *reinterpret_cast<const uint2*>(gy[0]);
@@ -82,7 +88,7 @@ __global__ void fill_s2d_kernel(uint2* __restrict__ s2d, size_t n_quads, uint32_
 int detector_fill_pad(gt_engine* e, cudaStream_t st) {  // constant letterbox border (value 114); the interior is rewritten per batch
   const int fp16 = e->cfg.act_dtype == GT_ACT_FP16;
   const uint16_t v = host_to_act(114.f, fp16);
-  const size_t n_quads = (size_t)e->cfg.max_batch * (e->net_h / 2) * (e->net_w / 2) * 4;  // one quad = R,G,B,0
+  const size_t n_quads = (size_t)e->cfg.max_batch * (e->net_h / 4) * (e->net_w / 4) * 16;  // one quad = R,G,B,0
   fill_s2d_kernel<<<(unsigned)((n_quads + 255) / 256), 256, 0, st>>>(reinterpret_cast<uint2*>(e->net_s2d), n_quads, (uint32_t)v | ((uint32_t)v << 16),
                                                                       (uint32_t)v);
   GT_CUDA(e, cudaGetLastError());
@@ -580,17 +586,18 @@ struct Builder {
     rc = plan_both(op, a);
     if (rc == GT_OK) push(op);
   }
-  // layer 0: Conv(3 -> 32, k3, s2) as a stride-1 2x2 convolution over the 16-channel space-to-depth input (see stage 1)
+  // layer 0: Conv(3 -> 32, k3, s2) as a stride-1 2x2 convolution over the 64-channel 4x4 space-to-depth input producing a 2x2
+  // block of output pixels x 32 channels per GEMM row (see stage 1)
   void conv0(const View& s2d, const View& out) {
     if (rc != GT_OK) return;
     ConvOp op;
     op.n_src = 1; op.src[0] = find("model.0");
     ConvPlanArgs a;
-    a.in = s2d; a.Bmax = B; a.cin = 16; a.cout = 32; a.k = 2; a.stride = 1; a.pad = 1; a.Ho = s2d.H; a.Wo = s2d.W; a.kb_elems = 16;
-    a.act = 1; a.scale = 1.0f / 255.0f; a.out = &out;
+    a.in = s2d; a.Bmax = B; a.cin = 64; a.cout = 128; a.k = 2; a.stride = 1; a.pad = 1; a.Ho = s2d.H; a.Wo = s2d.W;
+    a.act = 1; a.scale = 1.0f / 255.0f; a.out = &out; a.out_s2d = true;
     rc = plan_both(op, a);
     if (rc != GT_OK) return;
-    op.flops = 2.0 * s2d.H * s2d.W * 32.0 * 27.0;   // the algorithmic 3x3x3 work, not the zero-padded 2x2x16
+    op.flops = 2.0 * out.H * out.W * 32.0 * 27.0;   // the algorithmic 3x3x3 work, not the zero-padded 2x2x64 -> 128
     if (!e->conv_alt.empty()) e->conv_alt.back().flops = op.flops;
     e->conv0_op = (int)e->conv_ops.size();
     push(op);
@@ -688,7 +695,7 @@ int detector_build(gt_engine* e) {
   GT_TRY(e->dev_alloc((void**)&e->raw_head, (size_t)B * e->A * e->no_pad * sizeof(float)));
   GT_CUDA(e, cudaMemset(e->raw_head, 0, (size_t)B * e->A * e->no_pad * sizeof(float)));
 
-  View S2D = bl.alloc(16, H1, W1);          // written by stage 1
+  View S2D = bl.alloc(64, H2, W2);          // 4x4 space-to-depth network input, written by stage 1
   e->net_s2d = S2D.ptr;
   View T0 = bl.alloc(c1, H1, W1);
   bl.conv0(S2D, T0);
@@ -787,23 +794,27 @@ int detector_build(gt_engine* e) {
 static int load_op_weights(gt_engine* e, ConvOp& op, bool is_conv0, const float* const* w, const float* const* b) {
   const int fp16 = e->cfg.act_dtype == GT_ACT_FP16;
   if (is_conv0) {
-    // layer 0: [32][3][3][3] (cout, RGB, ky, kx) -> [cout_pad][tap = dy*2+dx][16 = (r*2+c)*4 + ch]; the s2d tap (dy, r) holds kernel
-    // row ky: (0,1)->0, (1,0)->1, (1,1)->2, (0,0)-> none (zero); columns likewise.  Unscaled: the 1/255 is the epilogue scale.
-    std::vector<uint16_t> hw((size_t)op.cout_pad * 4 * 16, 0);
+    // layer 0: [32][3][3][3] (cout, RGB, ky, kx) -> [n = (oy*2+ox)*32 + co][tap = dY*2+dX][c64 = (r*4+c)*4 + ch].  GEMM row =
+    // super-pixel (Y, X); output pixel (2Y+oy, 2X+ox) reads input row 4(Y-1+dY) + r as kernel row ky = 4 dY + r - 2 oy - 3 (columns
+    // likewise); combinations outside 0..2 are zero.  Unscaled: the 1/255 is the epilogue scale.
+    const int taps = 4, cpad = op.cin_pad;   // 64
+    std::vector<uint16_t> hw((size_t)op.cout_pad * taps * cpad, 0);
     std::vector<float> hb(op.cout_pad, 0.f);
-    const int kmap[2][2] = {{-1, 0}, {1, 2}};
-    for (int co = 0; co < 32; ++co) {
-      for (int dy = 0; dy < 2; ++dy)
-        for (int dx = 0; dx < 2; ++dx)
-          for (int r = 0; r < 2; ++r)
-            for (int c = 0; c < 2; ++c) {
-              const int ky = kmap[dy][r], kx = kmap[dx][c];
-              if (ky < 0 || kx < 0) continue;
-              for (int chn = 0; chn < 3; ++chn)
-                hw[((size_t)co * 4 + dy * 2 + dx) * 16 + (r * 2 + c) * 4 + chn] = host_to_act(w[0][((co * 3 + chn) * 3 + ky) * 3 + kx], fp16);
-            }
-      hb[co] = b[0][co];
-    }
+    for (int oy = 0; oy < 2; ++oy)
+      for (int ox = 0; ox < 2; ++ox)
+        for (int co = 0; co < 32; ++co) {
+          const int n = (oy * 2 + ox) * 32 + co;
+          for (int dY = 0; dY < 2; ++dY)
+            for (int dX = 0; dX < 2; ++dX)
+              for (int r = 0; r < 4; ++r)
+                for (int c = 0; c < 4; ++c) {
+                  const int ky = 4 * dY + r - 2 * oy - 3, kx = 4 * dX + c - 2 * ox - 3;
+                  if (ky < 0 || ky > 2 || kx < 0 || kx > 2) continue;
+                  for (int chn = 0; chn < 3; ++chn)
+                    hw[((size_t)n * taps + dY * 2 + dX) * cpad + (r * 4 + c) * 4 + chn] = host_to_act(w[0][((co * 3 + chn) * 3 + ky) * 3 + kx], fp16);
+                }
+          hb[n] = b[0][co];
+        }
     return conv_tc_upload_packed(e, &op, hw.data(), hb.data());
   }
   const float* ws[3];

@@ -65,7 +65,7 @@ struct gt_engine {
   int prefetch_next = 0;
   const uint8_t* deferred_src = nullptr;   // gt_prefetch_frames_deferred: started by the next gt_extract_batch
   int deferred_B = 0;
-  bf16* net_s2d = nullptr;              // [B][net_h/2][net_w/2][16] space-to-depth letterboxed RGB0 (exact u8 values, 16-bit)
+  bf16* net_s2d = nullptr;              // [B][net_h/4][net_w/4][64] 4x4 space-to-depth letterboxed RGB0 (exact u8 values, 16-bit)
   const uint8_t* cur_frames = nullptr;  // device pointer of the frames of the last gt_preprocess
 
   // detector

@@ -117,6 +117,11 @@ __device__ __forceinline__ void tma_store_4d(const CUtensorMap* tm, uint32_t src
                "r"(c2), "r"(c3)
                : "memory");
 }
+__device__ __forceinline__ void tma_store_5d(const CUtensorMap* tm, uint32_t src, int c0, int c1, int c2, int c3, int c4) {
+  asm volatile("cp.async.bulk.tensor.5d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5, %6}], [%1];" ::"l"(tm), "r"(src), "r"(c0), "r"(c1),
+               "r"(c2), "r"(c3), "r"(c4)
+               : "memory");
+}
 __device__ __forceinline__ bool elect_one() {   // true in exactly one lane of the (converged) warp
   uint32_t pred;
   asm volatile(
