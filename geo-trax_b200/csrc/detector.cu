@@ -380,6 +380,7 @@ __global__ void __launch_bounds__(512) nms_sweep_kernel(const unsigned long long
                                                         int* __restrict__ det_count, int* __restrict__ det_keep, int* __restrict__ overflow) {
   extern __shared__ unsigned long long s_removed[];  // [words]
   __shared__ int s_kept[64];
+  __shared__ unsigned long long s_diag[64];
   __shared__ int s_nk, s_total;
   const int b = blockIdx.x;
   const int ntrue = min(count[b], max_nms);
@@ -395,6 +396,12 @@ __global__ void __launch_bounds__(512) nms_sweep_kernel(const unsigned long long
   const int row = rotated ? 7 : 6;
   for (int chunk = 0; chunk < w_used; ++chunk) {
     if (s_total >= max_det) break;
+    // the 64 diagonal mask words of this chunk are fetched in parallel; the serial scan below then runs out of shared memory
+    if (threadIdx.x < 64) {
+      const int r = chunk * 64 + threadIdx.x;
+      s_diag[threadIdx.x] = r < n ? mask[((size_t)b * n_cap + r) * words + chunk] : 0ull;
+    }
+    __syncthreads();
     if (threadIdx.x == 0) {
       unsigned long long rem = s_removed[chunk];
       int nk = 0;
@@ -402,9 +409,9 @@ __global__ void __launch_bounds__(512) nms_sweep_kernel(const unsigned long long
       for (int j = 0; j < lim; ++j) {
         if (!((rem >> j) & 1ull)) {
           if (s_total + nk < max_det) s_kept[nk++] = chunk * 64 + j;
-          if (!rotated) rem |= mask[((size_t)b * n_cap + chunk * 64 + j) * words + chunk];
+          if (!rotated) rem |= s_diag[j];
         }
-        if (rotated) rem |= mask[((size_t)b * n_cap + chunk * 64 + j) * words + chunk];
+        if (rotated) rem |= s_diag[j];
       }
       s_nk = nk;
     }

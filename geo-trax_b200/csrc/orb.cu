@@ -79,8 +79,8 @@ __global__ void __launch_bounds__(256) pyr_resize_kernel(uint8_t* __restrict__ p
 
 // ---- FAST-9/16 score + 3x3 non-max suppression + mask / border filter -> candidate list ------------------------------------
 // Three phases per 64 x 32 tile so that the expensive part runs in dense warps:
-//   1. corner test for every position of the (tile + 1) ring: compass quick-reject, then the 16-bit arc masks; corners are
-//      compacted into a shared list;
+//   1. corner test for every position of the (tile + 1) ring: compass quick-reject on all positions, survivors compacted; the
+//      16-pixel arc masks only on the survivors; corners compacted into a second shared list;
 //   2. exact corner score (OpenCV cornerScore<16>) only for the listed positions;
 //   3. 3x3 non-max suppression, border filter, block-level compaction into the per-(frame, level) candidate list.
 // The vehicle mask is NOT applied here (it depends on the detections, which are computed concurrently): orb_select_kernel
@@ -96,14 +96,18 @@ __device__ __forceinline__ void fast_ring(const uint8_t (*t)[FT_X + 8], int x, i
   d[12] = v - t[y][x - 3];     d[13] = v - t[y + 1][x - 3]; d[14] = v - t[y + 2][x - 2]; d[15] = v - t[y + 3][x - 1];
 }
 
-// is (x, y) a FAST-9/16 corner at threshold kFastThr?  (x, y) are tile coordinates >= 3 from the tile edge
-__device__ __forceinline__ bool fast_is_corner(const uint8_t (*t)[FT_X + 8], int x, int y) {
+// cheap necessary condition: any 9 contiguous ring pixels contain two of the four compass pixels (0, 4, 8, 12)
+__device__ __forceinline__ bool fast_compass(const uint8_t (*t)[FT_X + 8], int x, int y) {
   const int v = t[y][x];
-  // any 9 contiguous ring pixels contain two of the four compass pixels (0, 4, 8, 12): cheap necessary condition
   const int c0 = v - t[y + 3][x], c4 = v - t[y][x + 3], c8 = v - t[y - 3][x], c12 = v - t[y][x - 3];
   const int nd = (c0 > kFastThr) + (c4 > kFastThr) + (c8 > kFastThr) + (c12 > kFastThr);
   const int nb = (c0 < -kFastThr) + (c4 < -kFastThr) + (c8 < -kFastThr) + (c12 < -kFastThr);
-  if (nd < 2 && nb < 2) return false;
+  return nd >= 2 || nb >= 2;
+}
+
+// is (x, y) a FAST-9/16 corner at threshold kFastThr?  (x, y) are tile coordinates >= 3 from the tile edge
+__device__ __forceinline__ bool fast_is_corner(const uint8_t (*t)[FT_X + 8], int x, int y) {
+  const int v = t[y][x];
   int d[16];
   fast_ring(t, x, y, v, d);
   unsigned dark = 0, bright = 0;  // d > thr : ring pixel darker than centre;  d < -thr : brighter
@@ -154,14 +158,15 @@ __global__ void __launch_bounds__(256) fast_kernel(const uint8_t* __restrict__ i
                                                    size_t cand_slab, size_t cand_off, int cand_cap, int* __restrict__ counts, int level) {
   __shared__ __align__(16) uint8_t s_img[FT_Y + 8][FT_X + 8];
   __shared__ uint8_t s_sc[FT_Y + 2][FT_X + 2];
-  __shared__ unsigned short s_list[FT_LIST];      // corner positions (sy * (FT_X + 2) + sx) of phase 1
-  __shared__ int s_nl, s_n, s_base;
+  __shared__ unsigned short s_cand[FT_LIST];      // positions (sy * (FT_X + 2) + sx) that pass the compass test
+  __shared__ unsigned short s_list[FT_LIST];      // corner positions
+  __shared__ int s_na, s_nl, s_n, s_base;
   __shared__ unsigned int s_xy[FT_X * FT_Y / 4];
   __shared__ uint8_t s_s[FT_X * FT_Y / 4];
   const int slot = slot0 + blockIdx.z;
   const uint8_t* im = img + (size_t)slot * slab + lvl_off;
   const int x0 = blockIdx.x * FT_X, y0 = blockIdx.y * FT_Y;
-  if (threadIdx.x == 0) { s_n = 0; s_nl = 0; }
+  if (threadIdx.x == 0) { s_n = 0; s_nl = 0; s_na = 0; }
   // stage the tile + 4-pixel apron: 4 bytes per thread-iteration where the row is 4-byte aligned, else bytes
   for (int i = threadIdx.x; i < (FT_Y + 8) * ((FT_X + 8) / 4); i += 256) {
     const int ty = i / ((FT_X + 8) / 4), tq = i - ty * ((FT_X + 8) / 4);
@@ -180,14 +185,35 @@ __global__ void __launch_bounds__(256) fast_kernel(const uint8_t* __restrict__ i
   }
   for (int i = threadIdx.x; i < (FT_Y + 2) * (FT_X + 2); i += 256) (&s_sc[0][0])[i] = 0;
   __syncthreads();
-  // phase 1: corner test, warp-aggregated compaction
+  // phase 1a: compass quick-reject on every position, survivors compacted (warp-aggregated) ...
   for (int i0 = 0; i0 < FT_LIST; i0 += 256) {
     const int i = i0 + threadIdx.x;
-    bool corner = false;
+    bool pass = false;
     if (i < FT_LIST) {
       const int sy = i / (FT_X + 2), sx = i - sy * (FT_X + 2);
       const int gx = x0 - 1 + sx, gy = y0 - 1 + sy;
-      if (gx >= 3 && gx < w - 3 && gy >= 3 && gy < h - 3) corner = fast_is_corner(s_img, sx + 3, sy + 3);
+      if (gx >= 3 && gx < w - 3 && gy >= 3 && gy < h - 3) pass = fast_compass(s_img, sx + 3, sy + 3);
+    }
+    const unsigned bal = __ballot_sync(0xffffffffu, pass);
+    if (bal) {
+      const int lane = threadIdx.x & 31;
+      int base = 0;
+      if (lane == 0) base = atomicAdd(&s_na, __popc(bal));
+      base = __shfl_sync(0xffffffffu, base, 0);
+      if (pass) s_cand[base + __popc(bal & ((1u << lane) - 1))] = (unsigned short)i;
+    }
+  }
+  __syncthreads();
+  // ... 1b: the 16-pixel arc test runs on the survivors only, in dense warps
+  const int na = s_na;
+  for (int k0 = 0; k0 < na; k0 += 256) {
+    const int k = k0 + threadIdx.x;
+    bool corner = false;
+    int i = 0;
+    if (k < na) {
+      i = s_cand[k];
+      const int sy = i / (FT_X + 2), sx = i - sy * (FT_X + 2);
+      corner = fast_is_corner(s_img, sx + 3, sy + 3);
     }
     const unsigned bal = __ballot_sync(0xffffffffu, corner);
     if (bal) {
