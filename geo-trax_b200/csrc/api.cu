@@ -428,7 +428,7 @@ int gt_conv2d(gt_handle e, const uint16_t* x, int B, int H, int W, int cin, cons
     if (out_f32) { pa.out_f32 = (float*)dout; pa.out_img_stride = (long long)Ho * Wo; pa.out_ctot_f32 = cout; pa.out_coff_f32 = 0; }
     else pa.out = &ov;
     pa.res = residual ? &rv : nullptr;
-    e->plan_variant = e->swap_mode < 0 ? 1 : e->swap_mode;   // unit parity of the swapped kernel by default, GT_SWAP=0: the pixel-major one
+    e->plan_variant = e->swap_mode < 0 ? 2 : e->swap_mode;   // unit parity of the swapped kernel (+ halo staging where it applies) by default; GT_SWAP=0: the pixel-major one, 1: swapped without halo
     rc = conv_tc_plan(e, &op, pa);
     e->plan_variant = 0;
     if (rc != GT_OK) break;

@@ -111,6 +111,7 @@ struct ConvOp {
   bf16* w_dev = nullptr;     // [cout_pad][taps][cin_pad]
   float* b_dev = nullptr;    // [cout_pad]
   int cin = 0, cout = 0, cout_pad = 0, cin_pad = 0, k = 1, stride = 1;
+  int occ2 = 0;              // 1: conv_tc.cu compiled for two CTAs per SM (variant 3)
   int swapped = 0;           // 1: conv_sw.cu (weights = A operand, 256-pixel tile = B operand); tmA = activations, tmB = weights either way
   int n_src = 0;             // 1..3 canonical convs fused along cout
   int src[3] = {0, 0, 0};    // canonical conv indices

@@ -18,6 +18,14 @@
 #include "engine.cuh"
 #include "tc_ptx.cuh"
 
+#ifdef GT_SW_TIMING
+__device__ unsigned long long g_sw_dbg[16 * 8];
+extern "C" int gt_debug_sw_timing(unsigned long long* out) { cudaMemcpyFromSymbol(out, g_sw_dbg, sizeof(g_sw_dbg)); unsigned long long z[128] = {}; cudaMemcpyToSymbol(g_sw_dbg, z, sizeof(z)); return 0; }
+__device__ __forceinline__ long long clk_now() { long long t; asm volatile("mov.u64 %0, %%clock64;" : "=l"(t)::"memory"); return t; }
+#define TCK(v) const long long v = clk_now()
+#else
+#define TCK(v)
+#endif
 namespace {
 
 constexpr int kSwThreads = 64 + kEpiWarps * 32;  // 320
@@ -25,6 +33,7 @@ constexpr int kSwMaxStages = 8;
 constexpr int kPx = 256;        // pixels per tile (GEMM N)
 constexpr int kCo = 128;        // output channels per tile (GEMM M)
 constexpr int kStagingBytes = 64 * 1024;
+constexpr int kSwWStages = 4;   // weight ring depth of the halo variant
 
 __device__ __forceinline__ void sts_u16(uint32_t saddr, uint32_t v) {
   asm volatile("st.shared.b16 [%0], %1;" ::"r"(saddr), "h"((unsigned short)v) : "memory");
@@ -42,6 +51,95 @@ __device__ __forceinline__ float from_act16(unsigned short u, int fp16) {
   return __uint_as_float((uint32_t)u << 16);
 }
 
+// ---- MMA issue helpers (see the MMA role in the kernel) -----------------------------------------------------------------------
+struct MmaCtx {
+  uint32_t full_bar, empty_bar, tfull_bar, tempty_bar, wfull_bar, wempty_bar;   // shared addresses of the barrier arrays
+  uint32_t smem_lo, wres_lo;        // descriptor low words (address >> 4) of ring stage 0 and of the weight region
+  uint32_t stage16, w16, x16, row16;  // byte sizes >> 4
+  uint32_t hi_std, hi_halo;         // descriptor high words: SBO = 8 rows / SBO = halo row pitch
+  uint32_t tmem_base, idesc;
+};
+template <int MPK>
+__device__ __forceinline__ void mma_role(const ConvParams& p, const MmaCtx& c) {
+  uint32_t s = 0, ph = 0, li = 0, s_lo = c.smem_lo;
+  const int num_kb = p.num_kb;
+  const bool res = p.b_resident != 0;
+  for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++li) {
+    const uint32_t as = li & 1u;
+    mbar_wait(c.tempty_bar + as * 8u, ((li >> 1) & 1u) ^ 1u);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tacc = c.tmem_base + as * (uint32_t)kPx;
+    uint32_t w_lo = c.wres_lo;
+    for (int kb = 0; kb < num_kb; ++kb) {
+      mbar_wait(c.full_bar + s * 8u, ph);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      if (elect_one()) {
+        issue_kb<MPK>(tacc, res ? w_lo : s_lo + c.x16, c.hi_std, s_lo, c.hi_std, c.idesc, kb ? 1u : 0u);
+        umma_commit(c.empty_bar + s * 8u);
+      }
+      __syncwarp();
+      w_lo += c.w16;
+      s_lo += c.stage16;
+      if (++s == (uint32_t)p.stages) { s = 0; ph ^= 1u; s_lo = c.smem_lo; }
+    }
+    if (elect_one()) umma_commit(c.tfull_bar + as * 8u);
+    __syncwarp();
+  }
+}
+
+// halo variant: one pixel box per (tile, k-block); tap (dy, dx) = the same box read from row dy * halo_w + dx, its 8-row groups
+// halo_w rows apart (hi_halo); weights resident ([tap][kc] k-blocks) or through the weight ring (one stage per tap)
+template <int KS, int MPK>
+__device__ __forceinline__ void mma_role_halo(const ConvParams& p, const MmaCtx& c) {
+  uint32_t s = 0, ph = 0, li = 0, ws = 0, wph = 0, s_lo = c.smem_lo;
+  const uint32_t halo_w16 = (uint32_t)(p.tw + KS - 1) * c.row16;
+  const bool res = p.b_resident != 0;
+  const uint32_t wtap16 = c.w16 * (uint32_t)p.kc_blocks;   // resident weights: distance between the taps of one kc
+  for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++li) {
+    const uint32_t as = li & 1u;
+    mbar_wait(c.tempty_bar + as * 8u, ((li >> 1) & 1u) ^ 1u);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tacc = c.tmem_base + as * (uint32_t)kPx;
+    for (int kc = 0; kc < p.kc_blocks; ++kc) {
+      mbar_wait(c.full_bar + s * 8u, ph);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      if (res) {
+        if (elect_one()) {
+          uint32_t w_lo = c.wres_lo + (uint32_t)kc * c.w16;
+#pragma unroll
+          for (int dy = 0; dy < KS; ++dy)
+#pragma unroll
+            for (int dx = 0; dx < KS; ++dx) {
+              issue_kb<MPK>(tacc, w_lo, c.hi_std, s_lo + (uint32_t)dy * halo_w16 + (uint32_t)dx * c.row16, c.hi_halo, c.idesc, (dy | dx | kc) ? 1u : 0u);
+              w_lo += wtap16;
+            }
+          umma_commit(c.empty_bar + s * 8u);
+        }
+        __syncwarp();
+      } else {
+#pragma unroll
+        for (int dy = 0; dy < KS; ++dy)
+#pragma unroll
+          for (int dx = 0; dx < KS; ++dx) {
+            mbar_wait(c.wfull_bar + ws * 8u, wph);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            if (elect_one()) {
+              issue_kb<MPK>(tacc, c.wres_lo + ws * c.w16, c.hi_std, s_lo + (uint32_t)dy * halo_w16 + (uint32_t)dx * c.row16, c.hi_halo, c.idesc, (dy | dx | kc) ? 1u : 0u);
+              umma_commit(c.wempty_bar + ws * 8u);
+              if (dy == KS - 1 && dx == KS - 1) umma_commit(c.empty_bar + s * 8u);
+            }
+            __syncwarp();
+            if (++ws == (uint32_t)p.a_stages) { ws = 0; wph ^= 1u; }
+          }
+      }
+      s_lo += c.stage16;
+      if (++s == (uint32_t)p.stages) { s = 0; ph ^= 1u; s_lo = c.smem_lo; }
+    }
+    if (elect_one()) umma_commit(c.tfull_bar + as * 8u);
+    __syncwarp();
+  }
+}
+
 __global__ void __launch_bounds__(kSwThreads, 1) conv_sw_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmX,
                                                                 const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ ConvUpMaps tmUp,
                                                                 const __grid_constant__ CUtensorMap tmRes, const ConvParams p) {
@@ -50,9 +148,12 @@ __global__ void __launch_bounds__(kSwThreads, 1) conv_sw_kernel(const __grid_con
   const int row_bytes = p.kb_elems * 2;
   const int w_bytes = kCo * row_bytes;          // A: 128 weight rows of one k-block
   const int x_bytes = kPx * row_bytes;          // B: 256 pixel rows of one k-block
-  const int stage_bytes = p.b_resident ? x_bytes : x_bytes + w_bytes;
-  uint8_t* w_res = smem + (size_t)p.stages * stage_bytes;
-  uint8_t* staging = w_res + (p.b_resident ? (size_t)p.num_kb * w_bytes : 0);
+  // halo mode (3x3 / 2x2 stride-1 layers, 8 x 32 pixel tiles): a ring stage holds ONE (tw + k - 1) x (th + k - 1) pixel box of a
+  // k-block; the k*k taps are row-shifted UMMA descriptors into it (the swizzle XOR acts on absolute smem address bits, so any
+  // whole-row shift and any row-multiple SBO address the bytes TMA wrote).  Weights are resident or flow through their own ring.
+  const int stage_bytes = p.halo ? p.halo_bytes : (p.b_resident ? x_bytes : x_bytes + w_bytes);
+  uint8_t* w_res = smem + (size_t)p.stages * stage_bytes;   // resident weights, or (halo, not resident) the weight ring
+  uint8_t* staging = w_res + (p.b_resident ? (size_t)p.num_kb * w_bytes : (p.halo ? (size_t)p.a_stages * w_bytes : 0));
   uint8_t* tail = staging + kStagingBytes;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(tail);
   uint64_t* empty_bar = full_bar + kSwMaxStages;
@@ -60,8 +161,10 @@ __global__ void __launch_bounds__(kSwThreads, 1) conv_sw_kernel(const __grid_con
   uint64_t* tempty_bar = tfull_bar + 2;
   uint64_t* wres_bar = tempty_bar + 2;
   uint64_t* res_bar = wres_bar + 1;               // [4] residual granule landed (one per 16-bit staging granule)
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(res_bar + 4);
-  float* s_bias = reinterpret_cast<float*>(tmem_ptr_smem + 2);
+  uint64_t* wfull_bar = res_bar + 4;              // [kSwWStages] halo mode, weights not resident: weight ring
+  uint64_t* wempty_bar = wfull_bar + kSwWStages;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(wempty_bar + kSwWStages);
+  float* s_bias = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(tmem_ptr_smem + 2) + 15) & ~(uintptr_t)15);   // 16-byte aligned (lds.128)
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -81,6 +184,10 @@ __global__ void __launch_bounds__(kSwThreads, 1) conv_sw_kernel(const __grid_con
     }
     mbar_init(smem_u32(wres_bar), 1);
     for (int s = 0; s < 4; ++s) mbar_init(smem_u32(&res_bar[s]), 1);
+    for (int s = 0; s < kSwWStages; ++s) {
+      mbar_init(smem_u32(&wfull_bar[s]), 1);
+      mbar_init(smem_u32(&wempty_bar[s]), 1);
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -107,13 +214,39 @@ __global__ void __launch_bounds__(kSwThreads, 1) conv_sw_kernel(const __grid_con
       __syncwarp();
     }
     const uint32_t tx_bytes = (uint32_t)stage_bytes;
-    uint32_t s = 0, ph = 0;
+    uint32_t s = 0, ph = 0, ws = 0, wph = 0;
     TileIter ti;
     ti.init(p, blockIdx.x, gridDim.x);
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ti.next(p)) {
       const TileCoord t = ti.coord(p);
       const int m0 = ti.nt * kCo;
       const int cx = t.x0 * p.stride - p.pad, cy = t.y0 * p.stride - p.pad;
+      if (p.halo) {
+        const int taps = p.ksize * p.ksize;
+        for (int kc = 0; kc < p.kc_blocks; ++kc) {
+          mbar_wait(smem_u32(&empty_bar[s]), ph ^ 1u);
+          if (elect_one()) {
+            const uint32_t fb = smem_u32(&full_bar[s]);
+            mbar_expect_tx(fb, (uint32_t)p.halo_tx);
+            tma_load_4d(smem_u32(smem + (size_t)s * stage_bytes), &tmX, fb, kc * p.kb_elems, cx, cy, t.n);
+          }
+          __syncwarp();
+          if (++s == (uint32_t)p.stages) { s = 0; ph ^= 1u; }
+          if (!p.b_resident) {
+            for (int tap = 0; tap < taps; ++tap) {
+              mbar_wait(smem_u32(&wempty_bar[ws]), wph ^ 1u);
+              if (elect_one()) {
+                const uint32_t fb = smem_u32(&wfull_bar[ws]);
+                mbar_expect_tx(fb, (uint32_t)w_bytes);
+                tma_load_2d(smem_u32(w_res + (size_t)ws * w_bytes), &tmW, fb, (tap * p.kc_blocks + kc) * p.kb_elems, m0);
+              }
+              __syncwarp();
+              if (++ws == (uint32_t)p.a_stages) { ws = 0; wph ^= 1u; }
+            }
+          }
+        }
+        continue;
+      }
       int kb = 0;
       for (int dy = 0; dy < p.ksize; ++dy)
         for (int dx = 0; dx < p.ksize; ++dx)
@@ -132,33 +265,28 @@ __global__ void __launch_bounds__(kSwThreads, 1) conv_sw_kernel(const __grid_con
     }
   } else if (warp == 1) {
     // ===== MMA issuer =====
+    // The issue loop is written for the single issuing lane's latency: descriptors are (constant high word, running 32-bit low
+    // word) pairs, the MMAs of a k-block are unrolled at compile time (MPK = k-block elements / 16), and nothing but two adds
+    // separates consecutive tcgen05.mma.  (With general 64-bit descriptor code the issue block cost ~360 cycles per k-block --
+    // more than the 2 x 135 cycles its MMAs take on the tensor pipe -- and the pipe idled half of the time.)
     const uint32_t fmt = p.fp16 ? 0u : 1u;
     const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(kPx >> 3) << 17) | ((uint32_t)(kCo >> 4) << 24);
-    const uint32_t sbo = 8u * (uint32_t)row_bytes, layout = p.kb_elems == 64 ? 2u : (p.kb_elems == 32 ? 4u : 6u);
-    const int mma_per_kb = p.kb_elems >> 4;
     if (p.b_resident) mbar_wait(smem_u32(wres_bar), 0);
-    uint32_t s = 0, ph = 0, li = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++li) {
-      const uint32_t as = li & 1u;
-      mbar_wait(smem_u32(&tempty_bar[as]), ((li >> 1) & 1u) ^ 1u);
-      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      const uint32_t tacc = tmem_base + as * (uint32_t)kPx;
-      for (int kb = 0; kb < p.num_kb; ++kb) {
-        mbar_wait(smem_u32(&full_bar[s]), ph);
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        if (elect_one()) {
-          uint8_t* sx = smem + (size_t)s * stage_bytes;
-          const uint64_t adesc = make_desc(smem_u32(p.b_resident ? w_res + (size_t)kb * w_bytes : sx + x_bytes), sbo, layout);   // weights
-          const uint64_t bdesc = make_desc(smem_u32(sx), sbo, layout);                                                          // pixels
-          for (int k = 0; k < mma_per_kb; ++k)
-            umma_f16(tacc, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kb | k) ? 1u : 0u);
-          umma_commit(smem_u32(&empty_bar[s]));
-        }
-        __syncwarp();
-        if (++s == (uint32_t)p.stages) { s = 0; ph ^= 1u; }
-      }
-      if (elect_one()) umma_commit(smem_u32(&tfull_bar[as]));
-      __syncwarp();
+    MmaCtx c;
+    c.full_bar = smem_u32(full_bar); c.empty_bar = smem_u32(empty_bar); c.tfull_bar = smem_u32(tfull_bar); c.tempty_bar = smem_u32(tempty_bar);
+    c.wfull_bar = smem_u32(wfull_bar); c.wempty_bar = smem_u32(wempty_bar);
+    c.smem_lo = (smem_u32(smem) & 0x3FFFFu) >> 4; c.wres_lo = (smem_u32(w_res) & 0x3FFFFu) >> 4;
+    c.stage16 = (uint32_t)stage_bytes >> 4; c.w16 = (uint32_t)w_bytes >> 4; c.x16 = (uint32_t)x_bytes >> 4; c.row16 = (uint32_t)row_bytes >> 4;
+    c.tmem_base = tmem_base; c.idesc = idesc;
+    const uint32_t layout = p.kb_elems == 64 ? 2u : (p.kb_elems == 32 ? 4u : 6u);
+    c.hi_std = desc_hi(8u * (uint32_t)row_bytes, layout);
+    c.hi_halo = desc_hi((uint32_t)((p.tw + p.ksize - 1) * row_bytes), layout);
+    const int mpk = p.kb_elems >> 4;
+    if (p.halo) {
+      if (p.ksize == 3) { if (mpk == 4) mma_role_halo<3, 4>(p, c); else if (mpk == 2) mma_role_halo<3, 2>(p, c); else mma_role_halo<3, 1>(p, c); }
+      else { if (mpk == 4) mma_role_halo<2, 4>(p, c); else if (mpk == 2) mma_role_halo<2, 2>(p, c); else mma_role_halo<2, 1>(p, c); }
+    } else {
+      if (mpk == 4) mma_role<4>(p, c); else if (mpk == 2) mma_role<2>(p, c); else mma_role<1>(p, c);
     }
   } else {
     // ===== epilogue =====
@@ -173,7 +301,11 @@ __global__ void __launch_bounds__(kSwThreads, 1) conv_sw_kernel(const __grid_con
     uint32_t li = 0, nstore = 0, res_uses = 0;
     TileIter ti;
     ti.init(p, blockIdx.x, gridDim.x);
+#ifdef GT_SW_TIMING
+    long long d_pre = 0, d_wait = 0, d_a = 0, d_b1 = 0, d_b = 0, d_b2 = 0;
+#endif
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++li, ti.next(p)) {
+      TCK(c0);
       const uint32_t as = li & 1u;
       const TileCoord t = ti.coord(p);
       const int m0 = ti.nt * kCo;
@@ -181,8 +313,17 @@ __global__ void __launch_bounds__(kSwThreads, 1) conv_sw_kernel(const __grid_con
       const bool warp_active = (m0 + q * 32) < p.cout;   // any valid channel in this lane quarter
       const float bias = s_bias[min(ch, p.n_tiles * kCo - 1)];
       const int ybase = t.y0 + h * half_rows;            // first image row of this pixel half
-      const bool gran_active = !p.out_f32 && (m0 + g * 64) < p.cout;
+      const bool xpose = !p.out_f32 && p.cout <= 64;   // small cout: two-phase epilogue through a shared-memory transpose (below)
+      const bool gran_active = !p.out_f32 && !xpose && (m0 + g * 64) < p.cout;
       const uint32_t buf = stg + (uint32_t)((h * 2 + g) * 16384);
+      if (xpose && q == 0 && lane == 0) {
+        if (li > 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        if (p.res) {
+          const uint32_t rb = smem_u32(&res_bar[h * 2]);
+          mbar_expect_tx(rb, 16384u);
+          tma_load_4d(stg + (uint32_t)(h * 2 * 16384), &tmRes, rb, 0, t.x0, ybase, t.n);
+        }
+      }
       if (gran_active) {
         // the granule is free once last tile's bulk stores have read it; then (residual layers) the residual tile is fetched
         // straight into the granule while the MMAs of this tile are still running
@@ -195,11 +336,118 @@ __global__ void __launch_bounds__(kSwThreads, 1) conv_sw_kernel(const __grid_con
           }
         }
       }
+      TCK(c1);
       if (lane == 0) mbar_wait(smem_u32(&tfull_bar[as]), (li >> 1) & 1u);
       __syncwarp();
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      TCK(c2);
+#ifdef GT_SW_TIMING
+      d_pre += c1 - c0; d_wait += c2 - c1;
+#endif
+#if defined(GT_SW_EXP) && GT_SW_EXP == 1   // debug experiment: no epilogue at all (accumulator released at once)
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&tempty_bar[as]));
+      continue;
+#endif
       const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + as * (uint32_t)kPx + (uint32_t)(h * 128);
-      if (!p.out_f32) {
+      if (xpose) {
+        // ---- 16-bit, cout <= 64: only cout / 32 lane quarters of the accumulator hold channels, and a TMEM lane quarter can only
+        // be read by the warps of ONE scheduler (warp % 4), so a direct epilogue does all the SiLU work (2 MUFU per value, 4 lanes /
+        // clk / scheduler) on one or two schedulers.  Instead the owning warps only move raw fp32 accumulators to shared memory
+        // (T[channel][pixel], 16-byte chunks XOR-swizzled by channel), and all four warps of the pixel half then run bias + SiLU
+        // (+ residual) with thread = pixel, packing 8 channels per 16-byte store into the TMA staging granule (h, 0).
+        // T lives in granule (h, 1), which these layers never store from: 16 KB = 128 pixels x 32 channels or 64 x 64.
+        const int steps = p.cout <= 32 ? 1 : 2;
+        const int px = 128 / steps;                        // pixels per step
+        const uint32_t G = stg + (uint32_t)(h * 2 * 16384);
+        const uint32_t T = G + 16384u;
+        const uint32_t trow_b = (uint32_t)px * 4u;         // bytes of one channel row of T
+        const int team_tid = q * 32 + lane;
+        const int pp = team_tid & (px - 1);                // this thread's pixel inside the step
+        const int cb = (team_tid / px) * 32;               // ... and its 32 channels
+#pragma unroll 1
+        for (int st = 0; st < steps; ++st) {
+          if (warp_active) {
+            const uint32_t tw_row = T + (uint32_t)(q * 32 + lane) * trow_b;
+            const int nch = px >> 5;
+#pragma unroll 1
+            for (int c = 0; c < nch; ++c) {
+              uint32_t v[32];
+              tmem_ld_x32(trow + (uint32_t)(st * px + c * 32), v);
+              tmem_ld_wait();
+#pragma unroll
+              for (int j = 0; j < 8; ++j)
+                sts_u4(tw_row + (uint32_t)((((c * 8 + j) ^ (lane & 7))) << 4), make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]));
+            }
+          }
+          if (st == steps - 1) {                            // accumulator fully read by this warp (or never needed)
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) mbar_arrive(smem_u32(&tempty_bar[as]));
+          }
+          TCK(c3);
+          named_bar(6 + h, 128);                            // T complete; the leader's wait_group.read (granule free) is visible
+          TCK(c4);
+          if (st == 0 && p.res) { mbar_wait(smem_u32(&res_bar[h * 2]), res_uses & 1u); ++res_uses; }
+          const int r = st * px + pp;                       // granule row = pixel of this half
+          const uint32_t trd = T + (uint32_t)(((pp >> 2) << 4) + (pp & 3) * 4);
+          // all 32 values of the thread are loaded first and run through SiLU as independent chains (the epilogue is bound by
+          // MUFU / fixed-latency stalls, so instruction-level parallelism across the four 8-channel groups matters)
+          float f[32];
+#pragma unroll
+          for (int k = 0; k < 32; ++k) {
+            uint32_t u;
+            asm volatile("ld.shared.b32 %0, [%1];" : "=r"(u) : "r"((trd ^ (uint32_t)((k & 7) << 4)) + (uint32_t)(cb + k) * trow_b) : "memory");
+            f[k] = __uint_as_float(u);
+          }
+#pragma unroll
+          for (int g8 = 0; g8 < 8; ++g8) {
+            const float4 b4 = lds_f4(smem_u32(s_bias + cb + g8 * 4));
+            const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const float a = fmaf(f[g8 * 4 + k], p.scale, bb[k]);
+              f[g8 * 4 + k] = p.act ? silu_fast(a) : a;
+            }
+          }
+#pragma unroll
+          for (int g8 = 0; g8 < 4; ++g8) {
+            const int c0 = cb + g8 * 8;
+            const uint32_t ga = G + (uint32_t)r * 128u + (uint32_t)((((c0 >> 3) ^ (r & 7))) << 4);
+            float* fg = f + g8 * 8;
+            if (p.res) {
+              uint4 rv;
+              asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(rv.x), "=r"(rv.y), "=r"(rv.z), "=r"(rv.w) : "r"(ga));
+              const uint32_t rr[4] = {rv.x, rv.y, rv.z, rv.w};
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                const float2 d = unpack2_act(rr[k], p.fp16);
+                fg[2 * k] += d.x; fg[2 * k + 1] += d.y;
+              }
+            }
+            uint4 o;
+            o.x = pack2_act(fg[0], fg[1], p.fp16); o.y = pack2_act(fg[2], fg[3], p.fp16);
+            o.z = pack2_act(fg[4], fg[5], p.fp16); o.w = pack2_act(fg[6], fg[7], p.fp16);
+            sts_u4(ga, o);
+          }
+          TCK(c5);
+          if (st == steps - 1) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          named_bar(6 + h, 128);                            // T may be overwritten; the granule is complete after the last step
+          TCK(c6);
+#ifdef GT_SW_TIMING
+          d_a += c3 - (st == 0 ? c2 : c2); d_b1 += c4 - c3; d_b += c5 - c4; d_b2 += c6 - c5;
+#endif
+        }
+        if (q == 0 && lane == 0) {
+          tma_store_4d(&tmOut, G, 0, t.x0, ybase, t.n);
+          if (p.up) {
+#pragma unroll
+            for (int d = 0; d < 4; ++d) tma_store_4d(tmUp.m + d, G, 0, t.x0, ybase, t.n);
+          }
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
+      } else if (!p.out_f32) {
         // ---- 16-bit: granule (h, g) = 128 pixels x 64 channels, shared by quarters 2g and 2g+1 ----
         if (gran_active) {
           named_bar(2 + h * 2 + g, 64);                  // leader's wait_group.read is visible to the neighbour warp
@@ -296,6 +544,14 @@ __global__ void __launch_bounds__(kSwThreads, 1) conv_sw_kernel(const __grid_con
         }
       }
     }
+#ifdef GT_SW_TIMING
+    if (lane == 0) {
+      unsigned long long* d = g_sw_dbg + (warp) * 8;
+      atomicAdd(d + 0, (unsigned long long)d_pre); atomicAdd(d + 1, (unsigned long long)d_wait); atomicAdd(d + 2, (unsigned long long)d_a);
+      atomicAdd(d + 3, (unsigned long long)d_b1); atomicAdd(d + 4, (unsigned long long)d_b); atomicAdd(d + 5, (unsigned long long)d_b2);
+      atomicAdd(d + 6, (unsigned long long)li);
+    }
+#endif
     if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   }
 
@@ -308,7 +564,7 @@ __global__ void __launch_bounds__(kSwThreads, 1) conv_sw_kernel(const __grid_con
 }
 
 size_t sw_smem_bytes(int stages, int stage_bytes, int wres_bytes, int bias_floats) {
-  return 1024 + (size_t)stages * stage_bytes + (size_t)wres_bytes + kStagingBytes + (2 * kSwMaxStages + 9) * 8 + 8 + (size_t)bias_floats * 4 + 16;
+  return 1024 + (size_t)stages * stage_bytes + (size_t)wres_bytes + kStagingBytes + (2 * kSwMaxStages + 9 + 2 * kSwWStages) * 8 + 8 + (size_t)bias_floats * 4 + 16;
 }
 
 void pick_tile256(int H, int W, bool f32, int* tw, int* th) {
@@ -346,6 +602,9 @@ int conv_sw_plan(gt_engine* e, ConvOp* op, const ConvPlanArgs& a) {
   p.B = a.Bmax; p.H = Ho; p.W = Wo;
   pick_tile256(Ho, Wo, a.out_f32 != nullptr, &p.tw, &p.th);
   if (a.out_s2d) { p.tw = 16; p.th = 16; GT_CHECK(e, (Ho % 8) == 0, "conv plan: s2d output needs Ho %% 8 == 0"); }   // granules are 16 x 8: never straddle images
+  // variant 2: halo staging for stride-1 k >= 2 layers with 16-bit NHWC outputs (8-pixel-wide tiles: one 8-row descriptor group per image row)
+  bool halo = e->plan_variant == 2 && stride == 1 && k >= 2 && !a.out_f32 && !a.out_s2d;
+  if (halo) { p.tw = 8; p.th = 32; }
   GT_CHECK(e, p.tw * stride <= 256 && p.th * stride <= 256, "conv plan: TMA box too large");
   p.tiles_x = ceil_div(Wo, p.tw); p.tiles_y = ceil_div(Ho, p.th);
   p.stride = stride; p.ksize = k; p.pad = pad;
@@ -362,7 +621,26 @@ int conv_sw_plan(gt_engine* e, ConvOp* op, const ConvPlanArgs& a) {
   const size_t budget = (size_t)e->conv_smem_kb * 1024;
   p.b_resident = (p.n_tiles == 1 && wres_bytes <= 80 * 1024) ? 1 : 0;
   int stage_bytes = 0, stages = 0;
-  for (int attempt = 0; attempt < 2; ++attempt) {   // resident weights only if at least 3 ring stages remain
+  if (halo) {
+    const int halo_rows = (p.tw + k - 1) * (p.th + k - 1);
+    p.halo_tx = halo_rows * kbe * 2;
+    p.halo_bytes = (p.halo_tx + 1023) / 1024 * 1024;
+    p.a_stages = kSwWStages;
+    const int wreg = p.b_resident ? wres_bytes : kSwWStages * w_bytes;
+    const size_t fixed = sw_smem_bytes(0, 0, wreg, op->cout_pad);
+    stages = fixed < budget ? (int)((budget - fixed) / p.halo_bytes) : 0;
+    if (stages >= 2) {
+      p.halo = 1;
+      stage_bytes = p.halo_bytes;
+      if (stages > kSwMaxStages) stages = kSwMaxStages;
+    } else {   // does not fit: plain swapped plan
+      halo = false;
+      pick_tile256(Ho, Wo, false, &p.tw, &p.th);
+      p.tiles_x = ceil_div(Wo, p.tw); p.tiles_y = ceil_div(Ho, p.th);
+      p.halo_tx = p.halo_bytes = p.a_stages = 0;
+    }
+  }
+  for (int attempt = 0; attempt < 2 && !halo; ++attempt) {   // resident weights only if at least 3 ring stages remain
     stage_bytes = p.b_resident ? x_bytes : x_bytes + w_bytes;
     const size_t fixed = sw_smem_bytes(0, stage_bytes, p.b_resident ? wres_bytes : 0, op->cout_pad);
     stages = fixed < budget ? (int)((budget - fixed) / stage_bytes) : 0;
@@ -372,7 +650,7 @@ int conv_sw_plan(gt_engine* e, ConvOp* op, const ConvPlanArgs& a) {
   if (stages > kSwMaxStages) stages = kSwMaxStages;
   GT_CHECK(e, stages >= 2, "conv plan (swapped): operands do not fit shared memory");
   p.stages = stages;
-  p.cout = cout; p.act = a.act; p.fp16 = e->cfg.act_dtype == GT_ACT_FP16 ? 1 : 0;
+  p.cout = cout; p.act = getenv("GT_DEBUG_NOACT") ? 0 : a.act; p.fp16 = e->cfg.act_dtype == GT_ACT_FP16 ? 1 : 0;
   p.scale = a.scale;
   if (a.out_f32) {
     p.out_f32 = 1; p.out = a.out_f32; p.out_img_stride = a.out_img_stride; p.out_ctot = a.out_ctot_f32; p.out_coff = a.out_coff_f32;
@@ -392,7 +670,7 @@ int conv_sw_plan(gt_engine* e, ConvOp* op, const ConvPlanArgs& a) {
     GT_CHECK(e, a.up->H == 2 * Ho && a.up->W == 2 * Wo && a.up->C == cout && !a.out_f32, "conv plan: upsample view mismatch");
     p.up = a.up->ptr; p.up_ctot = a.up->ctot; p.up_coff = a.up->coff;
   }
-  op->smem = sw_smem_bytes(p.stages, stage_bytes, p.b_resident ? wres_bytes : 0, op->cout_pad);
+  op->smem = sw_smem_bytes(p.stages, stage_bytes, p.b_resident ? wres_bytes : (p.halo ? kSwWStages * w_bytes : 0), op->cout_pad);
   op->flops = 2.0 * Ho * Wo * (double)cout * cin * k * k;
   op->bytes = (double)in.H * in.W * cin * 2 + (double)Ho * Wo * cout * (a.out_f32 ? 4 : 2) * (a.up ? 5 : 1) + (a.res ? (double)Ho * Wo * cout * 2 : 0.0);
 
@@ -408,7 +686,7 @@ int conv_sw_plan(gt_engine* e, ConvOp* op, const ConvPlanArgs& a) {
   {  // X: NHWC input slice {C, W, H, N}, box = one 256-pixel tile of one k-block (op->tmB keeps the "activation" map)
     cuuint64_t gdim[4] = {(cuuint64_t)cin, (cuuint64_t)in.W, (cuuint64_t)in.H, (cuuint64_t)a.Bmax};
     cuuint64_t gstr[3] = {(cuuint64_t)in.ctot * 2, (cuuint64_t)in.W * in.ctot * 2, (cuuint64_t)in.H * in.W * in.ctot * 2};
-    cuuint32_t box[4] = {(cuuint32_t)kbe, (cuuint32_t)(p.tw * stride), (cuuint32_t)(p.th * stride), 1};
+    cuuint32_t box[4] = {(cuuint32_t)kbe, (cuuint32_t)(p.halo ? p.tw + k - 1 : p.tw * stride), (cuuint32_t)(p.halo ? p.th + k - 1 : p.th * stride), 1};
     cuuint32_t estr[4] = {1, (cuuint32_t)stride, (cuuint32_t)stride, 1};
     CUresult r = conv_tc_encode()(&op->tmA, dt, 4, (void*)(in.ptr + in.coff), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
                                   CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);

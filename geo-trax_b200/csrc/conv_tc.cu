@@ -132,7 +132,10 @@ __device__ __forceinline__ void epilogue_tile(const ConvParams& p, const TileCoo
   }
 }
 
-__global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+// OCC = CTAs per SM the instantiation is compiled for: 2 (register cap 96, <= 113 KB shared memory, <= 256 TMEM columns per CTA)
+// doubles the number of epilogue chains in flight for layers whose tiles carry little MMA work (small cout / small K).
+template <int OCC>
+__global__ void __launch_bounds__(kThreads, OCC) conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                                                               const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ ConvUpMaps tmUp,
                                                               const ConvParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -266,6 +269,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
     const int mma_per_kb = p.kb_elems >> 4;
     if (p.b_resident) mbar_wait(smem_u32(bres_bar), 0);
     uint32_t s = 0, ph = 0, li = 0, hs = 0, hph = 0;
+    const uint32_t smem_lo = (smem_u32(smem) & 0x3FFFFu) >> 4, bres_lo = (smem_u32(b_res) & 0x3FFFFu) >> 4;
+    const uint32_t stage16 = (uint32_t)stage_bytes >> 4, a16 = (uint32_t)a_bytes >> 4, b16 = (uint32_t)b_bytes >> 4;
+    const uint32_t hi_std = desc_hi(sbo, layout), full_bar_a = smem_u32(full_bar), empty_bar_a = smem_u32(empty_bar);
+    uint32_t s_lo = smem_lo;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++li) {
       const uint32_t as = li & 1u;
       mbar_wait(smem_u32(&tempty_bar[as]), ((li >> 1) & 1u) ^ 1u);   // epilogue has drained this accumulator
@@ -303,21 +310,22 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
           if (++hs == (uint32_t)p.a_stages) { hs = 0; hph ^= 1u; }
         }
       } else {
+        // lean issue: running low words, MMAs of a k-block unrolled at compile time (tc_ptx.cuh)
+        uint32_t b_lo = bres_lo;
         for (int kb = 0; kb < p.num_kb; ++kb) {
-          mbar_wait(smem_u32(&full_bar[s]), ph);
+          mbar_wait(full_bar_a + s * 8u, ph);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           if (elect_one()) {
-            uint8_t* sa = smem + (size_t)s * stage_bytes;
-            const uint64_t adesc = make_desc(smem_u32(sa), sbo, layout);
-            const uint64_t bdesc = make_desc(smem_u32(p.b_resident ? b_res + (size_t)kb * b_bytes : sa + a_bytes), sbo, layout);
-            for (int k = 0; k < mma_per_kb; ++k) {
-              // advance 16 elements = 32 B along K inside the swizzle atom: +2 in the (>>4) start-address field
-              umma_f16(tacc, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kb | k) ? 1u : 0u);
-            }
-            umma_commit(smem_u32(&empty_bar[s]));  // frees this smem stage when the MMAs above retire
+            const uint32_t bl = p.b_resident ? b_lo : s_lo + a16;
+            if (mma_per_kb == 4) issue_kb<4>(tacc, s_lo, hi_std, bl, hi_std, idesc, kb ? 1u : 0u);
+            else if (mma_per_kb == 2) issue_kb<2>(tacc, s_lo, hi_std, bl, hi_std, idesc, kb ? 1u : 0u);
+            else issue_kb<1>(tacc, s_lo, hi_std, bl, hi_std, idesc, kb ? 1u : 0u);
+            umma_commit(empty_bar_a + s * 8u);  // frees this smem stage when the MMAs above retire
           }
           __syncwarp();
-          if (++s == (uint32_t)p.stages) { s = 0; ph ^= 1u; }
+          b_lo += b16;
+          s_lo += stage16;
+          if (++s == (uint32_t)p.stages) { s = 0; ph ^= 1u; s_lo = smem_lo; }
         }
       }
       if (elect_one()) umma_commit(smem_u32(&tfull_bar[as]));   // accumulator complete
@@ -397,7 +405,8 @@ int conv_tc_init(gt_engine* e) {
   cudaDeviceProp prop;
   GT_CUDA(e, cudaGetDeviceProperties(&prop, e->device));
   g_num_sms = prop.multiProcessorCount;
-  GT_CUDA(e, cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  GT_CUDA(e, cudaFuncSetAttribute(conv_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  GT_CUDA(e, cudaFuncSetAttribute(conv_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 113 * 1024));
   return conv_sw_init(e);
 }
 
@@ -418,7 +427,7 @@ static void pick_tile(int H, int W, int* tw, int* th) {
 
 int conv_tc_plan(gt_engine* e, ConvOp* op, const ConvPlanArgs& a) {
   GT_CHECK(e, g_encode != nullptr, "conv_tc_init not called");
-  if (e->plan_variant == 1) return conv_sw_plan(e, op, a);
+  if (e->plan_variant == 1 || e->plan_variant == 2) return conv_sw_plan(e, op, a);
   const View& in = a.in;
   const int cin = a.cin, k = a.k, stride = a.stride;
   const int kbe = (a.kb_elems == 64 && cin == 32) ? 32 : a.kb_elems;   // 32-channel inputs: 64-byte rows instead of half-empty 128-byte rows
@@ -471,7 +480,12 @@ int conv_tc_plan(gt_engine* e, ConvOp* op, const ConvPlanArgs& a) {
   const int a_bytes = 128 * kbe * 2, b_bytes = p.BN * kbe * 2;
   const int bres_bytes = p.num_kb * b_bytes;
   p.b_resident = (p.n_tiles == 1 && bres_bytes <= 112 * 1024 && (size_t)bres_bytes + 3 * a_bytes + 40 * 1024 <= (size_t)e->conv_smem_kb * 1024) ? 1 : 0;
-  const size_t budget = (size_t)e->conv_smem_kb * 1024;
+  const bool occ2 = e->plan_variant == 3 && p.tmem_cols <= 256 && !want_halo;   // two CTAs per SM (BN <= 128); else the plain plan
+  const size_t budget = occ2 ? (size_t)112 * 1024 : (size_t)e->conv_smem_kb * 1024;
+  if (occ2) {
+    p.b_resident = (p.n_tiles == 1 && (size_t)bres_bytes + 3 * a_bytes + 36 * 1024 <= budget) ? 1 : 0;
+  }
+  op->occ2 = occ2 ? 1 : 0;
   int stage_bytes = p.b_resident ? a_bytes : a_bytes + b_bytes;
   int halo_total = 0;
   if (want_halo) {
@@ -503,7 +517,7 @@ int conv_tc_plan(gt_engine* e, ConvOp* op, const ConvPlanArgs& a) {
     GT_CHECK(e, stages >= 2, "conv plan: tile does not fit shared memory (BN=%d)", p.BN);
     p.stages = stages;
   }
-  p.cout = cout_total; p.act = a.act; p.fp16 = e->cfg.act_dtype == GT_ACT_FP16 ? 1 : 0;
+  p.cout = cout_total; p.act = getenv("GT_DEBUG_NOACT") ? 0 : a.act; p.fp16 = e->cfg.act_dtype == GT_ACT_FP16 ? 1 : 0;
   p.scale = a.scale;
   if (a.out_f32) {
     p.out_f32 = 1; p.out = a.out_f32; p.out_img_stride = a.out_img_stride; p.out_ctot = a.out_ctot_f32; p.out_coff = a.out_coff_f32;
@@ -646,8 +660,10 @@ int conv_tc_launch_range(gt_engine* e, const ConvOp* op, int b0, int nb, cudaStr
   p.B = nb;
   p.img0 = b0;
   p.total_tiles = p.tiles_x * p.tiles_y * nb * p.n_tiles;
-  const int grid = p.total_tiles < g_num_sms ? p.total_tiles : g_num_sms;
-  conv_tc_kernel<<<grid, kThreads, op->smem, st>>>(op->tmA, op->tmB, op->tmOut, op->tmUp, p);
+  const int slots = g_num_sms * (op->occ2 ? 2 : 1);
+  const int grid = p.total_tiles < slots ? p.total_tiles : slots;
+  if (op->occ2) conv_tc_kernel<2><<<grid, kThreads, op->smem, st>>>(op->tmA, op->tmB, op->tmOut, op->tmUp, p);
+  else conv_tc_kernel<1><<<grid, kThreads, op->smem, st>>>(op->tmA, op->tmB, op->tmOut, op->tmUp, p);
   e->launches++;
   GT_CUDA(e, cudaGetLastError());
   return GT_OK;

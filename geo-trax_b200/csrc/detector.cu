@@ -565,7 +565,20 @@ struct Builder {
     e->plan_variant = 1;
     r = conv_tc_plan(e, &alt, a);
     e->plan_variant = 0;
-    if (r == GT_OK) e->conv_alt.push_back(alt);
+    if (r != GT_OK) return r;
+    e->conv_alt.push_back(alt);
+    ConvOp alt2 = op;               // variant 2: swapped + halo staging; kept only where the halo plan applies
+    e->plan_variant = 2;
+    r = conv_tc_plan(e, &alt2, a);
+    e->plan_variant = 0;
+    if (r != GT_OK) return r;
+    e->conv_alt2.push_back(alt2);
+    ConvOp alt3 = op;               // variant 3: pixel-major kernel at two CTAs per SM; kept only where it applies (BN <= 128)
+    e->plan_variant = 3;
+    r = conv_tc_plan(e, &alt3, a);
+    e->plan_variant = 0;
+    if (r != GT_OK) return r;
+    e->conv_alt3.push_back(alt3);
     return r;
   }
   // 16-bit conv writing a channel slice; several canonical convs reading the same input are fused along cout
@@ -605,7 +618,7 @@ struct Builder {
     rc = plan_both(op, a);
     if (rc != GT_OK) return;
     op.flops = 2.0 * out.H * out.W * 32.0 * 27.0;   // the algorithmic 3x3x3 work, not the zero-padded 2x2x64 -> 128
-    if (!e->conv_alt.empty()) e->conv_alt.back().flops = op.flops;
+    if (!e->conv_alt.empty()) { e->conv_alt.back().flops = op.flops; e->conv_alt2.back().flops = op.flops; e->conv_alt3.back().flops = op.flops; }
     e->conv0_op = (int)e->conv_ops.size();
     push(op);
   }
@@ -836,6 +849,8 @@ int detector_load_weights(gt_engine* e, const float* const* w, const float* cons
   for (size_t oi = 0; oi < e->conv_ops.size(); ++oi) {
     GT_TRY(load_op_weights(e, e->conv_ops[oi], (int)oi == e->conv0_op, w, b));
     if (!e->conv_alt.empty()) GT_TRY(load_op_weights(e, e->conv_alt[oi], (int)oi == e->conv0_op, w, b));
+    if (!e->conv_alt2.empty() && e->conv_alt2[oi].p.halo) GT_TRY(load_op_weights(e, e->conv_alt2[oi], (int)oi == e->conv0_op, w, b));
+    if (!e->conv_alt3.empty() && e->conv_alt3[oi].occ2) GT_TRY(load_op_weights(e, e->conv_alt3[oi], (int)oi == e->conv0_op, w, b));
   }
   e->weights_loaded = true;
   return GT_OK;
@@ -859,11 +874,26 @@ int detector_autotune(gt_engine* e, cudaStream_t st) {
     return GT_OK;
   };
   int n_swapped = 0;
+  const bool tune_log = getenv("GT_TUNE_LOG") != nullptr;   // per-layer times of both kernels on stderr
   for (size_t i = 0; i < e->conv_ops.size(); ++i) {
-    float t0 = 0, t1 = 0;
+    float t0 = 0, t1 = 0, t2 = 1e30f;
     GT_TRY(time_op(e->conv_ops[i], &t0));
     GT_TRY(time_op(e->conv_alt[i], &t1));
-    if (t1 < t0) { std::swap(e->conv_ops[i], e->conv_alt[i]); ++n_swapped; }
+    const bool has2 = e->conv_alt2[i].p.halo != 0;
+    if (has2) { GT_TRY(time_op(e->conv_alt2[i], &t2)); e->launches -= 3; }
+    float t3 = 1e30f;
+    const bool has3 = e->conv_alt3[i].occ2 != 0;
+    if (has3) { GT_TRY(time_op(e->conv_alt3[i], &t3)); e->launches -= 3; }
+    const float tb = std::min(std::min(t0, t1), std::min(t2, t3));
+    if (tune_log) {
+      const ConvOp& o = e->conv_ops[i];
+      fprintf(stderr, "[gt tune] op %2zu src %2d cin %4d cout %4d k %d s %d out %4dx%-4d  tc %7.1f us  sw %7.1f us  halo %7.1f us  tc2 %7.1f us  %6.1f TFLOP/s  %6.1f GB/s\n", i, o.src[0],
+              o.cin, o.cout, o.k, o.stride, o.p.H, o.p.W, 500.f * t0, 500.f * t1, has2 ? 500.f * t2 : 0.f, has3 ? 500.f * t3 : 0.f, o.flops * B / (tb * 0.5e-3) * 1e-12,
+              o.bytes * B / (tb * 0.5e-3) * 1e-9);
+    }
+    if (t3 == tb && has3) { std::swap(e->conv_ops[i], e->conv_alt3[i]); ++e->n_occ2; }
+    else if (t2 == tb && has2) { std::swap(e->conv_ops[i], e->conv_alt2[i]); ++n_swapped; ++e->n_halo; }
+    else if (t1 == tb) { std::swap(e->conv_ops[i], e->conv_alt[i]); ++n_swapped; }
   }
   e->launches -= (int64_t)e->conv_ops.size() * 6;   // tuning launches are not part of any step
   cudaEventDestroy(a);

@@ -37,7 +37,7 @@ struct gt_engine {
   cudaStream_t stream = nullptr;
   std::string err;
   int64_t launches = 0;
-  int swap_mode = -1;                   // conv kernel per layer: -1 autotune (time both at weight load), 0 pixel-major (conv_tc.cu), 1 swapped (conv_sw.cu); GT_SWAP env
+  int swap_mode = -1;                   // conv kernel per layer: -1 autotune (time the variants at weight load), 0 pixel-major (conv_tc.cu), 1 swapped (conv_sw.cu), 2 swapped + halo staging where it applies, 3 pixel-major at two CTAs per SM where it applies; GT_SWAP env
   int plan_variant = 0;                 // variant conv_tc_plan builds right now (0 / 1)
   int halo_mode = 0;                    // conv A-operand staging: 0 per-tap boxes, 1 halo boxes + shifted descriptors (GT_HALO=1 enables: fewer L2->SM bytes, but the layers are tensor-issue bound)
   std::vector<void*> dev_allocs;
@@ -76,6 +76,10 @@ struct gt_engine {
   std::vector<ConvOp> conv_ops;                     // fused tcgen05 ops (the variant in use)
   std::vector<ConvOp> conv_alt;                     // the other variant of each op (autotune), same indexing; empty when a variant is forced
   std::vector<PlanOp> plan;
+  std::vector<ConvOp> conv_alt2;                    // swapped + halo variant (valid where p.halo == 1), same indexing
+  std::vector<ConvOp> conv_alt3;                    // pixel-major kernel at two CTAs per SM (valid where occ2 == 1), same indexing
+  int n_occ2 = 0;                                   // convs on the two-CTA variant after autotune
+  int n_halo = 0;                                   // convs on the halo variant after autotune
   int conv0_op = -1;                                // index of layer 0 in conv_ops (custom weight packing)
   View feat_views[23];
   float* raw_head = nullptr;                        // [B][A][no_pad]

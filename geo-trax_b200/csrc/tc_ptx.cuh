@@ -73,6 +73,34 @@ __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// ---- lean issue helpers: descriptors as (running 32-bit low word, constant high word) ----------------------------------------
+// The single issuing lane is latency bound: with general 64-bit descriptor arithmetic the issue block of one k-block cost ~360
+// cycles (measured with clock64), more than the 2-4 MMAs of the block take on the tensor pipe (135 cycles for M128 N256 K16,
+// 71 for N128, 55 for N <= 64: tools/scratch/mma_bench.cu), so the pipe idled.  High word = SBO | version | layout.
+__device__ __forceinline__ uint32_t desc_hi(uint32_t sbo_bytes, uint32_t layout) { return (sbo_bytes >> 4) | (1u << 14) | (layout << 29); }
+// D (+)= A . B^T with descriptors given as (low word, high word); ACC = 0: overwrite, 1: accumulate, 2: runtime flag `acc`
+template <int ACC>
+__device__ __forceinline__ void umma_lohi(uint32_t tmem_d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi, uint32_t idesc, uint32_t acc = 1u) {
+  if constexpr (ACC == 2) {
+    asm volatile(
+        "{\n.reg .pred p;\n.reg .b64 da, db;\nsetp.ne.b32 p, %6, 0;\nmov.b64 da, {%1, %2};\nmov.b64 db, {%3, %4};\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n}\n" ::"r"(tmem_d), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(acc)
+        : "memory");
+  } else {
+    asm volatile(
+        "{\n.reg .pred p;\n.reg .b64 da, db;\nsetp.ne.b32 p, %6, 0;\nmov.b64 da, {%1, %2};\nmov.b64 db, {%3, %4};\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n}\n" ::"r"(tmem_d), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "n"(ACC)
+        : "memory");
+  }
+}
+// one k-block: MPK MMAs of K = 16 (32 bytes = 2 descriptor units apart); the first one accumulates iff `acc_first`
+template <int MPK>
+__device__ __forceinline__ void issue_kb(uint32_t tacc, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi, uint32_t idesc, uint32_t acc_first) {
+  umma_lohi<2>(tacc, a_lo, a_hi, b_lo, b_hi, idesc, acc_first);
+#pragma unroll
+  for (int k = 1; k < MPK; ++k) umma_lohi<1>(tacc, a_lo + 2u * k, a_hi, b_lo + 2u * k, b_hi, idesc);
+}
+
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }

@@ -64,6 +64,35 @@ def small_engine_tc():
     eng.close()
 
 
+def _forced_engine(swap):
+    import os
+    old = os.environ.get("GT_SWAP")
+    os.environ["GT_SWAP"] = str(swap)
+    try:
+        return _make_engine("fp16")
+    finally:
+        if old is None:
+            os.environ.pop("GT_SWAP")
+        else:
+            os.environ["GT_SWAP"] = old
+
+
+@pytest.fixture(scope="session")
+def small_engine_sw():
+    """Forced onto the swapped-operand kernel without halo staging (GT_SWAP=1)."""
+    eng = _forced_engine(1)
+    yield eng
+    eng.close()
+
+
+@pytest.fixture(scope="session")
+def small_engine_occ2():
+    """Forced onto the pixel-major kernel at two CTAs per SM wherever it applies (GT_SWAP=3)."""
+    eng = _forced_engine(3)
+    yield eng
+    eng.close()
+
+
 @pytest.fixture(scope="session")
 def small_engine_bf16():
     eng = _make_engine("bf16")

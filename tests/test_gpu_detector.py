@@ -50,13 +50,17 @@ CONV_CASES = [
     (1, 20, 28, 128, 4, 1, 1, False, False, True),      # final class conv: N padded to 16, fp32 rows
     (1, 20, 28, 64, 64, 1, 1, False, False, True),      # final box conv, fp32 rows
     (1, 68, 120, 128, 128, 3, 2, True, False, False),
+    (2, 40, 44, 64, 64, 3, 1, True, True, False),       # halo staging with the weight ring, ragged 8 x 32 tiles, residual
+    (1, 70, 20, 128, 64, 3, 1, True, False, False),     # halo staging, two k-blocks per tap
 ]
 
 
-@pytest.mark.parametrize("dtype", ["fp16", "bf16", "fp16-pixel-major"])
+@pytest.mark.parametrize("dtype", ["fp16", "bf16", "fp16-pixel-major", "fp16-swapped-nohalo", "fp16-two-cta"])
 @pytest.mark.parametrize("case", CONV_CASES)
-def test_conv2d_tcgen05_matches_torch(small_engine, small_engine_bf16, small_engine_tc, case, dtype):
-    eng = {"fp16": small_engine, "bf16": small_engine_bf16, "fp16-pixel-major": small_engine_tc}[dtype]
+def test_conv2d_tcgen05_matches_torch(request, case, dtype):
+    fixture = {"fp16": "small_engine", "bf16": "small_engine_bf16", "fp16-pixel-major": "small_engine_tc", "fp16-swapped-nohalo": "small_engine_sw",
+               "fp16-two-cta": "small_engine_occ2"}[dtype]
+    eng = request.getfixturevalue(fixture)
     rnd = lambda a: eng.act_to_f32(eng.f32_to_act(a))
     B, H, W, cin, cout, k, s, act, use_res, f32 = case
     g = torch.Generator().manual_seed(abs(hash(case)) % (2 ** 31))
@@ -122,11 +126,13 @@ def test_raw_head_within_1e2_of_fp32_oracle(small_engine, small_engine_bf16, dty
         assert rel < max(2.5 * rel_emu, 1e-2)   # the GPU also rounds the folded weights to bf16
 
 
-def test_pixel_major_kernel_raw_head(small_engine_tc):
-    """The forced pixel-major conv kernel (conv_tc.cu) through the whole network."""
+@pytest.mark.parametrize("variant", ["pixel-major", "two-cta", "swapped-nohalo"])
+def test_forced_kernel_raw_head(request, variant):
+    """Each forced conv kernel variant (conv_tc.cu at one / two CTAs per SM, conv_sw.cu without halo) through the whole network."""
     from oracle import prepost
-    eng = small_engine_tc
-    assert eng.conv_kernel_info()[1] == 0
+    eng = request.getfixturevalue({"pixel-major": "small_engine_tc", "two-cta": "small_engine_occ2", "swapped-nohalo": "small_engine_sw"}[variant])
+    if variant != "swapped-nohalo":
+        assert eng.conv_kernel_info()[1] == 0
     frames = _frames(2, 512, 768, seed=3)
     eng.preprocess(frames)
     eng.detect(2, conf=0.25)
