@@ -173,9 +173,10 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dev = torch.device("cuda", local)
 
-    eng = geotrax_b200.Engine(frame_hw=FRAME_HW, imgsz=IMGSZ, nc=4, max_batch=BATCH, device=local, act_dtype=args.dtype)
-    sd = weights.random_state_dict(4, "detect", seed=0, frame_hw=FRAME_HW, imgsz=IMGSZ, cls_bias=CLS_BIAS)
-    eng.load_weights(weights.fold(sd))
+    task = "obb" if args.workload == "obb" else "detect"
+    eng = geotrax_b200.Engine(frame_hw=FRAME_HW, imgsz=IMGSZ, nc=4, task=task, max_batch=BATCH, device=local, act_dtype=args.dtype)
+    sd = weights.random_state_dict(4, task, seed=0, frame_hw=FRAME_HW, imgsz=IMGSZ, cls_bias=CLS_BIAS)
+    eng.load_weights(weights.fold(sd, 4, task))
     # this rank's contiguous frame range of the synthetic flight: BATCH distinct frames (cycled), + the shared reference frame
     flight = synth.make_flight(BATCH, FRAME_HW[0], FRAME_HW[1], seed=100 + rank)
     frames_np = np.stack(flight[0])
@@ -183,6 +184,7 @@ def run_ours(args):
     # vehicle masks = the generator's 132 golden-like boxes per frame ("dense vehicle masks", configs[2]); in the reference
     # they are the tracker's boxes (extract.py:166,181) -- a random-init detector's own boxes are meaningless as masks
     mask = eng.pack_boxes(flight[1])
+    mask_list = flight[1]
     mask_dev = (torch.from_numpy(mask[0]).to(dev), torch.from_numpy(mask[1]).to(dev))
     mask_ref = eng.pack_boxes(flight[1][:1])
     frames_dev = torch.from_numpy(frames_np).to(dev)
@@ -211,8 +213,22 @@ def run_ours(args):
         else:   # end-to-end: pinned host frames; the H2D copy of step i+1 is started before step i's kernels (double-buffered ingest)
             src, nxt, mb = frames_pin[i % 2], frames_pin[(i + 1) % 2], (mask_pin if i % 2 == 0 else mask_roll_pin)
             if not last:
-                eng.prefetch(nxt, deferred=True)
-        o = eng.extract_batch(src, conf=CONF, iou=IOU, agnostic=True, classes=[0, 1, 2, 3], out=out, stream=stream, mask_boxes=mb)
+                eng.prefetch(nxt, deferred=args.workload in ("fused", "obb"))   # deferred copies are started by gt_extract_batch
+        if args.workload == "detect":        # configs[1]: letterbox + detector + decode/NMS, boxes read back
+            eng.preprocess(src, stream=stream)
+            bx, cnt = eng.detect(int(src.shape[0]), conf=CONF, iou=IOU, agnostic=True, classes=[0, 1, 2, 3], stream=stream)
+            out["boxes"][...] = bx
+            out["counts"][...] = cnt
+            o = out
+        elif args.workload == "stabilize":   # configs[2]: gray/half-res + ORB + match + RANSAC against the reference frame, H read back
+            eng.preprocess(src, stream=stream)
+            Hm, st_, stats = eng.stabilize(int(src.shape[0]), mask_list, stream=stream)
+            out["H"][...] = Hm.reshape(-1, 9)
+            out["status"][...] = st_
+            out["stats"][...] = stats
+            o = out
+        else:
+            o = eng.extract_batch(src, conf=CONF, iou=IOU, agnostic=True, classes=[0, 1, 2, 3], out=out, stream=stream, mask_boxes=mb)
         if world > 1:
             h = torch.from_numpy(np.concatenate([o["counts"].astype(np.float32).ravel(), o["boxes"].ravel(), o["H"].astype(np.float32).ravel(),
                                                  o["status"].astype(np.float32).ravel()]))
@@ -256,6 +272,11 @@ def run_ours(args):
     for i in range(2):
         step("host", i, True)
     ms_e2e, wall_e2e, stage_e2e, _, _ = timed("host", args.steps)               # pinned host frames: H2D inside the timed region
+    if args.workload == "detect":
+        stage[3] = 0.0
+    elif args.workload == "stabilize":
+        stage[1] = stage[2] = 0.0
+        conv_ms = 0.0
     det_counts = out["counts"].copy()
     ok_h = int((out["status"] == 0).sum())
 
@@ -267,12 +288,16 @@ def run_ours(args):
     total_frames = world * args.steps * BATCH
     value = total_frames / (ms / 1000)
     e2e = total_frames / max(wall_e2e, ms_e2e / 1000)
-    conv_tflops = CONV_GFLOP_PER_FRAME * BATCH / conv_ms  # GFLOP / ms = TFLOP/s
+    gflop_frame = 150.04 if args.workload == "obb" else CONV_GFLOP_PER_FRAME   # +cv4 branch for OBB
+    conv_tflops = gflop_frame * BATCH / conv_ms if conv_ms > 0 else 0.0  # GFLOP / ms = TFLOP/s
+    wl_name = {"fused": "detect+stabilize (configs[1]+[2] fused)", "detect": "detect+NMS only (configs[1])",
+               "stabilize": "ORB+match+RANSAC homography only (configs[2])", "obb": "YOLOv8s-OBB rotated NMS + stabilization (configs[3])"}[args.workload]
+    metric = METRIC if args.workload == "fused" else f"4K frames/sec {args.workload}"
     h2d = int(frames_np.nbytes)
     d2h = int(sum(v.nbytes for v in out.values()))
     h2d += int(mask[0].nbytes + mask[1].nbytes)
     cpu_base = None
-    if world == 1 and not args.no_cpu_baseline:
+    if world == 1 and not args.no_cpu_baseline and args.workload == "fused":
         cores = os.cpu_count() or 1
         cpu = CpuPath(sd, cores)
         cpu.frame(ref_np[0])
@@ -283,18 +308,35 @@ def run_ours(args):
             cpu.frame(frames_np[1 + i % (BATCH - 1)])
         cdt = time.perf_counter() - t0
         cpu_base = dict(value=n / cdt, unit=UNIT, cores=cores, kind="port", sample=f"{n} of the step's {BATCH} frames, batch 1, fp32 PyTorch + OpenCV")
-    line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=max(args.warmup, 3), ms_per_step=ms / args.steps,
+    # per-stage roofline fractions (algorithmic bytes / flops per frame from SURVEY.md 8d and DESIGN.md 4; peaks measured)
+    per_frame = dict(preprocess=("hbm", 43.67e6), inference=("tensor", gflop_frame * 1e9), postprocess=("hbm", 5.83e6), stabilize=("hbm", 30.0e6))
+    stages = {}
+    for name, ms_stage in zip(("preprocess", "inference", "postprocess", "stabilize"), stage):
+        kind, work = per_frame[name]
+        if ms_stage <= 0:
+            continue
+        rate = work * BATCH / (ms_stage * 1e-3)
+        pk = peaks["tf_sust"] * 1e12 if kind == "tensor" else peaks["hbm"] * 1e9
+        stages[name] = dict(ms_per_step=float(ms_stage), bound=kind, achieved=rate / (1e12 if kind == "tensor" else 1e9),
+                            unit="TFLOP/s" if kind == "tensor" else "GB/s", frac=rate / pk)
+    roof = dict(bound="tensor", achieved=conv_tflops, peak=peaks["tf_sust"], unit="TFLOP/s", frac=conv_tflops / peaks["tf_sust"], traffic=_conv_traffic(),
+                kernel="conv_tc_kernel / conv_sw_kernel x60 (the conv stack of one 16-frame step = one launch set; traffic = dram bytes of that set, ncu)",
+                peak_source=peaks["src"] + " bf16_tflops_sustained", algorithmic_flops_per_launch_set=gflop_frame * BATCH * 1e9)
+    if args.workload == "stabilize":
+        st = stages.get("stabilize", dict(achieved=0.0, frac=0.0))
+        roof = dict(bound="hbm", achieved=st["achieved"], peak=peaks["hbm"], unit="GB/s", frac=st["frac"], traffic=None,
+                    kernel="ORB pyramid + FAST + select + describe + match + RANSAC launch set of one 16-frame step (dominant: fast_kernel)",
+                    peak_source=peaks["src"] + " hbm_gbs", algorithmic_bytes_per_launch_set=30.0e6 * BATCH)
+    line = dict(metric=metric, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=max(args.warmup, 3), ms_per_step=ms / args.steps,
                 higher_is_better=True, scaling="weak", vs_baseline=None, dtype=args.dtype, data="synthetic",
-                config=dict(workload="detect+stabilize (configs[1]+[2] fused): 16 x 3840x2160 synthetic BGR frames / step, YOLOv8s nc=4 random-init "
+                config=dict(workload=wl_name + ": 16 x 3840x2160 synthetic BGR frames / step, YOLOv8s nc=4 random-init "
                                      "imgsz 1920 (1088x1920), conf 0.25 iou 0.7 agnostic, ORB 2000/4000 + Hamming 2-NN + 5000-hyp RANSAC, box warp",
                             frames_per_step=BATCH, parallelism=f"frame-range shard x{world}", l2="inputs (398 MB / step) larger than the 126 MB L2",
                             stage_ms_per_step=dict(preprocess=stage[0], inference=stage[1], postprocess=stage[2], stabilize=stage[3]),
                             detections_per_frame=float(det_counts.mean()), mask_boxes_per_frame=float(mask[1].mean()), homographies_ok=f"{ok_h}/{BATCH}",
                             matches_per_frame=float(out["stats"][:, 2].mean()), inliers_per_frame=float(out["stats"][:, 3].mean()),
                             conv_launches_per_step=eng.conv_kernel_info()[0], convs_on_swapped_kernel=eng.conv_kernel_info()[1]),
-                roofline=dict(bound="tensor", achieved=conv_tflops, peak=peaks["tf_sust"], unit="TFLOP/s", frac=conv_tflops / peaks["tf_sust"], traffic=_conv_traffic(),
-                              kernel="conv_tc_kernel x63 (the conv stack of one 16-frame step = one launch set; traffic = dram bytes of that set, ncu)", peak_source=peaks["src"] + " bf16_tflops_sustained",
-                              algorithmic_flops_per_launch_set=CONV_GFLOP_PER_FRAME * BATCH * 1e9),
+                roofline=roof, stages=stages,
                 cpu_baseline=cpu_base,
                 e2e=dict(value=e2e, unit=UNIT, h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h, ms_per_step=1000 * wall_e2e / args.steps),
                 gpu_launches=int(launches), clocks=clocks)
@@ -311,6 +353,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--dtype", default="fp16", choices=["fp16", "bf16"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="fused", choices=["fused", "detect", "stabilize", "obb"],
+                    help="fused = BASELINE configs[1]+[2] (default, the headline); detect = configs[1] (YOLOv8s detect+NMS only); "
+                         "stabilize = configs[2] (ORB + match + RANSAC + warp only); obb = configs[3] (YOLOv8s-OBB rotated NMS + stabilization)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

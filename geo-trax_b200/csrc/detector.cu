@@ -858,9 +858,32 @@ int detector_load_weights(gt_engine* e, const float* const* w, const float* cons
 
 // Times both kernel variants of every conv on the full batch and keeps the faster one in conv_ops ("measure, don't guess":
 // which operand order wins depends on cout, K and the epilogue, see profiles/conv_findings_r1.md).
+// Engines of one process with the same geometry reuse the first one's per-layer choice: the variants differ in accumulation
+// order, so re-timing could otherwise make two engine instances differ in the last bits of their outputs.
+static std::map<std::string, std::vector<int>>& tune_cache() { static std::map<std::string, std::vector<int>> c; return c; }
+
+static void apply_choice(gt_engine* e, size_t i, int v, int* n_swapped) {
+  if (v == 3) { std::swap(e->conv_ops[i], e->conv_alt3[i]); ++e->n_occ2; }
+  else if (v == 2) { std::swap(e->conv_ops[i], e->conv_alt2[i]); ++*n_swapped; ++e->n_halo; }
+  else if (v == 1) { std::swap(e->conv_ops[i], e->conv_alt[i]); ++*n_swapped; }
+}
+
 int detector_autotune(gt_engine* e, cudaStream_t st) {
   if (e->conv_alt.empty() || e->tuned) return GT_OK;
   const int B = e->cfg.max_batch;
+  char keybuf[160];
+  snprintf(keybuf, sizeof(keybuf), "%d:%dx%d:%d:%d:%d:%d:%d:%zu", e->device, e->cfg.frame_h, e->cfg.frame_w, e->cfg.imgsz, e->cfg.nc, (int)e->cfg.task, B,
+           (int)e->cfg.act_dtype, e->conv_ops.size());
+  const std::string key(keybuf);
+  auto hit = tune_cache().find(key);
+  if (hit != tune_cache().end() && hit->second.size() == e->conv_ops.size() && !getenv("GT_TUNE_LOG")) {
+    int ns = 0;
+    for (size_t i = 0; i < e->conv_ops.size(); ++i) apply_choice(e, i, hit->second[i], &ns);
+    e->n_swapped = ns;
+    e->tuned = true;
+    return GT_OK;
+  }
+  std::vector<int> choice(e->conv_ops.size(), 0);
   cudaEvent_t a, b;
   GT_CUDA(e, cudaEventCreate(&a));
   GT_CUDA(e, cudaEventCreate(&b));
@@ -891,15 +914,15 @@ int detector_autotune(gt_engine* e, cudaStream_t st) {
               o.cin, o.cout, o.k, o.stride, o.p.H, o.p.W, 500.f * t0, 500.f * t1, has2 ? 500.f * t2 : 0.f, has3 ? 500.f * t3 : 0.f, o.flops * B / (tb * 0.5e-3) * 1e-12,
               o.bytes * B / (tb * 0.5e-3) * 1e-9);
     }
-    if (t3 == tb && has3) { std::swap(e->conv_ops[i], e->conv_alt3[i]); ++e->n_occ2; }
-    else if (t2 == tb && has2) { std::swap(e->conv_ops[i], e->conv_alt2[i]); ++n_swapped; ++e->n_halo; }
-    else if (t1 == tb) { std::swap(e->conv_ops[i], e->conv_alt[i]); ++n_swapped; }
+    choice[i] = (t3 == tb && has3) ? 3 : ((t2 == tb && has2) ? 2 : (t1 == tb ? 1 : 0));
+    apply_choice(e, i, choice[i], &n_swapped);
   }
   e->launches -= (int64_t)e->conv_ops.size() * 6;   // tuning launches are not part of any step
   cudaEventDestroy(a);
   cudaEventDestroy(b);
   e->tuned = true;
   e->n_swapped = n_swapped;
+  tune_cache()[key] = choice;
   return GT_OK;
 }
 

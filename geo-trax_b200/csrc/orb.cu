@@ -77,57 +77,40 @@ __global__ void __launch_bounds__(256) pyr_resize_kernel(uint8_t* __restrict__ p
     for (int k = 0; k < nvalid; ++k) d[k] = (uint8_t)(packed >> (8 * k));
 }
 
-// ---- FAST-9/16 score + 3x3 non-max suppression + mask / border filter -> candidate list ------------------------------------
-// Three phases per 64 x 32 tile so that the expensive part runs in dense warps:
-//   1. corner test for every position of the (tile + 1) ring: compass quick-reject on all positions, survivors compacted; the
-//      16-pixel arc masks only on the survivors; corners compacted into a second shared list;
-//   2. exact corner score (OpenCV cornerScore<16>) only for the listed positions;
-//   3. 3x3 non-max suppression, border filter, block-level compaction into the per-(frame, level) candidate list.
+// ---- FAST-9/16 score + 3x3 non-max suppression + border filter -> candidate list --------------------------------------------
+// One launch covers all pyramid levels (blockIdx.x walks the 64 x 32 tiles of every level's candidate region
+// [kEdge, w - kEdge) x [kEdge, h - kEdge); blockIdx.y = frame slot).  Per tile:
+//   0. stage the tile + apron in shared memory with aligned 32-bit global loads (rows of the pyramid have arbitrary alignment: two
+//      aligned words + a funnel shift per staged word);
+//   1a. compass quick-reject (ring pixels 0, 4, 8, 12: any 9-arc contains two of them) on FOUR horizontally adjacent pixels per
+//      thread with byte-SIMD compares; groups with a surviving pixel are compacted;
+//   1b. the full 16-pixel arc test on the surviving groups, again four pixels per thread: 16 ring words (aligned words + funnel
+//      shifts), byte masks "brighter" / "darker", 9-in-a-row by three-input ANDs; corners are appended to a shared list;
+//   2. exact corner score (OpenCV cornerScore<16>) of the listed corners;
+//   3. 3x3 non-max suppression and compaction into the per-(frame, level) candidate list.
 // The vehicle mask is NOT applied here (it depends on the detections, which are computed concurrently): orb_select_kernel
 // drops masked candidates before its score cut, which is equivalent to OpenCV's order (mask, then retain-best).
 #define FT_X 64
 #define FT_Y 32
+#define FT_SW 76                         // staged columns: gx in [x0 - 5, x0 + 71)
+#define FT_SH (FT_Y + 8)                 // staged rows:    gy in [y0 - 4, y0 + 36)
+#define FT_G 17                          // 4-pixel groups per tested row: sx = 4 g + j, gx = x0 - 1 + sx
+#define FT_ROWS (FT_Y + 2)               // tested rows: sy in [0, 34), gy = y0 - 1 + sy
 #define FT_LIST ((FT_X + 2) * (FT_Y + 2))
 
-__device__ __forceinline__ void fast_ring(const uint8_t (*t)[FT_X + 8], int x, int y, int v, int* d) {
+struct FastLevels {                      // per-level geometry of the single FAST launch
+  int w[GT_ORB_LEVELS], h[GT_ORB_LEVELS], tiles_x[GT_ORB_LEVELS], tile0[GT_ORB_LEVELS + 1], cand_cap[GT_ORB_LEVELS];
+  unsigned long long off[GT_ORB_LEVELS], cand_off[GT_ORB_LEVELS];
+};
+
+__device__ __forceinline__ void fast_ring(const uint8_t (*t)[FT_SW], int x, int y, int v, int* d) {
   d[0] = v - t[y + 3][x];      d[1] = v - t[y + 3][x + 1];  d[2] = v - t[y + 2][x + 2];  d[3] = v - t[y + 1][x + 3];
   d[4] = v - t[y][x + 3];      d[5] = v - t[y - 1][x + 3];  d[6] = v - t[y - 2][x + 2];  d[7] = v - t[y - 3][x + 1];
   d[8] = v - t[y - 3][x];      d[9] = v - t[y - 3][x - 1];  d[10] = v - t[y - 2][x - 2]; d[11] = v - t[y - 1][x - 3];
   d[12] = v - t[y][x - 3];     d[13] = v - t[y + 1][x - 3]; d[14] = v - t[y + 2][x - 2]; d[15] = v - t[y + 3][x - 1];
 }
 
-// cheap necessary condition: any 9 contiguous ring pixels contain two of the four compass pixels (0, 4, 8, 12)
-__device__ __forceinline__ bool fast_compass(const uint8_t (*t)[FT_X + 8], int x, int y) {
-  const int v = t[y][x];
-  const int c0 = v - t[y + 3][x], c4 = v - t[y][x + 3], c8 = v - t[y - 3][x], c12 = v - t[y][x - 3];
-  const int nd = (c0 > kFastThr) + (c4 > kFastThr) + (c8 > kFastThr) + (c12 > kFastThr);
-  const int nb = (c0 < -kFastThr) + (c4 < -kFastThr) + (c8 < -kFastThr) + (c12 < -kFastThr);
-  return nd >= 2 || nb >= 2;
-}
-
-// is (x, y) a FAST-9/16 corner at threshold kFastThr?  (x, y) are tile coordinates >= 3 from the tile edge
-__device__ __forceinline__ bool fast_is_corner(const uint8_t (*t)[FT_X + 8], int x, int y) {
-  const int v = t[y][x];
-  int d[16];
-  fast_ring(t, x, y, v, d);
-  unsigned dark = 0, bright = 0;  // d > thr : ring pixel darker than centre;  d < -thr : brighter
-#pragma unroll
-  for (int k = 0; k < 16; ++k) {
-    dark |= (unsigned)(d[k] > kFastThr) << k;
-    bright |= (unsigned)(d[k] < -kFastThr) << k;
-  }
-  auto run9 = [](unsigned m) {
-    m |= m << 16;  // circular
-    unsigned a = m & (m >> 1);
-    a = a & (a >> 2);
-    a = a & (a >> 4);       // runs of 8
-    a = a & (m >> 8);       // runs of 9
-    return (a & 0xFFFFu) != 0;
-  };
-  return run9(dark) || run9(bright);
-}
-
-__device__ __forceinline__ int fast_corner_score(const uint8_t (*t)[FT_X + 8], int x, int y) {
+__device__ __forceinline__ int fast_corner_score(const uint8_t (*t)[FT_SW], int x, int y) {
   const int v = t[y][x];
   int d[16];
   fast_ring(t, x, y, v, d);
@@ -153,83 +136,142 @@ __device__ __forceinline__ int fast_corner_score(const uint8_t (*t)[FT_X + 8], i
   return best > kFastThr ? best - 1 : 0;
 }
 
-__global__ void __launch_bounds__(256) fast_kernel(const uint8_t* __restrict__ img, size_t slab, int slot0,
-                                                   size_t lvl_off, int w, int h, unsigned int* __restrict__ cand, uint8_t* __restrict__ cscore,
-                                                   size_t cand_slab, size_t cand_off, int cand_cap, int* __restrict__ counts, int level) {
-  __shared__ __align__(16) uint8_t s_img[FT_Y + 8][FT_X + 8];
-  __shared__ uint8_t s_sc[FT_Y + 2][FT_X + 2];
-  __shared__ unsigned short s_cand[FT_LIST];      // positions (sy * (FT_X + 2) + sx) that pass the compass test
-  __shared__ unsigned short s_list[FT_LIST];      // corner positions
+// bytes [o, o + 4) of the 12-byte window (w0, w1, w2), o in 1..7
+__device__ __forceinline__ uint32_t win4(uint32_t w0, uint32_t w1, uint32_t w2, int o) {
+  return o < 4 ? __funnelshift_r(w0, w1, 8 * o) : (o == 4 ? w1 : __funnelshift_r(w1, w2, 8 * (o - 4)));
+}
+// per byte: 0xFF where at least two of the four masks are set
+__device__ __forceinline__ uint32_t two_of_four(uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  return (a & b) | (c & d) | ((a | b) & (c | d));
+}
+// per byte: 0xFF where some 9 circularly consecutive masks of m[0..15] are all set
+__device__ __forceinline__ uint32_t arc9(const uint32_t* m) {
+  uint32_t a3[16];
+#pragma unroll
+  for (int k = 0; k < 16; ++k) a3[k] = m[k] & m[(k + 1) & 15] & m[(k + 2) & 15];
+  uint32_t any = 0;
+#pragma unroll
+  for (int k = 0; k < 16; ++k) any |= a3[k] & a3[(k + 3) & 15] & a3[(k + 6) & 15];
+  return any;
+}
+
+__global__ void __launch_bounds__(256) fast_kernel(const uint8_t* __restrict__ img, size_t slab, int slot0, const FastLevels fl,
+                                                   unsigned int* __restrict__ cand, uint8_t* __restrict__ cscore, size_t cand_slab,
+                                                   int* __restrict__ counts) {
+  __shared__ __align__(16) uint8_t s_img[FT_SH][FT_SW];
+  __shared__ __align__(4) uint8_t s_sc[FT_Y + 2][FT_X + 2];
+  __shared__ unsigned short s_cand[FT_ROWS * FT_G];   // (task << 4 | pixel mask) of the groups that pass the compass test
+  __shared__ unsigned short s_list[FT_LIST];          // corner positions sy * (FT_X + 2) + sx
   __shared__ int s_na, s_nl, s_n, s_base;
   __shared__ unsigned int s_xy[FT_X * FT_Y / 4];
   __shared__ uint8_t s_s[FT_X * FT_Y / 4];
-  const int slot = slot0 + blockIdx.z;
-  const uint8_t* im = img + (size_t)slot * slab + lvl_off;
-  const int x0 = blockIdx.x * FT_X, y0 = blockIdx.y * FT_Y;
-  if (threadIdx.x == 0) { s_n = 0; s_nl = 0; s_na = 0; }
-  // stage the tile + 4-pixel apron: 4 bytes per thread-iteration where the row is 4-byte aligned, else bytes
-  for (int i = threadIdx.x; i < (FT_Y + 8) * ((FT_X + 8) / 4); i += 256) {
-    const int ty = i / ((FT_X + 8) / 4), tq = i - ty * ((FT_X + 8) / 4);
-    const int gy = y0 - 4 + ty, gx = x0 - 4 + tq * 4;
-    uint32_t v = 0;
-    if (gy >= 0 && gy < h) {
-      const uint8_t* row = im + (size_t)gy * w;
-      if (gx >= 0 && gx + 3 < w && ((reinterpret_cast<uintptr_t>(row + gx) & 3) == 0)) v = *reinterpret_cast<const uint32_t*>(row + gx);
-      else {
+  int level = 0;
 #pragma unroll
-        for (int k = 0; k < 4; ++k)
-          if (gx + k >= 0 && gx + k < w) v |= (uint32_t)row[gx + k] << (8 * k);
+  for (int l = 1; l < GT_ORB_LEVELS; ++l) level += (int)blockIdx.x >= fl.tile0[l];
+  const int w = fl.w[level], h = fl.h[level];
+  const int tile = (int)blockIdx.x - fl.tile0[level];
+  const int by = tile / fl.tiles_x[level], bx = tile - by * fl.tiles_x[level];
+  const int slot = slot0 + blockIdx.y;
+  const uint8_t* im = img + (size_t)slot * slab + fl.off[level];
+  const int x0 = kEdge + bx * FT_X, y0 = kEdge + by * FT_Y;
+  if (threadIdx.x == 0) { s_n = 0; s_nl = 0; s_na = 0; }
+  // phase 0: staged word (ty, tq) = image bytes gx = x0 - 5 + 4 tq .. + 3 of row gy = y0 - 4 + ty (rows clamped into the image;
+  // columns outside it only feed positions that are never tested)
+  {
+    const uintptr_t lo = reinterpret_cast<uintptr_t>(im) & ~(uintptr_t)3, hi = (reinterpret_cast<uintptr_t>(im) + (size_t)w * h - 1) & ~(uintptr_t)3;
+    for (int i = threadIdx.x; i < FT_SH * (FT_SW / 4); i += 256) {
+      const int ty = i / (FT_SW / 4), tq = i - ty * (FT_SW / 4);
+      const int gy = min(max(y0 - 4 + ty, 0), h - 1);
+      const uintptr_t a = reinterpret_cast<uintptr_t>(im) + (size_t)gy * w + (x0 - 5 + 4 * tq);
+      const uintptr_t p0 = min(max(a & ~(uintptr_t)3, lo), hi), p1 = min(p0 + 4, hi);
+      const uint32_t v0 = __ldg(reinterpret_cast<const uint32_t*>(p0)), v1 = __ldg(reinterpret_cast<const uint32_t*>(p1));
+      *reinterpret_cast<uint32_t*>(&s_img[ty][tq * 4]) = __funnelshift_r(v0, v1, 8 * (int)(a & 3));
+    }
+  }
+  for (int i = threadIdx.x; i < (FT_Y + 2) * (FT_X + 2) / 2; i += 256) reinterpret_cast<unsigned short*>(&s_sc[0][0])[i] = 0;
+  __syncthreads();
+  const uint32_t thr4 = 0x01010101u * (uint32_t)kFastThr;
+  // tested positions: gx in [kEdge - 1, w - kEdge] (candidates + their 3x3 neighbours), same for gy
+  // phase 1a: compass quick-reject, four pixels per thread
+  for (int t0 = 0; t0 < FT_ROWS * FT_G; t0 += 256) {
+    const int t = t0 + threadIdx.x;
+    uint32_t pass = 0;
+    if (t < FT_ROWS * FT_G) {
+      const int sy = t / FT_G, g = t - sy * FT_G;
+      const int gy = y0 - 1 + sy;
+      if (gy >= kEdge - 1 && gy <= h - kEdge) {
+        const uint32_t* rc = reinterpret_cast<const uint32_t*>(&s_img[sy + 3][0]) + g;
+        const uint32_t w0 = rc[0], c = rc[1], w2 = rc[2];
+        const uint32_t r0 = reinterpret_cast<const uint32_t*>(&s_img[sy + 6][0])[g + 1], r8 = reinterpret_cast<const uint32_t*>(&s_img[sy][0])[g + 1];
+        const uint32_t r4 = __funnelshift_r(c, w2, 24), r12 = __funnelshift_r(w0, c, 8);
+        const uint32_t hi4 = __vaddus4(c, thr4), lo4 = __vsubus4(c, thr4);
+        const uint32_t br = two_of_four(__vcmpgtu4(r0, hi4), __vcmpgtu4(r4, hi4), __vcmpgtu4(r8, hi4), __vcmpgtu4(r12, hi4));
+        const uint32_t dk = two_of_four(__vcmpltu4(r0, lo4), __vcmpltu4(r4, lo4), __vcmpltu4(r8, lo4), __vcmpltu4(r12, lo4));
+        uint32_t m = br | dk;
+        // validity of the four pixels (sx = 4 g + j)
+        const int gx = x0 - 1 + 4 * g;
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if (gx + j < kEdge - 1 || gx + j > w - kEdge || 4 * g + j >= FT_X + 2) m &= ~(0xFFu << (8 * j));
+        pass = m;
       }
     }
-    *reinterpret_cast<uint32_t*>(&s_img[ty][tq * 4]) = v;
-  }
-  for (int i = threadIdx.x; i < (FT_Y + 2) * (FT_X + 2); i += 256) (&s_sc[0][0])[i] = 0;
-  __syncthreads();
-  // phase 1a: compass quick-reject on every position, survivors compacted (warp-aggregated) ...
-  for (int i0 = 0; i0 < FT_LIST; i0 += 256) {
-    const int i = i0 + threadIdx.x;
-    bool pass = false;
-    if (i < FT_LIST) {
-      const int sy = i / (FT_X + 2), sx = i - sy * (FT_X + 2);
-      const int gx = x0 - 1 + sx, gy = y0 - 1 + sy;
-      if (gx >= 3 && gx < w - 3 && gy >= 3 && gy < h - 3) pass = fast_compass(s_img, sx + 3, sy + 3);
-    }
-    const unsigned bal = __ballot_sync(0xffffffffu, pass);
+    const unsigned bal = __ballot_sync(0xffffffffu, pass != 0);
     if (bal) {
       const int lane = threadIdx.x & 31;
       int base = 0;
       if (lane == 0) base = atomicAdd(&s_na, __popc(bal));
       base = __shfl_sync(0xffffffffu, base, 0);
-      if (pass) s_cand[base + __popc(bal & ((1u << lane) - 1))] = (unsigned short)i;
+      if (pass) {
+        const unsigned bits = ((pass >> 7) & 1u) | ((pass >> 14) & 2u) | ((pass >> 21) & 4u) | ((pass >> 28) & 8u);
+        s_cand[base + __popc(bal & ((1u << lane) - 1))] = (unsigned short)((t << 4) | bits);
+      }
     }
   }
   __syncthreads();
-  // ... 1b: the 16-pixel arc test runs on the survivors only, in dense warps
+  // phase 1b: full arc test of the surviving groups
   const int na = s_na;
-  for (int k0 = 0; k0 < na; k0 += 256) {
-    const int k = k0 + threadIdx.x;
-    bool corner = false;
-    int i = 0;
-    if (k < na) {
-      i = s_cand[k];
-      const int sy = i / (FT_X + 2), sx = i - sy * (FT_X + 2);
-      corner = fast_is_corner(s_img, sx + 3, sy + 3);
+  for (int k = threadIdx.x; k < na; k += 256) {
+    const unsigned e = s_cand[k];
+    const int t = e >> 4;
+    const int sy = t / FT_G, g = t - sy * FT_G;
+    uint32_t r[16], c;
+    {
+      const uint32_t* q;
+      uint32_t w0, w1, w2;
+#define FT_ROW(dy) q = reinterpret_cast<const uint32_t*>(&s_img[sy + 3 + (dy)][0]) + g; w0 = q[0]; w1 = q[1]; w2 = q[2];
+      FT_ROW(3)  r[15] = win4(w0, w1, w2, 3); r[0] = w1; r[1] = win4(w0, w1, w2, 5);
+      FT_ROW(2)  r[14] = win4(w0, w1, w2, 2); r[2] = win4(w0, w1, w2, 6);
+      FT_ROW(1)  r[13] = win4(w0, w1, w2, 1); r[3] = win4(w0, w1, w2, 7);
+      FT_ROW(0)  r[12] = win4(w0, w1, w2, 1); r[4] = win4(w0, w1, w2, 7); c = w1;
+      FT_ROW(-1) r[11] = win4(w0, w1, w2, 1); r[5] = win4(w0, w1, w2, 7);
+      FT_ROW(-2) r[10] = win4(w0, w1, w2, 2); r[6] = win4(w0, w1, w2, 6);
+      FT_ROW(-3) r[9] = win4(w0, w1, w2, 3); r[8] = w1; r[7] = win4(w0, w1, w2, 5);
+#undef FT_ROW
     }
-    const unsigned bal = __ballot_sync(0xffffffffu, corner);
-    if (bal) {
-      const int lane = threadIdx.x & 31;
-      int base = 0;
-      if (lane == 0) base = atomicAdd(&s_nl, __popc(bal));
-      base = __shfl_sync(0xffffffffu, base, 0);
-      if (corner) s_list[base + __popc(bal & ((1u << lane) - 1))] = (unsigned short)i;
+    const uint32_t hi4 = __vaddus4(c, thr4), lo4 = __vsubus4(c, thr4);
+    uint32_t m[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) m[i] = __vcmpgtu4(r[i], hi4);
+    uint32_t corner = arc9(m);
+#pragma unroll
+    for (int i = 0; i < 16; ++i) m[i] = __vcmpltu4(r[i], lo4);
+    corner |= arc9(m);
+    unsigned bits = (((corner >> 7) & 1u) | ((corner >> 14) & 2u) | ((corner >> 21) & 4u) | ((corner >> 28) & 8u)) & (e & 15u);
+    if (bits) {
+      const int base = atomicAdd(&s_nl, __popc(bits));
+      int n = 0;
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (bits & (1u << j)) s_list[base + n++] = (unsigned short)(sy * (FT_X + 2) + 4 * g + j);
     }
   }
   __syncthreads();
-  // phase 2: exact score of the listed corners
+  // phase 2: exact score of the listed corners (tile coordinates: x = sx + 4, y = sy + 3)
   for (int k = threadIdx.x; k < s_nl; k += 256) {
     const int i = s_list[k];
     const int sy = i / (FT_X + 2), sx = i - sy * (FT_X + 2);
-    s_sc[sy][sx] = (uint8_t)fast_corner_score(s_img, sx + 3, sy + 3);
+    s_sc[sy][sx] = (uint8_t)fast_corner_score(s_img, sx + 4, sy + 3);
   }
   __syncthreads();
   // phase 3: 3x3 NMS over the listed corners that lie inside the tile, border filter
@@ -252,11 +294,12 @@ __global__ void __launch_bounds__(256) fast_kernel(const uint8_t* __restrict__ i
   __syncthreads();
   if (threadIdx.x == 0 && s_n) s_base = atomicAdd(&counts[slot * GT_ORB_LEVELS + level], s_n);
   __syncthreads();
+  const int cap = fl.cand_cap[level];
   for (int k = threadIdx.x; k < s_n; k += 256) {
     const int dst = s_base + k;
-    if (dst < cand_cap) {
-      cand[(size_t)slot * cand_slab + cand_off + dst] = s_xy[k];
-      cscore[(size_t)slot * cand_slab + cand_off + dst] = s_s[k];
+    if (dst < cap) {
+      cand[(size_t)slot * cand_slab + fl.cand_off[level] + dst] = s_xy[k];
+      cscore[(size_t)slot * cand_slab + fl.cand_off[level] + dst] = s_s[k];
     }
   }
 }
@@ -655,12 +698,21 @@ int orb_front(gt_engine* e, int slot0, int nslots, cudaStream_t st) {
     e->launches++;
   }
   GT_CUDA(e, cudaMemsetAsync(e->fast_count + (size_t)slot0 * GT_ORB_LEVELS, 0, (size_t)nslots * GT_ORB_LEVELS * sizeof(int), st));
-  for (int l = 0; l < GT_ORB_LEVELS; ++l) {
-    const OrbLevel& L = e->lv[l];
-    dim3 g((unsigned)ceil_div(L.w, FT_X), (unsigned)ceil_div(L.h, FT_Y), (unsigned)nslots);
-    fast_kernel<<<g, 256, 0, st>>>(e->pyr, slab, slot0, L.off, L.w, L.h, e->fast_cand, e->fast_score, e->cand_total, L.cand_off, L.cand_cap,
-                                   e->fast_count, l);
-    e->launches++;
+  {
+    FastLevels fl;
+    int tiles = 0;
+    for (int l = 0; l < GT_ORB_LEVELS; ++l) {
+      const OrbLevel& L = e->lv[l];
+      const int tx = std::max(0, ceil_div(L.w - 2 * kEdge, FT_X)), ty = std::max(0, ceil_div(L.h - 2 * kEdge, FT_Y));
+      fl.w[l] = L.w; fl.h[l] = L.h; fl.tiles_x[l] = std::max(tx, 1); fl.tile0[l] = tiles; fl.cand_cap[l] = L.cand_cap;
+      fl.off[l] = L.off; fl.cand_off[l] = L.cand_off;
+      tiles += tx * ty;
+    }
+    fl.tile0[GT_ORB_LEVELS] = tiles;
+    if (tiles > 0) {
+      fast_kernel<<<dim3((unsigned)tiles, (unsigned)nslots), 256, 0, st>>>(e->pyr, slab, slot0, fl, e->fast_cand, e->fast_score, e->cand_total, e->fast_count);
+      e->launches++;
+    }
   }
   GT_CUDA(e, cudaGetLastError());
   return GT_OK;

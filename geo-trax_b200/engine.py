@@ -182,7 +182,7 @@ class Engine:
         b = None if n == 0 else np.ascontiguousarray(boxes, np.float32)
         self._ck(self.lib.gt_set_reference(self.h, slot, _ptr(b), n, None))
 
-    def stabilize(self, B: int, boxes: Optional[Sequence[Optional[np.ndarray]]] = None):
+    def stabilize(self, B: int, boxes: Optional[Sequence[Optional[np.ndarray]]] = None, stream=None):
         md = self.max_det
         bx = np.zeros((B, md, 4), np.float32)
         nb = np.zeros((B,), np.int32)
@@ -194,7 +194,7 @@ class Engine:
         H = np.zeros((B, 9), np.float64)
         status = np.zeros((B,), np.int32)
         stats = np.zeros((B, 4), np.int32)
-        self._ck(self.lib.gt_stabilize(self.h, B, bx.ctypes.data, nb.ctypes.data, md, H.ctypes.data, status.ctypes.data, stats.ctypes.data, None))
+        self._ck(self.lib.gt_stabilize(self.h, B, bx.ctypes.data, nb.ctypes.data, md, H.ctypes.data, status.ctypes.data, stats.ctypes.data, stream))
         return H.reshape(B, 3, 3), status, stats
 
     def warp_boxes(self, H: np.ndarray, boxes_xywh: np.ndarray) -> np.ndarray:
