@@ -447,6 +447,15 @@ int gt_conv2d(gt_handle e, const uint16_t* x, int B, int H, int W, int cin, cons
 }
 
 // ---- stage 3 ------------------------------------------------------------------------------------------------------------
+// src / n live in mapped pinned host memory (cudaMallocHost, UVA: the host pointer is valid on the device)
+__global__ void boxes_from_host_kernel(const float* __restrict__ src, const int* __restrict__ n, float* __restrict__ dst, int* __restrict__ ndst, int md) {
+  const int b = blockIdx.x, cnt = n[b];
+  const float4* s4 = reinterpret_cast<const float4*>(src) + (size_t)b * md;
+  float4* d4 = reinterpret_cast<float4*>(dst) + (size_t)b * md;
+  for (int i = threadIdx.x; i < cnt; i += blockDim.x) d4[i] = s4[i];
+  if (threadIdx.x == 0) ndst[b] = cnt;
+}
+
 static int upload_boxes(gt_engine* e, int slot0, int B, const float* boxes, const int32_t* nboxes, int box_stride, cudaStream_t st) {
   const int md = e->cfg.max_det;
   if (!boxes || !nboxes) {
@@ -454,6 +463,33 @@ static int upload_boxes(gt_engine* e, int slot0, int B, const float* boxes, cons
     return GT_OK;
   }
   GT_CHECK(e, box_stride >= 0 && box_stride <= md, "boxes: stride %d exceeds max_det %d", box_stride, md);
+  // Host boxes never go through the H2D copy engine: it is busy with the next batch's 400 MB of frames (gt_prefetch_frames), and
+  // a 256 KB upload queued behind that copy delayed the whole step by milliseconds.  They are written into a mapped pinned
+  // staging buffer by the CPU (only nboxes[b] rows per frame) and pulled over PCIe by a small kernel (zero-copy reads).
+  cudaPointerAttributes at;
+  const bool on_device = cudaPointerGetAttributes(&at, boxes) == cudaSuccess && (at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged);
+  cudaPointerAttributes an;
+  const bool n_on_device = cudaPointerGetAttributes(&an, nboxes) == cudaSuccess && (an.type == cudaMemoryTypeDevice || an.type == cudaMemoryTypeManaged);
+  cudaGetLastError();
+  if (!on_device && !n_on_device && B <= e->cfg.max_batch + 1) {
+    if (!e->box_stage[0]) {
+      for (int k = 0; k < 2; ++k) {
+        GT_TRY(e->host_alloc((void**)&e->box_stage[k], (size_t)(e->cfg.max_batch + 1) * md * 16));
+        GT_TRY(e->host_alloc((void**)&e->nbox_stage[k], (size_t)(e->cfg.max_batch + 1) * sizeof(int)));
+      }
+    }
+    const int k = e->box_stage_next;
+    e->box_stage_next ^= 1;
+    for (int b = 0; b < B; ++b) {
+      const int n = std::min(std::max((int)nboxes[b], 0), box_stride);
+      memcpy(e->box_stage[k] + (size_t)b * md * 4, boxes + (size_t)b * box_stride * 4, (size_t)n * 16);
+      e->nbox_stage[k][b] = n;
+    }
+    boxes_from_host_kernel<<<B, 128, 0, st>>>(e->box_stage[k], e->nbox_stage[k], e->boxes_dev + (size_t)slot0 * md * 4, e->nboxes_dev + slot0, md);
+    e->launches++;
+    GT_CUDA(e, cudaGetLastError());
+    return GT_OK;
+  }
   GT_CUDA(e, cudaMemcpy2DAsync(e->boxes_dev + (size_t)slot0 * md * 4, (size_t)md * 16, boxes, (size_t)box_stride * 16, (size_t)box_stride * 16, B,
                                cudaMemcpyDefault, st));
   GT_CUDA(e, cudaMemcpyAsync(e->nboxes_dev + slot0, nboxes, sizeof(int) * B, cudaMemcpyDefault, st));

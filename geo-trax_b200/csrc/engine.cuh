@@ -119,6 +119,9 @@ struct gt_engine {
   int* nboxes_dev = nullptr;                        // [B+1]
   float* det_xywh_dev = nullptr;                    // [B][max_det][4] detections as xywh (warp input)
   int* det_nbox_dev = nullptr;                      // [B]
+  float* box_stage[2] = {nullptr, nullptr};         // mapped pinned staging for host-side mask boxes (see upload_boxes)
+  int* nbox_stage[2] = {nullptr, nullptr};
+  int box_stage_next = 0;
   bool have_ref = false;
   OrbLevel* lv_dev = nullptr;                       // device copy of lv[]
   int* rs_tab[GT_ORB_LEVELS][4] = {};               // per-level resize tables: xofs, xc1, yofs, yc1

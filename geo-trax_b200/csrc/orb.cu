@@ -176,16 +176,32 @@ __global__ void __launch_bounds__(256) fast_kernel(const uint8_t* __restrict__ i
   const int x0 = kEdge + bx * FT_X, y0 = kEdge + by * FT_Y;
   if (threadIdx.x == 0) { s_n = 0; s_nl = 0; s_na = 0; }
   // phase 0: staged word (ty, tq) = image bytes gx = x0 - 5 + 4 tq .. + 3 of row gy = y0 - 4 + ty (rows clamped into the image;
-  // columns outside it only feed positions that are never tested)
+  // columns outside it only feed positions that are never tested).  All loads of a thread are issued before the first use.
   {
-    const uintptr_t lo = reinterpret_cast<uintptr_t>(im) & ~(uintptr_t)3, hi = (reinterpret_cast<uintptr_t>(im) + (size_t)w * h - 1) & ~(uintptr_t)3;
-    for (int i = threadIdx.x; i < FT_SH * (FT_SW / 4); i += 256) {
-      const int ty = i / (FT_SW / 4), tq = i - ty * (FT_SW / 4);
-      const int gy = min(max(y0 - 4 + ty, 0), h - 1);
-      const uintptr_t a = reinterpret_cast<uintptr_t>(im) + (size_t)gy * w + (x0 - 5 + 4 * tq);
-      const uintptr_t p0 = min(max(a & ~(uintptr_t)3, lo), hi), p1 = min(p0 + 4, hi);
-      const uint32_t v0 = __ldg(reinterpret_cast<const uint32_t*>(p0)), v1 = __ldg(reinterpret_cast<const uint32_t*>(p1));
-      *reinterpret_cast<uint32_t*>(&s_img[ty][tq * 4]) = __funnelshift_r(v0, v1, 8 * (int)(a & 3));
+    const int mis = (int)(reinterpret_cast<uintptr_t>(im) & 3);
+    const uint32_t* base = reinterpret_cast<const uint32_t*>(im - mis);   // 4-byte aligned; word indices clamped to the level's words
+    const int last_word = (mis + w * h - 1) >> 2;
+    constexpr int kWords = FT_SH * (FT_SW / 4), kIter = (kWords + 255) / 256;
+    uint32_t v0[kIter], v1[kIter];
+    int sh[kIter];
+#pragma unroll
+    for (int it = 0; it < kIter; ++it) {
+      const int i = threadIdx.x + it * 256;
+      v0[it] = v1[it] = 0; sh[it] = 0;
+      if (i < kWords) {
+        const int ty = i / (FT_SW / 4), tq = i - ty * (FT_SW / 4);
+        const int gy = min(max(y0 - 4 + ty, 0), h - 1);
+        const int boff = mis + gy * w + (x0 - 5 + 4 * tq);
+        const int wi = boff >> 2;
+        v0[it] = __ldg(base + min(wi, last_word));
+        v1[it] = __ldg(base + min(wi + 1, last_word));
+        sh[it] = (boff & 3) * 8;
+      }
+    }
+#pragma unroll
+    for (int it = 0; it < kIter; ++it) {
+      const int i = threadIdx.x + it * 256;
+      if (i < kWords) reinterpret_cast<uint32_t*>(&s_img[0][0])[i] = __funnelshift_r(v0[it], v1[it], sh[it]);
     }
   }
   for (int i = threadIdx.x; i < (FT_Y + 2) * (FT_X + 2) / 2; i += 256) reinterpret_cast<unsigned short*>(&s_sc[0][0])[i] = 0;
@@ -208,11 +224,10 @@ __global__ void __launch_bounds__(256) fast_kernel(const uint8_t* __restrict__ i
         const uint32_t br = two_of_four(__vcmpgtu4(r0, hi4), __vcmpgtu4(r4, hi4), __vcmpgtu4(r8, hi4), __vcmpgtu4(r12, hi4));
         const uint32_t dk = two_of_four(__vcmpltu4(r0, lo4), __vcmpltu4(r4, lo4), __vcmpltu4(r8, lo4), __vcmpltu4(r12, lo4));
         uint32_t m = br | dk;
-        // validity of the four pixels (sx = 4 g + j)
+        // validity of the four pixels (sx = 4 g + j): j in [jlo, jhi]
         const int gx = x0 - 1 + 4 * g;
-#pragma unroll
-        for (int j = 0; j < 4; ++j)
-          if (gx + j < kEdge - 1 || gx + j > w - kEdge || 4 * g + j >= FT_X + 2) m &= ~(0xFFu << (8 * j));
+        const int jlo = max(kEdge - 1 - gx, 0), jhi = min(min(w - kEdge - gx, FT_X + 1 - 4 * g), 3);
+        if (jlo > 0 || jhi < 3) m = jhi < jlo ? 0u : (m & (0xFFFFFFFFu << (8 * jlo)) & (0xFFFFFFFFu >> (8 * (3 - jhi))));
         pass = m;
       }
     }
