@@ -73,6 +73,7 @@ int gt_create(const gt_config* cfg, int device, gt_handle* out) {
   e->cfg = *cfg;
   e->device = device;
   if (const char* hm = getenv("GT_HALO")) e->halo_mode = atoi(hm);
+  if (const char* pd = getenv("GT_PDL")) e->pdl = atoi(pd);
   if (const char* sm = getenv("GT_SWAP")) e->swap_mode = atoi(sm);
   if (const char* ov = getenv("GT_OVERLAP")) e->overlap = atoi(ov);
   if (const char* kb = getenv("GT_CONV_SMEM_KB")) e->conv_smem_kb = std::min(227, std::max(96, atoi(kb)));

@@ -143,6 +143,7 @@ __device__ __forceinline__ void mma_role_halo(const ConvParams& p, const MmaCtx&
 __global__ void __launch_bounds__(kSwThreads, 1) conv_sw_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmX,
                                                                 const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ ConvUpMaps tmUp,
                                                                 const __grid_constant__ CUtensorMap tmRes, const ConvParams p) {
+  pdl_launch_dependents();   // the next layer's CTAs may start their prologue as SMs free up
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const int row_bytes = p.kb_elems * 2;
@@ -213,6 +214,7 @@ __global__ void __launch_bounds__(kSwThreads, 1) conv_sw_kernel(const __grid_con
       }
       __syncwarp();
     }
+    pdl_wait();   // everything above touched only this layer's constants; activations of the previous layer are read below
     const uint32_t tx_bytes = (uint32_t)stage_bytes;
     uint32_t s = 0, ph = 0, ws = 0, wph = 0;
     TileIter ti;
@@ -298,6 +300,7 @@ __global__ void __launch_bounds__(kSwThreads, 1) conv_sw_kernel(const __grid_con
     const int half_rows = p.th >> 1;    // image rows per pixel half
     const int tw_shift = __ffs(p.tw) - 1, tw_mask = p.tw - 1;
     const uint32_t stg = smem_u32(staging);
+    pdl_wait();   // residual reads and output stores below
     uint32_t li = 0, nstore = 0, res_uses = 0;
     TileIter ti;
     ti.init(p, blockIdx.x, gridDim.x);
@@ -747,7 +750,13 @@ int conv_sw_launch_range(gt_engine* e, const ConvOp* op, int b0, int nb, cudaStr
   p.img0 = b0;
   p.total_tiles = p.tiles_x * p.tiles_y * nb * p.n_tiles;
   const int grid = p.total_tiles < conv_tc_num_sms() ? p.total_tiles : conv_tc_num_sms();
-  conv_sw_kernel<<<grid, kSwThreads, op->smem, st>>>(op->tmB, op->tmA, op->tmOut, op->tmUp, op->tmRes, p);   // (weights, activations, ...)
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(kSwThreads); cfg.dynamicSmemBytes = op->smem; cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at; cfg.numAttrs = e->pdl ? 1 : 0;
+  GT_CUDA(e, cudaLaunchKernelEx(&cfg, conv_sw_kernel, op->tmB, op->tmA, op->tmOut, op->tmUp, op->tmRes, p));   // (weights, activations, ...)
   e->launches++;
   GT_CUDA(e, cudaGetLastError());
   return GT_OK;

@@ -138,6 +138,7 @@ template <int OCC>
 __global__ void __launch_bounds__(kThreads, OCC) conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                                                               const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ ConvUpMaps tmUp,
                                                               const ConvParams p) {
+  pdl_launch_dependents();   // the next layer's CTAs may start their prologue (barriers, TMEM, resident weights) as SMs free up
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // carve (all 1024-aligned): operand ring | resident weights (optional) | 2 output staging slabs | barriers / tmem pointer / bias
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -208,6 +209,7 @@ __global__ void __launch_bounds__(kThreads, OCC) conv_tc_kernel(const __grid_con
       }
       __syncwarp();
     }
+    pdl_wait();   // everything above touched only this layer's constants; activations of the previous layer are read below
     const uint32_t tx_bytes = (uint32_t)stage_bytes;
     uint32_t s = 0, ph = 0;
     TileIter ti;
@@ -338,6 +340,7 @@ __global__ void __launch_bounds__(kThreads, OCC) conv_tc_kernel(const __grid_con
     const int row = q * 32 + lane;
     const int ly = row / p.tw, lx = row - ly * p.tw;
     const bool leader_warp = warp == 2;
+    pdl_wait();   // residual reads and output stores below
     uint32_t li = 0, slab_ctr = 0;
     const uint32_t out_stage_a = smem_u32(out_stage), s_bias_a = smem_u32(s_bias);
     TileIter ti;
@@ -662,8 +665,14 @@ int conv_tc_launch_range(gt_engine* e, const ConvOp* op, int b0, int nb, cudaStr
   p.total_tiles = p.tiles_x * p.tiles_y * nb * p.n_tiles;
   const int slots = g_num_sms * (op->occ2 ? 2 : 1);
   const int grid = p.total_tiles < slots ? p.total_tiles : slots;
-  if (op->occ2) conv_tc_kernel<2><<<grid, kThreads, op->smem, st>>>(op->tmA, op->tmB, op->tmOut, op->tmUp, p);
-  else conv_tc_kernel<1><<<grid, kThreads, op->smem, st>>>(op->tmA, op->tmB, op->tmOut, op->tmUp, p);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(kThreads); cfg.dynamicSmemBytes = op->smem; cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at; cfg.numAttrs = e->pdl ? 1 : 0;
+  if (op->occ2) GT_CUDA(e, cudaLaunchKernelEx(&cfg, conv_tc_kernel<2>, op->tmA, op->tmB, op->tmOut, op->tmUp, p));
+  else GT_CUDA(e, cudaLaunchKernelEx(&cfg, conv_tc_kernel<1>, op->tmA, op->tmB, op->tmOut, op->tmUp, p));
   e->launches++;
   GT_CUDA(e, cudaGetLastError());
   return GT_OK;

@@ -5,6 +5,11 @@
 
 constexpr int kEpiWarps = 8;
 
+// Programmatic dependent launch: consecutive conv layers are launched with programmaticStreamSerialization, so a layer's CTAs can
+// run their prologue while the previous layer drains; pdl_wait() blocks until the previous grid has completed and flushed.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
