@@ -99,14 +99,17 @@ int gt_create(const gt_config* cfg, int device, gt_handle* out) {
   const int pad_bot = round_half_even(dh + 0.1), pad_right = round_half_even(dw + 0.1);
   e->net_h = e->new_h + e->pad_top + pad_bot;
   e->net_w = e->new_w + e->pad_left + pad_right;
-  if (r != 0.5 || (c.frame_w % 16) || (c.frame_h % 4) || (e->net_h % 32) || (e->net_w % 32) || (e->pad_left % 8) || (e->pad_top % 2)) {
-    gt_set_error(e, "gt_create: only the exact 1/2 letterbox (imgsz = max(frame)/2, width %% 16 == 0) is implemented; got %dx%d imgsz %d",
-                 c.frame_w, c.frame_h, c.imgsz);
+  if ((e->net_h % 32) || (e->net_w % 32) || e->new_w < 32 || e->new_h < 32) {
+    gt_set_error(e, "gt_create: letterbox geometry %dx%d -> %dx%d (imgsz %d) is not a multiple of the stride", c.frame_w, c.frame_h, e->net_w, e->net_h, c.imgsz);
     return fail(GT_ERR_INVALID);
   }
-  if (c.downsample_ratio != 0.5f) { gt_set_error(e, "gt_create: only downsample_ratio 0.5 is implemented"); return fail(GT_ERR_INVALID); }
+  if (!(c.downsample_ratio > 0.f && c.downsample_ratio <= 1.0f)) { gt_set_error(e, "gt_create: downsample_ratio must be in (0, 1]"); return fail(GT_ERR_INVALID); }
   e->work_w = (int)(c.frame_w * c.downsample_ratio);
   e->work_h = (int)(c.frame_h * c.downsample_ratio);
+  if (e->work_w < 128 || e->work_h < 128) { gt_set_error(e, "gt_create: working image %dx%d too small for the 8-level ORB pyramid", e->work_w, e->work_h); return fail(GT_ERR_INVALID); }
+  // the fused vector kernel covers the default preset's geometry (exact 1/2 letterbox, 1/2 working image, 16-pixel-aligned rows)
+  e->pre_fast = r == 0.5 && c.downsample_ratio == 0.5f && (c.frame_w % 16) == 0 && (c.frame_h % 4) == 0 && (e->pad_left % 8) == 0 && (e->pad_top % 2) == 0 &&
+                e->work_w * 2 == c.frame_w && e->work_h * 2 == c.frame_h;
   const int B = c.max_batch;
   CR(e->dev_alloc((void**)&e->frames_dev, (size_t)B * c.frame_h * c.frame_w * 3));
   CR(e->dev_alloc((void**)&e->frames_dev2, (size_t)B * c.frame_h * c.frame_w * 3));
@@ -127,6 +130,7 @@ int gt_create(const gt_config* cfg, int device, gt_handle* out) {
   CR(detector_build(e));
   CR(stab_build(e));
   // constant letterbox border
+  if (!e->pre_fast) CR(detector_build_general_preprocess(e));
   CR(detector_fill_pad(e, e->stream));
   CRC(cudaStreamSynchronize(e->stream));
 #undef CR

@@ -5,6 +5,7 @@
 // Detect/OBB head + DFL + dist2bbox/dist2rbox, non_max_suppression (torchvision.ops.nms / nms_rotated), scale_boxes.
 #include <algorithm>
 #include <map>
+#include <vector>
 #include <type_traits>
 
 #include "engine.cuh"
@@ -80,6 +81,107 @@ __global__ void __launch_bounds__(256) preprocess_half_kernel(const uint8_t* __r
   }
 }
 
+// ---- general geometry (any frame size / imgsz / downsample_ratio): table-driven restatement of cv2.resize(INTER_LINEAR) ------
+// Tables per axis (host-built, resize_tables below): source index pair (i0, i1) and 11-bit coefficients (c0, c1) of every destination
+// coordinate, exactly as OpenCV's resize() computes them (oracle/prepost.py:resize_linear_u8 is the pinned restatement).
+// mode 0: identity copy, 1: exact 2x2 decimation (OpenCV reroutes it to INTER_AREA), 2: bilinear.
+struct ResizeTabs { const int *x0, *x1, *a0, *a1, *y0, *y1, *b0, *b1; int mode; };
+
+__device__ __forceinline__ uint32_t lin_u8(uint32_t p00, uint32_t p01, uint32_t p10, uint32_t p11, int a0, int a1, int b0, int b1) {
+  const int S0 = a0 * (int)p00 + a1 * (int)p01, S1 = a0 * (int)p10 + a1 * (int)p11;
+  return (uint32_t)((((b0 * (S0 >> 4)) >> 16) + ((b1 * (S1 >> 4)) >> 16) + 2) >> 2);
+}
+
+__global__ void __launch_bounds__(256) letterbox_general_kernel(const uint8_t* __restrict__ frames, bf16* __restrict__ s2d, int B, int H, int W,
+                                                                int net_h, int net_w, int pad_top, int pad_left, int new_h, int new_w,
+                                                                ResizeTabs t, int fp16) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long per_frame = (long long)new_h * new_w;
+  if (idx >= per_frame * B) return;
+  const int b = (int)(idx / per_frame);
+  const int rem = (int)(idx - (long long)b * per_frame);
+  const int oy = rem / new_w, ox = rem - oy * new_w;
+  const uint8_t* f = frames + (size_t)b * H * W * 3;
+  uint32_t v[3];
+  if (t.mode == 0) {
+    const uint8_t* p = f + ((size_t)oy * W + ox) * 3;
+    v[0] = p[0]; v[1] = p[1]; v[2] = p[2];
+  } else if (t.mode == 1) {
+    const uint8_t* p = f + ((size_t)(2 * oy) * W + 2 * ox) * 3;
+    const uint8_t* q = p + (size_t)W * 3;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) v[c] = ((uint32_t)p[c] + p[c + 3] + q[c] + q[c + 3] + 2) >> 2;
+  } else {
+    const int x0 = t.x0[ox], x1 = t.x1[ox], a0 = t.a0[ox], a1 = t.a1[ox];
+    const int y0 = t.y0[oy], y1 = t.y1[oy], b0 = t.b0[oy], b1 = t.b1[oy];
+    const uint8_t* r0 = f + (size_t)y0 * W * 3;
+    const uint8_t* r1 = f + (size_t)y1 * W * 3;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) v[c] = lin_u8(r0[x0 * 3 + c], r0[x1 * 3 + c], r1[x0 * 3 + c], r1[x1 * 3 + c], a0, a1, b0, b1);
+  }
+  // 4x4 space-to-depth destination: block (Y, X), row rb, column cb -> halves R, G, B, 0
+  const int ly = oy + pad_top, lx = ox + pad_left;
+  const int sh = net_h >> 2, sw = net_w >> 2;
+  uint32_t* dst = reinterpret_cast<uint32_t*>(s2d + (((size_t)b * sh + (ly >> 2)) * sw + (lx >> 2)) * 64 + (ly & 3) * 16 + (lx & 3) * 4);
+  dst[0] = pack2_act((float)v[2], (float)v[1], fp16);
+  dst[1] = pack2_act((float)v[0], 0.f, fp16);
+}
+
+// stabilizer working image: gray (cvtColor BGR2GRAY) first, then the resize to (work_w, work_h) -- stabilo's order
+__global__ void __launch_bounds__(256) gray_work_kernel(const uint8_t* __restrict__ frames, uint8_t* __restrict__ gray, size_t gray_frame_stride,
+                                                        int B, int H, int W, int work_h, int work_w, ResizeTabs t) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long per_frame = (long long)work_h * work_w;
+  if (idx >= per_frame * B) return;
+  const int b = (int)(idx / per_frame);
+  const int rem = (int)(idx - (long long)b * per_frame);
+  const int oy = rem / work_w, ox = rem - oy * work_w;
+  const uint8_t* f = frames + (size_t)b * H * W * 3;
+  auto g = [&](int y, int x) { const uint8_t* p = f + ((size_t)y * W + x) * 3; return gray15(p[0], p[1], p[2]); };
+  uint32_t v;
+  if (t.mode == 0) v = g(oy, ox);
+  else if (t.mode == 1) v = (g(2 * oy, 2 * ox) + g(2 * oy, 2 * ox + 1) + g(2 * oy + 1, 2 * ox) + g(2 * oy + 1, 2 * ox + 1) + 2) >> 2;
+  else {
+    const int x0 = t.x0[ox], x1 = t.x1[ox], y0 = t.y0[oy], y1 = t.y1[oy];
+    v = lin_u8(g(y0, x0), g(y0, x1), g(y1, x0), g(y1, x1), t.a0[ox], t.a1[ox], t.b0[oy], t.b1[oy]);
+  }
+  gray[(size_t)b * gray_frame_stride + (size_t)oy * work_w + ox] = (uint8_t)v;
+}
+
+// OpenCV resize() coordinate / coefficient computation for one axis (imgproc/src/resize.cpp, INTER_LINEAR branch)
+static void resize_axis(int n_src, int n_dst, bool vertical, std::vector<int>& i0, std::vector<int>& i1, std::vector<int>& c0, std::vector<int>& c1) {
+  i0.resize(n_dst); i1.resize(n_dst); c0.resize(n_dst); c1.resize(n_dst);
+  const double scale = 1.0 / ((double)n_dst / (double)n_src);
+  for (int d = 0; d < n_dst; ++d) {
+    float f = (float)((d + 0.5) * scale - 0.5);
+    int s = (int)floorf(f);
+    f -= (float)s;
+    if (!vertical && (s < 0 || s >= n_src - 1)) f = 0.f;    // horizontal: fraction zeroed where the index is clamped; vertical keeps it
+    i0[d] = std::min(std::max(s, 0), n_src - 1);
+    i1[d] = std::min(std::max(s + 1, 0), n_src - 1);
+    c0[d] = (int)nearbyintf((1.f - f) * 2048.f);
+    c1[d] = (int)nearbyintf(f * 2048.f);
+  }
+}
+
+static int upload_tabs(gt_engine* e, int src_w, int src_h, int dst_w, int dst_h, int* dev[8], int* mode) {
+  *mode = (src_w == dst_w && src_h == dst_h) ? 0 : ((src_w == 2 * dst_w && src_h == 2 * dst_h) ? 1 : 2);
+  std::vector<int> v[8];
+  resize_axis(src_w, dst_w, false, v[0], v[1], v[2], v[3]);
+  resize_axis(src_h, dst_h, true, v[4], v[5], v[6], v[7]);
+  for (int i = 0; i < 8; ++i) {
+    GT_TRY(e->dev_alloc((void**)&dev[i], v[i].size() * sizeof(int)));
+    GT_CUDA(e, cudaMemcpy(dev[i], v[i].data(), v[i].size() * sizeof(int), cudaMemcpyHostToDevice));
+  }
+  return GT_OK;
+}
+
+int detector_build_general_preprocess(gt_engine* e) {
+  GT_TRY(upload_tabs(e, e->cfg.frame_w, e->cfg.frame_h, e->new_w, e->new_h, e->lb_tab, &e->lb_mode));
+  GT_TRY(upload_tabs(e, e->cfg.frame_w, e->cfg.frame_h, e->work_w, e->work_h, e->gw_tab, &e->gw_mode));
+  return GT_OK;
+}
+
 __global__ void fill_s2d_kernel(uint2* __restrict__ s2d, size_t n_quads, uint32_t w0, uint32_t w1) {
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n_quads) s2d[i] = make_uint2(w0, w1);
@@ -96,8 +198,21 @@ int detector_fill_pad(gt_engine* e, cudaStream_t st) {  // constant letterbox bo
 }
 
 int detector_preprocess(gt_engine* e, const uint8_t* frames_dev, int B, cudaStream_t st) {
-  const long long threads = (long long)B * (e->new_h / 2) * (e->new_w / 8);
   uint8_t* gray = e->pyr;  // level 0 of each frame's pyramid slab
+  if (!e->pre_fast) {      // any other geometry: two table-driven kernels (letterbox, gray working image)
+    const int fp16 = e->cfg.act_dtype == GT_ACT_FP16;
+    const ResizeTabs lt = {e->lb_tab[0], e->lb_tab[1], e->lb_tab[2], e->lb_tab[3], e->lb_tab[4], e->lb_tab[5], e->lb_tab[6], e->lb_tab[7], e->lb_mode};
+    const ResizeTabs gt = {e->gw_tab[0], e->gw_tab[1], e->gw_tab[2], e->gw_tab[3], e->gw_tab[4], e->gw_tab[5], e->gw_tab[6], e->gw_tab[7], e->gw_mode};
+    const long long n1 = (long long)B * e->new_h * e->new_w, n2 = (long long)B * e->work_h * e->work_w;
+    letterbox_general_kernel<<<(unsigned)((n1 + 255) / 256), 256, 0, st>>>(frames_dev, e->net_s2d, B, e->cfg.frame_h, e->cfg.frame_w, e->net_h, e->net_w,
+                                                                           e->pad_top, e->pad_left, e->new_h, e->new_w, lt, fp16);
+    gray_work_kernel<<<(unsigned)((n2 + 255) / 256), 256, 0, st>>>(frames_dev, gray, e->pyr_bytes, B, e->cfg.frame_h, e->cfg.frame_w, e->work_h, e->work_w, gt);
+    e->launches += 2;
+    GT_CUDA(e, cudaGetLastError());
+    e->cur_frames = frames_dev;
+    return GT_OK;
+  }
+  const long long threads = (long long)B * (e->new_h / 2) * (e->new_w / 8);
   preprocess_half_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(frames_dev, e->net_s2d, gray, e->pyr_bytes, B, e->cfg.frame_h,
                                                                             e->cfg.frame_w, e->net_h, e->net_w, e->pad_top, e->pad_left,
                                                                             e->new_h, e->new_w, e->cfg.act_dtype == GT_ACT_FP16);

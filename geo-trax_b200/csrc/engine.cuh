@@ -66,6 +66,10 @@ struct gt_engine {
   int prefetch_next = 0;
   const uint8_t* deferred_src = nullptr;   // gt_prefetch_frames_deferred: started by the next gt_extract_batch
   int deferred_B = 0;
+  bool pre_fast = true;                 // exact-1/2 letterbox + 1/2 working image with 16-pixel-aligned rows: the fused vector kernel; else the table-driven general kernels
+  int* lb_tab[8] = {};                  // letterbox resize tables (x0, x1, a0, a1, y0, y1, b0, b1), see detector.cu
+  int* gw_tab[8] = {};                  // gray working-image resize tables
+  int lb_mode = 0, gw_mode = 0;         // 0 identity, 1 exact 2x2 decimation, 2 bilinear
   bf16* net_s2d = nullptr;              // [B][net_h/4][net_w/4][64] 4x4 space-to-depth letterboxed RGB0 (exact u8 values, 16-bit)
   const uint8_t* cur_frames = nullptr;  // device pointer of the frames of the last gt_preprocess
 
@@ -154,6 +158,7 @@ int detector_build(gt_engine* e);
 int detector_load_weights(gt_engine* e, const float* const* w, const float* const* b, int n);
 int detector_autotune(gt_engine* e, cudaStream_t st);
 int detector_fill_pad(gt_engine* e, cudaStream_t st);
+int detector_build_general_preprocess(gt_engine* e);
 int detector_preprocess(gt_engine* e, const uint8_t* frames_dev, int B, cudaStream_t st);
 int detector_forward(gt_engine* e, int B, cudaStream_t st);
 int detector_postprocess(gt_engine* e, int B, float conf, float iou, int agnostic, uint32_t classes_mask, cudaStream_t st);

@@ -40,10 +40,10 @@ class Stabilizer:
         if filter_type != "ratio": unsupported.append(f"filter_type={filter_type!r} (ratio)")
         if transformation_type != "projective": unsupported.append(f"transformation_type={transformation_type!r} (projective)")
         if clahe: unsupported.append("clahe=True")
-        if float(downsample_ratio) != 0.5: unsupported.append(f"downsample_ratio={downsample_ratio} (0.5)")
+        if not (0.0 < float(downsample_ratio) <= 1.0): unsupported.append(f"downsample_ratio={downsample_ratio} (0 < r <= 1)")
         if match_query_frame not in ("current", "reference"): unsupported.append(f"match_query_frame={match_query_frame!r}")
         if unsupported:
-            raise NotImplementedError("B200 stabilizer implements the default preset only; unsupported: " + ", ".join(unsupported))
+            raise NotImplementedError("B200 stabilizer implements the ORB / BF / ratio / projective pipeline; unsupported: " + ", ".join(unsupported))
         self.cfg = dict(downsample_ratio=float(downsample_ratio), max_features=int(max_features), ref_multiplier=float(ref_multiplier),
                         mask_use=bool(mask_use), mask_margin_ratio=float(mask_margin_ratio), filter_ratio=float(filter_ratio),
                         ransac_epipolar_threshold=float(ransac_epipolar_threshold), ransac_max_iter=int(ransac_max_iter),

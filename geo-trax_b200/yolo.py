@@ -78,6 +78,7 @@ class YOLO:
     def _get_engine(self, frame_hw, imgsz, device, max_det, nb):
         if isinstance(imgsz, (list, tuple)):
             imgsz = max(imgsz)
+        imgsz = max(32, -(-int(imgsz) // 32) * 32)      # ultralytics check_imgsz: rounded up to a multiple of the stride
         eng = session.acquire(tuple(frame_hw), int(imgsz), self.nc, self.task, session.device_index(device), max(self.max_batch, nb), None,
                               act_dtype=self.act_dtype, max_det=int(max_det))
         if self._engine is not eng or not getattr(eng, "_weights_owner", None) is self:

@@ -41,6 +41,48 @@ def letterbox_u8(frame_bgr: np.ndarray, imgsz: int = 1920, stride: int = 32) -> 
     return cv2.copyMakeBorder(img, top, bottom, left, right, cv2.BORDER_CONSTANT, value=(114, 114, 114))
 
 
+def resize_linear_u8(img: np.ndarray, new_w: int, new_h: int) -> np.ndarray:
+    """Integer restatement of ``cv2.resize(u8, (new_w, new_h), interpolation=cv2.INTER_LINEAR)`` (OpenCV imgproc/src/resize.cpp:
+    ``resize`` -> ``HResizeLinear`` / ``VResizeLinear<uchar,int,short>``): 11-bit coefficients ``cvRound(f * 2048)`` from the
+    *float* fractions of ``(d + 0.5) * scale - 0.5`` with ``scale = 1 / (dst / src)`` in double, source indices clamped at the borders,
+    horizontal pass in int32, vertical pass ``(((b0 * (S0 >> 4)) >> 16) + ((b1 * (S1 >> 4)) >> 16) + 2) >> 2``; an exact 2x2 decimation
+    is rerouted to INTER_AREA = ``(a + b + c + d + 2) >> 2``.  Pinned against cv2 in
+    tests/test_oracle_model.py::test_resize_linear_restatement_matches_cv2; the CUDA letterbox follows this function."""
+    src = img if img.ndim == 3 else img[..., None]
+    h, w, cn = src.shape
+    if (w, h) == (new_w, new_h):
+        return img.copy()
+    if w == 2 * new_w and h == 2 * new_h:
+        s = src.astype(np.int32)
+        out = (s[0::2, 0::2] + s[0::2, 1::2] + s[1::2, 0::2] + s[1::2, 1::2] + 2) >> 2
+        return out.astype(np.uint8).reshape((new_h, new_w) + ((cn,) if img.ndim == 3 else ()))
+
+    def axis(n_src, n_dst):
+        scale = 1.0 / (float(n_dst) / float(n_src))
+        f = ((np.arange(n_dst, dtype=np.float64) + 0.5) * scale - 0.5).astype(np.float32)
+        i = np.floor(f).astype(np.int64)
+        f = (f - i.astype(np.float32)).astype(np.float32)
+        return i, f
+
+    sx, fx = axis(w, new_w)
+    lo, hi = sx < 0, sx >= w - 1           # horizontal: the fraction is zeroed where the index is clamped
+    fx = np.where(lo | hi, np.float32(0), fx)
+    sx = np.clip(sx, 0, w - 1)
+    sx1 = np.minimum(sx + 1, w - 1)
+    a0 = np.rint((np.float32(1) - fx) * np.float32(2048)).astype(np.int32)
+    a1 = np.rint(fx * np.float32(2048)).astype(np.int32)
+    sy, fy = axis(h, new_h)               # vertical: rows are clamped, the fraction is kept
+    b0 = np.rint((np.float32(1) - fy) * np.float32(2048)).astype(np.int32)
+    b1 = np.rint(fy * np.float32(2048)).astype(np.int32)
+    r0, r1 = np.clip(sy, 0, h - 1), np.clip(sy + 1, 0, h - 1)
+    s = src.astype(np.int32)
+    hrow = s[:, sx, :] * a0[None, :, None] + s[:, sx1, :] * a1[None, :, None]       # (h, new_w, cn) int32
+    S0, S1 = hrow[r0], hrow[r1]
+    out = (((b0[:, None, None] * (S0 >> 4)) >> 16) + ((b1[:, None, None] * (S1 >> 4)) >> 16) + 2) >> 2
+    out = np.clip(out, 0, 255).astype(np.uint8)
+    return out if img.ndim == 3 else out[..., 0]
+
+
 def preprocess(frames_bgr: Sequence[np.ndarray], imgsz: int = 1920) -> torch.Tensor:
     """list of u8 HWC BGR -> f32 NCHW RGB in [0,1]."""
     im = np.stack([letterbox_u8(f, imgsz) for f in frames_bgr])

@@ -38,6 +38,35 @@ def test_preprocess_bit_exact(small_engine):
         assert np.array_equal(gray[i], g), "gray half-res differs from cv2 (bit-exact expected)"
 
 
+@pytest.mark.parametrize("hw,imgsz,ratio", [((380, 676), 480, 0.5),      # 0.71x letterbox (2704x1520-like), even frame
+                                            ((270, 480), 480, 1.0),      # identity letterbox, full-resolution working image
+                                            ((375, 667), 384, 0.5),      # odd frame: bilinear working image too
+                                            ((512, 360), 256, 0.5)])     # portrait: exact 1/2 but rows not 16-pixel aligned (2x2 decimation path)
+def test_preprocess_general_geometry_bit_exact(hw, imgsz, ratio):
+    """Any frame size / imgsz / downsample_ratio: letterbox and gray working image bit-exact against cv2 (table-driven kernels)."""
+    import cv2
+    import geotrax_b200
+    from oracle import prepost
+    eng = geotrax_b200.Engine(frame_hw=hw, imgsz=imgsz, nc=4, max_batch=2, max_det=100, max_features=300, downsample_ratio=ratio)
+    try:
+        rng = np.random.default_rng(1)
+        frames = rng.integers(0, 256, (2,) + hw + (3,), dtype=np.uint8)
+        eng.preprocess(frames)
+        got = eng.net_input(2)
+        ref = prepost.preprocess(list(frames), imgsz).numpy()
+        assert got.shape == ref.shape
+        assert np.array_equal(got.astype(np.float32) / np.float32(255.0), ref), "general letterbox differs from cv2 / ultralytics LetterBox"
+        gray = eng.gray(2)
+        ww, wh = int(hw[1] * ratio), int(hw[0] * ratio)
+        for i in range(2):
+            g = cv2.cvtColor(frames[i], cv2.COLOR_BGR2GRAY)
+            if ratio != 1.0:
+                g = cv2.resize(g, (ww, wh), interpolation=cv2.INTER_LINEAR)
+            assert np.array_equal(gray[i], g), "gray working image differs from cv2"
+    finally:
+        eng.close()
+
+
 CONV_CASES = [
     # (B, H, W, cin, cout, k, stride, act, residual, f32)
     (2, 32, 48, 64, 64, 1, 1, True, False, False),

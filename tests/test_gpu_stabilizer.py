@@ -158,6 +158,33 @@ def test_stabilize_matches_oracle_and_truth(stab_engine, flight):
         assert abs(H[i][2, 2] - 1.0) < 1e-12 and np.linalg.det(H[i]) > 0
 
 
+def test_stabilizer_shim_full_res_no_mask(flight):
+    """The reference's second construction: ``Stabilizer(downsample_ratio=1.0, mask_use=False, max_features=4000)``
+    (/root/reference/tools/compare_av_detections_and_tune_filters.py:739) -- full-resolution working image, no vehicle mask."""
+    import geotrax_b200
+    from geotrax_b200 import session
+    from oracle.stabilo_cv import Stabilizer as OracleStabilizer, warp_boxes_xywh
+    frames, boxes, Hs = flight
+    small = [np.ascontiguousarray(f[:540, :960]) for f in frames]            # 540 x 960 crops share the generator's homographies only
+    stab = geotrax_b200.Stabilizer(downsample_ratio=1.0, mask_use=False, max_features=4000)   # approximately; the oracle is the reference here
+    ora = OracleStabilizer(downsample_ratio=1.0, mask_use=False, max_features=4000)
+    try:
+        stab.set_ref_frame(small[0], None)
+        ora.set_ref_frame(small[0], None)
+        bx = np.array([[200, 150, 60, 30], [700, 400, 80, 40], [480, 270, 50, 50]], np.float32)
+        for i in (1, 2):
+            stab.stabilize(small[i], bx)
+            ora.stabilize(small[i], bx)
+            H, Ho = stab.get_cur_trans_matrix(), ora.get_cur_trans_matrix()
+            assert H is not None and Ho is not None
+            n_ref, n_cur = stab.get_cur_num_keypoints()
+            assert n_cur > 1000 and n_ref >= n_cur
+            got, want = stab.transform_cur_boxes(), ora.transform_cur_boxes()
+            assert np.linalg.norm(got[:, :2] - want[:, :2], axis=1).mean() < 0.5
+    finally:
+        session.close_all()
+
+
 def test_warp_boxes_reproduces_golden_rows(stab_engine):
     """Known-answer test from the reference's golden output (box-warp semantics)."""
     z = np.load(GOLDEN)

@@ -126,3 +126,17 @@ def test_oracle_stabilizer_recovers_known_homography():
     assert np.linalg.norm(got[:, :2] - want[:, :2], axis=1).mean() < 0.5
     nr, ncur = st.get_cur_num_keypoints()
     assert nr > ncur > 500 and st.get_cur_num_matches() >= st.get_cur_inliers_count() > 100
+
+
+@pytest.mark.parametrize("shape", [((1520, 2704), (1079, 1920)), ((1080, 1920), (960, 1706)), ((720, 1280), (1080, 1920)), ((333, 517), (258, 400)),
+                                   ((2160, 3840), (1080, 1920)), ((480, 640), (480, 640))])
+@pytest.mark.parametrize("cn", [1, 3])
+def test_resize_linear_restatement_matches_cv2(shape, cn):
+    """oracle/prepost.py:resize_linear_u8 (the integer formulas the CUDA general letterbox follows) is bit-exact against cv2.resize."""
+    import cv2
+    from oracle import prepost
+    (h, w), (nh, nw) = shape
+    rng = np.random.default_rng(h * 7 + cn)
+    img = rng.integers(0, 256, (h, w, 3) if cn == 3 else (h, w), dtype=np.uint8)
+    ref = cv2.resize(img, (nw, nh), interpolation=cv2.INTER_LINEAR)
+    assert np.array_equal(prepost.resize_linear_u8(img, nw, nh), ref)
