@@ -35,8 +35,6 @@ int g_num_sms = GT_NUM_SMS;
 constexpr int kThreads = 64 + kEpiWarps * 32;  // 320
 constexpr int kMaxStages = 12;
 constexpr int kMaxHaloStages = 8;
-constexpr int kHaloW = 16;   // halo row pitch in pixels: 8-pixel tile rows + (k - 1) halo columns, padded so that every image row
-                             // of the halo starts a fresh swizzle atom (8 rows)
 
 // Epilogue of one accumulator: slabs of 128 rows x SLAB_BYTES (128 or 64) are staged in shared memory in the TMA swizzle
 // layout and written with one bulk tensor store each (plus four for the 2x nearest-upsampled copy).  CW = accumulator
@@ -44,12 +42,30 @@ constexpr int kHaloW = 16;   // halo row pitch in pixels: 8-pixel tile rows + (k
 template <int CW, bool F32>
 __device__ __forceinline__ void epilogue_tile(const ConvParams& p, const TileCoord& t, uint32_t trow, uint32_t stage_base, uint32_t s_bias,
                                               const CUtensorMap* tmOut, const CUtensorMap* tmUp, int half, int row, int y, int x, bool valid,
-                                              uint32_t& slab_ctr, uint32_t tempty_bar, int lane, bool leader_warp) {
+                                              uint32_t& slab_ctr, uint32_t tempty_bar, int lane, bool leader_warp, uint32_t tfull_bar, uint32_t tfull_parity) {
   constexpr int ELEM = F32 ? 4 : 2;
   constexpr int ROW_BYTES = 2 * CW * ELEM;            // slab row: both halves
   constexpr int CHUNKS = CW * ELEM / 16;              // 16-byte chunks this thread writes per slab row
   constexpr uint32_t SWZ_MASK = ROW_BYTES == 128 ? 7u : (ROW_BYTES == 64 ? 3u : 1u);
   const int n_slabs = p.BN / (2 * CW);
+  // The residual of a slab is fetched one step ahead -- slab 0's before the wait for the accumulator, slab j+1's while slab j is
+  // processed -- so that its global-memory latency is off the per-tile epilogue chain (32->32 @272x480 with residual: 135 -> 80 us).
+  uint4 rres[F32 ? 1 : CHUNKS];
+  const bool has_res = !F32 && p.res != nullptr && valid;
+  const uint4* rbase = nullptr;
+  if constexpr (!F32) {
+    if (has_res) {
+      const long long rp = ((long long)t.n * p.H + y) * p.W + x;
+      rbase = reinterpret_cast<const uint4*>(p.res + rp * p.res_ctot + p.res_coff + t.n0 + half * CW);
+      if (t.n0 + half * CW < p.cout) {
+#pragma unroll
+        for (int c = 0; c < CHUNKS; ++c) rres[c] = __ldg(rbase + c);
+      }
+    }
+  }
+  if (lane == 0) mbar_wait(tfull_bar, tfull_parity);   // one lane polls; the warp reconverges below
+  __syncwarp();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   for (int j = 0; j < n_slabs; ++j, ++slab_ctr) {
     const uint32_t buf = stage_base + (slab_ctr & 1u) * (128 * 128);
     // the bulk store that last read this buffer (two slabs ago) must have finished reading shared memory
@@ -85,16 +101,18 @@ __device__ __forceinline__ void epilogue_tile(const ConvParams& p, const TileCoo
       for (int c = 0; c < CHUNKS; ++c)
         pk[c] = make_uint4(__float_as_uint(f[c * 4]), __float_as_uint(f[c * 4 + 1]), __float_as_uint(f[c * 4 + 2]), __float_as_uint(f[c * 4 + 3]));
     } else {
-      if (p.res && valid && gc0 < p.cout) {
-        const long long rp = ((long long)t.n * p.H + y) * p.W + x;
-        const uint4* r = reinterpret_cast<const uint4*>(p.res + rp * p.res_ctot + p.res_coff + gc0);
+      if (has_res && gc0 < p.cout) {
 #pragma unroll
         for (int c = 0; c < CHUNKS; ++c) {
-          const uint4 u = __ldg(r + c);
+          const uint4 u = rres[c];
           const float2 a0 = unpack2_act(u.x, p.fp16), a1 = unpack2_act(u.y, p.fp16), a2 = unpack2_act(u.z, p.fp16), a3 = unpack2_act(u.w, p.fp16);
           f[c * 8 + 0] += a0.x; f[c * 8 + 1] += a0.y; f[c * 8 + 2] += a1.x; f[c * 8 + 3] += a1.y;
           f[c * 8 + 4] += a2.x; f[c * 8 + 5] += a2.y; f[c * 8 + 6] += a3.x; f[c * 8 + 7] += a3.y;
         }
+      }
+      if (has_res && j + 1 < n_slabs && gc0 + 2 * CW < p.cout) {   // next slab's residual: in flight during this slab's stores
+#pragma unroll
+        for (int c = 0; c < CHUNKS; ++c) rres[c] = __ldg(rbase + (size_t)(j + 1) * (2 * CW * ELEM / 16) + c);
       }
       if (p.fp16) {   // warp-uniform: keeps the two encodings out of each other's instruction stream
 #pragma unroll
@@ -274,6 +292,10 @@ __global__ void __launch_bounds__(kThreads, OCC) conv_tc_kernel(const __grid_con
     const uint32_t smem_lo = (smem_u32(smem) & 0x3FFFFu) >> 4, bres_lo = (smem_u32(b_res) & 0x3FFFFu) >> 4;
     const uint32_t stage16 = (uint32_t)stage_bytes >> 4, a16 = (uint32_t)a_bytes >> 4, b16 = (uint32_t)b_bytes >> 4;
     const uint32_t hi_std = desc_hi(sbo, layout), full_bar_a = smem_u32(full_bar), empty_bar_a = smem_u32(empty_bar);
+    const int pitch = p.tw + p.ksize - 1;                                       // halo row pitch in pixels
+    const uint32_t hi_halo = desc_hi((uint32_t)(pitch * row_bytes), layout), row16 = (uint32_t)row_bytes >> 4;
+    const uint32_t halo_lo = (smem_u32(halo_ring) & 0x3FFFFu) >> 4, halo16 = (uint32_t)p.halo_bytes >> 4;
+    const uint32_t afull_bar_a = smem_u32(afull_bar), aempty_bar_a = smem_u32(aempty_bar);
     uint32_t s_lo = smem_lo;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++li) {
       const uint32_t as = li & 1u;
@@ -281,36 +303,50 @@ __global__ void __launch_bounds__(kThreads, OCC) conv_tc_kernel(const __grid_con
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const uint32_t tacc = tmem_base + as * (uint32_t)p.acc_stride;
       if (p.halo) {
-        const uint32_t hsbo = (uint32_t)(kHaloW * row_bytes);   // one halo image row = one 8-row group stride
+        // one pixel box per k-block; tap (dy, dx) = the same box read from row dy * pitch + dx, 8-row groups one pitch apart.
+        // Resident weights: the k*k taps of a k-block are issued back to back under one election.
+        const uint32_t h_lo = halo_lo + hs * halo16;
         for (int kc = 0; kc < p.kc_blocks; ++kc) {
-          mbar_wait(smem_u32(&afull_bar[hs]), hph);
+          mbar_wait(afull_bar_a + hs * 8u, hph);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-          const uint32_t hbase = smem_u32(halo_ring + (size_t)hs * p.halo_bytes);
-          int tap = 0;
-          for (int dy = 0; dy < p.ksize; ++dy)
-            for (int dx = 0; dx < p.ksize; ++dx, ++tap) {
-              const int kb = tap * p.kc_blocks + kc;
-              uint32_t baddr;
-              if (p.b_resident) baddr = smem_u32(b_res + (size_t)kb * b_bytes);
-              else {
-                mbar_wait(smem_u32(&full_bar[s]), ph);
-                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                baddr = smem_u32(smem + (size_t)s * stage_bytes);
-              }
-              if (elect_one()) {
-                const uint64_t adesc = make_desc(hbase + (uint32_t)((dy * kHaloW + dx) * row_bytes), hsbo, layout);
-                const uint64_t bdesc = make_desc(baddr, sbo, layout);
-                for (int k = 0; k < mma_per_kb; ++k)
-                  umma_f16(tacc, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kc | tap | k) ? 1u : 0u);
-                if (!p.b_resident) umma_commit(smem_u32(&empty_bar[s]));
-              }
-              __syncwarp();
-              if (!p.b_resident) { if (++s == (uint32_t)p.stages) { s = 0; ph ^= 1u; } }
+          const uint32_t hb_lo = halo_lo + hs * halo16;
+          if (p.b_resident) {
+            if (elect_one()) {
+              uint32_t w_lo = bres_lo + (uint32_t)kc * b16;
+              for (int dy = 0; dy < p.ksize; ++dy)
+                for (int dx = 0; dx < p.ksize; ++dx) {
+                  const uint32_t al = hb_lo + (uint32_t)(dy * pitch + dx) * row16;
+                  const uint32_t acc = (kc | dy | dx) ? 1u : 0u;
+                  if (mma_per_kb == 4) issue_kb<4>(tacc, al, hi_halo, w_lo, hi_std, idesc, acc);
+                  else if (mma_per_kb == 2) issue_kb<2>(tacc, al, hi_halo, w_lo, hi_std, idesc, acc);
+                  else issue_kb<1>(tacc, al, hi_halo, w_lo, hi_std, idesc, acc);
+                  w_lo += b16 * (uint32_t)p.kc_blocks;
+                }
+              umma_commit(aempty_bar_a + hs * 8u);   // halo stage free once its taps have retired
             }
-          if (elect_one()) umma_commit(smem_u32(&aempty_bar[hs]));   // halo stage free once its taps have retired
-          __syncwarp();
+            __syncwarp();
+          } else {
+            for (int dy = 0; dy < p.ksize; ++dy)
+              for (int dx = 0; dx < p.ksize; ++dx) {
+                mbar_wait(full_bar_a + s * 8u, ph);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                if (elect_one()) {
+                  const uint32_t al = hb_lo + (uint32_t)(dy * pitch + dx) * row16;
+                  const uint32_t acc = (kc | dy | dx) ? 1u : 0u;
+                  if (mma_per_kb == 4) issue_kb<4>(tacc, al, hi_halo, s_lo, hi_std, idesc, acc);
+                  else if (mma_per_kb == 2) issue_kb<2>(tacc, al, hi_halo, s_lo, hi_std, idesc, acc);
+                  else issue_kb<1>(tacc, al, hi_halo, s_lo, hi_std, idesc, acc);
+                  umma_commit(empty_bar_a + s * 8u);
+                  if (dy == p.ksize - 1 && dx == p.ksize - 1) umma_commit(aempty_bar_a + hs * 8u);
+                }
+                __syncwarp();
+                s_lo += stage16;
+                if (++s == (uint32_t)p.stages) { s = 0; ph ^= 1u; s_lo = smem_lo; }
+              }
+          }
           if (++hs == (uint32_t)p.a_stages) { hs = 0; hph ^= 1u; }
         }
+        (void)h_lo;
       } else {
         // lean issue: running low words, MMAs of a k-block unrolled at compile time (tc_ptx.cuh)
         uint32_t b_lo = bres_lo;
@@ -350,16 +386,22 @@ __global__ void __launch_bounds__(kThreads, OCC) conv_tc_kernel(const __grid_con
       const TileCoord t = ti.coord(p);
       const int y = t.y0 + ly, x = t.x0 + lx;
       const bool valid = (y < p.H) && (x < p.W);
-      if (lane == 0) mbar_wait(smem_u32(&tfull_bar[as]), (li >> 1) & 1u);   // one lane polls; the warp reconverges below
-      __syncwarp();
-      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t tfb = smem_u32(&tfull_bar[as]), tfp = (li >> 1) & 1u;   // waited for inside epilogue_tile, after the residual prefetch
       const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + as * (uint32_t)p.acc_stride;
       const uint32_t teb = smem_u32(&tempty_bar[as]);
+#if defined(GT_TC_EXP) && GT_TC_EXP == 1   // debug experiment: no epilogue (accumulator released at once, nothing stored)
+      if (lane == 0) mbar_wait(tfb, tfp);
+      __syncwarp();
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) mbar_arrive(teb);
+      continue;
+#endif
       switch (p.epi_mode) {
-        case 0: epilogue_tile<32, false>(p, t, trow, out_stage_a, s_bias_a, &tmOut, tmUp.m, half, row, y, x, valid, slab_ctr, teb, lane, leader_warp); break;
-        case 1: epilogue_tile<16, false>(p, t, trow, out_stage_a, s_bias_a, &tmOut, tmUp.m, half, row, y, x, valid, slab_ctr, teb, lane, leader_warp); break;
-        case 2: epilogue_tile<16, true>(p, t, trow, out_stage_a, s_bias_a, &tmOut, tmUp.m, half, row, y, x, valid, slab_ctr, teb, lane, leader_warp); break;
-        default: epilogue_tile<8, true>(p, t, trow, out_stage_a, s_bias_a, &tmOut, tmUp.m, half, row, y, x, valid, slab_ctr, teb, lane, leader_warp); break;
+        case 0: epilogue_tile<32, false>(p, t, trow, out_stage_a, s_bias_a, &tmOut, tmUp.m, half, row, y, x, valid, slab_ctr, teb, lane, leader_warp, tfb, tfp); break;
+        case 1: epilogue_tile<16, false>(p, t, trow, out_stage_a, s_bias_a, &tmOut, tmUp.m, half, row, y, x, valid, slab_ctr, teb, lane, leader_warp, tfb, tfp); break;
+        case 2: epilogue_tile<16, true>(p, t, trow, out_stage_a, s_bias_a, &tmOut, tmUp.m, half, row, y, x, valid, slab_ctr, teb, lane, leader_warp, tfb, tfp); break;
+        default: epilogue_tile<8, true>(p, t, trow, out_stage_a, s_bias_a, &tmOut, tmUp.m, half, row, y, x, valid, slab_ctr, teb, lane, leader_warp, tfb, tfp); break;
       }
     }
     if (leader_warp && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // all output stores complete before the CTA retires
@@ -449,12 +491,8 @@ int conv_tc_plan(gt_engine* e, ConvOp* op, const ConvPlanArgs& a) {
   pick_tile(Ho, Wo, &p.tw, &p.th);
   // Halo mode (stride-1 k x k): 8 x 16 output tiles; one TMA box per k-block brings the (16-pitch) x (16 + k - 1) halo and the
   // k*k taps are shifted shared-memory descriptors -> k*k times fewer A bytes from L2 and k*k times fewer TMA issues.
-  int want_halo = 0;
-  if (e->halo_mode && stride == 1 && k >= 2) {
-    const double u_halo = (double)Ho * Wo / ((double)ceil_div(Wo, 8) * 8 * ceil_div(Ho, 16) * 16);
-    const double u_best = (double)Ho * Wo / ((double)ceil_div(Wo, p.tw) * p.tw * ceil_div(Ho, p.th) * p.th);
-    if (u_halo >= 0.75 * u_best) want_halo = e->halo_mode;
-  }
+  // variants 4 / 5 (or GT_HALO=1): halo staging for stride-1 k >= 2 layers; the autotuner decides where it pays
+  int want_halo = ((e->plan_variant == 4 || e->plan_variant == 5 || e->halo_mode) && stride == 1 && k >= 2) ? 1 : 0;
   if (want_halo) { p.tw = 8; p.th = 16; }
   if (a.out_s2d) { p.tw = 16; p.th = 8; want_halo = 0; }   // Ho is a multiple of 8: tiles never straddle images in the folded row index
   p.tiles_x = ceil_div(Wo, p.tw); p.tiles_y = ceil_div(Ho, p.th);
@@ -483,7 +521,7 @@ int conv_tc_plan(gt_engine* e, ConvOp* op, const ConvPlanArgs& a) {
   const int a_bytes = 128 * kbe * 2, b_bytes = p.BN * kbe * 2;
   const int bres_bytes = p.num_kb * b_bytes;
   p.b_resident = (p.n_tiles == 1 && bres_bytes <= 112 * 1024 && (size_t)bres_bytes + 3 * a_bytes + 40 * 1024 <= (size_t)e->conv_smem_kb * 1024) ? 1 : 0;
-  const bool occ2 = e->plan_variant == 3 && p.tmem_cols <= 256 && !want_halo;   // two CTAs per SM (BN <= 128); else the plain plan
+  const bool occ2 = (e->plan_variant == 3 || e->plan_variant == 5) && p.tmem_cols <= 256;   // two CTAs per SM (BN <= 128); else the plain plan
   const size_t budget = occ2 ? (size_t)112 * 1024 : (size_t)e->conv_smem_kb * 1024;
   if (occ2) {
     p.b_resident = (p.n_tiles == 1 && (size_t)bres_bytes + 3 * a_bytes + 36 * 1024 <= budget) ? 1 : 0;
@@ -493,7 +531,7 @@ int conv_tc_plan(gt_engine* e, ConvOp* op, const ConvPlanArgs& a) {
   int halo_total = 0;
   if (want_halo) {
     const int hrows = p.th + k - 1;
-    p.halo_tx = kHaloW * hrows * kbe * 2;
+    p.halo_tx = (p.tw + k - 1) * hrows * kbe * 2;
     p.halo_bytes = (p.halo_tx + 1023) / 1024 * 1024;
     const size_t fixed = conv_smem_bytes(0, 0, 0, p.b_resident ? bres_bytes : 0, op->cout_pad);
     int a_st, b_st = 0;
@@ -565,7 +603,7 @@ int conv_tc_plan(gt_engine* e, ConvOp* op, const ConvPlanArgs& a) {
     cuuint64_t gdim[4] = {(cuuint64_t)cin, (cuuint64_t)in.W, (cuuint64_t)in.H, (cuuint64_t)a.Bmax};
     cuuint64_t gstr[3] = {(cuuint64_t)in.ctot * 2, (cuuint64_t)in.W * in.ctot * 2, (cuuint64_t)in.H * in.W * in.ctot * 2};
     cuuint32_t box[4] = {(cuuint32_t)kbe, (cuuint32_t)(p.tw * stride), (cuuint32_t)(p.th * stride), 1};
-    if (p.halo) { box[1] = kHaloW; box[2] = (cuuint32_t)(p.th + k - 1); }
+    if (p.halo) { box[1] = (cuuint32_t)(p.tw + k - 1); box[2] = (cuuint32_t)(p.th + k - 1); }
     cuuint32_t estr[4] = {1, (cuuint32_t)stride, (cuuint32_t)stride, 1};
     CUresult r = g_encode(&op->tmA, dt, 4, (void*)(in.ptr + in.coff), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
                           CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);

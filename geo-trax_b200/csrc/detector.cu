@@ -670,30 +670,32 @@ struct Builder {
     PlanOp po; po.type = OP_CONV; po.conv = (int)e->conv_ops.size() - 1;
     e->plan.push_back(po);
   }
-  // plans the op in the forced variant, or in both when the engine autotunes (conv_ops gets variant 0, conv_alt variant 1)
+  // plans the op in the forced variant, or in every variant when the engine autotunes (conv_ops gets variant 0, conv_var[v] the others;
+  // a variant that does not apply to the layer -- halo on a 1x1, two CTAs with BN > 128 -- is marked invalid and never timed)
+  static bool variant_applies(int v, const ConvOp& o) {
+    switch (v) {
+      case 1: return o.swapped && !o.p.halo;
+      case 2: return o.swapped && o.p.halo;
+      case 3: return !o.swapped && o.occ2 && !o.p.halo;
+      case 4: return !o.swapped && !o.occ2 && o.p.halo;
+      case 5: return !o.swapped && o.occ2 && o.p.halo;
+      default: return true;
+    }
+  }
   int plan_both(ConvOp& op, const ConvPlanArgs& a) {
     const bool tune = e->swap_mode < 0;
     e->plan_variant = tune ? 0 : e->swap_mode;
     int r = conv_tc_plan(e, &op, a);
     if (r != GT_OK || !tune) return r;
-    ConvOp alt = op;
-    e->plan_variant = 1;
-    r = conv_tc_plan(e, &alt, a);
-    e->plan_variant = 0;
-    if (r != GT_OK) return r;
-    e->conv_alt.push_back(alt);
-    ConvOp alt2 = op;               // variant 2: swapped + halo staging; kept only where the halo plan applies
-    e->plan_variant = 2;
-    r = conv_tc_plan(e, &alt2, a);
-    e->plan_variant = 0;
-    if (r != GT_OK) return r;
-    e->conv_alt2.push_back(alt2);
-    ConvOp alt3 = op;               // variant 3: pixel-major kernel at two CTAs per SM; kept only where it applies (BN <= 128)
-    e->plan_variant = 3;
-    r = conv_tc_plan(e, &alt3, a);
-    e->plan_variant = 0;
-    if (r != GT_OK) return r;
-    e->conv_alt3.push_back(alt3);
+    for (int v = 1; v < GT_CONV_VARIANTS; ++v) {
+      ConvOp alt = op;
+      e->plan_variant = v;
+      r = conv_tc_plan(e, &alt, a);
+      e->plan_variant = 0;
+      if (r != GT_OK) return r;
+      e->conv_var[v].push_back(alt);
+      e->conv_var_ok[v].push_back(variant_applies(v, alt) ? 1 : 0);
+    }
     return r;
   }
   // 16-bit conv writing a channel slice; several canonical convs reading the same input are fused along cout
@@ -733,7 +735,7 @@ struct Builder {
     rc = plan_both(op, a);
     if (rc != GT_OK) return;
     op.flops = 2.0 * out.H * out.W * 32.0 * 27.0;   // the algorithmic 3x3x3 work, not the zero-padded 2x2x64 -> 128
-    if (!e->conv_alt.empty()) { e->conv_alt.back().flops = op.flops; e->conv_alt2.back().flops = op.flops; e->conv_alt3.back().flops = op.flops; }
+    for (int v = 1; v < GT_CONV_VARIANTS; ++v) if (!e->conv_var[v].empty()) e->conv_var[v].back().flops = op.flops;
     e->conv0_op = (int)e->conv_ops.size();
     push(op);
   }
@@ -963,9 +965,8 @@ int detector_load_weights(gt_engine* e, const float* const* w, const float* cons
   GT_CHECK(e, n == (int)e->conv_descs.size(), "load_weights: expected %d convs, got %d", (int)e->conv_descs.size(), n);
   for (size_t oi = 0; oi < e->conv_ops.size(); ++oi) {
     GT_TRY(load_op_weights(e, e->conv_ops[oi], (int)oi == e->conv0_op, w, b));
-    if (!e->conv_alt.empty()) GT_TRY(load_op_weights(e, e->conv_alt[oi], (int)oi == e->conv0_op, w, b));
-    if (!e->conv_alt2.empty() && e->conv_alt2[oi].p.halo) GT_TRY(load_op_weights(e, e->conv_alt2[oi], (int)oi == e->conv0_op, w, b));
-    if (!e->conv_alt3.empty() && e->conv_alt3[oi].occ2) GT_TRY(load_op_weights(e, e->conv_alt3[oi], (int)oi == e->conv0_op, w, b));
+    for (int v = 1; v < GT_CONV_VARIANTS; ++v)
+      if (!e->conv_var[v].empty() && e->conv_var_ok[v][oi]) GT_TRY(load_op_weights(e, e->conv_var[v][oi], (int)oi == e->conv0_op, w, b));
   }
   e->weights_loaded = true;
   return GT_OK;
@@ -978,13 +979,15 @@ int detector_load_weights(gt_engine* e, const float* const* w, const float* cons
 static std::map<std::string, std::vector<int>>& tune_cache() { static std::map<std::string, std::vector<int>> c; return c; }
 
 static void apply_choice(gt_engine* e, size_t i, int v, int* n_swapped) {
-  if (v == 3) { std::swap(e->conv_ops[i], e->conv_alt3[i]); ++e->n_occ2; }
-  else if (v == 2) { std::swap(e->conv_ops[i], e->conv_alt2[i]); ++*n_swapped; ++e->n_halo; }
-  else if (v == 1) { std::swap(e->conv_ops[i], e->conv_alt[i]); ++*n_swapped; }
+  if (v <= 0) return;
+  std::swap(e->conv_ops[i], e->conv_var[v][i]);
+  if (v == 1 || v == 2) ++*n_swapped;
+  if (v == 2 || v == 4 || v == 5) ++e->n_halo;
+  if (v == 3 || v == 5) ++e->n_occ2;
 }
 
 int detector_autotune(gt_engine* e, cudaStream_t st) {
-  if (e->conv_alt.empty() || e->tuned) return GT_OK;
+  if (e->conv_var[1].empty() || e->tuned) return GT_OK;
   const int B = e->cfg.max_batch;
   char keybuf[160];
   snprintf(keybuf, sizeof(keybuf), "%d:%dx%d:%d:%d:%d:%d:%d:%zu", e->device, e->cfg.frame_h, e->cfg.frame_w, e->cfg.imgsz, e->cfg.nc, (int)e->cfg.task, B,
@@ -1002,6 +1005,7 @@ int detector_autotune(gt_engine* e, cudaStream_t st) {
   cudaEvent_t a, b;
   GT_CUDA(e, cudaEventCreate(&a));
   GT_CUDA(e, cudaEventCreate(&b));
+  int64_t tune_launches = 0;
   auto time_op = [&](const ConvOp& op, float* ms) -> int {
     GT_TRY(conv_tc_launch(e, &op, B, st));   // warm-up
     GT_CUDA(e, cudaEventRecord(a, st));
@@ -1009,30 +1013,32 @@ int detector_autotune(gt_engine* e, cudaStream_t st) {
     GT_CUDA(e, cudaEventRecord(b, st));
     GT_CUDA(e, cudaEventSynchronize(b));
     GT_CUDA(e, cudaEventElapsedTime(ms, a, b));
+    tune_launches += 3;
     return GT_OK;
   };
   int n_swapped = 0;
-  const bool tune_log = getenv("GT_TUNE_LOG") != nullptr;   // per-layer times of both kernels on stderr
+  const bool tune_log = getenv("GT_TUNE_LOG") != nullptr;   // per-layer times of every variant on stderr
+  static const char* vname[GT_CONV_VARIANTS] = {"tc", "sw", "sw-halo", "tc2", "tc-halo", "tc2-halo"};
   for (size_t i = 0; i < e->conv_ops.size(); ++i) {
-    float t0 = 0, t1 = 0, t2 = 1e30f;
-    GT_TRY(time_op(e->conv_ops[i], &t0));
-    GT_TRY(time_op(e->conv_alt[i], &t1));
-    const bool has2 = e->conv_alt2[i].p.halo != 0;
-    if (has2) { GT_TRY(time_op(e->conv_alt2[i], &t2)); e->launches -= 3; }
-    float t3 = 1e30f;
-    const bool has3 = e->conv_alt3[i].occ2 != 0;
-    if (has3) { GT_TRY(time_op(e->conv_alt3[i], &t3)); e->launches -= 3; }
-    const float tb = std::min(std::min(t0, t1), std::min(t2, t3));
+    float t[GT_CONV_VARIANTS];
+    int best = 0;
+    GT_TRY(time_op(e->conv_ops[i], &t[0]));
+    for (int v = 1; v < GT_CONV_VARIANTS; ++v) {
+      t[v] = 0.f;
+      if (!e->conv_var_ok[v][i]) continue;
+      GT_TRY(time_op(e->conv_var[v][i], &t[v]));
+      if (t[v] < t[best]) best = v;
+    }
     if (tune_log) {
       const ConvOp& o = e->conv_ops[i];
-      fprintf(stderr, "[gt tune] op %2zu src %2d cin %4d cout %4d k %d s %d out %4dx%-4d  tc %7.1f us  sw %7.1f us  halo %7.1f us  tc2 %7.1f us  %6.1f TFLOP/s  %6.1f GB/s\n", i, o.src[0],
-              o.cin, o.cout, o.k, o.stride, o.p.H, o.p.W, 500.f * t0, 500.f * t1, has2 ? 500.f * t2 : 0.f, has3 ? 500.f * t3 : 0.f, o.flops * B / (tb * 0.5e-3) * 1e-12,
-              o.bytes * B / (tb * 0.5e-3) * 1e-9);
+      fprintf(stderr, "[gt tune] op %2zu src %2d cin %4d cout %4d k %d s %d out %4dx%-4d ", i, o.src[0], o.cin, o.cout, o.k, o.stride, o.p.H, o.p.W);
+      for (int v = 0; v < GT_CONV_VARIANTS; ++v) fprintf(stderr, " %s %6.1f", vname[v], 500.f * t[v]);
+      fprintf(stderr, "  -> %s  %6.1f TFLOP/s  %6.1f GB/s\n", vname[best], o.flops * B / (t[best] * 0.5e-3) * 1e-12, o.bytes * B / (t[best] * 0.5e-3) * 1e-9);
     }
-    choice[i] = (t3 == tb && has3) ? 3 : ((t2 == tb && has2) ? 2 : (t1 == tb ? 1 : 0));
-    apply_choice(e, i, choice[i], &n_swapped);
+    choice[i] = best;
+    apply_choice(e, i, best, &n_swapped);
   }
-  e->launches -= (int64_t)e->conv_ops.size() * 6;   // tuning launches are not part of any step
+  e->launches -= tune_launches;   // tuning launches are not part of any step
   cudaEventDestroy(a);
   cudaEventDestroy(b);
   e->tuned = true;

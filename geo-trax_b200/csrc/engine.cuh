@@ -31,6 +31,9 @@ struct OrbSet {             // one frame's final features (device pointers into 
   int* count = nullptr;     // [1]
 };
 
+// conv kernel variants: 0 pixel-major, 1 swapped, 2 swapped + halo, 3 pixel-major two CTAs / SM, 4 pixel-major + halo, 5 = 3 + 4
+#define GT_CONV_VARIANTS 6
+
 struct gt_engine {
   gt_config cfg;
   int device = 0;
@@ -79,11 +82,10 @@ struct gt_engine {
   int n_swapped = 0;                                // convs running the swapped-operand kernel after autotune
   std::vector<gt_conv_desc> conv_descs;             // canonical list
   std::vector<ConvOp> conv_ops;                     // fused tcgen05 ops (the variant in use)
-  std::vector<ConvOp> conv_alt;                     // the other variant of each op (autotune), same indexing; empty when a variant is forced
+  std::vector<ConvOp> conv_var[GT_CONV_VARIANTS];   // the other variants of each op (autotune), same indexing as conv_ops; empty when a variant is forced
+  std::vector<char> conv_var_ok[GT_CONV_VARIANTS];  // 1 where the variant applies to the op
   std::vector<PlanOp> plan;
-  std::vector<ConvOp> conv_alt2;                    // swapped + halo variant (valid where p.halo == 1), same indexing
-  std::vector<ConvOp> conv_alt3;                    // pixel-major kernel at two CTAs per SM (valid where occ2 == 1), same indexing
-  int n_occ2 = 0;                                   // convs on the two-CTA variant after autotune
+  int n_occ2 = 0;                                   // convs on a two-CTA variant after autotune
   int n_halo = 0;                                   // convs on the halo variant after autotune
   int conv0_op = -1;                                // index of layer 0 in conv_ops (custom weight packing)
   View feat_views[23];

@@ -94,6 +94,22 @@ def small_engine_occ2():
 
 
 @pytest.fixture(scope="session")
+def small_engine_tc_halo():
+    """Forced onto the pixel-major kernel with halo staging wherever it applies (GT_SWAP=4)."""
+    eng = _forced_engine(4)
+    yield eng
+    eng.close()
+
+
+@pytest.fixture(scope="session")
+def small_engine_occ2_halo():
+    """Two CTAs per SM + halo staging wherever they apply (GT_SWAP=5)."""
+    eng = _forced_engine(5)
+    yield eng
+    eng.close()
+
+
+@pytest.fixture(scope="session")
 def small_engine_bf16():
     eng = _make_engine("bf16")
     yield eng

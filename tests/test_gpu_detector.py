@@ -84,11 +84,11 @@ CONV_CASES = [
 ]
 
 
-@pytest.mark.parametrize("dtype", ["fp16", "bf16", "fp16-pixel-major", "fp16-swapped-nohalo", "fp16-two-cta"])
+@pytest.mark.parametrize("dtype", ["fp16", "bf16", "fp16-pixel-major", "fp16-swapped-nohalo", "fp16-two-cta", "fp16-tc-halo", "fp16-two-cta-halo"])
 @pytest.mark.parametrize("case", CONV_CASES)
 def test_conv2d_tcgen05_matches_torch(request, case, dtype):
     fixture = {"fp16": "small_engine", "bf16": "small_engine_bf16", "fp16-pixel-major": "small_engine_tc", "fp16-swapped-nohalo": "small_engine_sw",
-               "fp16-two-cta": "small_engine_occ2"}[dtype]
+               "fp16-two-cta": "small_engine_occ2", "fp16-tc-halo": "small_engine_tc_halo", "fp16-two-cta-halo": "small_engine_occ2_halo"}[dtype]
     eng = request.getfixturevalue(fixture)
     rnd = lambda a: eng.act_to_f32(eng.f32_to_act(a))
     B, H, W, cin, cout, k, s, act, use_res, f32 = case
@@ -155,11 +155,12 @@ def test_raw_head_within_1e2_of_fp32_oracle(small_engine, small_engine_bf16, dty
         assert rel < max(2.5 * rel_emu, 1e-2)   # the GPU also rounds the folded weights to bf16
 
 
-@pytest.mark.parametrize("variant", ["pixel-major", "two-cta", "swapped-nohalo"])
+@pytest.mark.parametrize("variant", ["pixel-major", "two-cta", "swapped-nohalo", "tc-halo", "two-cta-halo"])
 def test_forced_kernel_raw_head(request, variant):
     """Each forced conv kernel variant (conv_tc.cu at one / two CTAs per SM, conv_sw.cu without halo) through the whole network."""
     from oracle import prepost
-    eng = request.getfixturevalue({"pixel-major": "small_engine_tc", "two-cta": "small_engine_occ2", "swapped-nohalo": "small_engine_sw"}[variant])
+    eng = request.getfixturevalue({"pixel-major": "small_engine_tc", "two-cta": "small_engine_occ2", "swapped-nohalo": "small_engine_sw",
+                                   "tc-halo": "small_engine_tc_halo", "two-cta-halo": "small_engine_occ2_halo"}[variant])
     if variant != "swapped-nohalo":
         assert eng.conv_kernel_info()[1] == 0
     frames = _frames(2, 512, 768, seed=3)
