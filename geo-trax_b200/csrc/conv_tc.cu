@@ -494,7 +494,7 @@ int conv_tc_plan(gt_engine* e, ConvOp* op, const ConvPlanArgs& a) {
   // variants 4 / 5 (or GT_HALO=1): halo staging for stride-1 k >= 2 layers; the autotuner decides where it pays
   int want_halo = ((e->plan_variant == 4 || e->plan_variant == 5 || e->halo_mode) && stride == 1 && k >= 2) ? 1 : 0;
   if (want_halo) { p.tw = 8; p.th = 16; }
-  if (a.out_s2d) { p.tw = 16; p.th = 8; want_halo = 0; }   // Ho is a multiple of 8: tiles never straddle images in the folded row index
+  if (a.out_s2d && !(want_halo && (Ho % 16) == 0)) { p.tw = 16; p.th = 8; want_halo = 0; }   // Ho is a multiple of th: tiles never straddle images in the folded row index
   p.tiles_x = ceil_div(Wo, p.tw); p.tiles_y = ceil_div(Ho, p.th);
   p.stride = stride; p.ksize = k; p.pad = pad;
   p.kb_elems = kbe;

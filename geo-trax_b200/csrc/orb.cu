@@ -47,34 +47,66 @@ __global__ void mask_rects_kernel(uint8_t* __restrict__ mask, size_t slab, const
 // ---- one pyramid level from the previous one: cv2.resize(INTER_LINEAR_EXACT) in Q8.8 x Q8.8, (v + 2^15) >> 16 -------------
 // One thread = 4 adjacent output pixels.  MASK = false: image plane.  MASK = true: mask plane, thresholded (<= 254 -> 0); the
 // mask pyramid depends on the detections and is built later than the image pyramid (see orb_front / orb_back).
+constexpr int kResizeRows = 4;
 template <bool MASK>
-__global__ void __launch_bounds__(256) pyr_resize_kernel(uint8_t* __restrict__ plane, size_t slab, int slot0, size_t src_off, int sw, int sh,
+__global__ void __launch_bounds__(128) pyr_resize_kernel(uint8_t* __restrict__ plane, size_t slab, int slot0, size_t src_off, int sw, int sh,
                                                          size_t dst_off, int dw, int dh, const int* __restrict__ xofs, const int* __restrict__ xc1,
                                                          const int* __restrict__ yofs, const int* __restrict__ yc1) {
   const int x4 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
-  const int y = blockIdx.y;
   if (x4 >= dw) return;
   const int slot = slot0 + blockIdx.z;
-  const int yo = __ldg(yofs + y), cy1 = __ldg(yc1 + y), cy0 = 256 - cy1, yo1 = min(yo + 1, sh - 1);
   uint8_t* base = plane + (size_t)slot * slab;
-  const uint8_t* r0 = base + src_off + (size_t)yo * sw;
-  const uint8_t* r1 = base + src_off + (size_t)yo1 * sw;
+  // the tables are padded to a multiple of four entries: one 16-byte load each
+  const int4 xo = __ldg(reinterpret_cast<const int4*>(xofs + x4)), xc = __ldg(reinterpret_cast<const int4*>(xc1 + x4));
+  const int a[4] = {xo.x, xo.y, xo.z, xo.w}, c1v[4] = {xc.x, xc.y, xc.z, xc.w};
   const int nvalid = min(4, dw - x4);
-  uint32_t packed = 0;
+  // the four outputs read source columns a[0] .. a[3] + 1 <= a[0] + 7 (scale 1.2): an 8-byte window per source row, fetched as three
+  // aligned words (the rows of a level have arbitrary alignment) and shifted into place.  A thread produces kResizeRows output rows
+  // and issues all of their loads before the first use (the kernel is latency bound, not bandwidth bound).
+  const uintptr_t hi = (reinterpret_cast<uintptr_t>(base + src_off) + (size_t)sw * sh - 1) & ~(uintptr_t)3;
+  const int y0 = blockIdx.y * kResizeRows;
+  uint32_t w[kResizeRows][2][3];
+  int cy[kResizeRows], sft[kResizeRows][2];
 #pragma unroll
-  for (int k = 0; k < 4; ++k) {
-    const int x = min(x4 + k, dw - 1);
-    const int a = __ldg(xofs + x), b = min(a + 1, sw - 1), c1 = __ldg(xc1 + x), c0 = 256 - c1;
-    const int h0 = r0[a] * c0 + r0[b] * c1;
-    const int h1 = r1[a] * c0 + r1[b] * c1;
-    int v = (h0 * cy0 + h1 * cy1 + 32768) >> 16;
-    if (MASK && v <= 254) v = 0;
-    packed |= (uint32_t)v << (8 * k);
+  for (int i = 0; i < kResizeRows; ++i) {
+    const int y = min(y0 + i, dh - 1);
+    const int yo = __ldg(yofs + y);
+    cy[i] = __ldg(yc1 + y);
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      const uintptr_t p = reinterpret_cast<uintptr_t>(base + src_off + (size_t)min(yo + r, sh - 1) * sw + a[0]);
+      const uintptr_t p0 = p & ~(uintptr_t)3;
+      w[i][r][0] = __ldg(reinterpret_cast<const uint32_t*>(min(p0, hi)));
+      w[i][r][1] = __ldg(reinterpret_cast<const uint32_t*>(min(p0 + 4, hi)));
+      w[i][r][2] = __ldg(reinterpret_cast<const uint32_t*>(min(p0 + 8, hi)));
+      sft[i][r] = 8 * (int)(p & 3);
+    }
   }
-  uint8_t* d = base + dst_off + (size_t)y * dw + x4;
-  if (nvalid == 4 && (reinterpret_cast<uintptr_t>(d) & 3) == 0) *reinterpret_cast<uint32_t*>(d) = packed;
-  else
-    for (int k = 0; k < nvalid; ++k) d[k] = (uint8_t)(packed >> (8 * k));
+#pragma unroll
+  for (int i = 0; i < kResizeRows; ++i) {
+    const int y = y0 + i;
+    if (y >= dh) break;
+    unsigned long long win[2];
+#pragma unroll
+    for (int r = 0; r < 2; ++r)
+      win[r] = (unsigned long long)__funnelshift_r(w[i][r][0], w[i][r][1], sft[i][r]) | ((unsigned long long)__funnelshift_r(w[i][r][1], w[i][r][2], sft[i][r]) << 32);
+    const int cy1 = cy[i], cy0 = 256 - cy1;
+    uint32_t packed = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int o0 = (a[k] - a[0]) * 8, o1 = (min(a[k] + 1, sw - 1) - a[0]) * 8;
+      const int c1 = c1v[k], c0 = 256 - c1;
+      const int h0 = (int)((win[0] >> o0) & 0xFF) * c0 + (int)((win[0] >> o1) & 0xFF) * c1;
+      const int h1 = (int)((win[1] >> o0) & 0xFF) * c0 + (int)((win[1] >> o1) & 0xFF) * c1;
+      int v = (h0 * cy0 + h1 * cy1 + 32768) >> 16;
+      if (MASK && v <= 254) v = 0;
+      packed |= (uint32_t)v << (8 * k);
+    }
+    uint8_t* d = base + dst_off + (size_t)y * dw + x4;
+    if (nvalid == 4 && (reinterpret_cast<uintptr_t>(d) & 3) == 0) *reinterpret_cast<uint32_t*>(d) = packed;
+    else
+      for (int k = 0; k < nvalid; ++k) d[k] = (uint8_t)(packed >> (8 * k));
+  }
 }
 
 // ---- FAST-9/16 score + 3x3 non-max suppression + border filter -> candidate list --------------------------------------------
@@ -689,6 +721,7 @@ int orb_build(gt_engine* e) {
     std::vector<int> xo, xc, yo, yc;
     resize_tables(e->lv[l - 1].w, e->lv[l].w, xo, xc);
     resize_tables(e->lv[l - 1].h, e->lv[l].h, yo, yc);
+    while (xo.size() % 4) { xo.push_back(xo.back()); xc.push_back(xc.back()); }   // the resize kernel loads four x entries at once
     const std::vector<int>* src[4] = {&xo, &xc, &yo, &yc};
     for (int k = 0; k < 4; ++k) {
       GT_TRY(e->dev_alloc((void**)&e->rs_tab[l][k], src[k]->size() * 4));
@@ -708,8 +741,8 @@ int orb_front(gt_engine* e, int slot0, int nslots, cudaStream_t st) {
     const OrbLevel& S = e->lv[l - 1];
     const OrbLevel& D = e->lv[l];
     int* const* t = e->rs_tab[l];
-    dim3 g((unsigned)ceil_div(D.w, 4 * 256), (unsigned)D.h, (unsigned)nslots);
-    pyr_resize_kernel<false><<<g, 256, 0, st>>>(e->pyr, slab, slot0, S.off, S.w, S.h, D.off, D.w, D.h, t[0], t[1], t[2], t[3]);
+    dim3 g((unsigned)ceil_div(D.w, 4 * 128), (unsigned)ceil_div(D.h, kResizeRows), (unsigned)nslots);
+    pyr_resize_kernel<false><<<g, 128, 0, st>>>(e->pyr, slab, slot0, S.off, S.w, S.h, D.off, D.w, D.h, t[0], t[1], t[2], t[3]);
     e->launches++;
   }
   GT_CUDA(e, cudaMemsetAsync(e->fast_count + (size_t)slot0 * GT_ORB_LEVELS, 0, (size_t)nslots * GT_ORB_LEVELS * sizeof(int), st));
@@ -751,8 +784,8 @@ int orb_back(gt_engine* e, int slot0, int nslots, bool as_reference, bool build_
     const OrbLevel& S = e->lv[l - 1];
     const OrbLevel& D = e->lv[l];
     int* const* t = e->rs_tab[l];
-    dim3 g((unsigned)ceil_div(D.w, 4 * 256), (unsigned)D.h, (unsigned)nslots);
-    pyr_resize_kernel<true><<<g, 256, 0, st>>>(e->pyr_mask, slab, slot0, S.off, S.w, S.h, D.off, D.w, D.h, t[0], t[1], t[2], t[3]);
+    dim3 g((unsigned)ceil_div(D.w, 4 * 128), (unsigned)ceil_div(D.h, kResizeRows), (unsigned)nslots);
+    pyr_resize_kernel<true><<<g, 128, 0, st>>>(e->pyr_mask, slab, slot0, S.off, S.w, S.h, D.off, D.w, D.h, t[0], t[1], t[2], t[3]);
     e->launches++;
   }
   {
