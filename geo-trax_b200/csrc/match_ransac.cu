@@ -277,31 +277,42 @@ __device__ __forceinline__ float reproj_err2(const float* H, const float4 q) {
   return du * du + dv * dv;
 }
 
-// one warp per hypothesis: MSAC score (sum of max(0, 1 - e^2/t^2)) over all matches
-__global__ void __launch_bounds__(256) ransac_score_kernel(const float4* __restrict__ npairs, const int* __restrict__ counts, int pair_stride,
-                                                           const Norm* __restrict__ norms, float thr, int max_iter, unsigned seed,
-                                                           float* __restrict__ scores) {
+// one warp per hypothesis: MSAC score (sum of max(0, 1 - e^2/t^2)) over all matches.  The 16 hypotheses of a block share the
+// matches through shared memory (tiles of kScoreTile pairs), four independent accumulation chains per lane.
+constexpr int kScoreWarps = 16, kScoreTile = 1024;
+__global__ void __launch_bounds__(kScoreWarps * 32) ransac_score_kernel(const float4* __restrict__ npairs, const int* __restrict__ counts, int pair_stride,
+                                                                        const Norm* __restrict__ norms, float thr, int max_iter, unsigned seed,
+                                                                        float* __restrict__ scores) {
+  __shared__ float4 s_np[kScoreTile];
   const int b = blockIdx.y;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int h = blockIdx.x * 8 + warp;
-  if (h >= max_iter) return;
+  const int h = blockIdx.x * kScoreWarps + warp;
   const int m = min(counts[b], pair_stride);
-  float score = -1.f;
-  if (m >= 4) {
-    const float4* np = npairs + (size_t)b * pair_stride;
-    int s[4];
-    float H[9];
-    if (draw_sample(seed, b, h, m, s) && homography_4pt(np, s, H)) {
-      const float t = thr * norms[b].sr;
-      const float it2 = 1.0f / (t * t);
-      float acc = 0.f;
-      for (int i = lane; i < m; i += 32) acc += fmaxf(0.f, 1.0f - reproj_err2(H, __ldg(&np[i])) * it2);
+  const float4* np = npairs + (size_t)b * pair_stride;
+  int s[4];
+  float H[9];
+  const bool ok = h < max_iter && m >= 4 && draw_sample(seed, b, h, m, s) && homography_4pt(np, s, H);
+  const float t = thr * norms[b].sr;
+  const float it2 = 1.0f / (t * t);
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int t0 = 0; t0 < m; t0 += kScoreTile) {
+    const int n = min(kScoreTile, m - t0);
+    __syncthreads();
+    for (int i = threadIdx.x; i < n; i += kScoreWarps * 32) s_np[i] = __ldg(&np[t0 + i]);
+    __syncthreads();
+    if (ok) {
+      int i = lane;
+      for (; i + 96 < n; i += 128) {
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-      score = acc;
+        for (int u = 0; u < 4; ++u) acc[u] += fmaxf(0.f, 1.0f - reproj_err2(H, s_np[i + 32 * u]) * it2);
+      }
+      for (; i < n; i += 32) acc[0] += fmaxf(0.f, 1.0f - reproj_err2(H, s_np[i]) * it2);
     }
   }
-  if (lane == 0) scores[(size_t)b * max_iter + h] = score;
+  float a = (acc[0] + acc[1]) + (acc[2] + acc[3]);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+  if (lane == 0 && h < max_iter) scores[(size_t)b * max_iter + h] = ok ? a : -1.f;
 }
 
 // 8x8 SPD solve (Cholesky, in place).  A is the full symmetric matrix row-major; returns false if not positive definite.
@@ -549,8 +560,8 @@ int match_run(gt_engine* e, const uint8_t* q, const int* nq_dev, int nq_max, con
 int homography_run(gt_engine* e, const float* pairs, const int* counts, int B, int pair_stride, float thr, int max_iter, double* out_H,
                    int* out_status, int* out_stats, float ratio, bool full_res, const int* kp_count, cudaStream_t st) {
   ransac_prepare_kernel<<<B, 256, 0, st>>>(pairs, counts, pair_stride, (float4*)e->npairs, (Norm*)e->norms);
-  dim3 g((unsigned)ceil_div(max_iter, 8), (unsigned)B);
-  ransac_score_kernel<<<g, 256, 0, st>>>((const float4*)e->npairs, counts, pair_stride, (const Norm*)e->norms, thr, max_iter, e->cfg.seed,
+  dim3 g((unsigned)ceil_div(max_iter, kScoreWarps), (unsigned)B);
+  ransac_score_kernel<<<g, kScoreWarps * 32, 0, st>>>((const float4*)e->npairs, counts, pair_stride, (const Norm*)e->norms, thr, max_iter, e->cfg.seed,
                                          e->hyp_score);
   ransac_finalize_kernel<<<B, 256, 0, st>>>((const float4*)e->npairs, counts, pair_stride, (const Norm*)e->norms, e->hyp_score, thr, max_iter,
                                             e->cfg.seed, ratio, full_res ? 1 : 0, out_H, out_status, out_stats, e->cfg.max_batch,

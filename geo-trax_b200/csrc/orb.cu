@@ -168,6 +168,25 @@ __device__ __forceinline__ int fast_corner_score(const uint8_t (*t)[FT_SW], int 
   return best > kFastThr ? best - 1 : 0;
 }
 
+// Byte-wise unsigned compares with the result in the MSB of each byte only (the other bits are don't-care: every consumer is a
+// bitwise AND / OR followed by a final mask with 0x80808080).  a > b  <=>  (a7 & ~b7) | (~(a7 ^ b7) & ~msb((b | H) - (a & ~H))): four
+// instructions instead of the ~6 of the emulated __vcmpgtu4, and `r & ~H`, `r | H` are shared by the two polarities of a ring word.
+struct RingCmp {            // per group: thresholds hi = sat(c + t), lo = sat(c - t)
+  uint32_t hi, hi_h, lo, lo_l;
+  __device__ __forceinline__ RingCmp(uint32_t c, uint32_t thr4) {
+    hi = __vaddus4(c, thr4); lo = __vsubus4(c, thr4);
+    hi_h = hi | 0x80808080u; lo_l = lo & 0x7f7f7f7fu;
+  }
+  __device__ __forceinline__ uint32_t brighter(uint32_t r) const {   // r > hi
+    const uint32_t d = hi_h - (r & 0x7f7f7f7fu);
+    return (r & ~hi) | (~(r ^ hi) & ~d);
+  }
+  __device__ __forceinline__ uint32_t darker(uint32_t r) const {     // lo > r
+    const uint32_t d = (r | 0x80808080u) - lo_l;
+    return (lo & ~r) | (~(lo ^ r) & ~d);
+  }
+};
+
 // bytes [o, o + 4) of the 12-byte window (w0, w1, w2), o in 1..7
 __device__ __forceinline__ uint32_t win4(uint32_t w0, uint32_t w1, uint32_t w2, int o) {
   return o < 4 ? __funnelshift_r(w0, w1, 8 * o) : (o == 4 ? w1 : __funnelshift_r(w1, w2, 8 * (o - 4)));
@@ -252,10 +271,10 @@ __global__ void __launch_bounds__(256) fast_kernel(const uint8_t* __restrict__ i
         const uint32_t w0 = rc[0], c = rc[1], w2 = rc[2];
         const uint32_t r0 = reinterpret_cast<const uint32_t*>(&s_img[sy + 6][0])[g + 1], r8 = reinterpret_cast<const uint32_t*>(&s_img[sy][0])[g + 1];
         const uint32_t r4 = __funnelshift_r(c, w2, 24), r12 = __funnelshift_r(w0, c, 8);
-        const uint32_t hi4 = __vaddus4(c, thr4), lo4 = __vsubus4(c, thr4);
-        const uint32_t br = two_of_four(__vcmpgtu4(r0, hi4), __vcmpgtu4(r4, hi4), __vcmpgtu4(r8, hi4), __vcmpgtu4(r12, hi4));
-        const uint32_t dk = two_of_four(__vcmpltu4(r0, lo4), __vcmpltu4(r4, lo4), __vcmpltu4(r8, lo4), __vcmpltu4(r12, lo4));
-        uint32_t m = br | dk;
+        const RingCmp rc4(c, thr4);
+        const uint32_t br = two_of_four(rc4.brighter(r0), rc4.brighter(r4), rc4.brighter(r8), rc4.brighter(r12));
+        const uint32_t dk = two_of_four(rc4.darker(r0), rc4.darker(r4), rc4.darker(r8), rc4.darker(r12));
+        uint32_t m = (br | dk) & 0x80808080u;
         // validity of the four pixels (sx = 4 g + j): j in [jlo, jhi]
         const int gx = x0 - 1 + 4 * g;
         const int jlo = max(kEdge - 1 - gx, 0), jhi = min(min(w - kEdge - gx, FT_X + 1 - 4 * g), 3);
@@ -296,13 +315,13 @@ __global__ void __launch_bounds__(256) fast_kernel(const uint8_t* __restrict__ i
       FT_ROW(-3) r[9] = win4(w0, w1, w2, 3); r[8] = w1; r[7] = win4(w0, w1, w2, 5);
 #undef FT_ROW
     }
-    const uint32_t hi4 = __vaddus4(c, thr4), lo4 = __vsubus4(c, thr4);
+    const RingCmp rc4(c, thr4);
     uint32_t m[16];
 #pragma unroll
-    for (int i = 0; i < 16; ++i) m[i] = __vcmpgtu4(r[i], hi4);
+    for (int i = 0; i < 16; ++i) m[i] = rc4.brighter(r[i]);
     uint32_t corner = arc9(m);
 #pragma unroll
-    for (int i = 0; i < 16; ++i) m[i] = __vcmpltu4(r[i], lo4);
+    for (int i = 0; i < 16; ++i) m[i] = rc4.darker(r[i]);
     corner |= arc9(m);
     unsigned bits = (((corner >> 7) & 1u) | ((corner >> 14) & 2u) | ((corner >> 21) & 4u) | ((corner >> 28) & 8u)) & (e & 15u);
     if (bits) {
