@@ -77,7 +77,7 @@ int gt_create(const gt_config* cfg, int device, gt_handle* out) {
   if (const char* sm = getenv("GT_SWAP")) e->swap_mode = atoi(sm);
   if (const char* ov = getenv("GT_OVERLAP")) e->overlap = atoi(ov);
   if (const char* kb = getenv("GT_CONV_SMEM_KB")) e->conv_smem_kb = std::min(227, std::max(96, atoi(kb)));
-  if (e->overlap && !getenv("GT_CONV_SMEM_KB")) e->conv_smem_kb = 200;
+  if (e->overlap == 1 && !getenv("GT_CONV_SMEM_KB")) e->conv_smem_kb = 200;   // room for ORB blocks beside the conv CTAs
   auto fail = [&](int rc) { g_create_error = e->err; gt_destroy(e); return rc; };
 #define CR(expr) do { int _rc = (expr); if (_rc != GT_OK) return fail(_rc); } while (0)
 #define CRC(call) do { cudaError_t _er = (call); if (_er != cudaSuccess) { gt_set_error(e, "%s -> %s", #call, cudaGetErrorString(_er)); return fail(GT_ERR_CUDA); } } while (0)
@@ -697,14 +697,23 @@ int gt_extract_batch(gt_handle e, const uint8_t* frames, int B, int first_is_ref
     GT_TRY(gt_prefetch_frames(e, nxt, e->deferred_B));
   }
   GT_TRY(gt_preprocess(e, frames, B, st));
+  // The mask-independent half of ORB (pyramid + FAST) needs only the gray frames.  overlap 2 (default): it runs on the aux stream beside
+  // decode + NMS, whose kernels occupy 16-64 blocks; overlap 1: beside the whole detector (no gain: the conv CTAs own the SMs); 0: serial.
   const bool ov = e->overlap != 0;
-  if (ov) {   // fork: the mask-independent half of ORB needs only the gray frames and runs beside the detector
+  auto fork_front = [&]() -> int {
     GT_CUDA(e, cudaEventRecord(e->ev_pre, st));
     GT_CUDA(e, cudaStreamWaitEvent(e->aux_stream, e->ev_pre, 0));
     GT_TRY(orb_front(e, 0, B, e->aux_stream));
     GT_CUDA(e, cudaEventRecord(e->ev_front, e->aux_stream));
-  }
-  GT_TRY(detect_impl(e, B, conf, iou, agnostic, classes_mask, st));
+    return GT_OK;
+  };
+  if (e->overlap == 1) GT_TRY(fork_front());
+  GT_CUDA(e, cudaEventRecord(e->ev[2], st));
+  GT_TRY(detector_forward(e, B, st));
+  GT_CUDA(e, cudaEventRecord(e->ev[3], st));
+  if (e->overlap >= 2) GT_TRY(fork_front());
+  GT_TRY(detector_postprocess(e, B, conf, iou, agnostic, classes_mask, st));
+  GT_CUDA(e, cudaEventRecord(e->ev[4], st));
   dim3 g((unsigned)ceil_div(md, 256), (unsigned)B);
   dets_to_xywh_kernel<<<g, 256, 0, st>>>(e->det_out, e->det_count, obb ? 7 : 6, md, e->det_xywh_dev, e->det_nbox_dev, B, obb);
   e->launches++;

@@ -61,7 +61,7 @@ struct gt_engine {
   cudaStream_t copy_stream = nullptr;
   cudaStream_t aux_stream = nullptr;    // low priority: the mask-independent half of ORB runs here next to the detector
   cudaEvent_t ev_pre = nullptr, ev_front = nullptr;
-  int overlap = 0;                      // GT_OVERLAP=1: ORB front on the aux stream beside the detector (measured +2 %: the conv CTAs own the SMs)
+  int overlap = 2;                      // GT_OVERLAP: 2 (default) ORB front on the aux stream beside decode + NMS; 1 beside the whole detector (no gain: the conv CTAs own the SMs); 0 serial
   int conv_smem_kb = 227;               // dynamic smem budget of the conv kernels (200 with GT_OVERLAP=1 to leave room for ORB blocks); GT_CONV_SMEM_KB
   cudaEvent_t ev_copied[2] = {nullptr, nullptr};   // H2D of staging buffer k finished (copy stream)
   cudaEvent_t ev_consumed[2] = {nullptr, nullptr}; // the preprocess kernel that read staging buffer k finished
