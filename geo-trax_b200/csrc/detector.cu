@@ -993,6 +993,24 @@ int detector_autotune(gt_engine* e, cudaStream_t st) {
   snprintf(keybuf, sizeof(keybuf), "%d:%dx%d:%d:%d:%d:%d:%d:%zu", e->device, e->cfg.frame_h, e->cfg.frame_w, e->cfg.imgsz, e->cfg.nc, (int)e->cfg.task, B,
            (int)e->cfg.act_dtype, e->conv_ops.size());
   const std::string key(keybuf);
+  // GT_TUNE_FILE=<path>: per-layer choices are read from / written to a text file ("key v0 v1 ..."), so that a profiled run (whose
+  // tuning launches would be timed under the profiler) uses the choices of a normal run
+  const char* tune_file = getenv("GT_TUNE_FILE");
+  if (tune_file && tune_cache().find(key) == tune_cache().end()) {
+    if (FILE* f = fopen(tune_file, "r")) {
+      char k[200];
+      while (fscanf(f, "%199s", k) == 1) {
+        std::vector<int> v(e->conv_ops.size(), 0);
+        bool ok = true;
+        for (size_t i = 0; i < v.size() && ok; ++i) ok = fscanf(f, "%d", &v[i]) == 1 && v[i] >= 0 && v[i] < GT_CONV_VARIANTS;
+        if (!ok) break;
+        bool applies = key == k;
+        for (size_t i = 0; i < v.size() && applies; ++i) applies = v[i] == 0 || e->conv_var_ok[v[i]][i];
+        if (applies) tune_cache()[key] = v;
+      }
+      fclose(f);
+    }
+  }
   auto hit = tune_cache().find(key);
   if (hit != tune_cache().end() && hit->second.size() == e->conv_ops.size() && !getenv("GT_TUNE_LOG")) {
     int ns = 0;
@@ -1044,6 +1062,14 @@ int detector_autotune(gt_engine* e, cudaStream_t st) {
   e->tuned = true;
   e->n_swapped = n_swapped;
   tune_cache()[key] = choice;
+  if (tune_file) {
+    if (FILE* f = fopen(tune_file, "a")) {
+      fprintf(f, "%s", key.c_str());
+      for (int v : choice) fprintf(f, " %d", v);
+      fprintf(f, "\n");
+      fclose(f);
+    }
+  }
   return GT_OK;
 }
 
