@@ -256,6 +256,47 @@ __global__ void __launch_bounds__(256) maxpool5_kernel(const bf16* __restrict__ 
   *reinterpret_cast<uint4*>(out + (((size_t)b * H + y) * W + x) * out_ctot + out_coff + cg * 8) = *reinterpret_cast<const uint4*>(m);
 }
 
+// SPPF chain in one launch: the three chained 5x5 / stride-1 pools (= 5x5, 9x9 and 13x13 windows of the input) of one image and one
+// 8-channel group, separable (row max, column max) in shared memory; the plane of a 34 x 60 level is 32 KB.  Replaces three
+// dependent launches that were pure latency (33 us each for an 8 MB tensor).
+template <typename T2>
+__global__ void __launch_bounds__(256) sppf_pool3_kernel(bf16* __restrict__ buf, int ctot, int coff, int C, int H, int W) {
+  extern __shared__ __align__(16) uint4 s_pool[];
+  uint4* A = s_pool;
+  uint4* R = s_pool + (size_t)H * W;
+  const int cg = blockIdx.x, b = blockIdx.y;
+  const int n = H * W;
+  bf16* base = buf + (size_t)b * n * ctot + coff + cg * 8;
+  for (int i = threadIdx.x; i < n; i += 256) A[i] = __ldg(reinterpret_cast<const uint4*>(base + (size_t)i * ctot));
+  __syncthreads();
+  auto vmax = [](uint4 a, const uint4& c) {
+    T2* pa = reinterpret_cast<T2*>(&a);
+    const T2* pc = reinterpret_cast<const T2*>(&c);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) pa[k] = __hmax2(pa[k], pc[k]);
+    return a;
+  };
+  for (int stage = 1; stage <= 3; ++stage) {
+    for (int i = threadIdx.x; i < n; i += 256) {       // row pass
+      const int y = i / W, x = i - y * W;
+      uint4 m = A[i];
+      for (int dx = -2; dx <= 2; ++dx)
+        if (dx != 0 && x + dx >= 0 && x + dx < W) m = vmax(m, A[i + dx]);
+      R[i] = m;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < n; i += 256) {       // column pass -> slice `stage`, and the next stage's input
+      const int y = i / W;
+      uint4 m = R[i];
+      for (int dy = -2; dy <= 2; ++dy)
+        if (dy != 0 && y + dy >= 0 && y + dy < H) m = vmax(m, R[i + dy * W]);
+      A[i] = m;
+      *reinterpret_cast<uint4*>(base + (size_t)i * ctot + (size_t)stage * C) = m;
+    }
+    __syncthreads();
+  }
+}
+
 // =====================================================================================================================
 // Decode + confidence filter: raw head rows [B][A][no] f32 -> dense candidate arrays indexed by anchor + a key list.
 // key = conf bits << 32 | ~anchor : descending key order == (conf desc, anchor asc) == the order torchvision.ops.nms's
@@ -1085,11 +1126,37 @@ static int launch_pool(gt_engine* e, const MaxpoolOp& po, int B, cudaStream_t st
   return GT_OK;
 }
 
+// the SPPF pools: in = slice i, out = slice i + 1 of one buffer, three in a row -> one fused launch when the plane fits shared memory
+static bool sppf_chain(const std::vector<PlanOp>& plan, size_t i) {
+  if (i + 2 >= plan.size()) return false;
+  for (int k = 0; k < 3; ++k) {
+    const PlanOp& p = plan[i + k];
+    if (p.type != OP_MAXPOOL || p.pool.in.ptr != plan[i].pool.in.ptr || p.pool.out.ptr != p.pool.in.ptr || p.pool.in.C != plan[i].pool.in.C ||
+        p.pool.in.coff != plan[i].pool.in.coff + k * p.pool.in.C || p.pool.out.coff != p.pool.in.coff + p.pool.in.C)
+      return false;
+  }
+  return (size_t)plan[i].pool.in.H * plan[i].pool.in.W * 32 <= 200 * 1024 && (plan[i].pool.in.C % 8) == 0;
+}
+
 int detector_forward(gt_engine* e, int B, cudaStream_t st) {
   GT_CHECK(e, e->weights_loaded, "detect: weights not loaded");
-  for (const PlanOp& po : e->plan) {
+  for (size_t pi = 0; pi < e->plan.size(); ++pi) {
+    const PlanOp& po = e->plan[pi];
     if (po.type == OP_CONV) GT_TRY(conv_tc_launch(e, &e->conv_ops[po.conv], B, st));
-    else GT_TRY(launch_pool(e, po.pool, B, st));
+    else if (sppf_chain(e->plan, pi)) {
+      const View& v = po.pool.in;
+      const size_t smem = (size_t)v.H * v.W * 32;
+      dim3 g((unsigned)(v.C / 8), (unsigned)B);
+      if (e->cfg.act_dtype == GT_ACT_FP16) {
+        GT_CUDA(e, cudaFuncSetAttribute(sppf_pool3_kernel<__half2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        sppf_pool3_kernel<__half2><<<g, 256, smem, st>>>(v.ptr, v.ctot, v.coff, v.C, v.H, v.W);
+      } else {
+        GT_CUDA(e, cudaFuncSetAttribute(sppf_pool3_kernel<__nv_bfloat162>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        sppf_pool3_kernel<__nv_bfloat162><<<g, 256, smem, st>>>(v.ptr, v.ctot, v.coff, v.C, v.H, v.W);
+      }
+      e->launches++;
+      pi += 2;
+    } else GT_TRY(launch_pool(e, po.pool, B, st));
   }
   GT_CUDA(e, cudaGetLastError());
   return GT_OK;
