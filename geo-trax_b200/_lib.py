@@ -8,6 +8,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libgeotrax_b200.so")
 
 GT_ABI_VERSION = 1
+GT_INPUT_BGR24, GT_INPUT_NV12 = 0, 1
 GT_TASK_DETECT, GT_TASK_OBB = 0, 1
 GT_ACT_BF16, GT_ACT_FP16 = 0, 1
 GT_MAX_KP = 8192
@@ -52,6 +53,7 @@ SYMBOLS = {
     "gt_preprocess": (_i, [_H, _P, _i, _P]),
     "gt_prefetch_frames": (_i, [_H, _P, _i]),
     "gt_prefetch_frames_deferred": (_i, [_H, _P, _i]),
+    "gt_set_input_format": (_i, [_H, _i]),
     "gt_get_net_input": (_i, [_H, _i, _P, _ip, _ip]),
     "gt_get_gray": (_i, [_H, _i, _P, _ip, _ip]),
     "gt_detect": (_i, [_H, _i, _f, _f, _i, _u, _P, _P, _P, _P]),

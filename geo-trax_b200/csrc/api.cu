@@ -207,6 +207,21 @@ int gt_load_weights(gt_handle e, const float* const* weights, const float* const
   return GT_OK;
 }
 
+static size_t frame_bytes(const gt_engine* e) {
+  const size_t px = (size_t)e->cfg.frame_h * e->cfg.frame_w;
+  return e->input_format == GT_INPUT_NV12 ? px * 3 / 2 : px * 3;
+}
+
+int gt_set_input_format(gt_handle e, int format) {
+  ENTER(e);
+  GT_CHECK(e, format == GT_INPUT_BGR24 || format == GT_INPUT_NV12, "gt_set_input_format: unknown format %d", format);
+  GT_CHECK(e, format == GT_INPUT_BGR24 || ((e->cfg.frame_h % 2) == 0 && (e->cfg.frame_w % 2) == 0), "gt_set_input_format: NV12 needs even frame dimensions");
+  if (format == GT_INPUT_NV12 && !e->frames_bgr)
+    GT_TRY(e->dev_alloc((void**)&e->frames_bgr, (size_t)e->cfg.max_batch * e->cfg.frame_h * e->cfg.frame_w * 3));
+  e->input_format = format;
+  return GT_OK;
+}
+
 // Starts the host->device copy of a batch on the copy stream into the idle staging buffer; a later gt_preprocess /
 // gt_extract_batch with the same `frames` pointer consumes it instead of copying.  Overlaps PCIe ingest with compute.
 int gt_prefetch_frames(gt_handle e, const uint8_t* frames, int B) {
@@ -219,7 +234,7 @@ int gt_prefetch_frames(gt_handle e, const uint8_t* frames, int B) {
   uint8_t* dst = k ? e->frames_dev2 : e->frames_dev;
   GT_CUDA(e, cudaStreamWaitEvent(e->copy_stream, e->ev_consumed[k], 0));   // the kernel that last read this buffer is done
   // one copy per frame: small uploads of the running batch (mask boxes) are not stuck behind one 400 MB transfer
-  const size_t fb = (size_t)e->cfg.frame_h * e->cfg.frame_w * 3;
+  const size_t fb = frame_bytes(e);
   for (int b = 0; b < B; ++b) GT_CUDA(e, cudaMemcpyAsync(dst + b * fb, frames + b * fb, fb, cudaMemcpyHostToDevice, e->copy_stream));
   GT_CUDA(e, cudaEventRecord(e->ev_copied[k], e->copy_stream));
   e->prefetched_src[k] = frames;
@@ -258,10 +273,15 @@ int gt_preprocess(gt_handle e, const uint8_t* frames, int B, void* stream) {
       }
       e->prefetch_next = used ^ 1;
       GT_CUDA(e, cudaStreamWaitEvent(st, e->ev_consumed[used], 0));
-      const size_t bytes = (size_t)B * e->cfg.frame_h * e->cfg.frame_w * 3;
+      const size_t bytes = (size_t)B * frame_bytes(e);
       GT_TRY(to_device(e, used ? e->frames_dev2 : e->frames_dev, frames, bytes, st));
     }
     src = used ? e->frames_dev2 : e->frames_dev;
+  }
+  if (e->input_format == GT_INPUT_NV12) {   // decoder-format ingest: NV12 -> BGR24 on the device, then the BGR path
+    GT_TRY(detector_nv12_to_bgr(e, src, e->frames_bgr, B, st));
+    if (used >= 0) { GT_CUDA(e, cudaEventRecord(e->ev_consumed[used], st)); used = -1; }   // the staging buffer is free already
+    src = e->frames_bgr;
   }
   GT_TRY(detector_preprocess(e, src, B, st));
   if (used >= 0) GT_CUDA(e, cudaEventRecord(e->ev_consumed[used], st));

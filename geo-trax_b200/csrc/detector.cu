@@ -182,6 +182,44 @@ int detector_build_general_preprocess(gt_engine* e) {
   return GT_OK;
 }
 
+// ---- NV12 -> BGR24 (decoder-format ingest): OpenCV's cvtColor(COLOR_YUV2BGR_NV12) integer arithmetic, bit-exact ----------------
+// One thread = 2 x 2 luma pixels sharing one (U, V) pair: reads 2 + 2 luma bytes and 2 chroma bytes, writes 2 x 6 BGR bytes.
+__global__ void __launch_bounds__(256) nv12_to_bgr_kernel(const uint8_t* __restrict__ nv12, uint8_t* __restrict__ bgr, int B, int H, int W) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int hw2 = W >> 1, hh2 = H >> 1;
+  const long long per_frame = (long long)hw2 * hh2;
+  if (idx >= per_frame * B) return;
+  const int b = (int)(idx / per_frame);
+  const int rem = (int)(idx - (long long)b * per_frame);
+  const int y2 = rem / hw2, x2 = rem - y2 * hw2;
+  const uint8_t* f = nv12 + (size_t)b * H * W * 3 / 2;
+  const uint8_t* uvp = f + (size_t)H * W + (size_t)y2 * W + 2 * x2;
+  const int u = (int)uvp[0] - 128, v = (int)uvp[1] - 128;
+  constexpr int CY = 1220542, CUB = 2116026, CUG = -409993, CVG = -852492, CVR = 1673527, SH = 20;
+  const int ruv = (1 << (SH - 1)) + CVR * v, guv = (1 << (SH - 1)) + CVG * v + CUG * u, buv = (1 << (SH - 1)) + CUB * u;
+  uint8_t* o = bgr + (size_t)b * H * W * 3;
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    const uint8_t* yp = f + (size_t)(2 * y2 + r) * W + 2 * x2;
+    uint8_t* op = o + ((size_t)(2 * y2 + r) * W + 2 * x2) * 3;
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+      const int yy = max(0, (int)yp[c] - 16) * CY;
+      op[c * 3 + 0] = (uint8_t)min(max((yy + buv) >> SH, 0), 255);
+      op[c * 3 + 1] = (uint8_t)min(max((yy + guv) >> SH, 0), 255);
+      op[c * 3 + 2] = (uint8_t)min(max((yy + ruv) >> SH, 0), 255);
+    }
+  }
+}
+
+int detector_nv12_to_bgr(gt_engine* e, const uint8_t* nv12_dev, uint8_t* bgr_dev, int B, cudaStream_t st) {
+  const long long n = (long long)B * (e->cfg.frame_h / 2) * (e->cfg.frame_w / 2);
+  nv12_to_bgr_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(nv12_dev, bgr_dev, B, e->cfg.frame_h, e->cfg.frame_w);
+  e->launches++;
+  GT_CUDA(e, cudaGetLastError());
+  return GT_OK;
+}
+
 __global__ void fill_s2d_kernel(uint2* __restrict__ s2d, size_t n_quads, uint32_t w0, uint32_t w1) {
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n_quads) s2d[i] = make_uint2(w0, w1);

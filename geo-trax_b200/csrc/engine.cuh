@@ -69,6 +69,8 @@ struct gt_engine {
   int prefetch_next = 0;
   const uint8_t* deferred_src = nullptr;   // gt_prefetch_frames_deferred: started by the next gt_extract_batch
   int deferred_B = 0;
+  int input_format = 0;                 // GT_INPUT_BGR24 | GT_INPUT_NV12 (gt_set_input_format)
+  uint8_t* frames_bgr = nullptr;        // NV12 ingest: device BGR24 frames produced by nv12_to_bgr_kernel (allocated on first use)
   bool pre_fast = true;                 // exact-1/2 letterbox + 1/2 working image with 16-pixel-aligned rows: the fused vector kernel; else the table-driven general kernels
   int* lb_tab[8] = {};                  // letterbox resize tables (x0, x1, a0, a1, y0, y1, b0, b1), see detector.cu
   int* gw_tab[8] = {};                  // gray working-image resize tables
@@ -161,6 +163,7 @@ int detector_load_weights(gt_engine* e, const float* const* w, const float* cons
 int detector_autotune(gt_engine* e, cudaStream_t st);
 int detector_fill_pad(gt_engine* e, cudaStream_t st);
 int detector_build_general_preprocess(gt_engine* e);
+int detector_nv12_to_bgr(gt_engine* e, const uint8_t* nv12_dev, uint8_t* bgr_dev, int B, cudaStream_t st);
 int detector_preprocess(gt_engine* e, const uint8_t* frames_dev, int B, cudaStream_t st);
 int detector_forward(gt_engine* e, int B, cudaStream_t st);
 int detector_postprocess(gt_engine* e, int B, float conf, float iou, int agnostic, uint32_t classes_mask, cudaStream_t st);

@@ -114,6 +114,12 @@ class Engine:
         self._ck(self.lib.gt_preprocess(self.h, _ptr(frames), B, stream))
         return B
 
+    def set_input_format(self, fmt: str = "bgr24"):
+        """'bgr24' (default: what the reference's reader delivers) or 'nv12' (decoder format: u8 [B][H * 3 / 2][W], half the PCIe bytes;
+        converted on the device with cv2.cvtColor(COLOR_YUV2BGR_NV12) arithmetic)."""
+        self._ck(self.lib.gt_set_input_format(self.h, {"bgr24": _lib.GT_INPUT_BGR24, "nv12": _lib.GT_INPUT_NV12}[fmt]))
+        self.input_format = fmt
+
     def prefetch(self, frames, deferred=False):
         """Start the H2D copy of a pinned host batch; the next preprocess / extract_batch on the same buffer consumes it.
         deferred=True: the copy is started inside the next extract_batch, after that call's own small uploads."""

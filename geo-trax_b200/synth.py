@@ -114,3 +114,15 @@ def make_frames(n: int, h: int = 2160, w: int = 3840, seed: int = 0, n_vehicles:
     """(n, h, w, 3) u8 BGR batch (bench input)."""
     frames, _, _ = make_flight(n, h, w, seed, n_vehicles)
     return np.stack(frames)
+
+
+def bgr_to_nv12(frame_bgr: np.ndarray) -> np.ndarray:
+    """BGR24 -> NV12 (u8 [H * 3 / 2][W]: Y plane, then interleaved U, V rows) through cv2: synthetic input for the decoder-format ingest."""
+    import cv2
+    h, w = frame_bgr.shape[:2]
+    i420 = cv2.cvtColor(frame_bgr, cv2.COLOR_BGR2YUV_I420)
+    flat, q = i420.reshape(-1), (h // 2) * (w // 2)
+    out = np.empty((h * 3 // 2, w), np.uint8)
+    out[:h] = i420[:h]
+    out[h:] = np.stack([flat[h * w:h * w + q].reshape(h // 2, w // 2), flat[h * w + q:h * w + 2 * q].reshape(h // 2, w // 2)], -1).reshape(h // 2, w)
+    return out

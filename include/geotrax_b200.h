@@ -100,6 +100,13 @@ int gt_preprocess(gt_handle h, const uint8_t* frames, int B, void* stream);
 int gt_prefetch_frames(gt_handle h, const uint8_t* frames, int B);
 /* same, started by the next gt_extract_batch right after it has queued its own small inputs (mask boxes) */
 int gt_prefetch_frames_deferred(gt_handle h, const uint8_t* frames, int B);
+/* Decoder-format ingest (what NVDEC / any H.26x decoder emits, half the bytes of BGR24 over PCIe).  After
+ * gt_set_input_format(h, GT_INPUT_NV12) every `frames` argument of gt_preprocess / gt_prefetch_frames* / gt_extract_batch is
+ * u8 NV12: [B][frame_h * 3 / 2][frame_w] (Y plane, then interleaved U,V at half resolution); frame_h and frame_w must be even.
+ * The frames are converted on the device to the BGR24 the rest of the path (and the reference, extract.py:146 reader.read())
+ * works on, with OpenCV's cvtColor(COLOR_YUV2BGR_NV12) integer arithmetic (ITU-R BT.601 limited range, 20-bit fixed point).   */
+enum { GT_INPUT_BGR24 = 0, GT_INPUT_NV12 = 1 };
+int gt_set_input_format(gt_handle h, int format);
 /* debug/parity read-back: letterboxed planar RGB u8 [B][3][net_h][net_w] (the 1/255 scale is folded into layer 0's
  * f32 weights, so the network input is exact) and u8 gray [B][work_h][work_w] */
 int gt_get_net_input(gt_handle h, int B, uint8_t* out_u8, int32_t* net_h, int32_t* net_w);

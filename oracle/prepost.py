@@ -83,6 +83,38 @@ def resize_linear_u8(img: np.ndarray, new_w: int, new_h: int) -> np.ndarray:
     return out if img.ndim == 3 else out[..., 0]
 
 
+def nv12_to_bgr(nv12: np.ndarray) -> np.ndarray:
+    """Integer restatement of ``cv2.cvtColor(nv12, cv2.COLOR_YUV2BGR_NV12)`` (OpenCV imgproc/src/color_yuv.simd.hpp, ITU-R BT.601 limited
+    range, 20-bit fixed point): nv12 is u8 [H * 3 / 2][W] (Y plane, then interleaved U, V rows at half resolution).  The decoder-format
+    ingest of the CUDA path (gt_set_input_format(GT_INPUT_NV12)) follows this function; pinned against cv2 in
+    tests/test_oracle_model.py::test_nv12_restatement_matches_cv2.  (The reference's reader converts with FFmpeg swscale, whose rounding
+    is not reproducible here: this ingest is SURVEY 8f rank 1, next to -- not inside -- the drop-in path.)"""
+    h = nv12.shape[0] * 2 // 3
+    w = nv12.shape[1]
+    y = nv12[:h].astype(np.int64)
+    uv = nv12[h:].reshape(h // 2, w // 2, 2).astype(np.int64)
+    u = np.repeat(np.repeat(uv[..., 0], 2, 0), 2, 1) - 128
+    v = np.repeat(np.repeat(uv[..., 1], 2, 0), 2, 1) - 128
+    cy, cub, cug, cvg, cvr, sh = 1220542, 2116026, -409993, -852492, 1673527, 20
+    yy = np.maximum(0, y - 16) * cy
+    half = 1 << (sh - 1)
+    r, g, b = (yy + half + cvr * v) >> sh, (yy + half + cvg * v + cug * u) >> sh, (yy + half + cub * u) >> sh
+    return np.stack([b, g, r], -1).clip(0, 255).astype(np.uint8)
+
+
+def bgr_to_nv12(frame_bgr: np.ndarray) -> np.ndarray:
+    """Test helper: BGR24 -> NV12 through cv2 (I420, then U and V interleaved)."""
+    h, w = frame_bgr.shape[:2]
+    i420 = cv2.cvtColor(frame_bgr, cv2.COLOR_BGR2YUV_I420)
+    out = np.empty((h * 3 // 2, w), np.uint8)
+    out[:h] = i420[:h]
+    flat, q = i420.reshape(-1), (h // 2) * (w // 2)
+    u = flat[h * w:h * w + q].reshape(h // 2, w // 2)
+    v = flat[h * w + q:h * w + 2 * q].reshape(h // 2, w // 2)
+    out[h:] = np.stack([u, v], -1).reshape(h // 2, w)
+    return out
+
+
 def preprocess(frames_bgr: Sequence[np.ndarray], imgsz: int = 1920) -> torch.Tensor:
     """list of u8 HWC BGR -> f32 NCHW RGB in [0,1]."""
     im = np.stack([letterbox_u8(f, imgsz) for f in frames_bgr])

@@ -67,6 +67,31 @@ def test_preprocess_general_geometry_bit_exact(hw, imgsz, ratio):
         eng.close()
 
 
+@pytest.mark.parametrize("hw,imgsz", [((512, 768), 384), ((380, 676), 480)])
+def test_nv12_ingest_bit_exact(hw, imgsz):
+    """Decoder-format ingest (gt_set_input_format(GT_INPUT_NV12)): network input and gray working image equal the BGR path fed with
+    cv2.cvtColor(COLOR_YUV2BGR_NV12) of the same NV12 frames -- bit for bit, for the fused default kernel and the general kernels."""
+    import cv2
+    import geotrax_b200
+    from oracle import prepost
+    eng = geotrax_b200.Engine(frame_hw=hw, imgsz=imgsz, nc=4, max_batch=2, max_det=100, max_features=300)
+    try:
+        rng = np.random.default_rng(3)
+        nv12 = rng.integers(0, 256, (2, hw[0] * 3 // 2, hw[1]), dtype=np.uint8)
+        bgr = np.stack([cv2.cvtColor(f, cv2.COLOR_YUV2BGR_NV12) for f in nv12])
+        assert np.array_equal(bgr[0], prepost.nv12_to_bgr(nv12[0]))
+        eng.set_input_format("nv12")
+        eng.preprocess(nv12)
+        got, gray = eng.net_input(2), eng.gray(2)
+        ref = prepost.preprocess(list(bgr), imgsz).numpy()
+        assert np.array_equal(got.astype(np.float32) / np.float32(255.0), ref)
+        eng.set_input_format("bgr24")
+        eng.preprocess(bgr)
+        assert np.array_equal(eng.net_input(2), got) and np.array_equal(eng.gray(2), gray)
+    finally:
+        eng.close()
+
+
 CONV_CASES = [
     # (B, H, W, cin, cout, k, stride, act, residual, f32)
     (2, 32, 48, 64, 64, 1, 1, True, False, False),

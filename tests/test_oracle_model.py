@@ -140,3 +140,16 @@ def test_resize_linear_restatement_matches_cv2(shape, cn):
     img = rng.integers(0, 256, (h, w, 3) if cn == 3 else (h, w), dtype=np.uint8)
     ref = cv2.resize(img, (nw, nh), interpolation=cv2.INTER_LINEAR)
     assert np.array_equal(prepost.resize_linear_u8(img, nw, nh), ref)
+
+
+@pytest.mark.parametrize("hw", [(64, 96), (270, 480), (1080, 1920)])
+def test_nv12_restatement_matches_cv2(hw):
+    """oracle/prepost.py:nv12_to_bgr (the arithmetic of the CUDA decoder-format ingest) is bit-exact against cv2.cvtColor."""
+    import cv2
+    from oracle import prepost
+    rng = np.random.default_rng(hw[0])
+    nv12 = rng.integers(0, 256, (hw[0] * 3 // 2, hw[1]), dtype=np.uint8)
+    assert np.array_equal(prepost.nv12_to_bgr(nv12), cv2.cvtColor(nv12, cv2.COLOR_YUV2BGR_NV12))
+    frame = rng.integers(0, 256, hw + (3,), dtype=np.uint8)
+    rt = prepost.bgr_to_nv12(frame)                                    # helper layout check: Y plane + interleaved chroma
+    assert rt.shape == (hw[0] * 3 // 2, hw[1]) and np.array_equal(rt[:hw[0]], cv2.cvtColor(frame, cv2.COLOR_BGR2YUV_I420)[:hw[0]])
