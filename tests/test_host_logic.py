@@ -205,9 +205,10 @@ def test_increment_path(tmp_path):
 
 def test_stabilizer_rejects_unsupported_presets():
     from geotrax_b200 import Stabilizer
-    for kw in (dict(detector_name="sift"), dict(matcher_name="flann"), dict(clahe=True), dict(downsample_ratio=1.0), dict(transformation_type="affine")):
+    for kw in (dict(detector_name="sift"), dict(matcher_name="flann"), dict(clahe=True), dict(downsample_ratio=1.5), dict(downsample_ratio=0.0), dict(transformation_type="affine")):
         with pytest.raises(NotImplementedError):
             Stabilizer(**kw)
+    Stabilizer(downsample_ratio=1.0, mask_use=False, max_features=4000)     # the reference's second construction (tools/compare_av_detections_and_tune_filters.py:739)
     s = Stabilizer(rsift_eps=1e-8, brisk_threshold=130, viz=False, benchmark=False, gpu=False)      # the whole default.yaml block is accepted
     assert s.get_cur_trans_matrix() is None and s.transform_cur_boxes() is None and s.get_cur_num_keypoints() == (0, 0)
 
