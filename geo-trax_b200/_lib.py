@@ -72,6 +72,8 @@ SYMBOLS = {
     "gt_match": (_i, [_H, _P, _i, _P, _i, _P, _P, _P]),
     "gt_find_homography": (_i, [_H, _P, _P, _i, _f, _i, _P, _ip, _P]),
     "gt_extract_batch": (_i, [_H, _P, _i, _i, _f, _f, _i, _u, _P, _P, _i, _P, _P, _P, _P, _P, _P, _P]),
+    "gt_extract_batch_async": (_i, [_H, _P, _i, _i, _f, _f, _i, _u, _P, _P, _i, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "gt_wait": (_i, [_H, _i]),
     "gt_stage_times": (_i, [_H, _P]),
     "gt_launch_count": (C.c_int64, [_H]),
     "gt_conv_stack_stats": (_i, [_H, _P, _P]),

@@ -148,7 +148,10 @@ struct gt_engine {
   float* boxes_stab_dev = nullptr;                  // [B][max_det][4]
 
   // timing
-  cudaEvent_t ev[8];
+  cudaEvent_t ev_sets[2][8];            // two sets of stage-timing events: gt_extract_batch_async alternates between them
+  cudaEvent_t* ev = ev_sets[0];         // the set of the call being enqueued
+  cudaEvent_t ev_done[2] = {nullptr, nullptr};   // all work and read-backs of ticket k are complete
+  int async_ticket = 0;
   float stage_ms[4] = {0, 0, 0, 0};
   float conv_ms = 0;
   double conv_flops = 0;

@@ -270,8 +270,9 @@ class Engine:
         if pinned:
             import torch
             tmap = {np.float32: torch.float32, np.int32: torch.int32, np.float64: torch.float64}
-            self._keep = [torch.zeros(s, dtype=tmap[d]).pin_memory() for s, d in shapes.values()]
-            return {k: t.numpy() for k, t in zip(shapes, self._keep)}
+            ts = [torch.zeros(s, dtype=tmap[d]).pin_memory() for s, d in shapes.values()]
+            self._keep.extend(ts)
+            return {k: t.numpy() for k, t in zip(shapes, ts)}
         return {k: np.zeros(s, d) for k, (s, d) in shapes.items()}
 
     def pack_boxes(self, boxes: Sequence[Optional[np.ndarray]]):
@@ -285,16 +286,30 @@ class Engine:
         return bx, nb
 
     def extract_batch(self, frames, first_is_reference=False, conf=0.25, iou=0.7, agnostic=True, classes=None, out=None, stream=None,
-                      mask_boxes=None):
-        """mask_boxes: None (mask = own detections) or the (bx, nb) pair from pack_boxes() (numpy or device tensors)."""
+                      mask_boxes=None, sync=True):
+        """mask_boxes: None (mask = own detections) or the (bx, nb) pair from pack_boxes() (numpy or device tensors).
+        sync=False: pipelined form (gt_extract_batch_async) -- returns (outputs, ticket) at once; the outputs (allocate them with
+        alloc_outputs(pinned=True)) are valid after wait(ticket); at most two tickets in flight."""
         B = int(frames.shape[0])
         o = out or self.alloc_outputs()
         mb, mn = (mask_boxes if mask_boxes is not None else (None, None))
+        if not sync:
+            self._keep_async = (frames, mb, mn)
+            t = C.c_int32()
+            self._ck(self.lib.gt_extract_batch_async(self.h, _ptr(frames), B, int(first_is_reference), conf, iou, int(bool(agnostic)),
+                                                     classes_to_mask(classes), _ptr(mb), _ptr(mn), self.max_det,
+                                                     o["boxes"].ctypes.data, o["counts"].ctypes.data, o["boxes_stab"].ctypes.data, o["H"].ctypes.data,
+                                                     o["status"].ctypes.data, o["stats"].ctypes.data, stream, C.byref(t)))
+            return o, t.value
         self._ck(self.lib.gt_extract_batch(self.h, _ptr(frames), B, int(first_is_reference), conf, iou, int(bool(agnostic)), classes_to_mask(classes),
                                            _ptr(mb), _ptr(mn), self.max_det,
                                            o["boxes"].ctypes.data, o["counts"].ctypes.data, o["boxes_stab"].ctypes.data, o["H"].ctypes.data,
                                            o["status"].ctypes.data, o["stats"].ctypes.data, stream))
         return o
+
+    def wait(self, ticket: int):
+        """Block until the batch enqueued under `ticket` (extract_batch(sync=False)) is complete; its outputs are then valid."""
+        self._ck(self.lib.gt_wait(self.h, int(ticket)))
 
     # -- 16-bit activation helpers (bit patterns <-> float32) -----------------------------------------------------------------
     def act_to_f32(self, bits: np.ndarray) -> np.ndarray:

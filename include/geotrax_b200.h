@@ -173,6 +173,17 @@ int gt_extract_batch(gt_handle h, const uint8_t* frames, int B, int first_is_ref
                      int mask_stride, float* out_boxes, int32_t* out_counts,
                      float* out_boxes_stab, double* out_H, int32_t* out_status, int32_t* out_stats, void* stream);
 
+/* Pipelined form of gt_extract_batch: enqueues the kernels and the read-backs (the out_* buffers must be pinned host memory for the
+ * read-backs to be asynchronous) and returns a ticket (0 / 1) immediately; gt_wait(ticket) blocks until that batch's outputs are
+ * valid.  At most two tickets in flight.  Lets the caller enqueue batch i+1 before reading batch i, so the GPU does not idle
+ * between batches.                                                                                                  */
+int gt_extract_batch_async(gt_handle h, const uint8_t* frames, int B, int first_is_reference, float conf, float iou,
+                           int agnostic, uint32_t classes_mask, const float* mask_boxes, const int32_t* mask_nboxes,
+                           int mask_stride, float* out_boxes, int32_t* out_counts,
+                           float* out_boxes_stab, double* out_H, int32_t* out_status, int32_t* out_stats, void* stream,
+                           int32_t* ticket);
+int gt_wait(gt_handle h, int ticket);
+
 /* ---- instrumentation ---------------------------------------------------------------------------------------------
  * ms[0..3] = preprocess, inference, postprocess(decode+NMS), stabilize of the last call (fills Results.speed,
  * extract.py:155-156).  gt_launch_count: kernels launched by this handle since creation.                         */

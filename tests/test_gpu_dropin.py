@@ -213,3 +213,30 @@ def test_obb_task_end_to_end():
             assert int(out["status"][i]) == 0
     finally:
         eng.close()
+
+
+def test_async_pipeline_matches_sync():
+    """gt_extract_batch_async / gt_wait: two batches in flight give exactly the arrays of two synchronous calls."""
+    import geotrax_b200
+    from geotrax_b200 import synth, weights
+    hw, imgsz = (512, 768), 384
+    eng = geotrax_b200.Engine(frame_hw=hw, imgsz=imgsz, nc=4, max_batch=2, max_det=300, max_features=500)
+    try:
+        eng.load_weights(weights.fold(weights.random_state_dict(4, "detect", seed=0, frame_hw=hw, imgsz=imgsz, cls_bias=-4.0)))
+        frames, boxes, _ = synth.make_flight(5, hw[0], hw[1], seed=4, n_vehicles=12)
+        fr = np.stack(frames)
+        eng.extract_batch(fr[:1], first_is_reference=True, conf=0.05, mask_boxes=eng.pack_boxes(boxes[:1]))
+        ref = [{k: v.copy() for k, v in eng.extract_batch(fr[a:a + 2], conf=0.05, mask_boxes=eng.pack_boxes(boxes[a:a + 2])).items()} for a in (1, 3)]
+        outs = [eng.alloc_outputs(pinned=True), eng.alloc_outputs(pinned=True)]
+        masks = [eng.pack_boxes(boxes[a:a + 2]) for a in (1, 3)]
+        o0, t0 = eng.extract_batch(fr[1:3], conf=0.05, mask_boxes=masks[0], out=outs[0], sync=False)
+        o1, t1 = eng.extract_batch(fr[3:5], conf=0.05, mask_boxes=masks[1], out=outs[1], sync=False)
+        assert {t0, t1} == {0, 1}
+        eng.wait(t0)
+        eng.wait(t1)
+        for got, want in zip((o0, o1), ref):
+            for k in want:
+                assert np.array_equal(got[k], want[k]), k
+        assert eng.stage_times()["inference"] > 0
+    finally:
+        eng.close()
