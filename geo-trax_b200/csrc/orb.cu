@@ -206,7 +206,7 @@ __device__ __forceinline__ uint32_t arc9(const uint32_t* m) {
   return any;
 }
 
-__global__ void __launch_bounds__(256) fast_kernel(const uint8_t* __restrict__ img, size_t slab, int slot0, const FastLevels fl,
+__global__ void __launch_bounds__(256, 5) fast_kernel(const uint8_t* __restrict__ img, size_t slab, int slot0, const FastLevels fl,
                                                    unsigned int* __restrict__ cand, uint8_t* __restrict__ cscore, size_t cand_slab,
                                                    int* __restrict__ counts) {
   __shared__ __align__(16) uint8_t s_img[FT_SH][FT_SW];
