@@ -28,7 +28,8 @@ __device__ __forceinline__ long long clk_now() { long long t; asm volatile("mov.
 #endif
 namespace {
 
-constexpr int kSwThreads = 64 + kEpiWarps * 32;  // 320
+constexpr int kSwThreads = 64 + kEpiWarps * 32 + 32;  // 352: warp 0 + warp 10 TMA producers, warp 1 MMA issuer, warps 2..9 epilogue
+constexpr int kSwProd2 = kSwThreads / 32 - 1;         // the second producer warp (per-tap path only): boxes of alternate k-blocks
 constexpr int kSwMaxStages = 8;
 constexpr int kPx = 256;        // pixels per tile (GEMM N)
 constexpr int kCo = 128;        // output channels per tile (GEMM M)
@@ -195,7 +196,7 @@ __global__ void __launch_bounds__(kSwThreads, 1) conv_sw_kernel(const __grid_con
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_smem)), "r"(512) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
-  if (warp >= 2) {
+  if (warp >= 2 && warp < kSwProd2) {
     const int nb = p.n_tiles * kCo;
     for (int i = threadIdx.x - 64; i < nb; i += kEpiWarps * 32) s_bias[i] = p.bias[i];
   }
@@ -204,9 +205,11 @@ __global__ void __launch_bounds__(kSwThreads, 1) conv_sw_kernel(const __grid_con
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = *tmem_ptr_smem;
 
-  if (warp == 0) {
-    // ===== TMA producer (converged warp, elected lane issues) =====
-    if (p.b_resident) {
+  if (warp == 0 || (warp == kSwProd2 && !p.halo)) {
+    // ===== TMA producers (converged warps, elected lane issues).  The per-tap path is bound by how fast boxes are issued (~3.4 cycles
+    // per box row with one issuing warp, fewer with two CTAs), so two warps issue the boxes of alternate k-blocks. =====
+    const uint32_t pid = warp == 0 ? 0u : 1u;     // (halo path: warp 0 only)
+    if (p.b_resident && pid == 0u) {
       if (elect_one()) {
         const uint32_t bb = smem_u32(wres_bar);
         mbar_expect_tx(bb, (uint32_t)(p.num_kb * w_bytes));
@@ -216,7 +219,7 @@ __global__ void __launch_bounds__(kSwThreads, 1) conv_sw_kernel(const __grid_con
     }
     pdl_wait();   // everything above touched only this layer's constants; activations of the previous layer are read below
     const uint32_t tx_bytes = (uint32_t)stage_bytes;
-    uint32_t s = 0, ph = 0, ws = 0, wph = 0;
+    uint32_t s = 0, ph = 0, ws = 0, wph = 0, gk = 0;
     TileIter ti;
     ti.init(p, blockIdx.x, gridDim.x);
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ti.next(p)) {
@@ -252,19 +255,23 @@ __global__ void __launch_bounds__(kSwThreads, 1) conv_sw_kernel(const __grid_con
       int kb = 0;
       for (int dy = 0; dy < p.ksize; ++dy)
         for (int dx = 0; dx < p.ksize; ++dx)
-          for (int kc = 0; kc < p.kc_blocks; ++kc, ++kb) {
-            mbar_wait(smem_u32(&empty_bar[s]), ph ^ 1u);
-            if (elect_one()) {
-              const uint32_t fb = smem_u32(&full_bar[s]);
-              mbar_expect_tx(fb, tx_bytes);
-              uint8_t* sx = smem + (size_t)s * stage_bytes;
-              tma_load_4d(smem_u32(sx), &tmX, fb, kc * p.kb_elems, cx + dx, cy + dy, t.n);
-              if (!p.b_resident) tma_load_2d(smem_u32(sx + x_bytes), &tmW, fb, kb * p.kb_elems, m0);
+          for (int kc = 0; kc < p.kc_blocks; ++kc, ++kb, ++gk) {
+            if ((gk & 1u) == pid) {
+              mbar_wait(smem_u32(&empty_bar[s]), ph ^ 1u);
+              if (elect_one()) {
+                const uint32_t fb = smem_u32(&full_bar[s]);
+                mbar_expect_tx(fb, tx_bytes);
+                uint8_t* sx = smem + (size_t)s * stage_bytes;
+                tma_load_4d(smem_u32(sx), &tmX, fb, kc * p.kb_elems, cx + dx, cy + dy, t.n);
+                if (!p.b_resident) tma_load_2d(smem_u32(sx + x_bytes), &tmW, fb, kb * p.kb_elems, m0);
+              }
+              __syncwarp();
             }
-            __syncwarp();
             if (++s == (uint32_t)p.stages) { s = 0; ph ^= 1u; }
           }
     }
+  } else if (warp == kSwProd2) {
+    // halo path: the second producer warp has nothing to do
   } else if (warp == 1) {
     // ===== MMA issuer =====
     // The issue loop is written for the single issuing lane's latency: descriptors are (constant high word, running 32-bit low
