@@ -285,7 +285,13 @@ int gt_preprocess(gt_handle e, const uint8_t* frames, int B, void* stream) {
     }
     src = used ? e->frames_dev2 : e->frames_dev;
   }
-  if (e->input_format == GT_INPUT_NV12) {   // decoder-format ingest: NV12 -> BGR24 on the device, then the BGR path
+  if (e->input_format == GT_INPUT_NV12 && e->pre_fast && (e->cfg.frame_w % 32) == 0) {   // default geometry: fused NV12 -> letterbox + gray
+    GT_TRY(detector_preprocess_nv12(e, src, B, st));
+    if (used >= 0) GT_CUDA(e, cudaEventRecord(e->ev_consumed[used], st));
+    GT_CUDA(e, cudaEventRecord(e->ev[1], st));
+    return GT_OK;
+  }
+  if (e->input_format == GT_INPUT_NV12) {   // decoder-format ingest, any geometry: NV12 -> BGR24 on the device, then the BGR path
     GT_TRY(detector_nv12_to_bgr(e, src, e->frames_bgr, B, st));
     if (used >= 0) { GT_CUDA(e, cudaEventRecord(e->ev_consumed[used], st)); used = -1; }   // the staging buffer is free already
     src = e->frames_bgr;

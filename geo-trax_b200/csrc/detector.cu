@@ -212,6 +212,77 @@ __global__ void __launch_bounds__(256) nv12_to_bgr_kernel(const uint8_t* __restr
   }
 }
 
+// Fused NV12 ingest for the default geometry (exact 1/2 letterbox + 1/2 working image): one output pixel = one 2 x 2 luma block, which
+// shares ONE chroma pair, so a thread reads 2 x 16 luma + 16 chroma bytes for 8 output pixels (1.5 B per source pixel instead of the
+// 3 B of the BGR path) and no BGR frame is ever written.  Arithmetic = cvtColor(NV12 -> BGR) per source pixel, then exactly what
+// preprocess_half_kernel does (2 x 2 average; gray first, then its 2 x 2 average), so the result is bit-identical to the two-pass path.
+__global__ void __launch_bounds__(256) preprocess_nv12_half_kernel(const uint8_t* __restrict__ nv12, bf16* __restrict__ s2d, uint8_t* __restrict__ gray,
+                                                                   size_t gray_frame_stride, int B, int H, int W, int net_h, int net_w, int pad_top,
+                                                                   int pad_left, int new_h, int new_w, int fp16) {
+  const int groups = new_w >> 3;  // 8 output pixels per thread
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long per_frame = (long long)(new_h >> 1) * groups;
+  if (idx >= per_frame * B) return;
+  const int b = (int)(idx / per_frame);
+  const int rem = (int)(idx - (long long)b * per_frame);
+  const int oy2 = rem / groups, og = rem - oy2 * groups;
+  const uint8_t* f = nv12 + (size_t)b * H * W * 3 / 2;
+  constexpr int CY = 1220542, CUB = 2116026, CUG = -409993, CVG = -852492, CVR = 1673527, SH = 20;
+  __align__(16) uint32_t line[32];
+  __align__(8) uint8_t gy[2][8];
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {     // output row parity: source rows 4 oy2 + 2 r + {0, 1}, chroma row 2 oy2 + r
+    const uint4 y0 = __ldg(reinterpret_cast<const uint4*>(f + (size_t)(4 * oy2 + 2 * r) * W + og * 16));
+    const uint4 y1 = __ldg(reinterpret_cast<const uint4*>(f + (size_t)(4 * oy2 + 2 * r + 1) * W + og * 16));
+    const uint4 uv = __ldg(reinterpret_cast<const uint4*>(f + (size_t)H * W + (size_t)(2 * oy2 + r) * W + og * 16));
+    const uint8_t* a = reinterpret_cast<const uint8_t*>(&y0);
+    const uint8_t* c = reinterpret_cast<const uint8_t*>(&y1);
+    const uint8_t* q = reinterpret_cast<const uint8_t*>(&uv);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int u = (int)q[2 * j] - 128, v = (int)q[2 * j + 1] - 128;
+      const int ruv = (1 << (SH - 1)) + CVR * v, guv = (1 << (SH - 1)) + CVG * v + CUG * u, buv = (1 << (SH - 1)) + CUB * u;
+      uint32_t bs = 0, gs = 0, rs = 0, ys = 0;
+      const int yv[4] = {a[2 * j], a[2 * j + 1], c[2 * j], c[2 * j + 1]};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int yy = max(0, yv[k] - 16) * CY;
+        const uint32_t bb = (uint32_t)min(max((yy + buv) >> SH, 0), 255), gg = (uint32_t)min(max((yy + guv) >> SH, 0), 255),
+                       rr = (uint32_t)min(max((yy + ruv) >> SH, 0), 255);
+        bs += bb; gs += gg; rs += rr; ys += gray15(bb, gg, rr);
+      }
+      const int w0 = (j >> 2) * 16 + (r * 4 + (j & 3)) * 2;
+      line[w0] = pack2_act((float)((rs + 2) >> 2), (float)((gs + 2) >> 2), fp16);
+      line[w0 + 1] = pack2_act((float)((bs + 2) >> 2), 0.f, fp16);
+      gy[r][j] = (uint8_t)((ys + 2) >> 2);
+    }
+  }
+  const int sh = net_h >> 2, sw = net_w >> 2;
+  const int ly = 2 * oy2 + pad_top, Y = ly >> 2, rb = ly & 3, X = (og * 8 + pad_left) >> 2;
+#pragma unroll
+  for (int blk = 0; blk < 2; ++blk) {
+    uint4* dst = reinterpret_cast<uint4*>(s2d + (((size_t)b * sh + Y) * sw + X + blk) * 64 + rb * 16);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) dst[i] = reinterpret_cast<const uint4*>(line)[blk * 4 + i];
+  }
+  if (gray) {
+    uint8_t* g = gray + (size_t)b * gray_frame_stride + (size_t)(2 * oy2) * new_w + og * 8;
+    *reinterpret_cast<uint2*>(g) = *reinterpret_cast<const uint2*>(gy[0]);
+    *reinterpret_cast<uint2*>(g + new_w) = *reinterpret_cast<const uint2*>(gy[1]);
+  }
+}
+
+int detector_preprocess_nv12(gt_engine* e, const uint8_t* nv12_dev, int B, cudaStream_t st) {
+  const long long threads = (long long)B * (e->new_h / 2) * (e->new_w / 8);
+  preprocess_nv12_half_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(nv12_dev, e->net_s2d, e->pyr, e->pyr_bytes, B, e->cfg.frame_h, e->cfg.frame_w,
+                                                                                 e->net_h, e->net_w, e->pad_top, e->pad_left, e->new_h, e->new_w,
+                                                                                 e->cfg.act_dtype == GT_ACT_FP16);
+  e->launches++;
+  GT_CUDA(e, cudaGetLastError());
+  e->cur_frames = nullptr;
+  return GT_OK;
+}
+
 int detector_nv12_to_bgr(gt_engine* e, const uint8_t* nv12_dev, uint8_t* bgr_dev, int B, cudaStream_t st) {
   const long long n = (long long)B * (e->cfg.frame_h / 2) * (e->cfg.frame_w / 2);
   nv12_to_bgr_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(nv12_dev, bgr_dev, B, e->cfg.frame_h, e->cfg.frame_w);

@@ -166,6 +166,7 @@ int detector_load_weights(gt_engine* e, const float* const* w, const float* cons
 int detector_autotune(gt_engine* e, cudaStream_t st);
 int detector_fill_pad(gt_engine* e, cudaStream_t st);
 int detector_build_general_preprocess(gt_engine* e);
+int detector_preprocess_nv12(gt_engine* e, const uint8_t* nv12_dev, int B, cudaStream_t st);   // fused (default geometry only)
 int detector_nv12_to_bgr(gt_engine* e, const uint8_t* nv12_dev, uint8_t* bgr_dev, int B, cudaStream_t st);
 int detector_preprocess(gt_engine* e, const uint8_t* frames_dev, int B, cudaStream_t st);
 int detector_forward(gt_engine* e, int B, cudaStream_t st);
