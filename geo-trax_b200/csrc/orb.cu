@@ -110,7 +110,7 @@ __global__ void __launch_bounds__(128) pyr_resize_kernel(uint8_t* __restrict__ p
 }
 
 // ---- FAST-9/16 score + 3x3 non-max suppression + border filter -> candidate list --------------------------------------------
-// One launch covers all pyramid levels (blockIdx.x walks the 64 x 32 tiles of every level's candidate region
+// One launch covers all pyramid levels (blockIdx.x walks the 64 x 64 tiles of every level's candidate region
 // [kEdge, w - kEdge) x [kEdge, h - kEdge); blockIdx.y = frame slot).  Per tile:
 //   0. stage the tile + apron in shared memory with aligned 32-bit global loads (rows of the pyramid have arbitrary alignment: two
 //      aligned words + a funnel shift per staged word);
@@ -123,7 +123,7 @@ __global__ void __launch_bounds__(128) pyr_resize_kernel(uint8_t* __restrict__ p
 // The vehicle mask is NOT applied here (it depends on the detections, which are computed concurrently): orb_select_kernel
 // drops masked candidates before its score cut, which is equivalent to OpenCV's order (mask, then retain-best).
 #define FT_X 64
-#define FT_Y 32
+#define FT_Y 64
 #define FT_SW 76                         // staged columns: gx in [x0 - 5, x0 + 71)
 #define FT_SH (FT_Y + 8)                 // staged rows:    gy in [y0 - 4, y0 + 36)
 #define FT_G 17                          // 4-pixel groups per tested row: sx = 4 g + j, gx = x0 - 1 + sx
