@@ -426,9 +426,34 @@ __global__ void __launch_bounds__(1024) orb_select_kernel(const uint8_t* __restr
   __syncthreads();
   if (threadIdx.x == 0) s_nu = 0;
   __syncthreads();
+  // The loop is latency bound (candidate -> mask address -> mask byte): four candidates per thread are in flight at a time, the
+  // mask verdicts are kept as a per-thread bit mask for pass (b), and lanes with equal scores merge their histogram updates.
   int my_unmasked = 0;
-  for (int i = threadIdx.x; i < n; i += blockDim.x)
-    if (unmasked(cxy[i])) { atomicAdd(&s_hist[csc[i]], 1); ++my_unmasked; }
+  unsigned long long um_bits = 0;       // bit j: this thread's j-th candidate (i = threadIdx.x + j * blockDim.x) is unmasked
+  const bool bits_ok = n <= 64 * (int)blockDim.x;
+  for (int i0 = threadIdx.x, j0 = 0; i0 < n; i0 += 4 * blockDim.x, j0 += 4) {
+    unsigned xy[4];
+    int sc[4];
+    bool um[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int i = i0 + u * blockDim.x;
+      xy[u] = i < n ? cxy[i] : 0u;
+      sc[u] = i < n ? (int)csc[i] : 0;
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) um[u] = (i0 + u * (int)blockDim.x < n) && unmasked(xy[u]);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const unsigned active = __ballot_sync(__activemask(), um[u]);
+      if (um[u]) {
+        const unsigned peers = __match_any_sync(active, sc[u]);
+        if ((int)(__ffs(peers) - 1) == (int)(threadIdx.x & 31)) atomicAdd(&s_hist[sc[u]], __popc(peers));
+        ++my_unmasked;
+        if (bits_ok) um_bits |= 1ull << (j0 + u);
+      }
+    }
+  }
   if (my_unmasked) atomicAdd(&s_nu, my_unmasked);
   __syncthreads();
   if (threadIdx.x == 0) {
@@ -446,8 +471,9 @@ __global__ void __launch_bounds__(1024) orb_select_kernel(const uint8_t* __restr
   __syncthreads();
   const int cut = s_cut;
   // (b) compact survivors + Harris response
-  for (int i = threadIdx.x; i < n; i += blockDim.x) {
-    if (csc[i] >= cut && unmasked(cxy[i])) {
+  for (int i = threadIdx.x, j = 0; i < n; i += blockDim.x, ++j) {
+    const bool um = bits_ok ? ((um_bits >> j) & 1ull) != 0 : unmasked(cxy[i]);
+    if (um && csc[i] >= cut) {
       const int k = atomicAdd(&s_m, 1);
       if (k < kSelCap) {
         const unsigned xy = cxy[i];
