@@ -372,16 +372,26 @@ __global__ void __launch_bounds__(256, 5) fast_kernel(const uint8_t* __restrict_
 
 // ---- per (frame, level): FAST-score cut (2 x quota, ties kept) -> Harris -> quota cut (ties kept) -> sort by position ------
 __device__ __forceinline__ float harris_at(const uint8_t* im, int w, int x0, int y0) {
+  // 7 x 7 block of 3 x 3 Sobel responses = a 9 x 9 window: three rows of nine pixels live in registers and slide down, so every
+  // pixel is loaded once (81 loads instead of 588; the loop was bound by its byte-load latency).  Integer sums: order-free, exact.
   int a = 0, b = 0, c = 0;
-  for (int dy = -3; dy <= 3; ++dy) {
-    const uint8_t* pm = im + (size_t)(y0 + dy - 1) * w + x0;
-    const uint8_t* p0 = pm + w;
-    const uint8_t* pp = p0 + w;
-    for (int dx = -3; dx <= 3; ++dx) {
-      const int Ix = ((int)p0[dx + 1] - (int)p0[dx - 1]) * 2 + ((int)pm[dx + 1] - (int)pm[dx - 1]) + ((int)pp[dx + 1] - (int)pp[dx - 1]);
-      const int Iy = ((int)pp[dx] - (int)pm[dx]) * 2 + ((int)pp[dx - 1] - (int)pm[dx - 1]) + ((int)pp[dx + 1] - (int)pm[dx + 1]);
+  int r0[9], r1[9], r2[9];
+  const uint8_t* p = im + (size_t)(y0 - 4) * w + (x0 - 4);
+#pragma unroll
+  for (int i = 0; i < 9; ++i) { r0[i] = p[i]; r1[i] = p[w + i]; }
+#pragma unroll
+  for (int dy = 0; dy < 7; ++dy) {
+    const uint8_t* q = p + (size_t)(dy + 2) * w;
+#pragma unroll
+    for (int i = 0; i < 9; ++i) r2[i] = q[i];
+#pragma unroll
+    for (int i = 1; i <= 7; ++i) {
+      const int Ix = (r1[i + 1] - r1[i - 1]) * 2 + (r0[i + 1] - r0[i - 1]) + (r2[i + 1] - r2[i - 1]);
+      const int Iy = (r2[i] - r0[i]) * 2 + (r2[i - 1] - r0[i - 1]) + (r2[i + 1] - r0[i + 1]);
       a += Ix * Ix; b += Iy * Iy; c += Ix * Iy;
     }
+#pragma unroll
+    for (int i = 0; i < 9; ++i) { r0[i] = r1[i]; r1[i] = r2[i]; }
   }
   const float scale = 1.0f / (4.0f * 7.0f * 255.0f);
   const float s2 = __fmul_rn(scale, scale), s4 = __fmul_rn(s2, s2);
