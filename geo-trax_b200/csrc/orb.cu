@@ -406,6 +406,39 @@ __device__ __forceinline__ unsigned f2key(float f) {  // order-preserving float 
   return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
 }
 
+// Warp-parallel "walk the 256-bin histogram from the top until `need` entries are covered": returns the bucket where the running
+// count reaches `need` and the count accumulated ABOVE that bucket (both in every lane); bucket = -1 if the total is below `need`.
+// Lane l owns buckets 255 - 8 l .. 248 - 8 l (descending), so lane order = descending bucket order.
+__device__ __forceinline__ void hist_cut_warp(const int* __restrict__ hist, int need, int* bucket, int* above) {
+  const int lane = threadIdx.x & 31;
+  int mine = 0;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) mine += hist[255 - 8 * lane - j];
+  int incl = mine;                              // inclusive prefix over lanes (descending buckets)
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int v = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += v;
+  }
+  const unsigned hit = __ballot_sync(0xffffffffu, incl >= need);
+  int bkt = -1, acc = 0;
+  if (hit) {
+    const int src = __ffs(hit) - 1;             // first lane whose running count reaches `need`
+    if (lane == src) {
+      acc = incl - mine;
+      for (int j = 0; j < 8; ++j) {
+        const int bb = 255 - 8 * lane - j;
+        if (acc + hist[bb] >= need) { bkt = bb; break; }
+        acc += hist[bb];
+      }
+    }
+    bkt = __shfl_sync(0xffffffffu, bkt, src);
+    acc = __shfl_sync(0xffffffffu, acc, src);
+  }
+  *bucket = bkt;
+  *above = acc;
+}
+
 __global__ void __launch_bounds__(1024) orb_select_kernel(const uint8_t* __restrict__ img, const uint8_t* __restrict__ msk, size_t slab, int slot0,
                                                           const OrbLevel* __restrict__ lv,
                                                           const unsigned int* __restrict__ cand, const uint8_t* __restrict__ cscore,
@@ -466,17 +499,15 @@ __global__ void __launch_bounds__(1024) orb_select_kernel(const uint8_t* __restr
   }
   if (my_unmasked) atomicAdd(&s_nu, my_unmasked);
   __syncthreads();
-  if (threadIdx.x == 0) {
+  if (threadIdx.x < 32) {
     int cut = 0;
     const int want = 2 * quota;
     if (s_nu > want) {
-      int acc = 0;
-      for (int s = 255; s >= 0; --s) {
-        acc += s_hist[s];
-        if (acc >= want) { cut = s; break; }
-      }
+      int bkt, above;
+      hist_cut_warp(s_hist, want, &bkt, &above);
+      cut = max(bkt, 0);
     }
-    s_cut = cut;
+    if (threadIdx.x == 0) s_cut = cut;
   }
   __syncthreads();
   const int cut = s_cut;
@@ -511,12 +542,11 @@ __global__ void __launch_bounds__(1024) orb_select_kernel(const uint8_t* __restr
         if ((k & himask) == (prefix & himask)) atomicAdd(&s_hist[(k >> shift) & 0xFF], 1);
       }
       __syncthreads();
-      if (threadIdx.x == 0) {
-        int need = s_need, acc = 0;
-        for (int bkt = 255; bkt >= 0; --bkt) {
-          if (acc + s_hist[bkt] >= need) { s_prefix = prefix | ((unsigned)bkt << shift); s_need = need - acc; break; }
-          acc += s_hist[bkt];
-        }
+      if (threadIdx.x < 32) {
+        int bkt, above;
+        const int need = s_need;
+        hist_cut_warp(s_hist, need, &bkt, &above);
+        if (threadIdx.x == 0 && bkt >= 0) { s_prefix = prefix | ((unsigned)bkt << shift); s_need = need - above; }
       }
       __syncthreads();
     }
