@@ -322,22 +322,23 @@ __device__ bool chol_solve8(double* A, double* rhs) {
     for (int k = 0; k < j; ++k) d -= A[j * 8 + k] * A[j * 8 + k];
     if (!(d > 1e-300)) return false;
     d = sqrt(d);
-    A[j * 8 + j] = d;
+    const double id = 1.0 / d;       // the solve runs on ONE thread: 8 divisions instead of 52
+    A[j * 8 + j] = id;               // the diagonal stores 1 / L_jj
     for (int i = j + 1; i < 8; ++i) {
       double v = A[i * 8 + j];
       for (int k = 0; k < j; ++k) v -= A[i * 8 + k] * A[j * 8 + k];
-      A[i * 8 + j] = v / d;
+      A[i * 8 + j] = v * id;
     }
   }
   for (int i = 0; i < 8; ++i) {
     double v = rhs[i];
     for (int k = 0; k < i; ++k) v -= A[i * 8 + k] * rhs[k];
-    rhs[i] = v / A[i * 8 + i];
+    rhs[i] = v * A[i * 8 + i];
   }
   for (int i = 7; i >= 0; --i) {
     double v = rhs[i];
     for (int k = i + 1; k < 8; ++k) v -= A[k * 8 + i] * rhs[k];
-    rhs[i] = v / A[i * 8 + i];
+    rhs[i] = v * A[i * 8 + i];
   }
   return true;
 }
@@ -417,7 +418,8 @@ __global__ void __launch_bounds__(256) ransac_finalize_kernel(const float4* __re
       const double x = q.x, y = q.y, u = q.z, v = q.w;
       const double w = h[6] * x + h[7] * y + h[8];
       if (!(w > 1e-9)) continue;
-      const double pu = (h[0] * x + h[1] * y + h[2]) / w, pv = (h[3] * x + h[4] * y + h[5]) / w;
+      const double iw = 1.0 / w;   // one double division per match instead of three
+      const double pu = (h[0] * x + h[1] * y + h[2]) * iw, pv = (h[3] * x + h[4] * y + h[5]) * iw;
       const double e2 = (pu - u) * (pu - u) + (pv - v) * (pv - v);
       if (!(e2 < tsel)) continue;
       const double wt = 1.0;
@@ -426,7 +428,6 @@ __global__ void __launch_bounds__(256) ransac_finalize_kernel(const float4* __re
         r0[0] = x; r0[1] = y; r0[2] = 1; r0[3] = 0; r0[4] = 0; r0[5] = 0; r0[6] = -u * x; r0[7] = -u * y; b0 = u;
         r1[0] = 0; r1[1] = 0; r1[2] = 0; r1[3] = x; r1[4] = y; r1[5] = 1; r1[6] = -v * x; r1[7] = -v * y; b1 = v;
       } else {
-        const double iw = 1.0 / w;
         r0[0] = x * iw; r0[1] = y * iw; r0[2] = iw; r0[3] = 0; r0[4] = 0; r0[5] = 0; r0[6] = -pu * x * iw; r0[7] = -pu * y * iw; b0 = u - pu;
         r1[0] = 0; r1[1] = 0; r1[2] = 0; r1[3] = x * iw; r1[4] = y * iw; r1[5] = iw; r1[6] = -pv * x * iw; r1[7] = -pv * y * iw; b1 = v - pv;
       }
@@ -464,7 +465,8 @@ __global__ void __launch_bounds__(256) ransac_finalize_kernel(const float4* __re
       const float4 q = np[i];
       const double w = h[6] * q.x + h[7] * q.y + h[8];
       if (!(w > 1e-9)) continue;
-      const double pu = (h[0] * q.x + h[1] * q.y + h[2]) / w, pv = (h[3] * q.x + h[4] * q.y + h[5]) / w;
+      const double iw = 1.0 / w;
+      const double pu = (h[0] * q.x + h[1] * q.y + h[2]) * iw, pv = (h[3] * q.x + h[4] * q.y + h[5]) * iw;
       if ((pu - q.z) * (pu - q.z) + (pv - q.w) * (pv - q.w) < t2) cnt[0] += 1.0;
     }
     block_sum<1>(cnt, s_buf, s_out);
