@@ -1,18 +1,21 @@
 // Swapped-operand tcgen05 implicit-GEMM convolution (sm_100a): D[cout][pixels] = W[cout][K] . X[pixels][K]^T.
 //
-// Why: with both operands in shared memory a K=16 tcgen05.mma with M = 128 costs ~130-150 cycles however small N is
-// (profiles/conv_findings_r1.md) -- its 4 KB A slice is read at ~32 B/clk.  YOLOv8s has cout in {32, 64, 128} on its large
-// feature maps, so "pixels as M, cout as N" (conv_tc.cu) leaves the pipe at 12-50 %.  Here the WEIGHTS are the A operand
-// (M = 128 output channels, zero rows above cout) and a 256-pixel spatial tile is the B operand (N = 256): one instruction
-// per 256 pixels x K16 instead of two, for every cout <= 128; cout > 128 runs ceil(cout / 128) M tiles.
+// Why: a 256-pixel tile as the GEMM N dimension halves the instruction count and the weight re-reads of the 3x3 layers with
+// cout >= 128 (one M128 x N256 x K16 tcgen05.mma = 135 cycles = 95 % of the pipe's nominal rate, tools/scratch/mma_bench.cu); the
+// WEIGHTS are the A operand (M = 128 output channels, zero rows above cout), the pixels the B operand; cout > 128 runs
+// ceil(cout / 128) M tiles.  (The first motivation written here -- "an MMA costs 130-150 cycles whatever N" -- was a measurement of
+// the old issue path, not of the pipe: profiles/round1_summary.md section 3.)  The per-layer autotuner picks this kernel for 17-24 of the
+// 60 launches, the pixel-major kernel (one or two CTAs per SM, with or without halo staging) for the rest.
 //
-// Same skeleton as conv_tc.cu: persistent CTA per SM, warp 0 TMA producer, warp 1 MMA issuer (elect.sync), warps 2..9
+// Same skeleton as conv_tc.cu: persistent CTA per SM, warps 0 and 10 TMA producers, warp 1 MMA issuer (elect.sync), warps 2..9
 // epilogue, shared-memory operand ring across tiles, two TMEM accumulators (2 x 256 columns = all of TMEM), weights resident
 // in shared memory when they fit.  The accumulator arrives transposed (TMEM lane = output channel, column = pixel), so the
 // epilogue thread owns ONE channel: bias is a register, and each value is written as a 2-byte (or 4-byte, fp32 head rows)
 // element into a [pixel][channel] staging granule in the TMA swizzle layout, stored with bulk tensor stores:
 //   16-bit: granule = 128 pixels x 64 channels (16 KB), filled by the two warps of a channel half; 4 granules per tile
 //   fp32  : granule = 32 pixels x 32 channels (4 KB), private to a warp, double-buffered
+//   cout <= 64: two-phase transposed epilogue (raw accumulators -> smem -> all warps finish them with thread = pixel), see below
+// Variant 2 (p.halo): one (8 + k - 1) x (32 + k - 1) pixel box per k-block, the k*k taps are row-shifted descriptors into it.
 #include <algorithm>
 
 #include "engine.cuh"

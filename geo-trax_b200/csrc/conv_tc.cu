@@ -19,6 +19,9 @@
 //                                 nearest-upsampled copy), or fp32 rows of the raw head tensor
 // so the epilogue of tile i overlaps the loads and MMAs of tile i+1 and the per-CTA prologue (barrier init, TMEM
 // allocation, descriptor prefetch) is paid once per SM instead of once per tile.
+// Variants (chosen per layer by detector_autotune): OCC = 2 compiles the kernel for two CTAs per SM (layers whose tiles carry little MMA
+// work are bound by the latency of the per-tile epilogue chain); p.halo stages one (8 + k - 1) x (16 + k - 1) pixel box per k-block and
+// reads the k*k taps through row-shifted UMMA descriptors (the per-tap path is bound by TMA box rows, ~3.4 cycles per row per SM).
 #include <algorithm>
 
 #include "engine.cuh"
