@@ -78,6 +78,7 @@ SYMBOLS = {
     "gt_launch_count": (C.c_int64, [_H]),
     "gt_conv_stack_stats": (_i, [_H, _P, _P]),
     "gt_conv_kernel_info": (_i, [_H, _ip, _ip]),
+    "gt_conv_pair_count": (_i, [_H]),
 }
 
 _lib = None

@@ -73,6 +73,7 @@ int gt_create(const gt_config* cfg, int device, gt_handle* out) {
   e->cfg = *cfg;
   e->device = device;
   if (const char* hm = getenv("GT_HALO")) e->halo_mode = atoi(hm);
+  if (const char* pm = getenv("GT_PAIR")) e->pair_mode = atoi(pm);
   if (const char* pd = getenv("GT_PDL")) e->pdl = atoi(pd);
   if (const char* sm = getenv("GT_SWAP")) e->swap_mode = atoi(sm);
   if (const char* ov = getenv("GT_OVERLAP")) e->overlap = atoi(ov);
@@ -830,6 +831,12 @@ int gt_conv_kernel_info(gt_handle e, int32_t* n_ops, int32_t* n_swapped) {
   if (n_ops) *n_ops = (int)e->conv_ops.size();
   if (n_swapped) *n_swapped = ns;
   return GT_OK;
+}
+int gt_conv_pair_count(gt_handle e) {
+  if (!e) return GT_ERR_INVALID;
+  int n = 0;
+  for (const ConvOp& op : e->conv_ops) n += op.pair;
+  return n;
 }
 int gt_conv_stack_stats(gt_handle e, float* ms, double* flops) {
   if (!e) return GT_ERR_INVALID;

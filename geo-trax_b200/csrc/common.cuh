@@ -112,6 +112,7 @@ struct ConvOp {
   float* b_dev = nullptr;    // [cout_pad]
   int cin = 0, cout = 0, cout_pad = 0, cin_pad = 0, k = 1, stride = 1;
   int occ2 = 0;              // 1: conv_tc.cu compiled for two CTAs per SM (variant 3)
+  int pair = 0;              // 1: conv_sw.cu as CTA pairs (cta_group::2, 256 channels x 256 pixels per pair tile; variant 6)
   int swapped = 0;           // 1: conv_sw.cu (weights = A operand, 256-pixel tile = B operand); tmA = activations, tmB = weights either way
   int n_src = 0;             // 1..3 canonical convs fused along cout
   int src[3] = {0, 0, 0};    // canonical conv indices

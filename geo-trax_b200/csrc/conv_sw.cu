@@ -63,12 +63,13 @@ struct MmaCtx {
   uint32_t hi_std, hi_halo;         // descriptor high words: SBO = 8 rows / SBO = halo row pitch
   uint32_t tmem_base, idesc;
 };
-template <int MPK>
+template <int MPK, int PAIR>
 __device__ __forceinline__ void mma_role(const ConvParams& p, const MmaCtx& c) {
   uint32_t s = 0, ph = 0, li = 0, s_lo = c.smem_lo;
   const int num_kb = p.num_kb;
   const bool res = p.b_resident != 0;
-  for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++li) {
+  const int first = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x, step = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  for (int tile = first; tile < p.total_tiles; tile += step, ++li) {
     const uint32_t as = li & 1u;
     mbar_wait(c.tempty_bar + as * 8u, ((li >> 1) & 1u) ^ 1u);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -78,15 +79,23 @@ __device__ __forceinline__ void mma_role(const ConvParams& p, const MmaCtx& c) {
       mbar_wait(c.full_bar + s * 8u, ph);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       if (elect_one()) {
-        issue_kb<MPK>(tacc, res ? w_lo : s_lo + c.x16, c.hi_std, s_lo, c.hi_std, c.idesc, kb ? 1u : 0u);
-        umma_commit(c.empty_bar + s * 8u);
+        if constexpr (PAIR) {   // one M = 256 MMA over both CTAs' operands; the stage is released in both CTAs
+          issue_kb_pair<MPK>(tacc, s_lo + c.x16, c.hi_std, s_lo, c.hi_std, c.idesc, kb ? 1u : 0u);
+          umma_commit_pair(c.empty_bar + s * 8u);
+        } else {
+          issue_kb<MPK>(tacc, res ? w_lo : s_lo + c.x16, c.hi_std, s_lo, c.hi_std, c.idesc, kb ? 1u : 0u);
+          umma_commit(c.empty_bar + s * 8u);
+        }
       }
       __syncwarp();
       w_lo += c.w16;
       s_lo += c.stage16;
       if (++s == (uint32_t)p.stages) { s = 0; ph ^= 1u; s_lo = c.smem_lo; }
     }
-    if (elect_one()) umma_commit(c.tfull_bar + as * 8u);
+    if (elect_one()) {
+      if constexpr (PAIR) umma_commit_pair(c.tfull_bar + as * 8u);
+      else umma_commit(c.tfull_bar + as * 8u);
+    }
     __syncwarp();
   }
 }
@@ -144,6 +153,12 @@ __device__ __forceinline__ void mma_role_halo(const ConvParams& p, const MmaCtx&
   }
 }
 
+// PAIR = 1 (variant 6, cout a multiple of 256, per-tap path): the kernel runs as clusters of two CTAs on one TPC.  A pair owns a
+// 256-channel x 256-pixel tile: each CTA stages its own 128 weight rows and its own half (th / 2 image rows) of the pixel tile, the
+// leader (cluster rank 0) issues M = 256 cta_group::2 MMAs that read both CTAs' shared memory, and each CTA's TMEM receives the
+// accumulator rows of its own 128 channels for all 256 pixels -- so the epilogue is the single-CTA one.  A stage is 32 KB instead of
+// 48 KB for the same MMA time: five or six ring stages, i.e. ~1.5x the load latency covered.
+template <int PAIR>
 __global__ void __launch_bounds__(kSwThreads, 1) conv_sw_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmX,
                                                                 const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ ConvUpMaps tmUp,
                                                                 const __grid_constant__ CUtensorMap tmRes, const ConvParams p) {
@@ -152,7 +167,10 @@ __global__ void __launch_bounds__(kSwThreads, 1) conv_sw_kernel(const __grid_con
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const int row_bytes = p.kb_elems * 2;
   const int w_bytes = kCo * row_bytes;          // A: 128 weight rows of one k-block
-  const int x_bytes = kPx * row_bytes;          // B: 256 pixel rows of one k-block
+  const int x_bytes = (PAIR ? kPx / 2 : kPx) * row_bytes;   // B: 256 pixel rows of one k-block (pair: this CTA's 128)
+  const uint32_t rank = PAIR ? cluster_ctarank() : 0u;
+  const int tile_first = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x, tile_step = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  constexpr int kCoTile = PAIR ? 2 * kCo : kCo;  // output channels per (pair) tile
   // halo mode (3x3 / 2x2 stride-1 layers, 8 x 32 pixel tiles): a ring stage holds ONE (tw + k - 1) x (th + k - 1) pixel box of a
   // k-block; the k*k taps are row-shifted UMMA descriptors into it (the swizzle XOR acts on absolute smem address bits, so any
   // whole-row shift and any row-multiple SBO address the bytes TMA wrote).  Weights are resident or flow through their own ring.
@@ -185,7 +203,7 @@ __global__ void __launch_bounds__(kSwThreads, 1) conv_sw_kernel(const __grid_con
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(smem_u32(&tfull_bar[s]), 1);
-      mbar_init(smem_u32(&tempty_bar[s]), kEpiWarps);
+      mbar_init(smem_u32(&tempty_bar[s]), PAIR ? 2 * kEpiWarps : kEpiWarps);   // pair: the leader's barrier collects both CTAs' epilogue warps
     }
     mbar_init(smem_u32(wres_bar), 1);
     for (int s = 0; s < 4; ++s) mbar_init(smem_u32(&res_bar[s]), 1);
@@ -196,15 +214,21 @@ __global__ void __launch_bounds__(kSwThreads, 1) conv_sw_kernel(const __grid_con
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_smem)), "r"(512) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if constexpr (PAIR) {   // warp 1 of both CTAs, same shared-memory offset
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_smem)), "r"(512) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_smem)), "r"(512) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
   }
   if (warp >= 2 && warp < kSwProd2) {
-    const int nb = p.n_tiles * kCo;
-    for (int i = threadIdx.x - 64; i < nb; i += kEpiWarps * 32) s_bias[i] = p.bias[i];
+    const int nb = p.n_tiles * kCo;   // (pair: s_bias keeps only this CTA's 128 channels of every 256-channel tile)
+    for (int i = threadIdx.x - 64; i < nb; i += kEpiWarps * 32) s_bias[i] = PAIR ? p.bias[(i >> 7) * kCoTile + (int)rank * kCo + (i & 127)] : p.bias[i];
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-  __syncthreads();
+  if constexpr (PAIR) { __syncthreads(); cluster_sync_all(); }   // the peer's barriers are initialised before anything signals them
+  else __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = *tmem_ptr_smem;
 
@@ -224,11 +248,11 @@ __global__ void __launch_bounds__(kSwThreads, 1) conv_sw_kernel(const __grid_con
     const uint32_t tx_bytes = (uint32_t)stage_bytes;
     uint32_t s = 0, ph = 0, ws = 0, wph = 0, gk = 0;
     TileIter ti;
-    ti.init(p, blockIdx.x, gridDim.x);
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ti.next(p)) {
+    ti.init(p, tile_first, tile_step);
+    for (int tile = tile_first; tile < total_tiles; tile += tile_step, ti.next(p)) {
       const TileCoord t = ti.coord(p);
-      const int m0 = ti.nt * kCo;
-      const int cx = t.x0 * p.stride - p.pad, cy = t.y0 * p.stride - p.pad;
+      const int m0 = ti.nt * kCoTile + (int)rank * kCo;
+      const int cx = t.x0 * p.stride - p.pad, cy = (t.y0 + (PAIR ? (int)rank * (p.th >> 1) : 0)) * p.stride - p.pad;
       if (p.halo) {
         const int taps = p.ksize * p.ksize;
         for (int kc = 0; kc < p.kc_blocks; ++kc) {
@@ -263,10 +287,17 @@ __global__ void __launch_bounds__(kSwThreads, 1) conv_sw_kernel(const __grid_con
               mbar_wait(smem_u32(&empty_bar[s]), ph ^ 1u);
               if (elect_one()) {
                 const uint32_t fb = smem_u32(&full_bar[s]);
-                mbar_expect_tx(fb, tx_bytes);
                 uint8_t* sx = smem + (size_t)s * stage_bytes;
-                tma_load_4d(smem_u32(sx), &tmX, fb, kc * p.kb_elems, cx + dx, cy + dy, t.n);
-                if (!p.b_resident) tma_load_2d(smem_u32(sx + x_bytes), &tmW, fb, kb * p.kb_elems, m0);
+                if constexpr (PAIR) {   // both CTAs' boxes are counted on the leader's barrier (the MMA reads both CTAs' stage s)
+                  const uint32_t fb0 = mapa_rank(fb, 0u);
+                  if (rank == 0u) mbar_expect_tx(fb, 2u * tx_bytes);
+                  tma_load_4d_pair(smem_u32(sx), &tmX, fb0, kc * p.kb_elems, cx + dx, cy + dy, t.n);
+                  tma_load_2d_pair(smem_u32(sx + x_bytes), &tmW, fb0, kb * p.kb_elems, m0);
+                } else {
+                  mbar_expect_tx(fb, tx_bytes);
+                  tma_load_4d(smem_u32(sx), &tmX, fb, kc * p.kb_elems, cx + dx, cy + dy, t.n);
+                  if (!p.b_resident) tma_load_2d(smem_u32(sx + x_bytes), &tmW, fb, kb * p.kb_elems, m0);
+                }
               }
               __syncwarp();
             }
@@ -275,6 +306,8 @@ __global__ void __launch_bounds__(kSwThreads, 1) conv_sw_kernel(const __grid_con
     }
   } else if (warp == kSwProd2) {
     // halo path: the second producer warp has nothing to do
+  } else if (warp == 1 && rank != 0u) {
+    // pair: only the leader CTA issues MMAs
   } else if (warp == 1) {
     // ===== MMA issuer =====
     // The issue loop is written for the single issuing lane's latency: descriptors are (constant high word, running 32-bit low
@@ -282,7 +315,7 @@ __global__ void __launch_bounds__(kSwThreads, 1) conv_sw_kernel(const __grid_con
     // separates consecutive tcgen05.mma.  (With general 64-bit descriptor code the issue block cost ~360 cycles per k-block --
     // more than the 2 x 135 cycles its MMAs take on the tensor pipe -- and the pipe idled half of the time.)
     const uint32_t fmt = p.fp16 ? 0u : 1u;
-    const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(kPx >> 3) << 17) | ((uint32_t)(kCo >> 4) << 24);
+    const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(kPx >> 3) << 17) | ((uint32_t)(kCoTile >> 4) << 24);
     if (p.b_resident) mbar_wait(smem_u32(wres_bar), 0);
     MmaCtx c;
     c.full_bar = smem_u32(full_bar); c.empty_bar = smem_u32(empty_bar); c.tfull_bar = smem_u32(tfull_bar); c.tempty_bar = smem_u32(tempty_bar);
@@ -294,11 +327,13 @@ __global__ void __launch_bounds__(kSwThreads, 1) conv_sw_kernel(const __grid_con
     c.hi_std = desc_hi(8u * (uint32_t)row_bytes, layout);
     c.hi_halo = desc_hi((uint32_t)((p.tw + p.ksize - 1) * row_bytes), layout);
     const int mpk = p.kb_elems >> 4;
-    if (p.halo) {
+    if constexpr (PAIR) {
+      if (mpk == 4) mma_role<4, 1>(p, c); else if (mpk == 2) mma_role<2, 1>(p, c); else mma_role<1, 1>(p, c);
+    } else if (p.halo) {
       if (p.ksize == 3) { if (mpk == 4) mma_role_halo<3, 4>(p, c); else if (mpk == 2) mma_role_halo<3, 2>(p, c); else mma_role_halo<3, 1>(p, c); }
       else { if (mpk == 4) mma_role_halo<2, 4>(p, c); else if (mpk == 2) mma_role_halo<2, 2>(p, c); else mma_role_halo<2, 1>(p, c); }
     } else {
-      if (mpk == 4) mma_role<4>(p, c); else if (mpk == 2) mma_role<2>(p, c); else mma_role<1>(p, c);
+      if (mpk == 4) mma_role<4, 0>(p, c); else if (mpk == 2) mma_role<2, 0>(p, c); else mma_role<1, 0>(p, c);
     }
   } else {
     // ===== epilogue =====
@@ -312,19 +347,24 @@ __global__ void __launch_bounds__(kSwThreads, 1) conv_sw_kernel(const __grid_con
     const uint32_t stg = smem_u32(staging);
     pdl_wait();   // residual reads and output stores below
     uint32_t li = 0, nstore = 0, res_uses = 0;
+    // accumulator `as` has been read by this warp (pair: counted on the leader's barrier, the leader's MMAs overwrite both CTAs' TMEM)
+    auto release_acc = [&](uint32_t as) {
+      if constexpr (PAIR) mbar_arrive_cluster(mapa_rank(smem_u32(&tempty_bar[as]), 0u));
+      else mbar_arrive(smem_u32(&tempty_bar[as]));
+    };
     TileIter ti;
-    ti.init(p, blockIdx.x, gridDim.x);
+    ti.init(p, tile_first, tile_step);
 #ifdef GT_SW_TIMING
     long long d_pre = 0, d_wait = 0, d_a = 0, d_b1 = 0, d_b = 0, d_b2 = 0;
 #endif
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++li, ti.next(p)) {
+    for (int tile = tile_first; tile < total_tiles; tile += tile_step, ++li, ti.next(p)) {
       TCK(c0);
       const uint32_t as = li & 1u;
       const TileCoord t = ti.coord(p);
-      const int m0 = ti.nt * kCo;
+      const int m0 = ti.nt * kCoTile + (int)rank * kCo;
       const int ch = m0 + q * 32 + lane;                 // this thread's output channel
       const bool warp_active = (m0 + q * 32) < p.cout;   // any valid channel in this lane quarter
-      const float bias = s_bias[min(ch, p.n_tiles * kCo - 1)];
+      const float bias = s_bias[PAIR ? ti.nt * kCo + q * 32 + lane : min(ch, p.n_tiles * kCo - 1)];
       const int ybase = t.y0 + h * half_rows;            // first image row of this pixel half
       const bool xpose = !p.out_f32 && p.cout <= 64;   // small cout: two-phase epilogue through a shared-memory transpose (below)
       const bool gran_active = !p.out_f32 && !xpose && (m0 + g * 64) < p.cout;
@@ -360,7 +400,7 @@ __global__ void __launch_bounds__(kSwThreads, 1) conv_sw_kernel(const __grid_con
 #if defined(GT_SW_EXP) && GT_SW_EXP == 1   // debug experiment: no epilogue at all (accumulator released at once)
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncwarp();
-      if (lane == 0) mbar_arrive(smem_u32(&tempty_bar[as]));
+      if (lane == 0) release_acc(as);
       continue;
 #endif
       const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + as * (uint32_t)kPx + (uint32_t)(h * 128);
@@ -397,7 +437,7 @@ __global__ void __launch_bounds__(kSwThreads, 1) conv_sw_kernel(const __grid_con
           if (st == steps - 1) {                            // accumulator fully read by this warp (or never needed)
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             __syncwarp();
-            if (lane == 0) mbar_arrive(smem_u32(&tempty_bar[as]));
+            if (lane == 0) release_acc(as);
           }
           TCK(c3);
           named_bar(6 + h, 128);                            // T complete; the leader's wait_group.read (granule free) is visible
@@ -480,7 +520,7 @@ __global__ void __launch_bounds__(kSwThreads, 1) conv_sw_kernel(const __grid_con
           if (c == 3) {                                   // accumulator fully read by this warp
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             __syncwarp();
-            if (lane == 0) mbar_arrive(smem_u32(&tempty_bar[as]));
+            if (lane == 0) release_acc(as);
           }
           if (!warp_active) continue;
           float f[32];
@@ -534,7 +574,7 @@ __global__ void __launch_bounds__(kSwThreads, 1) conv_sw_kernel(const __grid_con
           if (c == 3) {
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             __syncwarp();
-            if (lane == 0) mbar_arrive(smem_u32(&tempty_bar[as]));
+            if (lane == 0) release_acc(as);
           }
           if (!warp_active) continue;
           const uint32_t buf = wbuf + (nstore & 1u) * 4096u;
@@ -570,9 +610,11 @@ __global__ void __launch_bounds__(kSwThreads, 1) conv_sw_kernel(const __grid_con
 
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
+  if constexpr (PAIR) cluster_sync_all();   // neither CTA leaves (or frees TMEM) while the other may still signal its barriers
   if (warp == 1) {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+    if constexpr (PAIR) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+    else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
   }
 }
 
@@ -594,7 +636,8 @@ void pick_tile256(int H, int W, bool f32, int* tw, int* th) {
 }  // namespace
 
 int conv_sw_init(gt_engine* e) {
-  GT_CUDA(e, cudaFuncSetAttribute(conv_sw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  GT_CUDA(e, cudaFuncSetAttribute(conv_sw_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  GT_CUDA(e, cudaFuncSetAttribute(conv_sw_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
   return GT_OK;
 }
 
@@ -608,6 +651,7 @@ int conv_sw_plan(gt_engine* e, ConvOp* op, const ConvPlanArgs& a) {
   ConvParams& p = op->p;
   memset(&p, 0, sizeof(p));
   op->swapped = 1;
+  op->pair = 0;
   const int pad = a.pad >= 0 ? a.pad : k / 2;
   const int Ho = a.Ho > 0 ? a.Ho : (in.H + 2 * pad - k) / stride + 1, Wo = a.Wo > 0 ? a.Wo : (in.W + 2 * pad - k) / stride + 1;
   const int cout = a.cout;
@@ -618,6 +662,8 @@ int conv_sw_plan(gt_engine* e, ConvOp* op, const ConvPlanArgs& a) {
   // variant 2: halo staging for stride-1 k >= 2 layers with 16-bit NHWC outputs (8-pixel-wide tiles: one 8-row descriptor group per image row)
   bool halo = e->plan_variant == 2 && stride == 1 && k >= 2 && !a.out_f32 && !a.out_s2d;
   if (halo) { p.tw = 8; p.th = 32; }
+  // variant 6: CTA pairs (one 256-channel x 256-pixel tile per pair, per-tap path); every tile shape has an even number of image rows
+  const bool pair = e->plan_variant == 6 && (cout % (2 * kCo)) == 0 && !a.out_f32 && !a.out_s2d;
   GT_CHECK(e, p.tw * stride <= 256 && p.th * stride <= 256, "conv plan: TMA box too large");
   p.tiles_x = ceil_div(Wo, p.tw); p.tiles_y = ceil_div(Ho, p.th);
   p.stride = stride; p.ksize = k; p.pad = pad;
@@ -625,14 +671,16 @@ int conv_sw_plan(gt_engine* e, ConvOp* op, const ConvPlanArgs& a) {
   p.kc_blocks = ceil_div(cin, kbe);
   op->cin_pad = p.kc_blocks * kbe;
   p.num_kb = k * k * p.kc_blocks;
-  p.n_tiles = ceil_div(cout, kCo);
-  op->cout_pad = p.n_tiles * kCo;
+  p.n_tiles = pair ? cout / (2 * kCo) : ceil_div(cout, kCo);
+  op->cout_pad = p.n_tiles * (pair ? 2 * kCo : kCo);
+  op->pair = pair ? 1 : 0;
   p.BN = kCo;                       // TileIter::coord's n0 = nt * BN = first output channel of the tile
   p.tmem_cols = 512; p.acc_stride = kPx;
-  const int w_bytes = kCo * kbe * 2, x_bytes = kPx * kbe * 2;
+  const int w_bytes = kCo * kbe * 2, x_bytes = (pair ? kPx / 2 : kPx) * kbe * 2;   // (pair: per CTA)
   const int wres_bytes = p.num_kb * w_bytes;
   const size_t budget = (size_t)e->conv_smem_kb * 1024;
-  p.b_resident = (p.n_tiles == 1 && wres_bytes <= 80 * 1024) ? 1 : 0;
+  const int bias_floats = pair ? p.n_tiles * kCo : op->cout_pad;                    // (pair: a CTA keeps its own half of every tile)
+  p.b_resident = (!pair && p.n_tiles == 1 && wres_bytes <= 80 * 1024) ? 1 : 0;
   int stage_bytes = 0, stages = 0;
   if (halo) {
     const int halo_rows = (p.tw + k - 1) * (p.th + k - 1);
@@ -655,7 +703,7 @@ int conv_sw_plan(gt_engine* e, ConvOp* op, const ConvPlanArgs& a) {
   }
   for (int attempt = 0; attempt < 2 && !halo; ++attempt) {   // resident weights only if at least 3 ring stages remain
     stage_bytes = p.b_resident ? x_bytes : x_bytes + w_bytes;
-    const size_t fixed = sw_smem_bytes(0, stage_bytes, p.b_resident ? wres_bytes : 0, op->cout_pad);
+    const size_t fixed = sw_smem_bytes(0, stage_bytes, p.b_resident ? wres_bytes : 0, bias_floats);
     stages = fixed < budget ? (int)((budget - fixed) / stage_bytes) : 0;
     if (stages >= 3 || !p.b_resident) break;
     p.b_resident = 0;
@@ -683,7 +731,7 @@ int conv_sw_plan(gt_engine* e, ConvOp* op, const ConvPlanArgs& a) {
     GT_CHECK(e, a.up->H == 2 * Ho && a.up->W == 2 * Wo && a.up->C == cout && !a.out_f32, "conv plan: upsample view mismatch");
     p.up = a.up->ptr; p.up_ctot = a.up->ctot; p.up_coff = a.up->coff;
   }
-  op->smem = sw_smem_bytes(p.stages, stage_bytes, p.b_resident ? wres_bytes : (p.halo ? kSwWStages * w_bytes : 0), op->cout_pad);
+  op->smem = sw_smem_bytes(p.stages, stage_bytes, p.b_resident ? wres_bytes : (p.halo ? kSwWStages * w_bytes : 0), bias_floats);
   op->flops = 2.0 * Ho * Wo * (double)cout * cin * k * k;
   op->bytes = (double)in.H * in.W * cin * 2 + (double)Ho * Wo * cout * (a.out_f32 ? 4 : 2) * (a.up ? 5 : 1) + (a.res ? (double)Ho * Wo * cout * 2 : 0.0);
 
@@ -699,7 +747,8 @@ int conv_sw_plan(gt_engine* e, ConvOp* op, const ConvPlanArgs& a) {
   {  // X: NHWC input slice {C, W, H, N}, box = one 256-pixel tile of one k-block (op->tmB keeps the "activation" map)
     cuuint64_t gdim[4] = {(cuuint64_t)cin, (cuuint64_t)in.W, (cuuint64_t)in.H, (cuuint64_t)a.Bmax};
     cuuint64_t gstr[3] = {(cuuint64_t)in.ctot * 2, (cuuint64_t)in.W * in.ctot * 2, (cuuint64_t)in.H * in.W * in.ctot * 2};
-    cuuint32_t box[4] = {(cuuint32_t)kbe, (cuuint32_t)(p.halo ? p.tw + k - 1 : p.tw * stride), (cuuint32_t)(p.halo ? p.th + k - 1 : p.th * stride), 1};
+    cuuint32_t box[4] = {(cuuint32_t)kbe, (cuuint32_t)(p.halo ? p.tw + k - 1 : p.tw * stride),
+                         (cuuint32_t)(p.halo ? p.th + k - 1 : (pair ? p.th / 2 : p.th) * stride), 1};   // (pair: each CTA loads half of the tile's image rows)
     cuuint32_t estr[4] = {1, (cuuint32_t)stride, (cuuint32_t)stride, 1};
     CUresult r = conv_tc_encode()(&op->tmA, dt, 4, (void*)(in.ptr + in.coff), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
                                   CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -759,14 +808,25 @@ int conv_sw_launch_range(gt_engine* e, const ConvOp* op, int b0, int nb, cudaStr
   p.B = nb;
   p.img0 = b0;
   p.total_tiles = p.tiles_x * p.tiles_y * nb * p.n_tiles;
-  const int grid = p.total_tiles < conv_tc_num_sms() ? p.total_tiles : conv_tc_num_sms();
+  const int units = op->pair ? conv_tc_num_sms() / 2 : conv_tc_num_sms();   // persistent CTAs, or CTA pairs (one per TPC)
+  const int grid = (p.total_tiles < units ? p.total_tiles : units) * (op->pair ? 2 : 1);
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(kSwThreads); cfg.dynamicSmemBytes = op->smem; cfg.stream = st;
-  cudaLaunchAttribute at[1];
-  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  at[0].val.programmaticStreamSerializationAllowed = 1;
-  cfg.attrs = at; cfg.numAttrs = e->pdl ? 1 : 0;
-  GT_CUDA(e, cudaLaunchKernelEx(&cfg, conv_sw_kernel, op->tmB, op->tmA, op->tmOut, op->tmUp, op->tmRes, p));   // (weights, activations, ...)
+  cudaLaunchAttribute at[2];
+  int na = 0;
+  if (e->pdl) {
+    at[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
+  if (op->pair) {
+    at[na].id = cudaLaunchAttributeClusterDimension;
+    at[na].val.clusterDim.x = 2; at[na].val.clusterDim.y = 1; at[na].val.clusterDim.z = 1;
+    ++na;
+  }
+  cfg.attrs = at; cfg.numAttrs = na;
+  if (op->pair) GT_CUDA(e, cudaLaunchKernelEx(&cfg, conv_sw_kernel<1>, op->tmB, op->tmA, op->tmOut, op->tmUp, op->tmRes, p));
+  else GT_CUDA(e, cudaLaunchKernelEx(&cfg, conv_sw_kernel<0>, op->tmB, op->tmA, op->tmOut, op->tmUp, op->tmRes, p));   // (weights, activations, ...)
   e->launches++;
   GT_CUDA(e, cudaGetLastError());
   return GT_OK;

@@ -475,7 +475,7 @@ static void pick_tile(int H, int W, int* tw, int* th) {
 
 int conv_tc_plan(gt_engine* e, ConvOp* op, const ConvPlanArgs& a) {
   GT_CHECK(e, g_encode != nullptr, "conv_tc_init not called");
-  if (e->plan_variant == 1 || e->plan_variant == 2) return conv_sw_plan(e, op, a);
+  if (e->plan_variant == 1 || e->plan_variant == 2 || e->plan_variant == 6) return conv_sw_plan(e, op, a);
   const View& in = a.in;
   const int cin = a.cin, k = a.k, stride = a.stride;
   const int kbe = (a.kb_elems == 64 && cin == 32) ? 32 : a.kb_elems;   // 32-channel inputs: 64-byte rows instead of half-empty 128-byte rows

@@ -829,6 +829,7 @@ struct Builder {
       case 3: return !o.swapped && o.occ2 && !o.p.halo;
       case 4: return !o.swapped && !o.occ2 && o.p.halo;
       case 5: return !o.swapped && o.occ2 && o.p.halo;
+      case 6: return o.swapped && o.pair;
       default: return true;
     }
   }
@@ -839,6 +840,11 @@ struct Builder {
     if (r != GT_OK || !tune) return r;
     for (int v = 1; v < GT_CONV_VARIANTS; ++v) {
       ConvOp alt = op;
+      if (v == 6 && !e->pair_mode) {   // not planned (no weights, never timed) unless GT_PAIR=1
+        e->conv_var[v].push_back(alt);
+        e->conv_var_ok[v].push_back(0);
+        continue;
+      }
       e->plan_variant = v;
       r = conv_tc_plan(e, &alt, a);
       e->plan_variant = 0;
@@ -1131,7 +1137,7 @@ static std::map<std::string, std::vector<int>>& tune_cache() { static std::map<s
 static void apply_choice(gt_engine* e, size_t i, int v, int* n_swapped) {
   if (v <= 0) return;
   std::swap(e->conv_ops[i], e->conv_var[v][i]);
-  if (v == 1 || v == 2) ++*n_swapped;
+  if (v == 1 || v == 2 || v == 6) ++*n_swapped;
   if (v == 2 || v == 4 || v == 5) ++e->n_halo;
   if (v == 3 || v == 5) ++e->n_occ2;
 }
@@ -1186,7 +1192,7 @@ int detector_autotune(gt_engine* e, cudaStream_t st) {
   };
   int n_swapped = 0;
   const bool tune_log = getenv("GT_TUNE_LOG") != nullptr;   // per-layer times of every variant on stderr
-  static const char* vname[GT_CONV_VARIANTS] = {"tc", "sw", "sw-halo", "tc2", "tc-halo", "tc2-halo"};
+  static const char* vname[GT_CONV_VARIANTS] = {"tc", "sw", "sw-halo", "tc2", "tc-halo", "tc2-halo", "sw-pair"};
   for (size_t i = 0; i < e->conv_ops.size(); ++i) {
     float t[GT_CONV_VARIANTS];
     int best = 0;

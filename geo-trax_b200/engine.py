@@ -338,6 +338,10 @@ class Engine:
         self._ck(self.lib.gt_conv_kernel_info(self.h, C.byref(n), C.byref(ns)))
         return n.value, ns.value
 
+    def conv_pair_count(self) -> int:
+        """Fused conv launches that run as CTA pairs (conv variant 6)."""
+        return int(self.lib.gt_conv_pair_count(self.h))
+
     def conv_stack_stats(self):
         ms, fl = C.c_float(), C.c_double()
         self._ck(self.lib.gt_conv_stack_stats(self.h, C.byref(ms), C.byref(fl)))

@@ -193,6 +193,8 @@ int64_t gt_launch_count(gt_handle h);
 int gt_conv_stack_stats(gt_handle h, float* ms, double* flops);
 /* fused conv launches per forward, and how many of them the load-time autotune assigned to the swapped-operand kernel */
 int gt_conv_kernel_info(gt_handle h, int32_t* n_ops, int32_t* n_swapped);
+/* how many of the fused conv launches run as CTA pairs (cta_group::2 swapped kernel, cout a multiple of 256); < 0 on a null handle */
+int gt_conv_pair_count(gt_handle h);
 
 #ifdef __cplusplus
 }

@@ -110,6 +110,14 @@ def small_engine_occ2_halo():
 
 
 @pytest.fixture(scope="session")
+def small_engine_pair():
+    """Swapped kernel as CTA pairs (cta_group::2) on every layer whose cout is a multiple of 256 (GT_SWAP=6)."""
+    eng = _forced_engine(6)
+    yield eng
+    eng.close()
+
+
+@pytest.fixture(scope="session")
 def small_engine_bf16():
     eng = _make_engine("bf16")
     yield eng

@@ -106,14 +106,18 @@ CONV_CASES = [
     (1, 68, 120, 128, 128, 3, 2, True, False, False),
     (2, 40, 44, 64, 64, 3, 1, True, True, False),       # halo staging with the weight ring, ragged 8 x 32 tiles, residual
     (1, 70, 20, 128, 64, 3, 1, True, False, False),     # halo staging, two k-blocks per tap
+    (1, 34, 60, 128, 256, 3, 1, True, True, False),     # CTA-pair tile (cout % 256 == 0): ragged tiles, residual
+    (2, 68, 120, 128, 256, 3, 2, True, False, False),   # CTA-pair tile, stride 2 (half-height boxes with elementStrides)
+    (16, 34, 60, 256, 512, 1, 1, True, False, False),   # more pair tiles than TPCs, two pair tiles along cout
 ]
 
 
-@pytest.mark.parametrize("dtype", ["fp16", "bf16", "fp16-pixel-major", "fp16-swapped-nohalo", "fp16-two-cta", "fp16-tc-halo", "fp16-two-cta-halo"])
+@pytest.mark.parametrize("dtype", ["fp16", "bf16", "fp16-pixel-major", "fp16-swapped-nohalo", "fp16-two-cta", "fp16-tc-halo", "fp16-two-cta-halo", "fp16-pair"])
 @pytest.mark.parametrize("case", CONV_CASES)
 def test_conv2d_tcgen05_matches_torch(request, case, dtype):
     fixture = {"fp16": "small_engine", "bf16": "small_engine_bf16", "fp16-pixel-major": "small_engine_tc", "fp16-swapped-nohalo": "small_engine_sw",
-               "fp16-two-cta": "small_engine_occ2", "fp16-tc-halo": "small_engine_tc_halo", "fp16-two-cta-halo": "small_engine_occ2_halo"}[dtype]
+               "fp16-two-cta": "small_engine_occ2", "fp16-tc-halo": "small_engine_tc_halo", "fp16-two-cta-halo": "small_engine_occ2_halo",
+               "fp16-pair": "small_engine_pair"}[dtype]
     eng = request.getfixturevalue(fixture)
     rnd = lambda a: eng.act_to_f32(eng.f32_to_act(a))
     B, H, W, cin, cout, k, s, act, use_res, f32 = case
@@ -180,13 +184,15 @@ def test_raw_head_within_1e2_of_fp32_oracle(small_engine, small_engine_bf16, dty
         assert rel < max(2.5 * rel_emu, 1e-2)   # the GPU also rounds the folded weights to bf16
 
 
-@pytest.mark.parametrize("variant", ["pixel-major", "two-cta", "swapped-nohalo", "tc-halo", "two-cta-halo"])
+@pytest.mark.parametrize("variant", ["pixel-major", "two-cta", "swapped-nohalo", "tc-halo", "two-cta-halo", "pair"])
 def test_forced_kernel_raw_head(request, variant):
     """Each forced conv kernel variant (conv_tc.cu at one / two CTAs per SM, conv_sw.cu without halo) through the whole network."""
     from oracle import prepost
     eng = request.getfixturevalue({"pixel-major": "small_engine_tc", "two-cta": "small_engine_occ2", "swapped-nohalo": "small_engine_sw",
-                                   "tc-halo": "small_engine_tc_halo", "two-cta-halo": "small_engine_occ2_halo"}[variant])
-    if variant != "swapped-nohalo":
+                                   "tc-halo": "small_engine_tc_halo", "two-cta-halo": "small_engine_occ2_halo", "pair": "small_engine_pair"}[variant])
+    if variant == "pair":
+        assert eng.conv_pair_count() >= 10, "the cout % 256 == 0 layers must run on the CTA-pair kernel"
+    elif variant != "swapped-nohalo":
         assert eng.conv_kernel_info()[1] == 0
     frames = _frames(2, 512, 768, seed=3)
     eng.preprocess(frames)
