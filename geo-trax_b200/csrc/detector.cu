@@ -840,7 +840,7 @@ struct Builder {
     if (r != GT_OK || !tune) return r;
     for (int v = 1; v < GT_CONV_VARIANTS; ++v) {
       ConvOp alt = op;
-      if (v == 6 && !e->pair_mode) {   // not planned (no weights, never timed) unless GT_PAIR=1
+      if (v == 6 && !e->pair_mode) {   // GT_PAIR=0: not planned (no weights, never timed)
         e->conv_var[v].push_back(alt);
         e->conv_var_ok[v].push_back(0);
         continue;

@@ -43,8 +43,7 @@ struct gt_engine {
   int swap_mode = -1;                   // conv kernel per layer: -1 autotune (time the variants at weight load), 0 pixel-major (conv_tc.cu), 1 swapped (conv_sw.cu), 2 swapped + halo staging where it applies, 3 pixel-major at two CTAs per SM where it applies; GT_SWAP env
   int plan_variant = 0;                 // variant conv_tc_plan builds right now (0 / 1)
   int pdl = 1;                          // programmatic dependent launch between conv layers (GT_PDL=0 disables)
-  int pair_mode = 0;                    // 1: the autotuner also times variant 6 (CTA-pair swapped kernel, cout % 256 == 0); GT_PAIR env.  Off by default:
-                                        // the variant was written at the end of round 1 and has not run on hardware yet
+  int pair_mode = 1;                    // 1: the autotuner also times variant 6 (CTA-pair swapped kernel, cout % 256 == 0); GT_PAIR=0 leaves it out
   int halo_mode = 0;                    // conv A-operand staging: 0 per-tap boxes, 1 halo boxes + shifted descriptors (GT_HALO=1 enables: fewer L2->SM bytes, but the layers are tensor-issue bound)
   std::vector<void*> dev_allocs;
   std::vector<void*> host_allocs;
