@@ -1,7 +1,8 @@
-"""Scratch diagnostics run on the GPU box (not part of the product or the tests)."""
+"""Scratch diagnostics run by hand on the GPU box (`python tests/diag_gpu.py detector|...`): CUDA path vs the oracle with verbose output.
+Lives under tests/ because it imports oracle/ (test infrastructure); pytest does not collect it."""
 import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 import numpy as np, torch, cv2
 import geotrax_b200
 from geotrax_b200 import weights, synth

@@ -101,10 +101,10 @@ def test_missing_library_raises(tmp_path):
 
 
 def test_product_never_imports_oracle():
-    """The oracle is test infrastructure: nothing under geo-trax_b200/ may import or execute it."""
-    pkg = os.path.join(ROOT, "geo-trax_b200")
-    for dirpath, _, files in os.walk(pkg):
-        for f in files:
-            if f.endswith((".py", ".cu", ".cuh", ".h")):
-                txt = open(os.path.join(dirpath, f)).read()
-                assert not re.search(r"^\s*(from|import)\s+oracle\b", txt, flags=re.M), f"{f} imports the oracle"
+    """The oracle is test infrastructure: nothing under geo-trax_b200/ or tools/ may import or execute it."""
+    for sub in ("geo-trax_b200", "tools"):
+        for dirpath, _, files in os.walk(os.path.join(ROOT, sub)):
+            for f in files:
+                if f.endswith((".py", ".cu", ".cuh", ".h")):
+                    txt = open(os.path.join(dirpath, f)).read()
+                    assert not re.search(r"^\s*(from|import)\s+oracle\b", txt, flags=re.M), f"{sub}/{f} imports the oracle"
