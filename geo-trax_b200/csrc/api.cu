@@ -796,12 +796,17 @@ int gt_extract_batch_async(gt_handle e, const uint8_t* frames, int B, int first_
   GT_CHECK(e, ticket != nullptr, "gt_extract_batch_async: ticket is NULL");
   const int k = e->async_ticket;
   e->async_ticket ^= 1;
+  if (e->ticket_pending[k]) {   // a third batch without gt_wait on the first: its staging buffers and event set are about to be reused
+    GT_CUDA(e, cudaEventSynchronize(e->ev_done[k]));
+    e->ticket_pending[k] = false;
+  }
   e->ev = e->ev_sets[k];
   const int rc = extract_batch_impl(e, frames, B, first_is_reference, conf, iou, agnostic, classes_mask, mask_boxes, mask_nboxes, mask_stride, out_boxes,
                                     out_counts, out_boxes_stab, out_H, out_status, out_stats, stream, false);
   if (rc == GT_OK) {
     cudaError_t er = cudaEventRecord(e->ev_done[k], pick_stream(e, stream));
     if (er != cudaSuccess) { gt_set_error(e, "gt_extract_batch_async: %s", cudaGetErrorString(er)); e->ev = e->ev_sets[0]; return GT_ERR_CUDA; }
+    e->ticket_pending[k] = true;
   }
   e->ev = e->ev_sets[0];
   *ticket = k;
@@ -812,6 +817,7 @@ int gt_wait(gt_handle e, int ticket) {
   ENTER(e);
   GT_CHECK(e, ticket == 0 || ticket == 1, "gt_wait: bad ticket %d", ticket);
   GT_CUDA(e, cudaEventSynchronize(e->ev_done[ticket]));
+  e->ticket_pending[ticket] = false;
   e->ev = e->ev_sets[ticket];
   update_times(e);
   e->ev = e->ev_sets[0];

@@ -153,6 +153,7 @@ struct gt_engine {
   cudaEvent_t* ev = ev_sets[0];         // the set of the call being enqueued
   cudaEvent_t ev_done[2] = {nullptr, nullptr};   // all work and read-backs of ticket k are complete
   int async_ticket = 0;
+  bool ticket_pending[2] = {false, false};   // ticket issued by gt_extract_batch_async and not yet passed to gt_wait
   float stage_ms[4] = {0, 0, 0, 0};
   float conv_ms = 0;
   double conv_flops = 0;

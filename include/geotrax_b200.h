@@ -175,7 +175,8 @@ int gt_extract_batch(gt_handle h, const uint8_t* frames, int B, int first_is_ref
 
 /* Pipelined form of gt_extract_batch: enqueues the kernels and the read-backs (the out_* buffers must be pinned host memory for the
  * read-backs to be asynchronous) and returns a ticket (0 / 1) immediately; gt_wait(ticket) blocks until that batch's outputs are
- * valid.  At most two tickets in flight.  Lets the caller enqueue batch i+1 before reading batch i, so the GPU does not idle
+ * valid.  At most two tickets in flight (a third call first waits for the ticket it reuses).  Lets the caller enqueue batch i+1
+ * before reading batch i, so the GPU does not idle
  * between batches.                                                                                                  */
 int gt_extract_batch_async(gt_handle h, const uint8_t* frames, int B, int first_is_reference, float conf, float iou,
                            int agnostic, uint32_t classes_mask, const float* mask_boxes, const int32_t* mask_nboxes,
