@@ -74,7 +74,6 @@ int gt_create(const gt_config* cfg, int device, gt_handle* out) {
   e->device = device;
   if (const char* hm = getenv("GT_HALO")) e->halo_mode = atoi(hm);
   if (const char* pm = getenv("GT_PAIR")) e->pair_mode = atoi(pm);
-  if (const char* lc = getenv("GT_L2_CHUNK")) e->l2_chunk = std::max(0, atoi(lc));
   if (const char* pd = getenv("GT_PDL")) e->pdl = atoi(pd);
   if (const char* sm = getenv("GT_SWAP")) e->swap_mode = atoi(sm);
   if (const char* ov = getenv("GT_OVERLAP")) e->overlap = atoi(ov);

@@ -1255,15 +1255,7 @@ static bool sppf_chain(const std::vector<PlanOp>& plan, size_t i) {
 
 int detector_forward(gt_engine* e, int B, cudaStream_t st) {
   GT_CHECK(e, e->weights_loaded, "detect: weights not loaded");
-  size_t pi0 = 0;
-  if (e->l2_chunk > 0 && e->l2_chunk < B) {   // GT_L2_CHUNK experiment (engine.cuh): leading conv ops at >= 1/8 resolution, image chunk by image chunk
-    size_t n_pre = 0;
-    while (n_pre < e->plan.size() && e->plan[n_pre].type == OP_CONV && e->conv_ops[e->plan[n_pre].conv].p.H * 8 >= e->net_h) ++n_pre;
-    for (int b0 = 0; b0 < B; b0 += e->l2_chunk)
-      for (size_t pi = 0; pi < n_pre; ++pi) GT_TRY(conv_tc_launch_range(e, &e->conv_ops[e->plan[pi].conv], b0, std::min(e->l2_chunk, B - b0), st));
-    pi0 = n_pre;
-  }
-  for (size_t pi = pi0; pi < e->plan.size(); ++pi) {
+  for (size_t pi = 0; pi < e->plan.size(); ++pi) {
     const PlanOp& po = e->plan[pi];
     if (po.type == OP_CONV) GT_TRY(conv_tc_launch(e, &e->conv_ops[po.conv], B, st));
     else if (sppf_chain(e->plan, pi)) {

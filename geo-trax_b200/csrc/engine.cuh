@@ -43,8 +43,6 @@ struct gt_engine {
   int swap_mode = -1;                   // conv kernel per layer: -1 autotune (time the variants at weight load), 0 pixel-major (conv_tc.cu), 1 swapped (conv_sw.cu), 2 swapped + halo staging where it applies, 3 pixel-major at two CTAs per SM where it applies; GT_SWAP env
   int plan_variant = 0;                 // variant conv_tc_plan builds right now (0 / 1)
   int pdl = 1;                          // programmatic dependent launch between conv layers (GT_PDL=0 disables)
-  int l2_chunk = 0;                     // GT_L2_CHUNK=n (round-2 experiment, not measured yet, default off): the conv ops of the two largest levels run n
-                                        // images at a time, so that a producer's output (33 MB / image at 272x480) is still in the 126 MB L2 when its consumer reads it
   int pair_mode = 1;                    // 1: the autotuner also times variant 6 (CTA-pair swapped kernel, cout % 256 == 0); GT_PAIR=0 leaves it out
   int halo_mode = 0;                    // conv A-operand staging: 0 per-tap boxes, 1 halo boxes + shifted descriptors (GT_HALO=1 enables: fewer L2->SM bytes, but the layers are tensor-issue bound)
   std::vector<void*> dev_allocs;
