@@ -26,7 +26,7 @@ class gt_config(C.Structure):
         ("downsample_ratio", C.c_float), ("max_features", C.c_int32), ("ref_multiplier", C.c_float),
         ("mask_use", C.c_int32), ("mask_margin_ratio", C.c_float), ("filter_ratio", C.c_float),
         ("ransac_threshold", C.c_float), ("ransac_max_iter", C.c_int32), ("query_is_current", C.c_int32),
-        ("ransac_full_res", C.c_int32), ("seed", C.c_uint32), ("act_dtype", C.c_int32), ("reserved", C.c_int32 * 7),
+        ("ransac_full_res", C.c_int32), ("seed", C.c_uint32), ("act_dtype", C.c_int32), ("clahe", C.c_int32), ("reserved", C.c_int32 * 6),
     ]
 
 
@@ -57,6 +57,8 @@ SYMBOLS = {
     "gt_get_net_input": (_i, [_H, _i, _P, _ip, _ip]),
     "gt_get_gray": (_i, [_H, _i, _P, _ip, _ip]),
     "gt_detect": (_i, [_H, _i, _f, _f, _i, _u, _P, _P, _P, _P]),
+    "gt_set_class_filter": (_i, [_H, _ip, _i]),
+    "gt_get_health": (_i, [_H, C.POINTER(C.c_int64)]),
     "gt_get_raw_head": (_i, [_H, _i, _P, _ip, _ip]),
     "gt_get_feature": (_i, [_H, _i, _i, _P, _ip, _ip, _ip]),
     "gt_nms": (_i, [_H, _P, _i, _i, _i, _i, _f, _f, _i, _u, _i, _P, _P, _P, _P]),

@@ -50,6 +50,7 @@ void gt_default_config(gt_config* c) {
   c->filter_ratio = 0.9f; c->ransac_threshold = 2.0f; c->ransac_max_iter = 5000; c->query_is_current = 1; c->ransac_full_res = 0;
   c->seed = 0x9E3779B9u;
   c->act_dtype = GT_ACT_FP16;
+  c->clahe = 0;
 }
 
 const char* gt_last_error(gt_handle h) { return h ? h->err.c_str() : g_create_error.c_str(); }
@@ -76,6 +77,7 @@ int gt_create(const gt_config* cfg, int device, gt_handle* out) {
   if (const char* pm = getenv("GT_PAIR")) e->pair_mode = atoi(pm);
   if (const char* pd = getenv("GT_PDL")) e->pdl = atoi(pd);
   if (const char* sm = getenv("GT_SWAP")) e->swap_mode = atoi(sm);
+  if (const char* tm = getenv("GT_TUNE")) e->tune_mode = atoi(tm);
   if (const char* ov = getenv("GT_OVERLAP")) e->overlap = atoi(ov);
   if (const char* kb = getenv("GT_CONV_SMEM_KB")) e->conv_smem_kb = std::min(227, std::max(96, atoi(kb)));
   if (e->overlap == 1 && !getenv("GT_CONV_SMEM_KB")) e->conv_smem_kb = 200;   // room for ORB blocks beside the conv CTAs
@@ -113,8 +115,8 @@ int gt_create(const gt_config* cfg, int device, gt_handle* out) {
   e->work_h = (int)(c.frame_h * c.downsample_ratio);
   if (e->work_w < 128 || e->work_h < 128) { gt_set_error(e, "gt_create: working image %dx%d too small for the 8-level ORB pyramid", e->work_w, e->work_h); return fail(GT_ERR_INVALID); }
   // the fused vector kernel covers the default preset's geometry (exact 1/2 letterbox, 1/2 working image, 16-pixel-aligned rows)
-  e->pre_fast = r == 0.5 && c.downsample_ratio == 0.5f && (c.frame_w % 16) == 0 && (c.frame_h % 4) == 0 && (e->pad_left % 8) == 0 && (e->pad_top % 2) == 0 &&
-                e->work_w * 2 == c.frame_w && e->work_h * 2 == c.frame_h;
+  e->lb_fast = r == 0.5 && (c.frame_w % 16) == 0 && (c.frame_h % 4) == 0 && (e->pad_left % 8) == 0 && (e->pad_top % 2) == 0;
+  e->pre_fast = e->lb_fast && c.downsample_ratio == 0.5f && e->work_w * 2 == c.frame_w && e->work_h * 2 == c.frame_h;
   const int B = c.max_batch;
   CR(e->dev_alloc((void**)&e->frames_dev, (size_t)B * c.frame_h * c.frame_w * 3));
   CR(e->dev_alloc((void**)&e->frames_dev2, (size_t)B * c.frame_h * c.frame_w * 3));
@@ -135,7 +137,8 @@ int gt_create(const gt_config* cfg, int device, gt_handle* out) {
   CR(detector_build(e));
   CR(stab_build(e));
   // constant letterbox border
-  if (!e->pre_fast) CR(detector_build_general_preprocess(e));
+  if (!e->pre_fast || e->cfg.clahe) CR(detector_build_general_preprocess(e));
+  CR(clahe_build(e));
   CR(detector_fill_pad(e, e->stream));
   CRC(cudaStreamSynchronize(e->stream));
 #undef CR
@@ -286,7 +289,7 @@ int gt_preprocess(gt_handle e, const uint8_t* frames, int B, void* stream) {
     }
     src = used ? e->frames_dev2 : e->frames_dev;
   }
-  if (e->input_format == GT_INPUT_NV12 && e->pre_fast && (e->cfg.frame_w % 32) == 0) {   // default geometry: fused NV12 -> letterbox + gray
+  if (e->input_format == GT_INPUT_NV12 && e->pre_fast && (e->cfg.frame_w % 32) == 0 && !e->cfg.clahe) {   // default geometry: fused NV12 -> letterbox + gray
     GT_TRY(detector_preprocess_nv12(e, src, B, st));
     if (used >= 0) GT_CUDA(e, cudaEventRecord(e->ev_consumed[used], st));
     GT_CUDA(e, cudaEventRecord(e->ev[1], st));
@@ -298,6 +301,7 @@ int gt_preprocess(gt_handle e, const uint8_t* frames, int B, void* stream) {
     src = e->frames_bgr;
   }
   GT_TRY(detector_preprocess(e, src, B, st));
+  if (e->cfg.clahe) GT_TRY(clahe_run(e, src, B, st));   // the working image is CLAHE(gray) instead of gray (stable preset)
   if (used >= 0) GT_CUDA(e, cudaEventRecord(e->ev_consumed[used], st));
   GT_CUDA(e, cudaEventRecord(e->ev[1], st));
   return GT_OK;
@@ -378,6 +382,24 @@ int gt_detect(gt_handle e, int B, float conf, float iou, int agnostic, uint32_t 
   GT_TRY(copy_dets(e, B, out_boxes, out_counts, out_keep, st));
   GT_CUDA(e, cudaStreamSynchronize(st));
   update_times(e);
+  return GT_OK;
+}
+
+int gt_set_class_filter(gt_handle e, const int32_t* classes, int n) {
+  ENTER(e);
+  GT_CHECK(e, n >= 0 && (classes || n == 0), "gt_set_class_filter: bad arguments");
+  e->cls_filter[0] = e->cls_filter[1] = e->cls_filter[2] = 0u;
+  e->cls_filter_on = classes != nullptr;
+  for (int i = 0; i < n; ++i) {
+    GT_CHECK(e, classes[i] >= 0 && classes[i] < 96, "gt_set_class_filter: class id %d out of range", (int)classes[i]);
+    e->cls_filter[classes[i] >> 5] |= 1u << (classes[i] & 31);
+  }
+  return GT_OK;
+}
+
+int gt_get_health(gt_handle e, int64_t* nonfinite_rows) {
+  if (!e || !nonfinite_rows) return GT_ERR_INVALID;
+  *nonfinite_rows = e->nonfinite_host ? (int64_t)*(volatile int*)e->nonfinite_host : 0;
   return GT_OK;
 }
 

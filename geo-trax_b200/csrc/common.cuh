@@ -137,6 +137,11 @@ struct ConvPlanArgs {
   const View* up = nullptr;
 };
 
+// layer signature = key of the shipped per-layer kernel-variant table (csrc/conv_tune.inc)
+struct ConvSig { int cin, cout, k, stride, H, W, flags; };   // flags: 1 residual, 2 upsampled copy, 4 f32 rows, 8 s2d output
+ConvSig conv_signature(const ConvPlanArgs& a);
+int conv_choose_variant(const ConvSig& s);
+
 int conv_tc_init(gt_engine* e);  // resolves cuTensorMapEncodeTiled, sets kernel attributes
 int conv_tc_plan(gt_engine* e, ConvOp* op, const ConvPlanArgs& a);  // tensor maps + launch geometry + weight storage
 int conv_tc_pack_weights(gt_engine* e, ConvOp* op, const float* const* w, const float* const* b, const int* couts, int n);

@@ -5,6 +5,7 @@
 // Detect/OBB head + DFL + dist2bbox/dist2rbox, non_max_suppression (torchvision.ops.nms / nms_rotated), scale_boxes.
 #include <algorithm>
 #include <map>
+#include <string>
 #include <vector>
 #include <type_traits>
 
@@ -307,25 +308,32 @@ int detector_fill_pad(gt_engine* e, cudaStream_t st) {  // constant letterbox bo
 }
 
 int detector_preprocess(gt_engine* e, const uint8_t* frames_dev, int B, cudaStream_t st) {
-  uint8_t* gray = e->pyr;  // level 0 of each frame's pyramid slab
-  if (!e->pre_fast) {      // any other geometry: two table-driven kernels (letterbox, gray working image)
-    const int fp16 = e->cfg.act_dtype == GT_ACT_FP16;
+  // level 0 of each frame's pyramid slab receives the gray working image (CLAHE: written by clahe_run instead)
+  uint8_t* gray = e->cfg.clahe ? nullptr : e->pyr;
+  const int fp16 = e->cfg.act_dtype == GT_ACT_FP16;
+  const ResizeTabs gt = {e->gw_tab[0], e->gw_tab[1], e->gw_tab[2], e->gw_tab[3], e->gw_tab[4], e->gw_tab[5], e->gw_tab[6], e->gw_tab[7], e->gw_mode};
+  const long long n2 = (long long)B * e->work_h * e->work_w;
+  if (e->lb_fast) {   // exact-1/2 letterbox: the fused vector kernel (+ the 1/2 gray working image in the same pass for the default preset)
+    const long long threads = (long long)B * (e->new_h / 2) * (e->new_w / 8);
+    preprocess_half_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(frames_dev, e->net_s2d, e->pre_fast ? gray : nullptr, e->pyr_bytes, B, e->cfg.frame_h,
+                                                                              e->cfg.frame_w, e->net_h, e->net_w, e->pad_top, e->pad_left,
+                                                                              e->new_h, e->new_w, fp16);
+    e->launches++;
+    if (!e->pre_fast && gray) {
+      gray_work_kernel<<<(unsigned)((n2 + 255) / 256), 256, 0, st>>>(frames_dev, gray, e->pyr_bytes, B, e->cfg.frame_h, e->cfg.frame_w, e->work_h, e->work_w, gt);
+      e->launches++;
+    }
+  } else {            // any other geometry: two table-driven kernels (letterbox, gray working image)
     const ResizeTabs lt = {e->lb_tab[0], e->lb_tab[1], e->lb_tab[2], e->lb_tab[3], e->lb_tab[4], e->lb_tab[5], e->lb_tab[6], e->lb_tab[7], e->lb_mode};
-    const ResizeTabs gt = {e->gw_tab[0], e->gw_tab[1], e->gw_tab[2], e->gw_tab[3], e->gw_tab[4], e->gw_tab[5], e->gw_tab[6], e->gw_tab[7], e->gw_mode};
-    const long long n1 = (long long)B * e->new_h * e->new_w, n2 = (long long)B * e->work_h * e->work_w;
+    const long long n1 = (long long)B * e->new_h * e->new_w;
     letterbox_general_kernel<<<(unsigned)((n1 + 255) / 256), 256, 0, st>>>(frames_dev, e->net_s2d, B, e->cfg.frame_h, e->cfg.frame_w, e->net_h, e->net_w,
                                                                            e->pad_top, e->pad_left, e->new_h, e->new_w, lt, fp16);
-    gray_work_kernel<<<(unsigned)((n2 + 255) / 256), 256, 0, st>>>(frames_dev, gray, e->pyr_bytes, B, e->cfg.frame_h, e->cfg.frame_w, e->work_h, e->work_w, gt);
-    e->launches += 2;
-    GT_CUDA(e, cudaGetLastError());
-    e->cur_frames = frames_dev;
-    return GT_OK;
+    e->launches++;
+    if (gray) {
+      gray_work_kernel<<<(unsigned)((n2 + 255) / 256), 256, 0, st>>>(frames_dev, gray, e->pyr_bytes, B, e->cfg.frame_h, e->cfg.frame_w, e->work_h, e->work_w, gt);
+      e->launches++;
+    }
   }
-  const long long threads = (long long)B * (e->new_h / 2) * (e->new_w / 8);
-  preprocess_half_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(frames_dev, e->net_s2d, gray, e->pyr_bytes, B, e->cfg.frame_h,
-                                                                            e->cfg.frame_w, e->net_h, e->net_w, e->pad_top, e->pad_left,
-                                                                            e->new_h, e->new_w, e->cfg.act_dtype == GT_ACT_FP16);
-  e->launches++;
   GT_CUDA(e, cudaGetLastError());
   e->cur_frames = frames_dev;
   return GT_OK;
@@ -411,6 +419,18 @@ __global__ void __launch_bounds__(256) sppf_pool3_kernel(bf16* __restrict__ buf,
 // key = conf bits << 32 | ~anchor : descending key order == (conf desc, anchor asc) == the order torchvision.ops.nms's
 // stable descending sort gives to ultralytics' anchor-ordered candidate rows.
 // =====================================================================================================================
+struct ClassMask {            // allow-list over up to 96 classes (gt_create accepts nc <= 80); on == 0: every class passes
+  uint32_t w[3];
+  int on;
+  __device__ __forceinline__ bool allows(int c) const { return !on || ((w[c >> 5] >> (c & 31)) & 1u); }
+};
+static ClassMask make_class_mask(const gt_engine* e, uint32_t classes_mask) {
+  ClassMask m = {{0u, 0u, 0u}, 0};
+  if (classes_mask) { m.w[0] = classes_mask; m.on = 1; }                         // per-call mask (classes 0..31) wins
+  else if (e->cls_filter_on) { for (int i = 0; i < 3; ++i) m.w[i] = e->cls_filter[i]; m.on = 1; }   // gt_set_class_filter
+  return m;
+}
+
 struct DecodeGeom {
   int lvl_w[3], lvl_h[3], lvl_off[3];
   float stride[3];
@@ -433,27 +453,32 @@ __device__ __forceinline__ float dfl_side(const float* p) {
 }
 
 __global__ void __launch_bounds__(256) decode_filter_kernel(const float* __restrict__ raw, int B, int A, int no, int ang_col, int nc, int obb,
-                                                            DecodeGeom g, float conf_thr, uint32_t classes_mask,
+                                                            DecodeGeom g, float conf_thr, ClassMask cm,
                                                             float* __restrict__ cand_box, float* __restrict__ cand_conf,
                                                             int* __restrict__ cand_cls, unsigned long long* __restrict__ keys,
-                                                            int key_stride, int* __restrict__ count) {
+                                                            int key_stride, int* __restrict__ count, int* __restrict__ nonfinite) {
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= (long long)B * A) return;
   const int b = (int)(idx / A), a = (int)(idx - (long long)b * A);
   const float* r = raw + (size_t)idx * no;
   float best = r[64];
   int bj = 0;
+  bool bad = !isfinite(best);
   for (int j = 1; j < nc; ++j) {
     const float v = r[64 + j];
+    bad |= !isfinite(v);
     if (v > best) { best = v; bj = j; }
   }
+  // 16-bit overflow guard: an fp16 activation that left the format's range (|x| > 65504) reaches the head as inf / NaN.  Counted, never
+  // silently dropped: gt_get_health() reports it and the Python front end switches the engine to bf16 storage.
+  if (bad) { atomicAdd(nonfinite, 1); return; }
   const float conf = sigmoid_f(best);
   if (!(conf > conf_thr)) return;
   // the reference takes max/argmax over the *probabilities* (cls.sigmoid().max(1)): when the sigmoid saturates, several
   // classes tie at the same float and the first index wins
   for (int j = 0; j < bj; ++j)
     if (sigmoid_f(r[64 + j]) >= conf) { bj = j; break; }
-  if (classes_mask && !((classes_mask >> bj) & 1u)) return;
+  if (!cm.allows(bj)) return;
   int lvl = 0;
   if (a >= g.lvl_off[2]) lvl = 2; else if (a >= g.lvl_off[1]) lvl = 1;
   const int la = a - g.lvl_off[lvl];
@@ -467,6 +492,7 @@ __global__ void __launch_bounds__(256) decode_filter_kernel(const float* __restr
     for (int i = 0; i < 16; ++i) box[i] = r[k * 16 + i];
     d[k] = dfl_side(box);
   }
+  if (!isfinite(d[0] + d[1] + d[2] + d[3])) { atomicAdd(nonfinite, 1); return; }
   float* o = cand_box + ((size_t)b * A + a) * 5;
   if (!obb) {
     const float x1 = ax - d[0], y1 = ay - d[1], x2 = ax + d[2], y2 = ay + d[3];
@@ -489,7 +515,7 @@ __global__ void __launch_bounds__(256) decode_filter_kernel(const float* __restr
 
 // same filter for caller-supplied decoded predictions [B][A][4+nc(+1)] (gt_nms)
 __global__ void __launch_bounds__(256) pred_filter_kernel(const float* __restrict__ pred, int B, int A, int nc, int rotated, float conf_thr,
-                                                          uint32_t classes_mask, float* __restrict__ cand_box, float* __restrict__ cand_conf,
+                                                          ClassMask cm, float* __restrict__ cand_box, float* __restrict__ cand_conf,
                                                           int* __restrict__ cand_cls, unsigned long long* __restrict__ keys, int key_stride,
                                                           int* __restrict__ count) {
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -504,7 +530,7 @@ __global__ void __launch_bounds__(256) pred_filter_kernel(const float* __restric
     if (v > best) { best = v; bj = j; }
   }
   if (!(best > conf_thr)) return;
-  if (classes_mask && !((classes_mask >> bj) & 1u)) return;
+  if (!cm.allows(bj)) return;
   float* o = cand_box + ((size_t)b * A + a) * 5;
   if (!rotated) {
     const float hw = __fmul_rn(r[2], 0.5f), hh = __fmul_rn(r[3], 0.5f);  // xywh2xyxy: xy -+ wh/2
@@ -747,15 +773,17 @@ int nms_run(gt_engine* e, const float* pred_dev, int B, int A, int nc, int rotat
   GT_CHECK(e, max_det <= e->cfg.max_det, "nms: max_det %d exceeds configured %d", max_det, e->cfg.max_det);
   GT_CUDA(e, cudaMemsetAsync(e->cand_count, 0, sizeof(int) * B, st));
   const long long total = (long long)B * A;
+  const ClassMask cm = make_class_mask(e, classes_mask);
   if (pred_dev) {
-    pred_filter_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(pred_dev, B, A, nc, rotated, conf, classes_mask, e->cand_box,
+    pred_filter_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(pred_dev, B, A, nc, rotated, conf, cm, e->cand_box,
                                                                         e->cand_conf, e->cand_cls, e->cand_key, key_stride, e->cand_count);
   } else {
     DecodeGeom g;
     for (int i = 0; i < 3; ++i) { g.lvl_w[i] = e->lvl_w[i]; g.lvl_h[i] = e->lvl_h[i]; g.lvl_off[i] = e->lvl_off[i]; g.stride[i] = (float)(8 << i); }
-    decode_filter_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(e->raw_head, B, A, e->no_pad, e->ang_col, nc, rotated, g, conf, classes_mask,
+    decode_filter_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(e->raw_head, B, A, e->no_pad, e->ang_col, nc, rotated, g, conf, cm,
                                                                           e->cand_box, e->cand_conf, e->cand_cls, e->cand_key, key_stride,
-                                                                          e->cand_count);
+                                                                          e->cand_count, e->nonfinite_dev);
+    GT_CUDA(e, cudaMemcpyAsync(e->nonfinite_host, e->nonfinite_dev, sizeof(int), cudaMemcpyDeviceToHost, st));   // cumulative counter -> pinned mirror
   }
   e->launches++;
   sort_keys_kernel<<<B, 1024, 4096 * sizeof(unsigned long long), st>>>(e->cand_key, key_stride, e->cand_count);
@@ -790,6 +818,52 @@ int nms_run(gt_engine* e, const float* pred_dev, int B, int A, int nc, int rotat
   for (int b = 0; b < B; ++b)
     if (ov[b]) GT_TRY(run_pass(b, 1, ((max_nms + 63) / 64) * 64));
   return GT_OK;
+}
+
+// =====================================================================================================================
+// Conv kernel variant per layer: shipped table keyed by the layer signature, else a fixed rule (see plan_both)
+// =====================================================================================================================
+ConvSig conv_signature(const ConvPlanArgs& a) {
+  ConvSig s;
+  const int pad = a.pad >= 0 ? a.pad : a.k / 2;
+  s.cin = a.cin; s.cout = a.cout; s.k = a.k; s.stride = a.stride;
+  s.H = a.Ho > 0 ? a.Ho : (a.in.H + 2 * pad - a.k) / a.stride + 1;
+  s.W = a.Wo > 0 ? a.Wo : (a.in.W + 2 * pad - a.k) / a.stride + 1;
+  s.flags = (a.res ? 1 : 0) | (a.up ? 2 : 0) | (a.out_f32 ? 4 : 0) | (a.out_s2d ? 8 : 0);
+  return s;
+}
+
+struct TuneRow { int cin, cout, k, stride, H, W, flags, variant; };
+static const TuneRow kTuneTable[] = {
+#include "conv_tune.inc"
+};
+
+// Layers the table does not know (other frame sizes, other heads): the pattern of the tuned table, as a rule.
+static int rule_variant(const ConvSig& s) {
+  if (s.flags & (4 | 8)) return 3;                                     // f32 head rows, layer 0: pixel-major, two CTAs / SM
+  const long long px = (long long)s.H * s.W;
+  if (s.k == 1) {
+    if (s.flags & 2) return 0;                                         // upsampled copy: pixel-major slabs
+    if ((s.cout % 256) == 0) return s.cin >= 384 ? 6 : 1;
+    return s.cin >= 384 ? 0 : 3;
+  }
+  if (s.k == 2) return 3;
+  if (s.stride == 2) {
+    if ((s.cout % 256) == 0) return 6;
+    if (s.cout <= 64) return 3;
+    return s.cin <= 64 ? 1 : 0;
+  }
+  if ((s.cout % 256) == 0) return 6;
+  if (s.cout > 128) return 0;
+  if (s.cout == 128) return px >= 136 * 240 ? 2 : (px >= 68 * 120 ? 1 : 0);
+  if (s.cout > 32) return (s.flags & 1) ? 5 : 4;
+  return 5;
+}
+
+int conv_choose_variant(const ConvSig& s) {
+  for (const TuneRow& r : kTuneTable)
+    if (r.cin == s.cin && r.cout == s.cout && r.k == s.k && r.stride == s.stride && r.H == s.H && r.W == s.W && r.flags == s.flags) return r.variant;
+  return rule_variant(s);
 }
 
 // =====================================================================================================================
@@ -834,10 +908,22 @@ struct Builder {
     }
   }
   int plan_both(ConvOp& op, const ConvPlanArgs& a) {
-    const bool tune = e->swap_mode < 0;
-    e->plan_variant = tune ? 0 : e->swap_mode;
+    if (e->swap_mode >= 0) {               // GT_SWAP=v: one variant forced wherever it applies (tests)
+      e->plan_variant = e->swap_mode;
+      return conv_tc_plan(e, &op, a);
+    }
+    if (!e->tune_mode) {
+      // Default: the variant is a fixed function of the layer's signature (shipped table, else a rule) -- never of a timing -- so every
+      // process / rank / engine runs the same kernels in the same accumulation order and outputs are bit-identical across them.
+      e->plan_variant = conv_choose_variant(conv_signature(a));
+      const int r = conv_tc_plan(e, &op, a);   // (a variant that does not apply to the layer plans as its plain base kernel)
+      e->plan_variant = 0;
+      return r;
+    }
+    // GT_TUNE=1 (development): plan every variant; detector_autotune times them at weight load and prints the table rows
+    e->plan_variant = 0;
     int r = conv_tc_plan(e, &op, a);
-    if (r != GT_OK || !tune) return r;
+    if (r != GT_OK) return r;
     for (int v = 1; v < GT_CONV_VARIANTS; ++v) {
       ConvOp alt = op;
       if (v == 6 && !e->pair_mode) {   // GT_PAIR=0: not planned (no weights, never timed)
@@ -852,6 +938,7 @@ struct Builder {
       e->conv_var[v].push_back(alt);
       e->conv_var_ok[v].push_back(variant_applies(v, alt) ? 1 : 0);
     }
+    e->conv_sig.push_back(conv_signature(a));
     return r;
   }
   // 16-bit conv writing a channel slice; several canonical convs reading the same input are fused along cout
@@ -1073,6 +1160,10 @@ int detector_build(gt_engine* e) {
   GT_TRY(e->dev_alloc((void**)&e->cand_cls, (size_t)B * e->A * sizeof(int)));
   GT_TRY(e->dev_alloc((void**)&e->cand_key, (size_t)B * cap * sizeof(unsigned long long)));
   GT_TRY(e->dev_alloc((void**)&e->cand_count, (size_t)B * sizeof(int)));
+  GT_TRY(e->dev_alloc((void**)&e->nonfinite_dev, sizeof(int)));
+  GT_CUDA(e, cudaMemset(e->nonfinite_dev, 0, sizeof(int)));
+  GT_TRY(e->host_alloc((void**)&e->nonfinite_host, sizeof(int)));
+  *e->nonfinite_host = 0;
   e->nms_cap = 4096;
   const size_t big_cap = (size_t)((e->cfg.max_nms + 63) / 64) * 64;
   const size_t batched = (size_t)B * e->nms_cap * (e->nms_cap / 64) * 8 + (size_t)B * e->nms_cap * 5 * 4;
@@ -1128,70 +1219,33 @@ int detector_load_weights(gt_engine* e, const float* const* w, const float* cons
   return GT_OK;
 }
 
-// Times both kernel variants of every conv on the full batch and keeps the faster one in conv_ops ("measure, don't guess":
-// which operand order wins depends on cout, K and the epilogue, see profiles/conv_findings_r1.md).
-// Engines of one process with the same geometry reuse the first one's per-layer choice: the variants differ in accumulation
-// order, so re-timing could otherwise make two engine instances differ in the last bits of their outputs.
-static std::map<std::string, std::vector<int>>& tune_cache() { static std::map<std::string, std::vector<int>> c; return c; }
-
-static void apply_choice(gt_engine* e, size_t i, int v, int* n_swapped) {
-  if (v <= 0) return;
-  std::swap(e->conv_ops[i], e->conv_var[v][i]);
-  if (v == 1 || v == 2 || v == 6) ++*n_swapped;
-  if (v == 2 || v == 4 || v == 5) ++e->n_halo;
-  if (v == 3 || v == 5) ++e->n_occ2;
+// GT_TUNE=1 (development only): times every applicable variant of every conv on the full batch, runs the fastest, and prints one
+// `[gt tune]` line per layer; tools/make_tune_table.py turns that log into csrc/conv_tune.inc, the table that SHIPS.  A normal engine
+// never times anything: its per-layer variant comes from that table (plan_both), so it is the same in every process.
+static void apply_choice(gt_engine* e, size_t i, int v) {
+  if (v > 0) std::swap(e->conv_ops[i], e->conv_var[v][i]);
 }
 
 int detector_autotune(gt_engine* e, cudaStream_t st) {
-  if (e->conv_var[1].empty() || e->tuned) return GT_OK;
+  if (!e->tune_mode || e->conv_var[1].empty() || e->tuned) return GT_OK;
   const int B = e->cfg.max_batch;
-  char keybuf[160];
-  snprintf(keybuf, sizeof(keybuf), "%d:%dx%d:%d:%d:%d:%d:%d:%zu", e->device, e->cfg.frame_h, e->cfg.frame_w, e->cfg.imgsz, e->cfg.nc, (int)e->cfg.task, B,
-           (int)e->cfg.act_dtype, e->conv_ops.size());
-  const std::string key(keybuf);
-  // GT_TUNE_FILE=<path>: per-layer choices are read from / written to a text file ("key v0 v1 ..."), so that a profiled run (whose
-  // tuning launches would be timed under the profiler) uses the choices of a normal run
-  const char* tune_file = getenv("GT_TUNE_FILE");
-  if (tune_file && tune_cache().find(key) == tune_cache().end()) {
-    if (FILE* f = fopen(tune_file, "r")) {
-      char k[200];
-      while (fscanf(f, "%199s", k) == 1) {
-        std::vector<int> v(e->conv_ops.size(), 0);
-        bool ok = true;
-        for (size_t i = 0; i < v.size() && ok; ++i) ok = fscanf(f, "%d", &v[i]) == 1 && v[i] >= 0 && v[i] < GT_CONV_VARIANTS;
-        if (!ok) break;
-        bool applies = key == k;
-        for (size_t i = 0; i < v.size() && applies; ++i) applies = v[i] == 0 || e->conv_var_ok[v[i]][i];
-        if (applies) tune_cache()[key] = v;
-      }
-      fclose(f);
-    }
-  }
-  auto hit = tune_cache().find(key);
-  if (hit != tune_cache().end() && hit->second.size() == e->conv_ops.size() && !getenv("GT_TUNE_LOG")) {
-    int ns = 0;
-    for (size_t i = 0; i < e->conv_ops.size(); ++i) apply_choice(e, i, hit->second[i], &ns);
-    e->n_swapped = ns;
-    e->tuned = true;
-    return GT_OK;
-  }
-  std::vector<int> choice(e->conv_ops.size(), 0);
   cudaEvent_t a, b;
   GT_CUDA(e, cudaEventCreate(&a));
   GT_CUDA(e, cudaEventCreate(&b));
   int64_t tune_launches = 0;
-  auto time_op = [&](const ConvOp& op, float* ms) -> int {
+  constexpr int kReps = 5;
+  auto time_op = [&](const ConvOp& op, float* us) -> int {
     GT_TRY(conv_tc_launch(e, &op, B, st));   // warm-up
     GT_CUDA(e, cudaEventRecord(a, st));
-    for (int i = 0; i < 2; ++i) GT_TRY(conv_tc_launch(e, &op, B, st));
+    for (int i = 0; i < kReps; ++i) GT_TRY(conv_tc_launch(e, &op, B, st));
     GT_CUDA(e, cudaEventRecord(b, st));
     GT_CUDA(e, cudaEventSynchronize(b));
-    GT_CUDA(e, cudaEventElapsedTime(ms, a, b));
-    tune_launches += 3;
+    float ms = 0.f;
+    GT_CUDA(e, cudaEventElapsedTime(&ms, a, b));
+    *us = ms * 1000.f / kReps;
+    tune_launches += kReps + 1;
     return GT_OK;
   };
-  int n_swapped = 0;
-  const bool tune_log = getenv("GT_TUNE_LOG") != nullptr;   // per-layer times of every variant on stderr
   static const char* vname[GT_CONV_VARIANTS] = {"tc", "sw", "sw-halo", "tc2", "tc-halo", "tc2-halo", "sw-pair"};
   for (size_t i = 0; i < e->conv_ops.size(); ++i) {
     float t[GT_CONV_VARIANTS];
@@ -1203,29 +1257,17 @@ int detector_autotune(gt_engine* e, cudaStream_t st) {
       GT_TRY(time_op(e->conv_var[v][i], &t[v]));
       if (t[v] < t[best]) best = v;
     }
-    if (tune_log) {
-      const ConvOp& o = e->conv_ops[i];
-      fprintf(stderr, "[gt tune] op %2zu src %2d cin %4d cout %4d k %d s %d out %4dx%-4d ", i, o.src[0], o.cin, o.cout, o.k, o.stride, o.p.H, o.p.W);
-      for (int v = 0; v < GT_CONV_VARIANTS; ++v) fprintf(stderr, " %s %6.1f", vname[v], 500.f * t[v]);
-      fprintf(stderr, "  -> %s  %6.1f TFLOP/s  %6.1f GB/s\n", vname[best], o.flops * B / (t[best] * 0.5e-3) * 1e-12, o.bytes * B / (t[best] * 0.5e-3) * 1e-9);
-    }
-    choice[i] = best;
-    apply_choice(e, i, best, &n_swapped);
+    const ConvOp& o = e->conv_ops[i];
+    const ConvSig& sg = e->conv_sig[i];
+    fprintf(stderr, "[gt tune] op %2zu src %2d cin %4d cout %4d k %d s %d out %4dx%-4d flags %d ", i, o.src[0], sg.cin, sg.cout, sg.k, sg.stride, sg.H, sg.W, sg.flags);
+    for (int v = 0; v < GT_CONV_VARIANTS; ++v) fprintf(stderr, " %s %6.1f", vname[v], t[v]);
+    fprintf(stderr, "  -> %s  %6.1f TFLOP/s  %6.1f GB/s\n", vname[best], o.flops * B / (t[best] * 1e-6) * 1e-12, o.bytes * B / (t[best] * 1e-6) * 1e-9);
+    apply_choice(e, i, best);
   }
   e->launches -= tune_launches;   // tuning launches are not part of any step
   cudaEventDestroy(a);
   cudaEventDestroy(b);
   e->tuned = true;
-  e->n_swapped = n_swapped;
-  tune_cache()[key] = choice;
-  if (tune_file) {
-    if (FILE* f = fopen(tune_file, "a")) {
-      fprintf(f, "%s", key.c_str());
-      for (int v : choice) fprintf(f, " %d", v);
-      fprintf(f, "\n");
-      fclose(f);
-    }
-  }
   return GT_OK;
 }
 

@@ -40,6 +40,7 @@ struct gt_engine {
   cudaStream_t stream = nullptr;
   std::string err;
   int64_t launches = 0;
+  int tune_mode = 0;                    // GT_TUNE=1: time every conv variant at weight load and print table rows (development); 0: the shipped table / rule decides
   int swap_mode = -1;                   // conv kernel per layer: -1 autotune (time the variants at weight load), 0 pixel-major (conv_tc.cu), 1 swapped (conv_sw.cu), 2 swapped + halo staging where it applies, 3 pixel-major at two CTAs per SM where it applies; GT_SWAP env
   int plan_variant = 0;                 // variant conv_tc_plan builds right now (0 / 1)
   int pdl = 1;                          // programmatic dependent launch between conv layers (GT_PDL=0 disables)
@@ -72,24 +73,32 @@ struct gt_engine {
   int deferred_B = 0;
   int input_format = 0;                 // GT_INPUT_BGR24 | GT_INPUT_NV12 (gt_set_input_format)
   uint8_t* frames_bgr = nullptr;        // NV12 ingest: device BGR24 frames produced by nv12_to_bgr_kernel (allocated on first use)
+  bool lb_fast = true;                  // exact-1/2 letterbox with 16-pixel-aligned rows: the vector kernel writes the network input (pre_fast: and the gray working image)
   bool pre_fast = true;                 // exact-1/2 letterbox + 1/2 working image with 16-pixel-aligned rows: the fused vector kernel; else the table-driven general kernels
   int* lb_tab[8] = {};                  // letterbox resize tables (x0, x1, a0, a1, y0, y1, b0, b1), see detector.cu
   int* gw_tab[8] = {};                  // gray working-image resize tables
   int lb_mode = 0, gw_mode = 0;         // 0 identity, 1 exact 2x2 decimation, 2 bilinear
   bf16* net_s2d = nullptr;              // [B][net_h/4][net_w/4][64] 4x4 space-to-depth letterboxed RGB0 (exact u8 values, 16-bit)
   const uint8_t* cur_frames = nullptr;  // device pointer of the frames of the last gt_preprocess
+  // CLAHE front end (cfg.clahe; clahe.cu): full-resolution gray plane, per-tile histograms and LUTs, interpolation tables
+  uint8_t* gray_full = nullptr;         // [B][H][W]
+  uint8_t* gray_eq = nullptr;           // [B][H][W] equalised plane (only when the working image is smaller than the frame)
+  int* clahe_hist = nullptr;            // [B][64][256]
+  uint8_t* clahe_lut = nullptr;         // [B][64][256]
+  int clahe_tw = 0, clahe_th = 0, clahe_clip = 0;
+  float clahe_scale = 0.f;
+  int* clahe_xi[2] = {}; float* clahe_xa[2] = {};   // per column: tile indices (left, right), weights (xa, 1 - xa)
+  int* clahe_yi[2] = {}; float* clahe_ya[2] = {};   // per row
 
   // detector
   bool weights_loaded = false;
   bool tuned = false;
-  int n_swapped = 0;                                // convs running the swapped-operand kernel after autotune
   std::vector<gt_conv_desc> conv_descs;             // canonical list
   std::vector<ConvOp> conv_ops;                     // fused tcgen05 ops (the variant in use)
   std::vector<ConvOp> conv_var[GT_CONV_VARIANTS];   // the other variants of each op (autotune), same indexing as conv_ops; empty when a variant is forced
   std::vector<char> conv_var_ok[GT_CONV_VARIANTS];  // 1 where the variant applies to the op
+  std::vector<ConvSig> conv_sig;                    // GT_TUNE=1: signature of each op (table key)
   std::vector<PlanOp> plan;
-  int n_occ2 = 0;                                   // convs on a two-CTA variant after autotune
-  int n_halo = 0;                                   // convs on the halo variant after autotune
   int conv0_op = -1;                                // index of layer 0 in conv_ops (custom weight packing)
   View feat_views[23];
   float* raw_head = nullptr;                        // [B][A][no_pad]
@@ -101,6 +110,10 @@ struct gt_engine {
   int* cand_cls = nullptr;
   int* cand_anchor = nullptr;
   int* cand_count = nullptr;                        // [B]
+  int* nonfinite_dev = nullptr;                     // [1] cumulative count of anchors whose head row held inf / NaN (16-bit overflow guard)
+  int* nonfinite_host = nullptr;                    // pinned mirror, refreshed by every decode (valid after the call's sync / gt_wait)
+  uint32_t cls_filter[3] = {0, 0, 0};               // gt_set_class_filter: allow-list for classes 0..95
+  bool cls_filter_on = false;
   unsigned long long* nms_mask = nullptr;
   int nms_cap = 0;
   float* det_out = nullptr;                         // [B][max_det][7]
@@ -175,6 +188,10 @@ int detector_forward(gt_engine* e, int B, cudaStream_t st);
 int detector_postprocess(gt_engine* e, int B, float conf, float iou, int agnostic, uint32_t classes_mask, cudaStream_t st);
 int nms_run(gt_engine* e, const float* pred_dev, int B, int A, int nc, int rotated, float conf, float iou, int agnostic,
             uint32_t classes_mask, int max_det, bool scale_to_frame, cudaStream_t st);
+
+// clahe.cu
+int clahe_build(gt_engine* e);
+int clahe_run(gt_engine* e, const uint8_t* frames_dev, int B, cudaStream_t st);
 
 // orb.cu
 int orb_build(gt_engine* e);

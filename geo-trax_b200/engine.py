@@ -23,12 +23,29 @@ def _ptr(a) -> int:
     raise TypeError(type(a))
 
 
-def classes_to_mask(classes: Optional[Sequence[int]]) -> int:
+def normalize_classes(classes) -> Optional[list]:
+    """``classes: int | list[int] | None`` (/root/reference/geotrax/cfg/default.yaml:243) -> None or a sorted list of ints."""
     if classes is None:
+        return None
+    if isinstance(classes, (int, np.integer)):
+        classes = [int(classes)]
+    out = sorted({int(c) for c in classes})
+    for c in out:
+        if not 0 <= c < 96:
+            raise GtError(f"classes: id {c} is outside the supported range 0..95")
+    return out
+
+
+def classes_to_mask(classes) -> int:
+    """32-bit per-call mask of the ABI; only valid when every id is below 32 (Engine._classes_arg routes the rest)."""
+    cl = normalize_classes(classes)
+    if not cl:
         return 0
+    if cl[-1] >= 32:
+        raise GtError("classes >= 32 do not fit the per-call mask: use Engine (gt_set_class_filter)")
     m = 0
-    for c in classes:
-        m |= 1 << int(c)
+    for c in cl:
+        m |= 1 << c
     return m
 
 
@@ -68,6 +85,27 @@ class Engine:
         self._keep = []
 
     # -- plumbing --------------------------------------------------------------------------------------------------------
+    def _classes_arg(self, classes) -> int:
+        """Per-call `classes_mask` argument.  Lists with ids >= 32 (or the empty list = "keep nothing") go through the sticky
+        gt_set_class_filter allow-list and the per-call mask is 0; everything else uses the mask and clears the sticky filter."""
+        cl = normalize_classes(classes)
+        sticky = cl is not None and (len(cl) == 0 or cl[-1] >= 32)
+        if sticky:
+            arr = (C.c_int32 * max(len(cl), 1))(*cl)
+            self._ck(self.lib.gt_set_class_filter(self.h, arr, len(cl)))
+            self._sticky_classes = True
+            return 0
+        if getattr(self, "_sticky_classes", False):
+            self._ck(self.lib.gt_set_class_filter(self.h, None, 0))
+            self._sticky_classes = False
+        return classes_to_mask(cl)
+
+    def health(self) -> int:
+        """Cumulative count of anchors dropped because their head row was inf / NaN (16-bit overflow guard); 0 = healthy."""
+        n = C.c_int64()
+        self._ck(self.lib.gt_get_health(self.h, C.byref(n)))
+        return int(n.value)
+
     def _ck(self, rc: int):
         if rc < 0:
             raise GtError(f"geotrax_b200 error {rc}: {self.lib.gt_last_error(self.h).decode()}")
@@ -141,7 +179,7 @@ class Engine:
         boxes = np.zeros((B, self.max_det, self.row), np.float32)
         counts = np.zeros((B,), np.int32)
         keep = np.zeros((B, self.max_det), np.int32) if want_keep else None
-        self._ck(self.lib.gt_detect(self.h, B, conf, iou, int(bool(agnostic)), classes_to_mask(classes), boxes.ctypes.data, counts.ctypes.data,
+        self._ck(self.lib.gt_detect(self.h, B, conf, iou, int(bool(agnostic)), self._classes_arg(classes), boxes.ctypes.data, counts.ctypes.data,
                                     _ptr(keep), stream))
         return (boxes, counts, keep) if want_keep else (boxes, counts)
 
@@ -165,7 +203,7 @@ class Engine:
         rows = np.zeros((B, md, row), np.float32)
         counts = np.zeros((B,), np.int32)
         keep = np.zeros((B, md), np.int32)
-        self._ck(self.lib.gt_nms(self.h, pred.ctypes.data, B, A, nc, int(rotated), conf, iou, int(bool(agnostic)), classes_to_mask(classes), md,
+        self._ck(self.lib.gt_nms(self.h, pred.ctypes.data, B, A, nc, int(rotated), conf, iou, int(bool(agnostic)), self._classes_arg(classes), md,
                                  rows.ctypes.data, counts.ctypes.data, keep.ctypes.data, None))
         return rows, counts, keep
 
@@ -297,11 +335,11 @@ class Engine:
             self._keep_async = (frames, mb, mn)
             t = C.c_int32()
             self._ck(self.lib.gt_extract_batch_async(self.h, _ptr(frames), B, int(first_is_reference), conf, iou, int(bool(agnostic)),
-                                                     classes_to_mask(classes), _ptr(mb), _ptr(mn), self.max_det,
+                                                     self._classes_arg(classes), _ptr(mb), _ptr(mn), self.max_det,
                                                      o["boxes"].ctypes.data, o["counts"].ctypes.data, o["boxes_stab"].ctypes.data, o["H"].ctypes.data,
                                                      o["status"].ctypes.data, o["stats"].ctypes.data, stream, C.byref(t)))
             return o, t.value
-        self._ck(self.lib.gt_extract_batch(self.h, _ptr(frames), B, int(first_is_reference), conf, iou, int(bool(agnostic)), classes_to_mask(classes),
+        self._ck(self.lib.gt_extract_batch(self.h, _ptr(frames), B, int(first_is_reference), conf, iou, int(bool(agnostic)), self._classes_arg(classes),
                                            _ptr(mb), _ptr(mn), self.max_det,
                                            o["boxes"].ctypes.data, o["counts"].ctypes.data, o["boxes_stab"].ctypes.data, o["H"].ctypes.data,
                                            o["status"].ctypes.data, o["stats"].ctypes.data, stream))

@@ -86,40 +86,77 @@ def gather_records(local: Dict[str, np.ndarray], rank: int, world: int, device=N
     return gathered if rank == 0 else None
 
 
+class GmcFromHomography:
+    """Drop-in for ``BOTSORT.gmc`` (ultralytics ``trackers/utils/gmc.py``; ``gmc_method: sparseOptFlow`` in
+    /root/reference/geotrax/cfg/default.yaml:374) fed by the stabilizer's homographies instead of sparse optical flow on the frames.
+
+    BoT-SORT's global-motion compensation wants the previous-frame -> current-frame 2x3 affine.  The hot path already has, for every
+    frame, H_t : frame t -> reference; so prev -> cur = H_cur^-1 . H_prev (its perspective row is ~1e-6 on BEV drone footage and is
+    dropped).  The sharded driver therefore needs no pixels on rank 0 -- SURVEY.md section 8f "tracker-side GMC input"."""
+
+    def __init__(self):
+        self.prev_H: Optional[np.ndarray] = None
+        self.cur_H: Optional[np.ndarray] = None
+
+    def set_frame(self, H: Optional[np.ndarray]) -> None:
+        self.cur_H = None if H is None else np.asarray(H, np.float64).reshape(3, 3)
+
+    def apply(self, raw_frame=None, detections=None) -> np.ndarray:
+        out = np.eye(2, 3)
+        if self.prev_H is not None and self.cur_H is not None:
+            M = np.linalg.solve(self.cur_H, self.prev_H)      # inv(H_cur) @ H_prev
+            out = (M[:2, :] / M[2, 2]).copy()
+        if self.cur_H is not None:
+            self.prev_H = self.cur_H
+        return out
+
+    def reset_params(self) -> None:
+        self.prev_H = self.cur_H = None
+
+
 def replay_tracks(rec: Dict[str, np.ndarray], tracker, warp_boxes: Callable[[np.ndarray, np.ndarray], np.ndarray], ref_frame_index: int,
-                  obb: bool = False) -> Tuple[np.ndarray, np.ndarray]:
+                  obb: bool = False, frame_hw: Tuple[int, int] = (2160, 3840)) -> Tuple[np.ndarray, np.ndarray]:
     """Rank 0: sequential tracker over the gathered detections, then the stabilizer's box warp with the stored H.
 
     -> (tracks (N,12) f32 [frame,id,x,y,w,h,xs,ys,ws,hs,cls,conf], transforms (F,10) f64 [frame, H row-major]) -- the arrays
-    extract.py:273-293 ``aggregate_results`` builds; untracked rows (id -1) are dropped as extract.py:287 does."""
-    import types
+    extract.py:273-293 ``aggregate_results`` builds; untracked rows (id -1) are dropped as extract.py:287 does.
 
+    ``tracker``: anything with ultralytics' ``update(det, img, feats) -> rows [x1,y1,x2,y2,id,score,cls,det_idx]`` contract -- the real
+    BOTSORT / BYTETracker (``tracker.make_tracker``) or the stand-in.  ``det`` is a numpy-backed ``Boxes`` / ``OBB`` as in ultralytics.
+    A tracker that owns a ``gmc`` object (BoT-SORT) gets it replaced by ``GmcFromHomography``: no frame pixels are needed here."""
+    from .results import OBB, Boxes
+
+    gmc = None
+    if hasattr(tracker, "gmc"):
+        gmc = GmcFromHomography()
+        tracker.gmc = gmc
     order = np.argsort(rec["frame"], kind="stable")
     tracks, transforms = [], []
     for i in order:
         f, n = int(rec["frame"][i]), int(rec["count"][i])
         H = rec["H"][i].reshape(3, 3) if int(rec["status"][i]) == 0 else None
+        if gmc is not None:
+            gmc.set_frame(np.eye(3) if f == ref_frame_index else H)
         if f != ref_frame_index and H is not None:
             transforms.append(np.concatenate([[float(f)], H.ravel()])[None])
         if n == 0:
             continue
-        d = rec["boxes"][i, :n]
-        if obb:
-            c, s = np.abs(np.cos(d[:, 4])), np.abs(np.sin(d[:, 4]))
-            hw, hh = (d[:, 2] * c + d[:, 3] * s) / 2, (d[:, 2] * s + d[:, 3] * c) / 2
-            xyxy = np.stack([d[:, 0] - hw, d[:, 1] - hh, d[:, 0] + hw, d[:, 1] + hh], 1)
-            conf, cls = d[:, 5], d[:, 6]
-        else:
-            xyxy, conf, cls = d[:, :4], d[:, 4], d[:, 5]
-        rows = tracker.update(types.SimpleNamespace(xyxy=xyxy, conf=conf, cls=cls), None, None)
+        d = np.ascontiguousarray(rec["boxes"][i, :n])
+        rows = np.asarray(tracker.update(OBB(d, frame_hw) if obb else Boxes(d, frame_hw), None, None))
         if len(rows) == 0:
             continue
-        b = np.asarray(rows[:, :4], np.float32)
-        xywh = np.stack([(b[:, 0] + b[:, 2]) / 2, (b[:, 1] + b[:, 3]) / 2, b[:, 2] - b[:, 0], b[:, 3] - b[:, 1]], 1).astype(np.float32)
+        if obb and rows.shape[1] == 9:       # ultralytics rows for rotated boxes: [x, y, w, h, angle, id, score, cls, det_idx]
+            c, s = np.abs(np.cos(rows[:, 4])), np.abs(np.sin(rows[:, 4]))
+            xywh = np.stack([rows[:, 0], rows[:, 1], rows[:, 2] * c + rows[:, 3] * s, rows[:, 2] * s + rows[:, 3] * c], 1).astype(np.float32)
+            tid, score, cls = rows[:, 5], rows[:, 6], rows[:, 7]
+        else:
+            b = np.asarray(rows[:, :4], np.float32)
+            xywh = np.stack([(b[:, 0] + b[:, 2]) / 2, (b[:, 1] + b[:, 3]) / 2, b[:, 2] - b[:, 0], b[:, 3] - b[:, 1]], 1).astype(np.float32)
+            tid, score, cls = rows[:, 4], rows[:, 5], rows[:, 6]
         stab = xywh if (f == ref_frame_index or H is None) else warp_boxes(H, xywh)
-        ids = rows[:, 4].astype(np.uint16).astype(np.float32)          # extract.py:162 casts ids to uint16
-        tracks.append(np.concatenate([np.full((len(b), 1), f, np.float32), ids[:, None], xywh, stab.astype(np.float32),
-                                      rows[:, 6:7].astype(np.uint8).astype(np.float32), rows[:, 5:6].astype(np.float32)], 1))
+        ids = tid.astype(np.uint16).astype(np.float32)          # extract.py:162 casts ids to uint16
+        tracks.append(np.concatenate([np.full((len(xywh), 1), f, np.float32), ids[:, None], xywh, stab.astype(np.float32),
+                                      cls[:, None].astype(np.uint8).astype(np.float32), score[:, None].astype(np.float32)], 1))
     t = np.concatenate(tracks, 0).astype(np.float32) if tracks else np.empty((0, 12), np.float32)
     t = t[t[:, 1] != -1] if t.size else t
     tr = np.concatenate(transforms, 0) if transforms else np.empty((0, 10))
@@ -128,12 +165,16 @@ def replay_tracks(rec: Dict[str, np.ndarray], tracker, warp_boxes: Callable[[np.
 
 def run_flight(engine, get_frames: Callable[[int, int], np.ndarray], n_frames: int, rank: int = 0, world: int = 1, first_frame: int = 0,
                batch: int = 16, tracker=None, gather_device=None, **det_kw):
-    """Whole sharded job: local range -> gather -> (rank 0) tracker replay.  Returns (tracks, transforms) on rank 0, else None."""
-    from .tracker import GreedyIoUTracker
+    """Whole sharded job: local range -> gather -> (rank 0) tracker replay.  Returns (tracks, transforms) on rank 0, else None.
+
+    ``tracker``: a tracker object, a tracker yaml path / ``'greedy-iou'`` for ``tracker.make_tracker``, or None (ultralytics' default
+    BoT-SORT; raises when ultralytics is absent -- see ``tracker.make_tracker``)."""
+    from .tracker import make_tracker
 
     lo, hi = frame_ranges(n_frames, world, first_frame)[rank]
     local = run_range(engine, get_frames, lo, hi, first_frame, batch=batch, **det_kw)
     rec = gather_records(local, rank, world, gather_device)
     if rank != 0:
         return None
-    return replay_tracks(rec, tracker or GreedyIoUTracker(), engine.warp_boxes, first_frame, obb=(engine.row == 7))
+    trk = tracker if hasattr(tracker, "update") else make_tracker(tracker)
+    return replay_tracks(rec, trk, engine.warp_boxes, first_frame, obb=(engine.row == 7), frame_hw=(engine.cfg.frame_h, engine.cfg.frame_w))

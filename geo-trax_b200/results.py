@@ -15,12 +15,20 @@ import numpy as np
 import torch
 
 
+def _xp(a):
+    return torch if isinstance(a, torch.Tensor) else np
+
+
+def _stack(parts, axis):
+    return torch.stack(parts, axis) if isinstance(parts[0], torch.Tensor) else np.stack(parts, axis)
+
+
 class _Base:
-    """Tensor wrapper with the ``cpu()/numpy()/cuda()/to()`` chain and row indexing of ultralytics' BaseTensor."""
+    """Tensor wrapper with the ``cpu()/numpy()/cuda()/to()`` chain and row indexing of ultralytics' BaseTensor: ``data`` is a
+    ``torch.Tensor`` (what the reference reads, extract.py:154-168) or, after ``.numpy()``, a ``np.ndarray`` (what the host tracker
+    indexes with boolean masks, ultralytics ``trackers/byte_tracker.py``)."""
 
     def __init__(self, data, orig_shape: Tuple[int, int]):
-        if isinstance(data, np.ndarray):
-            data = torch.from_numpy(np.ascontiguousarray(data))
         if data.ndim == 1:
             data = data[None, :]
         self.data = data
@@ -37,16 +45,16 @@ class _Base:
         return self.__class__(self.data[idx], self.orig_shape)
 
     def cpu(self):
-        return self if not self.data.is_cuda else self.__class__(self.data.cpu(), self.orig_shape)
+        return self if not (isinstance(self.data, torch.Tensor) and self.data.is_cuda) else self.__class__(self.data.cpu(), self.orig_shape)
 
     def numpy(self):
         return self.__class__(self.data.detach().cpu().numpy(), self.orig_shape) if isinstance(self.data, torch.Tensor) else self
 
     def cuda(self):
-        return self.__class__(self.data.cuda(), self.orig_shape)
+        return self.__class__(torch.as_tensor(self.data).cuda(), self.orig_shape)
 
     def to(self, *a, **k):
-        return self.__class__(self.data.to(*a, **k), self.orig_shape)
+        return self.__class__(torch.as_tensor(self.data).to(*a, **k), self.orig_shape)
 
 
 class Boxes(_Base):
@@ -70,28 +78,25 @@ class Boxes(_Base):
         return self.data[:, -1]
 
     @property
-    def id(self) -> Optional[torch.Tensor]:
+    def id(self):
         return self.data[:, -3] if self.is_track else None
 
     @property
     def xywh(self):
         b = self.xyxy
-        out = torch.empty_like(b)
-        out[:, 0] = (b[:, 0] + b[:, 2]) / 2
-        out[:, 1] = (b[:, 1] + b[:, 3]) / 2
-        out[:, 2] = b[:, 2] - b[:, 0]
-        out[:, 3] = b[:, 3] - b[:, 1]
-        return out
+        return _stack([(b[:, 0] + b[:, 2]) / 2, (b[:, 1] + b[:, 3]) / 2, b[:, 2] - b[:, 0], b[:, 3] - b[:, 1]], 1)
+
+    def _wh4(self):
+        h, w = self.orig_shape
+        return torch.tensor([w, h, w, h], dtype=self.data.dtype) if isinstance(self.data, torch.Tensor) else np.array([w, h, w, h], self.data.dtype)
 
     @property
     def xyxyn(self):
-        h, w = self.orig_shape
-        return self.xyxy / torch.tensor([w, h, w, h], dtype=self.data.dtype)
+        return self.xyxy / self._wh4()
 
     @property
     def xywhn(self):
-        h, w = self.orig_shape
-        return self.xywh / torch.tensor([w, h, w, h], dtype=self.data.dtype)
+        return self.xywh / self._wh4()
 
 
 class OBB(_Base):
@@ -115,23 +120,26 @@ class OBB(_Base):
         return self.data[:, -1]
 
     @property
-    def id(self) -> Optional[torch.Tensor]:
+    def id(self):
         return self.data[:, -3] if self.is_track else None
 
     @property
     def xyxyxyxy(self):
         """(n, 4, 2) corner points."""
+        xp = _xp(self.data)
         x, y, w, h, r = (self.data[:, i] for i in range(5))
-        c, s = torch.cos(r), torch.sin(r)
-        vx, vy = torch.stack([w / 2 * c, w / 2 * s], -1), torch.stack([-h / 2 * s, h / 2 * c], -1)
-        ctr = torch.stack([x, y], -1)
-        return torch.stack([ctr + vx + vy, ctr + vx - vy, ctr - vx - vy, ctr - vx + vy], 1)
+        c, s = xp.cos(r), xp.sin(r)
+        vx, vy = _stack([w / 2 * c, w / 2 * s], -1), _stack([-h / 2 * s, h / 2 * c], -1)
+        ctr = _stack([x, y], -1)
+        return _stack([ctr + vx + vy, ctr + vx - vy, ctr - vx - vy, ctr - vx + vy], 1)
 
     @property
     def xyxy(self):
         """Axis-aligned envelope of each rotated box (what the stabilizer mask uses)."""
         p = self.xyxyxyxy
-        return torch.cat([p.min(1).values, p.max(1).values], -1)
+        if isinstance(p, torch.Tensor):
+            return torch.cat([p.min(1).values, p.max(1).values], -1)
+        return np.concatenate([p.min(1), p.max(1)], -1)
 
 
 class Results:
@@ -143,17 +151,22 @@ class Results:
         self.orig_shape = tuple(orig_img.shape[:2])
         self.path = path
         self.names = names or {}
-        self.boxes = Boxes(boxes, self.orig_shape) if boxes is not None else None
-        self.obb = OBB(obb, self.orig_shape) if obb is not None else None
+        self.boxes = Boxes(self._t(boxes), self.orig_shape) if boxes is not None else None
+        self.obb = OBB(self._t(obb), self.orig_shape) if obb is not None else None
         self.speed = speed or {"preprocess": None, "inference": None, "postprocess": None}
         self._keys = ("boxes", "obb")
+
+    @staticmethod
+    def _t(a):
+        """Detections live as torch tensors on a Results (the reference calls ``.detach().numpy(force=True)`` on them)."""
+        return torch.from_numpy(np.ascontiguousarray(a)) if isinstance(a, np.ndarray) else a
 
     def update(self, boxes=None, obb=None, **_unused):
         """ultralytics ``Results.update``: replace the detections (tracker output rows)."""
         if boxes is not None:
-            self.boxes = Boxes(boxes, self.orig_shape)
+            self.boxes = Boxes(self._t(boxes), self.orig_shape)
         if obb is not None:
-            self.obb = OBB(obb, self.orig_shape)
+            self.obb = OBB(self._t(obb), self.orig_shape)
 
     def __len__(self) -> int:
         for k in self._keys:

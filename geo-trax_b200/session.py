@@ -15,7 +15,8 @@ from ._lib import GtError
 
 # keys of the stabilo: block (/root/reference/geotrax/cfg/default.yaml:103-145) that map onto gt_config fields
 STAB_DEFAULTS = dict(downsample_ratio=0.5, max_features=2000, ref_multiplier=2.0, mask_use=True, mask_margin_ratio=0.15,
-                     filter_ratio=0.9, ransac_epipolar_threshold=2.0, ransac_max_iter=5000, match_query_frame="current")
+                     filter_ratio=0.9, ransac_epipolar_threshold=2.0, ransac_max_iter=5000, match_query_frame="current", clahe=False,
+                     ransac_space="working")
 
 _engines: Dict[tuple, "object"] = {}
 _latest_stab_cfg: Optional[dict] = None
@@ -37,7 +38,8 @@ def _engine_kwargs(cfg: dict) -> dict:
     return dict(downsample_ratio=float(c["downsample_ratio"]), max_features=int(c["max_features"]), ref_multiplier=float(c["ref_multiplier"]),
                 mask_use=int(bool(c["mask_use"])), mask_margin_ratio=float(c["mask_margin_ratio"]), filter_ratio=float(c["filter_ratio"]),
                 ransac_threshold=float(c["ransac_epipolar_threshold"]), ransac_max_iter=int(c["ransac_max_iter"]),
-                query_is_current=int(c["match_query_frame"] != "reference"))
+                query_is_current=int(c["match_query_frame"] != "reference"), clahe=int(bool(c["clahe"])),
+                ransac_full_res=int(c["ransac_space"] == "full"))
 
 
 def device_index(device) -> int:
@@ -69,7 +71,8 @@ def acquire(frame_hw: Tuple[int, int], imgsz: Optional[int], nc: int, task: str,
     if eng is not None and eng.max_batch >= max_batch:
         return eng
     if eng is not None:
-        eng.close()
+        eng.close()      # a larger batch was requested: the handle is re-created; owners (YOLO weights, Stabilizer reference) notice through
+                         # `eng.h` / `_weights_owner` / `_ref_owner` and restore their state on the new handle
     eng = Engine(frame_hw=tuple(frame_hw), imgsz=int(imgsz), nc=int(nc), task=task, max_batch=int(max_batch), device=device, max_det=int(max_det),
                  act_dtype=act_dtype, **_engine_kwargs(cfg))
     eng._frame_token = None

@@ -45,10 +45,30 @@ def increment_path(path, exist_ok: bool = False, sep: str = "", mkdir: bool = Fa
     return path
 
 
-def install_shims(force: bool = False) -> None:
-    """Registers the fake ``ultralytics`` and ``stabilo`` packages in sys.modules (idempotent).
+def _real_package_available(name: str) -> bool:
+    """True when an importable, real (non-shim) distribution of `name` exists on sys.path."""
+    import importlib.util
 
-    With ``force=False`` an already-imported real package is left alone and a warning is logged."""
+    have = sys.modules.get(name)
+    if have is not None:
+        return not getattr(have, "__geotrax_b200_shim__", False)
+    try:
+        return importlib.util.find_spec(name) is not None
+    except (ImportError, ValueError):
+        return False
+
+
+def install_shims(force: bool = False) -> None:
+    """Makes ``from ultralytics import YOLO, RTDETR`` and ``from stabilo import Stabilizer`` resolve to the B200 classes (idempotent).
+
+    * real ``ultralytics`` importable: ONLY ``YOLO`` / ``RTDETR`` are substituted, as attributes of the real package --
+      ``ultralytics.trackers`` (BoT-SORT / ByteTrack, which the reference's `model.track(..., tracker=<yaml>)` relies on,
+      /root/reference/geotrax/extract.py:153, cfg/default.yaml:361-379), ``ultralytics.utils`` and ``ultralytics.cfg`` stay the real ones.
+    * no real ``ultralytics`` (this image): a minimal package with the names the reference imports is registered; it has NO
+      ``trackers`` sub-package, so ``tracker.make_tracker`` cannot mistake it for the real one.
+    * ``stabilo`` is always the B200 ``Stabilizer`` (the stage is entirely replaced).
+
+    With ``force=False`` an already-imported real ``stabilo`` is left alone and a warning is logged."""
     from .stabilizer import Stabilizer
     from .yolo import RTDETR, YOLO
 
@@ -60,19 +80,24 @@ def install_shims(force: bool = False) -> None:
             setattr(m, k, v)
         return m
 
-    if not force:
-        for name in ("ultralytics", "stabilo"):
-            have = sys.modules.get(name)
-            if have is not None and not getattr(have, "__geotrax_b200_shim__", False):
-                log.warning("%s is already imported; not replacing it (install_shims(force=True) overrides)", name)
-                return
-    checks = mod("ultralytics.utils.checks", check_yolo=check_yolo)
-    files = mod("ultralytics.utils.files", increment_path=increment_path)
-    utils = mod("ultralytics.utils", checks=checks, files=files)
-    trackers = mod("ultralytics.trackers")
-    track = mod("ultralytics.trackers.track")
-    trackers.track = track
-    ul = mod("ultralytics", YOLO=YOLO, RTDETR=RTDETR, utils=utils, trackers=trackers, __version__="8.4.80+geotrax_b200")
-    sys.modules.update({"ultralytics": ul, "ultralytics.utils": utils, "ultralytics.utils.checks": checks, "ultralytics.utils.files": files,
-                        "ultralytics.trackers": trackers, "ultralytics.trackers.track": track})
+    for name in [k for k, m in sys.modules.items() if k.split(".")[0] == "ultralytics" and getattr(m, "__geotrax_b200_shim__", False)]:
+        del sys.modules[name]            # an earlier shim registration: rebuilt below
+    if _real_package_available("ultralytics"):
+        import importlib
+
+        ul = importlib.import_module("ultralytics")
+        ul.YOLO, ul.RTDETR = YOLO, RTDETR      # module attributes win over ultralytics' lazy __getattr__
+        ul.__geotrax_b200_patched__ = True
+        log.info("geotrax_b200: real ultralytics %s found -- YOLO / RTDETR substituted, trackers / utils / cfg left untouched",
+                 getattr(ul, "__version__", "?"))
+    else:
+        checks = mod("ultralytics.utils.checks", check_yolo=check_yolo)
+        files = mod("ultralytics.utils.files", increment_path=increment_path)
+        utils = mod("ultralytics.utils", checks=checks, files=files)
+        ul = mod("ultralytics", YOLO=YOLO, RTDETR=RTDETR, utils=utils, __version__="8.4.80+geotrax_b200")
+        sys.modules.update({"ultralytics": ul, "ultralytics.utils": utils, "ultralytics.utils.checks": checks, "ultralytics.utils.files": files})
+    have = sys.modules.get("stabilo")
+    if have is not None and not getattr(have, "__geotrax_b200_shim__", False) and not force:
+        log.warning("stabilo is already imported; not replacing it (install_shims(force=True) overrides)")
+        return
     sys.modules["stabilo"] = mod("stabilo", Stabilizer=Stabilizer, __version__="1.2.3+geotrax_b200")

@@ -11,6 +11,14 @@
 ORB, matching, RANSAC and the box warp run in libgeotrax_b200.so (gt_set_reference / gt_stabilize / gt_warp_boxes).  Poor
 matches never raise: the matrix is ``None`` (extract.py:185 then skips the transform row).  Unsupported presets raise
 ``NotImplementedError`` at construction instead of silently computing something else.
+
+Presets of the reference that run here: ``default.yaml`` and ``stable.yaml`` (CLAHE, full-resolution working image, 4000 / 8000 key
+points, ratio 0.8; /root/reference/geotrax/cfg/stable.yaml:115-128), and any ``downsample_ratio`` / ``max_features`` / ``filter_ratio``
+/ mask setting.  Not implemented (constructor raises): detectors other than ORB (sift, rsift, brisk, kaze, akaze), the FLANN
+matcher, filter types other than ``ratio``, affine models, ``ransac_method`` 4 (LMEDS) and 16 (RHO).  ``ransac_method`` 8 and the
+USAC family (32..38, default 38 = MAGSAC++) all run the library's own estimator (fixed ``ransac_max_iter`` hypotheses, MSAC score,
+Gauss-Newton polish -- DESIGN.md section 4.6); ``ransac_confidence`` only ever shortens OpenCV's iteration count and has no
+counterpart here (all ``ransac_max_iter`` hypotheses are always scored).
 """
 from __future__ import annotations
 
@@ -39,7 +47,8 @@ class Stabilizer:
         if matcher_name != "bf": unsupported.append(f"matcher_name={matcher_name!r} (bf)")
         if filter_type != "ratio": unsupported.append(f"filter_type={filter_type!r} (ratio)")
         if transformation_type != "projective": unsupported.append(f"transformation_type={transformation_type!r} (projective)")
-        if clahe: unsupported.append("clahe=True")
+        if int(ransac_method) not in (8, 32, 33, 34, 35, 36, 37, 38):
+            unsupported.append(f"ransac_method={ransac_method} (8 RANSAC or a USAC method 32..38; LMEDS / RHO have no counterpart)")
         if not (0.0 < float(downsample_ratio) <= 1.0): unsupported.append(f"downsample_ratio={downsample_ratio} (0 < r <= 1)")
         if match_query_frame not in ("current", "reference"): unsupported.append(f"match_query_frame={match_query_frame!r}")
         if unsupported:
@@ -47,7 +56,9 @@ class Stabilizer:
         self.cfg = dict(downsample_ratio=float(downsample_ratio), max_features=int(max_features), ref_multiplier=float(ref_multiplier),
                         mask_use=bool(mask_use), mask_margin_ratio=float(mask_margin_ratio), filter_ratio=float(filter_ratio),
                         ransac_epipolar_threshold=float(ransac_epipolar_threshold), ransac_max_iter=int(ransac_max_iter),
-                        match_query_frame=match_query_frame)
+                        match_query_frame=match_query_frame, clahe=bool(clahe), ransac_space=str(other.get("ransac_space", "working")))
+        if int(ransac_method) != 38:
+            log.warning("stabilizer: ransac_method=%d requested; the B200 estimator (MSAC + local optimisation) is used for every supported method", int(ransac_method))
         self.ransac_method, self.ransac_confidence = int(ransac_method), float(ransac_confidence)  # the estimator is the library's own
         self.min_good, self.min_inl = int(min_good_match_count_warning), int(min_inliers_match_count_warning)
         self.device = session.device_index(device)
@@ -57,6 +68,8 @@ class Stabilizer:
         self._boxes: Optional[np.ndarray] = None
         self._stats = np.zeros(4, np.int32)
         self._have_ref = False
+        self._ref_frame: Optional[np.ndarray] = None      # host copy of the reference frame (restores the handle's state, see _engine_for)
+        self._ref_boxes: Optional[np.ndarray] = None
 
     # -- engine --------------------------------------------------------------------------------------------------------------
     def _engine_for(self, frame: np.ndarray):
@@ -68,9 +81,16 @@ class Stabilizer:
             eng = session.find_for_stabilizer(hw, self.device, self.cfg)
             if eng is None:
                 eng = session.acquire(hw, None, 4, "detect", self.device, 1, self.cfg)
-            if eng is not self._eng:
-                self._have_ref = False
             self._eng = eng
+        # The reference lives in the handle.  If the handle was re-created (a larger batch was requested from the session) or another
+        # Stabilizer object set its own reference on the shared handle, this object's reference is restored from its host copy.
+        if self._have_ref and getattr(eng, "_ref_owner", None) is not self:
+            if self._ref_frame is None or tuple(self._ref_frame.shape[:2]) != hw:
+                raise GtError("Stabilizer: frame size changed after set_ref_frame()")
+            eng.preprocess(self._ref_frame[None])
+            eng._frame_token = None
+            eng.set_reference(0, self._ref_boxes)
+            eng._ref_owner = self
         return eng
 
     def _upload(self, eng, frame: np.ndarray):
@@ -88,11 +108,14 @@ class Stabilizer:
 
     # -- stabilo surface -----------------------------------------------------------------------------------------------------
     def set_ref_frame(self, frame: np.ndarray, boxes=None) -> None:
+        self._have_ref = False
         eng = self._engine_for(frame)
         self._upload(eng, frame)
         b = self._clean_boxes(boxes)
         eng.set_reference(0, b)
+        eng._ref_owner = self
         self._have_ref = True
+        self._ref_frame, self._ref_boxes = np.ascontiguousarray(frame).copy(), (None if b is None else b.copy())
         self._H, self._boxes = None, b
         self._stats[:] = 0
 

@@ -1,10 +1,13 @@
 """Host-side tracker hand-off: a BOUNDARY of the hot path, not part of it.
 
 The reference tracks with ultralytics' BoT-SORT on the CPU (``trackers/track.py:on_predict_postprocess_end``), fed by the
-detector's ``Boxes`` and the frame.  That tracker stays host code and is not rewritten here.  ``make_tracker`` returns the
-real ultralytics tracker when that package is importable, otherwise ``GreedyIoUTracker`` -- a deliberately small stand-in
-with the same ``update(det, img, feats) -> rows [x1,y1,x2,y2,id,score,cls,det_idx]`` contract, so that ``boxes.id`` is
-populated and the reference's output files keep their shape when ultralytics is absent (as in this image).
+detector's ``Boxes`` and the frame (/root/reference/geotrax/extract.py:153 ``model.track(..., tracker=<yaml>)``; the yaml is written
+by /root/reference/geotrax/utils/config_utils.py:197-226 from cfg/default.yaml:361-379).  That tracker stays host code and is not
+rewritten here.  ``make_tracker`` builds the REAL ultralytics tracker (``TRACKER_MAP[tracker_type]``) from that yaml whenever the
+package is importable.  When it is not (this image), it raises -- track ids are the product's main output and must not silently come
+from something else -- unless the caller opts in to ``GreedyIoUTracker``, a deliberately small stand-in with the same
+``update(det, img, feats) -> rows [x1,y1,x2,y2,id,score,cls,det_idx]`` contract: ``tracker='greedy-iou'`` or the environment variable
+``GEOTRAX_B200_TRACKER=greedy-iou`` (for the unmodified CLI).
 """
 from __future__ import annotations
 
@@ -67,18 +70,61 @@ class GreedyIoUTracker:
         return np.concatenate([xyxy, ids[:, None].astype(np.float32), conf[:, None], cls[:, None], np.arange(n, dtype=np.float32)[:, None]], 1)
 
 
-def make_tracker(tracker_cfg=None, frame_rate: int = 30):
-    """ultralytics BOTSORT / BYTETracker built from the yaml the reference passes (``tracker=<path>``), else the stand-in."""
+STAND_IN = "greedy-iou"
+
+
+def _load_tracker_cfg(tracker_cfg):
+    """The tracker yaml the reference passes -> attribute namespace (ultralytics' own loader when present, else PyYAML)."""
+    import types
+
+    if isinstance(tracker_cfg, dict):
+        data = dict(tracker_cfg)
+    else:
+        try:
+            from ultralytics.utils import YAML  # type: ignore
+
+            data = YAML.load(str(tracker_cfg))
+        except ImportError:
+            import yaml
+
+            with open(str(tracker_cfg)) as f:
+                data = yaml.safe_load(f)
     try:
-        import importlib
+        from ultralytics.utils import IterableSimpleNamespace  # type: ignore
 
-        real = importlib.import_module("ultralytics.trackers.track")
-        if getattr(real, "__geotrax_b200_shim__", False):
-            raise ImportError("shim")
-        from ultralytics.utils import IterableSimpleNamespace, YAML  # type: ignore
+        return IterableSimpleNamespace(**data)
+    except ImportError:
+        return types.SimpleNamespace(**data)
 
-        cfg = IterableSimpleNamespace(**YAML.load(tracker_cfg))
-        return real.TRACKER_MAP[cfg.tracker_type](args=cfg, frame_rate=frame_rate)
-    except Exception:
-        log.warning("ultralytics trackers not importable: using the built-in greedy IoU stand-in tracker (ids only; not BoT-SORT)")
+
+def make_tracker(tracker_cfg=None, frame_rate: int = 30):
+    """ultralytics BOTSORT / BYTETracker built from the yaml the reference passes (``tracker=<path>``).
+
+    ``tracker_cfg``: path / dict of a tracker yaml (``tracker_type: botsort | bytetrack`` ...), ``None`` (ultralytics' default
+    ``botsort.yaml``), or ``'greedy-iou'`` for the stand-in.  Raises ``GtError`` when the real tracker is unavailable and the
+    stand-in was not asked for."""
+    import importlib
+    import os
+
+    from ._lib import GtError
+
+    if tracker_cfg == STAND_IN or (tracker_cfg is None and os.environ.get("GEOTRAX_B200_TRACKER", "") == STAND_IN):
         return GreedyIoUTracker()
+    try:
+        real = importlib.import_module("ultralytics.trackers.track")
+    except ImportError as err:
+        if os.environ.get("GEOTRAX_B200_TRACKER", "") == STAND_IN:
+            log.warning("ultralytics trackers not importable: GEOTRAX_B200_TRACKER=greedy-iou selects the stand-in tracker (ids only; not BoT-SORT)")
+            return GreedyIoUTracker()
+        raise GtError("ultralytics.trackers is not importable, so BoT-SORT / ByteTrack cannot run.  Install ultralytics (the shims leave its "
+                      "trackers untouched), or opt in to the IoU stand-in with tracker='greedy-iou' / GEOTRAX_B200_TRACKER=greedy-iou") from err
+    if getattr(real, "__geotrax_b200_shim__", False):
+        raise GtError("ultralytics.trackers resolves to a geotrax_b200 shim module; re-run install_shims()")
+    if tracker_cfg is None:
+        root = os.path.dirname(importlib.import_module("ultralytics").__file__)
+        tracker_cfg = os.path.join(root, "cfg", "trackers", "botsort.yaml")
+    cfg = _load_tracker_cfg(tracker_cfg)
+    kind = getattr(cfg, "tracker_type", None)
+    if kind not in real.TRACKER_MAP:
+        raise GtError(f"tracker_type {kind!r} is not one of ultralytics' TRACKER_MAP {sorted(real.TRACKER_MAP)}")
+    return real.TRACKER_MAP[kind](args=cfg, frame_rate=frame_rate)

@@ -117,12 +117,45 @@ class _Stub:
 
 
 class _RestrictedUnpickler(pickle.Unpickler):
-    _ALLOW = ("torch", "collections", "numpy", "builtins", "_codecs")
+    """Unpickler for ultralytics checkpoints that can only rebuild tensors and plain containers.
+
+    ``find_class`` resolves an explicit (module, name) allow-list -- tensor / storage reconstruction, ``OrderedDict``, numpy array and
+    scalar reconstruction, a few harmless builtins -- and turns EVERYTHING else (the pickled ``nn.Module`` tree, but also ``eval``,
+    ``os.system``, ``torch.hub.load`` ...) into an inert ``_Stub`` class whose construction runs no code.  ``copyreg._reconstructor``
+    (protocol < 2 object pickles) is replaced by a version that only ever instantiates ``_Stub`` subclasses."""
+
+    _ALLOWED = {
+        ("collections", "OrderedDict"), ("collections", "defaultdict"),
+        ("builtins", "set"), ("builtins", "frozenset"), ("builtins", "dict"), ("builtins", "list"), ("builtins", "tuple"), ("builtins", "int"),
+        ("builtins", "float"), ("builtins", "bool"), ("builtins", "str"), ("builtins", "bytes"), ("builtins", "bytearray"), ("builtins", "complex"),
+        ("builtins", "slice"), ("builtins", "range"), ("builtins", "object"),
+        ("torch._utils", "_rebuild_tensor_v2"), ("torch._utils", "_rebuild_tensor"), ("torch._utils", "_rebuild_parameter"),
+        ("torch._utils", "_rebuild_parameter_with_state"), ("torch._utils", "_rebuild_qtensor"), ("torch._tensor", "_rebuild_from_type_v2"),
+        ("torch", "Size"), ("torch", "device"), ("torch", "dtype"), ("torch", "Tensor"), ("torch.nn.parameter", "Parameter"),
+        ("torch.serialization", "_get_layout"),
+        ("numpy", "ndarray"), ("numpy", "dtype"), ("numpy.core.multiarray", "_reconstruct"), ("numpy._core.multiarray", "_reconstruct"),
+        ("numpy.core.multiarray", "scalar"), ("numpy._core.multiarray", "scalar"), ("_codecs", "encode"),
+    }
+    _TORCH_TYPED = ("Storage", "Tensor")      # torch.FloatStorage, torch.HalfStorage, torch.cuda.FloatTensor ... : data-only classes
+
+    @staticmethod
+    def _reconstructor(cls, base, state):
+        """copyreg._reconstructor restricted to inert stubs (anything else is refused)."""
+        if not (isinstance(cls, type) and issubclass(cls, _Stub)):
+            raise pickle.UnpicklingError(f"refusing to reconstruct {cls!r} from a checkpoint")
+        return object.__new__(cls)
 
     def find_class(self, module, name):
-        root = module.split(".")[0]
-        if root in self._ALLOW and not (module.startswith("torch.nn.modules") or module.startswith("torch.nn.parallel")):
+        if (module, name) in self._ALLOWED:
             return super().find_class(module, name)
+        if module in ("torch", "torch.storage", "torch.cuda") and name.endswith(self._TORCH_TYPED) and name.isidentifier():
+            obj = super().find_class(module, name)
+            if isinstance(obj, type):
+                return obj
+        if module == "torch" and name in ("float32", "float16", "bfloat16", "float64", "int64", "int32", "int16", "int8", "uint8", "bool"):
+            return getattr(torch, name)
+        if (module, name) == ("copyreg", "_reconstructor"):
+            return self._reconstructor
         return type(name, (_Stub,), {"__module__": module})
 
 

@@ -8,8 +8,11 @@
 Every key of the YAML ``ultralytics:`` block arrives as a keyword (default.yaml:229-354); the ones that drive the kernels are
 ``imgsz, conf, iou, max_det, classes, agnostic_nms, device`` -- the rest are display/IO switches and are accepted and ignored.
 All arithmetic happens in libgeotrax_b200.so (gt_preprocess + gt_detect); a missing library or GPU raises, nothing falls
-back to the CPU.  ``half: false`` in the preset selects ultralytics' fp32 path; this implementation always stores
-activations in 16 bit with f32 accumulation (north_star), checked against the fp32 oracle to 1e-2.
+back to the CPU.  ``half: false`` in the preset selects ultralytics' fp32 path; this implementation stores activations and
+weights in 16 bit with f32 accumulation (north_star), checked against the fp32 oracle to 1e-2.  The storage format is **fp16**
+(11-bit significand: 4-6e-3 on the raw head; bf16's 8 bits give 2.4e-2 and miss the gate -- DESIGN.md section 2).  fp16's range
+ends at 65,504: every decode counts head rows that arrive as inf / NaN (``Engine.health()``), and on the first such row this front
+end re-runs the frame on a bf16 engine (8-bit exponent, fp32's range) and stays there -- loudly, never silently wrong.
 """
 from __future__ import annotations
 
@@ -22,6 +25,10 @@ import numpy as np
 from . import session, weights
 from ._lib import GtError
 from .results import Results
+
+import logging
+
+log = logging.getLogger("geotrax_b200")
 
 DEFAULT_NAMES = {0: "car", 1: "bus", 2: "truck", 3: "motorcycle"}
 
@@ -110,17 +117,27 @@ class YOLO:
         nb = frames.shape[0]
         eng = self._get_engine(frames.shape[1:3], imgsz, device, max_det, nb)
         out: List[Results] = []
-        for b0 in range(0, nb, eng.max_batch):
+        b0 = 0
+        while b0 < nb:
             chunk = frames[b0:b0 + eng.max_batch]
+            h0 = eng.health()
             eng.preprocess(chunk)
             eng._frame_token = session.frame_token(source) if (nb == 1 and isinstance(source, np.ndarray) and source.ndim == 3) else None
             boxes, counts = eng.detect(len(chunk), conf=conf, iou=iou, agnostic=agnostic_nms, classes=classes)
+            if eng.health() > h0:       # inf / NaN reached the head: fp16 range exceeded by this checkpoint's activations
+                if self.act_dtype != "fp16":
+                    raise GtError("detector produced non-finite head values in bf16 storage: the checkpoint or the input is broken")
+                log.warning("fp16 activation overflow detected (%d head rows non-finite): switching this model to bf16 storage", eng.health() - h0)
+                self.act_dtype = "bf16"
+                eng = self._get_engine(frames.shape[1:3], imgsz, device, max_det, nb)
+                continue                # same chunk again on the bf16 engine
             st = eng.stage_times()
             speed = {k: st[k] / len(chunk) for k in ("preprocess", "inference", "postprocess")}
             for i in range(len(chunk)):
                 rows = torch.from_numpy(boxes[i, : counts[i]].copy())
                 kw = {"obb": rows} if self.task == "obb" else {"boxes": rows}
                 out.append(Results(chunk[i], path="", names=self.names, speed=dict(speed), **kw))
+            b0 += len(chunk)
         return out
 
     __call__ = predict
@@ -134,16 +151,16 @@ class YOLO:
             self._tracker = make_tracker(tracker)
             self.trackers = [self._tracker]
         for r in results:
-            det = (r.obb if self.task == "obb" else r.boxes).cpu().numpy()
+            det = (r.obb if self.task == "obb" else r.boxes).cpu().numpy()      # numpy-backed Boxes / OBB: what ultralytics hands its trackers
             if len(det) == 0:
                 continue
-            view = types.SimpleNamespace(xyxy=np.asarray(det.xyxy), conf=np.asarray(det.conf), cls=np.asarray(det.cls),
-                                         xywh=np.asarray(getattr(det, "xywh", det.xyxy)), xywhr=np.asarray(getattr(det, "xywhr", det.xyxy)))
-            tracks = self._tracker.update(view, r.orig_img, None)
+            tracks = self._tracker.update(det, r.orig_img, None)
             if len(tracks) == 0:
                 continue                                         # untracked: boxes.id stays None (extract.py:161-164 writes -1)
             idx = tracks[:, -1].astype(int)
-            if self.task == "obb":
+            if self.task == "obb" and tracks.shape[1] == 9:      # ultralytics trackers: [x, y, w, h, angle, id, score, cls, det_idx]
+                r.update(obb=tracks[:, :-1].astype(np.float32))
+            elif self.task == "obb":                             # stand-in tracker rows are axis-aligned: keep the detector's xywhr
                 d = np.asarray(det.data)[idx]
                 r.update(obb=np.concatenate([d[:, :5], tracks[:, 4:5], d[:, 5:7]], 1).astype(np.float32))
             else:

@@ -66,7 +66,9 @@ typedef struct gt_config {
   int32_t ransac_full_res;     /* 0: threshold applies at working resolution, H conjugated afterwards */
   uint32_t seed;               /* RANSAC sampling seed (deterministic) */
   int32_t act_dtype;           /* 16-bit storage format of activations + weights: GT_ACT_BF16 | GT_ACT_FP16 (f32 accumulate) */
-  int32_t reserved[7];
+  int32_t clahe;               /* 1: CLAHE (clip 2.0, 8x8 tiles, as cv2.createCLAHE) on the gray frame before the working-image resize
+                                  -- stabilo's `clahe: true` (/root/reference/geotrax/cfg/stable.yaml:115); 0 = default preset */
+  int32_t reserved[6];
 } gt_config;
 
 void gt_default_config(gt_config* cfg);
@@ -119,6 +121,14 @@ int gt_get_gray(gt_handle h, int B, uint8_t* out, int32_t* work_h, int32_t* work
  * inference + non_max_suppression + scale_boxes (extract.py:153).                                             */
 int gt_detect(gt_handle h, int B, float conf, float iou, int agnostic, uint32_t classes_mask,
               float* out_boxes, int32_t* out_counts, int32_t* out_keep, void* stream);
+/* classes >= 32 (gt_create accepts nc <= 80; `classes: int | list[int]`, /root/reference/geotrax/cfg/default.yaml:243): a sticky
+ * allow-list used by gt_detect / gt_nms / gt_extract_batch whenever their per-call `classes_mask` is 0.  classes == NULL switches
+ * the filter off (every class passes); n == 0 with a non-NULL pointer filters every class out (ultralytics' `classes=[]`).       */
+int gt_set_class_filter(gt_handle h, const int32_t* classes, int n);
+/* 16-bit overflow guard: cumulative number of anchors whose head row held inf / NaN since gt_create (fp16 activations that left
+ * the format's range reach the head as non-finite values and are dropped from the candidates).  Valid after the call that ran the
+ * detector has synchronised (gt_detect / gt_extract_batch return, or gt_wait).  0 on a healthy engine.                           */
+int gt_get_health(gt_handle h, int64_t* nonfinite_rows);
 /* raw head tensor f32 [B][A][no] (A = anchors, no = 64+nc(+1)), anchor-major; parity gate (1) */
 int gt_get_raw_head(gt_handle h, int B, float* out, int32_t* A, int32_t* no);
 /* any intermediate feature map by ultralytics layer index (0..21): act_dtype NHWC as uint16 bit patterns */

@@ -275,3 +275,51 @@ def postprocess_obb(decoded: torch.Tensor, in_shape, orig_shape, conf=0.25, iou=
         rb[:, :4] = scale_boxes(in_shape, rb[:, :4], orig_shape, xywh=True)
         res.append(torch.cat([rb, o[:, 4:6]], dim=-1))
     return res
+
+
+def clahe_u8(src: np.ndarray, clip_limit: float = 2.0, tiles=(8, 8)) -> np.ndarray:
+    """``cv2.createCLAHE(clipLimit, tileGridSize).apply(src)`` for 8-bit images, restated (OpenCV imgproc/src/clahe.cpp).
+
+    stabilo applies it to the gray frame when ``clahe: true`` (/root/reference/geotrax/cfg/stable.yaml:115; clip 2.0, 8x8 tiles).
+    Steps: extend the image to a multiple of the grid with BORDER_REFLECT_101; per tile a 256-bin histogram, clipped at
+    ``max(1, int(clip * area / 256))``, the excess redistributed (equal batch + strided residual); LUT = rint(cumsum * 255 / area);
+    per pixel the bilinear blend of the four neighbouring tile LUTs in float32 (every product and sum rounded separately).
+    Pinned bit-exact against cv2 in tests/test_oracle_model.py; the CUDA kernels (csrc/clahe.cu) are checked against this / cv2."""
+    import cv2
+
+    tx, ty = tiles
+    h, w = src.shape
+    ext = src if (w % tx == 0 and h % ty == 0) else cv2.copyMakeBorder(src, 0, ty - (h % ty), 0, tx - (w % tx), cv2.BORDER_REFLECT_101)
+    tw, th = ext.shape[1] // tx, ext.shape[0] // ty
+    area = tw * th
+    lut_scale = np.float32(255.0) / np.float32(area)
+    clip = max(int(clip_limit * area / 256), 1) if clip_limit > 0 else 0
+    luts = np.zeros((ty, tx, 256), np.uint8)
+    for j in range(ty):
+        for i in range(tx):
+            hist = np.bincount(ext[j * th:(j + 1) * th, i * tw:(i + 1) * tw].ravel(), minlength=256).astype(np.int64)
+            if clip > 0:
+                clipped = int(np.maximum(hist - clip, 0).sum())
+                hist = np.minimum(hist, clip)
+                batch = clipped // 256
+                resid = clipped - batch * 256
+                hist += batch
+                if resid:
+                    hist[np.arange(0, 256, max(256 // resid, 1))[:resid]] += 1
+            luts[j, i] = np.clip(np.rint(np.cumsum(hist).astype(np.float32) * lut_scale), 0, 255).astype(np.uint8)
+
+    def axis(n, tile, nt):
+        f = np.arange(n, dtype=np.float32) * (np.float32(1.0) / np.float32(tile)) - np.float32(0.5)
+        t1 = np.floor(f).astype(np.int32)
+        a = (f - t1.astype(np.float32)).astype(np.float32)
+        return np.maximum(t1, 0), np.minimum(t1 + 1, nt - 1), a, np.float32(1.0) - a
+
+    x1, x2, xa, xa1 = axis(w, tw, tx)
+    y1, y2, ya, ya1 = axis(h, th, ty)
+    out = np.empty_like(src)
+    for y in range(h):
+        v = src[y]
+        top = luts[y1[y], x1, v].astype(np.float32) * xa1 + luts[y1[y], x2, v].astype(np.float32) * xa
+        bot = luts[y2[y], x1, v].astype(np.float32) * xa1 + luts[y2[y], x2, v].astype(np.float32) * xa
+        out[y] = np.clip(np.rint(top * ya1[y] + bot * ya[y]), 0, 255).astype(np.uint8)
+    return out

@@ -49,7 +49,7 @@ def clip(tmp_path_factory):
 def _config(path):
     ul = dict(task="detect", mode="track", model=MODEL, imgsz=IMGSZ, device=0, conf=0.05, iou=0.7, max_det=300, classes=[0, 1, 2, 3], augment=False,
               agnostic_nms=True, half=False, dnn=False, vid_stride=1, stream_buffer=False, visualize=False, show=False, save=False,
-              save_txt=False, save_conf=True, verbose=False, tracker=None)
+              save_txt=False, save_conf=True, verbose=False, tracker="greedy-iou")   # no ultralytics in this image: the stand-in is an explicit opt-in
     stab = dict(clahe=False, downsample_ratio=0.5, detector_name="orb", max_features=2000, ref_multiplier=2.0, sift_enable_precise_upscale=False,
                 rsift_eps=1e-8, matcher_name="bf", filter_type="ratio", filter_ratio=0.9, transformation_type="projective", ransac_method=38,
                 ransac_epipolar_threshold=2.0, ransac_max_iter=5000, ransac_confidence=0.999999, mask_use=False, mask_margin_ratio=0.15,   # random-init boxes would mask the whole frame

@@ -153,3 +153,15 @@ def test_nv12_restatement_matches_cv2(hw):
     frame = rng.integers(0, 256, hw + (3,), dtype=np.uint8)
     rt = prepost.bgr_to_nv12(frame)                                    # helper layout check: Y plane + interleaved chroma
     assert rt.shape == (hw[0] * 3 // 2, hw[1]) and np.array_equal(rt[:hw[0]], cv2.cvtColor(frame, cv2.COLOR_BGR2YUV_I420)[:hw[0]])
+
+
+@pytest.mark.parametrize("shape", [(270, 480), (135, 250), (547, 961)])
+def test_clahe_restatement_matches_cv2(shape):
+    """oracle/prepost.py:clahe_u8 == cv2.createCLAHE(2.0, (8, 8)).apply, bit for bit (divisible and reflect-extended tile grids)."""
+    import cv2
+    from oracle import prepost
+    rng = np.random.default_rng(shape[0])
+    base = cv2.GaussianBlur(rng.integers(0, 256, shape, dtype=np.uint8), (0, 0), 3)
+    img = np.clip(base.astype(np.int32) + rng.integers(-25, 25, shape), 0, 255).astype(np.uint8)
+    img[: shape[0] // 3, : shape[1] // 4] //= 4          # a dark, low-contrast corner: clipping and redistribution actually happen
+    assert np.array_equal(prepost.clahe_u8(img), cv2.createCLAHE(clipLimit=2.0, tileGridSize=(8, 8)).apply(img))
