@@ -64,7 +64,7 @@ class ClockSampler(threading.Thread):
 
     def __init__(self, index: int):
         super().__init__(daemon=True)
-        self.index, self.rows, self._halt = index, [], threading.Event()
+        self.index, self.rows, self.times, self._halt = index, [], [], threading.Event()
 
     def run(self):
         while not self._halt.is_set():
@@ -73,6 +73,7 @@ class ClockSampler(threading.Thread):
                                      capture_output=True, text=True, timeout=5).stdout.strip()
                 if out:
                     self.rows.append([c.strip() for c in out.split(",")])
+                    self.times.append(time.perf_counter())
             except Exception:
                 pass
             self._halt.wait(0.2)
@@ -88,7 +89,19 @@ class ClockSampler(threading.Thread):
             for n, v in zip(names, r[3:7]):
                 if v.lower().startswith("active"):
                     reasons.add(n)
-        return dict(sm_mhz=float(np.median(sm)) if sm else None, sm_max_mhz=max(mx) if mx else None, reasons=sorted(reasons), samples=len(self.rows))
+        pw = [float(r[2]) for r in self.rows if len(r) > 2 and r[2].replace(".", "").isdigit()]
+        return dict(sm_mhz=float(np.median(sm)) if sm else None, sm_max_mhz=max(mx) if mx else None, reasons=sorted(reasons), samples=len(self.rows),
+                    power_w_median=float(np.median(pw)) if pw else None)
+
+    def windows(self, t0: float, width: float = 1.0):
+        """Per-`width`-second medians of SM clock and power since t0 (sustained-run report)."""
+        out = {}
+        for t, r in zip(self.times, self.rows):
+            k = int((t - t0) // width)
+            if k < 0 or not r[0].replace(".", "").isdigit():
+                continue
+            out.setdefault(k, []).append((float(r[0]), float(r[2]) if r[2].replace(".", "").isdigit() else float("nan")))
+        return {k: dict(sm_mhz=float(np.median([a for a, _ in v])), power_w=float(np.nanmedian([b for _, b in v]))) for k, v in sorted(out.items())}
 
 
 # ------------------------------------------------------------------------------------------------------------------------
@@ -163,7 +176,7 @@ def run_ours(args):
     import torch.distributed as dist
 
     import geotrax_b200
-    from geotrax_b200 import synth, weights
+    from geotrax_b200 import pipeline, synth, weights
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -193,6 +206,7 @@ def run_ours(args):
     ref_np = frames_np[:1].copy()
     # vehicle masks = the generator's 132 golden-like boxes per frame ("dense vehicle masks", configs[2]); in the reference
     # they are the tracker's boxes (extract.py:166,181) -- a random-init detector's own boxes are meaningless as masks
+    # (tests/test_gpu_round2.py::test_mask_source_moves_centres_less_than_half_a_pixel bounds what the mask source changes)
     mask = eng.pack_boxes(flight[1])
     mask_list = flight[1]
     mask_dev = (torch.from_numpy(mask[0]).to(dev), torch.from_numpy(mask[1]).to(dev))
@@ -212,87 +226,64 @@ def run_ours(args):
     stream = tstream.cuda_stream
     eng.extract_batch(torch.from_numpy(ref_np).to(dev), first_is_reference=True, conf=CONF, iou=IOU, classes=[0, 1, 2, 3], out=out, stream=stream,
                       mask_boxes=mask_ref)
+    fused = args.workload in ("fused", "obb", "flight")
+    pipelined = fused and not args.no_pipeline
+    det_kw = dict(conf=CONF, iou=IOU, agnostic=True, classes=[0, 1, 2, 3], stream=stream)
 
-    rec = None
-    gathered = None
-    if world > 1:  # fixed-stride per-frame records gathered to rank 0: counts | boxes | H | status
-        rec_len = BATCH * (1 + eng.max_det * 6 + 9 + 1)
-        rec = torch.zeros(rec_len, dtype=torch.float32, device=dev)
-        gathered = [torch.zeros_like(rec) for _ in range(world)] if rank == 0 else None
-
-    outs = [out, eng.alloc_outputs(pinned=True)]      # two pinned output sets: batch i+1 is enqueued before batch i is read
-    pipelined = args.workload in ("fused", "obb") and not args.no_pipeline
-
-    def publish(o):
-        if world > 1:
-            h = torch.from_numpy(np.concatenate([o["counts"].astype(np.float32).ravel(), o["boxes"].ravel(), o["H"].astype(np.float32).ravel(),
-                                                 o["status"].astype(np.float32).ravel()]))
-            rec.copy_(h, non_blocking=True)
-            dist.gather(rec, gathered, dst=0)
-
-    def step_async(src, i):
-        """enqueue batch i (gt_extract_batch_async); returns (outputs, ticket)"""
-        if src is frames_dev:
-            mb = mask_dev
-        else:
-            src, nxt, mb = frames_pin[i % 2], frames_pin[(i + 1) % 2], (mask_pin if i % 2 == 0 else mask_roll_pin)
-            eng.prefetch(nxt)
-        return eng.extract_batch(src, conf=CONF, iou=IOU, agnostic=True, classes=[0, 1, 2, 3], out=outs[i % 2], stream=stream, mask_boxes=mb, sync=False)
-
-    def step(src, i=0, last=False):
-        if src is frames_dev:
-            mb = mask_dev
-        else:   # end-to-end: pinned host frames; the H2D copy of step i+1 is started before step i's kernels (double-buffered ingest)
-            src, nxt, mb = frames_pin[i % 2], frames_pin[(i + 1) % 2], (mask_pin if i % 2 == 0 else mask_roll_pin)
-            # steady-state ingest: EVERY step starts the H2D copy of the next batch before its own kernels, so the timed region holds
-            # exactly `steps` copies of 398 MB (the first timed batch was started by the last warm-up step, the copy started by the
-            # last timed step is never consumed but is synchronised inside the region)
-            eng.prefetch(nxt)
-        if args.workload == "detect":        # configs[1]: letterbox + detector + decode/NMS, boxes read back
+    def single_stage_step(src):
+        """configs[1] / configs[2] alone (N = 1 diagnostics; not the sharded driver)"""
+        if args.workload == "detect":        # letterbox + detector + decode/NMS, boxes read back
             eng.preprocess(src, stream=stream)
             bx, cnt = eng.detect(int(src.shape[0]), conf=CONF, iou=IOU, agnostic=True, classes=[0, 1, 2, 3], stream=stream)
             out["boxes"][...] = bx
             out["counts"][...] = cnt
-            o = out
-        elif args.workload == "stabilize":   # configs[2]: gray/half-res + ORB + match + RANSAC against the reference frame, H read back
+        else:                                # gray/half-res + ORB + match + RANSAC against the reference frame, H read back
             eng.preprocess(src, stream=stream)
             Hm, st_, stats = eng.stabilize(int(src.shape[0]), mask_list, stream=stream)
             out["H"][...] = Hm.reshape(-1, 9)
             out["status"][...] = st_
             out["stats"][...] = stats
-            o = out
-        else:
-            o = eng.extract_batch(src, conf=CONF, iou=IOU, agnostic=True, classes=[0, 1, 2, 3], out=out, stream=stream, mask_boxes=mb)
-        publish(o)
-        return o
 
-    def timed(src, steps):
+    def timed(host: bool, steps: int, seconds: float = 0.0):
+        """`steps` batches of BATCH frames through the PRODUCT's sharded driver: pipeline.run_range (two batches in flight, prefetched
+        H2D for host frames) on this rank's frames, then pipeline.gather_records to rank 0 (NCCL) -- all inside the timed region."""
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         l0 = eng.launch_count()
-        t0 = time.perf_counter()
-        e0.record()
-        stage = np.zeros(4)
-        conv_ms = 0.0
-        def account():
-            nonlocal conv_ms
+        stage, conv, marks = np.zeros(4), [0.0], []
+
+        def account(b0=0, b1=0):
             st = eng.stage_times()
             stage[:] += [st["preprocess"], st["inference"], st["postprocess"], st["stabilize"]]
-            conv_ms += eng.conv_stack_stats()[0]
-        pending = None
-        for i in range(steps):
-            if pipelined:   # batch i is enqueued before batch i-1 is read back: the GPU does not idle between batches
-                cur = step_async(src, i)
-                if pending is not None:
-                    eng.wait(pending[1]); account(); publish(pending[0])
-                pending = cur
+            conv[0] += eng.conv_stack_stats()[0]
+            marks.append(time.perf_counter())
+
+        if host:
+            get_frames = lambda a, b: frames_pin[(a // BATCH) % 2]
+            get_masks = lambda a, b: (mask_pin if (a // BATCH) % 2 == 0 else mask_roll_pin)
+        else:
+            get_frames = lambda a, b: frames_dev
+            get_masks = lambda a, b: mask_dev
+        t0 = time.perf_counter()
+        e0.record()
+        done = 0
+        while True:
+            if fused:
+                # steady-state ingest: every step starts the H2D copy of the NEXT batch (the last one that of the following round's first
+                # batch), so the timed region holds exactly `steps` copies of 398 MB; the first batch was put in flight by the previous round
+                rec_local = pipeline.run_range(eng, get_frames, 0, steps * BATCH, 0, batch=BATCH, get_masks=get_masks, set_reference=False,
+                                               pipelined=pipelined, on_batch=account,
+                                               next_range_frames=get_frames(steps * BATCH, (steps + 1) * BATCH) if host else None, **det_kw)
+                pipeline.gather_records(rec_local, rank, world, dev)
             else:
-                step(src, i, i == steps - 1)
-                account()
-        if pending is not None:
-            eng.wait(pending[1]); account(); publish(pending[0])
+                for i in range(steps):
+                    single_stage_step(frames_pin[i % 2] if host else frames_dev)
+                    account()
+            done += steps
+            if time.perf_counter() - t0 >= seconds:
+                break
         e1.record()
         torch.cuda.synchronize()
         if world > 1:
@@ -303,39 +294,48 @@ def run_ours(args):
             t = torch.tensor([ms, wall * 1000], device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             ms, wall = float(t[0]), float(t[1]) / 1000
-        return ms, wall, stage / steps, conv_ms / steps, eng.launch_count() - l0
+        return dict(ms=ms, wall=wall, stage=stage / done, conv_ms=conv[0] / done, launches=eng.launch_count() - l0, steps=done, t0=t0, marks=marks)
 
-    for _ in range(max(args.warmup, 3)):
-        step(frames_dev)
+    timed(False, max(args.warmup, 3))
     sampler = ClockSampler(local)
     sampler.start()
-    ms, wall, stage, conv_ms, launches = timed(frames_dev, args.steps)          # inputs resident in HBM
+    res = timed(False, args.steps, args.seconds if args.workload == "flight" else 0.0)          # inputs resident in HBM
     clocks = sampler.stop()
+    steps_done = res["steps"]
+    ms, stage, conv_ms, launches = res["ms"], res["stage"], res["conv_ms"], res["launches"]
+    flight_windows = None
+    if args.workload == "flight":       # sustained run: frames/s, SM clock and power per one-second window
+        win = sampler.windows(res["t0"])
+        per = {}
+        for t in res["marks"]:
+            per[int(t - res["t0"])] = per.get(int(t - res["t0"]), 0) + BATCH
+        flight_windows = [dict(second=k, frames_per_s=per.get(k, 0), **win.get(k, {})) for k in sorted(per)]
     eng.set_input_format(args.ingest)
-    for i in range(2):
-        step("host", i)
-    ms_e2e, wall_e2e, stage_e2e, _, _ = timed("host", args.steps)               # pinned host frames: H2D inside the timed region
+    timed(True, 2)
+    res2 = timed(True, args.steps)               # pinned host frames: H2D inside the timed region
+    ms_e2e, wall_e2e = res2["ms"], res2["wall"]
     if args.workload == "detect":
         stage[3] = 0.0
     elif args.workload == "stabilize":
         stage[1] = stage[2] = 0.0
         conv_ms = 0.0
-    det_counts = out["counts"].copy()
-    ok_h = int((out["status"] == 0).sum())
+    det_counts = out["counts"].copy() if not fused else None
+    health = eng.health()
 
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
     peaks = _peaks()
-    total_frames = world * args.steps * BATCH
+    total_frames = world * steps_done * BATCH
     value = total_frames / (ms / 1000)
-    e2e = total_frames / max(wall_e2e, ms_e2e / 1000)
+    e2e = world * args.steps * BATCH / max(wall_e2e, ms_e2e / 1000)
     gflop_frame = 150.04 if args.workload == "obb" else CONV_GFLOP_PER_FRAME   # +cv4 branch for OBB
     conv_tflops = gflop_frame * BATCH / conv_ms if conv_ms > 0 else 0.0  # GFLOP / ms = TFLOP/s
     wl_name = {"fused": "detect+stabilize (configs[1]+[2] fused)", "detect": "detect+NMS only (configs[1])",
-               "stabilize": "ORB+match+RANSAC homography only (configs[2])", "obb": "YOLOv8s-OBB rotated NMS + stabilization (configs[3])"}[args.workload]
-    metric = METRIC if args.workload == "fused" else f"4K frames/sec {args.workload}"
+               "stabilize": "ORB+match+RANSAC homography only (configs[2])", "obb": "YOLOv8s-OBB rotated NMS + stabilization (configs[3])",
+               "flight": "sustained detect+stabilize flight (configs[4] per-GPU share)"}[args.workload]
+    metric = METRIC if args.workload in ("fused", "flight") else f"4K frames/sec {args.workload}"
     h2d = int(host_batches[0].nbytes)
     d2h = int(sum(v.nbytes for v in out.values()))
     h2d += int(mask[0].nbytes + mask[1].nbytes)
@@ -351,8 +351,9 @@ def run_ours(args):
             cpu.frame(frames_np[1 + i % (BATCH - 1)])
         cdt = time.perf_counter() - t0
         cpu_base = dict(value=n / cdt, unit=UNIT, cores=cores, kind="port", sample=f"{n} of the step's {BATCH} frames, batch 1, fp32 PyTorch + OpenCV")
-    # per-stage roofline fractions (algorithmic bytes / flops per frame from SURVEY.md 8d and DESIGN.md 4; peaks measured)
-    per_frame = dict(preprocess=("hbm", 43.67e6), inference=("tensor", gflop_frame * 1e9), postprocess=("hbm", 5.83e6), stabilize=("hbm", 30.0e6))
+    # per-stage roofline fractions: algorithmic bytes / flops per frame from SURVEY.md 8d (preprocess 39.49 MB = 24.88 read + 12.53 net input
+    # + 2.07 gray) and DESIGN.md 4; peaks measured (MEASURED_PEAKS.json)
+    per_frame = dict(preprocess=("hbm", 39.49e6), inference=("tensor", gflop_frame * 1e9), postprocess=("hbm", 5.83e6), stabilize=("hbm", 30.0e6))
     stages = {}
     for name, ms_stage in zip(("preprocess", "inference", "postprocess", "stabilize"), stage):
         kind, work = per_frame[name]
@@ -362,28 +363,41 @@ def run_ours(args):
         pk = peaks["tf_sust"] * 1e12 if kind == "tensor" else peaks["hbm"] * 1e9
         stages[name] = dict(ms_per_step=float(ms_stage), bound=kind, achieved=rate / (1e12 if kind == "tensor" else 1e9),
                             unit="TFLOP/s" if kind == "tensor" else "GB/s", frac=rate / pk)
-    roof = dict(bound="tensor", achieved=conv_tflops, peak=peaks["tf_sust"], unit="TFLOP/s", frac=conv_tflops / peaks["tf_sust"], traffic=_conv_traffic(),
-                kernel="conv_tc_kernel / conv_sw_kernel x60 (the conv stack of one 16-frame step = one launch set; traffic = dram bytes of that set, ncu)",
-                peak_source=peaks["src"] + " bf16_tflops_sustained", algorithmic_flops_per_launch_set=gflop_frame * BATCH * 1e9)
+        if kind == "tensor":
+            stages[name]["frac_vs_burst_peak"] = rate / (peaks["tf_burst"] * 1e12)
+    # which peak applies: the burst figure for a kernel timed alone / a short run at full clocks, the sustained one inside a long step
+    sm = clocks.get("sm_mhz") or 0.0
+    use_burst = sm >= 0.95 * (clocks.get("sm_max_mhz") or 1e9)
+    peak_tf = peaks["tf_burst"] if use_burst else peaks["tf_sust"]
+    roof = dict(bound="tensor", achieved=conv_tflops, peak=peak_tf, unit="TFLOP/s", frac=conv_tflops / peak_tf, traffic=_conv_traffic(),
+                frac_vs_sustained_peak=conv_tflops / peaks["tf_sust"], frac_vs_burst_peak=conv_tflops / peaks["tf_burst"],
+                kernel="conv_tc_kernel / conv_sw_kernel launch set (the conv stack of one 16-frame step; traffic = dram bytes of that set, ncu)",
+                peak_source=peaks["src"] + (" bf16_tflops (burst: the run sat at max SM clock)" if use_burst else " bf16_tflops_sustained (SM clock below max)"),
+                algorithmic_flops_per_launch_set=gflop_frame * BATCH * 1e9)
     if args.workload == "stabilize":
         st = stages.get("stabilize", dict(achieved=0.0, frac=0.0))
         roof = dict(bound="hbm", achieved=st["achieved"], peak=peaks["hbm"], unit="GB/s", frac=st["frac"], traffic=None,
-                    kernel="ORB pyramid + FAST + select + describe + match + RANSAC launch set of one 16-frame step (dominant: fast_kernel)",
+                    kernel="ORB pyramid + FAST + select + describe + match + RANSAC launch set of one 16-frame step",
                     peak_source=peaks["src"] + " hbm_gbs", algorithmic_bytes_per_launch_set=30.0e6 * BATCH)
-    line = dict(metric=metric, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=max(args.warmup, 3), ms_per_step=ms / args.steps,
-                higher_is_better=True, scaling="weak", vs_baseline=None, dtype=args.dtype, data="synthetic",
-                config=dict(workload=wl_name + ": 16 x 3840x2160 synthetic BGR frames / step, YOLOv8s nc=4 random-init "
-                                     "imgsz 1920 (1088x1920), conf 0.25 iou 0.7 agnostic, ORB 2000/4000 + Hamming 2-NN + 5000-hyp RANSAC, box warp",
-                            frames_per_step=BATCH, parallelism=f"frame-range shard x{world}", pipeline=("two batches in flight (gt_extract_batch_async)" if pipelined else "synchronous"), l2="inputs (398 MB / step) larger than the 126 MB L2",
-                            stage_ms_per_step=dict(preprocess=stage[0], inference=stage[1], postprocess=stage[2], stabilize=stage[3]),
-                            detections_per_frame=float(det_counts.mean()), mask_boxes_per_frame=float(mask[1].mean()), homographies_ok=f"{ok_h}/{BATCH}",
-                            matches_per_frame=float(out["stats"][:, 2].mean()), inliers_per_frame=float(out["stats"][:, 3].mean()),
-                            conv_launches_per_step=eng.conv_kernel_info()[0], convs_on_swapped_kernel=eng.conv_kernel_info()[1]),
-                roofline=roof, stages=stages,
-                cpu_baseline=cpu_base,
+    cfg = dict(workload=wl_name + ": 16 x 3840x2160 synthetic BGR frames / step, YOLOv8s nc=4 random-init "
+                                  "imgsz 1920 (1088x1920), conf 0.25 iou 0.7 agnostic, ORB 2000/4000 + Hamming 2-NN + 5000-hyp RANSAC, box warp",
+               frames_per_step=BATCH, parallelism=f"frame-range shard x{world}",
+               driver="pipeline.run_range + gather_records (the product's sharded driver)" if fused else "single-stage loop",
+               pipeline=("two batches in flight (gt_extract_batch_async)" if pipelined else "synchronous"), l2="inputs (398 MB / step) larger than the 126 MB L2",
+               stage_ms_per_step=dict(preprocess=stage[0], inference=stage[1], postprocess=stage[2], stabilize=stage[3]),
+               mask_boxes_per_frame=float(mask[1].mean()), storage_dtype=args.dtype, nonfinite_head_rows=health,
+               conv_launches_per_step=eng.conv_kernel_info()[0], convs_on_swapped_kernel=eng.conv_kernel_info()[1],
+               conv_variant_choice="fixed table / rule keyed by layer signature (identical in every process)")
+    if det_counts is not None:
+        cfg["detections_per_frame"] = float(det_counts.mean())
+    line = dict(metric=metric, value=value, unit=UNIT, n_gpus=world, steps=steps_done, warmup=max(args.warmup, 3), ms_per_step=ms / steps_done,
+                higher_is_better=True, scaling="weak", vs_baseline=None, dtype=args.dtype, data="synthetic", config=cfg,
+                roofline=roof, stages=stages, cpu_baseline=cpu_base,
                 e2e=dict(value=e2e, unit=UNIT, h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h, ms_per_step=1000 * wall_e2e / args.steps,
                          ingest=args.ingest),
                 gpu_launches=int(launches), clocks=clocks)
+    if flight_windows is not None:
+        line["flight"] = dict(seconds=res["wall"], frames=total_frames, windows=flight_windows)
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
@@ -401,9 +415,11 @@ def main():
     ap.add_argument("--ingest", default="bgr24", choices=["bgr24", "nv12"],
                     help="host frame format of the end-to-end leg: bgr24 = what the reference's reader delivers (default, the headline); "
                          "nv12 = decoder format (SURVEY 8f rank 1), half the PCIe bytes, converted on the device")
-    ap.add_argument("--workload", default="fused", choices=["fused", "detect", "stabilize", "obb"],
+    ap.add_argument("--seconds", type=float, default=15.0, help="--workload flight: keep running whole `--steps` rounds until this much wall time has passed")
+    ap.add_argument("--workload", default="fused", choices=["fused", "detect", "stabilize", "obb", "flight"],
                     help="fused = BASELINE configs[1]+[2] (default, the headline); detect = configs[1] (YOLOv8s detect+NMS only); "
-                         "stabilize = configs[2] (ORB + match + RANSAC + warp only); obb = configs[3] (YOLOv8s-OBB rotated NMS + stabilization)")
+                         "stabilize = configs[2] (ORB + match + RANSAC + warp only); obb = configs[3] (YOLOv8s-OBB rotated NMS + stabilization); "
+                         "flight = the fused path sustained for --seconds with per-second frames/s, SM clock and power (configs[4] per-GPU share)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

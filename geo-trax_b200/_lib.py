@@ -59,6 +59,7 @@ SYMBOLS = {
     "gt_detect": (_i, [_H, _i, _f, _f, _i, _u, _P, _P, _P, _P]),
     "gt_set_class_filter": (_i, [_H, _ip, _i]),
     "gt_get_health": (_i, [_H, C.POINTER(C.c_int64)]),
+    "gt_get_candidate_counts": (_i, [_H, _i, _P]),
     "gt_get_raw_head": (_i, [_H, _i, _P, _ip, _ip]),
     "gt_get_feature": (_i, [_H, _i, _i, _P, _ip, _ip, _ip]),
     "gt_nms": (_i, [_H, _P, _i, _i, _i, _i, _f, _f, _i, _u, _i, _P, _P, _P, _P]),

@@ -403,6 +403,14 @@ int gt_get_health(gt_handle e, int64_t* nonfinite_rows) {
   return GT_OK;
 }
 
+int gt_get_candidate_counts(gt_handle e, int B, int32_t* out_counts) {
+  ENTER(e);
+  GT_CHECK(e, out_counts && B >= 1 && B <= e->cfg.max_batch, "gt_get_candidate_counts: bad arguments");
+  GT_CUDA(e, cudaStreamSynchronize(e->stream));
+  GT_CUDA(e, cudaMemcpy(out_counts, e->cand_count, sizeof(int) * B, cudaMemcpyDefault));
+  return GT_OK;
+}
+
 int gt_get_raw_head(gt_handle e, int B, float* out, int32_t* A, int32_t* no) {
   ENTER(e);
   if (A) *A = e->A;

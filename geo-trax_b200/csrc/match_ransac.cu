@@ -198,9 +198,11 @@ __device__ __forceinline__ unsigned hash32(unsigned x) {
   return x;
 }
 
-// deterministic 4-sample for hypothesis h of frame b; returns false if 4 distinct indices could not be drawn
-__device__ __forceinline__ bool draw_sample(unsigned seed, int b, int h, int m, int* s) {
-  unsigned st = hash32(seed ^ hash32((unsigned)b * 0x9E3779B9u + (unsigned)h));
+// deterministic 4-sample for hypothesis h; returns false if 4 distinct indices could not be drawn.  The sample is a function of
+// (seed, h, m) only -- NOT of the batch slot b the frame happens to sit in -- so a frame yields the same homography whichever batch
+// composition / rank / shard processes it (the sharded flight equals the single-GPU flight bit for bit, tests/test_gpu_round2.py).
+__device__ __forceinline__ bool draw_sample(unsigned seed, int /*b*/, int h, int m, int* s) {
+  unsigned st = hash32(seed ^ hash32(0x9E3779B9u + (unsigned)h));
   int got = 0;
   for (int tries = 0; tries < 16 && got < 4; ++tries) {
     st = hash32(st + 0x6D2B79F5u);

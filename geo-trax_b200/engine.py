@@ -183,6 +183,12 @@ class Engine:
                                     _ptr(keep), stream))
         return (boxes, counts, keep) if want_keep else (boxes, counts)
 
+    def candidate_counts(self, B: int) -> np.ndarray:
+        """Candidates per frame that passed the confidence / class filter in the last decode (before NMS)."""
+        out = np.zeros((B,), np.int32)
+        self._ck(self.lib.gt_get_candidate_counts(self.h, B, out.ctypes.data))
+        return out
+
     def raw_head(self, B: int) -> np.ndarray:
         out = np.empty((B, self.A, self.no), np.float32)
         self._ck(self.lib.gt_get_raw_head(self.h, B, out.ctypes.data, None, None))

@@ -26,27 +26,74 @@ def frame_ranges(n_frames: int, world: int, start: int = 0) -> List[Tuple[int, i
 
 
 def run_range(engine, get_frames: Callable[[int, int], np.ndarray], lo: int, hi: int, ref_frame_index: int, batch: int = 16, conf: float = 0.25,
-              iou: float = 0.7, agnostic: bool = True, classes: Optional[Sequence[int]] = None, stream=None) -> Dict[str, np.ndarray]:
-    """Runs frames [lo, hi) of a flight through ``engine.extract_batch`` in batches; -> per-frame arrays (see keys below).
+              iou: float = 0.7, agnostic: bool = True, classes: Optional[Sequence[int]] = None, stream=None,
+              get_masks: Optional[Callable[[int, int], tuple]] = None, set_reference: bool = True, pipelined: Optional[bool] = None,
+              on_batch: Optional[Callable[[int, int], None]] = None, next_range_frames=None) -> Dict[str, np.ndarray]:
+    """Runs frames [lo, hi) of a flight through the engine in batches; -> per-frame arrays (see keys below).
 
     The frame ``ref_frame_index`` (the first processed frame of the whole video, ``cut_frame_left``) is the stabilizer
-    reference: processed first on every rank; its own record is only kept by the rank that owns it."""
+    reference: processed first on every rank (``set_reference=False`` when the engine already holds it); its own record is only
+    kept by the rank that owns it.
+
+    ``get_frames(a, b)`` returns frames [a, b) as a (n, H, W, 3) u8 array: numpy (pageable or pinned) or a CUDA tensor.  With an
+    engine that has the asynchronous entry points the loop keeps TWO batches in flight (``gt_extract_batch_async`` / ``gt_wait``):
+    batch i+1 is enqueued -- and, for host frames, its H2D copy started (``gt_prefetch_frames``) -- before batch i is read back, so
+    the GPU never idles between batches.  ``get_masks(a, b)`` (optional) returns the ``(boxes, counts)`` pair of
+    ``Engine.pack_boxes`` used as ORB vehicle masks (the tracker's boxes in the reference, extract.py:166,181); default: this
+    batch's own detections.  ``on_batch(b0, b1)`` is called after each batch's outputs are valid (progress / timing hooks).
+    ``next_range_frames``: host frames of the batch that FOLLOWS this range (chunked / streaming ingest): their H2D copy is started
+    during the last batch, so the next ``run_range`` call finds its first batch already on the device (steady-state ingest)."""
     md, row = engine.max_det, engine.row
     n = max(hi - lo, 0)
     res = dict(frame=np.arange(lo, hi, dtype=np.int64), count=np.zeros(n, np.int32), status=np.zeros(n, np.int32), stats=np.zeros((n, 4), np.int32),
                H=np.zeros((n, 9), np.float64), boxes=np.zeros((n, md, row), np.float32), boxes_stab=np.zeros((n, md, 4), np.float32))
-    ref = engine.extract_batch(get_frames(ref_frame_index, ref_frame_index + 1), first_is_reference=True, conf=conf, iou=iou, agnostic=agnostic,
-                               classes=classes, stream=stream)
-    ref = {k: v.copy() for k, v in ref.items()}
-    out = engine.alloc_outputs()
-    for b0 in range(lo, hi, batch):
-        b1 = min(b0 + batch, hi)
-        o = engine.extract_batch(get_frames(b0, b1), conf=conf, iou=iou, agnostic=agnostic, classes=classes, out=out, stream=stream)
-        s = slice(b0 - lo, b1 - lo)
-        k = b1 - b0
+    kw = dict(conf=conf, iou=iou, agnostic=agnostic, classes=classes, stream=stream)
+    ref = None
+    if set_reference:
+        rm = get_masks(ref_frame_index, ref_frame_index + 1) if get_masks else None
+        ref = engine.extract_batch(get_frames(ref_frame_index, ref_frame_index + 1), first_is_reference=True, mask_boxes=rm, **kw) if rm is not None \
+            else engine.extract_batch(get_frames(ref_frame_index, ref_frame_index + 1), first_is_reference=True, **kw)
+        ref = {k: v.copy() for k, v in ref.items()}
+    if pipelined is None:
+        pipelined = hasattr(engine, "wait")
+    starts = list(range(lo, hi, batch))
+
+    def store(o, b0, b1):
+        s, k = slice(b0 - lo, b1 - lo), b1 - b0
         res["count"][s], res["status"][s], res["stats"][s], res["H"][s] = o["counts"][:k], o["status"][:k], o["stats"][:k], o["H"][:k]
         res["boxes"][s], res["boxes_stab"][s] = o["boxes"][:k], o["boxes_stab"][:k]
-    if lo <= ref_frame_index < hi:   # the reference frame maps to itself: identity, boxes unchanged (extract.py:176-179)
+        if on_batch:
+            on_batch(b0, b1)
+
+    if not pipelined:
+        out = engine.alloc_outputs()
+        for b0 in starts:
+            b1 = min(b0 + batch, hi)
+            mk = dict(mask_boxes=get_masks(b0, b1)) if get_masks else {}
+            store(engine.extract_batch(get_frames(b0, b1), out=out, **mk, **kw), b0, b1)
+    else:
+        outs = getattr(engine, "_pipeline_outs", None)       # two pinned output sets, allocated once per engine
+        if outs is None:
+            outs = engine._pipeline_outs = [engine.alloc_outputs(pinned=True), engine.alloc_outputs(pinned=True)]
+        is_host = lambda f: isinstance(f, np.ndarray) or (hasattr(f, "is_cuda") and not f.is_cuda)
+        nxt = get_frames(starts[0], min(starts[0] + batch, hi)) if starts else None
+        pending = None                      # (ticket, outputs, b0, b1, frames kept alive, masks kept alive)
+        for i, b0 in enumerate(starts):
+            b1 = min(b0 + batch, hi)
+            cur = nxt
+            nxt = get_frames(starts[i + 1], min(starts[i + 1] + batch, hi)) if i + 1 < len(starts) else next_range_frames
+            if nxt is not None and is_host(nxt) and hasattr(engine, "prefetch"):
+                engine.prefetch(nxt, deferred=True)        # copy of batch i+1 starts right after batch i's own small uploads
+            mk = get_masks(b0, b1) if get_masks else None
+            o, t = engine.extract_batch(cur, out=outs[i % 2], mask_boxes=mk, sync=False, **kw)
+            if pending is not None:
+                engine.wait(pending[0])
+                store(pending[1], pending[2], pending[3])
+            pending = (t, o, b0, b1, cur, mk)
+        if pending is not None:
+            engine.wait(pending[0])
+            store(pending[1], pending[2], pending[3])
+    if ref is not None and lo <= ref_frame_index < hi:   # the reference frame maps to itself: identity, boxes unchanged (extract.py:176-179)
         i = ref_frame_index - lo
         res["count"][i], res["status"][i], res["stats"][i] = ref["counts"][0], 0, ref["stats"][0]
         res["H"][i] = np.eye(3).ravel()

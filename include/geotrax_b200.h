@@ -129,6 +129,8 @@ int gt_set_class_filter(gt_handle h, const int32_t* classes, int n);
  * the format's range reach the head as non-finite values and are dropped from the candidates).  Valid after the call that ran the
  * detector has synchronised (gt_detect / gt_extract_batch return, or gt_wait).  0 on a healthy engine.                           */
 int gt_get_health(gt_handle h, int64_t* nonfinite_rows);
+/* candidates per frame that passed the confidence / class filter in the last decode (before NMS; capped by max_nms inside NMS) */
+int gt_get_candidate_counts(gt_handle h, int B, int32_t* out_counts);
 /* raw head tensor f32 [B][A][no] (A = anchors, no = 64+nc(+1)), anchor-major; parity gate (1) */
 int gt_get_raw_head(gt_handle h, int B, float* out, int32_t* A, int32_t* no);
 /* any intermediate feature map by ultralytics layer index (0..21): act_dtype NHWC as uint16 bit patterns */

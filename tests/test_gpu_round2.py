@@ -1,0 +1,495 @@
+"""Round-2 parity gates (VERDICT r1 "Next round" item 1 and ADVICE r1), all through the C-ABI on a real B200:
+
+ * gate (2) END TO END: GPU forward + decode + NMS against the fp32 oracle's forward + decode + NMS at BASELINE's full size, margin-aware
+ * outputs bit-identical across processes (the conv kernel variant is a fixed function of the layer signature)
+ * pipeline.run_flight on real Engines: 2 ranks == 1 rank, np.array_equal (NCCL with >= 2 GPUs, gloo on one)
+ * ORB key points / descriptors identical to cv2.ORB at the real working resolution WITH vehicle masks and the 4000-point reference
+ * mask source (detector boxes vs tracker-like boxes) moves stabilised centres < 0.5 px; the non-default [U] switches
+ * CLAHE / the `stable` preset, class ids >= 32, the fp16 overflow guard
+"""
+import hashlib
+import json
+import os
+import socket
+import subprocess
+import sys
+
+import cv2
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HW, IMGSZ = (2160, 3840), 1920
+
+
+# ---------------------------------------------------------------------------------------------------------------------------------
+# gate (2), end to end, margin-aware
+# ---------------------------------------------------------------------------------------------------------------------------------
+@pytest.fixture(scope="module")
+def full_engine4():
+    import geotrax_b200
+    from geotrax_b200 import weights
+    eng = geotrax_b200.Engine(frame_hw=HW, imgsz=IMGSZ, nc=4, max_batch=4)
+    sd = weights.random_state_dict(4, "detect", seed=0, frame_hw=HW, imgsz=IMGSZ, cls_bias=-4.4)
+    eng.load_weights(weights.fold(sd))
+    eng._sd = sd
+    yield eng
+    eng.close()
+
+
+@pytest.fixture(scope="module")
+def oracle_dense(full_engine4):
+    """fp32 oracle forward of 4 BASELINE-size frames: decoded dense predictions (B, 4 + nc, A), letterbox pixels."""
+    from geotrax_b200 import synth
+    from oracle import prepost
+    from oracle.yolov8 import YOLOv8
+    frames = np.stack(synth.make_flight(5, HW[0], HW[1], seed=100)[0][1:5])
+    m = YOLOv8(4).eval()
+    m.load_state_dict(full_engine4._sd, strict=False)
+    dec = []
+    with torch.no_grad():
+        for f in frames:
+            d, _ = m(prepost.preprocess([f], IMGSZ))
+            dec.append(d[0].numpy())
+    return frames, np.stack(dec)
+
+
+def _iou_matrix(a, b):
+    x1 = np.maximum(a[:, None, 0], b[None, :, 0]); y1 = np.maximum(a[:, None, 1], b[None, :, 1])
+    x2 = np.minimum(a[:, None, 2], b[None, :, 2]); y2 = np.minimum(a[:, None, 3], b[None, :, 3])
+    inter = np.clip(x2 - x1, 0, None) * np.clip(y2 - y1, 0, None)
+    aa = (a[:, 2] - a[:, 0]) * (a[:, 3] - a[:, 1]); ab = (b[:, 2] - b[:, 0]) * (b[:, 3] - b[:, 1])
+    return inter / np.maximum(aa[:, None] + ab[None, :] - inter, 1e-12)
+
+
+def _interval_nms(dec, conf_thr, iou_thr, agnostic, eps_c, eps_i, max_wh=7680.0):
+    """Greedy NMS of the ORACLE's dense predictions with every threshold comparison widened by a margin.
+
+    Returns (sure, maybe, cls, cls_sure, xyxy): anchors that are kept whatever happens inside the margins, anchors whose fate depends on a
+    comparison inside a margin (confidence within eps_c of the threshold or of a competitor's, IoU within eps_i of the threshold, class
+    decided by less than eps_c, or a suppressor that is itself uncertain), the oracle class of every anchor, whether that class is decided
+    by more than eps_c, and the letterbox boxes."""
+    box, prob = dec[:4].T, dec[4:].T                             # (A, 4) xywh, (A, nc)
+    conf, cls = prob.max(1), prob.argmax(1)
+    top2 = np.sort(prob, 1)[:, -2] if prob.shape[1] > 1 else np.zeros_like(conf)
+    cls_sure = (conf - top2) > eps_c
+    cand = np.nonzero(conf > conf_thr - eps_c)[0]
+    cand = cand[np.argsort(-conf[cand], kind="stable")]
+    xyxy = np.concatenate([box[:, :2] - box[:, 2:] / 2, box[:, :2] + box[:, 2:] / 2], 1)
+    c, b = conf[cand], xyxy[cand].astype(np.float64)
+    iou = _iou_matrix(b, b)
+    n = len(cand)
+    state = np.zeros(n, np.int8)                                  # 0 suppressed for sure, 1 kept for sure, 2 uncertain
+    same_sure = np.ones((n, n), bool) if agnostic else (cls[cand][:, None] == cls[cand][None, :]) & cls_sure[cand][:, None] & cls_sure[cand][None, :]
+    same_maybe = np.ones((n, n), bool) if agnostic else (cls[cand][:, None] == cls[cand][None, :]) | ~cls_sure[cand][:, None] | ~cls_sure[cand][None, :]
+    for i in range(n):
+        higher_sure = (c > c[i] + eps_c)                          # certainly processed before i
+        higher_maybe = (c > c[i] - eps_c)                         # possibly processed before i
+        higher_maybe[i] = False
+        sup_sure = np.any(higher_sure[:i] & (state[:i] == 1) & (iou[i, :i] > iou_thr + eps_i) & same_sure[i, :i])
+        if sup_sure:
+            state[i] = 0
+            continue
+        alive = np.ones(n, bool)
+        alive[:i] = state[:i] != 0                                # later (not yet decided) competitors inside the margin count as possibly kept
+        sup_maybe = np.any(higher_maybe & alive & (iou[i] > iou_thr - eps_i) & same_maybe[i])
+        state[i] = 2 if (sup_maybe or c[i] <= conf_thr + eps_c) else 1
+    return set(cand[state == 1].tolist()), set(cand[state == 2].tolist()), cls, cls_sure, xyxy
+
+
+@pytest.mark.parametrize("agnostic", [True, False], ids=["agnostic", "class-aware"])
+def test_gate2_end_to_end_margin_aware(full_engine4, oracle_dense, agnostic):
+    """north_star criterion (2) END TO END: GPU forward -> decode -> NMS against the fp32 oracle forward -> decode -> NMS on four
+    3840x2160 frames.  Every oracle decision that does not hinge on a comparison inside a small margin (confidence 0.01, IoU 0.02 --
+    the size of the 16-bit storage error on these quantities) must be reproduced EXACTLY: the anchor is kept, with the same class,
+    and its box matches at IoU >= 0.99; and the GPU may keep nothing the oracle certainly drops."""
+    from oracle import prepost
+    eng = full_engine4
+    frames, dense = oracle_dense
+    eng.preprocess(frames)
+    boxes, counts, keep = eng.detect(4, conf=0.25, iou=0.7, agnostic=agnostic, classes=[0, 1, 2, 3], want_keep=True)
+    tot_sure = tot_maybe = 0
+    for b in range(4):
+        sure, maybe, cls, cls_sure, xyxy = _interval_nms(dense[b], 0.25, 0.7, agnostic, eps_c=0.01, eps_i=0.02)
+        n = int(counts[b])
+        got = {int(a): boxes[b, i] for i, a in enumerate(keep[b, :n])}
+        missing = sure - set(got)
+        extra = set(got) - sure - maybe
+        assert not missing, f"frame {b}: {len(missing)} anchors the oracle certainly keeps are missing on the GPU: {sorted(missing)[:8]}"
+        assert not extra, f"frame {b}: the GPU keeps {len(extra)} anchors the oracle certainly drops: {sorted(extra)[:8]}"
+        for a in sure:
+            row = got[a]
+            if cls_sure[a]:
+                assert int(row[5]) == int(cls[a]), f"frame {b} anchor {a}: class {int(row[5])} vs oracle {int(cls[a])}"
+            ref = prepost.scale_boxes((1088, 1920), torch.from_numpy(xyxy[a:a + 1].astype(np.float32).copy()), HW).numpy()
+            iou = _iou_matrix(ref.astype(np.float64), row[None, :4].astype(np.float64))[0, 0]
+            assert iou >= 0.99, f"frame {b} anchor {a}: box IoU {iou:.4f}"
+        tot_sure += len(sure); tot_maybe += len(maybe)
+        print(f"frame {b}: gpu kept {n}, oracle certainly-kept {len(sure)}, inside-the-margin {len(maybe)}")
+    assert tot_sure >= 100 and tot_sure > 2 * tot_maybe, f"the test must not be vacuous: {tot_sure} certain vs {tot_maybe} margin anchors"
+
+
+# ---------------------------------------------------------------------------------------------------------------------------------
+# determinism across processes
+# ---------------------------------------------------------------------------------------------------------------------------------
+_CHILD = r"""
+import hashlib, json, sys
+import numpy as np
+sys.path.insert(0, sys.argv[1])
+import geotrax_b200
+from geotrax_b200 import synth, weights
+hw, imgsz = (1080, 1920), 960
+eng = geotrax_b200.Engine(frame_hw=hw, imgsz=imgsz, nc=4, max_batch=int(sys.argv[2]), max_det=300)
+eng.load_weights(weights.fold(weights.random_state_dict(4, "detect", seed=0, frame_hw=hw, imgsz=imgsz, cls_bias=-4.0)))
+frames, boxes, _ = synth.make_flight(3, hw[0], hw[1], seed=7, n_vehicles=40)
+out0 = eng.extract_batch(np.stack(frames[:1]), first_is_reference=True, conf=0.05, mask_boxes=eng.pack_boxes(boxes[:1]))
+out = eng.extract_batch(np.stack(frames[1:3]), conf=0.05, mask_boxes=eng.pack_boxes(boxes[1:3]))
+raw = eng.raw_head(2)
+h = lambda a: hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+print(json.dumps(dict(raw=h(raw), boxes=h(out["boxes"][:2]), counts=out["counts"][:2].tolist(), H=h(out["H"][:2]), stab=h(out["boxes_stab"][:2]),
+                      kernels=list(eng.conv_kernel_info()) + [eng.conv_pair_count()])))
+"""
+
+
+def test_two_fresh_processes_give_identical_bytes():
+    """Outputs are reproducible across processes AND across batch capacities: two fresh interpreters (no shared tune cache -- there is
+    none any more: the per-layer kernel variant is a table / rule keyed by the layer signature) hash identical raw-head, box, H bytes."""
+    runs = []
+    for max_batch in ("2", "2", "4"):
+        r = subprocess.run([sys.executable, "-c", _CHILD, ROOT, max_batch], capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, r.stderr[-2000:]
+        runs.append(json.loads(r.stdout.strip().splitlines()[-1]))
+    assert runs[0] == runs[1], "two fresh processes differ"
+    assert {k: v for k, v in runs[0].items()} == {k: v for k, v in runs[2].items()}, "batch capacity changes the output bytes"
+
+
+# ---------------------------------------------------------------------------------------------------------------------------------
+# pipeline.run_flight on real engines: sharded == single
+# ---------------------------------------------------------------------------------------------------------------------------------
+FL_HW, FL_IMGSZ, FL_N = (540, 960), 480, 14
+
+
+def _flight_engine(device):
+    import geotrax_b200
+    from geotrax_b200 import weights
+    eng = geotrax_b200.Engine(frame_hw=FL_HW, imgsz=FL_IMGSZ, nc=4, max_batch=4, max_det=300, max_features=1000, device=device)
+    eng.load_weights(weights.fold(weights.random_state_dict(4, "detect", seed=0, frame_hw=FL_HW, imgsz=FL_IMGSZ, cls_bias=-4.0)))
+    return eng
+
+
+def _flight_data():
+    from geotrax_b200 import synth
+    frames, boxes, _ = synth.make_flight(FL_N, FL_HW[0], FL_HW[1], seed=33, n_vehicles=20)
+    return np.stack(frames), boxes
+
+
+def _run_flight(rank, world, device, gather_device):
+    from geotrax_b200 import pipeline
+    eng = _flight_engine(device)
+    try:
+        frames, boxes = _flight_data()
+        get_frames = lambda a, b: frames[a:b]
+        get_masks = lambda a, b: eng.pack_boxes(boxes[a:b])
+        lo, hi = pipeline.frame_ranges(FL_N, world, 0)[rank]
+        local = pipeline.run_range(eng, get_frames, lo, hi, 0, batch=4, conf=0.05, get_masks=get_masks)
+        rec = pipeline.gather_records(local, rank, world, gather_device)
+        if rank != 0:
+            return None
+        from geotrax_b200.tracker import GreedyIoUTracker
+        return pipeline.replay_tracks(rec, GreedyIoUTracker(), eng.warp_boxes, 0, frame_hw=FL_HW)
+    finally:
+        eng.close()
+
+
+def _flight_worker(rank, world, port, backend, q):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    ngpu = torch.cuda.device_count()
+    device = rank % ngpu
+    torch.cuda.set_device(device)
+    dist.init_process_group(backend, rank=rank, world_size=world)
+    out = _run_flight(rank, world, device, torch.device("cuda", device) if backend == "nccl" else None)
+    if rank == 0:
+        q.put(out)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_run_flight_sharded_equals_single_on_real_engines():
+    """The product's multi-GPU driver (pipeline.run_range -> gather_records -> replay_tracks) on REAL engines: two ranks give exactly the
+    single-rank arrays.  NCCL gather with >= 2 GPUs (one rank per GPU); on a one-GPU box both ranks share the GPU and gather over gloo."""
+    import torch.multiprocessing as mp
+    single = _run_flight(0, 1, 0, None)
+    backend = "nccl" if torch.cuda.device_count() >= 2 else "gloo"
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_flight_worker, args=(r, 2, port, backend, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    tracks, transforms = q.get(timeout=600)
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    print("backend", backend, "tracks", tracks.shape, "transforms", transforms.shape)
+    assert len(transforms) >= FL_N - 2 and len(tracks) > 50
+    assert np.array_equal(transforms, single[1]), "homographies differ between the sharded and the single-rank run"
+    assert np.array_equal(tracks, single[0]), "tracks differ between the sharded and the single-rank run"
+
+
+# ---------------------------------------------------------------------------------------------------------------------------------
+# ORB at the real working resolution, with masks; mask source; [U] switches
+# ---------------------------------------------------------------------------------------------------------------------------------
+@pytest.fixture(scope="module")
+def full_engine2():
+    import geotrax_b200
+    eng = geotrax_b200.Engine(frame_hw=HW, imgsz=IMGSZ, nc=4, max_batch=2)
+    yield eng
+    eng.close()
+
+
+@pytest.fixture(scope="module")
+def full_flight():
+    from geotrax_b200 import synth
+    return synth.make_flight(3, HW[0], HW[1], seed=100)
+
+
+def _compare_keypoints(kp, desc, ref_kp, ref_desc, min_common):
+    ref = {(round(k.pt[0], 2), round(k.pt[1], 2), k.octave): (k, d) for k, d in zip(ref_kp, ref_desc)}
+    got = {(round(float(r[0]), 2), round(float(r[1]), 2), int(r[5])): (r, d) for r, d in zip(kp, desc)}
+    common = set(ref) & set(got)
+    ang_bad = resp_bad = bit_bad = 0
+    for key in common:
+        k, d = ref[key]
+        r, dd = got[key]
+        ang_bad += abs(((r[3] - k.angle) + 180) % 360 - 180) > 0.02
+        resp_bad += abs(r[4] - k.response) > 1e-5 * max(1e-9, abs(k.response)) + 1e-12
+        bit_bad += int(np.unpackbits(np.bitwise_xor(d, dd)).sum())
+    print(f"opencv {len(ref)} gpu {len(got)} common {len(common)} angle-bad {ang_bad} response-bad {resp_bad} descriptor bit errors {bit_bad}")
+    assert len(common) >= min_common * len(ref), f"only {len(common)} of {len(ref)} OpenCV key points reproduced"
+    assert abs(len(got) - len(ref)) <= 0.01 * len(ref)
+    assert ang_bad <= 0.01 * len(common) and resp_bad <= 0.01 * len(common)
+    assert bit_bad <= 0.002 * 256 * len(common)
+
+
+@pytest.mark.parametrize("as_reference", [False, True], ids=["current-2000", "reference-4000"])
+def test_orb_identity_fullres_with_masks(full_engine2, full_flight, as_reference):
+    """Key-point identity against cv2.ORB at the REAL working resolution (1920x1080 = half of 3840x2160) WITH the 132-box vehicle mask,
+    for the 2000-point current frame and the 4000-point reference; through the box path (mask_rects_kernel + mask pyramid), i.e. exactly
+    what gt_set_reference / gt_stabilize run."""
+    from oracle.stabilo_cv import build_mask, to_gray_half
+    eng = full_engine2
+    frames, boxes, _ = full_flight
+    f, bx = frames[1], boxes[1]
+    g = to_gray_half(f, 0.5)
+    mask = build_mask(bx, 0.15, 0.5, g.shape[1], g.shape[0])
+    assert (mask == 0).mean() > 0.02
+    ref_kp, ref_desc = cv2.ORB_create(nfeatures=4000 if as_reference else 2000).detectAndCompute(g, mask)
+    eng.preprocess(np.stack([f]))
+    assert np.array_equal(eng.gray(1)[0], g)
+    if as_reference:
+        eng.set_reference(0, bx)
+        kp, desc = eng.keypoints(1, 0)
+        _, m0 = eng.pyramid_level(1, 0, 0)
+    else:
+        eng.set_reference(0, bx)
+        eng.stabilize(1, [bx])
+        kp, desc = eng.keypoints(0, 0)
+        _, m0 = eng.pyramid_level(0, 0, 0)
+    assert np.array_equal(m0, mask), "level-0 vehicle mask differs from the oracle's rectangles"
+    _compare_keypoints(kp, desc, ref_kp, ref_desc, 0.98)
+
+
+def _stab_centres(eng, frames, boxes, mask_boxes):
+    eng.preprocess(np.stack(frames[:1]))
+    eng.set_reference(0, mask_boxes[0])
+    eng.preprocess(np.stack(frames[1:3]))
+    H, status, stats = eng.stabilize(2, mask_boxes[1:3])
+    assert status.tolist() == [0, 0]
+    return [eng.warp_boxes(H[i], boxes[1 + i]) for i in range(2)], stats
+
+
+def test_mask_source_moves_centres_less_than_half_a_pixel(full_engine2, full_flight):
+    """in the reference the ORB mask comes from the TRACKER's boxes of the same frame (extract.py:166,181); bench.py and
+    the sharded driver mask with the generator's / the detector's boxes.  Tracker-like boxes (Kalman-smoothed: jittered by a few pixels,
+    a few tracks lost, a few coasting ghosts) must move the stabilised centres by < 0.5 px mean."""
+    frames, boxes, _ = full_flight
+    rng = np.random.default_rng(5)
+    alt = []
+    for b in boxes:
+        t = b.copy()
+        t[:, :2] += rng.normal(0, 2.0, t[:, :2].shape)                   # positional lag / smoothing
+        t[:, 2:] *= rng.uniform(0.93, 1.07, t[:, 2:].shape)
+        t = t[rng.random(len(t)) > 0.06]                                  # lost tracks
+        ghosts = np.stack([rng.uniform(100, HW[1] - 100, 5), rng.uniform(100, HW[0] - 100, 5), rng.uniform(60, 110, 5), rng.uniform(30, 50, 5)], 1)
+        alt.append(np.concatenate([t, ghosts]).astype(np.float32))
+    a, sa = _stab_centres(full_engine2, frames, boxes, boxes)
+    b, sb = _stab_centres(full_engine2, frames, boxes, alt)
+    for i in range(2):
+        d = np.linalg.norm(a[i][:, :2] - b[i][:, :2], axis=1)
+        print(f"frame {i + 1}: centre shift from the mask source mean {d.mean():.4f} max {d.max():.4f} px; matches {sa[i][2]} vs {sb[i][2]}")
+        assert d.mean() < 0.5
+
+
+@pytest.mark.parametrize("switch", ["query_reference", "ransac_full_res", "both"])
+def test_non_default_unpinned_switches_match_oracle(switch):
+    """The [U] glue of SURVEY (query/train order, where the 0.5x rescale is applied) is a constructor switch on both sides; the non-default
+    values run on the GPU and agree with the OpenCV oracle under the same switch (criterion 3: centres < 0.5 px mean)."""
+    import geotrax_b200
+    from geotrax_b200 import synth
+    from oracle.stabilo_cv import Stabilizer as OStab
+    hw = (1080, 1920)
+    q_ref, full = switch in ("query_reference", "both"), switch in ("ransac_full_res", "both")
+    eng = geotrax_b200.Engine(frame_hw=hw, imgsz=960, nc=4, max_batch=2, max_det=300, query_is_current=0 if q_ref else 1, ransac_full_res=1 if full else 0)
+    try:
+        frames, boxes, Hs = synth.make_flight(3, hw[0], hw[1], seed=11, n_vehicles=40)
+        ora = OStab(match_query_frame="reference" if q_ref else "current", ransac_space="full" if full else "working")
+        ora.set_ref_frame(frames[0], boxes[0])
+        got, stats = _stab_centres(eng, frames, boxes, boxes)
+        for i in range(2):
+            ora.stabilize(frames[1 + i], boxes[1 + i])
+            want = ora.transform_cur_boxes()
+            d = np.linalg.norm(got[i][:, :2] - want[:, :2], axis=1)
+            print(f"{switch} frame {i + 1}: matches gpu {stats[i][2]} oracle {ora.get_cur_num_matches()} centre err {d.mean():.3f}")
+            assert d.mean() < 0.5
+            assert abs(int(stats[i][2]) - ora.get_cur_num_matches()) <= 0.03 * ora.get_cur_num_matches()
+    finally:
+        eng.close()
+
+
+# ---------------------------------------------------------------------------------------------------------------------------------
+# CLAHE / stable preset
+# ---------------------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("hw,imgsz,ratio", [((512, 768), 384, 0.5), ((512, 768), 384, 1.0), ((380, 676), 480, 0.5), ((375, 667), 384, 1.0)])
+def test_clahe_working_image_bit_exact(hw, imgsz, ratio):
+    """cfg.clahe: gray -> cv2.createCLAHE(2.0, (8, 8)) -> working-image resize, bit-exact (tile grids that divide the frame and that need
+    the reflect-101 extension; fused and table-driven letterbox paths); the detector input is unaffected."""
+    import geotrax_b200
+    from oracle import prepost
+    eng = geotrax_b200.Engine(frame_hw=hw, imgsz=imgsz, nc=4, max_batch=2, max_det=100, max_features=300, downsample_ratio=ratio, clahe=1)
+    try:
+        rng = np.random.default_rng(2)
+        base = cv2.GaussianBlur(rng.integers(0, 256, (2,) + hw + (3,), dtype=np.uint8).reshape(2 * hw[0], hw[1], 3), (0, 0), 2).reshape((2,) + hw + (3,))
+        frames = np.clip(base.astype(np.int32) + rng.integers(-30, 30, base.shape), 0, 255).astype(np.uint8)
+        frames[0, : hw[0] // 2] //= 3
+        eng.preprocess(frames)
+        gray = eng.gray(2)
+        clahe = cv2.createCLAHE(clipLimit=2.0, tileGridSize=(8, 8))
+        for i in range(2):
+            g = clahe.apply(cv2.cvtColor(frames[i], cv2.COLOR_BGR2GRAY))
+            if ratio != 1.0:
+                g = cv2.resize(g, (int(hw[1] * ratio), int(hw[0] * ratio)), interpolation=cv2.INTER_LINEAR)
+            assert np.array_equal(gray[i], g), f"CLAHE working image differs from cv2 (frame {i}): {(gray[i] != g).sum()} pixels"
+        ref = prepost.preprocess(list(frames), imgsz).numpy()
+        assert np.array_equal(eng.net_input(2).astype(np.float32) / np.float32(255.0), ref)
+    finally:
+        eng.close()
+
+
+def test_stable_preset_runs_and_matches_oracle():
+    """The reference's shipped `stable` preset (/root/reference/geotrax/cfg/stable.yaml:115-128: CLAHE, full-resolution working image,
+    4000 / 8000 key points, ratio 0.8) through the Stabilizer shim, against the OpenCV oracle with the same settings."""
+    import geotrax_b200
+    from geotrax_b200 import session, synth
+    from oracle.stabilo_cv import Stabilizer as OStab
+    kw = dict(clahe=True, downsample_ratio=1.0, max_features=4000, ref_multiplier=2.0, filter_ratio=0.8, mask_use=True, mask_margin_ratio=0.15)
+    frames, boxes, Hs = synth.make_flight(3, 1080, 1920, seed=12, n_vehicles=40)
+    st, ora = geotrax_b200.Stabilizer(**kw), OStab(**kw)
+    try:
+        st.set_ref_frame(frames[0], boxes[0]); ora.set_ref_frame(frames[0], boxes[0])
+        for i in (1, 2):
+            st.stabilize(frames[i], boxes[i]); ora.stabilize(frames[i], boxes[i])
+            assert st.get_cur_trans_matrix() is not None
+            d = np.linalg.norm(st.transform_cur_boxes()[:, :2] - ora.transform_cur_boxes()[:, :2], axis=1)
+            n_ref, n_cur = st.get_cur_num_keypoints()
+            print(f"stable preset frame {i}: kp {n_ref}/{n_cur} (oracle {ora.get_cur_num_keypoints()}), matches {st.get_cur_num_matches()} "
+                  f"(oracle {ora.get_cur_num_matches()}), centre err {d.mean():.3f}")
+            assert d.mean() < 0.5
+            assert abs(n_ref - ora.get_cur_num_keypoints()[0]) <= 0.02 * n_ref and abs(n_cur - ora.get_cur_num_keypoints()[1]) <= 0.02 * n_cur
+    finally:
+        session.close_all()
+
+
+# ---------------------------------------------------------------------------------------------------------------------------------
+# class ids >= 32, scalar classes, fp16 overflow guard, reference restore
+# ---------------------------------------------------------------------------------------------------------------------------------
+def test_class_filter_beyond_32_classes():
+    """`classes=[40]` must not be truncated to "no filter"; nc up to 80; scalar `classes: 2`; `classes=[]` keeps nothing."""
+    import geotrax_b200
+    from oracle import prepost
+    eng = geotrax_b200.Engine(frame_hw=(512, 768), imgsz=384, nc=80, max_batch=2, max_det=300, max_features=300)
+    try:
+        rng = np.random.default_rng(1)
+        A, nc = 2000, 80
+        xy, wh = rng.uniform(0, 380, (2, A, 2)), rng.uniform(8, 60, (2, A, 2))
+        cls = rng.uniform(0, 0.2, (2, A, nc))
+        hot = rng.random((2, A)) < 0.3
+        cls[hot, rng.integers(0, nc, hot.sum())] = rng.uniform(0.3, 0.99, hot.sum())
+        pred = np.concatenate([xy, wh, cls], 2).astype(np.float32)
+        for classes in ([40, 3], [79], 2, [0, 31, 32, 64], None, []):
+            rows, counts, keep = eng.nms(pred, nc, False, 0.25, 0.7, False, classes, 300)
+            cl = None if classes is None else ([classes] if isinstance(classes, int) else classes)
+            ref, idxs = prepost.non_max_suppression(torch.from_numpy(pred).permute(0, 2, 1), 0.25, 0.7, cl if cl else None, False, 300, nc=nc, return_idxs=True)
+            for b in range(2):
+                n = int(counts[b])
+                if classes == []:
+                    assert n == 0
+                    continue
+                assert n == len(ref[b]) and n > 0, (classes, n, len(ref[b]))
+                assert np.array_equal(keep[b, :n], idxs[b].numpy()) and np.array_equal(rows[b, :n, 5], ref[b][:, 5].numpy())
+                if cl:
+                    assert set(rows[b, :n, 5].astype(int)) <= set(cl)
+    finally:
+        eng.close()
+
+
+def test_fp16_overflow_is_detected_and_bf16_takes_over():
+    """fp16 storage ends at 65,504.  Weights scaled so that layer 0 overflows: the engine reports non-finite head rows (never silently
+    wrong detections), and the YOLO front end re-runs the frame on bf16 storage and stays there."""
+    import geotrax_b200
+    from geotrax_b200 import session, synth
+    model = geotrax_b200.YOLO("synthetic:nc=4,seed=0,cls_bias=-4.0,hw=512x768,imgsz=384", task="detect")
+    w, b = model._folded["model.0"]
+    frame = synth.make_flight(1, 512, 768, seed=3, n_vehicles=10)[0][0]
+    try:
+        r = model.predict(frame, imgsz=384, conf=0.25, max_det=300)
+        assert model.act_dtype == "fp16" and model._engine.health() == 0
+        model._folded["model.0"] = (w * 3.0e5, b * 3.0e5)
+        model._engine._weights_owner = None                 # force a weight reload on the next call
+        r = model.predict(frame, imgsz=384, conf=0.25, max_det=300)
+        assert model.act_dtype == "bf16", "the overflow must switch the model to bf16 storage"
+        assert np.isfinite(r[0].boxes.data.numpy()).all()
+        fp16_eng = [e for k, e in session._engines.items() if k[6] == "fp16"][0]
+        assert fp16_eng.health() > 0
+        assert model._engine.health() == 0
+    finally:
+        session.close_all()
+
+
+def test_stabilizer_reference_survives_engine_recreation():
+    """session.acquire() re-creates the handle when a larger batch is requested; the Stabilizer must carry its reference over."""
+    import geotrax_b200
+    from geotrax_b200 import session, synth
+    frames, boxes, _ = synth.make_flight(3, 512, 768, seed=8, n_vehicles=12)
+    st = geotrax_b200.Stabilizer(max_features=500)
+    try:
+        st.set_ref_frame(frames[0], boxes[0])
+        st.stabilize(frames[1], boxes[1])
+        H1 = st.get_cur_trans_matrix().copy()
+        old = st._eng
+        key = [k for k, e in session._engines.items() if e is old][0]
+        session.acquire(key[1], key[2], key[3], key[4], key[0], 4, st.cfg, act_dtype=key[6], max_det=key[7])     # larger batch: the old handle is closed
+        assert not old.h
+        st.stabilize(frames[1], boxes[1])
+        assert np.array_equal(st.get_cur_trans_matrix(), H1)
+        st2 = geotrax_b200.Stabilizer(max_features=500)                      # a second object sharing the handle sets another reference ...
+        st2.set_ref_frame(frames[2], boxes[2])
+        st.stabilize(frames[1], boxes[1])                                    # ... and the first one restores its own
+        assert np.array_equal(st.get_cur_trans_matrix(), H1)
+    finally:
+        session.close_all()
