@@ -244,6 +244,8 @@ def run_ours(args):
             out["status"][...] = st_
             out["stats"][...] = stats
 
+    phase = [0]
+
     def timed(host: bool, steps: int, seconds: float = 0.0):
         """`steps` batches of BATCH frames through the PRODUCT's sharded driver: pipeline.run_range (two batches in flight, prefetched
         H2D for host frames) on this rank's frames, then pipeline.gather_records to rank 0 (NCCL) -- all inside the timed region."""
@@ -260,9 +262,9 @@ def run_ours(args):
             conv[0] += eng.conv_stack_stats()[0]
             marks.append(time.perf_counter())
 
-        if host:
-            get_frames = lambda a, b: frames_pin[(a // BATCH) % 2]
-            get_masks = lambda a, b: (mask_pin if (a // BATCH) % 2 == 0 else mask_roll_pin)
+        if host:   # the two pinned batches alternate across rounds too, so that a round's first batch is the one the previous round prefetched
+            get_frames = lambda a, b: frames_pin[(a // BATCH + phase[0]) % 2]
+            get_masks = lambda a, b: (mask_pin if (a // BATCH + phase[0]) % 2 == 0 else mask_roll_pin)
         else:
             get_frames = lambda a, b: frames_dev
             get_masks = lambda a, b: mask_dev
@@ -282,6 +284,8 @@ def run_ours(args):
                     single_stage_step(frames_pin[i % 2] if host else frames_dev)
                     account()
             done += steps
+            if host:
+                phase[0] += steps
             if time.perf_counter() - t0 >= seconds:
                 break
         e1.record()

@@ -148,6 +148,9 @@ struct gt_engine {
   bool have_ref = false;
   OrbLevel* lv_dev = nullptr;                       // device copy of lv[]
   int* rs_tab[GT_ORB_LEVELS][4] = {};               // per-level resize tables: xofs, xc1, yofs, yc1
+  void* pyr_blocks = nullptr;                       // PyrBlock[pyr_nblocks]: per-tile regions of the single-launch chained pyramid (orb.cu)
+  int pyr_nblocks = 0, pyr_buf_bytes = 0;
+  bool pyr_chain = false;                           // GT_PYR_CHAIN=1: single-launch chained pyramid kernel (measured slower than the 7 per-level launches: 255 vs 160 us / plane / step; kept as an option)
   // matching / RANSAC
   int* match_idx = nullptr;                         // [B][GT_MAX_KP][2]
   int* match_dist = nullptr;                        // [B][GT_MAX_KP][2]
@@ -156,6 +159,7 @@ struct gt_engine {
   float* npairs = nullptr;                          // [B][GT_MAX_KP][4] Hartley-normalised pairs
   float* norms = nullptr;                           // [B][8] normalisation parameters
   float* hyp_score = nullptr;                       // [B][max_iter]
+  int* hyp_hist = nullptr;                          // [B][256] histogram of the subset scores (preemptive RANSAC scoring)
   double* H_dev = nullptr;                          // [B][9]
   int* H_status = nullptr;                          // [B]
   int* H_stats = nullptr;                           // [B][4]

@@ -280,42 +280,142 @@ __device__ __forceinline__ float reproj_err2(const float* H, const float4 q) {
   return du * du + dv * dv;
 }
 
-// one warp per hypothesis: MSAC score (sum of max(0, 1 - e^2/t^2)) over all matches.  The 16 hypotheses of a block share the
-// matches through shared memory (tiles of kScoreTile pairs), four independent accumulation chains per lane.
-constexpr int kScoreWarps = 16, kScoreTile = 1024;
-__global__ void __launch_bounds__(kScoreWarps * 32) ransac_score_kernel(const float4* __restrict__ npairs, const int* __restrict__ counts, int pair_stride,
-                                                                        const Norm* __restrict__ norms, float thr, int max_iter, unsigned seed,
-                                                                        float* __restrict__ scores) {
-  __shared__ float4 s_np[kScoreTile];
+// MSAC score of a hypothesis = sum over matches of max(0, 1 - e^2 / t^2).
+//
+// Preemptive scoring in two launches (the exhaustive round-1 kernel -- one warp per hypothesis, 5,000 hypotheses x ~1,600 matches x 16
+// frames -- was instruction bound at 155-205 us):
+//   pass 1  ransac_score_kernel: ONE THREAD per hypothesis scores it on the strided subset {0, sub, 2 sub, ...} of <= kSubsetPairs matches
+//           (matches are ordered by key-point index = pyramid level, then position, so a stride covers every level and the whole image;
+//           all threads of a block read the same match at the same time = shared-memory broadcast) and files the score in a
+//           per-frame 256-bin histogram (bin = score / subset size: the score of a hypothesis cannot exceed the number of matches);
+//   pass 2  ransac_rescore_kernel: walks the histogram from the top to the bin where kKeepHyp hypotheses are covered, scores the
+//           hypotheses at or above that bin on ALL matches (one warp each) and rewrites the score array: full score for the survivors,
+//           -1 for everything else -- ransac_finalize_kernel's arg-max (ties -> lowest hypothesis index) runs unchanged.
+// 6x less scoring work; the winner is the survivor with the best FULL score, and the local optimisation starts from it as before.
+// Everything is a deterministic function of the frame's matches (histogram counts, not arrival order, decide who survives).
+constexpr int kScoreThreads = 256, kSubsetPairs = 256, kKeepHyp = 64;
+__global__ void __launch_bounds__(kScoreThreads) ransac_score_kernel(const float4* __restrict__ npairs, const int* __restrict__ counts, int pair_stride,
+                                                                     const Norm* __restrict__ norms, float thr, int max_iter, unsigned seed,
+                                                                     float* __restrict__ scores, int* __restrict__ hist) {
+  __shared__ float4 s_np[kSubsetPairs * 2];
   const int b = blockIdx.y;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int h = blockIdx.x * kScoreWarps + warp;
+  const int h = blockIdx.x * kScoreThreads + threadIdx.x;
   const int m = min(counts[b], pair_stride);
+  const int sub = max(1, m / kSubsetPairs);          // pass 1 looks at every sub-th match: kSubsetPairs <= ms < 2 kSubsetPairs of them
+  const int ms = (m + sub - 1) / sub;
   const float4* np = npairs + (size_t)b * pair_stride;
+  for (int i = threadIdx.x; i < ms; i += kScoreThreads) s_np[i] = __ldg(&np[(size_t)i * sub]);
+  __syncthreads();
+  if (h >= max_iter) return;
   int s[4];
   float H[9];
-  const bool ok = h < max_iter && m >= 4 && draw_sample(seed, b, h, m, s) && homography_4pt(np, s, H);
+  const bool ok = m >= 4 && draw_sample(seed, b, h, m, s) && homography_4pt(np, s, H);
+  float a = -1.f;
+  if (ok) {
+    const float t = thr * norms[b].sr;
+    const float it2 = 1.0f / (t * t);
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    int i = 0;
+    for (; i + 3 < ms; i += 4) {
+#pragma unroll
+      for (int u = 0; u < 4; ++u) acc[u] += fmaxf(0.f, 1.0f - reproj_err2(H, s_np[i + u]) * it2);
+    }
+    for (; i < ms; ++i) acc[0] += fmaxf(0.f, 1.0f - reproj_err2(H, s_np[i]) * it2);
+    a = (acc[0] + acc[1]) + (acc[2] + acc[3]);
+    atomicAdd(&hist[b * 256 + min(255, (int)(a * 255.0f / (float)ms))], 1);
+  }
+  scores[(size_t)b * max_iter + h] = a;
+}
+
+// One block per frame, 32 warps.  Survivors = every hypothesis in a bin above the cut bin + the lowest-index hypotheses of the cut bin
+// up to kKeepHyp in total (an ordered compaction: which hypotheses survive depends on their index, never on thread timing).
+__global__ void __launch_bounds__(1024) ransac_rescore_kernel(const float4* __restrict__ npairs, const int* __restrict__ counts, int pair_stride,
+                                                              const Norm* __restrict__ norms, float thr, int max_iter, unsigned seed,
+                                                              float* __restrict__ scores, const int* __restrict__ hist) {
+  __shared__ int s_cut, s_need, s_nhi, s_ncut;
+  __shared__ int s_whi[32], s_wcut[32];
+  __shared__ int s_list[kKeepHyp];
+  __shared__ float s_full[kKeepHyp];
+  const int b = blockIdx.x;
+  const int m = min(counts[b], pair_stride);
+  const int sub = max(1, m / kSubsetPairs);
+  if (m < 4 || sub == 1) return;                             // pass 1 already scored every match
+  const int ms = (m + sub - 1) / sub;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp == 0) {      // cut bin = the highest bin q with count(bins >= q) >= kKeepHyp; need = how many of bin q's members complete the set
+    int mine = 0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) mine += hist[b * 256 + 255 - 8 * lane - j];      // lane l owns bins 255 - 8 l .. 248 - 8 l (descending)
+    int incl = mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int v = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += v;
+    }
+    const unsigned hit = __ballot_sync(0xffffffffu, incl >= kKeepHyp);
+    int cut = -1, need = 0;                                  // fewer than kKeepHyp valid hypotheses: all of them survive (cut -1)
+    if (hit) {
+      const int src = __ffs(hit) - 1;
+      if (lane == src) {
+        int acc = incl - mine;
+        for (int j = 0; j < 8; ++j) {
+          const int q = 255 - 8 * lane - j, c = hist[b * 256 + q];
+          if (acc + c >= kKeepHyp) { cut = q; need = kKeepHyp - acc; break; }
+          acc += c;
+        }
+      }
+      cut = __shfl_sync(0xffffffffu, cut, src);
+      need = __shfl_sync(0xffffffffu, need, src);
+    }
+    if (lane == 0) { s_cut = cut; s_need = need; s_nhi = 0; s_ncut = 0; }
+  }
+  __syncthreads();
+  float* sc = scores + (size_t)b * max_iter;
+  const int cut = s_cut, need = s_need;
+  for (int h0 = 0; h0 < max_iter; h0 += 1024) {
+    const int h = h0 + threadIdx.x;
+    const float part = h < max_iter ? sc[h] : -1.f;
+    const int bin = part >= 0.f ? min(255, (int)(part * 255.0f / (float)ms)) : -2;
+    const bool hi = bin > cut, eq = bin == cut && bin >= 0;
+    const unsigned bhi = __ballot_sync(0xffffffffu, hi), beq = __ballot_sync(0xffffffffu, eq);
+    if (lane == 0) { s_whi[warp] = __popc(bhi); s_wcut[warp] = __popc(beq); }
+    __syncthreads();
+    int phi = s_nhi, pcut = s_ncut;
+    for (int w = 0; w < warp; ++w) { phi += s_whi[w]; pcut += s_wcut[w]; }
+    // survivors are listed as [bins above the cut ... | cut-bin members ...]: slot = rank among "hi", or (kKeepHyp - need) + rank among "eq"
+    if (hi) { const int pos = phi + __popc(bhi & ((1u << lane) - 1)); if (pos < kKeepHyp) s_list[pos] = h; }
+    if (eq) { const int r = pcut + __popc(beq & ((1u << lane) - 1)); if (r < need) s_list[kKeepHyp - need + r] = h; }
+    __syncthreads();
+    if (threadIdx.x == 0) { int a = 0, c = 0; for (int w = 0; w < 32; ++w) { a += s_whi[w]; c += s_wcut[w]; } s_nhi += a; s_ncut += c; }
+    __syncthreads();
+  }
+  // cut >= 0: exactly kKeepHyp survivors (nhi = kKeepHyp - need above the cut, `need` from the cut bin); cut == -1: the nhi valid ones
+  const int nsel = cut >= 0 ? kKeepHyp : min(s_nhi, kKeepHyp);
+  const float4* np = npairs + (size_t)b * pair_stride;
   const float t = thr * norms[b].sr;
   const float it2 = 1.0f / (t * t);
-  float acc[4] = {0.f, 0.f, 0.f, 0.f};
-  for (int t0 = 0; t0 < m; t0 += kScoreTile) {
-    const int n = min(kScoreTile, m - t0);
-    __syncthreads();
-    for (int i = threadIdx.x; i < n; i += kScoreWarps * 32) s_np[i] = __ldg(&np[t0 + i]);
-    __syncthreads();
+  for (int k = warp; k < nsel; k += 32) {
+    int s[4];
+    float H[9];
+    const bool ok = draw_sample(seed, b, s_list[k], m, s) && homography_4pt(np, s, H);
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
     if (ok) {
       int i = lane;
-      for (; i + 96 < n; i += 128) {
+      for (; i + 96 < m; i += 128) {
 #pragma unroll
-        for (int u = 0; u < 4; ++u) acc[u] += fmaxf(0.f, 1.0f - reproj_err2(H, s_np[i + 32 * u]) * it2);
+        for (int u = 0; u < 4; ++u) acc[u] += fmaxf(0.f, 1.0f - reproj_err2(H, __ldg(&np[i + 32 * u])) * it2);
       }
-      for (; i < n; i += 32) acc[0] += fmaxf(0.f, 1.0f - reproj_err2(H, s_np[i]) * it2);
+      for (; i < m; i += 32) acc[0] += fmaxf(0.f, 1.0f - reproj_err2(H, __ldg(&np[i])) * it2);
     }
-  }
-  float a = (acc[0] + acc[1]) + (acc[2] + acc[3]);
+    float a = (acc[0] + acc[1]) + (acc[2] + acc[3]);
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
-  if (lane == 0 && h < max_iter) scores[(size_t)b * max_iter + h] = ok ? a : -1.f;
+    for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+    if (lane == 0) s_full[k] = ok ? a : -1.f;
+  }
+  __syncthreads();
+  for (int h = threadIdx.x; h < max_iter; h += 1024) sc[h] = -1.f;
+  __syncthreads();
+  for (int k = threadIdx.x; k < nsel; k += 1024) sc[s_list[k]] = s_full[k];
 }
 
 // 8x8 SPD solve (Cholesky, in place).  A is the full symmetric matrix row-major; returns false if not positive definite.
@@ -543,6 +643,7 @@ int stab_build(gt_engine* e) {
   GT_TRY(e->dev_alloc((void**)&e->norms, (size_t)B * 8 * sizeof(float)));
   GT_TRY(e->dev_alloc((void**)&e->pair_count, (size_t)B * sizeof(int)));
   GT_TRY(e->dev_alloc((void**)&e->hyp_score, (size_t)B * e->cfg.ransac_max_iter * sizeof(float)));
+  GT_TRY(e->dev_alloc((void**)&e->hyp_hist, (size_t)B * 256 * sizeof(int)));
   GT_TRY(e->dev_alloc((void**)&e->H_dev, (size_t)B * 9 * sizeof(double)));
   GT_TRY(e->dev_alloc((void**)&e->H_status, (size_t)B * sizeof(int)));
   GT_TRY(e->dev_alloc((void**)&e->H_stats, (size_t)B * 4 * sizeof(int)));
@@ -565,13 +666,15 @@ int match_run(gt_engine* e, const uint8_t* q, const int* nq_dev, int nq_max, con
 int homography_run(gt_engine* e, const float* pairs, const int* counts, int B, int pair_stride, float thr, int max_iter, double* out_H,
                    int* out_status, int* out_stats, float ratio, bool full_res, const int* kp_count, cudaStream_t st) {
   ransac_prepare_kernel<<<B, 256, 0, st>>>(pairs, counts, pair_stride, (float4*)e->npairs, (Norm*)e->norms);
-  dim3 g((unsigned)ceil_div(max_iter, kScoreWarps), (unsigned)B);
-  ransac_score_kernel<<<g, kScoreWarps * 32, 0, st>>>((const float4*)e->npairs, counts, pair_stride, (const Norm*)e->norms, thr, max_iter, e->cfg.seed,
-                                         e->hyp_score);
+  GT_CUDA(e, cudaMemsetAsync(e->hyp_hist, 0, (size_t)B * 256 * sizeof(int), st));
+  ransac_score_kernel<<<dim3((unsigned)ceil_div(max_iter, kScoreThreads), (unsigned)B), kScoreThreads, 0, st>>>(
+      (const float4*)e->npairs, counts, pair_stride, (const Norm*)e->norms, thr, max_iter, e->cfg.seed, e->hyp_score, e->hyp_hist);
+  ransac_rescore_kernel<<<B, 1024, 0, st>>>(
+      (const float4*)e->npairs, counts, pair_stride, (const Norm*)e->norms, thr, max_iter, e->cfg.seed, e->hyp_score, e->hyp_hist);
   ransac_finalize_kernel<<<B, 256, 0, st>>>((const float4*)e->npairs, counts, pair_stride, (const Norm*)e->norms, e->hyp_score, thr, max_iter,
                                             e->cfg.seed, ratio, full_res ? 1 : 0, out_H, out_status, out_stats, e->cfg.max_batch,
                                             kp_count);
-  e->launches += 3;
+  e->launches += 4;
   GT_CUDA(e, cudaGetLastError());
   return GT_OK;
 }

@@ -109,6 +109,71 @@ __global__ void __launch_bounds__(128) pyr_resize_kernel(uint8_t* __restrict__ p
   }
 }
 
+// ---- the whole chained pyramid (levels 1..7 from level 0) in ONE launch ------------------------------------------------------------
+// The 7 dependent pyr_resize launches per plane were latency bound (14 launches = 320 us per 16-frame step for 100 MB of traffic).
+// Here a block owns one tile of the LAST level and everything below it: it loads the level-0 region that tile depends on (a few pixels
+// of halo per level, regions precomputed on the host from the resize tables: PyrBlock), then produces level 1, 2, ... 7 of that region
+// in shared memory, ping-pong, with exactly pyr_resize_kernel's arithmetic (chained INTER_LINEAR_EXACT, Q8.8 x Q8.8, mask threshold per
+// level), and writes to global memory only the part of each level it OWNS -- the owned ranges partition every level exactly.
+struct PyrBlock { short cx0[GT_ORB_LEVELS], cx1[GT_ORB_LEVELS], cy0[GT_ORB_LEVELS], cy1[GT_ORB_LEVELS];     // computed region per level [lo, hi)
+                  short ox0[GT_ORB_LEVELS], ox1[GT_ORB_LEVELS], oy0[GT_ORB_LEVELS], oy1[GT_ORB_LEVELS]; };  // owned region per level
+struct PyrGeom {
+  int w[GT_ORB_LEVELS], h[GT_ORB_LEVELS];
+  unsigned long long off[GT_ORB_LEVELS];
+  const int* xofs[GT_ORB_LEVELS]; const int* xc1[GT_ORB_LEVELS]; const int* yofs[GT_ORB_LEVELS]; const int* yc1[GT_ORB_LEVELS];
+  int buf_bytes;
+};
+
+template <bool MASK>
+__global__ void __launch_bounds__(256) pyr_chain_kernel(uint8_t* __restrict__ plane, size_t slab, int slot0, const PyrBlock* __restrict__ blocks,
+                                                        const PyrGeom g) {
+  extern __shared__ __align__(16) uint8_t s_pyr[];
+  __shared__ PyrBlock B;
+  if (threadIdx.x < sizeof(PyrBlock) / 4) reinterpret_cast<int*>(&B)[threadIdx.x] = reinterpret_cast<const int*>(blocks + blockIdx.x)[threadIdx.x];
+  __syncthreads();
+  uint8_t* cur = s_pyr;
+  uint8_t* nxt = s_pyr + g.buf_bytes;
+  uint8_t* base = plane + (size_t)(slot0 + blockIdx.y) * slab;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  int pw = B.cx1[0] - B.cx0[0];
+  {
+    const int ph = B.cy1[0] - B.cy0[0];
+    const uint8_t* src = base + g.off[0] + (size_t)B.cy0[0] * g.w[0] + B.cx0[0];
+    for (int y = ty; y < ph; y += 8)
+      for (int x = tx; x < pw; x += 32) cur[y * pw + x] = src[(size_t)y * g.w[0] + x];
+  }
+  __syncthreads();
+#pragma unroll 1
+  for (int l = 1; l < GT_ORB_LEVELS; ++l) {
+    const int px0 = B.cx0[l - 1], py0 = B.cy0[l - 1], sw = g.w[l - 1], sh = g.h[l - 1];
+    const int x0 = B.cx0[l], y0 = B.cy0[l], dw = B.cx1[l] - x0, dh = B.cy1[l] - y0;
+    const int ox0 = B.ox0[l], ox1 = B.ox1[l], oy0 = B.oy0[l], oy1 = B.oy1[l];
+    uint8_t* dst = base + g.off[l];
+    const int dW = g.w[l];
+    for (int dy = ty; dy < dh; dy += 8) {
+      const int Y = y0 + dy;
+      const int yo = __ldg(g.yofs[l] + Y), cy1 = __ldg(g.yc1[l] + Y), cy0 = 256 - cy1;
+      const uint8_t* r0 = cur + (yo - py0) * pw;
+      const uint8_t* r1 = cur + (min(yo + 1, sh - 1) - py0) * pw;
+      const bool own_y = Y >= oy0 && Y < oy1;
+      for (int dx = tx; dx < dw; dx += 32) {
+        const int X = x0 + dx;
+        const int xo = __ldg(g.xofs[l] + X), c1 = __ldg(g.xc1[l] + X), c0 = 256 - c1;
+        const int a = xo - px0, b = min(xo + 1, sw - 1) - px0;
+        const int h0 = (int)r0[a] * c0 + (int)r0[b] * c1;
+        const int h1 = (int)r1[a] * c0 + (int)r1[b] * c1;
+        int v = (h0 * cy0 + h1 * cy1 + 32768) >> 16;
+        if (MASK && v <= 254) v = 0;
+        nxt[dy * dw + dx] = (uint8_t)v;
+        if (own_y && X >= ox0 && X < ox1) dst[(size_t)Y * dW + X] = (uint8_t)v;
+      }
+    }
+    __syncthreads();
+    uint8_t* t = cur; cur = nxt; nxt = t;
+    pw = dw;
+  }
+}
+
 // ---- FAST-9/16 score + 3x3 non-max suppression + border filter -> candidate list --------------------------------------------
 // One launch covers all pyramid levels (blockIdx.x walks the 64 x 64 tiles of every level's candidate region
 // [kEdge, w - kEdge) x [kEdge, h - kEdge); blockIdx.y = frame slot).  Per tile:
@@ -607,16 +672,18 @@ __device__ __forceinline__ float fast_atan2_deg(float y, float x) {
   return a;
 }
 
-// Per key point (one warp): the 45 x 45 source patch is staged in shared memory, blurred there (7x7 sigma-2, float32 separable,
-// every product and sum rounded separately in OpenCV's accumulation order -- bit-identical to blurring the whole level, which is
-// what cv2.ORB does, because key points stay 31 px away from the border so no reflection is involved), then the intensity
-// centroid and the 256 rotated pair tests read the patch.  Blurring only the ~2000 patches instead of the 6.4 MPix pyramid
-// removes a full read+write pass over the pyramid and ~55 % of the MACs.
-constexpr int kDescWarps = 4;
+// Per key point (one warp): the 45 x 45 source patch is staged in shared memory; the intensity centroid reads it; the 7-tap
+// horizontal Gaussian pass runs over the whole patch (45 rows x 39 columns, one lane per half row with the row's bytes held in
+// registers); the vertical pass is evaluated ON DEMAND at the 512 rotated test points only (~1/3 of the 39 x 39 blurred pixels, each
+// 7 shared-memory reads).  float32 separable 7x7 sigma-2 blur with every product and sum rounded separately in OpenCV's
+// accumulation order -- bit-identical to blurring the whole level, which is what cv2.ORB does, because key points stay 31 px away
+// from the border so no reflection is involved.  (Round 1 blurred the full 39 x 39 patch with per-element index arithmetic: 6,800
+// warp instructions per key point; this form needs ~1,700.)
+constexpr int kDescWarps = 8;
 constexpr int kSrcR = 22, kSrcW = 2 * kSrcR + 1;       // 45: descriptor reach 19 (pattern radius 13*sqrt2 rounded) + blur 3
 constexpr int kBlurR = 19, kBlurW = 2 * kBlurR + 1;    // 39
-constexpr int kSrcPitch = 48, kBlurPitch = 40;
-constexpr int kDescSmemPerWarp = kSrcW * kSrcPitch + kSrcW * kBlurW * 4 + kBlurW * kBlurPitch;   // 2160 + 7020 + 1560
+constexpr int kSrcPitchW = 13;                         // source rows are 13 words (52 B) apart: lanes on different rows hit different banks
+constexpr int kDescSmemPerWarp = kSrcW * kSrcPitchW * 4 + kSrcW * kBlurW * 4;   // 2340 + 7020
 
 __global__ void __launch_bounds__(kDescWarps * 32) orb_describe_kernel(const uint8_t* __restrict__ img, size_t slab, int slot0,
                                                                        const OrbLevel* __restrict__ lv, const unsigned int* __restrict__ sel_xy,
@@ -627,9 +694,7 @@ __global__ void __launch_bounds__(kDescWarps * 32) orb_describe_kernel(const uin
   __shared__ signed char s_pat[256][4];
   __shared__ int s_off[GT_ORB_LEVELS + 1];
   const int slot = slot0 + blockIdx.y;
-  for (int i = threadIdx.x; i < 256; i += blockDim.x) {
-    s_pat[i][0] = d_pattern[i][0]; s_pat[i][1] = d_pattern[i][1]; s_pat[i][2] = d_pattern[i][2]; s_pat[i][3] = d_pattern[i][3];
-  }
+  for (int i = threadIdx.x; i < 256; i += blockDim.x) *reinterpret_cast<uint32_t*>(s_pat[i]) = *reinterpret_cast<const uint32_t*>(d_pattern[i]);
   if (threadIdx.x == 0) {
     int acc = 0;
     for (int l = 0; l < GT_ORB_LEVELS; ++l) {
@@ -654,14 +719,18 @@ __global__ void __launch_bounds__(kDescWarps * 32) orb_describe_kernel(const uin
   const int x = (int)(xy & 0xFFFF), y = (int)(xy >> 16);
   const uint8_t* im = img + (size_t)slot * slab + L.off;
   unsigned char* base = s_dyn + (size_t)warp * ((kDescSmemPerWarp + 15) & ~15);
-  uint8_t (*s_src)[kSrcPitch] = reinterpret_cast<uint8_t (*)[kSrcPitch]>(base);
-  float (*s_hp)[kBlurW] = reinterpret_cast<float (*)[kBlurW]>(base + kSrcW * kSrcPitch);
-  uint8_t (*s_bl)[kBlurPitch] = reinterpret_cast<uint8_t (*)[kBlurPitch]>(base + kSrcW * kSrcPitch + kSrcW * kBlurW * 4);
-  // stage the source patch (clamped reads: positions outside the image are never used, see above)
-  for (int i = lane; i < kSrcW * kSrcW; i += 32) {
-    const int r = i / kSrcW, c = i - r * kSrcW;
-    const int gy = min(max(y - kSrcR + r, 0), L.h - 1), gx = min(max(x - kSrcR + c, 0), L.w - 1);
-    s_src[r][c] = im[(size_t)gy * L.w + gx];
+  uint8_t* s_src = base;                                             // [45][52]
+  const uint32_t* s_srcw = reinterpret_cast<const uint32_t*>(base);  // the same rows as words
+  float* s_hp = reinterpret_cast<float*>(base + kSrcW * kSrcPitchW * 4);   // [45][39] horizontally blurred rows
+  // stage the source patch: key points are >= 31 px from every border (edgeThreshold), the patch reaches 22 -> always inside the image
+  {
+    const uint8_t* p0 = im + (size_t)(y - kSrcR) * L.w + (x - kSrcR);
+#pragma unroll 5
+    for (int r = 0; r < kSrcW; ++r) {
+      const uint8_t* pr = p0 + (size_t)r * L.w;
+      s_src[r * (kSrcPitchW * 4) + lane] = pr[lane];
+      if (lane < kSrcW - 32) s_src[r * (kSrcPitchW * 4) + 32 + lane] = pr[32 + lane];
+    }
   }
   __syncwarp();
   // intensity centroid over the radius-15 disc: lane = column u
@@ -670,7 +739,7 @@ __global__ void __launch_bounds__(kDescWarps * 32) orb_describe_kernel(const uin
     const int u = lane - 15, au = abs(u);
     for (int v = -15; v <= 15; ++v) {
       if (au <= c_umax[abs(v)]) {
-        const int I = s_src[kSrcR + v][kSrcR + u];
+        const int I = s_src[(kSrcR + v) * (kSrcPitchW * 4) + kSrcR + u];
         m10 += u * I;
         m01 += v * I;
       }
@@ -691,27 +760,48 @@ __global__ void __launch_bounds__(kDescWarps * 32) orb_describe_kernel(const uin
     kp[4] = sel_resp[((size_t)slot * GT_ORB_LEVELS + level) * kSelCap + li];
     kp[5] = (float)level;
   }
-  // horizontal pass: 45 rows x 39 columns
-  for (int i = lane; i < kSrcW * kBlurW; i += 32) {
-    const int r = i / kBlurW, c = i - r * kBlurW;
-    float acc = __fmul_rn((float)s_src[r][c], c_gauss[0]);
+  // horizontal pass: 90 work items = (row, half); half 0 -> output columns 0..19 from source bytes 0..25 (words 0..6),
+  // half 1 -> output columns 20..38 from source bytes 20..44 (words 5..11)
+  const float g0 = c_gauss[0], g1 = c_gauss[1], g2 = c_gauss[2], g3 = c_gauss[3];   // symmetric kernel: g4 = g2, g5 = g1, g6 = g0
+#pragma unroll 1
+  for (int item = lane; item < 2 * kSrcW; item += 32) {
+    const int hf = item >= kSrcW ? 1 : 0, r = item - hf * kSrcW;
+    const uint32_t* rw = s_srcw + r * kSrcPitchW + hf * 5;
+    uint32_t wv[7];
 #pragma unroll
-    for (int k = 1; k < 7; ++k) acc = __fadd_rn(acc, __fmul_rn((float)s_src[r][c + k], c_gauss[k]));
-    s_hp[r][c] = acc;
+    for (int k = 0; k < 7; ++k) wv[k] = rw[k];
+    float f[28];
+#pragma unroll
+    for (int j = 0; j < 28; ++j) f[j] = (float)((wv[j >> 2] >> (8 * (j & 3))) & 0xFFu);
+    float* out = s_hp + r * kBlurW + hf * 20;
+    const int nout = hf ? 19 : 20;
+#pragma unroll
+    for (int o = 0; o < 20; ++o) {
+      float acc = __fmul_rn(f[o], g0);
+      acc = __fadd_rn(acc, __fmul_rn(f[o + 1], g1));
+      acc = __fadd_rn(acc, __fmul_rn(f[o + 2], g2));
+      acc = __fadd_rn(acc, __fmul_rn(f[o + 3], g3));
+      acc = __fadd_rn(acc, __fmul_rn(f[o + 4], g2));
+      acc = __fadd_rn(acc, __fmul_rn(f[o + 5], g1));
+      acc = __fadd_rn(acc, __fmul_rn(f[o + 6], g0));
+      if (o < nout) out[o] = acc;
+    }
   }
   __syncwarp();
-  // vertical pass: 39 x 39, rounded to u8 like the blurred image
-  for (int i = lane; i < kBlurW * kBlurW; i += 32) {
-    const int r = i / kBlurW, c = i - r * kBlurW;
-    float acc = __fmul_rn(s_hp[r][c], c_gauss[0]);
-#pragma unroll
-    for (int k = 1; k < 7; ++k) acc = __fadd_rn(acc, __fmul_rn(s_hp[r + k][c], c_gauss[k]));
-    s_bl[r][c] = (uint8_t)min(max(__float2int_rn(acc), 0), 255);
-  }
-  __syncwarp();
-  // descriptor: lane computes byte `lane` (bits 8*lane .. 8*lane+7)
+  // descriptor: lane computes byte `lane` (bits 8*lane .. 8*lane+7); the vertical blur pass is evaluated at the test points only
   const float ar = __fmul_rn(angle, 0.017453292519943295f);  // (float)(CV_PI/180)
   const float ca = (float)cos((double)ar), sa = (float)sin((double)ar);
+  auto blurred = [&](int ix, int iy) -> int {                 // blurred pixel (x + ix, y + iy), rounded to u8 like the blurred image
+    const float* c = s_hp + (kBlurR + iy) * kBlurW + (kBlurR + ix);
+    float acc = __fmul_rn(c[0], g0);
+    acc = __fadd_rn(acc, __fmul_rn(c[kBlurW], g1));
+    acc = __fadd_rn(acc, __fmul_rn(c[2 * kBlurW], g2));
+    acc = __fadd_rn(acc, __fmul_rn(c[3 * kBlurW], g3));
+    acc = __fadd_rn(acc, __fmul_rn(c[4 * kBlurW], g2));
+    acc = __fadd_rn(acc, __fmul_rn(c[5 * kBlurW], g1));
+    acc = __fadd_rn(acc, __fmul_rn(c[6 * kBlurW], g0));
+    return min(max(__float2int_rn(acc), 0), 255);
+  };
   unsigned byte = 0;
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
@@ -721,9 +811,7 @@ __global__ void __launch_bounds__(kDescWarps * 32) orb_describe_kernel(const uin
     const int iy0 = __float2int_rn(__fadd_rn(__fmul_rn(px, sa), __fmul_rn(py, ca)));
     const int ix1 = __float2int_rn(__fsub_rn(__fmul_rn(qx, ca), __fmul_rn(qy, sa)));
     const int iy1 = __float2int_rn(__fadd_rn(__fmul_rn(qx, sa), __fmul_rn(qy, ca)));
-    const int t0 = s_bl[kBlurR + iy0][kBlurR + ix0];
-    const int t1 = s_bl[kBlurR + iy1][kBlurR + ix1];
-    byte |= (unsigned)(t0 < t1) << j;
+    byte |= (unsigned)(blurred(ix0, iy0) < blurred(ix1, iy1)) << j;
   }
   desc_all[((size_t)slot * GT_MAX_KP + kpi) * 32 + lane] = (uint8_t)byte;
 }
@@ -802,10 +890,12 @@ int orb_build(gt_engine* e) {
   GT_CUDA(e, cudaMemset(e->pyr_mask, 255, (size_t)S * off));
   GT_TRY(e->dev_alloc((void**)&e->lv_dev, sizeof(OrbLevel) * GT_ORB_LEVELS));
   GT_CUDA(e, cudaMemcpy(e->lv_dev, e->lv, sizeof(OrbLevel) * GT_ORB_LEVELS, cudaMemcpyHostToDevice));
+  std::vector<int> hxo[GT_ORB_LEVELS], hyo[GT_ORB_LEVELS];   // host copies of the source-offset tables (pyramid chain planning below)
   for (int l = 1; l < GT_ORB_LEVELS; ++l) {
     std::vector<int> xo, xc, yo, yc;
     resize_tables(e->lv[l - 1].w, e->lv[l].w, xo, xc);
     resize_tables(e->lv[l - 1].h, e->lv[l].h, yo, yc);
+    hxo[l] = xo; hyo[l] = yo;
     while (xo.size() % 4) { xo.push_back(xo.back()); xc.push_back(xc.back()); }   // the resize kernel loads four x entries at once
     const std::vector<int>* src[4] = {&xo, &xc, &yo, &yc};
     for (int k = 0; k < 4; ++k) {
@@ -813,8 +903,80 @@ int orb_build(gt_engine* e) {
       GT_CUDA(e, cudaMemcpy(e->rs_tab[l][k], src[k]->data(), src[k]->size() * 4, cudaMemcpyHostToDevice));
     }
   }
+  // ---- plan of the single-launch chained pyramid (pyr_chain_kernel): per tile of the last level, the computed and owned range of every level
+  {
+    const int T = GT_ORB_LEVELS - 1;
+    struct Range { int lo, hi; };
+    auto plan_axis = [&](const std::vector<int>* ofs, auto size_of, int tile, std::vector<std::vector<Range>>& comp, std::vector<std::vector<Range>>& own) {
+      const int nT = size_of(T), nb = ceil_div(nT, tile);
+      comp.assign(nb, std::vector<Range>(GT_ORB_LEVELS));
+      own.assign(nb, std::vector<Range>(GT_ORB_LEVELS));
+      for (int b = 0; b < nb; ++b) own[b][T] = comp[b][T] = {b * tile, std::min((b + 1) * tile, nT)};
+      for (int l = T - 1; l >= 0; --l) {
+        const int n = size_of(l);
+        for (int b = 0; b < nb; ++b) {
+          own[b][l].lo = b == 0 ? 0 : ofs[l + 1][own[b][l + 1].lo];
+          own[b][l].hi = b == nb - 1 ? n : ofs[l + 1][own[b + 1][l + 1].lo];
+        }
+        for (int b = 0; b < nb; ++b) {
+          const int lo = ofs[l + 1][comp[b][l + 1].lo], hi = std::min(ofs[l + 1][comp[b][l + 1].hi - 1] + 2, n);
+          comp[b][l] = {std::min(lo, own[b][l].lo), std::max(hi, own[b][l].hi)};
+        }
+      }
+    };
+    std::vector<std::vector<Range>> cx, ox, cy, oy;
+    plan_axis(hxo, [&](int l) { return e->lv[l].w; }, 64, cx, ox);
+    plan_axis(hyo, [&](int l) { return e->lv[l].h; }, 32, cy, oy);
+    std::vector<PyrBlock> blocks;
+    size_t buf = 0;
+    for (size_t by = 0; by < cy.size(); ++by)
+      for (size_t bx = 0; bx < cx.size(); ++bx) {
+        PyrBlock pb;
+        for (int l = 0; l < GT_ORB_LEVELS; ++l) {
+          pb.cx0[l] = (short)cx[bx][l].lo; pb.cx1[l] = (short)cx[bx][l].hi; pb.cy0[l] = (short)cy[by][l].lo; pb.cy1[l] = (short)cy[by][l].hi;
+          pb.ox0[l] = (short)ox[bx][l].lo; pb.ox1[l] = (short)ox[bx][l].hi; pb.oy0[l] = (short)oy[by][l].lo; pb.oy1[l] = (short)oy[by][l].hi;
+          buf = std::max(buf, (size_t)(cx[bx][l].hi - cx[bx][l].lo) * (size_t)(cy[by][l].hi - cy[by][l].lo));
+        }
+        blocks.push_back(pb);
+      }
+    e->pyr_nblocks = (int)blocks.size();
+    e->pyr_buf_bytes = (int)((buf + 15) & ~(size_t)15);
+    e->pyr_chain = 2 * e->pyr_buf_bytes <= 200 * 1024 && e->lv[0].w < 32768 && e->lv[0].h < 32768 && getenv("GT_PYR_CHAIN") && atoi(getenv("GT_PYR_CHAIN")) != 0;
+    GT_TRY(e->dev_alloc((void**)&e->pyr_blocks, blocks.size() * sizeof(PyrBlock)));
+    GT_CUDA(e, cudaMemcpy(e->pyr_blocks, blocks.data(), blocks.size() * sizeof(PyrBlock), cudaMemcpyHostToDevice));
+    if (e->pyr_chain) {
+      GT_CUDA(e, cudaFuncSetAttribute(pyr_chain_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * e->pyr_buf_bytes));
+      GT_CUDA(e, cudaFuncSetAttribute(pyr_chain_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * e->pyr_buf_bytes));
+    }
+  }
   GT_CUDA(e, cudaFuncSetAttribute(orb_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSelCap * 4));
   GT_CUDA(e, cudaFuncSetAttribute(orb_describe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kDescWarps * ((kDescSmemPerWarp + 15) & ~15)));
+  return GT_OK;
+}
+
+// levels 1..7 of one plane (image or mask) for slots [slot0, slot0 + nslots): one chained launch, or the per-level kernels as fallback
+template <bool MASK>
+static int pyramid_run(gt_engine* e, uint8_t* plane, int slot0, int nslots, cudaStream_t st) {
+  const size_t slab = e->pyr_bytes;
+  if (e->pyr_chain) {
+    PyrGeom g;
+    for (int l = 0; l < GT_ORB_LEVELS; ++l) {
+      g.w[l] = e->lv[l].w; g.h[l] = e->lv[l].h; g.off[l] = e->lv[l].off;
+      g.xofs[l] = e->rs_tab[l][0]; g.xc1[l] = e->rs_tab[l][1]; g.yofs[l] = e->rs_tab[l][2]; g.yc1[l] = e->rs_tab[l][3];
+    }
+    g.buf_bytes = e->pyr_buf_bytes;
+    pyr_chain_kernel<MASK><<<dim3((unsigned)e->pyr_nblocks, (unsigned)nslots), 256, 2 * e->pyr_buf_bytes, st>>>(plane, slab, slot0, (const PyrBlock*)e->pyr_blocks, g);
+    e->launches++;
+    return GT_OK;
+  }
+  for (int l = 1; l < GT_ORB_LEVELS; ++l) {
+    const OrbLevel& S = e->lv[l - 1];
+    const OrbLevel& D = e->lv[l];
+    int* const* t = e->rs_tab[l];
+    dim3 g((unsigned)ceil_div(D.w, 4 * 128), (unsigned)ceil_div(D.h, kResizeRows), (unsigned)nslots);
+    pyr_resize_kernel<MASK><<<g, 128, 0, st>>>(plane, slab, slot0, S.off, S.w, S.h, D.off, D.w, D.h, t[0], t[1], t[2], t[3]);
+    e->launches++;
+  }
   return GT_OK;
 }
 
@@ -822,14 +984,7 @@ int orb_build(gt_engine* e) {
 // a second stream while the detector works on the same frames.
 int orb_front(gt_engine* e, int slot0, int nslots, cudaStream_t st) {
   const size_t slab = e->pyr_bytes;
-  for (int l = 1; l < GT_ORB_LEVELS; ++l) {
-    const OrbLevel& S = e->lv[l - 1];
-    const OrbLevel& D = e->lv[l];
-    int* const* t = e->rs_tab[l];
-    dim3 g((unsigned)ceil_div(D.w, 4 * 128), (unsigned)ceil_div(D.h, kResizeRows), (unsigned)nslots);
-    pyr_resize_kernel<false><<<g, 128, 0, st>>>(e->pyr, slab, slot0, S.off, S.w, S.h, D.off, D.w, D.h, t[0], t[1], t[2], t[3]);
-    e->launches++;
-  }
+  GT_TRY(pyramid_run<false>(e, e->pyr, slot0, nslots, st));
   GT_CUDA(e, cudaMemsetAsync(e->fast_count + (size_t)slot0 * GT_ORB_LEVELS, 0, (size_t)nslots * GT_ORB_LEVELS * sizeof(int), st));
   {
     FastLevels fl;
@@ -865,14 +1020,7 @@ int orb_back(gt_engine* e, int slot0, int nslots, bool as_reference, bool build_
       e->launches++;
     }
   }
-  for (int l = 1; l < GT_ORB_LEVELS; ++l) {
-    const OrbLevel& S = e->lv[l - 1];
-    const OrbLevel& D = e->lv[l];
-    int* const* t = e->rs_tab[l];
-    dim3 g((unsigned)ceil_div(D.w, 4 * 128), (unsigned)ceil_div(D.h, kResizeRows), (unsigned)nslots);
-    pyr_resize_kernel<true><<<g, 128, 0, st>>>(e->pyr_mask, slab, slot0, S.off, S.w, S.h, D.off, D.w, D.h, t[0], t[1], t[2], t[3]);
-    e->launches++;
-  }
+  GT_TRY(pyramid_run<true>(e, e->pyr_mask, slot0, nslots, st));
   {
     dim3 g(GT_ORB_LEVELS, (unsigned)nslots);
     orb_select_kernel<<<g, 1024, kSelCap * 4, st>>>(e->pyr, e->pyr_mask, slab, slot0, e->lv_dev, e->fast_cand, e->fast_score, e->cand_total,
