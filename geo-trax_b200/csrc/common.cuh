@@ -94,8 +94,10 @@ struct ConvParams {
   void* out;
   long long out_img_stride;  // destination pixels per image
   int out_ctot, out_coff;
-  const bf16* res;        // optional residual (same spatial dims as the output)
+  const bf16* res;        // optional residual (same spatial dims as the output), added AFTER the activation; or, with res_pre:
   int res_ctot, res_coff;
+  int res_pre;            // 1: `res` is a HALF-resolution pre-activation partial sum (H/2 x W/2): out = act(acc + bias + res[y/2][x/2]) -- the
+                          // upsampled branch of a 1x1 conv over cat(up2x(a), b), computed at a's resolution (1x1 convs commute with nearest upsampling)
   bf16* up;               // optional second, 2x nearest-upsampled destination (2H x 2W)
   int up_ctot, up_coff;
   const float* bias;      // [n_tiles * BN]
@@ -115,6 +117,8 @@ struct ConvOp {
   int pair = 0;              // 1: conv_sw.cu as CTA pairs (cta_group::2, 256 channels x 256 pixels per pair tile; variant 6)
   int swapped = 0;           // 1: conv_sw.cu (weights = A operand, 256-pixel tile = B operand); tmA = activations, tmB = weights either way
   int n_src = 0;             // 1..3 canonical convs fused along cout
+  int w_cin_total = 0, w_cin_off = 0;   // the op uses input channels [w_cin_off, w_cin_off + cin) of a canonical conv with w_cin_total of them (0: all)
+  int no_bias = 0;           // 1: bias is zero (partial-sum op; the consumer adds the conv's bias)
   int src[3] = {0, 0, 0};    // canonical conv indices
   double flops = 0;          // per image
   double bytes = 0;          // algorithmic HBM bytes per image (unfused: input + output (+ residual))
@@ -135,16 +139,17 @@ struct ConvPlanArgs {
   int out_ctot_f32 = 0, out_coff_f32 = 0;
   const View* res = nullptr;
   const View* up = nullptr;
+  const View* pre = nullptr;   // half-resolution pre-activation partial sum (see ConvParams::res_pre); excludes res
 };
 
 // layer signature = key of the shipped per-layer kernel-variant table (csrc/conv_tune.inc)
-struct ConvSig { int cin, cout, k, stride, H, W, flags; };   // flags: 1 residual, 2 upsampled copy, 4 f32 rows, 8 s2d output
+struct ConvSig { int cin, cout, k, stride, H, W, flags; };   // flags: 1 residual, 2 upsampled copy, 4 f32 rows, 8 s2d output, 16 half-res pre-activation add
 ConvSig conv_signature(const ConvPlanArgs& a);
 int conv_choose_variant(const ConvSig& s);
 
 int conv_tc_init(gt_engine* e);  // resolves cuTensorMapEncodeTiled, sets kernel attributes
 int conv_tc_plan(gt_engine* e, ConvOp* op, const ConvPlanArgs& a);  // tensor maps + launch geometry + weight storage
-int conv_tc_pack_weights(gt_engine* e, ConvOp* op, const float* const* w, const float* const* b, const int* couts, int n);
+int conv_tc_pack_weights(gt_engine* e, ConvOp* op, const float* const* w, const float* const* b, const int* couts, int n);   // honours op->w_cin_total / w_cin_off / no_bias
 int conv_tc_upload_packed(gt_engine* e, ConvOp* op, const uint16_t* packed, const float* bias);
 int conv_tc_launch(gt_engine* e, const ConvOp* op, int B, cudaStream_t st);
 int conv_tc_launch_range(gt_engine* e, const ConvOp* op, int b0, int nb, cudaStream_t st);

@@ -648,6 +648,7 @@ int conv_sw_plan(gt_engine* e, ConvOp* op, const ConvPlanArgs& a) {
   GT_CHECK(e, in.C == cin, "conv plan: input view has %d channels, conv expects %d", in.C, cin);
   GT_CHECK(e, (in.ctot % 8) == 0 && (in.coff % 8) == 0, "conv plan: input slice must be 16-byte aligned");
   GT_CHECK(e, k >= 1 && k <= 3 && (stride == 1 || stride == 2), "conv plan: k=%d stride=%d unsupported", k, stride);
+  GT_CHECK(e, a.pre == nullptr, "conv plan (swapped): the half-resolution pre-activation add is a pixel-major epilogue feature");
   ConvParams& p = op->p;
   memset(&p, 0, sizeof(p));
   op->swapped = 1;

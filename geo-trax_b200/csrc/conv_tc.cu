@@ -58,7 +58,8 @@ __device__ __forceinline__ void epilogue_tile(const ConvParams& p, const TileCoo
   const uint4* rbase = nullptr;
   if constexpr (!F32) {
     if (has_res) {
-      const long long rp = ((long long)t.n * p.H + y) * p.W + x;
+      const long long rp = p.res_pre ? ((long long)t.n * (p.H >> 1) + (y >> 1)) * (p.W >> 1) + (x >> 1)   // half-resolution partial sum
+                                     : ((long long)t.n * p.H + y) * p.W + x;
       rbase = reinterpret_cast<const uint4*>(p.res + rp * p.res_ctot + p.res_coff + t.n0 + half * CW);
       if (t.n0 + half * CW < p.cout) {
 #pragma unroll
@@ -94,6 +95,17 @@ __device__ __forceinline__ void epilogue_tile(const ConvParams& p, const TileCoo
       f[i + 2] = fmaf(__uint_as_float(v[i + 2]), p.scale, bv.z);
       f[i + 3] = fmaf(__uint_as_float(v[i + 3]), p.scale, bv.w);
     }
+    if constexpr (!F32) {
+      if (p.res_pre && has_res && gc0 < p.cout) {   // pre-activation partial sum of the upsampled branch (warp-uniform branch)
+#pragma unroll
+        for (int c = 0; c < CHUNKS; ++c) {
+          const uint4 u = rres[c];
+          const float2 a0 = unpack2_act(u.x, p.fp16), a1 = unpack2_act(u.y, p.fp16), a2 = unpack2_act(u.z, p.fp16), a3 = unpack2_act(u.w, p.fp16);
+          f[c * 8 + 0] += a0.x; f[c * 8 + 1] += a0.y; f[c * 8 + 2] += a1.x; f[c * 8 + 3] += a1.y;
+          f[c * 8 + 4] += a2.x; f[c * 8 + 5] += a2.y; f[c * 8 + 6] += a3.x; f[c * 8 + 7] += a3.y;
+        }
+      }
+    }
     if (p.act) {
 #pragma unroll
       for (int i = 0; i < CW; ++i) f[i] = silu_fast(f[i]);
@@ -104,7 +116,7 @@ __device__ __forceinline__ void epilogue_tile(const ConvParams& p, const TileCoo
       for (int c = 0; c < CHUNKS; ++c)
         pk[c] = make_uint4(__float_as_uint(f[c * 4]), __float_as_uint(f[c * 4 + 1]), __float_as_uint(f[c * 4 + 2]), __float_as_uint(f[c * 4 + 3]));
     } else {
-      if (has_res && gc0 < p.cout) {
+      if (has_res && !p.res_pre && gc0 < p.cout) {
 #pragma unroll
         for (int c = 0; c < CHUNKS; ++c) {
           const uint4 u = rres[c];
@@ -475,7 +487,7 @@ static void pick_tile(int H, int W, int* tw, int* th) {
 
 int conv_tc_plan(gt_engine* e, ConvOp* op, const ConvPlanArgs& a) {
   GT_CHECK(e, g_encode != nullptr, "conv_tc_init not called");
-  if (e->plan_variant == 1 || e->plan_variant == 2 || e->plan_variant == 6) return conv_sw_plan(e, op, a);
+  if ((e->plan_variant == 1 || e->plan_variant == 2 || e->plan_variant == 6) && !a.pre) return conv_sw_plan(e, op, a);   // (the half-resolution pre-activation add lives in the pixel-major epilogue only)
   const View& in = a.in;
   const int cin = a.cin, k = a.k, stride = a.stride;
   const int kbe = (a.kb_elems == 64 && cin == 32) ? 32 : a.kb_elems;   // 32-channel inputs: 64-byte rows instead of half-empty 128-byte rows
@@ -585,11 +597,16 @@ int conv_tc_plan(gt_engine* e, ConvOp* op, const ConvPlanArgs& a) {
     GT_CHECK(e, a.up->H == 2 * Ho && a.up->W == 2 * Wo && a.up->C == cout_total && !a.out_f32, "conv plan: upsample view mismatch");
     p.up = a.up->ptr; p.up_ctot = a.up->ctot; p.up_coff = a.up->coff;
   }
+  if (a.pre) {
+    GT_CHECK(e, !a.res && !a.out_f32 && (Ho % 2) == 0 && (Wo % 2) == 0 && a.pre->H * 2 == Ho && a.pre->W * 2 == Wo && a.pre->C == cout_total &&
+                    (a.pre->ctot % 8) == 0 && (a.pre->coff % 8) == 0, "conv plan: half-resolution partial-sum view mismatch");
+    p.res = a.pre->ptr; p.res_ctot = a.pre->ctot; p.res_coff = a.pre->coff; p.res_pre = 1;
+  }
   op->smem = conv_smem_bytes(p.stages, stage_bytes, halo_total, p.b_resident ? bres_bytes : 0, op->cout_pad);
   op->flops = 2.0 * Ho * Wo * (double)cout_total * cin * k * k;
   // algorithmic HBM bytes per image: input slice + output (+ residual, + upsampled copy) + weights (once per launch, ignored)
   op->bytes = (double)in.H * in.W * cin * 2 + (double)Ho * Wo * cout_total * (a.out_f32 ? 4 : 2) * (a.up ? 5 : 1) +
-              (a.res ? (double)Ho * Wo * cout_total * 2 : 0.0);
+              (a.res ? (double)Ho * Wo * cout_total * 2 : 0.0) + (a.pre ? (double)Ho * Wo * cout_total * 2 / 4 : 0.0);
 
   // weights + bias storage
   const size_t wn = (size_t)op->cout_pad * k * k * op->cin_pad;
@@ -671,6 +688,7 @@ int conv_tc_pack_weights(gt_engine* e, ConvOp* op, const float* const* w, const 
   const int taps = op->k * op->k;
   const size_t wn = (size_t)op->cout_pad * taps * op->cin_pad;
   const int fp16 = op->p.fp16;
+  const int cin_total = op->w_cin_total > 0 ? op->w_cin_total : op->cin, cin_off = op->w_cin_total > 0 ? op->w_cin_off : 0;   // input-channel slice of the canonical conv
   std::vector<uint16_t> hw(wn, 0);
   std::vector<float> hb(op->cout_pad, 0.f);
   int co0 = 0;
@@ -678,8 +696,8 @@ int conv_tc_pack_weights(gt_engine* e, ConvOp* op, const float* const* w, const 
     for (int co = 0; co < couts[s]; ++co) {
       for (int ci = 0; ci < op->cin; ++ci)
         for (int t = 0; t < taps; ++t)
-          hw[((size_t)(co0 + co) * taps + t) * op->cin_pad + ci] = host_to_act(w[s][((size_t)co * op->cin + ci) * taps + t], fp16);
-      hb[co0 + co] = b[s] ? b[s][co] : 0.f;
+          hw[((size_t)(co0 + co) * taps + t) * op->cin_pad + ci] = host_to_act(w[s][((size_t)co * cin_total + cin_off + ci) * taps + t], fp16);
+      hb[co0 + co] = (b[s] && !op->no_bias) ? b[s][co] : 0.f;
     }
     co0 += couts[s];
   }

@@ -829,7 +829,7 @@ ConvSig conv_signature(const ConvPlanArgs& a) {
   s.cin = a.cin; s.cout = a.cout; s.k = a.k; s.stride = a.stride;
   s.H = a.Ho > 0 ? a.Ho : (a.in.H + 2 * pad - a.k) / a.stride + 1;
   s.W = a.Wo > 0 ? a.Wo : (a.in.W + 2 * pad - a.k) / a.stride + 1;
-  s.flags = (a.res ? 1 : 0) | (a.up ? 2 : 0) | (a.out_f32 ? 4 : 0) | (a.out_s2d ? 8 : 0);
+  s.flags = (a.res ? 1 : 0) | (a.up ? 2 : 0) | (a.out_f32 ? 4 : 0) | (a.out_s2d ? 8 : 0) | (a.pre ? 16 : 0);
   return s;
 }
 
@@ -843,6 +843,7 @@ static int rule_variant(const ConvSig& s) {
   if (s.flags & (4 | 8)) return 3;                                     // f32 head rows, layer 0: pixel-major, two CTAs / SM
   const long long px = (long long)s.H * s.W;
   if (s.k == 1) {
+    if (s.flags & 16) return s.cout <= 128 ? 3 : 0;                    // half-resolution pre-activation add: pixel-major epilogue only
     if (s.flags & 2) return 0;                                         // upsampled copy: pixel-major slabs
     if ((s.cout % 256) == 0) return s.cin >= 384 ? 6 : 1;
     return s.cin >= 384 ? 0 : 3;
@@ -982,11 +983,41 @@ struct Builder {
     e->conv0_op = (int)e->conv_ops.size();
     push(op);
   }
-  void c2f(const std::string& pre, const View& in, int c2, int n, bool shortcut, const View& out, const View* up = nullptr) {
+  // 1x1 conv over cat(up2x(lo), hi) WITHOUT materialising the upsampled tensor: a 1x1 convolution commutes with nearest upsampling,
+  // so the `lo` branch (the first lo.C input channels of the canonical conv) runs at lo's resolution into a half-resolution
+  // pre-activation partial sum Z (no bias, no activation: 4x fewer MACs, and neither the 4 upsampled stores of the producer nor their
+  // read-back exist any more), and the `hi` branch adds Z[y/2][x/2] + bias before its activation (ConvParams::res_pre).
+  void conv_cat_up(const std::string& name, const View& lo, const View& hi, const View& out) {
+    if (rc != GT_OK) return;
+    const int ci = find(name);
+    const gt_conv_desc& d = e->conv_descs[ci];
+    if (d.k != 1 || d.stride != 1 || d.cin != lo.C + hi.C || hi.H != 2 * lo.H || hi.W != 2 * lo.W) { gt_set_error(e, "plan: %s is not a 1x1 conv over cat(up2x, .)", name.c_str()); rc = GT_ERR_INVALID; return; }
+    View Z = alloc(d.cout, lo.H, lo.W);
+    ConvOp part;
+    part.n_src = 1; part.src[0] = ci; part.w_cin_total = d.cin; part.w_cin_off = 0; part.no_bias = 1;
+    ConvPlanArgs a;
+    a.in = lo; a.Bmax = B; a.cin = lo.C; a.cout = d.cout; a.k = 1; a.stride = 1; a.act = 0; a.out = &Z;
+    rc = plan_both(part, a);
+    if (rc != GT_OK) return;
+    part.flops = 0;                                            // the algorithmic FLOPs of the canonical conv are booked on the final op
+    for (int v = 1; v < GT_CONV_VARIANTS; ++v) if (!e->conv_var[v].empty()) e->conv_var[v].back().flops = 0;
+    push(part);
+    ConvOp fin;
+    fin.n_src = 1; fin.src[0] = ci; fin.w_cin_total = d.cin; fin.w_cin_off = lo.C;
+    ConvPlanArgs b;
+    b.in = hi; b.Bmax = B; b.cin = hi.C; b.cout = d.cout; b.k = 1; b.stride = 1; b.act = d.act; b.out = &out; b.pre = &Z;
+    rc = plan_both(fin, b);
+    if (rc != GT_OK) return;
+    fin.flops = 2.0 * hi.H * hi.W * (double)d.cout * d.cin;   // what ultralytics' conv over the materialised concat costs
+    for (int v = 1; v < GT_CONV_VARIANTS; ++v) if (!e->conv_var[v].empty()) e->conv_var[v].back().flops = fin.flops;
+    push(fin);
+  }
+  void c2f(const std::string& pre, const View& in, int c2, int n, bool shortcut, const View& out, const View* up = nullptr, const View* in_lo = nullptr) {
     const int c = c2 / 2;
     View cat = alloc((2 + n) * c, in.H, in.W);
     View tmp = alloc(c, in.H, in.W);
-    conv({pre + ".cv1"}, in, cat.slice(0, 2 * c));
+    if (in_lo) conv_cat_up(pre + ".cv1", *in_lo, in, cat.slice(0, 2 * c));   // the block's input is cat(up2x(in_lo), in)
+    else conv({pre + ".cv1"}, in, cat.slice(0, 2 * c));
     for (int i = 0; i < n; ++i) {
       View src = cat.slice(c * (1 + i), c);
       conv({pre + ".m." + std::to_string(i) + ".cv1"}, src, tmp);
@@ -1085,13 +1116,11 @@ int detector_build(gt_engine* e) {
   bl.c2f("model.2", T1, c2, 1, true, T2);
   View T3 = bl.alloc(c3, H3, W3);
   bl.conv({"model.3"}, T2, T3);
-  View cat14 = bl.alloc(c4 + c3, H3, W3);   // [up(12) | 4]
-  View L4 = cat14.slice(c4, c3);
+  View L4 = bl.alloc(c3, H3, W3);
   bl.c2f("model.4", T3, c3, 2, true, L4);
   View T5 = bl.alloc(c4, H4, W4);
   bl.conv({"model.5"}, L4, T5);
-  View cat11 = bl.alloc(c5 + c4, H4, W4);   // [up(9) | 6]
-  View L6 = cat11.slice(c5, c4);
+  View L6 = bl.alloc(c4, H4, W4);
   bl.c2f("model.6", T5, c4, 2, true, L6);
   View T7 = bl.alloc(c5, H5, W5);
   bl.conv({"model.7"}, L6, T7);
@@ -1108,14 +1137,14 @@ int detector_build(gt_engine* e) {
   }
   View cat20 = bl.alloc(c4 + c5, H5, W5);   // [19 | 9]
   View L9 = cat20.slice(c4, c5);
-  View up9 = cat11.slice(0, c5);
-  bl.conv({"model.9.cv2"}, s9, L9, nullptr, &up9);
+  bl.conv({"model.9.cv2"}, s9, L9);
   View cat17 = bl.alloc(c3 + c4, H4, W4);   // [16 | 12]
   View L12 = cat17.slice(c3, c4);
-  View up12 = cat14.slice(0, c4);
-  bl.c2f("model.12", cat11, c4, 1, false, L12, &up12);
+  // Upsample + Concat (model.10/11, model.13/14) are never materialised: model.12.cv1 / model.15.cv1 are 1x1 convs over
+  // cat(up2x(lo), hi) and run as conv_cat_up (lo branch at lo's resolution, added before the activation of the hi branch)
+  bl.c2f("model.12", L6, c4, 1, false, L12, nullptr, &L9);
   View P3 = bl.alloc(c3, H3, W3);
-  bl.c2f("model.15", cat14, c3, 1, false, P3);
+  bl.c2f("model.15", L4, c3, 1, false, P3, nullptr, &L12);
   bl.conv({"model.16"}, P3, cat17.slice(0, c3));
   View P4 = bl.alloc(c4, H4, W4);
   bl.c2f("model.18", cat17, c4, 1, false, P4);
