@@ -1,4 +1,9 @@
-"""Runs a few steps of the 4K hot path for ncu (launch list / full capture).  Usage: python tools/profile_step.py [steps] [dtype]"""
+"""Runs a few steps of the 4K hot path for ncu (launch list / full capture).
+
+    python tools/profile_step.py [steps] [dtype]
+    ncu --profile-from-start off ... python tools/profile_step.py 1      # only the LAST step is inside cudaProfilerStart/Stop
+
+The per-layer conv kernels come from the shipped table (csrc/conv_tune.inc): a profiled run uses exactly the kernels of a normal run."""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
@@ -16,7 +21,11 @@ dev = torch.from_numpy(frames).cuda()
 mask = eng.pack_boxes(boxes)
 eng.extract_batch(dev[:1], first_is_reference=True, classes=[0, 1, 2, 3], mask_boxes=eng.pack_boxes(boxes[:1]))
 out = eng.alloc_outputs()
-for _ in range(steps):
+for i in range(steps + 1):
+    if i == steps:
+        torch.cuda.synchronize()
+        torch.cuda.profiler.start()
     eng.extract_batch(dev, classes=[0, 1, 2, 3], mask_boxes=mask, out=out)
 torch.cuda.synchronize()
+torch.cuda.profiler.stop()
 print("launches", eng.launch_count(), eng.stage_times())
