@@ -46,7 +46,8 @@ def run_range(engine, get_frames: Callable[[int, int], np.ndarray], lo: int, hi:
     md, row = engine.max_det, engine.row
     n = max(hi - lo, 0)
     res = dict(frame=np.arange(lo, hi, dtype=np.int64), count=np.zeros(n, np.int32), status=np.zeros(n, np.int32), stats=np.zeros((n, 4), np.int32),
-               H=np.zeros((n, 9), np.float64), boxes=np.zeros((n, md, row), np.float32), boxes_stab=np.zeros((n, md, 4), np.float32))
+               H=np.zeros((n, 9), np.float64), boxes=np.empty((n, md, row), np.float32), boxes_stab=np.empty((n, md, 4), np.float32))
+    # (boxes / boxes_stab rows at and beyond a frame's `count` are unspecified: np.empty avoids touching ~40 KB per frame twice)
     kw = dict(conf=conf, iou=iou, agnostic=agnostic, classes=classes, stream=stream)
     ref = None
     if set_reference:
@@ -101,9 +102,17 @@ def run_range(engine, get_frames: Callable[[int, int], np.ndarray], lo: int, hi:
     return res
 
 
+def _record_dtype(c_max: int, row: int) -> np.dtype:
+    """One frame's record as a packed structure (what travels in the gather)."""
+    return np.dtype([("frame", "<i8"), ("count", "<i4"), ("status", "<i4"), ("stats", "<i4", (4,)), ("H", "<f8", (9,)),
+                     ("boxes", "<f4", (c_max, row)), ("boxes_stab", "<f4", (c_max, 4))])
+
+
 def gather_records(local: Dict[str, np.ndarray], rank: int, world: int, device=None) -> Optional[Dict[str, np.ndarray]]:
-    """Gathers every rank's per-frame records on rank 0 (returns None elsewhere).  Boxes are trimmed to the largest
-    per-frame count over all ranks before they travel (real payload ~3 KB / frame instead of max_det rows)."""
+    """Gathers every rank's per-frame records on rank 0 (returns None elsewhere): ONE small all_gather (frames per rank, largest
+    per-frame detection count) and ONE gather of packed per-frame structures -- boxes trimmed to the largest count over all ranks
+    (real payload ~3-10 KB / frame instead of max_det rows), H kept f64 and frame numbers i64 because the bytes travel, not floats.
+    NCCL when ``device`` is a CUDA device (the GPU box), gloo on the CPU (tests)."""
     if world == 1:
         return local
     import torch
@@ -114,23 +123,25 @@ def gather_records(local: Dict[str, np.ndarray], rank: int, world: int, device=N
     meta = torch.tensor([n_local, int(local["count"].max()) if n_local else 0], dtype=torch.int64, device=dev)
     metas = [torch.zeros_like(meta) for _ in range(world)]
     dist.all_gather(metas, meta)
+    metas = [m.cpu() for m in metas]
     n_max = max(int(m[0]) for m in metas)
     c_max = max(1, max(int(m[1]) for m in metas))
-    gathered: Dict[str, np.ndarray] = {}
-    for key, arr in local.items():
-        a = arr[:, :c_max] if key in ("boxes", "boxes_stab") else arr
-        pad = np.zeros((n_max,) + a.shape[1:], a.dtype)
-        pad[:n_local] = a
-        t = torch.from_numpy(np.ascontiguousarray(pad)).view(torch.uint8).to(dev)   # bytes: keeps f64 / i64 exact
-        parts = [torch.zeros_like(t) for _ in range(world)] if rank == 0 else None
-        dist.gather(t, parts, dst=0)
-        if rank == 0:
-            chunks = []
-            for r, p in enumerate(parts):
-                full = p.cpu().numpy().view(a.dtype).reshape((n_max,) + a.shape[1:])
-                chunks.append(full[: int(metas[r][0])])
-            gathered[key] = np.concatenate(chunks, 0)
-    return gathered if rank == 0 else None
+    row = local["boxes"].shape[2]
+    dt = _record_dtype(c_max, row)
+    rec = np.zeros(max(n_max, 1), dt)
+    for key in ("frame", "count", "status", "stats", "H"):
+        rec[key][:n_local] = local[key]
+    rec["boxes"][:n_local] = local["boxes"][:, :c_max]
+    rec["boxes_stab"][:n_local] = local["boxes_stab"][:, :c_max]
+    t = torch.from_numpy(rec.view(np.uint8).reshape(len(rec), dt.itemsize)).to(dev)
+    parts = [torch.zeros_like(t) for _ in range(world)] if rank == 0 else None
+    dist.gather(t, parts, dst=0)
+    if rank != 0:
+        return None
+    chunks = [p.cpu().numpy().reshape(-1).view(dt)[: int(metas[r][0])] for r, p in enumerate(parts)]
+    allrec = np.concatenate(chunks, 0)
+    # boxes / boxes_stab come back trimmed to (n, c_max, .): every consumer reads rows [:count] only
+    return {key: np.ascontiguousarray(allrec[key]) for key in ("frame", "count", "status", "stats", "H", "boxes", "boxes_stab")}
 
 
 class GmcFromHomography:
