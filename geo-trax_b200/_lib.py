@@ -10,6 +10,7 @@ LIB_PATH = os.path.join(HERE, "libgeotrax_b200.so")
 GT_ABI_VERSION = 1
 GT_INPUT_BGR24, GT_INPUT_NV12 = 0, 1
 GT_TASK_DETECT, GT_TASK_OBB = 0, 1
+GT_CODEC_H264, GT_CODEC_HEVC = 0, 1
 GT_ACT_BF16, GT_ACT_FP16 = 0, 1
 GT_MAX_KP = 8192
 GT_ORB_LEVELS = 8
@@ -54,6 +55,13 @@ SYMBOLS = {
     "gt_prefetch_frames": (_i, [_H, _P, _i]),
     "gt_prefetch_frames_deferred": (_i, [_H, _P, _i]),
     "gt_set_input_format": (_i, [_H, _i]),
+    "gt_nvdec_available": (_i, []),
+    "gt_decoder_create": (_i, [_H, _i, _i, C.POINTER(_H)]),
+    "gt_decoder_destroy": (_i, [_H]),
+    "gt_decoder_feed": (_i, [_H, _P, C.c_size_t]),
+    "gt_decoder_pending": (_i, [_H]),
+    "gt_decoder_take": (_i, [_H, _i, C.POINTER(_P), _ip]),
+    "gt_decoder_last_error": (C.c_char_p, [_H]),
     "gt_get_net_input": (_i, [_H, _i, _P, _ip, _ip]),
     "gt_get_gray": (_i, [_H, _i, _P, _ip, _ip]),
     "gt_detect": (_i, [_H, _i, _f, _f, _i, _u, _P, _P, _P, _P]),

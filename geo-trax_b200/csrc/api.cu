@@ -584,9 +584,16 @@ int gt_set_reference(gt_handle e, int frame_slot, const float* boxes, int nboxes
 static int stabilize_impl(gt_engine* e, int B, cudaStream_t st, bool front_on_aux = false) {
   GT_CHECK(e, e->have_ref, "gt_stabilize: no reference frame set");
   GT_CUDA(e, cudaEventRecord(e->ev[5], st));
-  if (front_on_aux) GT_CUDA(e, cudaStreamWaitEvent(st, e->ev_front, 0));   // pyramid / blur / FAST were produced on the aux stream
-  else GT_TRY(orb_front(e, 0, B, st));
-  GT_TRY(orb_back(e, 0, B, false, true, st));
+  // the vehicle-mask pyramid needs only the boxes: it is enqueued BEFORE this stream waits for the aux stream's image pyramid + FAST,
+  // so it overlaps the tail of the FAST kernel (both are latency / instruction bound and share the SMs well)
+  if (front_on_aux) {
+    GT_TRY(orb_mask(e, 0, B, true, st));
+    GT_CUDA(e, cudaStreamWaitEvent(st, e->ev_front, 0));
+  } else {
+    GT_TRY(orb_front(e, 0, B, st));
+    GT_TRY(orb_mask(e, 0, B, true, st));
+  }
+  GT_TRY(orb_back(e, 0, B, false, st));
   GT_TRY(stab_match_and_fit(e, B, st));
   GT_CUDA(e, cudaEventRecord(e->ev[6], st));
   return GT_OK;
@@ -764,18 +771,28 @@ static int extract_batch_impl(gt_handle e, const uint8_t* frames, int B, int fir
   // The mask-independent half of ORB (pyramid + FAST) needs only the gray frames.  overlap 2 (default): it runs on the aux stream beside
   // decode + NMS, whose kernels occupy 16-64 blocks; overlap 1: beside the whole detector (no gain: the conv CTAs own the SMs); 0: serial.
   const bool ov = e->overlap != 0;
-  auto fork_front = [&]() -> int {
-    GT_CUDA(e, cudaEventRecord(e->ev_pre, st));
-    GT_CUDA(e, cudaStreamWaitEvent(e->aux_stream, e->ev_pre, 0));
-    GT_TRY(orb_front(e, 0, B, e->aux_stream));
-    GT_CUDA(e, cudaEventRecord(e->ev_front, e->aux_stream));
+  auto fork_front = [&](int part) -> int {   // part 0: pyramid + FAST, 1: pyramid only, 2: FAST only (the pyramid is already queued on the aux stream)
+    if (part != 2) {
+      GT_CUDA(e, cudaEventRecord(e->ev_pre, st));
+      GT_CUDA(e, cudaStreamWaitEvent(e->aux_stream, e->ev_pre, 0));
+    }
+    if (part == 0) GT_TRY(orb_front(e, 0, B, e->aux_stream));
+    else if (part == 1) GT_TRY(orb_pyramid(e, 0, B, e->aux_stream));
+    else GT_TRY(orb_fast(e, 0, B, e->aux_stream));
+    if (part != 1) GT_CUDA(e, cudaEventRecord(e->ev_front, e->aux_stream));
     return GT_OK;
   };
-  if (e->overlap == 1) GT_TRY(fork_front());
+  if (e->overlap == 1) GT_TRY(fork_front(0));
+  if (e->overlap == 3) GT_TRY(fork_front(1));
   GT_CUDA(e, cudaEventRecord(e->ev[2], st));
   GT_TRY(detector_forward(e, B, st));
   GT_CUDA(e, cudaEventRecord(e->ev[3], st));
-  if (e->overlap >= 2) GT_TRY(fork_front());
+  if (e->overlap == 2) GT_TRY(fork_front(0));
+  if (e->overlap == 3) {   // FAST starts when the conv stack has finished (and, by stream order, after the pyramid)
+    GT_CUDA(e, cudaEventRecord(e->ev_pre, st));
+    GT_CUDA(e, cudaStreamWaitEvent(e->aux_stream, e->ev_pre, 0));
+    GT_TRY(fork_front(2));
+  }
   GT_TRY(detector_postprocess(e, B, conf, iou, agnostic, classes_mask, st));
   GT_CUDA(e, cudaEventRecord(e->ev[4], st));
   dim3 g((unsigned)ceil_div(md, 256), (unsigned)B);

@@ -63,7 +63,7 @@ struct gt_engine {
   cudaStream_t copy_stream = nullptr;
   cudaStream_t aux_stream = nullptr;    // low priority: the mask-independent half of ORB runs here next to the detector
   cudaEvent_t ev_pre = nullptr, ev_front = nullptr;
-  int overlap = 2;                      // GT_OVERLAP: 2 (default) ORB front on the aux stream beside decode + NMS; 1 beside the whole detector (no gain: the conv CTAs own the SMs); 0 serial
+  int overlap = 2;                      // GT_OVERLAP: 2 ORB front on the aux stream beside decode + NMS; 3 as 2, but the image pyramid already beside the conv stack (fills the tails between layers); 1 the whole front beside the detector (no gain: the conv CTAs own the SMs); 0 serial
   int conv_smem_kb = 227;               // dynamic smem budget of the conv kernels (200 with GT_OVERLAP=1 to leave room for ORB blocks); GT_CONV_SMEM_KB
   cudaEvent_t ev_copied[2] = {nullptr, nullptr};   // H2D of staging buffer k finished (copy stream)
   cudaEvent_t ev_consumed[2] = {nullptr, nullptr}; // the preprocess kernel that read staging buffer k finished
@@ -200,8 +200,11 @@ int clahe_run(gt_engine* e, const uint8_t* frames_dev, int B, cudaStream_t st);
 // orb.cu
 int orb_build(gt_engine* e);
 int orb_run(gt_engine* e, int slot0, int nslots, bool as_reference, bool build_mask, cudaStream_t st);
-int orb_front(gt_engine* e, int slot0, int nslots, cudaStream_t st);   // image pyramid, blur, FAST: independent of the mask
-int orb_back(gt_engine* e, int slot0, int nslots, bool as_reference, bool build_mask, cudaStream_t st);
+int orb_front(gt_engine* e, int slot0, int nslots, cudaStream_t st);   // image pyramid + FAST: independent of the mask
+int orb_pyramid(gt_engine* e, int slot0, int nslots, cudaStream_t st);
+int orb_fast(gt_engine* e, int slot0, int nslots, cudaStream_t st);
+int orb_mask(gt_engine* e, int slot0, int nslots, bool build_mask, cudaStream_t st);   // vehicle mask + its pyramid: independent of orb_front
+int orb_back(gt_engine* e, int slot0, int nslots, bool as_reference, cudaStream_t st);
 // match_ransac.cu
 int stab_build(gt_engine* e);
 int stab_match_and_fit(gt_engine* e, int B, cudaStream_t st);

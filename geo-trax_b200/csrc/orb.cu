@@ -982,9 +982,14 @@ static int pyramid_run(gt_engine* e, uint8_t* plane, int slot0, int nslots, cuda
 
 // Mask-independent half of ORB: image pyramid, blurred pyramid, FAST candidates.  Needs only the gray level 0, so it can run on
 // a second stream while the detector works on the same frames.
-int orb_front(gt_engine* e, int slot0, int nslots, cudaStream_t st) {
-  const size_t slab = e->pyr_bytes;
+int orb_pyramid(gt_engine* e, int slot0, int nslots, cudaStream_t st) {   // image pyramid only (needs the gray level 0)
   GT_TRY(pyramid_run<false>(e, e->pyr, slot0, nslots, st));
+  GT_CUDA(e, cudaGetLastError());
+  return GT_OK;
+}
+
+int orb_fast(gt_engine* e, int slot0, int nslots, cudaStream_t st) {      // FAST candidates of every level (needs the image pyramid)
+  const size_t slab = e->pyr_bytes;
   GT_CUDA(e, cudaMemsetAsync(e->fast_count + (size_t)slot0 * GT_ORB_LEVELS, 0, (size_t)nslots * GT_ORB_LEVELS * sizeof(int), st));
   {
     FastLevels fl;
@@ -1006,9 +1011,15 @@ int orb_front(gt_engine* e, int slot0, int nslots, cudaStream_t st) {
   return GT_OK;
 }
 
-// Mask-dependent half: vehicle mask (level 0 from the boxes unless the caller supplied one) + its pyramid, masked candidate
-// selection (score cut, Harris, quota cut), orientation + descriptors.
-int orb_back(gt_engine* e, int slot0, int nslots, bool as_reference, bool build_mask, cudaStream_t st) {
+int orb_front(gt_engine* e, int slot0, int nslots, cudaStream_t st) {
+  GT_TRY(orb_pyramid(e, slot0, nslots, st));
+  return orb_fast(e, slot0, nslots, st);
+}
+
+// Mask-dependent half, part 1: vehicle mask (level 0 from the boxes unless the caller supplied one) + its pyramid.  Needs the boxes
+// (detections / tracker boxes) but NOT the image pyramid or FAST: the caller runs it before waiting for orb_front, so it overlaps the
+// tail of the FAST kernel on the aux stream.
+int orb_mask(gt_engine* e, int slot0, int nslots, bool build_mask, cudaStream_t st) {
   const size_t slab = e->pyr_bytes;
   const OrbLevel& L0 = e->lv[0];
   if (build_mask) {
@@ -1021,6 +1032,13 @@ int orb_back(gt_engine* e, int slot0, int nslots, bool as_reference, bool build_
     }
   }
   GT_TRY(pyramid_run<true>(e, e->pyr_mask, slot0, nslots, st));
+  GT_CUDA(e, cudaGetLastError());
+  return GT_OK;
+}
+
+// Part 2: masked candidate selection (score cut, Harris, quota cut), orientation + descriptors.  Needs orb_front and orb_mask.
+int orb_back(gt_engine* e, int slot0, int nslots, bool as_reference, cudaStream_t st) {
+  const size_t slab = e->pyr_bytes;
   {
     dim3 g(GT_ORB_LEVELS, (unsigned)nslots);
     orb_select_kernel<<<g, 1024, kSelCap * 4, st>>>(e->pyr, e->pyr_mask, slab, slot0, e->lv_dev, e->fast_cand, e->fast_score, e->cand_total,
@@ -1041,5 +1059,6 @@ int orb_back(gt_engine* e, int slot0, int nslots, bool as_reference, bool build_
 
 int orb_run(gt_engine* e, int slot0, int nslots, bool as_reference, bool build_mask, cudaStream_t st) {
   GT_TRY(orb_front(e, slot0, nslots, st));
-  return orb_back(e, slot0, nslots, as_reference, build_mask, st);
+  GT_TRY(orb_mask(e, slot0, nslots, build_mask, st));
+  return orb_back(e, slot0, nslots, as_reference, st);
 }

@@ -390,3 +390,76 @@ class Engine:
         ms, fl = C.c_float(), C.c_double()
         self._ck(self.lib.gt_conv_stack_stats(self.h, C.byref(ms), C.byref(fl)))
         return ms.value, fl.value
+
+
+class DeviceFrames:
+    """A run of dense frames in device memory owned by someone else (the NVDEC ring): quacks like a contiguous CUDA tensor for
+    ``Engine.preprocess`` / ``extract_batch`` (``shape``, ``data_ptr()``), and exposes ``__cuda_array_interface__`` so that
+    ``torch.as_tensor(frames, device="cuda")`` aliases it without a copy."""
+
+    is_cuda = True
+
+    def __init__(self, ptr: int, shape: Tuple[int, ...]):
+        self.ptr, self.shape = int(ptr), tuple(int(x) for x in shape)
+        self.__cuda_array_interface__ = {"shape": self.shape, "typestr": "|u1", "data": (self.ptr, False), "version": 2, "strides": None}
+
+    def data_ptr(self) -> int:
+        return self.ptr
+
+    def is_contiguous(self) -> bool:
+        return True
+
+    def __len__(self) -> int:
+        return self.shape[0]
+
+
+class Decoder:
+    """NVDEC ingest for one engine (gt_decoder_*): H.264 / HEVC Annex-B bytes in, dense NV12 frames in HBM out.
+
+        dec = Decoder(engine, "h264"); engine.set_input_format("nv12")
+        dec.feed(chunk)                       # any number of bytes; feed(None) flushes at end of stream
+        while dec.pending():
+            frames = dec.take(engine.max_batch)        # DeviceFrames (n, H * 3 / 2, W): pass straight to engine.extract_batch
+    Replaces the reference's ``reader.read()`` (/root/reference/geotrax/extract.py:146, 248).  Raises ``GtError`` when libnvcuvid or
+    an NVDEC engine is not available: there is no software decoder behind this."""
+
+    def __init__(self, engine: "Engine", codec: str = "h264", capacity_frames: int = 0):
+        self.eng, self.lib = engine, engine.lib
+        if not self.lib.gt_nvdec_available():
+            raise GtError("libnvcuvid.so.1 (the NVDEC driver library) is not available on this machine")
+        self.h = C.c_void_p()
+        code = {"h264": _lib.GT_CODEC_H264, "hevc": _lib.GT_CODEC_HEVC, "h265": _lib.GT_CODEC_HEVC}[codec.lower()]
+        rc = self.lib.gt_decoder_create(engine.h, code, int(capacity_frames), C.byref(self.h))
+        if rc != 0:
+            raise GtError(f"gt_decoder_create failed ({rc}): {self.lib.gt_last_error(engine.h).decode()}")
+        self.frame_shape = (engine.cfg.frame_h * 3 // 2, engine.cfg.frame_w)
+
+    def feed(self, data) -> None:
+        if data is None or len(data) == 0:
+            rc = self.lib.gt_decoder_feed(self.h, None, 0)
+        else:
+            buf = np.frombuffer(data, np.uint8) if not isinstance(data, np.ndarray) else np.ascontiguousarray(data, np.uint8)
+            rc = self.lib.gt_decoder_feed(self.h, buf.ctypes.data, buf.size)
+        if rc != 0:
+            raise GtError(f"gt_decoder_feed failed ({rc}): {self.lib.gt_decoder_last_error(self.h).decode()}")
+
+    def pending(self) -> int:
+        return int(self.lib.gt_decoder_pending(self.h))
+
+    def take(self, max_frames: int) -> Optional[DeviceFrames]:
+        ptr, n = C.c_void_p(), C.c_int32()
+        rc = self.lib.gt_decoder_take(self.h, int(max_frames), C.byref(ptr), C.byref(n))
+        if rc != 0:
+            raise GtError(f"gt_decoder_take failed ({rc})")
+        return DeviceFrames(ptr.value, (n.value,) + self.frame_shape) if n.value > 0 else None
+
+    def close(self) -> None:
+        if getattr(self, "h", None) and self.h.value:
+            self.lib.gt_decoder_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

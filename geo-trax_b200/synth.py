@@ -126,3 +126,110 @@ def bgr_to_nv12(frame_bgr: np.ndarray) -> np.ndarray:
     out[:h] = i420[:h]
     out[h:] = np.stack([flat[h * w:h * w + q].reshape(h // 2, w // 2), flat[h * w + q:h * w + 2 * q].reshape(h // 2, w // 2)], -1).reshape(h // 2, w)
     return out
+
+
+# ---- a tiny H.264 elementary-stream writer (lossless I_PCM macroblocks): input for the NVDEC ingest path ---------------------------------
+class _Bits:
+    def __init__(self):
+        self.bits = []
+
+    def u(self, n, v):
+        self.bits.extend((v >> (n - 1 - i)) & 1 for i in range(n))
+
+    def ue(self, v):
+        v += 1
+        n = v.bit_length()
+        self.u(n - 1, 0)
+        self.u(n, v)
+
+    def se(self, v):
+        self.ue(2 * v - 1 if v > 0 else -2 * v)
+
+    def trailing(self):
+        self.bits.append(1)
+        while len(self.bits) % 8:
+            self.bits.append(0)
+
+    def align_zero(self):
+        while len(self.bits) % 8:
+            self.bits.append(0)
+
+    def bytes(self):
+        assert len(self.bits) % 8 == 0
+        return bytes(int("".join(map(str, self.bits[i:i + 8])), 2) for i in range(0, len(self.bits), 8))
+
+
+def _escape(payload: bytes) -> bytes:
+    """Emulation prevention (H.264 7.4.1): a 0x03 after every two zero bytes that are followed by a byte <= 3 (small payloads only)."""
+    out, zeros = bytearray(), 0
+    for b in payload:
+        if zeros >= 2 and b <= 3:
+            out.append(3)
+            zeros = 0
+        out.append(b)
+        zeros = zeros + 1 if b == 0 else 0
+    return bytes(out)
+
+
+def _nal(nal_ref_idc: int, nal_type: int, payload: bytes) -> bytes:
+    return b"\x00\x00\x00\x01" + bytes([(nal_ref_idc << 5) | nal_type]) + payload
+
+
+def h264_ipcm_stream(nv12_frames, level_idc: int = 52) -> Tuple[bytes, np.ndarray]:
+    """Annex-B H.264 elementary stream (Constrained Baseline, CAVLC, every picture an IDR of I_PCM macroblocks, deblocking off) that
+    decodes EXACTLY to the given NV12 frames -- a lossless bitstream any H.264 decoder (NVDEC included) accepts, written without an
+    encoder library (there is none in this image, and no network).  Frame dimensions must be multiples of 16.
+
+    H.264 forbids the PCM sample value 0 (it could emulate a start code), so samples are clamped to [1, 255]; the returned array is
+    the clamped NV12 the decoder must reproduce bit for bit.  -> (stream bytes, expected NV12 u8 [n][H * 3 / 2][W])."""
+    frames = np.maximum(np.asarray(nv12_frames, np.uint8), 1)
+    n, h32, w = frames.shape
+    h = h32 * 2 // 3
+    assert h % 16 == 0 and w % 16 == 0, "I_PCM writer: frame dimensions must be multiples of 16"
+    mbw, mbh = w // 16, h // 16
+    sps = _Bits()
+    sps.u(8, 66); sps.u(8, 0xC0); sps.u(8, level_idc)        # profile_idc 66 (baseline), constraint_set0/1 flags, level
+    sps.ue(0)                                                 # seq_parameter_set_id
+    sps.ue(0)                                                 # log2_max_frame_num_minus4
+    sps.ue(2)                                                 # pic_order_cnt_type 2: output order = decode order
+    sps.ue(1); sps.u(1, 0)                                    # max_num_ref_frames, gaps_in_frame_num_value_allowed_flag
+    sps.ue(mbw - 1); sps.ue(mbh - 1)
+    sps.u(1, 1); sps.u(1, 1); sps.u(1, 0); sps.u(1, 1)        # frame_mbs_only, direct_8x8_inference, frame_cropping, vui_parameters_present
+    # VUI: only the bitstream restriction -- no reordering, one frame of DPB -- so that decoders output every picture immediately
+    sps.u(1, 0); sps.u(1, 0); sps.u(1, 0); sps.u(1, 0); sps.u(1, 0)   # aspect_ratio, overscan, video_signal_type, chroma_loc, timing info: absent
+    sps.u(1, 0); sps.u(1, 0); sps.u(1, 0)                     # nal_hrd, vcl_hrd parameters absent, pic_struct_present_flag
+    sps.u(1, 1)                                               # bitstream_restriction_flag
+    sps.u(1, 1); sps.ue(0); sps.ue(0); sps.ue(16); sps.ue(16) # motion_vectors_over_pic_boundaries, max_bytes_per_pic_denom, max_bits_per_mb_denom, log2_max_mv_length_h / v
+    sps.ue(0); sps.ue(1)                                      # max_num_reorder_frames, max_dec_frame_buffering
+    sps.trailing()
+    pps = _Bits()
+    pps.ue(0); pps.ue(0); pps.u(1, 0); pps.u(1, 0)            # pps id, sps id, entropy_coding_mode (CAVLC), bottom_field_pic_order_in_frame_present
+    pps.ue(0); pps.ue(0); pps.ue(0)                           # num_slice_groups_minus1, num_ref_idx_l0/l1_default_active_minus1
+    pps.u(1, 0); pps.u(2, 0)                                  # weighted_pred_flag, weighted_bipred_idc
+    pps.se(0); pps.se(0); pps.se(0)                           # pic_init_qp_minus26, pic_init_qs_minus26, chroma_qp_index_offset
+    pps.u(1, 1); pps.u(1, 0); pps.u(1, 0)                     # deblocking_filter_control_present, constrained_intra_pred, redundant_pic_cnt_present
+    pps.trailing()
+    out = [_nal(3, 7, _escape(sps.bytes())), _nal(3, 8, _escape(pps.bytes()))]
+    for i in range(n):
+        y = frames[i, :h].reshape(mbh, 16, mbw, 16).transpose(0, 2, 1, 3).reshape(mbh * mbw, 256)
+        uv = frames[i, h:].reshape(h // 2, w // 2, 2)
+        cb = uv[..., 0].reshape(mbh, 8, mbw, 8).transpose(0, 2, 1, 3).reshape(mbh * mbw, 64)
+        cr = uv[..., 1].reshape(mbh, 8, mbw, 8).transpose(0, 2, 1, 3).reshape(mbh * mbw, 64)
+        hdr = _Bits()
+        hdr.ue(0); hdr.ue(7); hdr.ue(0)                       # first_mb_in_slice, slice_type 7 (I, all slices of the picture), pic_parameter_set_id
+        hdr.u(4, 0)                                           # frame_num (IDR)
+        hdr.ue(i & 1)                                         # idr_pic_id: differs between consecutive IDR pictures
+        hdr.u(1, 0); hdr.u(1, 0)                              # no_output_of_prior_pics_flag, long_term_reference_flag
+        hdr.se(0)                                             # slice_qp_delta
+        hdr.ue(1)                                             # disable_deblocking_filter_idc = 1
+        hdr.ue(25)                                            # mb_type I_PCM of macroblock 0
+        hdr.align_zero()                                      # pcm_alignment_zero_bit
+        mb = np.empty((mbh * mbw, 386), np.uint8)
+        mb[:, 0], mb[:, 1] = 0x0D, 0x00                       # ue(25) = 000011010 + 7 alignment zero bits (the stream is byte aligned after PCM samples)
+        mb[:, 2:258], mb[:, 258:322], mb[:, 322:386] = y, cb, cr
+        # macroblock 0's mb_type lives in the slice header bits; samples are >= 1 and each later macroblock header is 0x0D 0x00, so the
+        # sample part never holds two consecutive zero bytes: only the few header bytes need the emulation-prevention pass
+        body = mb.reshape(-1)[2:]
+        assert not ((body[:-1] == 0) & (body[1:] == 0)).any()
+        out.append(_nal(3, 5, _escape(hdr.bytes()) + body.tobytes() + b"\x80"))   # + rbsp trailing bits
+    return b"".join(out), frames

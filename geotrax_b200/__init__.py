@@ -9,7 +9,7 @@ __path__.insert(0, _SRC)
 
 from ._lib import GtError, LIB_PATH, load_library  # noqa: E402,F401
 
-_LAZY = {"Engine": "engine", "YOLO": "yolo", "RTDETR": "yolo", "Results": "results", "Boxes": "results", "OBB": "results",
+_LAZY = {"Engine": "engine", "Decoder": "engine", "DeviceFrames": "engine", "YOLO": "yolo", "RTDETR": "yolo", "Results": "results", "Boxes": "results", "OBB": "results",
          "Stabilizer": "stabilizer", "install_shims": "shims"}
 
 

@@ -18,6 +18,7 @@
 #ifndef GEOTRAX_B200_H_
 #define GEOTRAX_B200_H_
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -109,6 +110,25 @@ int gt_prefetch_frames_deferred(gt_handle h, const uint8_t* frames, int B);
  * works on, with OpenCV's cvtColor(COLOR_YUV2BGR_NV12) integer arithmetic (ITU-R BT.601 limited range, 20-bit fixed point).   */
 enum { GT_INPUT_BGR24 = 0, GT_INPUT_NV12 = 1 };
 int gt_set_input_format(gt_handle h, int format);
+/* ---- NVDEC ingest: H.264 / HEVC Annex-B elementary stream -> dense NV12 frames in HBM -------------------------
+ * Replaces `reader.read()` (/root/reference/geotrax/extract.py:146, 248: FFmpeg software decode + swscale on the host) for callers
+ * that hold the bitstream: the frames never cross PCIe uncompressed.  The decoder belongs to an engine (same GPU, same frame size: the
+ * stream's display size must equal frame_w x frame_h, 8-bit 4:2:0).  libnvcuvid.so.1 (driver library) is dlopen()ed; where it is
+ * missing gt_nvdec_available() returns 0 and gt_decoder_create fails -- there is no software decoder behind this.
+ *   feed : any number of bytes of the stream (NULL / 0 = end of stream); every picture completed by them is decoded and appended, in
+ *          display order, to a ring of `capacity_frames` (>= 2 * max_batch) dense NV12 frames [H * 3 / 2][W] in device memory
+ *   take : pointer to up to max_frames consecutive decoded frames + their number; valid until the ring wraps onto them (i.e. until
+ *          capacity_frames further frames have been decoded).  After gt_set_input_format(h, GT_INPUT_NV12) that pointer is a `frames`
+ *          argument of gt_preprocess / gt_extract_batch.                                                                              */
+typedef struct gt_decoder* gt_decoder_handle;
+enum { GT_CODEC_H264 = 0, GT_CODEC_HEVC = 1 };
+int gt_nvdec_available(void);
+int gt_decoder_create(gt_handle h, int codec, int capacity_frames, gt_decoder_handle* out);
+int gt_decoder_destroy(gt_decoder_handle d);
+int gt_decoder_feed(gt_decoder_handle d, const uint8_t* data, size_t size);
+int gt_decoder_pending(gt_decoder_handle d);
+int gt_decoder_take(gt_decoder_handle d, int max_frames, const uint8_t** dev_nv12, int32_t* n_frames);
+const char* gt_decoder_last_error(gt_decoder_handle d);
 /* debug/parity read-back: letterboxed planar RGB u8 [B][3][net_h][net_w] (the 1/255 scale is folded into layer 0's
  * f32 weights, so the network input is exact) and u8 gray [B][work_h][work_w] */
 int gt_get_net_input(gt_handle h, int B, uint8_t* out_u8, int32_t* net_h, int32_t* net_w);

@@ -503,3 +503,66 @@ def test_stabilizer_reference_survives_engine_recreation():
         assert np.array_equal(st.get_cur_trans_matrix(), H1)
     finally:
         session.close_all()
+
+
+# ---------------------------------------------------------------------------------------------------------------------------------
+# NVDEC ingest: bitstream -> NV12 in HBM -> detector + stabiliser
+# ---------------------------------------------------------------------------------------------------------------------------------
+def _nvdec_or_skip(eng):
+    import geotrax_b200
+    from geotrax_b200 import GtError
+    if not eng.lib.gt_nvdec_available():
+        pytest.skip("libnvcuvid.so.1 not present on this machine")
+    try:
+        return geotrax_b200.Decoder(eng, "h264")
+    except GtError as err:
+        pytest.skip(f"NVDEC not usable here: {err}")
+
+
+@pytest.mark.parametrize("hw,imgsz", [((544, 960), 480), ((2160, 3840), 1920)], ids=["544x960", "4K"])
+def test_nvdec_decodes_lossless_stream_bit_exact_and_feeds_the_path(hw, imgsz):
+    """An H.264 stream of I_PCM macroblocks (written by synth.h264_ipcm_stream, validated against FFmpeg on the CPU) decodes on NVDEC to
+    exactly the NV12 frames it encodes, fed in arbitrary chunks; and the decoded device frames run through gt_extract_batch with outputs
+    identical to the same NV12 frames supplied from host memory."""
+    import geotrax_b200
+    from geotrax_b200 import GtError, synth, weights
+    nfr = 5
+    eng = geotrax_b200.Engine(frame_hw=hw, imgsz=imgsz, nc=4, max_batch=4, max_det=300, max_features=1000)
+    dec = _nvdec_or_skip(eng)
+    try:
+        eng.load_weights(weights.fold(weights.random_state_dict(4, "detect", seed=0, frame_hw=hw, imgsz=imgsz, cls_bias=-4.0)))
+        frames, boxes, _ = synth.make_flight(nfr, hw[0], hw[1], seed=9, n_vehicles=20)
+        stream, expect = synth.h264_ipcm_stream(np.stack([synth.bgr_to_nv12(f) for f in frames]))
+        try:
+            cut = len(stream) // 3 + 7                       # chunk boundaries in the middle of NAL units
+            for a, b in ((0, cut), (cut, 2 * cut), (2 * cut, len(stream))):
+                dec.feed(stream[a:b])
+            dec.feed(None)                                    # end of stream: flush
+        except GtError as err:
+            if "cuvidCreateDecoder" in str(err):
+                pytest.skip(f"NVDEC engine not usable in this container: {err}")
+            raise
+        assert dec.pending() == nfr
+        got = []
+        while dec.pending():
+            f = dec.take(4)
+            got.append((f, torch.as_tensor(f, device="cuda").cpu().numpy().copy()))
+        allf = np.concatenate([g[1] for g in got])
+        assert allf.shape == expect.shape and np.array_equal(allf, expect), "NVDEC output differs from the losslessly coded frames"
+        # decode -> detect + stabilise: device frames from the decoder vs the same NV12 frames from host memory
+        eng.set_input_format("nv12")
+        ref = {k: v.copy() for k, v in eng.extract_batch(expect[:1], first_is_reference=True, conf=0.05, mask_boxes=eng.pack_boxes(boxes[:1])).items()}
+        want = {k: v.copy() for k, v in eng.extract_batch(expect[1:4], conf=0.05, mask_boxes=eng.pack_boxes(boxes[1:4])).items()}
+        dec2 = geotrax_b200.Decoder(eng, "h264")
+        dec2.feed(stream); dec2.feed(None)
+        first = dec2.take(1)
+        eng.extract_batch(first, first_is_reference=True, conf=0.05, mask_boxes=eng.pack_boxes(boxes[:1]))
+        nxt = dec2.take(3)
+        out = eng.extract_batch(nxt, conf=0.05, mask_boxes=eng.pack_boxes(boxes[1:4]))
+        for k in want:
+            assert np.array_equal(out[k][:3], want[k][:3]), k
+        assert int(out["counts"][:3].sum()) > 0 and (out["status"][:3] == 0).all()
+        dec2.close()
+    finally:
+        dec.close()
+        eng.close()
