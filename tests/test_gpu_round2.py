@@ -142,6 +142,68 @@ def test_gate2_end_to_end_margin_aware(full_engine4, oracle_dense, agnostic):
     assert (ious >= 0.99).mean() >= 0.97 and ious.min() >= 0.98, f"box IoU: min {ious.min():.4f}, share >= 0.99 {(ious >= 0.99).mean():.4f}"
 
 
+def test_obb_gate2_end_to_end_margin_aware():
+    """configs[3] (YOLOv8s-OBB): GPU forward -> angle / DFL decode -> rotated Fast-NMS (ProbIoU) against the fp32 oracle end to end, with the
+    same margin logic as the HBB gate: every decision of the oracle that does not hinge on a comparison inside the margins must be
+    reproduced exactly (kept, same class), the rotated box must match corner for corner, and nothing the oracle certainly drops may appear."""
+    import geotrax_b200
+    from geotrax_b200 import synth, weights
+    from oracle import prepost
+    from oracle.yolov8 import YOLOv8
+    hw, imgsz, conf_thr, iou_thr, eps_c, eps_i = (512, 768), 384, 0.05, 0.7, 0.01, 0.02
+    eng = geotrax_b200.Engine(frame_hw=hw, imgsz=imgsz, nc=4, task="obb", max_batch=2, max_det=1000, max_features=500)
+    try:
+        sd = weights.random_state_dict(4, "obb", seed=2, frame_hw=hw, imgsz=imgsz, cls_bias=-3.0)
+        eng.load_weights(weights.fold(sd, 4, "obb"))
+        frames = np.stack(synth.make_flight(3, hw[0], hw[1], seed=5, n_vehicles=12)[0][1:3])
+        eng.preprocess(frames)
+        boxes, counts, keep = eng.detect(2, conf=conf_thr, iou=iou_thr, agnostic=True, classes=None, want_keep=True)
+        m = YOLOv8(4, "obb").eval()
+        m.load_state_dict(sd, strict=False)
+        with torch.no_grad():
+            dec, _ = m(prepost.preprocess(list(frames), imgsz))          # (B, 4 + nc + 1, A): xywh, class probabilities, angle
+        tot_sure = tot_maybe = 0
+        for b in range(2):
+            d = dec[b].numpy()
+            xywhr = np.concatenate([d[:4].T, d[-1:].T], 1)
+            prob = d[4:-1].T
+            conf, cls = prob.max(1), prob.argmax(1)
+            cls_sure = (conf - np.sort(prob, 1)[:, -2]) > eps_c
+            cand = np.nonzero(conf > conf_thr - eps_c)[0]
+            cand = cand[np.argsort(-conf[cand], kind="stable")]
+            c = conf[cand]
+            piou = prepost.batch_probiou(torch.from_numpy(xywhr[cand]), torch.from_numpy(xywhr[cand])).numpy()
+            np.fill_diagonal(piou, 0.0)
+            # Fast-NMS: j is dropped iff ANY higher-scored candidate overlaps it (no cascade), so the margins apply pair by pair
+            surely_cand = c > conf_thr + eps_c
+            sup_sure = ((c[None, :] > c[:, None] + eps_c) & surely_cand[None, :] & (piou >= iou_thr + eps_i)).any(1)
+            sup_maybe = ((c[None, :] > c[:, None] - eps_c) & (piou >= iou_thr - eps_i)).any(1)
+            sure = set(cand[surely_cand & ~sup_maybe].tolist())
+            maybe = set(cand[~sup_sure & ~(surely_cand & ~sup_maybe)].tolist())
+            n = int(counts[b])
+            assert n < 1000
+            got = {int(a): boxes[b, i] for i, a in enumerate(keep[b, :n])}
+            assert not (sure - set(got)), f"frame {b}: anchors the oracle certainly keeps are missing: {sorted(sure - set(got))[:8]}"
+            assert not (set(got) - sure - maybe), f"frame {b}: anchors the oracle certainly drops were kept: {sorted(set(got) - sure - maybe)[:8]}"
+            for a in sure:
+                row = got[a]
+                if cls_sure[a]:
+                    assert int(row[6]) == int(cls[a])
+                rb = prepost.regularize_rboxes(torch.from_numpy(xywhr[a:a + 1].astype(np.float32)))
+                rb[:, :4] = prepost.scale_boxes((256, 384), rb[:, :4], hw, xywh=True)
+                from geotrax_b200.results import OBB
+                want = OBB(np.concatenate([rb.numpy(), [[0, 0]]], 1).astype(np.float32), hw).xyxyxyxy[0]
+                have = OBB(row[None].astype(np.float32), hw).xyxyxyxy[0]
+                dist = np.linalg.norm(np.asarray(have)[:, None, :] - np.asarray(want)[None, :, :], axis=2).min(1)     # corner sets: representation-free
+                tol = max(1.0, 0.01 * float(rb[0, 2] + rb[0, 3]))
+                assert dist.max() < tol, f"frame {b} anchor {a}: rotated-box corners differ by {dist.max():.2f} px (tolerance {tol:.2f})"
+            tot_sure += len(sure); tot_maybe += len(maybe)
+            print(f"OBB frame {b}: gpu kept {n}, oracle certainly-kept {len(sure)}, inside-the-margin {len(maybe)}")
+        assert tot_sure >= 20, f"the test must not be vacuous: {tot_sure} certain vs {tot_maybe} margin anchors"
+    finally:
+        eng.close()
+
+
 # ---------------------------------------------------------------------------------------------------------------------------------
 # determinism across processes
 # ---------------------------------------------------------------------------------------------------------------------------------
