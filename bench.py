@@ -38,8 +38,8 @@ CONV_GFLOP_PER_FRAME = 145.03
 
 
 def _conv_traffic():
-    """DRAM bytes of the conv launches of one step, from the committed ncu capture (profiles/conv_traffic_r1_final.json)."""
-    p = os.path.join(ROOT, "profiles", "conv_traffic_r1_final.json")
+    """DRAM bytes of the conv launches of one step, from the committed ncu capture (profiles/conv_traffic_r2.json)."""
+    p = os.path.join(ROOT, "profiles", "conv_traffic_r2.json")
     try:
         with open(p) as f:
             return float(json.load(f)["traffic_bytes_per_step"])
