@@ -79,6 +79,7 @@ int gt_create(const gt_config* cfg, int device, gt_handle* out) {
   if (const char* sm = getenv("GT_SWAP")) e->swap_mode = atoi(sm);
   if (const char* tm = getenv("GT_TUNE")) e->tune_mode = atoi(tm);
   if (const char* ov = getenv("GT_OVERLAP")) e->overlap = atoi(ov);
+  if (const char* fs = getenv("GT_FRONT_SPLIT")) e->front_split = atoi(fs);
   if (const char* kb = getenv("GT_CONV_SMEM_KB")) e->conv_smem_kb = std::min(227, std::max(96, atoi(kb)));
   if (e->overlap == 1 && !getenv("GT_CONV_SMEM_KB")) e->conv_smem_kb = 200;   // room for ORB blocks beside the conv CTAs
   auto fail = [&](int rc) { g_create_error = e->err; gt_destroy(e); return rc; };
@@ -125,6 +126,9 @@ int gt_create(const gt_config* cfg, int device, gt_handle* out) {
     int lo = 0, hi = 0;
     CRC(cudaDeviceGetStreamPriorityRange(&lo, &hi));
     CRC(cudaStreamCreateWithPriority(&e->aux_stream, cudaStreamNonBlocking, lo));
+    CRC(cudaStreamCreateWithPriority(&e->aux2_stream, cudaStreamNonBlocking, lo));
+    CRC(cudaEventCreateWithFlags(&e->ev_aux_a, cudaEventDisableTiming));
+    CRC(cudaEventCreateWithFlags(&e->ev_aux_b, cudaEventDisableTiming));
     CRC(cudaEventCreateWithFlags(&e->ev_pre, cudaEventDisableTiming));
     CRC(cudaEventCreateWithFlags(&e->ev_front, cudaEventDisableTiming));
   }
@@ -163,6 +167,9 @@ int gt_destroy(gt_handle e) {
   }
   if (e->copy_stream) cudaStreamDestroy(e->copy_stream);
   if (e->aux_stream) cudaStreamDestroy(e->aux_stream);
+  if (e->aux2_stream) cudaStreamDestroy(e->aux2_stream);
+  if (e->ev_aux_a) cudaEventDestroy(e->ev_aux_a);
+  if (e->ev_aux_b) cudaEventDestroy(e->ev_aux_b);
   if (e->ev_pre) cudaEventDestroy(e->ev_pre);
   if (e->ev_front) cudaEventDestroy(e->ev_front);
   if (e->stream) cudaStreamDestroy(e->stream);
@@ -776,9 +783,11 @@ static int extract_batch_impl(gt_handle e, const uint8_t* frames, int B, int fir
       GT_CUDA(e, cudaEventRecord(e->ev_pre, st));
       GT_CUDA(e, cudaStreamWaitEvent(e->aux_stream, e->ev_pre, 0));
     }
-    if (part == 0) GT_TRY(orb_front(e, 0, B, e->aux_stream));
-    else if (part == 1) GT_TRY(orb_pyramid(e, 0, B, e->aux_stream));
-    else GT_TRY(orb_fast(e, 0, B, e->aux_stream));
+    if (part == 0) {
+      if (e->front_split) GT_TRY(orb_front_split(e, 0, B, e->aux_stream, e->aux2_stream, e->ev_aux_a, e->ev_aux_b));
+      else GT_TRY(orb_front(e, 0, B, e->aux_stream));
+    } else if (part == 1) GT_TRY(orb_pyramid(e, 0, B, e->aux_stream));
+    else GT_TRY(orb_fast(e, 0, B, e->aux_stream, 0, GT_ORB_LEVELS, true));
     if (part != 1) GT_CUDA(e, cudaEventRecord(e->ev_front, e->aux_stream));
     return GT_OK;
   };

@@ -62,8 +62,11 @@ struct gt_engine {
   uint8_t* frames_dev2 = nullptr;       // staging buffer 1: gt_prefetch_frames copies batch i+1 while batch i computes
   cudaStream_t copy_stream = nullptr;
   cudaStream_t aux_stream = nullptr;    // low priority: the mask-independent half of ORB runs here next to the detector
+  cudaStream_t aux2_stream = nullptr;   // the image pyramid, beside FAST on level 0 (orb_front_split)
+  cudaEvent_t ev_aux_a = nullptr, ev_aux_b = nullptr;
   cudaEvent_t ev_pre = nullptr, ev_front = nullptr;
   int overlap = 2;                      // GT_OVERLAP: 2 ORB front on the aux stream beside decode + NMS; 3 as 2, but the image pyramid already beside the conv stack (fills the tails between layers); 1 the whole front beside the detector (no gain: the conv CTAs own the SMs); 0 serial
+  int front_split = 0;                  // GT_FRONT_SPLIT=1: FAST on level 0 runs beside the seven pyramid launches (two aux streams) -- measured neutral (5.013 vs 5.020 ms / step), off by default
   int conv_smem_kb = 227;               // dynamic smem budget of the conv kernels (200 with GT_OVERLAP=1 to leave room for ORB blocks); GT_CONV_SMEM_KB
   cudaEvent_t ev_copied[2] = {nullptr, nullptr};   // H2D of staging buffer k finished (copy stream)
   cudaEvent_t ev_consumed[2] = {nullptr, nullptr}; // the preprocess kernel that read staging buffer k finished
@@ -202,7 +205,8 @@ int orb_build(gt_engine* e);
 int orb_run(gt_engine* e, int slot0, int nslots, bool as_reference, bool build_mask, cudaStream_t st);
 int orb_front(gt_engine* e, int slot0, int nslots, cudaStream_t st);   // image pyramid + FAST: independent of the mask
 int orb_pyramid(gt_engine* e, int slot0, int nslots, cudaStream_t st);
-int orb_fast(gt_engine* e, int slot0, int nslots, cudaStream_t st);
+int orb_fast(gt_engine* e, int slot0, int nslots, cudaStream_t st, int level_lo, int level_hi, bool reset);
+int orb_front_split(gt_engine* e, int slot0, int nslots, cudaStream_t st, cudaStream_t st2, cudaEvent_t ev_a, cudaEvent_t ev_b);
 int orb_mask(gt_engine* e, int slot0, int nslots, bool build_mask, cudaStream_t st);   // vehicle mask + its pyramid: independent of orb_front
 int orb_back(gt_engine* e, int slot0, int nslots, bool as_reference, cudaStream_t st);
 // match_ransac.cu

@@ -273,7 +273,7 @@ __device__ __forceinline__ uint32_t arc9(const uint32_t* m) {
 
 __global__ void __launch_bounds__(256, 5) fast_kernel(const uint8_t* __restrict__ img, size_t slab, int slot0, const FastLevels fl,
                                                    unsigned int* __restrict__ cand, uint8_t* __restrict__ cscore, size_t cand_slab,
-                                                   int* __restrict__ counts) {
+                                                   int* __restrict__ counts, int tile_first) {
   __shared__ __align__(16) uint8_t s_img[FT_SH][FT_SW];
   __shared__ __align__(4) uint8_t s_sc[FT_Y + 2][FT_X + 2];
   __shared__ unsigned short s_cand[FT_ROWS * FT_G];   // (task << 4 | pixel mask) of the groups that pass the compass test
@@ -281,11 +281,12 @@ __global__ void __launch_bounds__(256, 5) fast_kernel(const uint8_t* __restrict_
   __shared__ int s_na, s_nl, s_n, s_base;
   __shared__ unsigned int s_xy[FT_X * FT_Y / 4];
   __shared__ uint8_t s_s[FT_X * FT_Y / 4];
+  const int gtile = (int)blockIdx.x + tile_first;   // (a launch may cover a sub-range of the levels: orb_fast)
   int level = 0;
 #pragma unroll
-  for (int l = 1; l < GT_ORB_LEVELS; ++l) level += (int)blockIdx.x >= fl.tile0[l];
+  for (int l = 1; l < GT_ORB_LEVELS; ++l) level += gtile >= fl.tile0[l];
   const int w = fl.w[level], h = fl.h[level];
-  const int tile = (int)blockIdx.x - fl.tile0[level];
+  const int tile = gtile - fl.tile0[level];
   const int by = tile / fl.tiles_x[level], bx = tile - by * fl.tiles_x[level];
   const int slot = slot0 + blockIdx.y;
   const uint8_t* im = img + (size_t)slot * slab + fl.off[level];
@@ -988,24 +989,24 @@ int orb_pyramid(gt_engine* e, int slot0, int nslots, cudaStream_t st) {   // ima
   return GT_OK;
 }
 
-int orb_fast(gt_engine* e, int slot0, int nslots, cudaStream_t st) {      // FAST candidates of every level (needs the image pyramid)
+// FAST candidates of pyramid levels [level_lo, level_hi) (needs those levels of the image pyramid); `reset` clears the per-level counters
+int orb_fast(gt_engine* e, int slot0, int nslots, cudaStream_t st, int level_lo, int level_hi, bool reset) {
   const size_t slab = e->pyr_bytes;
-  GT_CUDA(e, cudaMemsetAsync(e->fast_count + (size_t)slot0 * GT_ORB_LEVELS, 0, (size_t)nslots * GT_ORB_LEVELS * sizeof(int), st));
-  {
-    FastLevels fl;
-    int tiles = 0;
-    for (int l = 0; l < GT_ORB_LEVELS; ++l) {
-      const OrbLevel& L = e->lv[l];
-      const int tx = std::max(0, ceil_div(L.w - 2 * kEdge, FT_X)), ty = std::max(0, ceil_div(L.h - 2 * kEdge, FT_Y));
-      fl.w[l] = L.w; fl.h[l] = L.h; fl.tiles_x[l] = std::max(tx, 1); fl.tile0[l] = tiles; fl.cand_cap[l] = L.cand_cap;
-      fl.off[l] = L.off; fl.cand_off[l] = L.cand_off;
-      tiles += tx * ty;
-    }
-    fl.tile0[GT_ORB_LEVELS] = tiles;
-    if (tiles > 0) {
-      fast_kernel<<<dim3((unsigned)tiles, (unsigned)nslots), 256, 0, st>>>(e->pyr, slab, slot0, fl, e->fast_cand, e->fast_score, e->cand_total, e->fast_count);
-      e->launches++;
-    }
+  if (reset) GT_CUDA(e, cudaMemsetAsync(e->fast_count + (size_t)slot0 * GT_ORB_LEVELS, 0, (size_t)nslots * GT_ORB_LEVELS * sizeof(int), st));
+  FastLevels fl;
+  int tiles = 0;
+  for (int l = 0; l < GT_ORB_LEVELS; ++l) {
+    const OrbLevel& L = e->lv[l];
+    const int tx = std::max(0, ceil_div(L.w - 2 * kEdge, FT_X)), ty = std::max(0, ceil_div(L.h - 2 * kEdge, FT_Y));
+    fl.w[l] = L.w; fl.h[l] = L.h; fl.tiles_x[l] = std::max(tx, 1); fl.tile0[l] = tiles; fl.cand_cap[l] = L.cand_cap;
+    fl.off[l] = L.off; fl.cand_off[l] = L.cand_off;
+    tiles += tx * ty;
+  }
+  fl.tile0[GT_ORB_LEVELS] = tiles;
+  const int first = fl.tile0[level_lo], n = fl.tile0[level_hi] - first;
+  if (n > 0) {
+    fast_kernel<<<dim3((unsigned)n, (unsigned)nslots), 256, 0, st>>>(e->pyr, slab, slot0, fl, e->fast_cand, e->fast_score, e->cand_total, e->fast_count, first);
+    e->launches++;
   }
   GT_CUDA(e, cudaGetLastError());
   return GT_OK;
@@ -1013,7 +1014,19 @@ int orb_fast(gt_engine* e, int slot0, int nslots, cudaStream_t st) {      // FAS
 
 int orb_front(gt_engine* e, int slot0, int nslots, cudaStream_t st) {
   GT_TRY(orb_pyramid(e, slot0, nslots, st));
-  return orb_fast(e, slot0, nslots, st);
+  return orb_fast(e, slot0, nslots, st, 0, GT_ORB_LEVELS, true);
+}
+
+// The same on two streams: FAST on level 0 (53 % of the pixels; needs only the gray frame) runs on `st` WHILE the seven latency-bound
+// pyramid launches run on `st2`; FAST on levels 1..7 follows on `st` once both are done.  ev_a / ev_b order the two streams.
+int orb_front_split(gt_engine* e, int slot0, int nslots, cudaStream_t st, cudaStream_t st2, cudaEvent_t ev_a, cudaEvent_t ev_b) {
+  GT_CUDA(e, cudaEventRecord(ev_a, st));
+  GT_CUDA(e, cudaStreamWaitEvent(st2, ev_a, 0));
+  GT_TRY(orb_pyramid(e, slot0, nslots, st2));
+  GT_CUDA(e, cudaEventRecord(ev_b, st2));
+  GT_TRY(orb_fast(e, slot0, nslots, st, 0, 1, true));
+  GT_CUDA(e, cudaStreamWaitEvent(st, ev_b, 0));
+  return orb_fast(e, slot0, nslots, st, 1, GT_ORB_LEVELS, false);
 }
 
 // Mask-dependent half, part 1: vehicle mask (level 0 from the boxes unless the caller supplied one) + its pyramid.  Needs the boxes
