@@ -32,6 +32,8 @@ BATCH = 16
 CONF, IOU = 0.25, 0.7
 CLS_BIAS = -4.4           # random-init class bias giving ~300 candidates / frame at conf 0.25 (golden: 127-136 kept / frame)
 METRIC = "4K frames/sec detect+stabilize"
+WORKLOAD_FUSED = ("detect+stabilize (configs[1]+[2] fused): 16 x 3840x2160 synthetic BGR frames / step, YOLOv8s nc=4 random-init "
+                  "imgsz 1920 (1088x1920), conf 0.25 iou 0.7 agnostic, ORB 2000/4000 + Hamming 2-NN + 5000-hyp RANSAC, box warp")
 UNIT = "frames/s"
 # algorithmic work per 4K frame (SURVEY.md 8d / BASELINE.md section 2)
 CONV_GFLOP_PER_FRAME = 145.03
@@ -158,12 +160,14 @@ def run_reference(args):
             cpu.frame(frames[1 + (s + j) % 2])
     dt = time.perf_counter() - t0
     fps = args.steps * per_step / dt
+    # same `config` keys as the GPU arm's line (workload, frames_per_step, parallelism): the step is the same 16-frame workload, of which
+    # this arm processes a bounded sample (cpu_baseline.sample) -- the CPU path is batch 1 like extract.py, frames/s is what compares
     line = dict(metric=METRIC, value=fps, unit=UNIT, n_gpus=args.gpus, steps=args.steps, warmup=args.warmup, ms_per_step=1000 * dt / args.steps,
                 higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32", data="synthetic", impl="reference",
-                config=dict(workload="detect+stabilize, 3840x2160 synthetic frames, YOLOv8s nc=4 imgsz 1920, ORB 2000/4000 + BF + MAGSAC++ (default preset)",
-                            frames_per_step=per_step, note="CPU oracle port (fp32 PyTorch + OpenCV), batch 1 like extract.py"),
+                config=dict(workload=WORKLOAD_FUSED, frames_per_step=BATCH, parallelism=f"frame-range shard x{args.gpus}"),
                 cpu_baseline=dict(value=fps, unit=UNIT, cores=cores, kind="port",
-                                  sample=f"{per_step} frames per step x {args.steps} steps (a full step is {BATCH} frames)"),
+                                  sample=f"{per_step} of the step's {BATCH} frames per step x {args.steps} steps, batch 1 like extract.py; "
+                                         "CPU oracle port (fp32 PyTorch YOLOv8s + OpenCV ORB / BFMatcher / findHomography(USAC_MAGSAC)) on all host cores"),
                 e2e=dict(value=fps, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0), gpu_launches=0)
     print(json.dumps(line))
 
@@ -221,7 +225,7 @@ def run_ours(args):
     pin = lambda pair: tuple(torch.from_numpy(a).pin_memory() for a in pair)
     mask_pin, mask_roll_pin = pin(mask), pin(mask_roll)
     out = eng.alloc_outputs(pinned=True)
-    tstream = torch.cuda.Stream(device=dev)     # every kernel / copy of the path is issued on this stream; events time it
+    tstream = torch.cuda.Stream(device=dev, priority=-1)     # every kernel / copy of the path is issued on this (high-priority) stream; events time it
     torch.cuda.set_stream(tstream)
     stream = tstream.cuda_stream
     eng.extract_batch(torch.from_numpy(ref_np).to(dev), first_is_reference=True, conf=CONF, iou=IOU, classes=[0, 1, 2, 3], out=out, stream=stream,
@@ -383,8 +387,9 @@ def run_ours(args):
         roof = dict(bound="hbm", achieved=st["achieved"], peak=peaks["hbm"], unit="GB/s", frac=st["frac"], traffic=None,
                     kernel="ORB pyramid + FAST + select + describe + match + RANSAC launch set of one 16-frame step",
                     peak_source=peaks["src"] + " hbm_gbs", algorithmic_bytes_per_launch_set=30.0e6 * BATCH)
-    cfg = dict(workload=wl_name + ": 16 x 3840x2160 synthetic BGR frames / step, YOLOv8s nc=4 random-init "
-                                  "imgsz 1920 (1088x1920), conf 0.25 iou 0.7 agnostic, ORB 2000/4000 + Hamming 2-NN + 5000-hyp RANSAC, box warp",
+    cfg = dict(workload=WORKLOAD_FUSED if args.workload == "fused" else
+               wl_name + ": 16 x 3840x2160 synthetic BGR frames / step, YOLOv8s nc=4 random-init imgsz 1920 (1088x1920), conf 0.25 iou 0.7 agnostic, "
+                         "ORB 2000/4000 + Hamming 2-NN + 5000-hyp RANSAC, box warp",
                frames_per_step=BATCH, parallelism=f"frame-range shard x{world}",
                driver="pipeline.run_range + gather_records (the product's sharded driver)" if fused else "single-stage loop",
                pipeline=("two batches in flight (gt_extract_batch_async)" if pipelined else "synchronous"), l2="inputs (398 MB / step) larger than the 126 MB L2",

@@ -86,7 +86,12 @@ int gt_create(const gt_config* cfg, int device, gt_handle* out) {
 #define CR(expr) do { int _rc = (expr); if (_rc != GT_OK) return fail(_rc); } while (0)
 #define CRC(call) do { cudaError_t _er = (call); if (_er != cudaSuccess) { gt_set_error(e, "%s -> %s", #call, cudaGetErrorString(_er)); return fail(GT_ERR_CUDA); } } while (0)
   CRC(cudaSetDevice(device));
-  CRC(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
+  {   // the handle's own stream is HIGH priority: its small kernels (decode, NMS, mask pyramid) must get SM slots ahead of the thousands of
+      // queued FAST blocks of the low-priority aux stream that run beside them (GT_TIMELINE: the mask pyramid took 471 us instead of 177)
+    int lo = 0, hi = 0;
+    CRC(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    CRC(cudaStreamCreateWithPriority(&e->stream, cudaStreamNonBlocking, hi));
+  }
   for (int k = 0; k < 2; ++k) {
     for (int i = 0; i < 8; ++i) CRC(cudaEventCreate(&e->ev_sets[k][i]));
     CRC(cudaEventCreateWithFlags(&e->ev_done[k], cudaEventDisableTiming));
@@ -588,6 +593,23 @@ int gt_set_reference(gt_handle e, int frame_slot, const float* boxes, int nboxes
   return GT_OK;
 }
 
+// GT_TIMELINE=1 (diagnostic): timestamps inside one synchronous gt_extract_batch, printed relative to the end of the preprocess kernel
+static cudaEvent_t g_tl[12];
+static bool g_tl_on = false, g_tl_init = false;
+static void tl_mark(int i, cudaStream_t st) {
+  if (!g_tl_init) { g_tl_init = true; g_tl_on = getenv("GT_TIMELINE") != nullptr; if (g_tl_on) for (auto& ev : g_tl) cudaEventCreate(&ev); }
+  if (g_tl_on) cudaEventRecord(g_tl[i], st);
+}
+static void tl_print() {
+  if (!g_tl_on) return;
+  static const char* name[12] = {"preprocess done", "conv stack done", "decode+NMS done", "mask pyramid done", "front (aux) done", "waited for front", "select+describe done",
+                                 "match+RANSAC done", "", "", "", ""};
+  fprintf(stderr, "[gt timeline]");
+  for (int i = 1; i < 8; ++i) { float ms = 0.f; if (cudaEventElapsedTime(&ms, g_tl[0], g_tl[i]) == cudaSuccess) fprintf(stderr, " %s %.0f us |", name[i], ms * 1e3f); }
+  fprintf(stderr, "\n");
+  cudaGetLastError();
+}
+
 static int stabilize_impl(gt_engine* e, int B, cudaStream_t st, bool front_on_aux = false) {
   GT_CHECK(e, e->have_ref, "gt_stabilize: no reference frame set");
   GT_CUDA(e, cudaEventRecord(e->ev[5], st));
@@ -595,13 +617,17 @@ static int stabilize_impl(gt_engine* e, int B, cudaStream_t st, bool front_on_au
   // so it overlaps the tail of the FAST kernel (both are latency / instruction bound and share the SMs well)
   if (front_on_aux) {
     GT_TRY(orb_mask(e, 0, B, true, st));
+    tl_mark(3, st);
     GT_CUDA(e, cudaStreamWaitEvent(st, e->ev_front, 0));
+    tl_mark(5, st);
   } else {
     GT_TRY(orb_front(e, 0, B, st));
     GT_TRY(orb_mask(e, 0, B, true, st));
   }
   GT_TRY(orb_back(e, 0, B, false, st));
+  tl_mark(6, st);
   GT_TRY(stab_match_and_fit(e, B, st));
+  tl_mark(7, st);
   GT_CUDA(e, cudaEventRecord(e->ev[6], st));
   return GT_OK;
 }
@@ -788,14 +814,16 @@ static int extract_batch_impl(gt_handle e, const uint8_t* frames, int B, int fir
       else GT_TRY(orb_front(e, 0, B, e->aux_stream));
     } else if (part == 1) GT_TRY(orb_pyramid(e, 0, B, e->aux_stream));
     else GT_TRY(orb_fast(e, 0, B, e->aux_stream, 0, GT_ORB_LEVELS, true));
-    if (part != 1) GT_CUDA(e, cudaEventRecord(e->ev_front, e->aux_stream));
+    if (part != 1) { GT_CUDA(e, cudaEventRecord(e->ev_front, e->aux_stream)); tl_mark(4, e->aux_stream); }
     return GT_OK;
   };
+  tl_mark(0, st);
   if (e->overlap == 1) GT_TRY(fork_front(0));
   if (e->overlap == 3) GT_TRY(fork_front(1));
   GT_CUDA(e, cudaEventRecord(e->ev[2], st));
   GT_TRY(detector_forward(e, B, st));
   GT_CUDA(e, cudaEventRecord(e->ev[3], st));
+  tl_mark(1, st);
   if (e->overlap == 2) GT_TRY(fork_front(0));
   if (e->overlap == 3) {   // FAST starts when the conv stack has finished (and, by stream order, after the pyramid)
     GT_CUDA(e, cudaEventRecord(e->ev_pre, st));
@@ -804,6 +832,7 @@ static int extract_batch_impl(gt_handle e, const uint8_t* frames, int B, int fir
   }
   GT_TRY(detector_postprocess(e, B, conf, iou, agnostic, classes_mask, st));
   GT_CUDA(e, cudaEventRecord(e->ev[4], st));
+  tl_mark(2, st);
   dim3 g((unsigned)ceil_div(md, 256), (unsigned)B);
   dets_to_xywh_kernel<<<g, 256, 0, st>>>(e->det_out, e->det_count, obb ? 7 : 6, md, e->det_xywh_dev, e->det_nbox_dev, B, obb);
   e->launches++;
@@ -829,6 +858,7 @@ static int extract_batch_impl(gt_handle e, const uint8_t* frames, int B, int fir
   if (!sync) return GT_OK;
   GT_CUDA(e, cudaStreamSynchronize(st));
   update_times(e);
+  tl_print();
   return GT_OK;
 }
 

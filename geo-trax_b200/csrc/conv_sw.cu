@@ -1,7 +1,7 @@
 // Swapped-operand tcgen05 implicit-GEMM convolution (sm_100a): D[cout][pixels] = W[cout][K] . X[pixels][K]^T.
 //
 // Why: a 256-pixel tile as the GEMM N dimension halves the instruction count and the weight re-reads of the 3x3 layers with
-// cout >= 128 (one M128 x N256 x K16 tcgen05.mma = 135 cycles = 95 % of the pipe's nominal rate, tools/scratch/mma_bench.cu); the
+// cout >= 128 (one M128 x N256 x K16 tcgen05.mma = 135 cycles = 95 % of the pipe's nominal rate, tools/mma_bench.cu); the
 // WEIGHTS are the A operand (M = 128 output channels, zero rows above cout), the pixels the B operand; cout > 128 runs
 // ceil(cout / 128) M tiles.  (The first motivation written here -- "an MMA costs 130-150 cycles whatever N" -- was a measurement of
 // the old issue path, not of the pipe: profiles/round1_summary.md section 3.)  The per-layer autotuner picks this kernel for 17-24 of the

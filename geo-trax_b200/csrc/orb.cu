@@ -214,7 +214,7 @@ __device__ __forceinline__ int fast_corner_score(const uint8_t (*t)[FT_SW], int 
   // exact corner score: the largest threshold for which the pixel is still a corner = max over the 16 circular 9-arcs of
   // min(d) (darker arcs) and of min(-d) (brighter arcs), minus 1.  Written as a doubling min-network on d and on an
   // explicitly negated copy: the straightforward "max(mn, -mx)" form is miscompiled by ptxas 12.9 -O1..-O3 for sm_100a
-  // (wrong VIMNMX3 fusion; repro in tools/scratch/fast_test.cu: 7,325 wrong scores at -O3, 0 at -Xptxas -O0).
+  // (wrong VIMNMX3 fusion; repro in tools/fast_test.cu: 7,325 wrong scores at -O3, 0 at -Xptxas -O0).
   int nd[16], a2[16], a4[16], a8[16], b2[16], b4[16], b8[16];
 #pragma unroll
   for (int k = 0; k < 16; ++k) nd[k] = -d[k];

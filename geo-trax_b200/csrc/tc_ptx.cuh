@@ -81,7 +81,7 @@ __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64
 // ---- lean issue helpers: descriptors as (running 32-bit low word, constant high word) ----------------------------------------
 // The single issuing lane is latency bound: with general 64-bit descriptor arithmetic the issue block of one k-block cost ~360
 // cycles (measured with clock64), more than the 2-4 MMAs of the block take on the tensor pipe (135 cycles for M128 N256 K16,
-// 71 for N128, 55 for N <= 64: tools/scratch/mma_bench.cu), so the pipe idled.  High word = SBO | version | layout.
+// 71 for N128, 55 for N <= 64: tools/mma_bench.cu), so the pipe idled.  High word = SBO | version | layout.
 __device__ __forceinline__ uint32_t desc_hi(uint32_t sbo_bytes, uint32_t layout) { return (sbo_bytes >> 4) | (1u << 14) | (layout << 29); }
 // D (+)= A . B^T with descriptors given as (low word, high word); ACC = 0: overwrite, 1: accumulate, 2: runtime flag `acc`
 template <int ACC>

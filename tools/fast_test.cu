@@ -78,7 +78,7 @@ __global__ void score_kernel(const uint8_t* im, int w, int h, uint8_t* out) {
 int main() {
   const int w = 960, h = 540;
   std::vector<uint8_t> im(w * h), ref(w * h, 0), got(w * h);
-  FILE* f = fopen("tools/scratch/g.bin", "rb"); if (!f) { printf("no g.bin\n"); return 1; } size_t n = fread(im.data(), 1, w * h, f); fclose(f); (void)n;
+  FILE* f = fopen("gpurun_out/g.bin", "rb"); if (!f) { printf("no g.bin\n"); return 1; } size_t n = fread(im.data(), 1, w * h, f); fclose(f); (void)n;
   static uint8_t tile[FT_Y + 8][FT_X + 8];
   for (int y = 3; y < h - 3; ++y) for (int x = 3; x < w - 3; ++x) {
     for (int ty = 0; ty < 9; ++ty) for (int tx = 0; tx < 9; ++tx) tile[ty][tx] = im[(y - 4 + ty) < 0 || (y - 4 + ty) >= h || (x - 4 + tx) < 0 || (x - 4 + tx) >= w ? 0 : (size_t)(y - 4 + ty) * w + (x - 4 + tx)];

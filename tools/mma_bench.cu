@@ -1,5 +1,5 @@
 // Microbenchmark: back-to-back tcgen05.mma (cta_group::1, kind::f16, SS operands) issue rate on sm_100a.
-// nvcc -gencode arch=compute_100a,code=sm_100a -O3 -I geo-trax_b200/csrc -o gpurun_out/mma_bench tools/scratch/mma_bench.cu -lcuda
+// nvcc -gencode arch=compute_100a,code=sm_100a -O3 -I geo-trax_b200/csrc -o gpurun_out/mma_bench tools/mma_bench.cu -lcuda
 #include <cstdio>
 #include <cuda.h>
 #include <cuda_runtime.h>
