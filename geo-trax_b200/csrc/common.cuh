@@ -84,7 +84,7 @@ struct ConvParams {
   int b_resident;         // 1: all weight k-blocks stay in shared memory for the CTA's lifetime (ring holds A only)
   int epi_mode;           // 0: 16-bit 128-B slabs, 1: 16-bit 64-B slab, 2: f32 128-B slabs, 3: f32 64-B slab
   int cout;               // real output channels
-  int act;                // 1 = SiLU
+  int act;                // 0 linear, 1 SiLU (ex2 + rcp: 2 MUFU), 2 SiLU in the one-MUFU tanh form (MUFU-bound layers, see tc_ptx.cuh)
   int out_f32;            // 1: out is float (raw head), 0: 16-bit act dtype
   int fp16;               // 16-bit format: 1 = fp16, 0 = bf16
   float scale;            // accumulator scale applied before the bias (1/255 for layer 0, else 1)

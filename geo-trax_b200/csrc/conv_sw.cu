@@ -459,11 +459,9 @@ __global__ void __launch_bounds__(kSwThreads, 1) conv_sw_kernel(const __grid_con
             const float4 b4 = lds_f4(smem_u32(s_bias + cb + g8 * 4));
             const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              const float a = fmaf(f[g8 * 4 + k], p.scale, bb[k]);
-              f[g8 * 4 + k] = p.act ? silu_fast(a) : a;
-            }
+            for (int k = 0; k < 4; ++k) f[g8 * 4 + k] = fmaf(f[g8 * 4 + k], p.scale, bb[k]);
           }
+          act_inplace<32>(f, p.act);
 #pragma unroll
           for (int g8 = 0; g8 < 4; ++g8) {
             const int c0 = cb + g8 * 8;
@@ -525,10 +523,8 @@ __global__ void __launch_bounds__(kSwThreads, 1) conv_sw_kernel(const __grid_con
           if (!warp_active) continue;
           float f[32];
 #pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            const float a = fmaf(__uint_as_float(v[i]), p.scale, bias);
-            f[i] = p.act ? silu_fast(a) : a;
-          }
+          for (int i = 0; i < 32; ++i) f[i] = fmaf(__uint_as_float(v[i]), p.scale, bias);
+          act_inplace<32>(f, p.act);
           const uint32_t rowoff = (uint32_t)(c * 32) * 128u;
           if (p.res) {   // residual values sit in the granule at the very addresses this thread is about to overwrite
 #pragma unroll
@@ -582,11 +578,13 @@ __global__ void __launch_bounds__(kSwThreads, 1) conv_sw_kernel(const __grid_con
           __syncwarp();
           // row i (pixel), 4-byte element `lane`: chunk = lane >> 2, swizzled with row & 7
 #pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            const float a = fmaf(__uint_as_float(v[i]), p.scale, bias);
-            const float o = p.act ? silu_fast(a) : a;
-            sts_u32(buf + (uint32_t)i * 128u + (uint32_t)((((lane >> 2) ^ (i & 7)) << 4) + (lane & 3) * 4), __float_as_uint(o));
-          }
+          float fo[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) fo[i] = fmaf(__uint_as_float(v[i]), p.scale, bias);
+          act_inplace<32>(fo, p.act);
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            sts_u32(buf + (uint32_t)i * 128u + (uint32_t)((((lane >> 2) ^ (i & 7)) << 4) + (lane & 3) * 4), __float_as_uint(fo[i]));
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
           __syncwarp();
           if (lane == 0) {

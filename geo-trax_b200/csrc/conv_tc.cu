@@ -106,9 +106,12 @@ __device__ __forceinline__ void epilogue_tile(const ConvParams& p, const TileCoo
         }
       }
     }
-    if (p.act) {
+    if (p.act == 1) {
 #pragma unroll
       for (int i = 0; i < CW; ++i) f[i] = silu_fast(f[i]);
+    } else if (p.act == 2) {   // one-MUFU form (MUFU-bound layers)
+#pragma unroll
+      for (int i = 0; i < CW; ++i) f[i] = silu_tanh(f[i]);
     }
     uint4 pk[CHUNKS];
     if constexpr (F32) {

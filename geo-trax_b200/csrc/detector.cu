@@ -908,7 +908,13 @@ struct Builder {
       default: return true;
     }
   }
-  int plan_both(ConvOp& op, const ConvPlanArgs& a) {
+  int plan_both(ConvOp& op, const ConvPlanArgs& a_in) {
+    ConvPlanArgs a = a_in;
+    // MUFU-bound layers (>= silu_tanh_px output pixels per image; layer 0 counts its 2 x 2 pixels per GEMM row) use the one-MUFU SiLU
+    if (a.act == 1 && e->silu_tanh_px > 0) {
+      const ConvSig sg = conv_signature(a);
+      if ((long long)sg.H * sg.W * (a.out_s2d ? 4 : 1) >= e->silu_tanh_px) a.act = 2;
+    }
     if (e->swap_mode >= 0) {               // GT_SWAP=v: one variant forced wherever it applies (tests)
       e->plan_variant = e->swap_mode;
       return conv_tc_plan(e, &op, a);

@@ -235,6 +235,27 @@ __device__ __forceinline__ float silu_fast(float a) {
   asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + e));
   return a * r;
 }
+// SiLU with ONE MUFU op: a * (0.5 + 0.5 * tanh(a / 2)) -- FMUL, MUFU.TANH, FFMA, FMUL.  tanh.approx.f32 has an absolute error of 2^-11, so
+// sigma is off by <= 2.4e-4 absolute: comparable to the fp16 rounding of the stored output (4.9e-4 relative) for positive a, larger in
+// relative terms on the negative tail.  Used where the epilogue is MUFU bound (ConvParams::act == 2: the 544x960 / 272x480 layers,
+// 2 MUFU x 50 M outputs per frame = 345 us per step at 16 / clk / SM) and accounted for in the raw-head gate (tests + DESIGN.md 4.2).
+__device__ __forceinline__ float silu_tanh(float a) {
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(a * 0.5f));
+  return a * fmaf(0.5f, t, 0.5f);
+}
+// activation of N register values; the (warp-uniform) mode is tested ONCE, outside the unrolled loops -- a per-element `mode == 1 ? .. : ..`
+// makes the compiler evaluate both forms and select (3 MUFU per value: the swapped kernels got 10-70 % slower that way)
+template <int N>
+__device__ __forceinline__ void act_inplace(float* f, int mode) {
+  if (mode == 2) {
+#pragma unroll
+    for (int i = 0; i < N; ++i) f[i] = silu_tanh(f[i]);
+  } else if (mode == 1) {
+#pragma unroll
+    for (int i = 0; i < N; ++i) f[i] = silu_fast(f[i]);
+  }
+}
 __device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, %0;" ::"n"(kEpiWarps * 32) : "memory"); }
 
 struct TileCoord { int n, y0, x0, n0; };
