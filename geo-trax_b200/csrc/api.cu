@@ -430,10 +430,11 @@ int gt_get_raw_head(gt_handle e, int B, float* out, int32_t* A, int32_t* no) {
   if (no) *no = e->no;
   if (out) {
     GT_CUDA(e, cudaStreamSynchronize(e->stream));
-    const size_t rows = (size_t)B * e->A, nb = (size_t)(64 + e->cfg.nc) * 4;   // dense [no] rows out of the padded device rows
-    GT_CUDA(e, cudaMemcpy2D(out, (size_t)e->no * 4, e->raw_head, (size_t)e->no_pad * 4, nb, rows, cudaMemcpyDefault));
+    const size_t rows = (size_t)B * e->A;   // dense [no] rows assembled from the three device arrays
+    GT_CUDA(e, cudaMemcpy2D(out, (size_t)e->no * 4, e->raw_box, 64 * 4, 64 * 4, rows, cudaMemcpyDefault));
+    GT_CUDA(e, cudaMemcpy2D(out + 64, (size_t)e->no * 4, e->raw_cls, (size_t)e->ncp * 4, (size_t)e->cfg.nc * 4, rows, cudaMemcpyDefault));
     if (e->cfg.task == GT_TASK_OBB)
-      GT_CUDA(e, cudaMemcpy2D(out + 64 + e->cfg.nc, (size_t)e->no * 4, e->raw_head + e->ang_col, (size_t)e->no_pad * 4, 4, rows, cudaMemcpyDefault));
+      GT_CUDA(e, cudaMemcpy2D(out + 64 + e->cfg.nc, (size_t)e->no * 4, e->raw_ang, 4 * 4, 4, rows, cudaMemcpyDefault));
   }
   return GT_OK;
 }

@@ -452,7 +452,8 @@ __device__ __forceinline__ float dfl_side(const float* p) {
   return ws / s;
 }
 
-__global__ void __launch_bounds__(256) decode_filter_kernel(const float* __restrict__ raw, int B, int A, int no, int ang_col, int nc, int obb,
+__global__ void __launch_bounds__(256) decode_filter_kernel(const float* __restrict__ raw_box, const float* __restrict__ raw_cls, const float* __restrict__ raw_ang,
+                                                            int B, int A, int ncp, int nc, int obb,
                                                             DecodeGeom g, float conf_thr, ClassMask cm,
                                                             float* __restrict__ cand_box, float* __restrict__ cand_conf,
                                                             int* __restrict__ cand_cls, unsigned long long* __restrict__ keys,
@@ -460,12 +461,15 @@ __global__ void __launch_bounds__(256) decode_filter_kernel(const float* __restr
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= (long long)B * A) return;
   const int b = (int)(idx / A), a = (int)(idx - (long long)b * A);
-  const float* r = raw + (size_t)idx * no;
-  float best = r[64];
+  // the class logits are a dense [anchor][ncp] array of their own: the confidence test of the ~99 % of anchors that fail it touches
+  // 4 * ncp contiguous bytes per anchor, the 256-byte DFL row only for candidates
+  const float* rc = raw_cls + (size_t)idx * ncp;
+  const float* r = raw_box + (size_t)idx * 64;
+  float best = rc[0];
   int bj = 0;
   bool bad = !isfinite(best);
   for (int j = 1; j < nc; ++j) {
-    const float v = r[64 + j];
+    const float v = rc[j];
     bad |= !isfinite(v);
     if (v > best) { best = v; bj = j; }
   }
@@ -477,7 +481,7 @@ __global__ void __launch_bounds__(256) decode_filter_kernel(const float* __restr
   // the reference takes max/argmax over the *probabilities* (cls.sigmoid().max(1)): when the sigmoid saturates, several
   // classes tie at the same float and the first index wins
   for (int j = 0; j < bj; ++j)
-    if (sigmoid_f(r[64 + j]) >= conf) { bj = j; break; }
+    if (sigmoid_f(rc[j]) >= conf) { bj = j; break; }
   if (!cm.allows(bj)) return;
   int lvl = 0;
   if (a >= g.lvl_off[2]) lvl = 2; else if (a >= g.lvl_off[1]) lvl = 1;
@@ -501,7 +505,7 @@ __global__ void __launch_bounds__(256) decode_filter_kernel(const float* __restr
     const float hw = __fmul_rn(w, 0.5f), hh = __fmul_rn(h, 0.5f);
     o[0] = __fsub_rn(cx, hw); o[1] = __fsub_rn(cy, hh); o[2] = __fadd_rn(cx, hw); o[3] = __fadd_rn(cy, hh); o[4] = 0.f;
   } else {
-    const float ang = (sigmoid_f(r[ang_col]) - 0.25f) * 3.14159265358979323846f;
+    const float ang = (sigmoid_f(raw_ang[(size_t)idx * 4]) - 0.25f) * 3.14159265358979323846f;
     const float cs = cosf(ang), sn = sinf(ang);
     const float xf = (d[2] - d[0]) * 0.5f, yf = (d[3] - d[1]) * 0.5f;
     o[0] = (xf * cs - yf * sn + ax) * s; o[1] = (xf * sn + yf * cs + ay) * s;
@@ -780,7 +784,7 @@ int nms_run(gt_engine* e, const float* pred_dev, int B, int A, int nc, int rotat
   } else {
     DecodeGeom g;
     for (int i = 0; i < 3; ++i) { g.lvl_w[i] = e->lvl_w[i]; g.lvl_h[i] = e->lvl_h[i]; g.lvl_off[i] = e->lvl_off[i]; g.stride[i] = (float)(8 << i); }
-    decode_filter_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(e->raw_head, B, A, e->no_pad, e->ang_col, nc, rotated, g, conf, cm,
+    decode_filter_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(e->raw_box, e->raw_cls, e->raw_ang, B, A, e->ncp, nc, rotated, g, conf, cm,
                                                                           e->cand_box, e->cand_conf, e->cand_cls, e->cand_key, key_stride,
                                                                           e->cand_count, e->nonfinite_dev);
     GT_CUDA(e, cudaMemcpyAsync(e->nonfinite_host, e->nonfinite_dev, sizeof(int), cudaMemcpyDeviceToHost, st));   // cumulative counter -> pinned mirror
@@ -961,15 +965,15 @@ struct Builder {
     rc = plan_both(op, a);
     if (rc == GT_OK) push(op);
   }
-  // final head conv writing fp32 raw rows
-  void conv_raw(const std::string& name, const View& in, int lvl_off, int coff) {
+  // final head conv writing fp32 rows of one of the three raw-head arrays (box logits [A][64], class logits [A][ncp], angle [A][4])
+  void conv_raw(const std::string& name, const View& in, int lvl_off, float* base, int ctot) {
     if (rc != GT_OK) return;
     ConvOp op;
     op.n_src = 1; op.src[0] = find(name);
     const gt_conv_desc& d = e->conv_descs[op.src[0]];
     ConvPlanArgs a;
     a.in = in; a.Bmax = B; a.cin = d.cin; a.cout = d.cout; a.k = d.k; a.stride = d.stride; a.act = d.act;
-    a.out_f32 = e->raw_head + (size_t)lvl_off * e->no_pad; a.out_img_stride = e->A; a.out_ctot_f32 = e->no_pad; a.out_coff_f32 = coff;
+    a.out_f32 = base + (size_t)lvl_off * ctot; a.out_img_stride = e->A; a.out_ctot_f32 = ctot; a.out_coff_f32 = 0;
     rc = plan_both(op, a);
     if (rc == GT_OK) push(op);
   }
@@ -1107,10 +1111,20 @@ int detector_build(gt_engine* e) {
   e->lvl_off[0] = 0; e->lvl_off[1] = H3 * W3; e->lvl_off[2] = H3 * W3 + H4 * W4;
   e->A = H3 * W3 + H4 * W4 + H5 * W5;
   e->no = 64 + nc + (obb ? 1 : 0);
-  e->ang_col = (64 + nc + 3) / 4 * 4;
-  e->no_pad = ((obb ? e->ang_col + 1 : 64 + nc) + 3) / 4 * 4;
-  GT_TRY(e->dev_alloc((void**)&e->raw_head, (size_t)B * e->A * e->no_pad * sizeof(float)));
-  GT_CUDA(e, cudaMemset(e->raw_head, 0, (size_t)B * e->A * e->no_pad * sizeof(float)));
+  // The raw head lives in three dense fp32 arrays -- box logits [B][A][64] (256-byte rows), class logits [B][A][ncp] (ncp = nc rounded up
+  // to 4: 16-byte rows for the 4-class head), OBB angle [B][A][4] -- so that every row and every slab chunk the final 1x1 convs store
+  // starts on a 32-byte DRAM sector and a tile's class rows are contiguous.  (One interleaved [A][68] array put odd rows 16 bytes off
+  // a sector: the 64->64 box conv took 63 us instead of 37, and decode read a 32-byte sector for every 16 bytes of class logits.)
+  e->ncp = (nc + 3) / 4 * 4;
+  const size_t nA = (size_t)B * e->A;
+  GT_TRY(e->dev_alloc((void**)&e->raw_box, nA * 64 * sizeof(float)));
+  GT_TRY(e->dev_alloc((void**)&e->raw_cls, nA * e->ncp * sizeof(float)));
+  GT_CUDA(e, cudaMemset(e->raw_box, 0, nA * 64 * sizeof(float)));
+  GT_CUDA(e, cudaMemset(e->raw_cls, 0, nA * e->ncp * sizeof(float)));
+  if (obb) {
+    GT_TRY(e->dev_alloc((void**)&e->raw_ang, nA * 4 * sizeof(float)));
+    GT_CUDA(e, cudaMemset(e->raw_ang, 0, nA * 4 * sizeof(float)));
+  }
 
   View S2D = bl.alloc(64, H2, W2);          // 4x4 space-to-depth network input, written by stage 1
   e->net_s2d = S2D.ptr;
@@ -1169,12 +1183,12 @@ int detector_build(gt_engine* e) {
     View b2 = bl.alloc(hc2, feats[i].H, feats[i].W), b3 = bl.alloc(hc3, feats[i].H, feats[i].W);
     bl.conv({"model.22.cv2." + s + ".1"}, a.slice(0, hc2), b2);
     bl.conv({"model.22.cv3." + s + ".1"}, a.slice(hc2, hc3), b3);
-    bl.conv_raw("model.22.cv2." + s + ".2", b2, e->lvl_off[i], 0);
-    bl.conv_raw("model.22.cv3." + s + ".2", b3, e->lvl_off[i], 64);
+    bl.conv_raw("model.22.cv2." + s + ".2", b2, e->lvl_off[i], e->raw_box, 64);
+    bl.conv_raw("model.22.cv3." + s + ".2", b3, e->lvl_off[i], e->raw_cls, e->ncp);
     if (obb) {
       View b4 = bl.alloc(hc4, feats[i].H, feats[i].W);
       bl.conv({"model.22.cv4." + s + ".1"}, a.slice(hc2 + hc3, hc4), b4);
-      bl.conv_raw("model.22.cv4." + s + ".2", b4, e->lvl_off[i], e->ang_col);
+      bl.conv_raw("model.22.cv4." + s + ".2", b4, e->lvl_off[i], e->raw_ang, 4);
     }
   }
   if (bl.rc != GT_OK) return bl.rc;

@@ -54,7 +54,7 @@ struct gt_engine {
   float gain = 1.f;
   int work_h = 0, work_w = 0;
   int A = 0, no = 0;                    // anchors, raw head row width (64 + nc (+1))
-  int no_pad = 0, ang_col = 0;          // raw_head row stride in floats (multiple of 4: TMA store rows are 16-byte aligned); OBB angle column
+  int ncp = 0;                          // class-logit row width (nc rounded up to 4 floats)
   int lvl_h[3], lvl_w[3], lvl_off[3];
 
   // staging + stage 1
@@ -105,7 +105,9 @@ struct gt_engine {
   std::vector<PlanOp> plan;
   int conv0_op = -1;                                // index of layer 0 in conv_ops (custom weight packing)
   View feat_views[23];
-  float* raw_head = nullptr;                        // [B][A][no_pad]
+  float* raw_box = nullptr;                         // [B][A][64] DFL logits (f32 rows written by the cv2.x.2 convs)
+  float* raw_cls = nullptr;                         // [B][A][ncp] class logits (cv3.x.2)
+  float* raw_ang = nullptr;                         // [B][A][4] OBB angle logit in column 0 (cv4.x.2)
   // decode + NMS workspaces
   int cand_cap = 0;                                 // candidates per image
   float* cand_box = nullptr;                        // [B][cand_cap][5] x1,y1,x2,y2 (or x,y,w,h) + angle
