@@ -75,6 +75,7 @@ SYMBOLS = {
     "gt_set_reference": (_i, [_H, _i, _P, _i, _P]),
     "gt_stabilize": (_i, [_H, _i, _P, _P, _i, _P, _P, _P, _P]),
     "gt_warp_boxes": (_i, [_H, _P, _P, _i, _P]),
+    "gt_warp_frames": (_i, [_H, _P, _P, _i, _P, _P]),
     "gt_orb_level_info": (_i, [_H, _i, _ip, _ip, _ip, _ip]),
     "gt_get_pyramid_level": (_i, [_H, _i, _i, _i, _P, _P]),
     "gt_get_keypoints": (_i, [_H, _i, _i, _i, _P, _P, _ip]),

@@ -663,6 +663,27 @@ int gt_warp_boxes(gt_handle e, const double* H, float* boxes, int n, void* strea
   return GT_OK;
 }
 
+int gt_warp_frames(gt_handle e, const uint8_t* frames, const double* H, int B, uint8_t* out, void* stream) {
+  ENTER(e);
+  GT_CHECK(e, frames && H && out && B >= 1 && B <= e->cfg.max_batch, "gt_warp_frames: bad arguments (B=%d)", B);
+  cudaStream_t st = pick_stream(e, stream);
+  const size_t bytes = (size_t)B * e->cfg.frame_h * e->cfg.frame_w * 3;
+  const uint8_t* src = frames;
+  if (!is_device_ptr(frames)) {
+    GT_TRY(to_device(e, e->frames_dev, frames, bytes, st));
+    src = e->frames_dev;
+  }
+  uint8_t* dst = out;
+  if (!is_device_ptr(out)) {
+    if (!e->warp_out) GT_TRY(e->dev_alloc((void**)&e->warp_out, (size_t)e->cfg.max_batch * e->cfg.frame_h * e->cfg.frame_w * 3));
+    dst = e->warp_out;
+  }
+  GT_TRY(warp_frames_run(e, src, dst, H, B, st));
+  if (dst != out) GT_CUDA(e, cudaMemcpyAsync(out, dst, bytes, cudaMemcpyDeviceToHost, st));
+  GT_CUDA(e, cudaStreamSynchronize(st));
+  return GT_OK;
+}
+
 int gt_orb_level_info(gt_handle e, int level, int32_t* w, int32_t* hgt, int32_t* quota_cur, int32_t* quota_ref) {
   if (!e || level < 0 || level >= GT_ORB_LEVELS) return GT_ERR_INVALID;
   if (w) *w = e->lv[level].w;

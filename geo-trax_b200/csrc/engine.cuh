@@ -170,6 +170,8 @@ struct gt_engine {
   int* H_status = nullptr;                          // [B]
   int* H_stats = nullptr;                           // [B][4]
   float* boxes_stab_dev = nullptr;                  // [B][max_det][4]
+  double* warp_minv = nullptr;                      // [B][9] inverse transforms of gt_warp_frames
+  uint8_t* warp_out = nullptr;                      // [B][H][W][3] device staging of gt_warp_frames for host destinations (allocated on first use)
 
   // timing
   cudaEvent_t ev_sets[2][8];            // two sets of stage-timing events: gt_extract_batch_async alternates between them
@@ -198,6 +200,9 @@ int detector_forward(gt_engine* e, int B, cudaStream_t st);
 int detector_postprocess(gt_engine* e, int B, float conf, float iou, int agnostic, uint32_t classes_mask, cudaStream_t st);
 int nms_run(gt_engine* e, const float* pred_dev, int B, int A, int nc, int rotated, float conf, float iou, int agnostic,
             uint32_t classes_mask, int max_det, bool scale_to_frame, cudaStream_t st);
+
+// warp.cu
+int warp_frames_run(gt_engine* e, const uint8_t* src_dev, uint8_t* dst_dev, const double* H_host, int B, cudaStream_t st);
 
 // clahe.cu
 int clahe_build(gt_engine* e);

@@ -253,6 +253,16 @@ class Engine:
         self._ck(self.lib.gt_warp_boxes(self.h, Hc.ctypes.data, b.ctypes.data, len(b), None))
         return b
 
+    def warp_frames(self, frames, H, out=None):
+        """``cv2.warpPerspective(frame, H, (w, h))`` for a batch of BGR frames (numpy or CUDA tensor), bit-exact: the stabilised view the
+        reference's visualisation renders (/root/reference/geotrax/visualize.py:285-289).  H: (B, 3, 3) / (B, 9) f64 current -> reference."""
+        B = int(frames.shape[0])
+        Hc = np.ascontiguousarray(np.asarray(H, np.float64).reshape(B, 9))
+        if out is None:
+            out = np.empty((B, self.cfg.frame_h, self.cfg.frame_w, 3), np.uint8)
+        self._ck(self.lib.gt_warp_frames(self.h, _ptr(frames), Hc.ctypes.data, B, _ptr(out), None))
+        return out
+
     def orb_level_info(self):
         out = []
         for l in range(GT_ORB_LEVELS):

@@ -179,6 +179,11 @@ int gt_stabilize(gt_handle h, int B, const float* boxes, const int32_t* nboxes, 
 /* boxes xywh (n,4) warped in place: 4 corners -> H -> axis-aligned envelope -> xywh (extract.py:183)            */
 int gt_warp_boxes(gt_handle h, const double* H, float* boxes, int n, void* stream);
 
+/* frames u8 BGR [B][frame_h][frame_w][3] warped into the reference frame: out = cv2.warpPerspective(frame, H, (w, h)) with INTER_LINEAR and
+ * a constant 0 border, bit for bit -- what the reference's visualisation does with every frame and its transform
+ * (/root/reference/geotrax/visualize.py:285-289).  H f64 [B][9] row-major (host), frames / out host or device.                          */
+int gt_warp_frames(gt_handle h, const uint8_t* frames, const double* H, int B, uint8_t* out, void* stream);
+
 /* ORB stage read-backs for stage-wise parity against OpenCV.  which: 0 = current batch slot b, 1 = reference.   */
 int gt_orb_level_info(gt_handle h, int level, int32_t* w, int32_t* hgt, int32_t* quota_cur, int32_t* quota_ref);
 int gt_get_pyramid_level(gt_handle h, int which, int b, int level, uint8_t* out_img, uint8_t* out_mask);

@@ -323,3 +323,40 @@ def clahe_u8(src: np.ndarray, clip_limit: float = 2.0, tiles=(8, 8)) -> np.ndarr
         bot = luts[y2[y], x1, v].astype(np.float32) * xa1 + luts[y2[y], x2, v].astype(np.float32) * xa
         out[y] = np.clip(np.rint(top * ya1[y] + bot * ya[y]), 0, 255).astype(np.uint8)
     return out
+
+
+def warp_perspective_u8(src: np.ndarray, H: np.ndarray, dsize=None) -> np.ndarray:
+    """``cv2.warpPerspective(src, H, (w, h))`` (INTER_LINEAR, BORDER_CONSTANT 0) for 8-bit images, restated -- what the reference's
+    visualisation does with every frame and its transform (/root/reference/geotrax/visualize.py:285-289).
+
+    OpenCV inverts H, walks the destination in 64-pixel-wide blocks with ``X0 = M0*bx + M1*y + M2`` per block row and
+    ``X = round(((X0 + M0*x1) * (32 / W)))`` in double precision (1/32-pixel fixed point), and blends the 2 x 2 source pixels with the
+    15-bit weights ``(32 - ay)(32 - ax) * 32`` ... , rounding with ``(sum + 2^14) >> 15``.  Pinned bit-exact against cv2 in
+    tests/test_oracle_model.py; the CUDA kernel (gt_warp_frames) is checked against cv2 on the GPU."""
+    import cv2
+
+    h, w = src.shape[:2]
+    W, Hh = dsize if dsize is not None else (w, h)
+    M = cv2.invert(np.asarray(H, np.float64))[1].ravel()
+    cn = src.shape[2] if src.ndim == 3 else 1
+    s = src.reshape(h, w, cn).astype(np.int64)
+    out = np.zeros((Hh, W, cn), np.uint8)
+    xs = np.arange(W)
+    bx = (xs // 64) * 64
+    x1 = xs - bx
+
+    def fetch(yy, xx):
+        ok = (xx >= 0) & (xx < w) & (yy >= 0) & (yy < h)
+        return np.where(ok[:, None], s[np.clip(yy, 0, h - 1), np.clip(xx, 0, w - 1)], 0)
+
+    for y in range(Hh):
+        X0, Y0, W0 = M[0] * bx + M[1] * y + M[2], M[3] * bx + M[4] * y + M[5], M[6] * bx + M[7] * y + M[8]
+        Wd = W0 + M[6] * x1
+        Wd = np.where(Wd != 0, 32.0 / np.where(Wd != 0, Wd, 1.0), 0.0)
+        X = np.rint(np.clip((X0 + M[0] * x1) * Wd, -2147483648.0, 2147483647.0)).astype(np.int64)
+        Y = np.rint(np.clip((Y0 + M[3] * x1) * Wd, -2147483648.0, 2147483647.0)).astype(np.int64)
+        sx, sy, ax, ay = np.clip(X >> 5, -32768, 32767), np.clip(Y >> 5, -32768, 32767), X & 31, Y & 31
+        acc = (fetch(sy, sx) * ((32 - ay) * (32 - ax) * 32)[:, None] + fetch(sy, sx + 1) * ((32 - ay) * ax * 32)[:, None]
+               + fetch(sy + 1, sx) * (ay * (32 - ax) * 32)[:, None] + fetch(sy + 1, sx + 1) * (ay * ax * 32)[:, None])
+        out[y] = np.clip((acc + (1 << 14)) >> 15, 0, 255)
+    return out if src.ndim == 3 else out[..., 0]

@@ -1,6 +1,6 @@
 """Raw-head error vs the fp32 oracle and conv-stack time at 3840x2160 for the current GT_SILU_TANH_PX setting (one-MUFU SiLU experiment)."""
 import os, sys
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))   # diagnostic (uses the oracle as the checker, hence under tests/)
 import numpy as np, torch
 import geotrax_b200
 from geotrax_b200 import synth, weights

@@ -633,3 +633,21 @@ def test_nvdec_decodes_lossless_stream_bit_exact_and_feeds_the_path(hw, imgsz):
     finally:
         dec.close()
         eng.close()
+
+
+def test_warp_frames_bit_exact_vs_cv2(full_engine2, full_flight):
+    """the stabilised frame the reference's visualisation renders, `cv2.warpPerspective(frame, H, (w, h))`
+    (/root/reference/geotrax/visualize.py:285-289), on the GPU -- bit for bit, at 3840x2160, with the flight's homographies and a stronger one."""
+    frames, boxes, Hs = full_flight
+    fr = np.stack(frames[1:3])
+    a = np.deg2rad(1.3)
+    strong = np.array([[1.01 * np.cos(a), -1.01 * np.sin(a), 37.4], [1.01 * np.sin(a), 1.01 * np.cos(a), -21.7], [2e-6, -3e-6, 1.0]])
+    H = np.stack([Hs[1], strong])
+    got = full_engine2.warp_frames(fr, H)
+    for i in range(2):
+        want = cv2.warpPerspective(fr[i], H[i], (HW[1], HW[0]))
+        assert np.array_equal(got[i], want), f"frame {i}: {(got[i] != want).any(2).sum()} pixels differ from cv2.warpPerspective"
+    dev = torch.from_numpy(fr).cuda()
+    out = torch.empty_like(dev)
+    full_engine2.warp_frames(dev, H, out)
+    assert np.array_equal(out.cpu().numpy(), got)

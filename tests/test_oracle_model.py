@@ -165,3 +165,15 @@ def test_clahe_restatement_matches_cv2(shape):
     img = np.clip(base.astype(np.int32) + rng.integers(-25, 25, shape), 0, 255).astype(np.uint8)
     img[: shape[0] // 3, : shape[1] // 4] //= 4          # a dark, low-contrast corner: clipping and redistribution actually happen
     assert np.array_equal(prepost.clahe_u8(img), cv2.createCLAHE(clipLimit=2.0, tileGridSize=(8, 8)).apply(img))
+
+
+def test_warp_perspective_restatement_matches_cv2():
+    """oracle/prepost.py:warp_perspective_u8 == cv2.warpPerspective (INTER_LINEAR, constant border), bit for bit, colour and gray."""
+    from oracle import prepost
+    rng = np.random.default_rng(4)
+    for shape in ((135, 250, 3), (270, 480)):
+        src = rng.integers(0, 256, shape, dtype=np.uint8)
+        a, sc = np.deg2rad(rng.uniform(-3, 3)), 1 + rng.uniform(-0.03, 0.03)
+        H = np.array([[sc * np.cos(a), -sc * np.sin(a), rng.uniform(-15, 15)], [sc * np.sin(a), sc * np.cos(a), rng.uniform(-15, 15)],
+                      [rng.uniform(-2e-5, 2e-5), rng.uniform(-2e-5, 2e-5), 1.0]])
+        assert np.array_equal(prepost.warp_perspective_u8(src, H), cv2.warpPerspective(src, H, (shape[1], shape[0])))
