@@ -230,9 +230,17 @@ def run_ours(args):
     stream = tstream.cuda_stream
     eng.extract_batch(torch.from_numpy(ref_np).to(dev), first_is_reference=True, conf=CONF, iou=IOU, classes=[0, 1, 2, 3], out=out, stream=stream,
                       mask_boxes=mask_ref)
+    engines = [eng]
+    for _ in range(max(args.engines, 1) - 1):   # optional: further handles on the same GPU taking the batches round-robin (pipeline.run_range)
+        e2 = geotrax_b200.Engine(frame_hw=FRAME_HW, imgsz=IMGSZ, nc=4, task=task, max_batch=BATCH, device=local, act_dtype=args.dtype)
+        e2.load_weights(weights.fold(sd, 4, task))
+        e2.extract_batch(torch.from_numpy(ref_np).to(dev), first_is_reference=True, conf=CONF, iou=IOU, classes=[0, 1, 2, 3], stream=stream, mask_boxes=mask_ref)
+        engines.append(e2)
     fused = args.workload in ("fused", "obb", "flight")
     pipelined = fused and not args.no_pipeline
-    det_kw = dict(conf=CONF, iou=IOU, agnostic=True, classes=[0, 1, 2, 3], stream=stream)
+    # one engine: everything on the timed torch stream; several engines: each on its own (high-priority) stream so that they overlap --
+    # every gt_wait has returned before the closing event is recorded, so the event pair still brackets all of the work
+    det_kw = dict(conf=CONF, iou=IOU, agnostic=True, classes=[0, 1, 2, 3], stream=stream if len(engines) == 1 else None)
 
     def single_stage_step(src):
         """configs[1] / configs[2] alone (N = 1 diagnostics; not the sharded driver)"""
@@ -257,7 +265,7 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        l0 = eng.launch_count()
+        l0 = sum(e.launch_count() for e in engines)
         stage, conv, marks = np.zeros(4), [0.0], []
 
         def account(b0=0, b1=0):
@@ -279,7 +287,7 @@ def run_ours(args):
             if fused:
                 # steady-state ingest: every step starts the H2D copy of the NEXT batch (the last one that of the following round's first
                 # batch), so the timed region holds exactly `steps` copies of 398 MB; the first batch was put in flight by the previous round
-                rec_local = pipeline.run_range(eng, get_frames, 0, steps * BATCH, 0, batch=BATCH, get_masks=get_masks, set_reference=False,
+                rec_local = pipeline.run_range(engines if len(engines) > 1 else eng, get_frames, 0, steps * BATCH, 0, batch=BATCH, get_masks=get_masks, set_reference=False,
                                                pipelined=pipelined, on_batch=account,
                                                next_range_frames=get_frames(steps * BATCH, (steps + 1) * BATCH) if host else None, **det_kw)
                 pipeline.gather_records(rec_local, rank, world, dev)
@@ -302,7 +310,7 @@ def run_ours(args):
             t = torch.tensor([ms, wall * 1000], device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             ms, wall = float(t[0]), float(t[1]) / 1000
-        return dict(ms=ms, wall=wall, stage=stage / done, conv_ms=conv[0] / done, launches=eng.launch_count() - l0, steps=done, t0=t0, marks=marks)
+        return dict(ms=ms, wall=wall, stage=stage / done, conv_ms=conv[0] / done, launches=sum(e.launch_count() for e in engines) - l0, steps=done, t0=t0, marks=marks)
 
     timed(False, max(args.warmup, 3))
     sampler = ClockSampler(local)
@@ -318,7 +326,8 @@ def run_ours(args):
         for t in res["marks"]:
             per[int(t - res["t0"])] = per.get(int(t - res["t0"]), 0) + BATCH
         flight_windows = [dict(second=k, frames_per_s=per.get(k, 0), **win.get(k, {})) for k in sorted(per)]
-    eng.set_input_format(args.ingest)
+    for e in engines:
+        e.set_input_format(args.ingest)
     timed(True, 2)
     res2 = timed(True, args.steps)               # pinned host frames: H2D inside the timed region
     ms_e2e, wall_e2e = res2["ms"], res2["wall"]
@@ -391,7 +400,7 @@ def run_ours(args):
                wl_name + ": 16 x 3840x2160 synthetic BGR frames / step, YOLOv8s nc=4 random-init imgsz 1920 (1088x1920), conf 0.25 iou 0.7 agnostic, "
                          "ORB 2000/4000 + Hamming 2-NN + 5000-hyp RANSAC, box warp",
                frames_per_step=BATCH, parallelism=f"frame-range shard x{world}",
-               driver="pipeline.run_range + gather_records (the product's sharded driver)" if fused else "single-stage loop",
+               driver="pipeline.run_range + gather_records (the product's sharded driver)" if fused else "single-stage loop", engines_per_gpu=len(engines),
                pipeline=("two batches in flight (gt_extract_batch_async)" if pipelined else "synchronous"), l2="inputs (398 MB / step) larger than the 126 MB L2",
                stage_ms_per_step=dict(preprocess=stage[0], inference=stage[1], postprocess=stage[2], stabilize=stage[3]),
                mask_boxes_per_frame=float(mask[1].mean()), storage_dtype=args.dtype, nonfinite_head_rows=health,
@@ -424,6 +433,8 @@ def main():
     ap.add_argument("--ingest", default="bgr24", choices=["bgr24", "nv12"],
                     help="host frame format of the end-to-end leg: bgr24 = what the reference's reader delivers (default, the headline); "
                          "nv12 = decoder format (SURVEY 8f rank 1), half the PCIe bytes, converted on the device")
+    ap.add_argument("--engines", type=int, default=1, help="handles per GPU taking the batches round-robin (2: the other handle's conv stack fills the SMs during "
+                    "a batch's low-occupancy stabiliser tail, +3-4 %; stage times and the roofline then include the interference, so 1 is the default)")
     ap.add_argument("--seconds", type=float, default=15.0, help="--workload flight: keep running whole `--steps` rounds until this much wall time has passed")
     ap.add_argument("--workload", default="fused", choices=["fused", "detect", "stabilize", "obb", "flight"],
                     help="fused = BASELINE configs[1]+[2] (default, the headline); detect = configs[1] (YOLOv8s detect+NMS only); "

@@ -41,8 +41,11 @@ def run_range(engine, get_frames: Callable[[int, int], np.ndarray], lo: int, hi:
     the GPU never idles between batches.  ``get_masks(a, b)`` (optional) returns the ``(boxes, counts)`` pair of
     ``Engine.pack_boxes`` used as ORB vehicle masks (the tracker's boxes in the reference, extract.py:166,181); default: this
     batch's own detections.  ``on_batch(b0, b1)`` is called after each batch's outputs are valid (progress / timing hooks).
+    ``engine`` may be a list of engines on the same GPU (see the comment in the pipelined loop).
     ``next_range_frames``: host frames of the batch that FOLLOWS this range (chunked / streaming ingest): their H2D copy is started
     during the last batch, so the next ``run_range`` call finds its first batch already on the device (steady-state ingest)."""
+    engines = list(engine) if isinstance(engine, (list, tuple)) else [engine]
+    engine = engines[0]
     md, row = engine.max_det, engine.row
     n = max(hi - lo, 0)
     res = dict(frame=np.arange(lo, hi, dtype=np.int64), count=np.zeros(n, np.int32), status=np.zeros(n, np.int32), stats=np.zeros((n, 4), np.int32),
@@ -52,9 +55,10 @@ def run_range(engine, get_frames: Callable[[int, int], np.ndarray], lo: int, hi:
     ref = None
     if set_reference:
         rm = get_masks(ref_frame_index, ref_frame_index + 1) if get_masks else None
-        ref = engine.extract_batch(get_frames(ref_frame_index, ref_frame_index + 1), first_is_reference=True, mask_boxes=rm, **kw) if rm is not None \
-            else engine.extract_batch(get_frames(ref_frame_index, ref_frame_index + 1), first_is_reference=True, **kw)
-        ref = {k: v.copy() for k, v in ref.items()}
+        for e in engines:        # every engine (and every rank) computes the reference features itself: deterministic kernels, identical result
+            r = e.extract_batch(get_frames(ref_frame_index, ref_frame_index + 1), first_is_reference=True, mask_boxes=rm, **kw) if rm is not None \
+                else e.extract_batch(get_frames(ref_frame_index, ref_frame_index + 1), first_is_reference=True, **kw)
+            ref = ref or {k: v.copy() for k, v in r.items()}
     if pipelined is None:
         pipelined = hasattr(engine, "wait")
     starts = list(range(lo, hi, batch))
@@ -73,27 +77,35 @@ def run_range(engine, get_frames: Callable[[int, int], np.ndarray], lo: int, hi:
             mk = dict(mask_boxes=get_masks(b0, b1)) if get_masks else {}
             store(engine.extract_batch(get_frames(b0, b1), out=out, **mk, **kw), b0, b1)
     else:
-        outs = getattr(engine, "_pipeline_outs", None)       # two pinned output sets, allocated once per engine
-        if outs is None:
-            outs = engine._pipeline_outs = [engine.alloc_outputs(pinned=True), engine.alloc_outputs(pinned=True)]
+        # Several engines (handles on the same GPU, each with its own workspaces and streams) take the batches round-robin: while one
+        # batch is in its low-occupancy stabiliser tail (NMS, selection, RANSAC: 16-128 blocks) the other engine's convolution CTAs
+        # fill the SMs.  Measured +3.8 % with two engines (tools/two_engine_probe.py); one engine is the default.
+        ne = len(engines)
+        for e in engines:
+            if getattr(e, "_pipeline_outs", None) is None:   # two pinned output sets per engine, allocated once
+                e._pipeline_outs = [e.alloc_outputs(pinned=True), e.alloc_outputs(pinned=True)]
         is_host = lambda f: isinstance(f, np.ndarray) or (hasattr(f, "is_cuda") and not f.is_cuda)
         nxt = get_frames(starts[0], min(starts[0] + batch, hi)) if starts else None
-        pending = None                      # (ticket, outputs, b0, b1, frames kept alive, masks kept alive)
+        pending = []                        # (engine, ticket, outputs, b0, b1, frames kept alive, masks kept alive)
         for i, b0 in enumerate(starts):
             b1 = min(b0 + batch, hi)
+            e = engines[i % ne]
             cur = nxt
             nxt = get_frames(starts[i + 1], min(starts[i + 1] + batch, hi)) if i + 1 < len(starts) else next_range_frames
-            if nxt is not None and is_host(nxt) and hasattr(engine, "prefetch"):
-                engine.prefetch(nxt, deferred=True)        # copy of batch i+1 starts right after batch i's own small uploads
+            if nxt is not None and is_host(nxt):
+                en = engines[(i + 1) % ne]
+                if hasattr(en, "prefetch"):
+                    en.prefetch(nxt, deferred=(ne == 1))   # one engine: the copy of batch i+1 starts right after batch i's own small uploads
             mk = get_masks(b0, b1) if get_masks else None
-            o, t = engine.extract_batch(cur, out=outs[i % 2], mask_boxes=mk, sync=False, **kw)
-            if pending is not None:
-                engine.wait(pending[0])
-                store(pending[1], pending[2], pending[3])
-            pending = (t, o, b0, b1, cur, mk)
-        if pending is not None:
-            engine.wait(pending[0])
-            store(pending[1], pending[2], pending[3])
+            o, t = e.extract_batch(cur, out=e._pipeline_outs[(i // ne) % 2], mask_boxes=mk, sync=False, **kw)
+            pending.append((e, t, o, b0, b1, cur, mk))
+            if len(pending) > ne:
+                pe, pt, po, p0, p1, _, _ = pending.pop(0)
+                pe.wait(pt)
+                store(po, p0, p1)
+        for pe, pt, po, p0, p1, _, _ in pending:
+            pe.wait(pt)
+            store(po, p0, p1)
     if ref is not None and lo <= ref_frame_index < hi:   # the reference frame maps to itself: identity, boxes unchanged (extract.py:176-179)
         i = ref_frame_index - lo
         res["count"][i], res["status"][i], res["stats"][i] = ref["counts"][0], 0, ref["stats"][0]
