@@ -66,6 +66,7 @@ struct gt_engine {
   cudaEvent_t ev_aux_a = nullptr, ev_aux_b = nullptr;
   cudaEvent_t ev_pre = nullptr, ev_front = nullptr;
   int overlap = 2;                      // GT_OVERLAP: 2 ORB front on the aux stream beside decode + NMS; 3 as 2, but the image pyramid already beside the conv stack (fills the tails between layers); 1 the whole front beside the detector (no gain: the conv CTAs own the SMs); 0 serial
+  int mask_sparse = 1;                  // GT_MASK_SPARSE=0: dense mask pyramid (7 full-plane launches) instead of the box-driven sparse one
   long long silu_tanh_px = 1;           // GT_SILU_TANH_PX: layers with at least this many output pixels per image use the one-MUFU SiLU (default 1 = every SiLU layer: measured raw-head error unchanged at 5.8e-3, conv stack -3 %; 0 = none)
   int front_split = 0;                  // GT_FRONT_SPLIT=1: FAST on level 0 runs beside the seven pyramid launches (two aux streams) -- measured neutral (5.013 vs 5.020 ms / step), off by default
   int conv_smem_kb = 227;               // dynamic smem budget of the conv kernels (200 with GT_OVERLAP=1 to leave room for ORB blocks); GT_CONV_SMEM_KB

@@ -30,9 +30,8 @@ __device__ const signed char d_pattern[256][4] = {
 __global__ void mask_rects_kernel(uint8_t* __restrict__ mask, size_t slab, const float* __restrict__ boxes, const int* __restrict__ nboxes,
                                   int max_det, int slot0, int w, int h, float margin, float ratio) {
   const int slot = slot0 + blockIdx.y;
-  const int n = nboxes[slot];
-  const int i = blockIdx.x;
-  if (i >= n) return;
+  const int n = min(nboxes[slot], max_det);
+  for (int i = blockIdx.x; i < n; i += gridDim.x) {
   const float* b = boxes + ((size_t)slot * max_det + i) * 4;
   const double gw = (double)b[2] * (1.0 + (double)margin), gh = (double)b[3] * (1.0 + (double)margin);
   int x0 = (int)floor(((double)b[0] - gw / 2) * (double)ratio), y0 = (int)floor(((double)b[1] - gh / 2) * (double)ratio);
@@ -42,6 +41,55 @@ __global__ void mask_rects_kernel(uint8_t* __restrict__ mask, size_t slab, const
   const int rw = x1 - x0;
   for (int y = y0 + (int)(threadIdx.x / 32); y < y1; y += blockDim.x / 32)
     for (int x = threadIdx.x % 32; x < rw; x += 32) m[(size_t)y * w + x0 + x] = 0;
+  }
+}
+
+// ---- sparse mask pyramid: a level of the vehicle-mask pyramid recomputed only around the boxes ---------------------------------------
+// The mask is 255 everywhere except inside the (grown) vehicle rectangles -- ~3 % of the pixels for the 132 boxes of a frame -- and a
+// pyramid pixel whose 2 x 2 source pixels are all 255 is 255 exactly ((255*256*256 + 32768) >> 16).  So every level is preset to 255 and
+// only the pixels whose source footprint can reach a rectangle are computed, with pyr_resize_kernel<true>'s arithmetic (chained
+// INTER_LINEAR_EXACT + threshold): bit-identical to the dense chain, ~30x less work.  Levels are separate launches because a pixel near
+// two boxes needs the finished previous level of both (overlapping regions write equal values); a block walks boxes b, b + gridDim.x, ...
+// (A single launch with one block per frame and __syncthreads between levels was measured at 0.9-2.5 ms: one block has too little
+// memory-level parallelism for the dependent table -> pixel loads; the seven small launches take ~250 us beside the FAST kernel.)
+struct MaskLevels { int w[GT_ORB_LEVELS], h[GT_ORB_LEVELS]; unsigned long long off[GT_ORB_LEVELS]; double sx[GT_ORB_LEVELS], sy[GT_ORB_LEVELS]; };
+
+__global__ void __launch_bounds__(128) mask_pyr_sparse_kernel(uint8_t* __restrict__ mask, size_t slab, const float* __restrict__ boxes, const int* __restrict__ nboxes,
+                                                              int max_det, int slot0, float margin, float ratio, const MaskLevels ml, int level,
+                                                              const int* __restrict__ xofs, const int* __restrict__ xc1, const int* __restrict__ yofs,
+                                                              const int* __restrict__ yc1) {
+  const int slot = slot0 + blockIdx.y;
+  const int nb = min(nboxes[slot], max_det);
+  uint8_t* base = mask + (size_t)slot * slab;
+  const uint8_t* src = base + ml.off[level - 1];
+  uint8_t* dst = base + ml.off[level];
+  const int sw = ml.w[level - 1], sh = ml.h[level - 1], dw = ml.w[level];
+  for (int bi = blockIdx.x; bi < nb; bi += gridDim.x) {
+    const float* b = boxes + ((size_t)slot * max_det + bi) * 4;
+    // level-0 rectangle exactly as mask_rects_kernel draws it, then the range of each further level that can see it (conservative by
+    // one pixel: extra pixels are computed with the same arithmetic, hence exact)
+    const double gw = (double)b[2] * (1.0 + (double)margin), gh = (double)b[3] * (1.0 + (double)margin);
+    int x0 = (int)floor(((double)b[0] - gw / 2) * (double)ratio), y0 = (int)floor(((double)b[1] - gh / 2) * (double)ratio);
+    int x1 = (int)ceil(((double)b[0] + gw / 2) * (double)ratio) - 1, y1 = (int)ceil(((double)b[1] + gh / 2) * (double)ratio) - 1;   // inclusive
+    x0 = max(x0, 0); y0 = max(y0, 0); x1 = min(x1, ml.w[0] - 1); y1 = min(y1, ml.h[0] - 1);
+    if (x1 < x0 || y1 < y0) continue;
+    for (int l = 1; l <= level; ++l) {
+      x0 = max((int)floor(((double)x0 - 1.5) / ml.sx[l] - 0.5) - 1, 0); x1 = min((int)ceil(((double)x1 + 1.5) / ml.sx[l]) + 1, ml.w[l] - 1);
+      y0 = max((int)floor(((double)y0 - 1.5) / ml.sy[l] - 0.5) - 1, 0); y1 = min((int)ceil(((double)y1 + 1.5) / ml.sy[l]) + 1, ml.h[l] - 1);
+    }
+    const int rw = x1 - x0 + 1, n = rw * (y1 - y0 + 1);
+    for (int i = threadIdx.x; i < n; i += 128) {
+      const int yy = i / rw, y = y0 + yy, x = x0 + i - yy * rw;
+      const int xo = __ldg(xofs + x), c1 = __ldg(xc1 + x), c0 = 256 - c1, yo = __ldg(yofs + y), cy1 = __ldg(yc1 + y), cy0 = 256 - cy1;
+      const uint8_t* r0 = src + (size_t)yo * sw;
+      const uint8_t* r1 = src + (size_t)min(yo + 1, sh - 1) * sw;
+      const int xb = min(xo + 1, sw - 1);
+      const int h0 = (int)r0[xo] * c0 + (int)r0[xb] * c1, h1 = (int)r1[xo] * c0 + (int)r1[xb] * c1;
+      int v = (h0 * cy0 + h1 * cy1 + 32768) >> 16;
+      if (v <= 254) v = 0;
+      dst[(size_t)y * dw + x] = (uint8_t)v;
+    }
+  }
 }
 
 // ---- one pyramid level from the previous one: cv2.resize(INTER_LINEAR_EXACT) in Q8.8 x Q8.8, (v + 2^15) >> 16 -------------
@@ -1035,16 +1083,38 @@ int orb_front_split(gt_engine* e, int slot0, int nslots, cudaStream_t st, cudaSt
 int orb_mask(gt_engine* e, int slot0, int nslots, bool build_mask, cudaStream_t st) {
   const size_t slab = e->pyr_bytes;
   const OrbLevel& L0 = e->lv[0];
+  const dim3 gbox((unsigned)std::min(e->cfg.max_det, 160), (unsigned)nslots);   // blocks walk the boxes
+  if (build_mask && e->mask_sparse) {
+    // box-derived masks: every level preset to 255, rectangles drawn at level 0, then levels 1..7 recomputed around the boxes only
+    GT_CUDA(e, cudaMemsetAsync(e->pyr_mask + (size_t)slot0 * slab, 255, (size_t)nslots * slab, st));
+    if (e->cfg.mask_use) {
+      mask_rects_kernel<<<gbox, 128, 0, st>>>(e->pyr_mask, slab, e->boxes_dev, e->nboxes_dev, e->cfg.max_det, slot0, L0.w, L0.h,
+                                              e->cfg.mask_margin_ratio, e->cfg.downsample_ratio);
+      e->launches++;
+      MaskLevels ml;
+      for (int l = 0; l < GT_ORB_LEVELS; ++l) {
+        ml.w[l] = e->lv[l].w; ml.h[l] = e->lv[l].h; ml.off[l] = e->lv[l].off;
+        ml.sx[l] = l ? (double)e->lv[l - 1].w / e->lv[l].w : 1.0; ml.sy[l] = l ? (double)e->lv[l - 1].h / e->lv[l].h : 1.0;
+      }
+      for (int l = 1; l < GT_ORB_LEVELS; ++l) {
+        int* const* t = e->rs_tab[l];
+        mask_pyr_sparse_kernel<<<gbox, 128, 0, st>>>(e->pyr_mask, slab, e->boxes_dev, e->nboxes_dev, e->cfg.max_det, slot0, e->cfg.mask_margin_ratio,
+                                                     e->cfg.downsample_ratio, ml, l, t[0], t[1], t[2], t[3]);
+        e->launches++;
+      }
+    }
+    GT_CUDA(e, cudaGetLastError());
+    return GT_OK;
+  }
   if (build_mask) {
     GT_CUDA(e, cudaMemset2DAsync(e->pyr_mask + (size_t)slot0 * slab, slab, 255, (size_t)L0.w * L0.h, nslots, st));
     if (e->cfg.mask_use) {
-      dim3 g((unsigned)e->cfg.max_det, (unsigned)nslots);
-      mask_rects_kernel<<<g, 128, 0, st>>>(e->pyr_mask, slab, e->boxes_dev, e->nboxes_dev, e->cfg.max_det, slot0, L0.w, L0.h,
-                                           e->cfg.mask_margin_ratio, e->cfg.downsample_ratio);
+      mask_rects_kernel<<<gbox, 128, 0, st>>>(e->pyr_mask, slab, e->boxes_dev, e->nboxes_dev, e->cfg.max_det, slot0, L0.w, L0.h,
+                                              e->cfg.mask_margin_ratio, e->cfg.downsample_ratio);
       e->launches++;
     }
   }
-  GT_TRY(pyramid_run<true>(e, e->pyr_mask, slot0, nslots, st));
+  GT_TRY(pyramid_run<true>(e, e->pyr_mask, slot0, nslots, st));   // caller-supplied level-0 masks (gt_orb_detect) / GT_MASK_SPARSE=0: the dense chain
   GT_CUDA(e, cudaGetLastError());
   return GT_OK;
 }

@@ -651,3 +651,27 @@ def test_warp_frames_bit_exact_vs_cv2(full_engine2, full_flight):
     out = torch.empty_like(dev)
     full_engine2.warp_frames(dev, H, out)
     assert np.array_equal(out.cpu().numpy(), got)
+
+
+@pytest.mark.parametrize("nbox", [132, 1000])
+def test_sparse_mask_pyramid_equals_dense_cv2_chain(full_engine2, full_flight, nbox):
+    """The vehicle-mask pyramid is recomputed only around the boxes (mask_pyr_sparse_kernel); every level must equal OpenCV ORB's dense
+    chain -- resize(INTER_LINEAR_EXACT) of the previous level, then threshold(254, TOZERO) -- bit for bit, including overlapping and
+    border-clipped boxes (1,000 random boxes)."""
+    from geotrax_b200 import synth
+    from oracle.stabilo_cv import build_mask
+    eng = full_engine2
+    frames, boxes, _ = full_flight
+    bx = boxes[1] if nbox == 132 else synth.make_boxes(nbox, HW[0], HW[1], np.random.default_rng(3))
+    if nbox != 132:
+        bx[:20, 0] = np.linspace(5, HW[1] - 5, 20); bx[:20, 1] = 8            # boxes cut by the frame border
+    eng.preprocess(np.stack([frames[1]]))
+    eng.set_reference(0, bx)
+    info = eng.orb_level_info()
+    prev = build_mask(bx, 0.15, 0.5, info[0][0], info[0][1])
+    for lvl, (w, h, _, _) in enumerate(info):
+        _, msk = eng.pyramid_level(1, 0, lvl)
+        if lvl > 0:
+            prev = cv2.resize(prev, (w, h), interpolation=cv2.INTER_LINEAR_EXACT)
+            prev[prev <= 254] = 0
+        assert np.array_equal(msk, prev), f"mask level {lvl} differs from the dense chain in {(msk != prev).sum()} pixels"
