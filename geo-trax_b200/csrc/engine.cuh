@@ -155,9 +155,6 @@ struct gt_engine {
   bool have_ref = false;
   OrbLevel* lv_dev = nullptr;                       // device copy of lv[]
   int* rs_tab[GT_ORB_LEVELS][4] = {};               // per-level resize tables: xofs, xc1, yofs, yc1
-  void* pyr_blocks = nullptr;                       // PyrBlock[pyr_nblocks]: per-tile regions of the single-launch chained pyramid (orb.cu)
-  int pyr_nblocks = 0, pyr_buf_bytes = 0;
-  bool pyr_chain = false;                           // GT_PYR_CHAIN=1: single-launch chained pyramid kernel (measured slower than the 7 per-level launches: 255 vs 160 us / plane / step; kept as an option)
   // matching / RANSAC
   int* match_idx = nullptr;                         // [B][GT_MAX_KP][2]
   int* match_dist = nullptr;                        // [B][GT_MAX_KP][2]

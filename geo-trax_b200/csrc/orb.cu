@@ -157,71 +157,6 @@ __global__ void __launch_bounds__(128) pyr_resize_kernel(uint8_t* __restrict__ p
   }
 }
 
-// ---- the whole chained pyramid (levels 1..7 from level 0) in ONE launch ------------------------------------------------------------
-// The 7 dependent pyr_resize launches per plane were latency bound (14 launches = 320 us per 16-frame step for 100 MB of traffic).
-// Here a block owns one tile of the LAST level and everything below it: it loads the level-0 region that tile depends on (a few pixels
-// of halo per level, regions precomputed on the host from the resize tables: PyrBlock), then produces level 1, 2, ... 7 of that region
-// in shared memory, ping-pong, with exactly pyr_resize_kernel's arithmetic (chained INTER_LINEAR_EXACT, Q8.8 x Q8.8, mask threshold per
-// level), and writes to global memory only the part of each level it OWNS -- the owned ranges partition every level exactly.
-struct PyrBlock { short cx0[GT_ORB_LEVELS], cx1[GT_ORB_LEVELS], cy0[GT_ORB_LEVELS], cy1[GT_ORB_LEVELS];     // computed region per level [lo, hi)
-                  short ox0[GT_ORB_LEVELS], ox1[GT_ORB_LEVELS], oy0[GT_ORB_LEVELS], oy1[GT_ORB_LEVELS]; };  // owned region per level
-struct PyrGeom {
-  int w[GT_ORB_LEVELS], h[GT_ORB_LEVELS];
-  unsigned long long off[GT_ORB_LEVELS];
-  const int* xofs[GT_ORB_LEVELS]; const int* xc1[GT_ORB_LEVELS]; const int* yofs[GT_ORB_LEVELS]; const int* yc1[GT_ORB_LEVELS];
-  int buf_bytes;
-};
-
-template <bool MASK>
-__global__ void __launch_bounds__(256) pyr_chain_kernel(uint8_t* __restrict__ plane, size_t slab, int slot0, const PyrBlock* __restrict__ blocks,
-                                                        const PyrGeom g) {
-  extern __shared__ __align__(16) uint8_t s_pyr[];
-  __shared__ PyrBlock B;
-  if (threadIdx.x < sizeof(PyrBlock) / 4) reinterpret_cast<int*>(&B)[threadIdx.x] = reinterpret_cast<const int*>(blocks + blockIdx.x)[threadIdx.x];
-  __syncthreads();
-  uint8_t* cur = s_pyr;
-  uint8_t* nxt = s_pyr + g.buf_bytes;
-  uint8_t* base = plane + (size_t)(slot0 + blockIdx.y) * slab;
-  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-  int pw = B.cx1[0] - B.cx0[0];
-  {
-    const int ph = B.cy1[0] - B.cy0[0];
-    const uint8_t* src = base + g.off[0] + (size_t)B.cy0[0] * g.w[0] + B.cx0[0];
-    for (int y = ty; y < ph; y += 8)
-      for (int x = tx; x < pw; x += 32) cur[y * pw + x] = src[(size_t)y * g.w[0] + x];
-  }
-  __syncthreads();
-#pragma unroll 1
-  for (int l = 1; l < GT_ORB_LEVELS; ++l) {
-    const int px0 = B.cx0[l - 1], py0 = B.cy0[l - 1], sw = g.w[l - 1], sh = g.h[l - 1];
-    const int x0 = B.cx0[l], y0 = B.cy0[l], dw = B.cx1[l] - x0, dh = B.cy1[l] - y0;
-    const int ox0 = B.ox0[l], ox1 = B.ox1[l], oy0 = B.oy0[l], oy1 = B.oy1[l];
-    uint8_t* dst = base + g.off[l];
-    const int dW = g.w[l];
-    for (int dy = ty; dy < dh; dy += 8) {
-      const int Y = y0 + dy;
-      const int yo = __ldg(g.yofs[l] + Y), cy1 = __ldg(g.yc1[l] + Y), cy0 = 256 - cy1;
-      const uint8_t* r0 = cur + (yo - py0) * pw;
-      const uint8_t* r1 = cur + (min(yo + 1, sh - 1) - py0) * pw;
-      const bool own_y = Y >= oy0 && Y < oy1;
-      for (int dx = tx; dx < dw; dx += 32) {
-        const int X = x0 + dx;
-        const int xo = __ldg(g.xofs[l] + X), c1 = __ldg(g.xc1[l] + X), c0 = 256 - c1;
-        const int a = xo - px0, b = min(xo + 1, sw - 1) - px0;
-        const int h0 = (int)r0[a] * c0 + (int)r0[b] * c1;
-        const int h1 = (int)r1[a] * c0 + (int)r1[b] * c1;
-        int v = (h0 * cy0 + h1 * cy1 + 32768) >> 16;
-        if (MASK && v <= 254) v = 0;
-        nxt[dy * dw + dx] = (uint8_t)v;
-        if (own_y && X >= ox0 && X < ox1) dst[(size_t)Y * dW + X] = (uint8_t)v;
-      }
-    }
-    __syncthreads();
-    uint8_t* t = cur; cur = nxt; nxt = t;
-    pw = dw;
-  }
-}
-
 // ---- FAST-9/16 score + 3x3 non-max suppression + border filter -> candidate list --------------------------------------------
 // One launch covers all pyramid levels (blockIdx.x walks the 64 x 64 tiles of every level's candidate region
 // [kEdge, w - kEdge) x [kEdge, h - kEdge); blockIdx.y = frame slot).  Per tile:
@@ -939,12 +874,10 @@ int orb_build(gt_engine* e) {
   GT_CUDA(e, cudaMemset(e->pyr_mask, 255, (size_t)S * off));
   GT_TRY(e->dev_alloc((void**)&e->lv_dev, sizeof(OrbLevel) * GT_ORB_LEVELS));
   GT_CUDA(e, cudaMemcpy(e->lv_dev, e->lv, sizeof(OrbLevel) * GT_ORB_LEVELS, cudaMemcpyHostToDevice));
-  std::vector<int> hxo[GT_ORB_LEVELS], hyo[GT_ORB_LEVELS];   // host copies of the source-offset tables (pyramid chain planning below)
   for (int l = 1; l < GT_ORB_LEVELS; ++l) {
     std::vector<int> xo, xc, yo, yc;
     resize_tables(e->lv[l - 1].w, e->lv[l].w, xo, xc);
     resize_tables(e->lv[l - 1].h, e->lv[l].h, yo, yc);
-    hxo[l] = xo; hyo[l] = yo;
     while (xo.size() % 4) { xo.push_back(xo.back()); xc.push_back(xc.back()); }   // the resize kernel loads four x entries at once
     const std::vector<int>* src[4] = {&xo, &xc, &yo, &yc};
     for (int k = 0; k < 4; ++k) {
@@ -952,72 +885,17 @@ int orb_build(gt_engine* e) {
       GT_CUDA(e, cudaMemcpy(e->rs_tab[l][k], src[k]->data(), src[k]->size() * 4, cudaMemcpyHostToDevice));
     }
   }
-  // ---- plan of the single-launch chained pyramid (pyr_chain_kernel): per tile of the last level, the computed and owned range of every level
-  {
-    const int T = GT_ORB_LEVELS - 1;
-    struct Range { int lo, hi; };
-    auto plan_axis = [&](const std::vector<int>* ofs, auto size_of, int tile, std::vector<std::vector<Range>>& comp, std::vector<std::vector<Range>>& own) {
-      const int nT = size_of(T), nb = ceil_div(nT, tile);
-      comp.assign(nb, std::vector<Range>(GT_ORB_LEVELS));
-      own.assign(nb, std::vector<Range>(GT_ORB_LEVELS));
-      for (int b = 0; b < nb; ++b) own[b][T] = comp[b][T] = {b * tile, std::min((b + 1) * tile, nT)};
-      for (int l = T - 1; l >= 0; --l) {
-        const int n = size_of(l);
-        for (int b = 0; b < nb; ++b) {
-          own[b][l].lo = b == 0 ? 0 : ofs[l + 1][own[b][l + 1].lo];
-          own[b][l].hi = b == nb - 1 ? n : ofs[l + 1][own[b + 1][l + 1].lo];
-        }
-        for (int b = 0; b < nb; ++b) {
-          const int lo = ofs[l + 1][comp[b][l + 1].lo], hi = std::min(ofs[l + 1][comp[b][l + 1].hi - 1] + 2, n);
-          comp[b][l] = {std::min(lo, own[b][l].lo), std::max(hi, own[b][l].hi)};
-        }
-      }
-    };
-    std::vector<std::vector<Range>> cx, ox, cy, oy;
-    plan_axis(hxo, [&](int l) { return e->lv[l].w; }, 64, cx, ox);
-    plan_axis(hyo, [&](int l) { return e->lv[l].h; }, 32, cy, oy);
-    std::vector<PyrBlock> blocks;
-    size_t buf = 0;
-    for (size_t by = 0; by < cy.size(); ++by)
-      for (size_t bx = 0; bx < cx.size(); ++bx) {
-        PyrBlock pb;
-        for (int l = 0; l < GT_ORB_LEVELS; ++l) {
-          pb.cx0[l] = (short)cx[bx][l].lo; pb.cx1[l] = (short)cx[bx][l].hi; pb.cy0[l] = (short)cy[by][l].lo; pb.cy1[l] = (short)cy[by][l].hi;
-          pb.ox0[l] = (short)ox[bx][l].lo; pb.ox1[l] = (short)ox[bx][l].hi; pb.oy0[l] = (short)oy[by][l].lo; pb.oy1[l] = (short)oy[by][l].hi;
-          buf = std::max(buf, (size_t)(cx[bx][l].hi - cx[bx][l].lo) * (size_t)(cy[by][l].hi - cy[by][l].lo));
-        }
-        blocks.push_back(pb);
-      }
-    e->pyr_nblocks = (int)blocks.size();
-    e->pyr_buf_bytes = (int)((buf + 15) & ~(size_t)15);
-    e->pyr_chain = 2 * e->pyr_buf_bytes <= 200 * 1024 && e->lv[0].w < 32768 && e->lv[0].h < 32768 && getenv("GT_PYR_CHAIN") && atoi(getenv("GT_PYR_CHAIN")) != 0;
-    GT_TRY(e->dev_alloc((void**)&e->pyr_blocks, blocks.size() * sizeof(PyrBlock)));
-    GT_CUDA(e, cudaMemcpy(e->pyr_blocks, blocks.data(), blocks.size() * sizeof(PyrBlock), cudaMemcpyHostToDevice));
-    if (e->pyr_chain) {
-      GT_CUDA(e, cudaFuncSetAttribute(pyr_chain_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * e->pyr_buf_bytes));
-      GT_CUDA(e, cudaFuncSetAttribute(pyr_chain_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * e->pyr_buf_bytes));
-    }
-  }
   GT_CUDA(e, cudaFuncSetAttribute(orb_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSelCap * 4));
   GT_CUDA(e, cudaFuncSetAttribute(orb_describe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kDescWarps * ((kDescSmemPerWarp + 15) & ~15)));
   return GT_OK;
 }
 
-// levels 1..7 of one plane (image or mask) for slots [slot0, slot0 + nslots): one chained launch, or the per-level kernels as fallback
+// levels 1..7 of one plane (image or mask) for slots [slot0, slot0 + nslots): seven chained launches.  (A single-launch form -- a block owns
+// a tile of the last level and the halo regions of every level below it in shared memory -- was bit-exact but slower, 255 vs 160 us per
+// plane: 1.4x the pixels with byte-granular shared-memory traffic; profiles/round2_summary.md section 2.)
 template <bool MASK>
 static int pyramid_run(gt_engine* e, uint8_t* plane, int slot0, int nslots, cudaStream_t st) {
   const size_t slab = e->pyr_bytes;
-  if (e->pyr_chain) {
-    PyrGeom g;
-    for (int l = 0; l < GT_ORB_LEVELS; ++l) {
-      g.w[l] = e->lv[l].w; g.h[l] = e->lv[l].h; g.off[l] = e->lv[l].off;
-      g.xofs[l] = e->rs_tab[l][0]; g.xc1[l] = e->rs_tab[l][1]; g.yofs[l] = e->rs_tab[l][2]; g.yc1[l] = e->rs_tab[l][3];
-    }
-    g.buf_bytes = e->pyr_buf_bytes;
-    pyr_chain_kernel<MASK><<<dim3((unsigned)e->pyr_nblocks, (unsigned)nslots), 256, 2 * e->pyr_buf_bytes, st>>>(plane, slab, slot0, (const PyrBlock*)e->pyr_blocks, g);
-    e->launches++;
-    return GT_OK;
-  }
   for (int l = 1; l < GT_ORB_LEVELS; ++l) {
     const OrbLevel& S = e->lv[l - 1];
     const OrbLevel& D = e->lv[l];
