@@ -7,7 +7,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libgeotrax_b200.so")
-SOURCES = ["api.cu", "conv_tc.cu", "conv_sw.cu", "detector.cu", "clahe.cu", "orb.cu", "match_ransac.cu", "nvdec.cu", "warp.cu"]
+SOURCES = ["api.cu", "conv_tc.cu", "conv_sw.cu", "detector.cu", "clahe.cu", "orb.cu", "match_ransac.cu", "match_tc.cu", "nvdec.cu", "warp.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xptxas", "-v",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-O3"]
 

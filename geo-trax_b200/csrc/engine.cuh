@@ -66,6 +66,7 @@ struct gt_engine {
   cudaEvent_t ev_aux_a = nullptr, ev_aux_b = nullptr;
   cudaEvent_t ev_pre = nullptr, ev_front = nullptr;
   int overlap = 2;                      // GT_OVERLAP: 2 ORB front on the aux stream beside decode + NMS; 3 as 2, but the image pyramid already beside the conv stack (fills the tails between layers); 1 the whole front beside the detector (no gain: the conv CTAs own the SMs); 0 serial
+  int match_mode = 2;                   // GT_MATCH: 2 Hamming 2-NN as E4M3 tcgen05 GEMM (match_tc.cu), 1 the same with fp16 operands, 0 POPC kernel
   int mask_sparse = 1;                  // GT_MASK_SPARSE=0: dense mask pyramid (7 full-plane launches) instead of the box-driven sparse one
   long long silu_tanh_px = 1;           // GT_SILU_TANH_PX: layers with at least this many output pixels per image use the one-MUFU SiLU (default 1 = every SiLU layer: measured raw-head error unchanged at 5.8e-3, conv stack -3 %; 0 = none)
   int front_split = 0;                  // GT_FRONT_SPLIT=1: FAST on level 0 runs beside the seven pyramid launches (two aux streams) -- measured neutral (5.013 vs 5.020 ms / step), off by default
@@ -156,6 +157,8 @@ struct gt_engine {
   OrbLevel* lv_dev = nullptr;                       // device copy of lv[]
   int* rs_tab[GT_ORB_LEVELS][4] = {};               // per-level resize tables: xofs, xc1, yofs, yc1
   // matching / RANSAC
+  uint8_t* desc_x = nullptr;                        // [B+1][64 groups][k-blocks][128][128 B] descriptors expanded to MMA operand tiles (match_tc.cu)
+  float* desc_c = nullptr;                          // [B+1][GT_MAX_KP] popc * 8192 + row (float), huge beyond the count
   int* match_idx = nullptr;                         // [B][GT_MAX_KP][2]
   int* match_dist = nullptr;                        // [B][GT_MAX_KP][2]
   float* pairs = nullptr;                           // [B][GT_MAX_KP][4] cur x,y, ref x,y (working res)
@@ -220,6 +223,9 @@ int stab_build(gt_engine* e);
 int stab_match_and_fit(gt_engine* e, int B, cudaStream_t st);
 int match_run(gt_engine* e, const uint8_t* q, const int* nq_dev, int nq_max, const uint8_t* t, const int* nt_dev, int nt_max,
               int* out_idx, int* out_dist, int batch, size_t q_stride, size_t out_stride, cudaStream_t st);
+// match_tc.cu
+int match_tc_build(gt_engine* e);
+int match_tc_run(gt_engine* e, int q_slot0, int q_step, int nq_cap, int t_slot0, int t_step, int batch, cudaStream_t st);
 int homography_run(gt_engine* e, const float* pairs, const int* counts, int B, int pair_stride, float thr, int max_iter,
                    double* out_H, int* out_status, int* out_stats, float ratio, bool full_res, const int* kp_count, cudaStream_t st);
 int warp_boxes_run(gt_engine* e, const double* H_dev, const int* status_dev, const float* in, float* out, const int* counts, int B,

@@ -649,12 +649,14 @@ int stab_build(gt_engine* e) {
   GT_TRY(e->dev_alloc((void**)&e->H_stats, (size_t)B * 4 * sizeof(int)));
   GT_TRY(e->dev_alloc((void**)&e->boxes_stab_dev, (size_t)B * e->cfg.max_det * 4 * sizeof(float)));
   GT_CUDA(e, cudaMemset(e->H_status, 0, (size_t)B * sizeof(int)));
-  return GT_OK;
+  return match_tc_build(e);
 }
 
 int match_run(gt_engine* e, const uint8_t* q, const int* nq_dev, int nq_max, const uint8_t* t, const int* nt_dev, int nt_max, int* out_idx,
               int* out_dist, int batch, size_t q_stride, size_t out_stride, cudaStream_t st) {
   (void)nt_max;
+  if (e->match_mode != 0 && q == e->desc_all && t == e->desc_all + (size_t)e->cfg.max_batch * GT_MAX_KP * 32 && out_idx == e->match_idx && batch == 1)
+    return match_tc_run(e, 0, 0, nq_max, e->cfg.max_batch, 0, 1, st);   // gt_match: slot 0 against the reference slot
   dim3 g((unsigned)ceil_div(nq_max, 8 * kQPW), (unsigned)batch);
   // batch > 1: queries advance by q_stride per frame with per-frame counts, the train set is shared (stride 0)
   match_kernel<<<g, 256, 0, st>>>(q, q_stride, nq_dev, batch > 1 ? 1 : 0, t, 0, nt_dev, 0, out_idx, out_dist, out_stride);
@@ -684,7 +686,11 @@ int stab_match_and_fit(gt_engine* e, int B, cudaStream_t st) {
   const size_t dstride = (size_t)GT_MAX_KP * 32, ostride = (size_t)GT_MAX_KP * 2;
   const int nkp_cur = std::min(GT_MAX_KP, e->cfg.max_features + GT_ORB_LEVELS * 64);
   const int nkp_ref = std::min(GT_MAX_KP, (int)(e->cfg.max_features * e->cfg.ref_multiplier) + GT_ORB_LEVELS * 64);
-  if (e->cfg.query_is_current) {
+  if (e->match_mode != 0) {
+    if (e->cfg.query_is_current) GT_TRY(match_tc_run(e, 0, 1, nkp_cur, R, 0, B, st));
+    else GT_TRY(match_tc_run(e, R, 0, nkp_ref, 0, 1, B, st));
+    e->launches -= 1;   // (the common `launches += 2` below counts build_pairs + one matcher launch)
+  } else if (e->cfg.query_is_current) {
     dim3 g((unsigned)ceil_div(nkp_cur, 8 * kQPW), (unsigned)B);
     match_kernel<<<g, 256, 0, st>>>(e->desc_all, dstride, e->kp_count, 1, e->desc_all + (size_t)R * dstride, 0, e->kp_count + R, 0, e->match_idx,
                                     e->match_dist, ostride);

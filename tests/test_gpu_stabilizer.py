@@ -100,6 +100,55 @@ def test_matcher_bit_exact(stab_engine):
     assert np.array_equal(idx, ri)
 
 
+def _engine_with_matcher(mode):
+    import geotrax_b200
+    old = os.environ.get("GT_MATCH")
+    os.environ["GT_MATCH"] = str(mode)
+    try:
+        return geotrax_b200.Engine(frame_hw=(256, 384), imgsz=192, nc=4, max_batch=2, max_det=50, max_features=500)
+    finally:
+        if old is None:
+            os.environ.pop("GT_MATCH")
+        else:
+            os.environ["GT_MATCH"] = old
+
+
+def _bf_knn(query, train):
+    """cv2.BFMatcher(NORM_HAMMING).knnMatch(k=2) as arrays; -1 where the train set has fewer than two rows."""
+    ref = cv2.BFMatcher(cv2.NORM_HAMMING).knnMatch(query, train, k=2)
+    ri = -np.ones((len(query), 2), np.int64); rd = -np.ones((len(query), 2), np.int64)
+    for q, ms in enumerate(ref):
+        for k, m in enumerate(ms):
+            ri[q, k], rd[q, k] = m.trainIdx, int(m.distance)
+    return ri, rd
+
+
+@pytest.mark.parametrize("mode", [2, 1, 0], ids=["e4m3-tcgen05", "f16-tcgen05", "popc"])
+def test_matcher_modes_bit_exact(mode):
+    """Every matcher (GT_MATCH: E4M3 GEMM, fp16 GEMM, POPC kernel) against cv2.BFMatcher on ragged sizes, ties, distance 0 and 256,
+    all-zero descriptors, one-row train sets and the full 8192 x 8192 capacity (csrc/match_tc.cu, match_ransac.cu)."""
+    eng = _engine_with_matcher(mode)
+    try:
+        rng = np.random.default_rng(17)
+        for nq, nt in [(1, 1), (1, 2), (130, 257), (127, 128), (129, 129), (1999, 4000), (2512, 4512), (8192, 8192), (300, 7)]:
+            train = rng.integers(0, 256, (nt, 32), dtype=np.uint8)
+            query = train[rng.integers(0, nt, nq)].copy()
+            query ^= rng.integers(0, 256, query.shape, dtype=np.uint8) & rng.integers(0, 256, query.shape, dtype=np.uint8) & rng.integers(0, 256, query.shape, dtype=np.uint8)
+            if nq > 60:
+                query[:20] = rng.integers(0, 256, (20, 32), dtype=np.uint8)
+                query[20] = 0; query[21] = 255                      # popc 0 and 256
+                query[22] = ~train[min(5, nt - 1)]                    # distance 256 to one train row
+            if nt > 250:
+                train[100] = train[50]; train[200] = train[50]      # exact ties -> lower index must win
+                train[249] = 0; train[17] = 255
+            idx, dist = eng.match(query, train)
+            ri, rd = _bf_knn(query, train)
+            assert np.array_equal(dist, rd), f"distances differ at nq={nq} nt={nt} (mode {mode}): {np.argwhere(dist != rd)[:5].tolist()}"
+            assert np.array_equal(idx, ri), f"indices differ at nq={nq} nt={nt} (mode {mode}): {np.argwhere(idx != ri)[:5].tolist()}"
+    finally:
+        eng.close()
+
+
 def test_find_homography_recovers_ground_truth(stab_engine):
     rng = np.random.default_rng(3)
     from geotrax_b200 import synth
