@@ -239,9 +239,11 @@ struct RingCmp {            // per group: thresholds hi = sat(c + t), lo = sat(c
 __device__ __forceinline__ uint32_t win4(uint32_t w0, uint32_t w1, uint32_t w2, int o) {
   return o < 4 ? __funnelshift_r(w0, w1, 8 * o) : (o == 4 ? w1 : __funnelshift_r(w1, w2, 8 * (o - 4)));
 }
-// per byte: 0xFF where at least two of the four masks are set
+// per byte: set where two ADJACENT compass points (0-4, 4-8, 8-12 or 12-0) are both set.  Nine circularly consecutive ring positions always
+// contain two adjacent compass points, so this is a necessary condition for a 9-arc -- strictly stronger than "any two of four" (which
+// also passes the opposite pairs 0-8 / 4-12) and one instruction shorter: (a&b)|(b&c)|(c&d)|(d&a) = (a|c)&(b|d).
 __device__ __forceinline__ uint32_t two_of_four(uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
-  return (a & b) | (c & d) | ((a | b) & (c | d));
+  return (a | c) & (b | d);
 }
 // per byte: 0xFF where some 9 circularly consecutive masks of m[0..15] are all set
 __device__ __forceinline__ uint32_t arc9(const uint32_t* m) {
