@@ -82,6 +82,7 @@ SYMBOLS = {
     "gt_orb_get_candidates": (_i, [_H, _i, _i, _i, _i, _P, _P, _ip]),
     "gt_orb_detect": (_i, [_H, _P, _P, _i, _i, _P]),
     "gt_match": (_i, [_H, _P, _i, _P, _i, _P, _P, _P]),
+    "gt_match_l2": (_i, [_H, _P, _i, _P, _i, _i, _P, _P, _P]),
     "gt_find_homography": (_i, [_H, _P, _P, _i, _f, _i, _P, _ip, _P]),
     "gt_extract_batch": (_i, [_H, _P, _i, _i, _f, _f, _i, _u, _P, _P, _i, _P, _P, _P, _P, _P, _P, _P]),
     "gt_extract_batch_async": (_i, [_H, _P, _i, _i, _f, _f, _i, _u, _P, _P, _i, _P, _P, _P, _P, _P, _P, _P, _P]),

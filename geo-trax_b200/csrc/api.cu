@@ -82,6 +82,7 @@ int gt_create(const gt_config* cfg, int device, gt_handle* out) {
   if (const char* fs = getenv("GT_FRONT_SPLIT")) e->front_split = atoi(fs);
   if (const char* sp = getenv("GT_SILU_TANH_PX")) e->silu_tanh_px = atoll(sp);
   if (const char* ms = getenv("GT_MASK_SPARSE")) e->mask_sparse = atoi(ms);
+  if (const char* cm = getenv("GT_CHAIN")) e->chain_mode = atoi(cm);
   if (const char* mm = getenv("GT_MATCH")) e->match_mode = std::min(2, std::max(0, atoi(mm)));
   if (const char* kb = getenv("GT_CONV_SMEM_KB")) e->conv_smem_kb = std::min(227, std::max(96, atoi(kb)));
   if (e->overlap == 1 && !getenv("GT_CONV_SMEM_KB")) e->conv_smem_kb = 200;   // room for ORB blocks beside the conv CTAs
@@ -164,6 +165,9 @@ int gt_destroy(gt_handle e) {
   cudaSetDevice(e->device);
   cudaDeviceSynchronize();
   for (void* p : e->dev_allocs) cudaFree(p);
+  for (void* p : {(void*)e->reg_xq, (void*)e->reg_xt, (void*)e->reg_cq, (void*)e->reg_ct, (void*)e->reg_cand, (void*)e->reg_n, (void*)e->reg_q32,
+                  (void*)e->reg_t32, (void*)e->reg_idx, (void*)e->reg_dist})
+    if (p) cudaFree(p);
   for (void* p : e->host_allocs) cudaFreeHost(p);
   for (int k = 0; k < 2; ++k) {
     for (int i = 0; i < 8; ++i) if (e->ev_sets[k][i]) cudaEventDestroy(e->ev_sets[k][i]);
@@ -771,18 +775,44 @@ int gt_match(gt_handle e, const uint8_t* query, int nq, const uint8_t* train, in
   return GT_OK;
 }
 
+int gt_match_l2(gt_handle e, const float* query, int nq, const float* train, int nt, int dim, int32_t* out_idx, float* out_dist, void* stream) {
+  ENTER(e);
+  GT_CHECK(e, query && train && out_idx && out_dist && nq >= 1 && nt >= 1 && nq <= GT_MATCH_L2_MAX && nt <= GT_MATCH_L2_MAX,
+           "gt_match_l2: bad arguments (nq=%d, nt=%d, limit %d)", nq, nt, GT_MATCH_L2_MAX);
+  GT_CHECK(e, dim == 128, "gt_match_l2: only 128-element descriptors (SIFT / RootSIFT) are supported, got %d", dim);
+  cudaStream_t st = pick_stream(e, stream);
+  const int need = std::max(nq, nt);
+  if (need > e->reg_io_cap) {
+    for (void* p : {(void*)e->reg_q32, (void*)e->reg_t32, (void*)e->reg_idx, (void*)e->reg_dist}) if (p) cudaFree(p);
+    e->reg_q32 = e->reg_t32 = nullptr; e->reg_idx = nullptr; e->reg_dist = nullptr; e->reg_io_cap = 0;
+    GT_CUDA(e, cudaMalloc((void**)&e->reg_q32, (size_t)need * 128 * sizeof(float)));
+    GT_CUDA(e, cudaMalloc((void**)&e->reg_t32, (size_t)need * 128 * sizeof(float)));
+    GT_CUDA(e, cudaMalloc((void**)&e->reg_idx, (size_t)need * 2 * sizeof(int)));
+    GT_CUDA(e, cudaMalloc((void**)&e->reg_dist, (size_t)need * 2 * sizeof(float)));
+    e->reg_io_cap = need;
+  }
+  GT_TRY(to_device(e, e->reg_q32, query, (size_t)nq * 128 * sizeof(float), st));
+  GT_TRY(to_device(e, e->reg_t32, train, (size_t)nt * 128 * sizeof(float), st));
+  GT_TRY(match_l2_run(e, e->reg_q32, nq, e->reg_t32, nt, e->reg_idx, e->reg_dist, st));
+  GT_TRY(to_caller(e, out_idx, e->reg_idx, (size_t)nq * 2 * sizeof(int), st));
+  GT_TRY(to_caller(e, out_dist, e->reg_dist, (size_t)nq * 2 * sizeof(float), st));
+  GT_CUDA(e, cudaStreamSynchronize(st));
+  return GT_OK;
+}
+
 int gt_find_homography(gt_handle e, const float* src, const float* dst, int n, float thr, int max_iter, double* out_H, int32_t* out_inliers,
                        void* stream) {
   ENTER(e);
-  GT_CHECK(e, src && dst && n >= 0 && n <= GT_MAX_KP && out_H && max_iter >= 1 && max_iter <= e->cfg.ransac_max_iter,
-           "gt_find_homography: bad arguments (n=%d, max_iter=%d)", n, max_iter);
+  const int pair_cap = e->cfg.max_batch * GT_MAX_KP;   // a single pair set may use the pair buffers of the whole batch
+  GT_CHECK(e, src && dst && n >= 0 && n <= pair_cap && out_H && max_iter >= 1 && max_iter <= e->cfg.ransac_max_iter,
+           "gt_find_homography: bad arguments (n=%d of at most %d, max_iter=%d of at most %d)", n, pair_cap, max_iter, e->cfg.ransac_max_iter);
   cudaStream_t st = pick_stream(e, stream);
   std::vector<float> pr((size_t)std::max(n, 1) * 4);
   for (int i = 0; i < n; ++i) { pr[i * 4] = src[i * 2]; pr[i * 4 + 1] = src[i * 2 + 1]; pr[i * 4 + 2] = dst[i * 2]; pr[i * 4 + 3] = dst[i * 2 + 1]; }
   GT_CUDA(e, cudaMemcpyAsync(e->pairs, pr.data(), (size_t)n * 16, cudaMemcpyHostToDevice, st));
   GT_CUDA(e, cudaMemcpyAsync(e->pair_count, &n, sizeof(int), cudaMemcpyHostToDevice, st));
   GT_CUDA(e, cudaStreamSynchronize(st));
-  GT_TRY(homography_run(e, e->pairs, e->pair_count, 1, GT_MAX_KP, thr, max_iter, e->H_dev, e->H_status, e->H_stats, 1.0f, true, nullptr, st));
+  GT_TRY(homography_run(e, e->pairs, e->pair_count, 1, pair_cap, thr, max_iter, e->H_dev, e->H_status, e->H_stats, 1.0f, true, nullptr, st));
   int stats[4], status = 0;
   GT_CUDA(e, cudaMemcpyAsync(out_H, e->H_dev, 9 * sizeof(double), cudaMemcpyDefault, st));
   GT_CUDA(e, cudaMemcpyAsync(stats, e->H_stats, sizeof(stats), cudaMemcpyDeviceToHost, st));

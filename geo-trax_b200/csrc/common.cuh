@@ -101,17 +101,26 @@ struct ConvParams {
   bf16* up;               // optional second, 2x nearest-upsampled destination (2H x 2W)
   int up_ctot, up_coff;
   const float* bias;      // [n_tiles * BN]
+  // chained 1x1 conv (conv_tc.cu, pixel-major 16-bit slabs only): the activated tile of this conv never goes to HBM -- its staging slabs
+  // are the A operand of a second GEMM against resident weights [chain_n][BN], whose activated result is what gets stored
+  int chain_n;            // output channels of the chained conv (64 or 128; 0 = no chain); its K is this conv's BN
+  int chain_act;          // its activation (same codes as `act`)
+  int chain_tmem;         // TMEM column offset of its accumulator (after the two accumulators of the main conv)
+  const float* chain_bias;   // [chain_n]
 };
 
 struct ConvUpMaps { CUtensorMap m[4]; };   // the four (dy, dx) phases of the 2x nearest-upsampled destination
 
 struct ConvOp {
-  CUtensorMap tmA, tmB, tmOut, tmRes;
+  CUtensorMap tmA, tmB, tmOut, tmRes, tmC;   // tmC: weights of the chained 1x1 conv (ConvParams::chain_n)
   ConvUpMaps tmUp;
   ConvParams p;
   size_t smem = 0;
   bf16* w_dev = nullptr;     // [cout_pad][taps][cin_pad]
   float* b_dev = nullptr;    // [cout_pad]
+  bf16* w2_dev = nullptr;    // chained conv: [chain_n][BN]
+  float* b2_dev = nullptr;   // [chain_n]
+  int chain_src = -1;        // canonical conv index of the chained 1x1 conv (-1: none)
   int cin = 0, cout = 0, cout_pad = 0, cin_pad = 0, k = 1, stride = 1;
   int occ2 = 0;              // 1: conv_tc.cu compiled for two CTAs per SM (variant 3)
   int pair = 0;              // 1: conv_sw.cu as CTA pairs (cta_group::2, 256 channels x 256 pixels per pair tile; variant 6)
@@ -140,10 +149,11 @@ struct ConvPlanArgs {
   const View* res = nullptr;
   const View* up = nullptr;
   const View* pre = nullptr;   // half-resolution pre-activation partial sum (see ConvParams::res_pre); excludes res
+  int chain_cout = 0, chain_act = 1;   // > 0: a 1x1 conv with chain_cout outputs follows in the same kernel; `out` is ITS destination
 };
 
 // layer signature = key of the shipped per-layer kernel-variant table (csrc/conv_tune.inc)
-struct ConvSig { int cin, cout, k, stride, H, W, flags; };   // flags: 1 residual, 2 upsampled copy, 4 f32 rows, 8 s2d output, 16 half-res pre-activation add
+struct ConvSig { int cin, cout, k, stride, H, W, flags; };   // flags: 1 residual, 2 upsampled copy, 4 f32 rows, 8 s2d output, 16 half-res pre-activation add, 32 chained 1x1 conv
 ConvSig conv_signature(const ConvPlanArgs& a);
 int conv_choose_variant(const ConvSig& s);
 
@@ -151,6 +161,7 @@ int conv_tc_init(gt_engine* e);  // resolves cuTensorMapEncodeTiled, sets kernel
 int conv_tc_plan(gt_engine* e, ConvOp* op, const ConvPlanArgs& a);  // tensor maps + launch geometry + weight storage
 int conv_tc_pack_weights(gt_engine* e, ConvOp* op, const float* const* w, const float* const* b, const int* couts, int n);   // honours op->w_cin_total / w_cin_off / no_bias
 int conv_tc_upload_packed(gt_engine* e, ConvOp* op, const uint16_t* packed, const float* bias);
+int conv_tc_pack_chain(gt_engine* e, ConvOp* op, const float* w, const float* b);   // weights of the chained 1x1 conv (ConvOp::chain_src)
 int conv_tc_launch(gt_engine* e, const ConvOp* op, int B, cudaStream_t st);
 int conv_tc_launch_range(gt_engine* e, const ConvOp* op, int b0, int nb, cudaStream_t st);
 // swapped-operand variant (conv_sw.cu); conv_tc_plan / conv_tc_launch* dispatch to it when the engine's swap_mode is on

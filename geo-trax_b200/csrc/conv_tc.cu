@@ -168,12 +168,89 @@ __device__ __forceinline__ void epilogue_tile(const ConvParams& p, const TileCoo
   }
 }
 
+// Epilogue of a tile whose conv is followed by a CHAINED 1x1 conv (ConvParams::chain_n): the activated 16-bit slabs of the main conv
+// (128 pixels x 64 channels each, written in the 128-byte swizzle the TMA store would want) are at the same time canonical K-major
+// SWIZZLE_128B A-operand tiles.  So instead of storing them, the leader warp issues a second GEMM D2[128 px][chain_n] = slab . W2^T
+// against the resident chain weights into a third TMEM accumulator, every warp then runs a second epilogue on D2, and only that
+// result is stored.  The intermediate tensor (model.1's output: 16.7 MB per 4K frame) is never written to or read from HBM.
+__device__ __forceinline__ void epilogue_chain_tile(const ConvParams& p, const TileCoord& t, uint32_t trow, uint32_t trow2, uint32_t tacc2, uint32_t stage_base,
+                                                    uint32_t s_bias, uint32_t s_bias2, const CUtensorMap* tmOut, int half, int row, uint32_t tempty_bar, int lane,
+                                                    bool leader_warp, uint32_t tfull_bar, uint32_t tfull_parity, uint32_t chain_bar, uint32_t chain_parity,
+                                                    uint32_t cres_lo, uint32_t idesc2, bool first_tile) {
+  constexpr int CW = 32, CHUNKS = 4;
+  const int n1 = p.BN >> 6, n2 = p.chain_n >> 6;
+  const uint32_t hi = desc_hi(1024u, 2u);
+  if (lane == 0) mbar_wait(tfull_bar, tfull_parity);
+  __syncwarp();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  // both staging buffers are free once the previous tile's bulk stores have read them
+  if (leader_warp && lane == 0 && !first_tile) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+  epi_bar();
+  auto finish_slab = [&](const uint32_t* v, uint32_t bias_addr, int act, float scale, uint32_t buf) {
+    float f[CW];
+#pragma unroll
+    for (int i = 0; i < CW; i += 4) {
+      const float4 bv = lds_f4(bias_addr + (uint32_t)i * 4u);
+      f[i] = fmaf(__uint_as_float(v[i]), scale, bv.x); f[i + 1] = fmaf(__uint_as_float(v[i + 1]), scale, bv.y);
+      f[i + 2] = fmaf(__uint_as_float(v[i + 2]), scale, bv.z); f[i + 3] = fmaf(__uint_as_float(v[i + 3]), scale, bv.w);
+    }
+    act_inplace<CW>(f, act);
+#pragma unroll
+    for (int c = 0; c < CHUNKS; ++c) {
+      uint4 pk;
+      pk.x = pack2_act(f[c * 8 + 0], f[c * 8 + 1], p.fp16); pk.y = pack2_act(f[c * 8 + 2], f[c * 8 + 3], p.fp16);
+      pk.z = pack2_act(f[c * 8 + 4], f[c * 8 + 5], p.fp16); pk.w = pack2_act(f[c * 8 + 6], f[c * 8 + 7], p.fp16);
+      const uint32_t logical = (uint32_t)row * 128u + (uint32_t)(half * CHUNKS + c) * 16u;
+      sts_u4(buf + (logical ^ (((logical >> 7) & 7u) << 4)), pk);
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  };
+  for (int j = 0; j < n1; ++j) {
+    const uint32_t buf = stage_base + (uint32_t)j * (128 * 128);
+    uint32_t v[CW];
+    tmem_ld<CW>(trow + (uint32_t)(j * 64 + half * CW), v);
+    tmem_ld_wait();
+    if (j == n1 - 1) {                                // main accumulator fully read: hand it back to the MMA warp
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar);
+    }
+    finish_slab(v, s_bias + (uint32_t)(j * 64 + half * CW) * 4u, p.act, p.scale, buf);
+    epi_bar();
+    if (leader_warp) {                                // k-block j of the chained GEMM: A = the slab just written, B = W2[:, 64 j .. 64 j + 63]
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      if (elect_one()) {
+        const uint32_t a_lo = (buf & 0x3FFFFu) >> 4, b_lo = cres_lo + (uint32_t)j * ((uint32_t)p.chain_n * 128u >> 4);
+        issue_kb<4>(tacc2, a_lo, hi, b_lo, hi, idesc2, j ? 1u : 0u);
+        if (j == n1 - 1) umma_commit(chain_bar);
+      }
+      __syncwarp();
+    }
+  }
+  if (lane == 0) mbar_wait(chain_bar, chain_parity);
+  __syncwarp();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  for (int j = 0; j < n2; ++j) {
+    const uint32_t buf = stage_base + (uint32_t)j * (128 * 128);   // (the chained MMAs have consumed both buffers)
+    uint32_t v[CW];
+    tmem_ld<CW>(trow2 + (uint32_t)(j * 64 + half * CW), v);
+    tmem_ld_wait();
+    if (j == n2 - 1) asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");   // D2 is free for the next tile after the barrier below
+    finish_slab(v, s_bias2 + (uint32_t)(j * 64 + half * CW) * 4u, p.chain_act, 1.0f, buf);
+    epi_bar();
+    if (leader_warp && lane == 0) {
+      tma_store_4d(tmOut, buf, j * 64, t.x0, t.y0, t.n);
+      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    }
+  }
+}
+
 // OCC = CTAs per SM the instantiation is compiled for: 2 (register cap 96, <= 113 KB shared memory, <= 256 TMEM columns per CTA)
 // doubles the number of epilogue chains in flight for layers whose tiles carry little MMA work (small cout / small K).
 template <int OCC>
 __global__ void __launch_bounds__(kThreads, OCC) conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                                                               const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ ConvUpMaps tmUp,
-                                                              const ConvParams p) {
+                                                              const __grid_constant__ CUtensorMap tmC, const ConvParams p) {
   pdl_launch_dependents();   // the next layer's CTAs may start their prologue (barriers, TMEM, resident weights) as SMs free up
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // carve (all 1024-aligned): operand ring | resident weights (optional) | 2 output staging slabs | barriers / tmem pointer / bias
@@ -184,7 +261,8 @@ __global__ void __launch_bounds__(kThreads, OCC) conv_tc_kernel(const __grid_con
   const int stage_bytes = p.halo ? b_bytes : (p.b_resident ? a_bytes : a_bytes + b_bytes);
   uint8_t* halo_ring = smem + (size_t)p.stages * stage_bytes;
   uint8_t* b_res = halo_ring + (size_t)p.a_stages * p.halo_bytes;
-  uint8_t* out_stage = b_res + (p.b_resident ? (size_t)p.num_kb * b_bytes : 0);
+  uint8_t* c_res = b_res + (p.b_resident ? (size_t)p.num_kb * b_bytes : 0);   // chained conv: weights [BN / 64][chain_n rows][128 B]
+  uint8_t* out_stage = c_res + (size_t)(p.BN >> 6) * p.chain_n * 128;
   uint8_t* tail = out_stage + 2 * 128 * 128;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(tail);
   uint64_t* empty_bar = full_bar + kMaxStages;
@@ -193,7 +271,9 @@ __global__ void __launch_bounds__(kThreads, OCC) conv_tc_kernel(const __grid_con
   uint64_t* tfull_bar = aempty_bar + kMaxHaloStages;   // [2] accumulator ready
   uint64_t* tempty_bar = tfull_bar + 2;           // [2] accumulator drained
   uint64_t* bres_bar = tempty_bar + 2;            // resident weights landed
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bres_bar + 1);
+  uint64_t* cres_bar = bres_bar + 1;              // chain weights landed
+  uint64_t* chain_bar = cres_bar + 1;             // chained GEMM of the current tile complete
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(chain_bar + 1);
   float* s_bias = reinterpret_cast<float*>(tmem_ptr_smem + 2);
 
   const int warp = threadIdx.x >> 5;
@@ -217,6 +297,8 @@ __global__ void __launch_bounds__(kThreads, OCC) conv_tc_kernel(const __grid_con
       mbar_init(smem_u32(&tempty_bar[s]), kEpiWarps);
     }
     mbar_init(smem_u32(bres_bar), 1);
+    mbar_init(smem_u32(cres_bar), 1);
+    mbar_init(smem_u32(chain_bar), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -227,6 +309,7 @@ __global__ void __launch_bounds__(kThreads, OCC) conv_tc_kernel(const __grid_con
   if (warp >= 2) {
     const int nb = p.n_tiles * p.BN;
     for (int i = threadIdx.x - 64; i < nb; i += kEpiWarps * 32) s_bias[i] = p.bias[i];
+    for (int i = threadIdx.x - 64; i < p.chain_n; i += kEpiWarps * 32) s_bias[nb + i] = p.chain_bias[i];
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
@@ -242,6 +325,14 @@ __global__ void __launch_bounds__(kThreads, OCC) conv_tc_kernel(const __grid_con
         const uint32_t bb = smem_u32(bres_bar);
         mbar_expect_tx(bb, (uint32_t)(p.num_kb * b_bytes));
         for (int kb = 0; kb < p.num_kb; ++kb) tma_load_2d(smem_u32(b_res + (size_t)kb * b_bytes), &tmB, bb, kb * p.kb_elems, 0);
+      }
+      __syncwarp();
+    }
+    if (p.chain_n) {
+      if (elect_one()) {
+        const uint32_t cb = smem_u32(cres_bar), kb_bytes = (uint32_t)p.chain_n * 128u;
+        mbar_expect_tx(cb, (uint32_t)(p.BN >> 6) * kb_bytes);
+        for (int kb = 0; kb < (p.BN >> 6); ++kb) tma_load_2d(smem_u32(c_res) + (uint32_t)kb * kb_bytes, &tmC, cb, kb * 64, 0);
       }
       __syncwarp();
     }
@@ -394,9 +485,14 @@ __global__ void __launch_bounds__(kThreads, OCC) conv_tc_kernel(const __grid_con
     const int row = q * 32 + lane;
     const int ly = row / p.tw, lx = row - ly * p.tw;
     const bool leader_warp = warp == 2;
+    if (p.chain_n) {
+      if (lane == 0) mbar_wait(smem_u32(cres_bar), 0);
+      __syncwarp();
+    }
     pdl_wait();   // residual reads and output stores below
     uint32_t li = 0, slab_ctr = 0;
     const uint32_t out_stage_a = smem_u32(out_stage), s_bias_a = smem_u32(s_bias);
+    const uint32_t cres_lo = (smem_u32(c_res) & 0x3FFFFu) >> 4, idesc2 = make_idesc(p.chain_n ? p.chain_n : 64, p.fp16);
     TileIter ti;
     ti.init(p, blockIdx.x, gridDim.x);
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++li, ti.next(p)) {
@@ -415,6 +511,12 @@ __global__ void __launch_bounds__(kThreads, OCC) conv_tc_kernel(const __grid_con
       if (lane == 0) mbar_arrive(teb);
       continue;
 #endif
+      if (p.chain_n) {
+        epilogue_chain_tile(p, t, trow, tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)p.chain_tmem, tmem_base + (uint32_t)p.chain_tmem, out_stage_a, s_bias_a,
+                            s_bias_a + (uint32_t)(p.n_tiles * p.BN) * 4u, &tmOut, half, row, teb, lane, leader_warp, tfb, tfp, smem_u32(chain_bar), li & 1u, cres_lo,
+                            idesc2, li == 0);
+        continue;
+      }
       switch (p.epi_mode) {
         case 0: epilogue_tile<32, false>(p, t, trow, out_stage_a, s_bias_a, &tmOut, tmUp.m, half, row, y, x, valid, slab_ctr, teb, lane, leader_warp, tfb, tfp); break;
         case 1: epilogue_tile<16, false>(p, t, trow, out_stage_a, s_bias_a, &tmOut, tmUp.m, half, row, y, x, valid, slab_ctr, teb, lane, leader_warp, tfb, tfp); break;
@@ -433,9 +535,9 @@ __global__ void __launch_bounds__(kThreads, OCC) conv_tc_kernel(const __grid_con
   }
 }
 
-size_t conv_smem_bytes(int stages, int stage_bytes, int halo_total, int bres_bytes, int bias_floats) {
-  return 1024 /*alignment slack*/ + (size_t)stages * stage_bytes + (size_t)halo_total + (size_t)bres_bytes + 2 * 128 * 128 /*output staging*/ +
-         (2 * kMaxStages + 2 * kMaxHaloStages + 5) * 8 + 8 + (size_t)bias_floats * 4 + 16;
+size_t conv_smem_bytes(int stages, int stage_bytes, int halo_total, int bres_bytes, int bias_floats, int chain_bytes = 0) {
+  return 1024 /*alignment slack*/ + (size_t)stages * stage_bytes + (size_t)halo_total + (size_t)bres_bytes + (size_t)chain_bytes + 2 * 128 * 128 /*output staging*/ +
+         (2 * kMaxStages + 2 * kMaxHaloStages + 7) * 8 + 8 + (size_t)bias_floats * 4 + 16;
 }
 
 }  // namespace
@@ -490,7 +592,7 @@ static void pick_tile(int H, int W, int* tw, int* th) {
 
 int conv_tc_plan(gt_engine* e, ConvOp* op, const ConvPlanArgs& a) {
   GT_CHECK(e, g_encode != nullptr, "conv_tc_init not called");
-  if ((e->plan_variant == 1 || e->plan_variant == 2 || e->plan_variant == 6) && !a.pre) return conv_sw_plan(e, op, a);   // (the half-resolution pre-activation add lives in the pixel-major epilogue only)
+  if ((e->plan_variant == 1 || e->plan_variant == 2 || e->plan_variant == 6) && !a.pre && !a.chain_cout) return conv_sw_plan(e, op, a);   // (the half-resolution pre-activation add and the chained 1x1 conv live in the pixel-major epilogue only)
   const View& in = a.in;
   const int cin = a.cin, k = a.k, stride = a.stride;
   const int kbe = (a.kb_elems == 64 && cin == 32) ? 32 : a.kb_elems;   // 32-channel inputs: 64-byte rows instead of half-empty 128-byte rows
@@ -536,13 +638,24 @@ int conv_tc_plan(gt_engine* e, ConvOp* op, const ConvPlanArgs& a) {
   p.tmem_cols = 32;
   while (p.tmem_cols < 2 * p.BN) p.tmem_cols *= 2;
   p.acc_stride = p.tmem_cols / 2;
+  int chain_bytes = 0;
+  if (a.chain_cout) {
+    GT_CHECK(e, !a.out_f32 && !a.out_s2d && !a.res && !a.up && !a.pre && p.epi_mode == 0 && p.n_tiles == 1 && p.BN == cout_total && p.BN <= 128 &&
+                    (a.chain_cout % 64) == 0 && a.chain_cout <= 128,
+             "conv plan: a chained 1x1 conv needs a plain 16-bit conv with 64 or 128 outputs (got %d -> %d)", cout_total, a.chain_cout);
+    p.chain_n = a.chain_cout; p.chain_act = getenv("GT_DEBUG_NOACT") ? 0 : a.chain_act;
+    p.acc_stride = p.BN; p.chain_tmem = 2 * p.BN;
+    p.tmem_cols = 32;
+    while (p.tmem_cols < 2 * p.BN + p.chain_n) p.tmem_cols *= 2;
+    chain_bytes = (p.BN >> 6) * p.chain_n * 128;
+  }
   const int a_bytes = 128 * kbe * 2, b_bytes = p.BN * kbe * 2;
   const int bres_bytes = p.num_kb * b_bytes;
-  p.b_resident = (p.n_tiles == 1 && bres_bytes <= 112 * 1024 && (size_t)bres_bytes + 3 * a_bytes + 40 * 1024 <= (size_t)e->conv_smem_kb * 1024) ? 1 : 0;
+  p.b_resident = (p.n_tiles == 1 && bres_bytes <= 112 * 1024 && (size_t)bres_bytes + chain_bytes + 3 * a_bytes + 40 * 1024 <= (size_t)e->conv_smem_kb * 1024) ? 1 : 0;
   const bool occ2 = (e->plan_variant == 3 || e->plan_variant == 5) && p.tmem_cols <= 256;   // two CTAs per SM (BN <= 128); else the plain plan
   const size_t budget = occ2 ? (size_t)112 * 1024 : (size_t)e->conv_smem_kb * 1024;
   if (occ2) {
-    p.b_resident = (p.n_tiles == 1 && (size_t)bres_bytes + 3 * a_bytes + 36 * 1024 <= budget) ? 1 : 0;
+    p.b_resident = (p.n_tiles == 1 && (size_t)bres_bytes + chain_bytes + 3 * a_bytes + 36 * 1024 <= budget) ? 1 : 0;
   }
   op->occ2 = occ2 ? 1 : 0;
   int stage_bytes = p.b_resident ? a_bytes : a_bytes + b_bytes;
@@ -551,7 +664,7 @@ int conv_tc_plan(gt_engine* e, ConvOp* op, const ConvPlanArgs& a) {
     const int hrows = p.th + k - 1;
     p.halo_tx = (p.tw + k - 1) * hrows * kbe * 2;
     p.halo_bytes = (p.halo_tx + 1023) / 1024 * 1024;
-    const size_t fixed = conv_smem_bytes(0, 0, 0, p.b_resident ? bres_bytes : 0, op->cout_pad);
+    const size_t fixed = conv_smem_bytes(0, 0, 0, p.b_resident ? bres_bytes : 0, op->cout_pad + p.chain_n, chain_bytes);
     int a_st, b_st = 0;
     if (p.b_resident) a_st = (int)((budget - fixed) / p.halo_bytes);
     else {
@@ -570,7 +683,7 @@ int conv_tc_plan(gt_engine* e, ConvOp* op, const ConvPlanArgs& a) {
   }
   p.tiles_x = ceil_div(Wo, p.tw); p.tiles_y = ceil_div(Ho, p.th);
   if (!p.halo) {
-    const size_t fixed = conv_smem_bytes(0, stage_bytes, 0, p.b_resident ? bres_bytes : 0, op->cout_pad);
+    const size_t fixed = conv_smem_bytes(0, stage_bytes, 0, p.b_resident ? bres_bytes : 0, op->cout_pad + p.chain_n, chain_bytes);
     int stages = (int)((budget - fixed) / stage_bytes);
     if (stages > kMaxStages) stages = kMaxStages;
     GT_CHECK(e, stages >= 2, "conv plan: tile does not fit shared memory (BN=%d)", p.BN);
@@ -586,8 +699,8 @@ int conv_tc_plan(gt_engine* e, ConvOp* op, const ConvPlanArgs& a) {
                                    out->ctot == 32 && out->coff == 0,
                             "conv plan: s2d output view mismatch");
     else
-    GT_CHECK(e, out && out->H == Ho && out->W == Wo && out->C == cout_total, "conv plan: output view mismatch (%dx%dx%d vs %dx%dx%d)",
-             out ? out->H : -1, out ? out->W : -1, out ? out->C : -1, Ho, Wo, cout_total);
+    GT_CHECK(e, out && out->H == Ho && out->W == Wo && out->C == (a.chain_cout ? a.chain_cout : cout_total), "conv plan: output view mismatch (%dx%dx%d vs %dx%dx%d)",
+             out ? out->H : -1, out ? out->W : -1, out ? out->C : -1, Ho, Wo, a.chain_cout ? a.chain_cout : cout_total);
     GT_CHECK(e, (out->ctot % 8) == 0 && (out->coff % 8) == 0 && (cout_total % 8) == 0, "conv plan: output slice must be 16-byte aligned");
     p.out_f32 = 0; p.out = out->ptr; p.out_img_stride = (long long)Ho * Wo; p.out_ctot = out->ctot; p.out_coff = out->coff;
     p.out_s2d = a.out_s2d ? 1 : 0; p.out_rows = Ho;
@@ -605,10 +718,10 @@ int conv_tc_plan(gt_engine* e, ConvOp* op, const ConvPlanArgs& a) {
                     (a.pre->ctot % 8) == 0 && (a.pre->coff % 8) == 0, "conv plan: half-resolution partial-sum view mismatch");
     p.res = a.pre->ptr; p.res_ctot = a.pre->ctot; p.res_coff = a.pre->coff; p.res_pre = 1;
   }
-  op->smem = conv_smem_bytes(p.stages, stage_bytes, halo_total, p.b_resident ? bres_bytes : 0, op->cout_pad);
-  op->flops = 2.0 * Ho * Wo * (double)cout_total * cin * k * k;
+  op->smem = conv_smem_bytes(p.stages, stage_bytes, halo_total, p.b_resident ? bres_bytes : 0, op->cout_pad + p.chain_n, chain_bytes);
+  op->flops = 2.0 * Ho * Wo * (double)cout_total * cin * k * k + 2.0 * Ho * Wo * (double)a.chain_cout * cout_total;
   // algorithmic HBM bytes per image: input slice + output (+ residual, + upsampled copy) + weights (once per launch, ignored)
-  op->bytes = (double)in.H * in.W * cin * 2 + (double)Ho * Wo * cout_total * (a.out_f32 ? 4 : 2) * (a.up ? 5 : 1) +
+  op->bytes = (double)in.H * in.W * cin * 2 + (double)Ho * Wo * (a.chain_cout ? a.chain_cout : cout_total) * (a.out_f32 ? 4 : 2) * (a.up ? 5 : 1) +
               (a.res ? (double)Ho * Wo * cout_total * 2 : 0.0) + (a.pre ? (double)Ho * Wo * cout_total * 2 / 4 : 0.0);
 
   // weights + bias storage
@@ -618,6 +731,13 @@ int conv_tc_plan(gt_engine* e, ConvOp* op, const ConvPlanArgs& a) {
   GT_CUDA(e, cudaMemset(op->w_dev, 0, wn * sizeof(bf16)));
   GT_CUDA(e, cudaMemset(op->b_dev, 0, (size_t)op->cout_pad * sizeof(float)));
   p.bias = op->b_dev;
+  if (a.chain_cout) {
+    GT_TRY(e->dev_alloc((void**)&op->w2_dev, (size_t)p.chain_n * p.BN * sizeof(bf16)));
+    GT_TRY(e->dev_alloc((void**)&op->b2_dev, (size_t)p.chain_n * sizeof(float)));
+    GT_CUDA(e, cudaMemset(op->w2_dev, 0, (size_t)p.chain_n * p.BN * sizeof(bf16)));
+    GT_CUDA(e, cudaMemset(op->b2_dev, 0, (size_t)p.chain_n * sizeof(float)));
+    p.chain_bias = op->b2_dev;
+  }
 
   const CUtensorMapDataType dt = p.fp16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
   const CUtensorMapSwizzle sw = kbe == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : (kbe == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
@@ -645,6 +765,16 @@ int conv_tc_plan(gt_engine* e, ConvOp* op, const ConvPlanArgs& a) {
     GT_CHECK(e, r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(B) failed: %d (ktot=%llu cout_pad=%d BN=%d)", (int)r,
              (unsigned long long)ktot, op->cout_pad, p.BN);
   }
+  memset(&op->tmC, 0, sizeof(op->tmC));
+  if (a.chain_cout) {   // chained conv weights [chain_n][BN] (K-major): one box = one 64-channel k-block of all chain_n rows
+    cuuint64_t gdim[2] = {(cuuint64_t)p.BN, (cuuint64_t)p.chain_n};
+    cuuint64_t gstr[1] = {(cuuint64_t)p.BN * 2};
+    cuuint32_t box[2] = {64, (cuuint32_t)p.chain_n};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = g_encode(&op->tmC, dt, 2, (void*)op->w2_dev, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                          CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    GT_CHECK(e, r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(chain weights) failed: %d", (int)r);
+  }
   // Output: destination slice as a 4-D tensor {C, W, H, N}; one box = one staging slab (128 rows x 128 or 64 bytes).
   // Out-of-range rows / columns / channels of ragged tiles are clipped by the TMA unit.
   {
@@ -653,7 +783,7 @@ int conv_tc_plan(gt_engine* e, ConvOp* op, const ConvPlanArgs& a) {
     const CUtensorMapDataType odt = a.out_f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : dt;
     auto enc = [&](CUtensorMap* tm, void* base, cuuint64_t W_, cuuint64_t H_, cuuint64_t pix_stride_b, cuuint64_t row_stride_b,
                    cuuint64_t img_stride_b) -> CUresult {
-      cuuint64_t gdim[4] = {(cuuint64_t)cout_total, W_, H_, (cuuint64_t)a.Bmax};
+      cuuint64_t gdim[4] = {(cuuint64_t)(a.chain_cout ? a.chain_cout : cout_total), W_, H_, (cuuint64_t)a.Bmax};
       cuuint64_t gstr[3] = {pix_stride_b, row_stride_b, img_stride_b};
       cuuint32_t box[4] = {(cuuint32_t)box_c, (cuuint32_t)p.tw, (cuuint32_t)p.th, 1};
       cuuint32_t estr[4] = {1, 1, 1, 1};
@@ -708,6 +838,21 @@ int conv_tc_pack_weights(gt_engine* e, ConvOp* op, const float* const* w, const 
   return conv_tc_upload_packed(e, op, hw.data(), hb.data());
 }
 
+// chained 1x1 conv: w f32 [chain_n][cin2 = this conv's cout] (PyTorch [cout][cin][1][1]) -> 16-bit [chain_n][BN]; bias f32 [chain_n]
+int conv_tc_pack_chain(gt_engine* e, ConvOp* op, const float* w, const float* b) {
+  const int n = op->p.chain_n, K = op->p.BN;
+  GT_CHECK(e, n > 0 && op->w2_dev && K == op->cout, "pack chain weights: the op has no chained conv");
+  std::vector<uint16_t> hw((size_t)n * K, 0);
+  std::vector<float> hb(n, 0.f);
+  for (int co = 0; co < n; ++co) {
+    for (int ci = 0; ci < K; ++ci) hw[(size_t)co * K + ci] = host_to_act(w[(size_t)co * K + ci], op->p.fp16);
+    hb[co] = b ? b[co] : 0.f;
+  }
+  GT_CUDA(e, cudaMemcpy(op->w2_dev, hw.data(), hw.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
+  GT_CUDA(e, cudaMemcpy(op->b2_dev, hb.data(), hb.size() * sizeof(float), cudaMemcpyHostToDevice));
+  return GT_OK;
+}
+
 // packed: 16-bit [cout_pad][taps][cin_pad] already in the activation format; bias f32 [cout_pad]
 int conv_tc_upload_packed(gt_engine* e, ConvOp* op, const uint16_t* packed, const float* bias) {
   const size_t wn = (size_t)op->cout_pad * op->k * op->k * op->cin_pad;
@@ -733,8 +878,8 @@ int conv_tc_launch_range(gt_engine* e, const ConvOp* op, int b0, int nb, cudaStr
   at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   at[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = at; cfg.numAttrs = e->pdl ? 1 : 0;
-  if (op->occ2) GT_CUDA(e, cudaLaunchKernelEx(&cfg, conv_tc_kernel<2>, op->tmA, op->tmB, op->tmOut, op->tmUp, p));
-  else GT_CUDA(e, cudaLaunchKernelEx(&cfg, conv_tc_kernel<1>, op->tmA, op->tmB, op->tmOut, op->tmUp, p));
+  if (op->occ2) GT_CUDA(e, cudaLaunchKernelEx(&cfg, conv_tc_kernel<2>, op->tmA, op->tmB, op->tmOut, op->tmUp, op->tmC, p));
+  else GT_CUDA(e, cudaLaunchKernelEx(&cfg, conv_tc_kernel<1>, op->tmA, op->tmB, op->tmOut, op->tmUp, op->tmC, p));
   e->launches++;
   GT_CUDA(e, cudaGetLastError());
   return GT_OK;

@@ -833,7 +833,7 @@ ConvSig conv_signature(const ConvPlanArgs& a) {
   s.cin = a.cin; s.cout = a.cout; s.k = a.k; s.stride = a.stride;
   s.H = a.Ho > 0 ? a.Ho : (a.in.H + 2 * pad - a.k) / a.stride + 1;
   s.W = a.Wo > 0 ? a.Wo : (a.in.W + 2 * pad - a.k) / a.stride + 1;
-  s.flags = (a.res ? 1 : 0) | (a.up ? 2 : 0) | (a.out_f32 ? 4 : 0) | (a.out_s2d ? 8 : 0) | (a.pre ? 16 : 0);
+  s.flags = (a.res ? 1 : 0) | (a.up ? 2 : 0) | (a.out_f32 ? 4 : 0) | (a.out_s2d ? 8 : 0) | (a.pre ? 16 : 0) | (a.chain_cout ? 32 : 0);
   return s;
 }
 
@@ -845,6 +845,7 @@ static const TuneRow kTuneTable[] = {
 // Layers the table does not know (other frame sizes, other heads): the pattern of the tuned table, as a rule.
 static int rule_variant(const ConvSig& s) {
   if (s.flags & (4 | 8)) return 3;                                     // f32 head rows, layer 0: pixel-major, two CTAs / SM
+  if (s.flags & 32) return s.cout <= 64 ? 3 : 0;                       // chained 1x1 conv: pixel-major epilogue only
   const long long px = (long long)s.H * s.W;
   if (s.k == 1) {
     if (s.flags & 16) return s.cout <= 128 ? 3 : 0;                    // half-resolution pre-activation add: pixel-major epilogue only
@@ -965,6 +966,21 @@ struct Builder {
     rc = plan_both(op, a);
     if (rc == GT_OK) push(op);
   }
+  // conv `name` followed, inside the same kernel, by the 1x1 conv `name2` (ConvParams::chain_n): only name2's output reaches HBM
+  void conv_chain(const std::string& name, const std::string& name2, const View& in, const View& out) {
+    if (rc != GT_OK) return;
+    ConvOp op;
+    op.n_src = 1; op.src[0] = find(name); op.chain_src = find(name2);
+    const gt_conv_desc& d = e->conv_descs[op.src[0]];
+    const gt_conv_desc& d2 = e->conv_descs[op.chain_src];
+    if (d2.k != 1 || d2.stride != 1 || d2.cin != d.cout) { gt_set_error(e, "plan: %s cannot be chained after %s", name2.c_str(), name.c_str()); rc = GT_ERR_INVALID; return; }
+    ConvPlanArgs a;
+    a.in = in; a.Bmax = B; a.cin = d.cin; a.cout = d.cout; a.k = d.k; a.stride = d.stride; a.act = d.act; a.out = &out;
+    a.chain_cout = d2.cout; a.chain_act = d2.act;
+    if (a.chain_act == 1 && e->silu_tanh_px > 0 && (long long)out.H * out.W >= e->silu_tanh_px) a.chain_act = 2;
+    rc = plan_both(op, a);
+    if (rc == GT_OK) push(op);
+  }
   // final head conv writing fp32 rows of one of the three raw-head arrays (box logits [A][64], class logits [A][ncp], angle [A][4])
   void conv_raw(const std::string& name, const View& in, int lvl_off, float* base, int ctot) {
     if (rc != GT_OK) return;
@@ -1022,11 +1038,15 @@ struct Builder {
     for (int v = 1; v < GT_CONV_VARIANTS; ++v) if (!e->conv_var[v].empty()) e->conv_var[v].back().flops = fin.flops;
     push(fin);
   }
-  void c2f(const std::string& pre, const View& in, int c2, int n, bool shortcut, const View& out, const View* up = nullptr, const View* in_lo = nullptr) {
+  // chain_from / chain_in: the conv that produces the block's input runs in the same kernel as the block's cv1 (conv_chain); `in` then
+  // only gives the geometry (its buffer is never written)
+  void c2f(const std::string& pre, const View& in, int c2, int n, bool shortcut, const View& out, const View* up = nullptr, const View* in_lo = nullptr,
+           const char* chain_from = nullptr, const View* chain_in = nullptr) {
     const int c = c2 / 2;
     View cat = alloc((2 + n) * c, in.H, in.W);
     View tmp = alloc(c, in.H, in.W);
-    if (in_lo) conv_cat_up(pre + ".cv1", *in_lo, in, cat.slice(0, 2 * c));   // the block's input is cat(up2x(in_lo), in)
+    if (chain_from) conv_chain(chain_from, pre + ".cv1", *chain_in, cat.slice(0, 2 * c));
+    else if (in_lo) conv_cat_up(pre + ".cv1", *in_lo, in, cat.slice(0, 2 * c));   // the block's input is cat(up2x(in_lo), in)
     else conv({pre + ".cv1"}, in, cat.slice(0, 2 * c));
     for (int i = 0; i < n; ++i) {
       View src = cat.slice(c * (1 + i), c);
@@ -1130,10 +1150,14 @@ int detector_build(gt_engine* e) {
   e->net_s2d = S2D.ptr;
   View T0 = bl.alloc(c1, H1, W1);
   bl.conv0(S2D, T0);
-  View T1 = bl.alloc(c2, H2, W2);
-  bl.conv({"model.1"}, T0, T1);
+  // model.1 (3x3 s2, 32 -> 64) + model.2.cv1 (1x1, 64 -> 64) as ONE kernel: model.1's output (16.7 MB per 4K frame) never exists in HBM
+  const bool chain1 = e->chain_mode != 0;
+  View T1;
+  if (chain1) { T1.ptr = nullptr; T1.C = c2; T1.ctot = c2; T1.coff = 0; T1.H = H2; T1.W = W2; }
+  else { T1 = bl.alloc(c2, H2, W2); bl.conv({"model.1"}, T0, T1); }
   View T2 = bl.alloc(c2, H2, W2);
-  bl.c2f("model.2", T1, c2, 1, true, T2);
+  if (chain1) bl.c2f("model.2", T1, c2, 1, true, T2, nullptr, nullptr, "model.1", &T0);
+  else bl.c2f("model.2", T1, c2, 1, true, T2);
   View T3 = bl.alloc(c3, H3, W3);
   bl.conv({"model.3"}, T2, T3);
   View L4 = bl.alloc(c3, H3, W3);
@@ -1254,7 +1278,9 @@ static int load_op_weights(gt_engine* e, ConvOp& op, bool is_conv0, const float*
   const float* bs[3];
   int couts[3];
   for (int i = 0; i < op.n_src; ++i) { ws[i] = w[op.src[i]]; bs[i] = b[op.src[i]]; couts[i] = e->conv_descs[op.src[i]].cout; }
-  return conv_tc_pack_weights(e, &op, ws, bs, couts, op.n_src);
+  GT_TRY(conv_tc_pack_weights(e, &op, ws, bs, couts, op.n_src));
+  if (op.chain_src >= 0) GT_TRY(conv_tc_pack_chain(e, &op, w[op.chain_src], b[op.chain_src]));
+  return GT_OK;
 }
 
 int detector_load_weights(gt_engine* e, const float* const* w, const float* const* b, int n) {

@@ -66,6 +66,7 @@ struct gt_engine {
   cudaEvent_t ev_aux_a = nullptr, ev_aux_b = nullptr;
   cudaEvent_t ev_pre = nullptr, ev_front = nullptr;
   int overlap = 2;                      // GT_OVERLAP: 2 ORB front on the aux stream beside decode + NMS; 3 as 2, but the image pyramid already beside the conv stack (fills the tails between layers); 1 the whole front beside the detector (no gain: the conv CTAs own the SMs); 0 serial
+  int chain_mode = 1;                   // GT_CHAIN=0: model.1 and model.2.cv1 as two launches instead of one chained kernel
   int match_mode = 2;                   // GT_MATCH: 2 Hamming 2-NN as E4M3 tcgen05 GEMM (match_tc.cu), 1 the same with fp16 operands, 0 POPC kernel
   int mask_sparse = 1;                  // GT_MASK_SPARSE=0: dense mask pyramid (7 full-plane launches) instead of the box-driven sparse one
   long long silu_tanh_px = 1;           // GT_SILU_TANH_PX: layers with at least this many output pixels per image use the one-MUFU SiLU (default 1 = every SiLU layer: measured raw-head error unchanged at 5.8e-3, conv stack -3 %; 0 = none)
@@ -159,6 +160,13 @@ struct gt_engine {
   // matching / RANSAC
   uint8_t* desc_x = nullptr;                        // [B+1][64 groups][k-blocks][128][128 B] descriptors expanded to MMA operand tiles (match_tc.cu)
   float* desc_c = nullptr;                          // [B+1][GT_MAX_KP] popc * 8192 + row (float), huge beyond the count
+  // registration (f-3): L2 matcher work buffers, grown on demand by match_l2_run / gt_match_l2 and freed by gt_destroy
+  int reg_cap = 0, reg_io_cap = 0;
+  uint8_t* reg_xq = nullptr; uint8_t* reg_xt = nullptr;   // fp16 operand images [cap / 128][2][128][128 B]
+  float* reg_cq = nullptr; float* reg_ct = nullptr;         // |d|^2 per row
+  int* reg_cand = nullptr; int* reg_n = nullptr;            // [cap][4] tensor-core candidates; the two counts
+  float* reg_q32 = nullptr; float* reg_t32 = nullptr;       // device copies of host descriptors [io_cap][128]
+  int* reg_idx = nullptr; float* reg_dist = nullptr;        // [io_cap][2]
   int* match_idx = nullptr;                         // [B][GT_MAX_KP][2]
   int* match_dist = nullptr;                        // [B][GT_MAX_KP][2]
   float* pairs = nullptr;                           // [B][GT_MAX_KP][4] cur x,y, ref x,y (working res)
@@ -226,6 +234,7 @@ int match_run(gt_engine* e, const uint8_t* q, const int* nq_dev, int nq_max, con
 // match_tc.cu
 int match_tc_build(gt_engine* e);
 int match_tc_run(gt_engine* e, int q_slot0, int q_step, int nq_cap, int t_slot0, int t_step, int batch, cudaStream_t st);
+int match_l2_run(gt_engine* e, const float* q_dev, int nq, const float* t_dev, int nt, int* out_idx_dev, float* out_dist_dev, cudaStream_t st);
 int homography_run(gt_engine* e, const float* pairs, const int* counts, int B, int pair_stride, float thr, int max_iter,
                    double* out_H, int* out_status, int* out_stats, float ratio, bool full_res, const int* kp_count, cudaStream_t st);
 int warp_boxes_run(gt_engine* e, const double* H_dev, const int* status_dev, const float* in, float* out, const int* counts, int B,

@@ -308,6 +308,14 @@ class Engine:
         self._ck(self.lib.gt_match(self.h, q.ctypes.data, len(q), t.ctypes.data, len(t), idx.ctypes.data, dist.ctypes.data, None))
         return idx, dist
 
+    def match_l2(self, query: np.ndarray, train: np.ndarray):
+        """Brute-force L2 2-NN of float descriptors (SIFT / RootSIFT, 128 elements): (idx [nq, 2] i32, dist [nq, 2] f32)."""
+        q, t = np.ascontiguousarray(query, np.float32), np.ascontiguousarray(train, np.float32)
+        idx = np.zeros((len(q), 2), np.int32)
+        dist = np.zeros((len(q), 2), np.float32)
+        self._ck(self.lib.gt_match_l2(self.h, q.ctypes.data, len(q), t.ctypes.data, len(t), q.shape[1], idx.ctypes.data, dist.ctypes.data, None))
+        return idx, dist
+
     def find_homography(self, src: np.ndarray, dst: np.ndarray, thr=2.0, max_iter=5000):
         s, d = np.ascontiguousarray(src, np.float32), np.ascontiguousarray(dst, np.float32)
         H = np.zeros(9, np.float64)

@@ -196,7 +196,14 @@ int gt_orb_detect(gt_handle h, const uint8_t* gray, const uint8_t* mask, int B, 
 /* stand-alone 2-NN Hamming matcher + ratio test: query [nq][32], train [nt][32] -> per query best/second index/dist */
 int gt_match(gt_handle h, const uint8_t* query, int nq, const uint8_t* train, int nt, int32_t* out_idx /*[nq][2]*/,
              int32_t* out_dist /*[nq][2]*/, void* stream);
-/* stand-alone robust homography: pts f32 [n][2] each -> H f64[9], inlier count                                  */
+/* f-3 (registration, /root/reference/geotrax/utils/registration.py:57-93 -> stabilo BFMatcher(NORM_L2).knnMatch(k=2) on RootSIFT
+ * descriptors): brute-force L2 2-NN of float descriptors, query f32 [nq][dim], train f32 [nt][dim], dim == 128, host or device
+ * pointers; out_idx i32 [nq][2] (-1 where the train set has fewer rows), out_dist f32 [nq][2] = L2 distance.  Tensor-core candidate
+ * pass (fp16 operands, four candidates per query) + exact fp32 re-rank; equal distances -> lower train index.               */
+#define GT_MATCH_L2_MAX 262144
+int gt_match_l2(gt_handle h, const float* query, int nq, const float* train, int nt, int dim, int32_t* out_idx /*[nq][2]*/,
+                float* out_dist /*[nq][2]*/, void* stream);
+/* stand-alone robust homography: pts f32 [n][2] each (n <= max_batch * 8192) -> H f64[9], inlier count              */
 int gt_find_homography(gt_handle h, const float* src, const float* dst, int n, float thr, int max_iter,
                        double* out_H, int32_t* out_inliers, void* stream);
 

@@ -215,8 +215,13 @@ def test_intermediate_features_close(small_engine):
     taps = {}
     with torch.no_grad():
         m(prepost.preprocess(list(frames), 384), taps)
+    from geotrax_b200 import GtError
     for layer in (0, 1, 2, 4, 6, 9, 12, 15, 18, 21):
-        got = eng.act_to_f32(eng.feature(layer, 1))
+        try:
+            got = eng.act_to_f32(eng.feature(layer, 1))
+        except GtError:
+            assert layer == 1, f"layer {layer} has no buffer"   # model.1 is chained into model.2.cv1: its output never exists in HBM
+            continue
         ref = taps[str(layer)].permute(0, 2, 3, 1).numpy()
         rel = np.linalg.norm(got - ref) / np.linalg.norm(ref)
         print("layer", layer, "rel", rel)
@@ -294,3 +299,30 @@ def test_detect_end_to_end_matches_oracle_on_same_raw(small_engine):
         for a in common:
             assert got_by[a][5] == ref_by[a][5]
             np.testing.assert_allclose(got_by[a][:5], ref_by[a][:5], rtol=2e-4, atol=2e-3)
+
+
+def test_chained_conv_equals_two_launches():
+    """model.1 + model.2.cv1 as one chained kernel (GT_CHAIN=1, the default) against the two-launch form (GT_CHAIN=0): same 16-bit
+    intermediate, same accumulation order -> the C2f output and the raw head must agree to the last bit."""
+    import os
+    from conftest import _make_engine
+    frames = _frames(2, 512, 768, seed=9)
+    outs = []
+    for chain in ("1", "0"):
+        old = os.environ.get("GT_CHAIN")
+        os.environ["GT_CHAIN"] = chain
+        try:
+            eng = _make_engine("fp16")
+        finally:
+            if old is None:
+                os.environ.pop("GT_CHAIN")
+            else:
+                os.environ["GT_CHAIN"] = old
+        eng.preprocess(frames)
+        eng.detect(2, conf=0.25)
+        outs.append((eng.feature(2, 2).copy(), eng.raw_head(2).copy(), eng.conv_kernel_info()[0]))
+        eng.close()
+    (f1, r1, n1), (f0, r0, n0) = outs
+    assert n1 == n0 - 1, f"chained graph should have one conv launch less ({n1} vs {n0})"
+    assert np.array_equal(f1, f0), f"C2f output differs: {np.mean(f1 != f0):.2e} of the values"
+    assert np.array_equal(r1, r0)
