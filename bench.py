@@ -433,8 +433,9 @@ def main():
     ap.add_argument("--ingest", default="bgr24", choices=["bgr24", "nv12"],
                     help="host frame format of the end-to-end leg: bgr24 = what the reference's reader delivers (default, the headline); "
                          "nv12 = decoder format (SURVEY 8f rank 1), half the PCIe bytes, converted on the device")
-    ap.add_argument("--engines", type=int, default=1, help="handles per GPU taking the batches round-robin (2: the other handle's conv stack fills the SMs during "
-                    "a batch's low-occupancy stabiliser tail, +3-4 %; stage times and the roofline then include the interference, so 1 is the default)")
+    ap.add_argument("--engines", type=int, default=2, help="handles per GPU taking the batches round-robin (pipeline.run_range): while one batch is in its low-occupancy "
+                    "stabiliser tail (selection, matching, RANSAC: 16-128 blocks) the other handle's conv CTAs fill the SMs: +6.8 %% frames/s with two (r2 final build; "
+                    "the conv-stack time the roofline uses is unchanged: 3.27 ms either way).  1 = a single handle; stage_ms_per_step is only meaningful then")
     ap.add_argument("--seconds", type=float, default=15.0, help="--workload flight: keep running whole `--steps` rounds until this much wall time has passed")
     ap.add_argument("--workload", default="fused", choices=["fused", "detect", "stabilize", "obb", "flight"],
                     help="fused = BASELINE configs[1]+[2] (default, the headline); detect = configs[1] (YOLOv8s detect+NMS only); "

@@ -664,6 +664,35 @@ __global__ void __launch_bounds__(64) nms_mask_kernel(const float* __restrict__ 
   mask[((size_t)b * n_cap + i) * words + cb] = bits;
 }
 
+// one kept candidate -> its det_out row: source-frame pixels (scale_boxes + clip / regularize_rboxes) or letterboxed pixels (scale == 0)
+__device__ __forceinline__ void nms_emit_row(const float* __restrict__ bx, float cf, float cl, int rotated, int scale, float pad_x, float pad_y, float gain,
+                                             float fw, float fh, float* __restrict__ o) {
+  if (!rotated) {
+    float x1 = bx[0], y1 = bx[1], x2 = bx[2], y2 = bx[3];
+    if (scale) {
+      x1 = __fdiv_rn(__fsub_rn(x1, pad_x), gain); y1 = __fdiv_rn(__fsub_rn(y1, pad_y), gain);
+      x2 = __fdiv_rn(__fsub_rn(x2, pad_x), gain); y2 = __fdiv_rn(__fsub_rn(y2, pad_y), gain);
+      x1 = fminf(fmaxf(x1, 0.f), fw); x2 = fminf(fmaxf(x2, 0.f), fw);
+      y1 = fminf(fmaxf(y1, 0.f), fh); y2 = fminf(fmaxf(y2, 0.f), fh);
+    }
+    o[0] = x1; o[1] = y1; o[2] = x2; o[3] = y2; o[4] = cf; o[5] = cl;
+  } else {
+    float x = bx[0], y = bx[1], w = bx[2], h = bx[3], t = bx[4];
+    if (scale) {
+      const float PI = 3.14159265358979323846f;
+      float tm = fmodf(t, PI);
+      if (tm < 0.f) tm += PI;
+      const bool swap = tm >= PI * 0.5f;  // regularize_rboxes
+      const float w2 = swap ? h : w, h2 = swap ? w : h;
+      float t2 = fmodf(t, PI * 0.5f);
+      if (t2 < 0.f) t2 += PI * 0.5f;
+      x = __fdiv_rn(__fsub_rn(x, pad_x), gain); y = __fdiv_rn(__fsub_rn(y, pad_y), gain);
+      w = __fdiv_rn(w2, gain); h = __fdiv_rn(h2, gain); t = t2;
+    }
+    o[0] = x; o[1] = y; o[2] = w; o[3] = h; o[4] = t; o[5] = cf; o[6] = cl;
+  }
+}
+
 // ---- sweep + output.  HBB: greedy (a suppressed box does not suppress).  Rotated: Fast-NMS (every higher box suppresses).
 // Writes det_out rows in source-frame pixels (scale_boxes + clip) or letterboxed pixels (scale == 0).
 __global__ void __launch_bounds__(512) nms_sweep_kernel(const unsigned long long* __restrict__ mask, const float* __restrict__ sbox,
@@ -732,34 +761,8 @@ __global__ void __launch_bounds__(512) nms_sweep_kernel(const unsigned long long
       const int si = s_kept[k];
       const unsigned long long key = keys[(size_t)b * key_stride + si];
       const int a = (int)(0xFFFFFFFFu - (uint32_t)(key & 0xFFFFFFFFull));
-      const float* bx = cand_box + ((size_t)b * A + a) * 5;
-      float* o = det_out + ((size_t)b * max_det + s_total + k) * row;
-      const float cf = cand_conf[(size_t)b * A + a];
-      const float cl = (float)cand_cls[(size_t)b * A + a];
-      if (!rotated) {
-        float x1 = bx[0], y1 = bx[1], x2 = bx[2], y2 = bx[3];
-        if (scale) {
-          x1 = __fdiv_rn(__fsub_rn(x1, pad_x), gain); y1 = __fdiv_rn(__fsub_rn(y1, pad_y), gain);
-          x2 = __fdiv_rn(__fsub_rn(x2, pad_x), gain); y2 = __fdiv_rn(__fsub_rn(y2, pad_y), gain);
-          x1 = fminf(fmaxf(x1, 0.f), fw); x2 = fminf(fmaxf(x2, 0.f), fw);
-          y1 = fminf(fmaxf(y1, 0.f), fh); y2 = fminf(fmaxf(y2, 0.f), fh);
-        }
-        o[0] = x1; o[1] = y1; o[2] = x2; o[3] = y2; o[4] = cf; o[5] = cl;
-      } else {
-        float x = bx[0], y = bx[1], w = bx[2], h = bx[3], t = bx[4];
-        if (scale) {
-          const float PI = 3.14159265358979323846f;
-          float tm = fmodf(t, PI);
-          if (tm < 0.f) tm += PI;
-          const bool swap = tm >= PI * 0.5f;  // regularize_rboxes
-          const float w2 = swap ? h : w, h2 = swap ? w : h;
-          float t2 = fmodf(t, PI * 0.5f);
-          if (t2 < 0.f) t2 += PI * 0.5f;
-          x = __fdiv_rn(__fsub_rn(x, pad_x), gain); y = __fdiv_rn(__fsub_rn(y, pad_y), gain);
-          w = __fdiv_rn(w2, gain); h = __fdiv_rn(h2, gain); t = t2;
-        }
-        o[0] = x; o[1] = y; o[2] = w; o[3] = h; o[4] = t; o[5] = cf; o[6] = cl;
-      }
+      nms_emit_row(cand_box + ((size_t)b * A + a) * 5, cand_conf[(size_t)b * A + a], (float)cand_cls[(size_t)b * A + a], rotated, scale, pad_x, pad_y, gain,
+                   fw, fh, det_out + ((size_t)b * max_det + s_total + k) * row);
       det_keep[(size_t)b * max_det + s_total + k] = a;
     }
     __syncthreads();
@@ -767,6 +770,130 @@ __global__ void __launch_bounds__(512) nms_sweep_kernel(const unsigned long long
     __syncthreads();
   }
   if (threadIdx.x == 0) det_count[b] = s_total;
+}
+
+// ---- the common case in ONE launch: frames with at most kNmsSmall candidates (the default flight has ~320) ------------------------
+// sort (bitonic, shared memory) -> gather -> suppression bit matrix (shared memory) -> sweep -> rows, one block per frame: the same
+// arithmetic and the same order as sort_keys / nms_gather / nms_mask / nms_sweep (iou_gt / probiou, greedy for HBB, Fast-NMS for OBB),
+// so keep indices stay bit-exact; it replaces four launches whose cost was launch geometry (65,536 mostly empty mask blocks for the
+// 4096-candidate capacity) and global-memory round trips.  Frames with more candidates raise `over[b]` and the batch falls back to
+// the multi-launch path.
+constexpr int kNmsSmall = 1024, kNmsSmallWords = kNmsSmall / 64;
+constexpr size_t kNmsSmallSmem = (size_t)kNmsSmall * 8 /*keys*/ + (size_t)kNmsSmall * 5 * 4 /*boxes*/ + (size_t)kNmsSmall * kNmsSmallWords * 8 /*mask*/;
+__global__ void __launch_bounds__(1024) nms_small_kernel(unsigned long long* __restrict__ keys, int key_stride, const int* __restrict__ count, int max_nms, int A,
+                                                         const float* __restrict__ cand_box, const float* __restrict__ cand_conf,
+                                                         const int* __restrict__ cand_cls, int agnostic, int rotated, float thr, int max_det, int scale,
+                                                         float pad_x, float pad_y, float gain, float fw, float fh, float* __restrict__ det_out,
+                                                         int* __restrict__ det_count, int* __restrict__ det_keep, int* __restrict__ over) {
+  extern __shared__ __align__(16) unsigned char s_raw[];
+  unsigned long long* s_keys = reinterpret_cast<unsigned long long*>(s_raw);
+  float* s_box = reinterpret_cast<float*>(s_raw + (size_t)kNmsSmall * 8);
+  unsigned long long* s_mask = reinterpret_cast<unsigned long long*>(s_raw + (size_t)kNmsSmall * 8 + (size_t)kNmsSmall * 5 * 4);
+  __shared__ unsigned long long s_removed[kNmsSmallWords];
+  __shared__ int s_kept[kNmsSmall];
+  __shared__ int s_total;
+  const int b = blockIdx.x;
+  const int nall = min(count[b], key_stride);
+  const int n = min(nall, max_nms);
+  if (nall > kNmsSmall) {               // (sorting needs every candidate, not only the max_nms best)
+    if (threadIdx.x == 0) { over[b] = 1; det_count[b] = 0; }
+    return;
+  }
+  unsigned long long* k = keys + (size_t)b * key_stride;
+  int np2 = 1;
+  while (np2 < nall) np2 <<= 1;
+  for (int i = threadIdx.x; i < np2; i += blockDim.x) s_keys[i] = i < nall ? k[i] : 0ull;
+  __syncthreads();
+  for (int size = 2; size <= np2; size <<= 1) {
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      for (int t = threadIdx.x; t < (np2 >> 1); t += blockDim.x) {
+        const int lo = 2 * t - (t & (stride - 1));
+        const int hi = lo + stride;
+        const bool desc = ((lo & size) == 0);
+        const unsigned long long a = s_keys[lo], c = s_keys[hi];
+        if ((a < c) == desc) { s_keys[lo] = c; s_keys[hi] = a; }
+      }
+      __syncthreads();
+    }
+  }
+  for (int i = threadIdx.x; i < nall; i += blockDim.x) k[i] = s_keys[i];     // (the sorted order stays visible, as after sort_keys_kernel)
+  // gather (class offset as in nms_gather_kernel)
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const int a = (int)(0xFFFFFFFFu - (uint32_t)(s_keys[i] & 0xFFFFFFFFull));
+    const float* src = cand_box + ((size_t)b * A + a) * 5;
+    const float c = agnostic ? 0.f : __fmul_rn((float)cand_cls[(size_t)b * A + a], 7680.0f);
+    float* d = s_box + (size_t)i * 5;
+    d[0] = __fadd_rn(src[0], c); d[1] = __fadd_rn(src[1], c);
+    if (rotated) { d[2] = src[2]; d[3] = src[3]; } else { d[2] = __fadd_rn(src[2], c); d[3] = __fadd_rn(src[3], c); }
+    d[4] = src[4];
+  }
+  const int w_used = (n + 63) >> 6;
+  if (threadIdx.x < kNmsSmallWords) s_removed[threadIdx.x] = 0ull;
+  if (threadIdx.x == 0) s_total = 0;
+  __syncthreads();
+  // suppression bits: word (i, cb), cb >= i / 64, bit j = box i suppresses box cb * 64 + j (j beyond i only)
+  for (int t = threadIdx.x; t < n * w_used; t += blockDim.x) {
+    const int i = t / w_used, cb = t - i * w_used;
+    unsigned long long bits = 0ull;
+    if (cb >= (i >> 6)) {
+      const float* me = s_box + (size_t)i * 5;
+      const int ncol = min(64, n - cb * 64);
+      const int start = (cb == (i >> 6)) ? (i & 63) + 1 : 0;
+      for (int j = start; j < ncol; ++j) {
+        const float* other = s_box + (size_t)(cb * 64 + j) * 5;
+        const bool sup = rotated ? (probiou(me, other) >= thr) : iou_gt(me, other, thr);
+        if (sup) bits |= 1ull << j;
+      }
+    }
+    s_mask[(size_t)i * kNmsSmallWords + cb] = bits;
+  }
+  __syncthreads();
+  // sweep: chunk by chunk, the serial part on one thread (shared memory only)
+  __shared__ int s_nk;
+  for (int chunk = 0; chunk < w_used; ++chunk) {
+    if (s_total >= max_det) break;
+    if (threadIdx.x == 0) {
+      unsigned long long rem = s_removed[chunk];
+      int nk = 0;
+      const int lim = min(64, n - chunk * 64);
+      for (int j = 0; j < lim; ++j) {
+        const unsigned long long dg = s_mask[(size_t)(chunk * 64 + j) * kNmsSmallWords + chunk];
+        if (!((rem >> j) & 1ull)) {
+          if (s_total + nk < max_det) s_kept[s_total + nk++] = chunk * 64 + j;
+          if (!rotated) rem |= dg;
+        }
+        if (rotated) rem |= dg;
+      }
+      s_nk = nk;
+    }
+    __syncthreads();
+    const int nk = s_nk, base = s_total;
+    if (!rotated) {
+      for (int wd = chunk + 1 + threadIdx.x; wd < w_used; wd += blockDim.x) {
+        unsigned long long acc = 0ull;
+        for (int q = 0; q < nk; ++q) acc |= s_mask[(size_t)s_kept[base + q] * kNmsSmallWords + wd];
+        s_removed[wd] |= acc;
+      }
+    } else {
+      const int lim = min(64, n - chunk * 64);
+      for (int wd = chunk + 1 + threadIdx.x; wd < w_used; wd += blockDim.x) {
+        unsigned long long acc = 0ull;
+        for (int j = 0; j < lim; ++j) acc |= s_mask[(size_t)(chunk * 64 + j) * kNmsSmallWords + wd];
+        s_removed[wd] |= acc;
+      }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) s_total = base + nk;
+    __syncthreads();
+  }
+  const int total = s_total, row = rotated ? 7 : 6;
+  for (int q = threadIdx.x; q < total; q += blockDim.x) {
+    const int a = (int)(0xFFFFFFFFu - (uint32_t)(s_keys[s_kept[q]] & 0xFFFFFFFFull));
+    nms_emit_row(cand_box + ((size_t)b * A + a) * 5, cand_conf[(size_t)b * A + a], (float)cand_cls[(size_t)b * A + a], rotated, scale, pad_x, pad_y, gain, fw,
+                 fh, det_out + ((size_t)b * max_det + q) * row);
+    det_keep[(size_t)b * max_det + q] = a;
+  }
+  if (threadIdx.x == 0) det_count[b] = total;
 }
 
 int nms_run(gt_engine* e, const float* pred_dev, int B, int A, int nc, int rotated, float conf, float iou, int agnostic,
@@ -790,11 +917,27 @@ int nms_run(gt_engine* e, const float* pred_dev, int B, int A, int nc, int rotat
     GT_CUDA(e, cudaMemcpyAsync(e->nonfinite_host, e->nonfinite_dev, sizeof(int), cudaMemcpyDeviceToHost, st));   // cumulative counter -> pinned mirror
   }
   e->launches++;
+  const int max_nms = e->cfg.max_nms;
+  int* overflow = e->det_keep + (size_t)e->cfg.max_batch * e->cfg.max_det;  // [max_batch] tail of det_keep
+  const float fw0 = (float)e->cfg.frame_w, fh0 = (float)e->cfg.frame_h;
+  std::vector<int> ov(B);
+  if (e->nms_fused && max_det <= kNmsSmall) {
+    // the common case: every frame has at most kNmsSmall candidates -> one launch does sort + mask + sweep per frame
+    GT_CUDA(e, cudaMemsetAsync(overflow, 0, sizeof(int) * B, st));
+    nms_small_kernel<<<B, 1024, kNmsSmallSmem, st>>>(e->cand_key, key_stride, e->cand_count, max_nms, A, e->cand_box, e->cand_conf, e->cand_cls, agnostic, rotated,
+                                                     iou, max_det, scale_to_frame ? 1 : 0, (float)e->pad_left, (float)e->pad_top, e->gain, fw0, fh0, e->det_out,
+                                                     e->det_count, e->det_keep, overflow);
+    e->launches++;
+    GT_CUDA(e, cudaGetLastError());
+    GT_CUDA(e, cudaMemcpyAsync(ov.data(), overflow, sizeof(int) * B, cudaMemcpyDeviceToHost, st));
+    GT_CUDA(e, cudaStreamSynchronize(st));
+    bool any = false;
+    for (int b = 0; b < B; ++b) any |= ov[b] != 0;
+    if (!any) return GT_OK;
+  }
   sort_keys_kernel<<<B, 1024, 4096 * sizeof(unsigned long long), st>>>(e->cand_key, key_stride, e->cand_count);
   e->launches++;
-  const int max_nms = e->cfg.max_nms;
   // pass 1: batched, capacity nms_cap per image
-  int* overflow = e->det_keep + (size_t)e->cfg.max_batch * e->cfg.max_det;  // [max_batch] tail of det_keep
   GT_CUDA(e, cudaMemsetAsync(overflow, 0, sizeof(int) * B, st));
   auto run_pass = [&](int b0, int nb, int n_cap) -> int {
     const int words = (n_cap + 63) / 64;
@@ -816,7 +959,6 @@ int nms_run(gt_engine* e, const float* pred_dev, int B, int A, int nc, int rotat
   };
   GT_TRY(run_pass(0, B, e->nms_cap));
   // pass 2 (rare): images with more than nms_cap candidates, one at a time with the full max_nms capacity
-  std::vector<int> ov(B);
   GT_CUDA(e, cudaMemcpyAsync(ov.data(), overflow, sizeof(int) * B, cudaMemcpyDeviceToHost, st));
   GT_CUDA(e, cudaStreamSynchronize(st));
   for (int b = 0; b < B; ++b)
@@ -1078,6 +1220,7 @@ void add_c2f_desc(gt_engine* e, const std::string& pre, int c1, int c2, int n) {
 }  // namespace
 
 int detector_build(gt_engine* e) {
+  GT_CUDA(e, cudaFuncSetAttribute(nms_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kNmsSmallSmem));
   const int B = e->cfg.max_batch, nc = e->cfg.nc;
   const bool obb = e->cfg.task == GT_TASK_OBB;
   const int c1 = 32, c2 = 64, c3 = 128, c4 = 256, c5 = 512;  // YOLOv8 s-scale widths

@@ -79,7 +79,7 @@ def run_range(engine, get_frames: Callable[[int, int], np.ndarray], lo: int, hi:
     else:
         # Several engines (handles on the same GPU, each with its own workspaces and streams) take the batches round-robin: while one
         # batch is in its low-occupancy stabiliser tail (NMS, selection, RANSAC: 16-128 blocks) the other engine's convolution CTAs
-        # fill the SMs.  Measured +3.8 % with two engines (tools/two_engine_probe.py); one engine is the default.
+        # fill the SMs.  Measured +6.8 % with two engines on the final round-2 build (3,491 -> 3,730 frames/s; bench.py runs two).
         ne = len(engines)
         for e in engines:
             if getattr(e, "_pipeline_outs", None) is None:   # two pinned output sets per engine, allocated once
