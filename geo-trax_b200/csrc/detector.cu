@@ -604,6 +604,7 @@ __device__ __forceinline__ bool iou_gt(const float* a, const float* b, float thr
   const float xx1 = fmaxf(a[0], b[0]), yy1 = fmaxf(a[1], b[1]);
   const float xx2 = fminf(a[2], b[2]), yy2 = fminf(a[3], b[3]);
   const float w = fmaxf(0.f, __fsub_rn(xx2, xx1)), h = fmaxf(0.f, __fsub_rn(yy2, yy1));
+  if (thr >= 0.f && (!(w > 0.f) || !(h > 0.f))) return false;   // disjoint boxes (almost every pair): inter = 0 -> 0 / union (or NaN) > thr is false; skips the IEEE division
   const float inter = __fmul_rn(w, h);
   const float aa = __fmul_rn(__fsub_rn(a[2], a[0]), __fsub_rn(a[3], a[1]));
   const float ab = __fmul_rn(__fsub_rn(b[2], b[0]), __fsub_rn(b[3], b[1]));
