@@ -130,22 +130,31 @@ __global__ void __launch_bounds__(128) pyr_resize_kernel(uint8_t* __restrict__ p
       sft[i][r] = 8 * (int)(p & 3);
     }
   }
+  // per output column: a byte-permute selector that picks the two source bytes (a[k], min(a[k] + 1, sw - 1)) out of the 8-byte window, and the
+  // two horizontal weights as a 16-bit pair -> one PRMT + one IDP.2A per source row instead of 64-bit shifts, masks and two IMADs
+  uint32_t sel[4], cw[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int o0 = a[k] - a[0], o1 = min(a[k] + 1, sw - 1) - a[0];     // 0 .. 7
+    sel[k] = (uint32_t)o0 | ((uint32_t)o1 << 4);                       // (bytes 2, 3 of the result are don't-care: dp2a_lo reads bytes 0, 1)
+    cw[k] = (uint32_t)(256 - c1v[k]) | ((uint32_t)c1v[k] << 16);
+  }
 #pragma unroll
   for (int i = 0; i < kResizeRows; ++i) {
     const int y = y0 + i;
     if (y >= dh) break;
-    unsigned long long win[2];
+    uint32_t lo[2], hi2[2];
 #pragma unroll
-    for (int r = 0; r < 2; ++r)
-      win[r] = (unsigned long long)__funnelshift_r(w[i][r][0], w[i][r][1], sft[i][r]) | ((unsigned long long)__funnelshift_r(w[i][r][1], w[i][r][2], sft[i][r]) << 32);
+    for (int r = 0; r < 2; ++r) {
+      lo[r] = __funnelshift_r(w[i][r][0], w[i][r][1], sft[i][r]);
+      hi2[r] = __funnelshift_r(w[i][r][1], w[i][r][2], sft[i][r]);
+    }
     const int cy1 = cy[i], cy0 = 256 - cy1;
     uint32_t packed = 0;
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-      const int o0 = (a[k] - a[0]) * 8, o1 = (min(a[k] + 1, sw - 1) - a[0]) * 8;
-      const int c1 = c1v[k], c0 = 256 - c1;
-      const int h0 = (int)((win[0] >> o0) & 0xFF) * c0 + (int)((win[0] >> o1) & 0xFF) * c1;
-      const int h1 = (int)((win[1] >> o0) & 0xFF) * c0 + (int)((win[1] >> o1) & 0xFF) * c1;
+      const int h0 = (int)__dp2a_lo(cw[k], __byte_perm(lo[0], hi2[0], sel[k]), 0u);
+      const int h1 = (int)__dp2a_lo(cw[k], __byte_perm(lo[1], hi2[1], sel[k]), 0u);
       int v = (h0 * cy0 + h1 * cy1 + 32768) >> 16;
       if (MASK && v <= 254) v = 0;
       packed |= (uint32_t)v << (8 * k);
