@@ -125,6 +125,54 @@ class FakeEngine:
 def _get_frames(lo, hi):
     return np.arange(lo, hi, dtype=np.uint8).reshape(-1, 1, 1, 1) * np.ones((1, 2, 2, 3), np.uint8)
 
+class FakeAsyncEngine(FakeEngine):
+    """FakeEngine with the asynchronous entry points (tickets, wait): drives the pipelined branch of run_range on the CPU."""
+
+    def __init__(self):
+        super().__init__()
+        self.in_flight, self.max_in_flight, self.batches = {}, 0, 0
+
+    def alloc_outputs(self, pinned=False):
+        return super().alloc_outputs()
+
+    def extract_batch(self, frames, first_is_reference=False, out=None, sync=True, mask_boxes=None, **kw):
+        if sync:
+            return super().extract_batch(frames, first_is_reference=first_is_reference, out=out)
+        t = self.batches % 2
+        assert t not in self.in_flight, "a ticket was reused before gt_wait"
+        assert not any(o is out for o in self.in_flight.values()), "an output set was reused while its batch was in flight"
+        self.in_flight[t] = out
+        self.max_in_flight = max(self.max_in_flight, len(self.in_flight))
+        self.batches += 1
+        # (results are produced at wait time: reading them earlier would be a bug in the driver)
+        self._deferred = getattr(self, "_deferred", {})
+        self._deferred[t] = (frames.copy(), out)
+        return out, t
+
+    def wait(self, ticket):
+        frames, out = self._deferred.pop(ticket)
+        super().extract_batch(frames, out=out)
+        del self.in_flight[ticket]
+
+
+@pytest.mark.parametrize("n_frames,n_engines", [(23, 2), (23, 3), (5, 2), (1, 2)])
+def test_run_range_round_robin_over_several_engines(n_frames, n_engines):
+    """pipeline.run_range with a LIST of handles on one GPU (the bench default is two): batches go round-robin, at most two tickets per
+    handle are in flight, no output set is reused before its wait, and the records equal a single handle's."""
+    from geotrax_b200 import pipeline
+    single = pipeline.run_range(FakeEngine(), _get_frames, 0, n_frames, 0, batch=4)
+    engines = [FakeAsyncEngine() for _ in range(n_engines)]
+    multi = pipeline.run_range(engines, _get_frames, 0, n_frames, 0, batch=4)
+    for k in ("frame", "count", "status", "stats", "H"):
+        assert np.array_equal(single[k], multi[k]), k
+    for i in range(n_frames):
+        c = int(single["count"][i])
+        assert np.array_equal(single["boxes"][i, :c], multi["boxes"][i, :c]) and np.array_equal(single["boxes_stab"][i, :c], multi["boxes_stab"][i, :c])
+    assert all(e.max_in_flight <= 2 and not e.in_flight for e in engines)
+    n_batches = (n_frames + 3) // 4
+    assert sorted(e.batches for e in engines) == sorted((n_batches + n_engines - 1 - j) // n_engines for j in range(n_engines))
+
+
 
 def _worker(rank, world, port, n_frames, q):
     import torch.distributed as dist
