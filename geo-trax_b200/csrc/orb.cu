@@ -269,23 +269,32 @@ __global__ void __launch_bounds__(256, 5) fast_kernel(const uint8_t* __restrict_
                                                    unsigned int* __restrict__ cand, uint8_t* __restrict__ cscore, size_t cand_slab,
                                                    int* __restrict__ counts, int tile_first) {
   __shared__ __align__(16) uint8_t s_img[FT_SH][FT_SW];
-  __shared__ __align__(4) uint8_t s_sc[FT_Y + 2][FT_X + 2];
+  __shared__ __align__(16) uint8_t s_sc_buf[((FT_Y + 2) * (FT_X + 2) + 15) & ~15];   // corner scores, cleared with 16-byte stores
+  uint8_t (*s_sc)[FT_X + 2] = reinterpret_cast<uint8_t (*)[FT_X + 2]>(s_sc_buf);
+  __shared__ int s_geo[5];
   __shared__ unsigned short s_cand[FT_ROWS * FT_G];   // (task << 4 | pixel mask) of the groups that pass the compass test
   __shared__ unsigned short s_list[FT_LIST];          // corner positions sy * (FT_X + 2) + sx
   __shared__ int s_na, s_nl, s_n, s_base;
   __shared__ unsigned int s_xy[FT_X * FT_Y / 4];
   __shared__ uint8_t s_s[FT_X * FT_Y / 4];
-  const int gtile = (int)blockIdx.x + tile_first;   // (a launch may cover a sub-range of the levels: orb_fast)
-  int level = 0;
+  // tile -> (level, tile row, tile column): one thread does the search and the division, the block reads the five numbers (the per-thread
+  // form was 6 % of the kernel's instructions)
+  if (threadIdx.x == 0) {
+    const int gtile = (int)blockIdx.x + tile_first;   // (a launch may cover a sub-range of the levels: orb_fast)
+    int lv = 0;
 #pragma unroll
-  for (int l = 1; l < GT_ORB_LEVELS; ++l) level += gtile >= fl.tile0[l];
-  const int w = fl.w[level], h = fl.h[level];
-  const int tile = gtile - fl.tile0[level];
-  const int by = tile / fl.tiles_x[level], bx = tile - by * fl.tiles_x[level];
+    for (int l = 1; l < GT_ORB_LEVELS; ++l) lv += gtile >= fl.tile0[l];
+    const int tl = gtile - fl.tile0[lv];
+    const int ty_ = tl / fl.tiles_x[lv];
+    s_geo[0] = lv; s_geo[1] = fl.w[lv]; s_geo[2] = fl.h[lv]; s_geo[3] = ty_; s_geo[4] = tl - ty_ * fl.tiles_x[lv];
+    s_n = 0; s_nl = 0; s_na = 0;
+  }
+  for (int i = threadIdx.x; i < (int)(sizeof(s_sc_buf) / 16); i += 256) reinterpret_cast<uint4*>(s_sc_buf)[i] = make_uint4(0u, 0u, 0u, 0u);
+  __syncthreads();
+  const int level = s_geo[0], w = s_geo[1], h = s_geo[2], by = s_geo[3], bx = s_geo[4];
   const int slot = slot0 + blockIdx.y;
   const uint8_t* im = img + (size_t)slot * slab + fl.off[level];
   const int x0 = kEdge + bx * FT_X, y0 = kEdge + by * FT_Y;
-  if (threadIdx.x == 0) { s_n = 0; s_nl = 0; s_na = 0; }
   // phase 0: staged word (ty, tq) = image bytes gx = x0 - 5 + 4 tq .. + 3 of row gy = y0 - 4 + ty (rows clamped into the image;
   // columns outside it only feed positions that are never tested).  All loads of a thread are issued before the first use.
   {
@@ -315,8 +324,8 @@ __global__ void __launch_bounds__(256, 5) fast_kernel(const uint8_t* __restrict_
       if (i < kWords) reinterpret_cast<uint32_t*>(&s_img[0][0])[i] = __funnelshift_r(v0[it], v1[it], sh[it]);
     }
   }
-  for (int i = threadIdx.x; i < (FT_Y + 2) * (FT_X + 2) / 2; i += 256) reinterpret_cast<unsigned short*>(&s_sc[0][0])[i] = 0;
   __syncthreads();
+  const bool right_edge = x0 + FT_X + 1 > w - kEdge;   // only the last tile column can run past the tested range
   const uint32_t thr4 = 0x01010101u * (uint32_t)kFastThr;
   // tested positions: gx in [kEdge - 1, w - kEdge] (candidates + their 3x3 neighbours), same for gy
   // phase 1a: compass quick-reject, four pixels per thread
@@ -335,10 +344,13 @@ __global__ void __launch_bounds__(256, 5) fast_kernel(const uint8_t* __restrict_
         const uint32_t br = two_of_four(rc4.brighter(r0), rc4.brighter(r4), rc4.brighter(r8), rc4.brighter(r12));
         const uint32_t dk = two_of_four(rc4.darker(r0), rc4.darker(r4), rc4.darker(r8), rc4.darker(r12));
         uint32_t m = (br | dk) & 0x80808080u;
-        // validity of the four pixels (sx = 4 g + j): j in [jlo, jhi]
-        const int gx = x0 - 1 + 4 * g;
-        const int jlo = max(kEdge - 1 - gx, 0), jhi = min(min(w - kEdge - gx, FT_X + 1 - 4 * g), 3);
-        if (jlo > 0 || jhi < 3) m = jhi < jlo ? 0u : (m & (0xFFFFFFFFu << (8 * jlo)) & (0xFFFFFFFFu >> (8 * (3 - jhi))));
+        // validity of the four pixels (sx = 4 g + j): j in [0, jhi] -- the left limit never cuts (gx >= x0 - 1 >= kEdge - 1); the right one
+        // only in the last group of a row (two of its four pixels lie beyond the tile's apron) and in the last tile column
+        if (g == FT_G - 1 || right_edge) {
+          const int gx = x0 - 1 + 4 * g;
+          const int jhi = min(min(w - kEdge - gx, FT_X + 1 - 4 * g), 3);
+          if (jhi < 3) m = jhi < 0 ? 0u : (m & (0xFFFFFFFFu >> (8 * (3 - jhi))));
+        }
         pass = m;
       }
     }
