@@ -377,14 +377,14 @@ __global__ void __launch_bounds__(256) maxpool5_kernel(const bf16* __restrict__ 
 // 8-channel group, separable (row max, column max) in shared memory; the plane of a 34 x 60 level is 32 KB.  Replaces three
 // dependent launches that were pure latency (33 us each for an 8 MB tensor).
 template <typename T2>
-__global__ void __launch_bounds__(256) sppf_pool3_kernel(bf16* __restrict__ buf, int ctot, int coff, int C, int H, int W) {
+__global__ void __launch_bounds__(1024) sppf_pool3_kernel(bf16* __restrict__ buf, int ctot, int coff, int C, int H, int W) {
   extern __shared__ __align__(16) uint4 s_pool[];
   uint4* A = s_pool;
   uint4* R = s_pool + (size_t)H * W;
   const int cg = blockIdx.x, b = blockIdx.y;
   const int n = H * W;
   bf16* base = buf + (size_t)b * n * ctot + coff + cg * 8;
-  for (int i = threadIdx.x; i < n; i += 256) A[i] = __ldg(reinterpret_cast<const uint4*>(base + (size_t)i * ctot));
+  for (int i = threadIdx.x; i < n; i += blockDim.x) A[i] = __ldg(reinterpret_cast<const uint4*>(base + (size_t)i * ctot));
   __syncthreads();
   auto vmax = [](uint4 a, const uint4& c) {
     T2* pa = reinterpret_cast<T2*>(&a);
@@ -394,7 +394,7 @@ __global__ void __launch_bounds__(256) sppf_pool3_kernel(bf16* __restrict__ buf,
     return a;
   };
   for (int stage = 1; stage <= 3; ++stage) {
-    for (int i = threadIdx.x; i < n; i += 256) {       // row pass
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {       // row pass
       const int y = i / W, x = i - y * W;
       uint4 m = A[i];
       for (int dx = -2; dx <= 2; ++dx)
@@ -402,7 +402,7 @@ __global__ void __launch_bounds__(256) sppf_pool3_kernel(bf16* __restrict__ buf,
       R[i] = m;
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < n; i += 256) {       // column pass -> slice `stage`, and the next stage's input
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {       // column pass -> slice `stage`, and the next stage's input
       const int y = i / W;
       uint4 m = R[i];
       for (int dy = -2; dy <= 2; ++dy)
@@ -1525,10 +1525,10 @@ int detector_forward(gt_engine* e, int B, cudaStream_t st) {
       dim3 g((unsigned)(v.C / 8), (unsigned)B);
       if (e->cfg.act_dtype == GT_ACT_FP16) {
         GT_CUDA(e, cudaFuncSetAttribute(sppf_pool3_kernel<__half2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        sppf_pool3_kernel<__half2><<<g, 256, smem, st>>>(v.ptr, v.ctot, v.coff, v.C, v.H, v.W);
+        sppf_pool3_kernel<__half2><<<g, 1024, smem, st>>>(v.ptr, v.ctot, v.coff, v.C, v.H, v.W);
       } else {
         GT_CUDA(e, cudaFuncSetAttribute(sppf_pool3_kernel<__nv_bfloat162>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        sppf_pool3_kernel<__nv_bfloat162><<<g, 256, smem, st>>>(v.ptr, v.ctot, v.coff, v.C, v.H, v.W);
+        sppf_pool3_kernel<__nv_bfloat162><<<g, 1024, smem, st>>>(v.ptr, v.ctot, v.coff, v.C, v.H, v.W);
       }
       e->launches++;
       pi += 2;
