@@ -15,6 +15,14 @@ frames = np.stack(fl[0])
 out0 = eng.extract_batch(frames[:1], first_is_reference=True, conf=0.05, mask_boxes=eng.pack_boxes(fl[1][:1]))
 out = eng.extract_batch(frames[1:3], conf=0.05, mask_boxes=eng.pack_boxes(fl[1][1:3]))
 print("default geometry:", out["counts"].tolist(), out["status"].tolist(), out["stats"].tolist())
+# stand-alone matchers: Hamming on the tensor cores (ragged sizes) and the L2 registration matcher + robust fit
+rng = np.random.default_rng(3)
+for nq, nt in [(130, 257), (1, 1), (700, 1999)]:
+    i_, d_ = eng.match(rng.integers(0, 256, (nq, 32), dtype=np.uint8), rng.integers(0, 256, (nt, 32), dtype=np.uint8))
+for nq, nt in [(3, 2), (300, 517)]:
+    t_ = np.abs(rng.normal(size=(nt, 128))).astype(np.float32); q_ = np.abs(rng.normal(size=(nq, 128))).astype(np.float32)
+    i2, d2 = eng.match_l2(q_, t_)
+print("matchers:", i_[:2].tolist(), i2[:2].tolist())
 eng.close()
 # general geometry: odd frame size, bilinear letterbox and working image
 hw2 = (375, 667)
