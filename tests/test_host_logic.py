@@ -453,3 +453,25 @@ def test_restricted_unpickler_blocks_code_execution(tmp_path):
     except Exception:
         pass
     assert not (tmp_path / "pwned2").exists()
+
+
+def test_bench_reference_arm_contract_line():
+    """`bench.py --impl reference` (the CPU arm the driver times beside the GPU arm) runs without a GPU and prints ONE JSON line with
+    the contract's keys: same metric / unit / config.workload as the GPU arm, impl = reference, cpu_baseline.kind = port, e2e = value."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1"],
+                       capture_output=True, text=True, timeout=600, cwd=root)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1, lines
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == "4K frames/sec detect+stabilize" and d["unit"] == "frames/s"
+    assert d["higher_is_better"] is True and d["n_gpus"] == 1 and d["value"] > 0 and d["vs_baseline"] is None
+    assert "3840x2160" in d["config"]["workload"] and "model" not in d["config"]
+    cb = d["cpu_baseline"]
+    assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == d["value"] and cb["sample"]
+    assert d["e2e"] == dict(value=d["value"], unit="frames/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0)
+    assert d["gpu_launches"] == 0
