@@ -131,3 +131,22 @@ def test_estimate_homography_failure_returns_nones(reg_engine):
     assert registration.estimate_homography(flat, flat, None, engine=reg_engine, max_features=20000) == (None, None, None, None)
     with pytest.raises(NotImplementedError):
         registration.estimate_homography(flat, flat, None, engine=reg_engine, detector_name="orb")
+
+
+def test_find_homography_on_more_pairs_than_one_frame_holds(reg_engine):
+    """A single pair set may use the pair buffers of the whole batch (max_batch x 8192): 40,000 matches with 30 % outliers, 10,000 hypotheses."""
+    from geotrax_b200 import synth
+    rng = np.random.default_rng(5)
+    Hgt = synth.small_homography(rng, 2160, 3840, max_t=40.0, max_rot_deg=2.0, max_persp=1e-5)
+    n = 40_000
+    src = np.stack([rng.uniform(0, 3840, n), rng.uniform(0, 2160, n)], 1)
+    p = np.c_[src, np.ones(n)] @ Hgt.T
+    dst = p[:, :2] / p[:, 2:] + rng.normal(0, 0.4, (n, 2))
+    out = rng.random(n) < 0.30
+    dst[out] = np.stack([rng.uniform(0, 3840, out.sum()), rng.uniform(0, 2160, out.sum())], 1)
+    H, inl = reg_engine.find_homography(src.astype(np.float32), dst.astype(np.float32), 3.0, 10000)
+    assert H is not None
+    assert _corner_err(H, Hgt, 2160, 3840) < 0.1
+    assert abs(inl - int((~out).sum())) < 0.02 * n
+    with pytest.raises(Exception):
+        reg_engine.find_homography(np.zeros((16 * 8192 + 1, 2), np.float32), np.zeros((16 * 8192 + 1, 2), np.float32))
