@@ -372,7 +372,8 @@ static int detect_impl(gt_engine* e, int B, float conf, float iou, int agnostic,
   GT_TRY(detector_forward(e, B, st));
   GT_CUDA(e, cudaEventRecord(e->ev[3], st));
   GT_TRY(detector_postprocess(e, B, conf, iou, agnostic, classes_mask, st));
-  GT_CUDA(e, cudaEventRecord(e->ev[4], st));
+  if (!e->post_event_done) GT_CUDA(e, cudaEventRecord(e->ev[4], st));   // (else nms_run recorded it right behind its last kernel)
+  e->post_event_done = false;
   return GT_OK;
 }
 
@@ -887,7 +888,8 @@ static int extract_batch_impl(gt_handle e, const uint8_t* frames, int B, int fir
     GT_TRY(fork_front(2));
   }
   GT_TRY(detector_postprocess(e, B, conf, iou, agnostic, classes_mask, st));
-  GT_CUDA(e, cudaEventRecord(e->ev[4], st));
+  if (!e->post_event_done) GT_CUDA(e, cudaEventRecord(e->ev[4], st));   // (else nms_run recorded it right behind its last kernel)
+  e->post_event_done = false;
   tl_mark(2, st);
   dim3 g((unsigned)ceil_div(md, 256), (unsigned)B);
   dets_to_xywh_kernel<<<g, 256, 0, st>>>(e->det_out, e->det_count, obb ? 7 : 6, md, e->det_xywh_dev, e->det_nbox_dev, B, obb);

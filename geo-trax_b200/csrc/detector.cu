@@ -930,12 +930,15 @@ int nms_run(gt_engine* e, const float* pred_dev, int B, int A, int nc, int rotat
                                                      e->det_count, e->det_keep, overflow);
     e->launches++;
     GT_CUDA(e, cudaGetLastError());
+    // the stage's GPU work ends here: the postprocess stage time must not include the host's wait for the flags below
+    GT_CUDA(e, cudaEventRecord(e->ev[4], st));
     GT_CUDA(e, cudaMemcpyAsync(ov.data(), overflow, sizeof(int) * B, cudaMemcpyDeviceToHost, st));
     GT_CUDA(e, cudaStreamSynchronize(st));
     bool any = false;
     for (int b = 0; b < B; ++b) any |= ov[b] != 0;
-    if (!any) return GT_OK;
+    if (!any) { e->post_event_done = true; return GT_OK; }
   }
+  e->post_event_done = false;
   sort_keys_kernel<<<B, 1024, 4096 * sizeof(unsigned long long), st>>>(e->cand_key, key_stride, e->cand_count);
   e->launches++;
   // pass 1: batched, capacity nms_cap per image

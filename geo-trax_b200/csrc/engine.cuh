@@ -189,6 +189,7 @@ struct gt_engine {
   cudaEvent_t ev_done[2] = {nullptr, nullptr};   // all work and read-backs of ticket k are complete
   int async_ticket = 0;
   bool ticket_pending[2] = {false, false};   // ticket issued by gt_extract_batch_async and not yet passed to gt_wait
+  bool post_event_done = false;         // nms_run recorded ev[4] right behind the one-launch NMS (before its host-side look at the overflow flags)
   float stage_ms[4] = {0, 0, 0, 0};
   float conv_ms = 0;
   double conv_flops = 0;
