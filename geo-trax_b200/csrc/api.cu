@@ -84,6 +84,7 @@ int gt_create(const gt_config* cfg, int device, gt_handle* out) {
   if (const char* ms = getenv("GT_MASK_SPARSE")) e->mask_sparse = atoi(ms);
   if (const char* cm = getenv("GT_CHAIN")) e->chain_mode = atoi(cm);
   if (const char* nf = getenv("GT_NMS_FUSED")) e->nms_fused = atoi(nf);
+  if (const char* lp = getenv("GT_L2PROMO")) e->l2promo_128 = atoi(lp) == 128;
   if (const char* mm = getenv("GT_MATCH")) e->match_mode = std::min(2, std::max(0, atoi(mm)));
   if (const char* kb = getenv("GT_CONV_SMEM_KB")) e->conv_smem_kb = std::min(227, std::max(96, atoi(kb)));
   if (e->overlap == 1 && !getenv("GT_CONV_SMEM_KB")) e->conv_smem_kb = 200;   // room for ORB blocks beside the conv CTAs

@@ -748,8 +748,12 @@ int conv_tc_plan(gt_engine* e, ConvOp* op, const ConvPlanArgs& a) {
     cuuint32_t box[4] = {(cuuint32_t)kbe, (cuuint32_t)(p.tw * stride), (cuuint32_t)(p.th * stride), 1};
     if (p.halo) { box[1] = (cuuint32_t)(p.tw + k - 1); box[2] = (cuuint32_t)(p.th + k - 1); }
     cuuint32_t estr[4] = {1, (cuuint32_t)stride, (cuuint32_t)stride, 1};
+    // L2 promotion no wider than a box row: a 32-channel slice (64 B) of a wider pixel promoted to 128 B pulls the neighbouring
+    // slice's bytes out of DRAM as well (GT_L2PROMO=128 restores the old setting)
+    const CUtensorMapL2promotion promo = (kbe * 2 >= 128 || e->l2promo_128) ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B
+                                        : (kbe * 2 >= 64 ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B : CU_TENSOR_MAP_L2_PROMOTION_NONE);
     CUresult r = g_encode(&op->tmA, dt, 4, (void*)(in.ptr + in.coff), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
-                          CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                          promo, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     GT_CHECK(e, r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(A) failed: %d (C=%d W=%d H=%d ctot=%d box %dx%dx%d s=%d)", (int)r, cin,
              in.W, in.H, in.ctot, kbe, p.tw * stride, p.th * stride, stride);
   }

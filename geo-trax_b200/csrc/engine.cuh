@@ -66,6 +66,7 @@ struct gt_engine {
   cudaEvent_t ev_aux_a = nullptr, ev_aux_b = nullptr;
   cudaEvent_t ev_pre = nullptr, ev_front = nullptr;
   int overlap = 2;                      // GT_OVERLAP: 2 ORB front on the aux stream beside decode + NMS; 3 as 2, but the image pyramid already beside the conv stack (fills the tails between layers); 1 the whole front beside the detector (no gain: the conv CTAs own the SMs); 0 serial
+  int l2promo_128 = 0;                  // GT_L2PROMO=128: 128-byte L2 promotion for every activation tensor map (the round-1 setting)
   int nms_fused = 1;                    // GT_NMS_FUSED=0: always the multi-launch sort / gather / mask / sweep path
   int chain_mode = 1;                   // GT_CHAIN=0: model.1 and model.2.cv1 as two launches instead of one chained kernel
   int match_mode = 2;                   // GT_MATCH: 2 Hamming 2-NN as E4M3 tcgen05 GEMM (match_tc.cu), 1 the same with fp16 operands, 0 POPC kernel
