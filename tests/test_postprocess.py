@@ -1,0 +1,79 @@
+"""`geotrax_b200.postprocess` (vectorised track post-processing) against golden vectors produced by the REFERENCE's
+own functions (/root/reference/geotrax/extract.py:296-484; tests/golden/make_postprocess_golden.py).  Bit-exact: small cases are
+compared array by array, the larger ones by SHA-256 of the output bytes (their inputs are regenerated from the seed)."""
+import hashlib
+import logging
+import os
+import sys
+import time
+import types
+
+import numpy as np
+import pytest
+
+sys.path.insert(0, os.path.join(os.path.dirname(__file__), "golden"))
+from make_postprocess_golden import CASES, CFG_DIM, synth_tracks  # noqa: E402  (imports nothing from the reference at module level)
+
+GOLD = np.load(os.path.join(os.path.dirname(__file__), "golden", "postprocess_golden.npz"))
+LOG = logging.getLogger("test_postprocess")
+
+
+def _cfg(interpolate=True):
+    return dict(main=dict(args=types.SimpleNamespace(source="none.mp4", interpolate=interpolate),
+                          extraction=dict(min_track_length=3, dimension_estimation=CFG_DIM), tracker=dict(active="botsort", botsort=dict(track_buffer=30))))
+
+
+def _sha(a):
+    return np.frombuffer(hashlib.sha256(np.ascontiguousarray(a, np.float64).tobytes()).digest(), np.uint8)
+
+
+@pytest.mark.parametrize("case", CASES, ids=[c[0] for c in CASES])
+def test_every_stage_equals_the_reference(case):
+    from geotrax_b200 import postprocess as pp
+    name, seed, n_tracks, n_frames, stab, whole = case
+    tr = synth_tracks(seed, n_tracks, n_frames, stab)
+    a = pp.remove_short_tracks(tr.copy(), LOG, 3)
+    b = pp.calculate_unique_classes(a.copy())
+    c = pp.estimate_vehicle_dimensions(b.copy(), _cfg()["main"], frame_size=(3840, 2160))
+    d = pp.interpolate_tracks(c.copy(), LOG, 30)
+    e = pp.postprocess_tracks(tr.copy(), _cfg(), LOG, frame_size=(3840, 2160))
+    assert np.array_equal(e, d, equal_nan=True)
+    for stage, arr in (("short", a), ("classes", b), ("dims", c), ("interp", d)):
+        assert tuple(GOLD[f"{name}/{stage}/shape"]) == arr.shape, (stage, arr.shape)
+        if whole:
+            ref = GOLD[f"{name}/{stage}"]
+            assert np.array_equal(arr, ref, equal_nan=True), f"{name}/{stage}: {np.argwhere(~((arr == ref) | (np.isnan(arr) & np.isnan(ref))))[:5].tolist()}"
+        assert np.array_equal(_sha(arr), GOLD[f"{name}/{stage}/sha256"]), f"{name}/{stage}: bytes differ from the reference's output"
+
+
+def test_edge_cases_and_flags():
+    from geotrax_b200 import postprocess as pp
+    empty = np.zeros((0, 12))
+    assert pp.remove_short_tracks(empty, LOG).shape == (0, 12) and pp.calculate_unique_classes(empty).shape == (0, 12)
+    assert pp.interpolate_tracks(empty, LOG, 30).shape == (0, 12)
+    # a class the track never had cannot win the vote, even with zero confidences; ties go to the lowest class id
+    t = np.array([[0, 7, 10, 10, 5, 5, 10, 10, 5, 5, 2, 0.0], [1, 7, 10, 10, 5, 5, 10, 10, 5, 5, 2, 0.0], [2, 7, 10, 10, 5, 5, 10, 10, 5, 5, 3, 0.0],
+                  [0, 9, 10, 10, 5, 5, 10, 10, 5, 5, 3, 0.5], [1, 9, 10, 10, 5, 5, 10, 10, 5, 5, 1, 0.5]], float)
+    out = pp.calculate_unique_classes(t.copy())
+    assert out[:3, -2].tolist() == [2, 2, 2] and out[3:, -2].tolist() == [1, 1]
+    # without --interpolate the table has 14 columns and keeps its row order
+    tr = synth_tracks(1, 20, 160, True)
+    out = pp.postprocess_tracks(tr.copy(), _cfg(interpolate=False), LOG, frame_size=(3840, 2160))
+    assert out.shape[1] == 14 and np.array_equal(out[:, :2], pp.remove_short_tracks(tr.copy(), LOG, 3)[:, :2])
+    # a gap longer than the tracker's buffer stays open; a gap inside it is filled with flagged rows
+    g = np.array([[0, 1, 0, 0, 4, 2, 0, 0, 4, 2, 0, 1.0], [4, 1, 8, 4, 4, 2, 8, 4, 4, 2, 0, 0.5], [50, 1, 9, 9, 4, 2, 9, 9, 4, 2, 0, 0.5]], float)
+    it = pp.interpolate_tracks(g, LOG, 30)
+    assert it[:, 0].tolist() == [0, 1, 2, 3, 4, 50] and it[:, -1].tolist() == [0, 1, 1, 1, 0, 0] and it[2, 2] == 4.0 and it[2, -2] == 0.75
+
+
+def test_vectorised_form_is_much_faster_than_row_loops():
+    """The point of the exercise: a 27,000-frame flight has millions of rows.  The reference's `remove_short_tracks` alone is
+    O(track ids x rows); here a 1.2 M-row table goes through the whole post-processing in seconds."""
+    from geotrax_b200 import postprocess as pp
+    tr = synth_tracks(11, 6000, 6000, True)
+    t0 = time.perf_counter()
+    out = pp.postprocess_tracks(tr.copy(), _cfg(), LOG, frame_size=(3840, 2160))
+    dt = time.perf_counter() - t0
+    print(f"{len(tr)} rows, {len(np.unique(tr[:, 1]))} tracks -> {out.shape} in {dt:.2f} s")
+    assert out.shape[1] == 15 and len(out) >= len(tr) * 0.9
+    assert dt < 60.0
