@@ -51,9 +51,9 @@ def root_sift(desc: np.ndarray, eps: float) -> np.ndarray:
     return np.sqrt(d, out=d)
 
 
-def detect_and_describe(img: np.ndarray, detector_name: str, max_features: int, precise_upscale: bool, rsift_eps: float):
+def detect_and_describe(img: np.ndarray, detector_name: str, max_features: int, precise_upscale: bool, rsift_eps: float, mask: Optional[np.ndarray] = None):
     sift = cv2.SIFT_create(nfeatures=int(max_features), enable_precise_upscale=bool(precise_upscale))
-    kps, desc = sift.detectAndCompute(_gray(img), None)
+    kps, desc = sift.detectAndCompute(_gray(img), mask)
     if desc is None or len(kps) == 0:
         return np.zeros((0, 2), np.float32), np.zeros((0, 128), np.float32)
     pts = np.array([k.pt for k in kps], np.float32)
@@ -62,15 +62,16 @@ def detect_and_describe(img: np.ndarray, detector_name: str, max_features: int, 
     return pts, np.ascontiguousarray(desc, np.float32)
 
 
-def match_and_fit(pts_src, desc_src, pts_dst, desc_dst, filter_ratio, threshold, max_iter, engine=None):
-    """GPU half: L2 2-NN (query = source/current, train = destination/reference), ratio test, robust homography src -> dst.
+def match_and_fit(pts_src, desc_src, pts_dst, desc_dst, filter_ratio, threshold, max_iter, engine=None, query_is_src: bool = True):
+    """GPU half: L2 2-NN, ratio test, robust homography src -> dst.  The query set is the source / current frame and the train set the
+    destination / reference (stabilo's ``match_query_frame='current'``, what registration.py:72 passes) unless ``query_is_src`` is False.
     Returns (H or None, inliers, good matches)."""
     eng = engine or _engine()
     if len(desc_src) < 2 or len(desc_dst) < 2:
         return None, 0, 0
     if max(len(desc_src), len(desc_dst)) > _MATCH_CAP:
         raise GtError(f"registration: {max(len(desc_src), len(desc_dst))} descriptors exceed the matcher's capacity of {_MATCH_CAP}")
-    idx, dist = eng.match_l2(desc_src, desc_dst)
+    idx, dist = eng.match_l2(desc_src, desc_dst) if query_is_src else eng.match_l2(desc_dst, desc_src)
     good = (idx[:, 1] >= 0) & (dist[:, 0].astype(np.float64) < float(filter_ratio) * dist[:, 1].astype(np.float64))
     q = np.nonzero(good)[0]
     cap = eng.max_batch * GT_MAX_KP
@@ -79,8 +80,9 @@ def match_and_fit(pts_src, desc_src, pts_dst, desc_dst, filter_ratio, threshold,
         q = np.sort(q[order])
     if len(q) < 4:
         return None, 0, int(len(q))
-    src = np.ascontiguousarray(pts_src[q], np.float32)
-    dst = np.ascontiguousarray(pts_dst[idx[q, 0]], np.float32)
+    i_src, i_dst = (q, idx[q, 0]) if query_is_src else (idx[q, 0], q)
+    src = np.ascontiguousarray(pts_src[i_src], np.float32)
+    dst = np.ascontiguousarray(pts_dst[i_dst], np.float32)
     H, inl = eng.find_homography(src, dst, float(threshold), int(min(max_iter, _MAX_ITER_CAP)))
     return H, int(inl), int(len(q))
 

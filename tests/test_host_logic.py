@@ -255,7 +255,7 @@ def test_increment_path(tmp_path):
 
 def test_stabilizer_rejects_unsupported_presets():
     from geotrax_b200 import Stabilizer
-    for kw in (dict(detector_name="sift"), dict(matcher_name="flann"), dict(downsample_ratio=1.5), dict(downsample_ratio=0.0), dict(transformation_type="affine"),
+    for kw in (dict(detector_name="brisk"), dict(detector_name="akaze"), dict(matcher_name="flann"), dict(downsample_ratio=1.5), dict(downsample_ratio=0.0), dict(transformation_type="affine"),
                dict(ransac_method=4), dict(ransac_method=16), dict(filter_type="distance")):
         with pytest.raises(NotImplementedError):
             Stabilizer(**kw)
@@ -475,3 +475,94 @@ def test_bench_reference_arm_contract_line():
     assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == d["value"] and cb["sample"]
     assert d["e2e"] == dict(value=d["value"], unit="frames/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0)
     assert d["gpu_launches"] == 0
+
+
+class FakeRegistrationEngine:
+    """CPU stand-in for the handle behind registration.match_and_fit (host-logic tests only): OpenCV's BFMatcher / findHomography with the
+    argument and return conventions of Engine.match_l2 / Engine.find_homography / Engine.warp_boxes."""
+    max_batch, max_det = 16, 16
+
+    def match_l2(self, query, train):
+        import cv2
+        ms = cv2.BFMatcher(cv2.NORM_L2).knnMatch(np.ascontiguousarray(query, np.float32), np.ascontiguousarray(train, np.float32), k=2)
+        idx = -np.ones((len(query), 2), np.int32); dist = -np.ones((len(query), 2), np.float32)
+        for q, pair in enumerate(ms):
+            for k, m in enumerate(pair):
+                idx[q, k], dist[q, k] = m.trainIdx, m.distance
+        return idx, dist
+
+    def find_homography(self, src, dst, thr=2.0, max_iter=5000):
+        import cv2
+        H, mask = cv2.findHomography(src, dst, cv2.USAC_MAGSAC, thr, maxIters=max_iter, confidence=0.999999)
+        return (None, 0) if H is None else (H, int(mask.sum()))
+
+    @staticmethod
+    def warp_boxes(H, b):
+        out = np.empty_like(b)
+        for i, (x, y, w, h) in enumerate(b.astype(np.float64)):
+            c = np.array([[x - w / 2, y - h / 2, 1], [x + w / 2, y - h / 2, 1], [x + w / 2, y + h / 2, 1], [x - w / 2, y + h / 2, 1]]) @ H.T
+            c = c[:, :2] / c[:, 2:]
+            out[i] = [(c[:, 0].min() + c[:, 0].max()) / 2, (c[:, 1].min() + c[:, 1].max()) / 2, c[:, 0].max() - c[:, 0].min(), c[:, 1].max() - c[:, 1].min()]
+        return out
+
+
+def _registration_pair():
+    sys.path.insert(0, os.path.dirname(__file__))
+    from test_gpu_registration import _corner_err, _image_pair
+    return _image_pair(seed=4, h=540, w=720), _corner_err
+
+
+def test_stabilizer_shim_runs_the_rsift_preset(monkeypatch):
+    """`Stabilizer(detector_name='rsift', ...)` as registration.py:59-77 constructs it: host SIFT, then registration.match_and_fit on the
+    handle (a CPU stand-in here; the GPU kernels behind it are checked in tests/test_gpu_registration.py).  Both match directions, the
+    half-resolution working image, the getters and the box warp."""
+    from geotrax_b200 import Stabilizer, registration
+    monkeypatch.setattr(registration, "_engine", lambda device=0: FakeRegistrationEngine())
+    (src, dst, Hgt), corner_err = _registration_pair()
+    for kw in (dict(match_query_frame="current"), dict(match_query_frame="reference"), dict(downsample_ratio=0.5, detector_name="sift")):
+        args = dict(detector_name="rsift", matcher_name="bf", filter_type="ratio", transformation_type="projective", clahe=False, mask_use=False,
+                    downsample_ratio=1.0, ref_multiplier=1.0, max_features=20000, filter_ratio=0.55, rsift_eps=1e-8, sift_enable_precise_upscale=True,
+                    ransac_method=38, ransac_confidence=0.999999, ransac_epipolar_threshold=3.0, ransac_max_iter=10000)
+        args.update(kw)
+        st = Stabilizer(**args)
+        st.set_ref_frame(dst)
+        assert st.get_cur_trans_matrix() is None
+        boxes = np.array([[200, 150, 40, 20], [500, 400, 30, 60]], np.float32)
+        st.stabilize(src, boxes)
+        H = st.get_cur_trans_matrix()
+        assert H is not None and corner_err(H, Hgt, *src.shape[:2]) < (0.5 if args["downsample_ratio"] == 1.0 else 1.5)
+        n_ref, n_cur = st.get_cur_num_keypoints()
+        assert n_ref > 200 and n_cur > 200 and 0 < st.get_cur_inliers_count() <= st.get_cur_num_matches()
+        wb = st.transform_cur_boxes()
+        c = np.array([200, 150, 1.0]) @ Hgt.T
+        assert wb.shape == (2, 4) and abs(wb[0, 0] - c[0] / c[2]) < 1.5 and abs(wb[0, 1] - c[1] / c[2]) < 1.5
+    flat = np.full((200, 300, 3), 127, np.uint8)
+    st = Stabilizer(detector_name="rsift", mask_use=False, downsample_ratio=1.0, ref_multiplier=1.0, max_features=20000)
+    st.set_ref_frame(flat)
+    st.stabilize(flat)
+    assert st.get_cur_trans_matrix() is None              # poor matches never raise (extract.py:185 / registration.py:80)
+
+
+def test_unmodified_reference_registration_runs_on_the_shims(monkeypatch):
+    """The reference's own `geotrax/utils/registration.py` (unmodified: from baseline/_ref, else /root/reference) calls
+    `from stabilo import Stabilizer` -> the shim -> the rsift preset; same result tuple as the product's mirror."""
+    import importlib
+    import logging
+    import geotrax_b200
+    from geotrax_b200 import registration
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    ref = next((p for p in (os.path.join(root, "baseline", "_ref"), "/root/reference") if os.path.exists(os.path.join(p, "geotrax", "utils", "registration.py"))), None)
+    if ref is None:
+        pytest.skip("the reference package is not available (baseline/_ref)")
+    monkeypatch.setattr(registration, "_engine", lambda device=0: FakeRegistrationEngine())
+    monkeypatch.syspath_prepend(ref)
+    geotrax_b200.install_shims()
+    for name in [m for m in sys.modules if m == "geotrax" or m.startswith("geotrax.")]:
+        monkeypatch.delitem(sys.modules, name)
+    ref_reg = importlib.import_module("geotrax.utils.registration")
+    assert os.path.abspath(ref_reg.__file__).startswith(os.path.abspath(ref))
+    (src, dst, Hgt), corner_err = _registration_pair()
+    H, inl, nm, (n_src, n_dst) = ref_reg.estimate_homography(src, dst, logging.getLogger("ref"), max_features=20000)
+    H2, inl2, nm2, (n_src2, n_dst2) = registration.estimate_homography(src, dst, None, max_features=20000, engine=FakeRegistrationEngine())
+    assert H is not None and corner_err(H, Hgt, *src.shape[:2]) < 0.5
+    assert (nm, n_src, n_dst) == (nm2, n_src2, n_dst2) and abs(inl - inl2) <= 0.02 * nm and corner_err(H, H2, *src.shape[:2]) < 0.2
