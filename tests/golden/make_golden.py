@@ -5,7 +5,8 @@ Run in the build container (needs /root/reference, which does not exist on the G
 Source files (README-documented output of `geotrax batch data/U_video_cut.mp4 --no-geo`, /root/reference/data/README.md:15-19):
     /root/reference/data/results-pixel/U_video_cut.txt             (19,817 x 14: frame,id,x,y,w,h,xs,ys,ws,hs,cls,conf,len,wid)
     /root/reference/data/results-pixel/U_video_cut_vid_transf.txt  (149 x 10: frame, H row-major)
-The fixture keeps every transform and the track rows of a frame subset (enough to pin box-warp semantics).
+The fixture keeps every transform and the track rows of a frame subset (enough to pin box-warp semantics);
+u_video_cut_tracks_full.npz keeps the whole 19,817 x 14 table for the post-processing pin.
 """
 import os
 import numpy as np
@@ -22,3 +23,6 @@ np.savez_compressed(os.path.join(HERE, "u_video_cut_golden.npz"),
                     tracks=tracks[keep], transforms=transf, dets_per_frame=per_frame,
                     n_rows_total=np.int64(len(tracks)))
 print("rows kept", int(keep.sum()), "of", len(tracks), "; transforms", transf.shape)
+# the whole track table too (14 columns = the OUTPUT of postprocess_tracks: the last two are estimate_vehicle_dimensions' length / width):
+# tests/test_postprocess.py recomputes them from the first twelve with the vectorised mirror
+np.savez_compressed(os.path.join(HERE, "u_video_cut_tracks_full.npz"), tracks=tracks)

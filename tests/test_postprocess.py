@@ -77,3 +77,25 @@ def test_vectorised_form_is_much_faster_than_row_loops():
     print(f"{len(tr)} rows, {len(np.unique(tr[:, 1]))} tracks -> {out.shape} in {dt:.2f} s")
     assert out.shape[1] == 15 and len(out) >= len(tr) * 0.9
     assert dt < 60.0
+
+
+def test_dimension_estimate_reproduces_the_references_golden_output():
+    """The reference's committed result file data/results-pixel/U_video_cut.txt (19,817 rows x 14 columns; tests/golden/make_golden.py) IS the
+    output of its postprocess_tracks: columns 12-13 are estimate_vehicle_dimensions' length / width.  Re-running the vectorised mirror on
+    the first twelve columns must give them back -- same NaN pattern, values to the file's `%g` precision (6 significant digits: the
+    inputs are rounded too) -- and the other two steps must be fixed points (no short track left, classes already unique)."""
+    from geotrax_b200 import postprocess as pp
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "u_video_cut_tracks_full.npz"))["tracks"]
+    assert g.shape == (19817, 14)
+    base = g[:, :12].copy()
+    a = pp.remove_short_tracks(base.copy(), LOG, 3)
+    assert len(a) == len(base)
+    b = pp.calculate_unique_classes(a.copy())
+    assert np.array_equal(b, a)
+    c = pp.estimate_vehicle_dimensions(b, _cfg(interpolate=False)["main"], frame_size=(3840, 2160))
+    assert np.array_equal(c[:, :12], base)
+    assert np.array_equal(np.isnan(c[:, 12:]), np.isnan(g[:, 12:]))
+    ok = ~np.isnan(g[:, 12:])
+    err = np.abs(c[:, 12:][ok] - g[:, 12:][ok])
+    assert err.max() <= 1e-3 and (err / g[:, 12:][ok]).max() < 1e-5, err.max()
+    assert int(ok[:, 0].sum()) > 15000 and len(np.unique(g[ok[:, 0], 12])) > 100       # non-vacuous: most tracks carry an estimate
